@@ -1,0 +1,116 @@
+"""Export a *reference* `EV2Gym` object (after `reset()`) into `Topology` / `Scenario`.
+
+This is the drop-in "scenario source" for users who have the reference installed: the
+reference's own host-side generators (loaders.py / utils.py, out of scope per SURVEY.md
+section 2 rows 5 and 7) keep producing the episode, and the B200 engine consumes the
+exported tensors.  This module never imports the reference; it only reads attributes of the
+object it is handed (duck typing), so it also works on unpickled replay scenarios.
+
+Attribute provenance (paths relative to /root/reference):
+  env.charging_stations[*]    ev2gym/models/ev_charger.py:41-75
+  env.transformers[*]         ev2gym/models/transformer.py:15-78
+  env.EVs_profiles[*]         ev2gym/models/ev.py:45-113, built by ev2gym/utilities/utils.py:298-345
+  env.charge_prices etc.      ev2gym/models/ev2gym_env.py:293-296
+"""
+from __future__ import annotations
+
+import math
+from typing import Tuple
+
+import numpy as np
+
+from .scenario import LUT_LEN, SESSION_F64_FIELDS, SESSION_INT_FIELDS, Scenario, Topology
+
+
+def topology_from_env(env) -> Topology:
+    cs = env.charging_stations
+    cfg = env.config
+    return Topology(
+        cs_n_ports=np.array([c.n_ports for c in cs]),
+        cs_tr=np.array([c.connected_transformer for c in cs]),
+        cs_imax=np.array([c.max_charge_current for c in cs], dtype=np.float64),
+        cs_imin=np.array([c.min_charge_current for c in cs], dtype=np.float64),
+        cs_imax_dis=np.array([c.max_discharge_current for c in cs], dtype=np.float64),
+        cs_imin_dis=np.array([c.min_discharge_current for c in cs], dtype=np.float64),
+        cs_voltage=np.array([c.voltage for c in cs], dtype=np.float64),
+        cs_phases=np.array([c.phases for c in cs]),
+        n_transformers=len(env.transformers),
+        tr_voltage=float(env.transformers[0].voltage) if len(env.transformers) else
+        float(cfg["charging_station"]["voltage"] * math.sqrt(cfg["charging_station"]["phases"])),
+        timescale=int(env.timescale),
+        sim_length=int(env.simulation_length),
+        dr_steps_ahead=int(cfg["demand_response"]["notification_of_event_minutes"] // env.timescale),
+        v2g_enabled=bool(cfg["v2g_enabled"]),
+    )
+
+
+def _lut_row(d: dict) -> Tuple[float, ...]:
+    """`dict.get(k, 1)` for k = 0..100, the only keys `np.round(amps)` can hit within LUT_LEN
+    (ev.py:287-288; the dict is dense over 0..100 after utils.py:282-288)."""
+    bad = [k for k in d if not (0 <= k < LUT_LEN) or k != int(k)]
+    if bad:
+        raise ValueError(f"efficiency table has keys outside 0..{LUT_LEN - 1}: {bad[:5]}")
+    return tuple(float(d.get(k, 1)) for k in range(LUT_LEN))
+
+
+def scenario_from_env(env) -> Scenario:
+    """Snapshot everything `reset()` sampled.  Call right after `reset()` (before any `step`)."""
+    T = int(env.simulation_length)
+    trs = env.transformers
+    Tr = len(trs)
+    cp, dp = np.asarray(env.charge_prices, dtype=np.float64), np.asarray(env.discharge_prices, dtype=np.float64)
+    if not (np.all(cp == cp[0:1]) and np.all(dp == dp[0:1])):
+        raise ValueError("per-charger prices differ; the engine stores one price row per env (loaders.py:423-424)")
+
+    def series(name):
+        return np.stack([np.asarray(getattr(tr, name), dtype=np.float64)[:T] for tr in trs]) if Tr else \
+            np.zeros((0, T))
+
+    ndr = max([len(tr.dr_events) for tr in trs] + [1])
+    dr_start = np.zeros((Tr, ndr), dtype=np.int32)
+    dr_end = np.zeros((Tr, ndr), dtype=np.int32)
+    dr_cap = np.zeros((Tr, ndr))
+    dr_count = np.zeros(Tr, dtype=np.int32)
+    for i, tr in enumerate(trs):
+        dr_count[i] = len(tr.dr_events)
+        for j, ev in enumerate(tr.dr_events):
+            dr_start[i, j], dr_end[i, j], dr_cap[i, j] = ev["event_start_step"], ev["event_end_step"], \
+                float(ev["capacity_percentage"])
+
+    sess = {k: [] for k in SESSION_INT_FIELDS + SESSION_F64_FIELDS}
+    luts_c, luts_d, lut_index = [], [], {}
+    for ev in env.EVs_profiles:
+        ce, de = ev.charge_efficiency, ev.discharge_efficiency
+        if isinstance(ce, dict):
+            # ev.py:375 tests the *charge* efficiency's type before using the discharge dict
+            key = (_lut_row(ce), _lut_row(de))
+            if key not in lut_index:
+                lut_index[key] = len(luts_c)
+                luts_c.append(key[0])
+                luts_d.append(key[1])
+            lut, eta_c, eta_d = lut_index[key], math.nan, math.nan
+        else:
+            lut, eta_c, eta_d = -1, float(ce), float(de)
+        vals = dict(loc=ev.location, t_arr=ev.time_of_arrival, t_dep=ev.time_of_departure,
+                    ev_phases=ev.ev_phases, lut=lut, cap0=ev.battery_capacity_at_arrival,
+                    B=ev.battery_capacity, pmax_ac=ev.max_ac_charge_power, pmin_ac=ev.min_ac_charge_power,
+                    pmax_dis=ev.max_discharge_power, pmin_dis=ev.min_discharge_power,
+                    bmin=ev.min_battery_capacity, bmin_em=ev.min_emergency_battery_capacity,
+                    desired=ev.desired_capacity, ts=ev.transition_soc, mult=ev.transition_soc_multiplier,
+                    eta_c=eta_c, eta_d=eta_d)
+        for k, v in vals.items():
+            sess[k].append(v)
+    sessions = {k: np.array(v, dtype=np.int32 if k in SESSION_INT_FIELDS else np.float64) for k, v in sess.items()}
+
+    return Scenario(
+        charge_price=cp[0].copy(), discharge_price=dp[0].copy(),
+        setpoint=np.asarray(env.power_setpoints, dtype=np.float64)[:T].copy(),
+        tr_infl=series("inflexible_load"), tr_solar=series("solar_power"),
+        tr_max_power=series("max_power"), tr_min_power=series("min_power"),
+        tr_load_fc=series("inflexible_load_forecast"), tr_pv_fc=series("pv_generation_forecast"),
+        dr_start=dr_start, dr_end=dr_end, dr_cap=dr_cap, dr_count=dr_count,
+        sessions=sessions,
+        luts_c=np.array(luts_c, dtype=np.float64).reshape(-1, LUT_LEN),
+        luts_d=np.array(luts_d, dtype=np.float64).reshape(-1, LUT_LEN),
+        meta={"sim_date": str(getattr(env, "sim_date", "")), "seed": getattr(env, "seed", None)},
+    ).normalise()

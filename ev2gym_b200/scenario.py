@@ -1,0 +1,246 @@
+"""Scenario containers: everything `EV2Gym.reset()` samples, as plain fp64/int arrays.
+
+The reference's `step()` consumes no randomness (SURVEY.md "Quick facts"): it is a
+deterministic function of the scenario produced by `reset()` and of the action
+sequence.  A `Scenario` is that scenario for ONE env replica; a `ScenarioPack` is a
+bank of scenarios sharing one charger/transformer `Topology`.
+
+Provenance of every field (reference file:line, relative to /root/reference):
+  Topology      <- ev2gym/utilities/loaders.py:299-365 (chargers), :227-296 + :464-500 (cs->tr map),
+                   ev2gym/models/transformer.py:39-40 (transformer voltage)
+  prices        <- loaders.py:392-461   (identical rows for all chargers -> one row per env)
+  setpoints     <- loaders.py:92-103 / ev2gym/utilities/utils.py:664-757
+  tr_* series   <- transformer.py:43-78 (after normalisation / DR events / forecasts)
+  sessions      <- utils.py:177-345 (`spawn_single_EV`), list order = `env.EVs_profiles`
+                   (arrival sorted, utils.py:504-557)
+This module is host-side product code (numpy only, no CUDA, no reference import).
+"""
+from __future__ import annotations
+
+import dataclasses
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+# Session fields (one entry per EV profile, in `EVs_profiles` order).
+SESSION_INT_FIELDS = ("loc", "t_arr", "t_dep", "ev_phases", "lut")
+SESSION_F64_FIELDS = (
+    "cap0",        # battery_capacity_at_arrival            ev.py:76
+    "B",           # battery_capacity                       ev.py:79
+    "pmax_ac",     # max_ac_charge_power                    ev.py:82
+    "pmin_ac",     # min_ac_charge_power                    ev.py:83
+    "pmax_dis",    # max_discharge_power (<= 0)             ev.py:84
+    "pmin_dis",    # min_discharge_power                    ev.py:85
+    "bmin",        # min_battery_capacity                   ev.py:80
+    "bmin_em",     # min_emergency_battery_capacity         ev.py:81
+    "desired",     # desired_capacity                       ev.py:75
+    "ts",          # transition_soc                         ev.py:87
+    "mult",        # transition_soc_multiplier              ev.py:88
+    "eta_c",       # charge_efficiency (scalar; NaN if LUT) ev.py:91
+    "eta_d",       # discharge_efficiency (scalar; NaN if LUT)
+)
+TR_SERIES = ("tr_infl", "tr_solar", "tr_max_power", "tr_min_power", "tr_load_fc", "tr_pv_fc")
+LUT_LEN = 101  # efficiency dict keys 0..100 A (utils.py:282-288)
+
+
+@dataclass
+class Topology:
+    """Static charger / transformer layout (identical for every env of a handle)."""
+    cs_n_ports: np.ndarray      # [C] int32
+    cs_tr: np.ndarray           # [C] int32  connected_transformer
+    cs_imax: np.ndarray         # [C] f64    max_charge_current
+    cs_imin: np.ndarray         # [C] f64    min_charge_current
+    cs_imax_dis: np.ndarray     # [C] f64    max_discharge_current (<= 0)
+    cs_imin_dis: np.ndarray     # [C] f64    min_discharge_current
+    cs_voltage: np.ndarray      # [C] f64
+    cs_phases: np.ndarray       # [C] int32
+    n_transformers: int
+    tr_voltage: float           # voltage * sqrt(phases) of the config   transformer.py:39-40
+    timescale: int              # minutes per step
+    sim_length: int             # T
+    dr_steps_ahead: int = 0     # notification_of_event_minutes // timescale  transformer.py:69
+    v2g_enabled: bool = True
+
+    def __post_init__(self):
+        self.cs_n_ports = np.ascontiguousarray(self.cs_n_ports, dtype=np.int32)
+        self.cs_tr = np.ascontiguousarray(self.cs_tr, dtype=np.int32)
+        self.cs_phases = np.ascontiguousarray(self.cs_phases, dtype=np.int32)
+        for k in ("cs_imax", "cs_imin", "cs_imax_dis", "cs_imin_dis", "cs_voltage"):
+            setattr(self, k, np.ascontiguousarray(getattr(self, k), dtype=np.float64))
+
+    @property
+    def C(self) -> int:
+        return int(self.cs_n_ports.shape[0])
+
+    @property
+    def P(self) -> int:
+        return int(self.cs_n_ports.sum())
+
+    @property
+    def Tr(self) -> int:
+        return int(self.n_transformers)
+
+    @property
+    def T(self) -> int:
+        return int(self.sim_length)
+
+    @property
+    def cs_port_off(self) -> np.ndarray:
+        off = np.zeros(self.C + 1, dtype=np.int32)
+        np.cumsum(self.cs_n_ports, out=off[1:])
+        return off
+
+    @classmethod
+    def uniform(cls, C: int, n_ports: int, Tr: int, T: int = 112, timescale: int = 15,
+                imax: float = 32.0, imin: float = 0.0, imax_dis: float = -32.0,
+                imin_dis: float = 0.0, voltage: float = 400.0, phases: int = 3,
+                v2g_enabled: bool = True, dr_steps_ahead: int = 4) -> "Topology":
+        """The reference's default layout: charger i -> transformer i mod Tr (loaders.py:495-498)."""
+        import math
+        return cls(
+            cs_n_ports=np.full(C, n_ports), cs_tr=np.arange(C) % Tr,
+            cs_imax=np.full(C, imax), cs_imin=np.full(C, imin),
+            cs_imax_dis=np.full(C, imax_dis if v2g_enabled else 0.0),
+            cs_imin_dis=np.full(C, imin_dis if v2g_enabled else 0.0),
+            cs_voltage=np.full(C, voltage), cs_phases=np.full(C, phases),
+            n_transformers=Tr, tr_voltage=voltage * math.sqrt(phases), timescale=timescale,
+            sim_length=T, dr_steps_ahead=dr_steps_ahead, v2g_enabled=v2g_enabled)
+
+    def to_dict(self) -> Dict[str, np.ndarray]:
+        d = {f"topo_{k}": np.asarray(v) for k, v in dataclasses.asdict(self).items()}
+        return d
+
+    @classmethod
+    def from_dict(cls, d) -> "Topology":
+        kw = {}
+        for f in dataclasses.fields(cls):
+            v = d[f"topo_{f.name}"]
+            if f.name in ("n_transformers", "timescale", "sim_length", "dr_steps_ahead"):
+                v = int(v)
+            elif f.name == "tr_voltage":
+                v = float(v)
+            elif f.name == "v2g_enabled":
+                v = bool(v)
+            kw[f.name] = v
+        return cls(**kw)
+
+
+@dataclass
+class Scenario:
+    """One env replica's pre-sampled episode (everything `reset()` draws)."""
+    charge_price: np.ndarray        # [T] f64  (= -price/1000, loaders.py:439)
+    discharge_price: np.ndarray     # [T] f64
+    setpoint: np.ndarray            # [T] f64  power_setpoints
+    tr_infl: np.ndarray             # [Tr,T] f64 inflexible_load
+    tr_solar: np.ndarray            # [Tr,T] f64 solar_power (stored negative, transformer.py:197)
+    tr_max_power: np.ndarray        # [Tr,T] f64 (after DR events, transformer.py:118-130)
+    tr_min_power: np.ndarray        # [Tr,T] f64
+    tr_load_fc: np.ndarray          # [Tr,T] f64 inflexible_load_forecast
+    tr_pv_fc: np.ndarray            # [Tr,T] f64 pv_generation_forecast
+    dr_start: np.ndarray            # [Tr,NDR] int32 event_start_step
+    dr_end: np.ndarray              # [Tr,NDR] int32 event_end_step
+    dr_cap: np.ndarray              # [Tr,NDR] f64 capacity_percentage
+    dr_count: np.ndarray            # [Tr] int32 number of events
+    sessions: Dict[str, np.ndarray] = field(default_factory=dict)  # SESSION_*_FIELDS, each [S]
+    luts_c: np.ndarray = field(default_factory=lambda: np.ones((0, LUT_LEN)))  # [L,101] percent
+    luts_d: np.ndarray = field(default_factory=lambda: np.ones((0, LUT_LEN)))
+    meta: Dict[str, object] = field(default_factory=dict)
+
+    @property
+    def n_sessions(self) -> int:
+        return int(self.sessions["t_arr"].shape[0])
+
+    def normalise(self) -> "Scenario":
+        for k in ("charge_price", "discharge_price", "setpoint", "dr_cap") + TR_SERIES:
+            setattr(self, k, np.ascontiguousarray(getattr(self, k), dtype=np.float64))
+        for k in ("dr_start", "dr_end", "dr_count"):
+            setattr(self, k, np.ascontiguousarray(getattr(self, k), dtype=np.int32))
+        for k in SESSION_INT_FIELDS:
+            self.sessions[k] = np.ascontiguousarray(self.sessions[k], dtype=np.int32)
+        for k in SESSION_F64_FIELDS:
+            self.sessions[k] = np.ascontiguousarray(self.sessions[k], dtype=np.float64)
+        self.luts_c = np.ascontiguousarray(self.luts_c, dtype=np.float64).reshape(-1, LUT_LEN)
+        self.luts_d = np.ascontiguousarray(self.luts_d, dtype=np.float64).reshape(-1, LUT_LEN)
+        return self
+
+
+def assign_ports(topo: Topology, t_arr: np.ndarray, t_dep: np.ndarray, loc: np.ndarray) -> np.ndarray:
+    """Replay the reference's first-free-port rule on the host.
+
+    `EV_Charger.spawn_ev` puts an arriving EV into `evs_connected.index(None)`
+    (ev_charger.py:273), NOT into the port the spawner drew; departures of step t
+    (t >= time_of_departure, ev_charger.py:209-224) free their port BEFORE the arrivals
+    of t+1 are placed (ev2gym_env.py:363-417).  Sessions must be arrival-sorted with
+    t_arr >= 1, which is what `EV_spawner` emits (utils.py:504-557; first arrival is 3).
+    Returns the flat port index (charger-major = action order) of every session.
+    """
+    t_arr = np.asarray(t_arr)
+    if t_arr.size and (np.any(np.diff(t_arr) < 0) or t_arr.min() < 1):
+        raise ValueError("sessions must be sorted by time_of_arrival and arrive at step >= 1")
+    off = topo.cs_port_off
+    occupied_until = np.full(topo.P, -1, dtype=np.int64)  # t_dep of the occupant, -1 = free
+    port = np.full(t_arr.shape[0], -1, dtype=np.int32)
+    for i in range(t_arr.shape[0]):
+        t = int(t_arr[i]) - 1                       # the EV is placed at the END of step t
+        c = int(loc[i])
+        lo, hi = int(off[c]), int(off[c + 1])
+        seg = occupied_until[lo:hi]
+        seg[(seg >= 0) & (seg <= t)] = -1           # departures of steps <= t already happened
+        free = np.nonzero(seg < 0)[0]
+        if free.size == 0:
+            raise ValueError(f"session {i}: charger {c} has no free port at step {t + 1}")
+        seg[free[0]] = int(t_dep[i])
+        port[i] = lo + int(free[0])
+    return port
+
+
+@dataclass
+class ScenarioPack:
+    """A bank of scenarios on one topology, with npz (de)serialisation."""
+    topo: Topology
+    scenarios: List[Scenario]
+    config_name: str = ""
+
+    def __len__(self):
+        return len(self.scenarios)
+
+    def save(self, path: str) -> None:
+        d = dict(self.topo.to_dict())
+        d["config_name"] = np.array(self.config_name)
+        d["n_scenarios"] = np.array(len(self.scenarios))
+        sc = self.scenarios
+        for k in ("charge_price", "discharge_price", "setpoint", "dr_start", "dr_end", "dr_cap",
+                  "dr_count") + TR_SERIES:
+            d[k] = np.stack([getattr(s, k) for s in sc])
+        s_off = np.zeros(len(sc) + 1, dtype=np.int64)
+        l_off = np.zeros(len(sc) + 1, dtype=np.int64)
+        for i, s in enumerate(sc):
+            s_off[i + 1] = s_off[i] + s.n_sessions
+            l_off[i + 1] = l_off[i] + s.luts_c.shape[0]
+        d["s_off"], d["l_off"] = s_off, l_off
+        for k in SESSION_INT_FIELDS + SESSION_F64_FIELDS:
+            d["s_" + k] = np.concatenate([s.sessions[k] for s in sc])
+        d["luts_c"] = np.concatenate([s.luts_c for s in sc]).reshape(-1, LUT_LEN)
+        d["luts_d"] = np.concatenate([s.luts_d for s in sc]).reshape(-1, LUT_LEN)
+        np.savez_compressed(path, **d)
+
+    @classmethod
+    def load(cls, path: str) -> "ScenarioPack":
+        z = np.load(path, allow_pickle=False)
+        topo = Topology.from_dict(z)
+        n = int(z["n_scenarios"])
+        s_off, l_off = z["s_off"], z["l_off"]
+        out = []
+        for i in range(n):
+            sess = {k: z["s_" + k][s_off[i]:s_off[i + 1]] for k in SESSION_INT_FIELDS + SESSION_F64_FIELDS}
+            out.append(Scenario(
+                charge_price=z["charge_price"][i], discharge_price=z["discharge_price"][i],
+                setpoint=z["setpoint"][i], tr_infl=z["tr_infl"][i], tr_solar=z["tr_solar"][i],
+                tr_max_power=z["tr_max_power"][i], tr_min_power=z["tr_min_power"][i],
+                tr_load_fc=z["tr_load_fc"][i], tr_pv_fc=z["tr_pv_fc"][i],
+                dr_start=z["dr_start"][i], dr_end=z["dr_end"][i], dr_cap=z["dr_cap"][i],
+                dr_count=z["dr_count"][i], sessions=sess,
+                luts_c=z["luts_c"][l_off[i]:l_off[i + 1]], luts_d=z["luts_d"][l_off[i]:l_off[i + 1]],
+            ).normalise())
+        return cls(topo=topo, scenarios=out, config_name=str(z["config_name"]))

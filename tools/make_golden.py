@@ -1,0 +1,235 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by EXECUTING the unmodified Python reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tools/make_golden.py            # all cases -> tests/golden/*.npz
+    python tools/make_golden.py --packs    # scenario banks for bench.py -> ev2gym_b200/data/*.npz
+
+The reference is imported read-only from /root/reference through the stub packages in
+oracle/refshim (gymnasium / matplotlib / pandapower / multicopula are absent here, SURVEY.md
+section 8c).  Nothing from the reference is copied: fixtures hold only *inputs* (the scenario
+`reset()` sampled, the action sequence) and *outputs* (what `step()` returned / left in the
+env), as arrays.
+
+Each fixture = one episode: config (a shipped YAML + size overrides), seed, agent.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(REPO, "oracle", "refshim"))
+sys.path.insert(0, REF)
+sys.path.insert(0, REPO)
+sys.dont_write_bytecode = True
+os.chdir(REF)  # shipped configs use ./ev2gym/data/... relative paths
+
+import warnings  # noqa: E402
+
+warnings.filterwarnings("ignore")
+
+import yaml  # noqa: E402
+from ev2gym.models.ev2gym_env import EV2Gym  # noqa: E402
+from ev2gym.rl_agent import reward as ref_reward  # noqa: E402
+from ev2gym.rl_agent import state as ref_state  # noqa: E402
+from ev2gym.baselines import heuristics as ref_agents  # noqa: E402
+
+from ev2gym_b200.reference_export import scenario_from_env, topology_from_env  # noqa: E402
+from ev2gym_b200.scenario import ScenarioPack  # noqa: E402
+
+PAIRS = {  # config -> (state, reward)   train_stable_baselines.py:39-51
+    "PublicPST": ("PublicPST", "SquaredTrackingErrorReward"),
+    "V2GProfitMax": ("V2G_profit_max", "profit_maximization"),
+    "V2GProfitPlusLoads": ("V2G_profit_max_loads", "ProfitMax_TrPenalty_UserIncentives"),
+}
+
+
+def make_config(base: str, overrides: dict) -> str:
+    cfg = yaml.safe_load(open(f"{REF}/ev2gym/example_config_files/{base}.yaml"))
+
+    def merge(d, o):
+        for k, v in o.items():
+            if isinstance(v, dict):
+                merge(d[k], v)
+            else:
+                d[k] = v
+    merge(cfg, overrides)
+    f = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+    yaml.safe_dump(cfg, f)
+    f.close()
+    return f.name
+
+
+def make_env(base, overrides, seed, state=None, reward=None):
+    st, rw = PAIRS[base]
+    st, rw = state or st, reward or rw
+    path = make_config(base, overrides)
+    env = EV2Gym(config_file=path, seed=seed, state_function=getattr(ref_state, st),
+                 reward_function=getattr(ref_reward, rw))
+    os.unlink(path)
+    return env, st, rw
+
+
+def make_actions(kind: str, env, rng) -> np.ndarray:
+    P = env.number_of_ports
+    low = -1.0 if env.config["v2g_enabled"] else 0.0
+    if kind == "afap":
+        return np.ones(P)
+    if kind == "zeros":
+        return np.zeros(P)
+    if kind == "discharge":
+        return -np.ones(P)
+    if kind == "uniform":
+        return rng.uniform(low, 1.0, P)
+    if kind == "mixed":   # exact zeros, saturations, tiny values under the min-current gate, |sum|>1 on multi-port
+        a = rng.uniform(low, 1.0, P)
+        r = rng.random(P)
+        a[r < 0.15] = 0.0
+        a[(r >= 0.15) & (r < 0.25)] = 1.0
+        a[(r >= 0.25) & (r < 0.32)] = low
+        a[(r >= 0.32) & (r < 0.40)] *= 1e-3
+        return a
+    raise ValueError(kind)
+
+
+def record_episode(base, overrides, seed, agent, state=None, reward=None):
+    env, st, rw = make_env(base, overrides, seed, state, reward)
+    obs0, _ = env.reset(seed=seed)
+    topo, scn = topology_from_env(env), scenario_from_env(env)
+    T, P, C, Tr = env.simulation_length, env.number_of_ports, env.cs, len(env.transformers)
+    rng = np.random.default_rng(seed + 7919)
+    rr = ref_agents.RoundRobin(env) if agent == "roundrobin" else None
+
+    captured = {}
+    inner = env.reward_function
+
+    def spy(e, total_costs, sat_list, invalid):
+        captured.update(total_costs=total_costs, sat=list(sat_list), invalid=invalid)
+        return inner(e, total_costs, sat_list, invalid)
+    env.reward_function = spy
+
+    rec = {k: [] for k in ("actions", "actions_eff", "obs", "reward", "done", "cs_power", "cs_current", "tr_power",
+                           "tr_amps", "tr_overload", "cap", "port_t_arr", "energy_exch", "total_costs", "invalid",
+                           "n_departed", "sat_sum", "action_mask")}
+    stats = None
+    for t in range(T):
+        a = rr.get_action(env) if rr is not None else make_actions(agent, env, rng)
+        a = np.asarray(a, dtype=np.float64)
+        rec["actions"].append(a.copy())
+        obs, r, done, trunc, info = env.step(a)       # mutates `a` in place (ev_charger.py:137-140)
+        rec["actions_eff"].append(a.copy())
+        rec["obs"].append(np.asarray(obs, dtype=np.float64))
+        rec["reward"].append(float(r))
+        rec["done"].append(bool(done))
+        rec["cs_power"].append(env.cs_power[:, t].copy())
+        rec["cs_current"].append(env.cs_current[:, t].copy())
+        rec["tr_power"].append(np.array([tr.current_power for tr in env.transformers], dtype=np.float64))
+        rec["tr_amps"].append(np.array([tr.current_amps for tr in env.transformers], dtype=np.float64))
+        rec["tr_overload"].append(env.tr_overload[:, t].copy())
+        cap = np.full(P, np.nan)
+        tarr = np.full(P, -1, dtype=np.int32)
+        exch = np.zeros(P)
+        p = 0
+        for cs in env.charging_stations:
+            for ev in cs.evs_connected:
+                if ev is not None:
+                    cap[p], tarr[p], exch[p] = ev.current_capacity, ev.time_of_arrival, ev.total_energy_exchanged
+                p += 1
+        rec["cap"].append(cap)
+        rec["port_t_arr"].append(tarr)
+        rec["energy_exch"].append(exch)
+        rec["total_costs"].append(float(captured["total_costs"]))
+        rec["invalid"].append(int(captured["invalid"]))
+        rec["n_departed"].append(len(captured["sat"]))
+        rec["sat_sum"].append(float(np.sum(captured["sat"])) if captured["sat"] else 0.0)
+        rec["action_mask"].append(np.asarray(info["action_mask"], dtype=np.float64))
+        if done:
+            stats = info
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["obs0"] = np.asarray(obs0, dtype=np.float64)
+    out["usage"] = env.current_power_usage.copy()
+    out["potential"] = env.charge_power_potential.copy()
+    out["total_reward"] = np.array(env.total_reward)
+    for k in ("total_ev_served", "total_profits", "total_energy_charged", "total_energy_discharged",
+              "average_user_satisfaction", "total_transformer_overload", "tracking_error",
+              "energy_tracking_error", "power_tracker_violation"):
+        out["stat_" + k] = np.array(float(stats[k]))
+    out["state_fn"], out["reward_fn"] = np.array(st), np.array(rw)
+    out["seed"], out["agent"], out["base"] = np.array(seed), np.array(agent), np.array(base)
+    return topo, scn, out
+
+
+HOMOG = {"heterogeneous_ev_specs": False}
+CASES = [
+    # name, base config, overrides, seed, agent
+    ("c1_afap_s42", "V2GProfitPlusLoads", {"number_of_charging_stations": 10}, 42, "afap"),          # KA7
+    ("c1_uniform_s7", "V2GProfitPlusLoads", {"number_of_charging_stations": 10}, 7, "uniform"),
+    ("pst25_uniform_s3", "PublicPST", {"number_of_charging_stations": 25}, 3, "uniform"),           # c2 shape
+    ("pst25_roundrobin_s5", "PublicPST", {"number_of_charging_stations": 25}, 5, "roundrobin"),
+    ("loads_c20n2tr3_mixed_s11", "V2GProfitPlusLoads",
+     {"number_of_charging_stations": 20, "number_of_ports_per_cs": 2, "number_of_transformers": 3}, 11, "mixed"),
+    ("loads_c100n2tr5_uniform_s1", "V2GProfitPlusLoads",                                              # c3 shape
+     {"number_of_charging_stations": 100, "number_of_ports_per_cs": 2, "number_of_transformers": 5}, 1, "uniform"),
+    ("loads_c12n3tr2_discharge_s2", "V2GProfitPlusLoads",
+     {"number_of_charging_stations": 12, "number_of_ports_per_cs": 3, "number_of_transformers": 2}, 2, "discharge"),
+    ("profitmax_c25_mixed_s9", "V2GProfitMax", {"number_of_charging_stations": 25}, 9, "mixed"),      # c4 family
+    ("homog_ts1_afap_s4", "V2GProfitPlusLoads", {"number_of_charging_stations": 8, **HOMOG}, 4, "afap"),  # ceil lattice
+    ("homog_ts08_mixed_s6", "V2GProfitPlusLoads",
+     {"number_of_charging_stations": 8, **HOMOG, "ev": {"transition_soc": 0.8, "charge_efficiency": 0.93,
+                                                       "discharge_efficiency": 0.91, "min_ac_charge_power": 1.5}},
+     6, "mixed"),
+    ("mincur_c6n2_mixed_s8", "PublicPST",
+     {"number_of_charging_stations": 6, "number_of_ports_per_cs": 2, "v2g_enabled": True,
+      "charging_station": {"min_charge_current": 6, "max_charge_current": 32, "max_discharge_current": -32,
+                           "min_discharge_current": -6}}, 8, "mixed"),
+    ("ts10_c5_uniform_s10", "V2GProfitMax", {"number_of_charging_stations": 5, "timescale": 10,
+                                             "simulation_length": 150}, 10, "uniform"),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--packs", action="store_true", help="write the scenario banks used by bench.py")
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    if args.packs:
+        out_dir = os.path.join(REPO, "ev2gym_b200", "data")
+        os.makedirs(out_dir, exist_ok=True)
+        banks = [
+            ("c2_publicpst_c25", "PublicPST", {"number_of_charging_stations": 25}, 64),
+            ("c3_v2gloads_c100n2tr5", "V2GProfitPlusLoads",
+             {"number_of_charging_stations": 100, "number_of_ports_per_cs": 2, "number_of_transformers": 5}, 64),
+            ("c4_v2gprofitmax_c250", "V2GProfitMax", {"number_of_charging_stations": 250}, 32),
+        ]
+        for name, base, ov, n in banks:
+            if args.only and args.only not in name:
+                continue
+            env, _, _ = make_env(base, ov, 1000)
+            scns = []
+            for i in range(n):      # seed = 1000 + i
+                env.reset(seed=1000 + i)
+                scns.append(scenario_from_env(env))
+            ScenarioPack(topology_from_env(env), scns, config_name=name).save(os.path.join(out_dir, name + ".npz"))
+            print("pack", name, n, "scenarios")
+        return
+    out_dir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, base, ov, seed, agent in CASES:
+        if args.only and args.only not in name:
+            continue
+        topo, scn, tr = record_episode(base, ov, seed, agent)
+        pack = ScenarioPack(topo, [scn], config_name=name)
+        pack.save(os.path.join(out_dir, name + ".scenario.npz"))
+        np.savez_compressed(os.path.join(out_dir, name + ".trace.npz"), **tr)
+        print(f"{name}: P={topo.P} Tr={topo.Tr} sessions={scn.n_sessions} sum_reward={tr['reward'].sum():.12f}")
+
+
+if __name__ == "__main__":
+    main()
