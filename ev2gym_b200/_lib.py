@@ -1,0 +1,135 @@
+"""Build and load libev2b.so (the C-ABI CUDA library, include/ev2b.h) through ctypes.
+
+There is NO CPU fallback: if the library is missing or no CUDA device is present the engine
+raises.  The library is built in-tree (ev2gym_b200/csrc/libev2b.so) so it travels with the repo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libev2b.so")
+SOURCES = [os.path.join(CSRC, f) for f in ("ev2b.cu", "ev2b_device.cuh")] + \
+          [os.path.join(os.path.dirname(_HERE), "include", "ev2b.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off"]
+
+_pd, _pi, _pf = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float)
+_pl, _pu, _pb = C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+
+
+class Dims(C.Structure):
+    _fields_ = [("n_envs", C.c_int32), ("n_chargers", C.c_int32), ("n_transformers", C.c_int32),
+                ("sim_length", C.c_int32), ("timescale", C.c_int32), ("dr_steps_ahead", C.c_int32),
+                ("reward_kind", C.c_int32), ("state_kind", C.c_int32), ("tr_voltage", C.c_double)]
+
+
+class TopologyView(C.Structure):
+    _fields_ = [("cs_n_ports", _pi), ("cs_tr", _pi), ("cs_phases", _pi), ("cs_imax", _pd), ("cs_imin", _pd),
+                ("cs_imax_dis", _pd), ("cs_imin_dis", _pd), ("cs_voltage", _pd)]
+
+
+_SCN_F64 = ("charge_price", "discharge_price", "setpoint", "tr_infl", "tr_solar", "tr_max_power", "tr_min_power",
+            "tr_load_fc", "tr_pv_fc")
+_SESS_I = ("s_loc", "s_t_arr", "s_t_dep", "s_ev_phases", "s_lut")
+_SESS_D = ("s_cap0", "s_B", "s_pmax_ac", "s_pmin_ac", "s_pmax_dis", "s_pmin_dis", "s_bmin", "s_bmin_em",
+           "s_desired", "s_ts", "s_mult", "s_eta_c", "s_eta_d")
+
+
+class ScenariosView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_dr", C.c_int32), ("lut_len", C.c_int32)] + \
+               [(k, _pd) for k in _SCN_F64] + \
+               [("dr_start", _pi), ("dr_end", _pi), ("dr_cap", _pd), ("dr_count", _pi), ("sess_off", _pl)] + \
+               [(k, _pi) for k in _SESS_I] + [(k, _pd) for k in _SESS_D] + \
+               [("lut_off", _pl), ("luts_c", _pd), ("luts_d", _pd)]
+
+
+class StepOut(C.Structure):
+    _fields_ = [("reward", C.c_void_p), ("status", C.c_void_p), ("obs", C.c_void_p), ("cs_power", C.c_void_p),
+                ("cs_current", C.c_void_p), ("tr_power", C.c_void_p), ("tr_overload", C.c_void_p),
+                ("total_costs", C.c_void_p), ("action_mask", C.c_void_p), ("dep_sat", C.c_void_p),
+                ("port_energy", C.c_void_p)]
+
+
+class StateView(C.Structure):
+    _fields_ = [("n_envs", C.c_int32), ("n_ports", C.c_int32), ("n_chargers", C.c_int32),
+                ("n_transformers", C.c_int32), ("obs_dim", C.c_int32), ("n_kpi", C.c_int32),
+                ("port_cap", C.c_void_p), ("port_exch", C.c_void_p), ("port_hot", C.c_void_p),
+                ("env_step", C.c_void_p), ("env_scn", C.c_void_p), ("env_potential", C.c_void_p),
+                ("env_usage", C.c_void_p), ("env_kpi", C.c_void_p)]
+
+
+EXPORTS = ("ev2b_abi_version", "ev2b_last_error", "ev2b_create", "ev2b_destroy", "ev2b_obs_dim", "ev2b_n_ports",
+           "ev2b_load_scenarios", "ev2b_n_scenarios", "ev2b_reset", "ev2b_step", "ev2b_step_host",
+           "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in SOURCES)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc-compile libev2b.so for sm_100a (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found and ev2gym_b200/csrc/libev2b.so is missing or stale")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "ev2b.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load libev2b.so; build it first if sources are newer and nvcc exists.  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        if os.path.exists(nvcc):
+            build()
+        elif not os.path.exists(LIB_PATH):
+            raise RuntimeError("libev2b.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+    L = C.CDLL(LIB_PATH)
+    L.ev2b_abi_version.restype = C.c_int
+    L.ev2b_last_error.restype = C.c_char_p
+    L.ev2b_last_error.argtypes = [C.c_void_p]
+    L.ev2b_create.restype = C.c_int
+    L.ev2b_create.argtypes = [C.POINTER(Dims), C.POINTER(TopologyView), C.c_int, C.POINTER(C.c_void_p)]
+    L.ev2b_destroy.restype = None
+    L.ev2b_destroy.argtypes = [C.c_void_p]
+    for f in ("ev2b_obs_dim", "ev2b_n_ports", "ev2b_n_scenarios"):
+        getattr(L, f).restype = C.c_int
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.ev2b_load_scenarios.restype = C.c_int
+    L.ev2b_load_scenarios.argtypes = [C.c_void_p, C.POINTER(ScenariosView)]
+    L.ev2b_reset.restype = C.c_int
+    L.ev2b_reset.argtypes = [C.c_void_p, C.c_int, C.c_int, _pi, C.c_void_p, C.c_void_p]
+    L.ev2b_step.restype = C.c_int
+    L.ev2b_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(StepOut), C.c_void_p]
+    L.ev2b_step_host.restype = C.c_int
+    L.ev2b_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ev2b_reset_done.restype = C.c_int
+    L.ev2b_reset_done.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ev2b_state_view_get.restype = C.c_int
+    L.ev2b_state_view_get.argtypes = [C.c_void_p, C.POINTER(StateView)]
+    L.ev2b_launch_count.restype = C.c_int64
+    L.ev2b_launch_count.argtypes = [C.c_void_p]
+    if L.ev2b_abi_version() != 1:
+        raise RuntimeError("libev2b.so ABI version mismatch")
+    _lib = L
+    return L

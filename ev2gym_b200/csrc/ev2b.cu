@@ -1,0 +1,525 @@
+// ev2b.cu -- host side of libev2b.so: handle, scenario packing, kernel launches (C ABI of include/ev2b.h).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// (-fmad=false: the battery update must round like the reference's float64 Python arithmetic.)
+#include "ev2b_device.cuh"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace ev2b;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T> &v) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct ev2b_handle {
+    ev2b_dims dims{};
+    int device = 0;
+    int C = 0, P = 0, Tr = 0, T = 0, E = 0, D = 0, EPB = 1, block = 32, n_cls = 1, np_uniform = 0;
+    size_t smem = 0;
+    std::string err;
+    int64_t launches = 0;
+    // host copies of the static layout (needed to pack scenarios)
+    std::vector<CsStatic> cs_h;
+    std::vector<int> port_cs;           // port -> charger
+    std::vector<double> cls_imax;       // per charger class
+    std::vector<std::array<double, 4>> cls_veff;
+    // device: static
+    DevBuf<CsStatic> cs; DevBuf<int> tr_cs_off, tr_cs_idx, obs_slot, tr_obs_off;
+    // device: bank
+    int S = 0, Smax = 1, n_dr = 1, lut_len = 101;
+    DevBuf<EnvT> env_t; DevBuf<TrT> tr_t; DevBuf<SessRec> sess; DevBuf<EvSpec> spec;
+    DevBuf<double> luts_c, luts_d, pot_kw; DevBuf<float> trA, trF, tr_limit; DevBuf<DrEv> dr; DevBuf<uint8_t> dr_count;
+    // device: state
+    DevBuf<uint4> hot; DevBuf<double> cap; DevBuf<float> exch; DevBuf<int> env_step, env_scn;
+    DevBuf<double> env_pot, env_usage, env_kpi;
+    // e2e staging (ev2b_step_host)
+    DevBuf<unsigned char> st_actions; DevBuf<double> st_reward; DevBuf<uint32_t> st_status; DevBuf<float> st_obs;
+    DevBuf<int> st_scn;
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+        return code;
+    }
+    Params params() const {
+        Params p{};
+        p.E = E; p.C = C; p.P = P; p.Tr = Tr; p.T = T; p.D = D; p.EPB = EPB; p.n_dr = n_dr; p.lut_len = lut_len;
+        p.Smax = Smax; p.S = S; p.n_cls = n_cls;
+        p.reward_kind = dims.reward_kind; p.state_kind = dims.state_kind; p.dr_steps_ahead = dims.dr_steps_ahead;
+        p.c60 = 60.0 / (double)dims.timescale; p.p60 = (double)dims.timescale / 60.0; p.period = (double)dims.timescale;
+        p.tr_voltage = dims.tr_voltage;
+        p.cs = cs.p; p.tr_cs_off = tr_cs_off.p; p.tr_cs_idx = tr_cs_idx.p; p.obs_slot = obs_slot.p; p.tr_obs_off = tr_obs_off.p;
+        p.env_t = env_t.p; p.tr_t = tr_t.p; p.sess = sess.p; p.spec = spec.p; p.luts_c = luts_c.p; p.luts_d = luts_d.p;
+        p.pot_kw = pot_kw.p; p.trA = trA.p; p.trF = trF.p; p.tr_limit = tr_limit.p; p.dr = dr.p; p.dr_count = dr_count.p;
+        p.hot = hot.p; p.cap = cap.p; p.exch = exch.p; p.env_step = env_step.p; p.env_scn = env_scn.p;
+        p.env_pot = env_pot.p; p.env_usage = env_usage.p; p.env_kpi = env_kpi.p;
+        return p;
+    }
+};
+
+#define CUDA_TRY(h, expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return (h)->fail(EV2B_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+static int obs_dim_for(int kind, int P, int Tr) {
+    switch (kind) {
+    case EV2B_STATE_PUBLIC_PST: return 3 + 3 * P;
+    case EV2B_STATE_V2G_PROFIT_MAX: return 22 + 2 * P;
+    case EV2B_STATE_V2G_PROFIT_MAX_LOADS: return 22 + 40 * Tr + 2 * P;
+    default: return 0;
+    }
+}
+
+template <typename ActT>
+static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st) {
+    const unsigned grid = (unsigned)((h->E + h->EPB - 1) / h->EPB);
+    auto go = [&](auto kern) -> cudaError_t {
+        if (h->smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, h->block, h->smem, st>>>(p);
+        return cudaGetLastError();
+    };
+    if (h->block <= 256) {
+        if (h->np_uniform == 1) return go(step_kernel<ActT, 1, 256>);
+        if (h->np_uniform == 2) return go(step_kernel<ActT, 2, 256>);
+        return go(step_kernel<ActT, 0, 256>);
+    }
+    if (h->np_uniform == 1) return go(step_kernel<ActT, 1, kMaxThreads>);
+    if (h->np_uniform == 2) return go(step_kernel<ActT, 2, kMaxThreads>);
+    return go(step_kernel<ActT, 0, kMaxThreads>);
+}
+
+extern "C" {
+
+int ev2b_abi_version(void) { return EV2B_ABI_VERSION; }
+
+const char *ev2b_last_error(const ev2b_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_handle **out) {
+    if (!d || !tp || !out) { g_create_error = "null argument"; return EV2B_E_ARG; }
+    *out = nullptr;
+    if (d->n_envs < 1 || d->n_chargers < 1 || d->n_transformers < 1 || d->sim_length < 1 || d->timescale < 1) {
+        g_create_error = "ev2b_create: sizes must be >= 1"; return EV2B_E_ARG;
+    }
+    if (d->sim_length > 32000) { g_create_error = "ev2b_create: sim_length > 32000 (int16 step fields)"; return EV2B_E_LIMIT; }
+    if (d->n_chargers > kMaxThreads) {
+        g_create_error = "ev2b_create: more than 1024 chargers per env is not supported yet"; return EV2B_E_LIMIT;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "ev2b_create: no CUDA device (this library has no CPU fallback)"; return EV2B_E_CUDA;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "ev2b_create: cudaSetDevice failed"; return EV2B_E_CUDA; }
+    ev2b_handle *h = new ev2b_handle();
+    h->dims = *d; h->device = device;
+    h->E = d->n_envs; h->C = d->n_chargers; h->Tr = d->n_transformers; h->T = d->sim_length;
+    const int C = h->C;
+    // ---- static charger table ------------------------------------------------------------------
+    h->cs_h.resize(C);
+    int off = 0;
+    bool uniform_ports = true;
+    std::map<std::array<double, 3>, int> cls_of;
+    for (int c = 0; c < C; ++c) {
+        CsStatic &s = h->cs_h[c];
+        const int ph = tp->cs_phases[c];
+        if (ph < 1 || ph > 3 || tp->cs_n_ports[c] < 1 || tp->cs_n_ports[c] > 1023 || tp->cs_tr[c] < 0 ||
+            tp->cs_tr[c] >= h->Tr) {
+            delete h; g_create_error = "ev2b_create: bad charger entry (phases 1..3, n_ports 1..1023, tr in range)";
+            return EV2B_E_ARG;
+        }
+        s.imax = tp->cs_imax[c]; s.imin = tp->cs_imin[c];
+        s.imax_dis_abs = std::fabs(tp->cs_imax_dis[c]);          // ev_charger.py:184
+        s.imin_dis = tp->cs_imin_dis[c];
+        s.veff[0] = 0.0;
+        for (int k = 1; k <= 3; ++k) s.veff[k] = tp->cs_voltage[c] * std::sqrt((double)k);   // ev.py:279
+        s.max_power = std::sqrt((double)ph) * tp->cs_voltage[c] * s.imax / 1000.0;           // utils.py:779-780
+        s.min_power = std::sqrt((double)ph) * tp->cs_voltage[c] * s.imin / 1000.0;           // utils.py:781-782
+        s.port_off = off; s.n_ports = tp->cs_n_ports[c]; s.tr = tp->cs_tr[c]; s.phases = ph;
+        std::array<double, 3> key{s.imax, tp->cs_voltage[c], (double)ph};
+        auto it = cls_of.find(key);
+        if (it == cls_of.end()) {
+            it = cls_of.emplace(key, (int)cls_of.size()).first;
+            h->cls_imax.push_back(s.imax);
+            h->cls_veff.push_back({s.veff[0], s.veff[1], s.veff[2], s.veff[3]});
+        }
+        s.cls = it->second;
+        off += s.n_ports;
+        if (s.n_ports != h->cs_h[0].n_ports) uniform_ports = false;
+        for (int j = 0; j < s.n_ports; ++j) h->port_cs.push_back(c);
+    }
+    h->P = off;
+    h->n_cls = (int)cls_of.size();
+    h->np_uniform = uniform_ports ? h->cs_h[0].n_ports : 0;
+    h->D = obs_dim_for(d->state_kind, h->P, h->Tr);
+    // transformer -> chargers CSR (id order)
+    std::vector<int> tr_off(h->Tr + 1, 0), tr_idx(C);
+    for (int c = 0; c < C; ++c) tr_off[h->cs_h[c].tr + 1]++;
+    for (int k = 0; k < h->Tr; ++k) tr_off[k + 1] += tr_off[k];
+    { std::vector<int> fill(tr_off.begin(), tr_off.end() - 1);
+      for (int c = 0; c < C; ++c) tr_idx[fill[h->cs_h[c].tr]++] = c; }
+    // observation slots: transformer-major, then charger id, then port   state.py:37-42, 85-92, 128-141
+    std::vector<int> slot(h->P, 0), tr_obs(h->Tr, 0);
+    {
+        const int kind = d->state_kind;
+        const int tuple = kind == EV2B_STATE_PUBLIC_PST ? 3 : 2;
+        int o = kind == EV2B_STATE_PUBLIC_PST ? 3 : 22;
+        for (int k = 0; k < h->Tr; ++k) {
+            if (kind == EV2B_STATE_V2G_PROFIT_MAX_LOADS) { tr_obs[k] = o; o += 40; }
+            for (int i = tr_off[k]; i < tr_off[k + 1]; ++i) {
+                const CsStatic &s = h->cs_h[tr_idx[i]];
+                for (int j = 0; j < s.n_ports; ++j) { slot[s.port_off + j] = o; o += tuple; }
+            }
+        }
+    }
+    // launch shape: a CTA owns EPB whole envs, one thread per (env, charger)
+    {
+        int best_epb = 1; double best_u = -1;
+        const int cap_thr = C > 256 ? kMaxThreads : 256;
+        for (int epb = 1; epb <= 64 && epb <= h->E; ++epb) {
+            const int thr = epb * C;
+            if (thr > cap_thr) break;
+            const int blk = (thr + 31) / 32 * 32;
+            const double u = (double)thr / blk;
+            if (u > best_u + 1e-9) { best_u = u; best_epb = epb; }
+        }
+        h->EPB = best_epb;
+        h->block = std::max(32, (best_epb * C + 31) / 32 * 32);
+        h->smem = sizeof(double) * ((size_t)kNRed * h->block + (size_t)h->EPB * h->Tr + (size_t)h->EPB * kNRed) +
+                  sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4) + sizeof(float) * (size_t)h->EPB * h->D;
+    }
+#define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+        g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e); delete h; return EV2B_E_CUDA; } } while (0)
+    CREATE_TRY(h->cs.upload(h->cs_h));
+    CREATE_TRY(h->tr_cs_off.upload(tr_off));
+    CREATE_TRY(h->tr_cs_idx.upload(tr_idx));
+    CREATE_TRY(h->obs_slot.upload(slot));
+    CREATE_TRY(h->tr_obs_off.upload(tr_obs));
+    const size_t EP = (size_t)h->E * h->P;
+    CREATE_TRY(h->hot.alloc(EP)); CREATE_TRY(h->cap.alloc(EP)); CREATE_TRY(h->exch.alloc(EP));
+    CREATE_TRY(h->env_step.alloc(h->E)); CREATE_TRY(h->env_scn.alloc(h->E));
+    CREATE_TRY(h->env_pot.alloc(h->E)); CREATE_TRY(h->env_usage.alloc(h->E));
+    CREATE_TRY(h->env_kpi.alloc((size_t)h->E * EV2B_KPI_COUNT));
+    CREATE_TRY(cudaMemset(h->hot.p, 0, EP * sizeof(uint4)));
+    CREATE_TRY(cudaMemset(h->cap.p, 0, EP * sizeof(double)));
+    CREATE_TRY(cudaMemset(h->exch.p, 0, EP * sizeof(float)));
+    CREATE_TRY(cudaMemset(h->env_scn.p, 0, h->E * sizeof(int)));
+    CREATE_TRY(cudaMemset(h->env_pot.p, 0, h->E * sizeof(double)));
+    CREATE_TRY(cudaMemset(h->env_usage.p, 0, h->E * sizeof(double)));
+    CREATE_TRY(cudaMemset(h->env_kpi.p, 0, (size_t)h->E * EV2B_KPI_COUNT * sizeof(double)));
+    {   // until reset() is called every env reads as "done"
+        std::vector<int> st(h->E, h->T);
+        CREATE_TRY(cudaMemcpy(h->env_step.p, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+#undef CREATE_TRY
+    *out = h;
+    return EV2B_OK;
+}
+
+void ev2b_destroy(ev2b_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    delete h;
+}
+
+int ev2b_obs_dim(const ev2b_handle *h) { return h ? h->D : 0; }
+int ev2b_n_ports(const ev2b_handle *h) { return h ? h->P : 0; }
+int ev2b_n_scenarios(const ev2b_handle *h) { return h ? h->S : 0; }
+int64_t ev2b_launch_count(const ev2b_handle *h) { return h ? h->launches : 0; }
+
+// k/1000.0 == v  <=>  v is what np.round(x, 3) produces (utils.py:293-296, 309-310)
+static bool milli(double v, unsigned *k) {
+    const double r = std::rint(v * 1000.0);
+    if (!(r >= 0.0 && r < 65535.0)) return false;
+    if (r / 1000.0 != v) return false;
+    *k = (unsigned)r;
+    return true;
+}
+
+int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
+    if (!h || !b) return EV2B_E_ARG;
+    if (b->n < 1) return h->fail(EV2B_E_ARG, "load_scenarios: empty bank");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int S = b->n, P = h->P, T = h->T, Tr = h->Tr, C = h->C;
+    const int n_dr = std::max(1, b->n_dr);
+    const int lut_len = b->lut_len > 0 ? b->lut_len : 101;
+
+    // ---- efficiency tables: global de-duplication ------------------------------------------------
+    std::vector<double> luts_c, luts_d;
+    std::map<std::string, int> lut_ids;
+    std::vector<int> lut_global((size_t)b->lut_off[S], -1);
+    for (int64_t i = 0; i < b->lut_off[S]; ++i) {
+        std::string key((const char *)(b->luts_c + i * lut_len), sizeof(double) * lut_len);
+        key.append((const char *)(b->luts_d + i * lut_len), sizeof(double) * lut_len);
+        auto it = lut_ids.find(key);
+        if (it == lut_ids.end()) {
+            it = lut_ids.emplace(key, (int)lut_ids.size()).first;
+            luts_c.insert(luts_c.end(), b->luts_c + i * lut_len, b->luts_c + (i + 1) * lut_len);
+            luts_d.insert(luts_d.end(), b->luts_d + i * lut_len, b->luts_d + (i + 1) * lut_len);
+        }
+        lut_global[i] = it->second;
+    }
+
+    // ---- sessions: replay evs_connected.index(None) (ev_charger.py:273) and pack ----------------
+    std::vector<EvSpec> specs;
+    std::map<std::string, int> spec_ids;
+    struct Placed { int port; int64_t row; };
+    std::vector<std::vector<Placed>> placed(S);
+    int Smax = 1;
+    std::vector<int> occupied_until(P);
+    std::vector<int> per_port(P);
+    for (int i = 0; i < S; ++i) {
+        std::fill(occupied_until.begin(), occupied_until.end(), -1);
+        std::fill(per_port.begin(), per_port.end(), 0);
+        int prev_arr = 1;
+        for (int64_t r = b->sess_off[i]; r < b->sess_off[i + 1]; ++r) {
+            const int ta = b->s_t_arr[r], td = b->s_t_dep[r], loc = b->s_loc[r];
+            if (ta < prev_arr) return h->fail(EV2B_E_SCENARIO, "scenario %d: sessions must be arrival-sorted with t_arr >= 1", i);
+            prev_arr = ta;
+            if (loc < 0 || loc >= C) return h->fail(EV2B_E_SCENARIO, "scenario %d: session location %d out of range", i, loc);
+            if (td < ta) return h->fail(EV2B_E_SCENARIO, "scenario %d: departure before arrival", i);
+            const CsStatic &cs = h->cs_h[loc];
+            int port = -1;
+            for (int j = 0; j < cs.n_ports; ++j) {
+                int &ou = occupied_until[cs.port_off + j];
+                if (ou >= 0 && ou <= ta - 1) ou = -1;     // left during a step <= ta-1
+                if (ou < 0 && port < 0) port = cs.port_off + j;
+            }
+            if (port < 0) return h->fail(EV2B_E_SCENARIO, "scenario %d: charger %d has no free port at step %d", i, loc, ta);
+            occupied_until[port] = td;
+            placed[i].push_back({port, r});
+            Smax = std::max(Smax, ++per_port[port]);
+        }
+    }
+    if (Smax > 255) return h->fail(EV2B_E_LIMIT, "more than 255 sessions on one port");
+    SessRec empty{};
+    empty.hot.x = ((unsigned)kNoArrival & 0xFFFFu) | (0xFFFFu << 16);
+    empty.hot.y = (unsigned)kNoArrival & 0xFFFFu;
+    std::vector<SessRec> sess((size_t)S * P * Smax, empty);
+    std::vector<int> last_of_port(P);
+    for (int i = 0; i < S; ++i) {
+        std::fill(per_port.begin(), per_port.end(), 0);
+        std::fill(last_of_port.begin(), last_of_port.end(), -1);
+        for (const Placed &pl : placed[i]) {
+            const int64_t r = pl.row;
+            EvSpec sp{};
+            sp.B = b->s_B[r]; sp.pmax_ac = b->s_pmax_ac[r]; sp.pmin_ac = b->s_pmin_ac[r];
+            sp.pmax_dis = b->s_pmax_dis[r]; sp.pmin_dis = b->s_pmin_dis[r]; sp.bmin = b->s_bmin[r];
+            sp.bmin_em = b->s_bmin_em[r]; sp.desired = b->s_desired[r]; sp.mult = b->s_mult[r];
+            sp.ev_phases = b->s_ev_phases[r];
+            if (sp.ev_phases < 1 || sp.ev_phases > 3) return h->fail(EV2B_E_SCENARIO, "scenario %d: ev_phases must be 1..3", i);
+            sp.lut = b->s_lut[r] >= 0 ? lut_global[b->lut_off[i] + b->s_lut[r]] : -1;
+            unsigned tsm = 0xFFFFu, ecm = 0xFFFFu, edm = 0xFFFFu;
+            sp.ts = sp.eta_c = sp.eta_d = 0.0;
+            if (!milli(b->s_ts[r], &tsm)) { tsm = 0xFFFFu; sp.ts = b->s_ts[r]; }
+            if (sp.lut < 0) {
+                if (!milli(b->s_eta_c[r], &ecm)) { ecm = 0xFFFFu; sp.eta_c = b->s_eta_c[r]; }
+                if (!milli(b->s_eta_d[r], &edm)) { edm = 0xFFFFu; sp.eta_d = b->s_eta_d[r]; }
+                if (!(b->s_eta_c[r] > 0.0)) return h->fail(EV2B_E_SCENARIO, "scenario %d: charge_efficiency must be > 0 (ev.py:293)", i);
+            } else { ecm = edm = 0; }
+            std::string key((const char *)&sp, sizeof sp);
+            auto it = spec_ids.find(key);
+            if (it == spec_ids.end()) {
+                if (specs.size() >= 65535) return h->fail(EV2B_E_LIMIT, "more than 65535 distinct EV specs");
+                it = spec_ids.emplace(key, (int)specs.size()).first;
+                specs.push_back(sp);
+            }
+            const int ta = std::min(b->s_t_arr[r], 32766), td = std::min(b->s_t_dep[r], 32766);
+            const int k = per_port[pl.port]++;
+            SessRec &rec = sess[((size_t)i * P + pl.port) * Smax + k];
+            rec.hot.x = ((unsigned)ta & 0xFFFFu) | (((unsigned)td & 0xFFFFu) << 16);
+            rec.hot.y = ((unsigned)kNoArrival & 0xFFFFu) | ((unsigned)(k + 1) << 16);   // next_arr patched below
+            rec.hot.z = (unsigned)it->second | (tsm << 16);
+            rec.hot.w = ecm | (edm << 16);
+            rec.cap0 = b->s_cap0[r];
+            if (last_of_port[pl.port] >= 0) {
+                SessRec &prev = sess[((size_t)i * P + pl.port) * Smax + last_of_port[pl.port]];
+                prev.hot.y = (prev.hot.y & 0xFFFF0000u) | ((unsigned)ta & 0xFFFFu);
+            }
+            last_of_port[pl.port] = k;
+        }
+    }
+    // potential contribution per (spec, charger class)          utils.py:772-777
+    std::vector<double> pot_kw(specs.size() * h->n_cls);
+    {
+        std::vector<int> cls_ph(h->n_cls, 3);
+        for (const CsStatic &s : h->cs_h) cls_ph[s.cls] = s.phases;
+        for (size_t q = 0; q < specs.size(); ++q)
+            for (int k = 0; k < h->n_cls; ++k) {
+                const int ph = std::min(cls_ph[k], specs[q].ev_phases);
+                const double sv = h->cls_veff[k][ph];                       // sqrt(phases)*voltage
+                const double ev_current = specs[q].pmax_ac * 1000.0 / sv;
+                const double current = std::min(h->cls_imax[k], ev_current);
+                pot_kw[q * h->n_cls + k] = sv * current / 1000.0;
+            }
+    }
+    // ---- time series -----------------------------------------------------------------------------
+    std::vector<EnvT> env_t((size_t)S * T);
+    std::vector<TrT> tr_t((size_t)S * T * Tr);
+    std::vector<float> trA((size_t)S * Tr * T), trF((size_t)S * Tr * T), tr_limit((size_t)S * Tr);
+    std::vector<DrEv> dr((size_t)S * Tr * n_dr, DrEv{0, 0, 0.f});
+    std::vector<uint8_t> dr_count((size_t)S * Tr, 0);
+    for (int i = 0; i < S; ++i) {
+        for (int t = 0; t < T; ++t) {
+            EnvT &e = env_t[(size_t)i * T + t];
+            e.cp = b->charge_price[(size_t)i * T + t]; e.dp = b->discharge_price[(size_t)i * T + t];
+            e.setpoint = b->setpoint[(size_t)i * T + t]; e.pad = 0;
+        }
+        for (int k = 0; k < Tr; ++k) {
+            const size_t base = ((size_t)i * Tr + k) * T;
+            double limit = b->tr_max_power[base];
+            for (int t = 0; t < T; ++t) {
+                TrT &x = tr_t[((size_t)i * T + t) * Tr + k];
+                x.infl = b->tr_infl[base + t]; x.solar = b->tr_solar[base + t];
+                x.maxp = b->tr_max_power[base + t]; x.minp = b->tr_min_power[base + t];
+                trA[base + t] = (float)(b->tr_infl[base + t] - b->tr_solar[base + t]);
+                trF[base + t] = (float)(b->tr_load_fc[base + t] - b->tr_pv_fc[base + t]);
+                limit = std::max(limit, x.maxp);                            // max(self.max_power) transformer.py:150
+            }
+            tr_limit[(size_t)i * Tr + k] = (float)limit;
+            const int nd = b->dr_count ? b->dr_count[(size_t)i * Tr + k] : 0;
+            if (nd > n_dr || nd > 255) return h->fail(EV2B_E_SCENARIO, "scenario %d: dr_count > n_dr", i);
+            dr_count[(size_t)i * Tr + k] = (uint8_t)nd;
+            for (int q = 0; q < nd; ++q) {
+                const size_t di = ((size_t)i * Tr + k) * b->n_dr + q;
+                DrEv &d = dr[((size_t)i * Tr + k) * n_dr + q];
+                d.start = (int16_t)std::max(-32000, std::min(32000, b->dr_start[di]));
+                d.end = (int16_t)std::max(-32000, std::min(32000, b->dr_end[di]));
+                d.value = (float)(limit - limit * b->dr_cap[di] / 100.0);   // transformer.py:158-159
+            }
+        }
+    }
+    if (luts_c.empty()) { luts_c.assign(lut_len, 1.0); luts_d.assign(lut_len, 1.0); }
+    if (specs.empty()) { specs.push_back(EvSpec{}); pot_kw.assign(h->n_cls, 0.0); }
+    CUDA_TRY(h, h->env_t.upload(env_t)); CUDA_TRY(h, h->tr_t.upload(tr_t)); CUDA_TRY(h, h->sess.upload(sess));
+    CUDA_TRY(h, h->spec.upload(specs)); CUDA_TRY(h, h->luts_c.upload(luts_c)); CUDA_TRY(h, h->luts_d.upload(luts_d));
+    CUDA_TRY(h, h->pot_kw.upload(pot_kw)); CUDA_TRY(h, h->trA.upload(trA)); CUDA_TRY(h, h->trF.upload(trF));
+    CUDA_TRY(h, h->tr_limit.upload(tr_limit)); CUDA_TRY(h, h->dr.upload(dr)); CUDA_TRY(h, h->dr_count.upload(dr_count));
+    h->S = S; h->Smax = Smax; h->n_dr = n_dr; h->lut_len = lut_len;
+    {   // a new bank invalidates every running episode
+        std::vector<int> st(h->E, h->T);
+        CUDA_TRY(h, cudaMemcpy(h->env_step.p, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return EV2B_OK;
+}
+
+static int launch_reset(ev2b_handle *h, int lo, int hi, const int *scn_dev, int mode, float *obs0, cudaStream_t st) {
+    const Params p = h->params();
+    const size_t n = (size_t)(hi - lo) * h->P;
+    const int blk = 256;
+    reset_ports_kernel<<<(unsigned)((n + blk - 1) / blk), blk, 0, st>>>(p, lo, hi, scn_dev, mode);
+    reset_envs_kernel<<<hi - lo, 128, 0, st>>>(p, lo, hi, scn_dev, mode, obs0);
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    return EV2B_OK;
+}
+
+int ev2b_reset(ev2b_handle *h, int env_lo, int env_hi, const int32_t *scn_ids, float *obs0, void *stream) {
+    if (!h) return EV2B_E_ARG;
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "reset: no scenario bank loaded");
+    if (env_lo < 0 || env_hi > h->E || env_lo >= env_hi) return h->fail(EV2B_E_ARG, "reset: bad env range [%d,%d)", env_lo, env_hi);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int *scn_dev = nullptr;
+    if (scn_ids) {
+        for (int i = 0; i < env_hi - env_lo; ++i)
+            if (scn_ids[i] < 0 || scn_ids[i] >= h->S) return h->fail(EV2B_E_ARG, "reset: scenario id %d out of range", scn_ids[i]);
+        if (h->st_scn.n < (size_t)h->E) CUDA_TRY(h, h->st_scn.alloc(h->E));
+        CUDA_TRY(h, cudaMemcpyAsync(h->st_scn.p, scn_ids, sizeof(int) * (env_hi - env_lo), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaStreamSynchronize(st));   // scn_ids is a caller-owned (possibly pageable) host buffer
+        scn_dev = h->st_scn.p;
+    }
+    return launch_reset(h, env_lo, env_hi, scn_dev, 0, obs0, st);
+}
+
+int ev2b_reset_done(ev2b_handle *h, float *obs0, void *stream) {
+    if (!h) return EV2B_E_ARG;
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "reset_done: no scenario bank loaded");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return launch_reset(h, 0, h->E, nullptr, 1, obs0, (cudaStream_t)stream);
+}
+
+int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, void *stream) {
+    if (!h || !actions) return h ? h->fail(EV2B_E_ARG, "step: null actions") : EV2B_E_ARG;
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "step: no scenario bank loaded");
+    Params p = h->params();
+    p.actions = actions;
+    if (out) p.out = *out;
+    cudaError_t e;
+    if (action_dtype == EV2B_F32) e = launch_step<float>(h, p, (cudaStream_t)stream);
+    else if (action_dtype == EV2B_F64) e = launch_step<double>(h, p, (cudaStream_t)stream);
+    else return h->fail(EV2B_E_ARG, "step: unknown action dtype %d", action_dtype);
+    if (e != cudaSuccess) return h->fail(EV2B_E_CUDA, "step launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return EV2B_OK;
+}
+
+int ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype, double *reward_host,
+                   uint32_t *status_host, float *obs_host, void *stream) {
+    if (!h || !actions_host) return h ? h->fail(EV2B_E_ARG, "step_host: null actions") : EV2B_E_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = action_dtype == EV2B_F64 ? 8 : 4;
+    const size_t nbytes = (size_t)h->E * h->P * esz;
+    if (h->st_actions.n < nbytes) CUDA_TRY(h, h->st_actions.alloc(nbytes));
+    if (h->st_reward.n < (size_t)h->E) { CUDA_TRY(h, h->st_reward.alloc(h->E)); CUDA_TRY(h, h->st_status.alloc(h->E)); }
+    if (obs_host && h->D > 0 && h->st_obs.n < (size_t)h->E * h->D) CUDA_TRY(h, h->st_obs.alloc((size_t)h->E * h->D));
+    CUDA_TRY(h, cudaMemcpyAsync(h->st_actions.p, actions_host, nbytes, cudaMemcpyHostToDevice, st));
+    ev2b_step_out out{};
+    out.reward = h->st_reward.p; out.status = h->st_status.p;
+    out.obs = (obs_host && h->D > 0) ? h->st_obs.p : nullptr;
+    int rc = ev2b_step(h, h->st_actions.p, action_dtype, &out, stream);
+    if (rc != EV2B_OK) return rc;
+    if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host, h->st_reward.p, sizeof(double) * h->E, cudaMemcpyDeviceToHost, st));
+    if (status_host) CUDA_TRY(h, cudaMemcpyAsync(status_host, h->st_status.p, sizeof(uint32_t) * h->E, cudaMemcpyDeviceToHost, st));
+    if (out.obs) CUDA_TRY(h, cudaMemcpyAsync(obs_host, h->st_obs.p, sizeof(float) * (size_t)h->E * h->D, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return EV2B_OK;
+}
+
+int ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *v) {
+    if (!h || !v) return EV2B_E_ARG;
+    v->n_envs = h->E; v->n_ports = h->P; v->n_chargers = h->C; v->n_transformers = h->Tr; v->obs_dim = h->D;
+    v->n_kpi = EV2B_KPI_COUNT;
+    v->port_cap = h->cap.p; v->port_exch = h->exch.p; v->port_hot = reinterpret_cast<uint32_t *>(h->hot.p);
+    v->env_step = h->env_step.p; v->env_scn = h->env_scn.p; v->env_potential = h->env_pot.p;
+    v->env_usage = h->env_usage.p; v->env_kpi = h->env_kpi.p;
+    return EV2B_OK;
+}
+
+}  // extern "C"

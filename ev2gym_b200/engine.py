@@ -1,0 +1,237 @@
+"""BatchedEngine: thin Python owner of one libev2b handle (one per GPU).
+
+PyTorch is plumbing here: it allocates the output buffers, provides the CUDA stream, and wraps
+the engine's struct-of-arrays state as zero-copy `torch.Tensor` views for RL code.  All compute
+is in the hand-written CUDA kernels behind the C ABI (include/ev2b.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .scenario import LUT_LEN, SESSION_F64_FIELDS, SESSION_INT_FIELDS, Scenario, Topology
+
+REWARD_KINDS = {None: 0, "none": 0, "SquaredTrackingErrorReward": 1,
+                "ProfitMax_TrPenalty_UserIncentives": 2, "profit_maximization": 3}
+STATE_KINDS = {None: 0, "none": 0, "PublicPST": 1, "V2G_profit_max": 2, "V2G_profit_max_loads": 3}
+
+ST_DONE, ST_AMPS_OVERFLOW, ST_WAS_DONE = 1, 2, 4
+KPI_NAMES = ("total_reward", "total_profits", "total_energy_charged", "total_energy_discharged",
+             "total_transformer_overload", "total_ev_served", "sat_sum", "tracking_error",
+             "energy_tracking_error_steps", "power_tracker_violation", "total_evs_spawned", "invalid_actions",
+             "steps")
+
+_OUT_SPECS = {  # name -> (dtype, per-env shape key)
+    "reward": ("float64", ()), "status": ("int32", ()), "obs": ("float32", ("D",)),
+    "cs_power": ("float32", ("C",)), "cs_current": ("float32", ("C",)),
+    "tr_power": ("float64", ("Tr",)), "tr_overload": ("float64", ("Tr",)), "total_costs": ("float64", ()),
+    "action_mask": ("uint8", ("P",)), "dep_sat": ("float32", ("P",)), "port_energy": ("float32", ("P",)),
+}
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _fn_name(f) -> Optional[str]:
+    if f is None or isinstance(f, str):
+        return f
+    return getattr(f, "__name__", None)
+
+
+class _CudaView:
+    """Minimal __cuda_array_interface__ carrier so torch can wrap a raw device pointer zero-copy."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+        self._owner = owner
+
+
+class BatchedEngine:
+    def __init__(self, topo: Topology, n_envs: int, reward=None, state=None, device: int = 0,
+                 outputs: Iterable[str] = ("reward", "status", "obs")):
+        import torch  # plumbing only
+        if not torch.cuda.is_available():
+            raise EngineError("ev2gym_b200 needs a CUDA device: there is no CPU fallback in the product path")
+        self.torch = torch
+        self.L = _lib.load()
+        self.topo, self.E, self.device = topo, int(n_envs), int(device)
+        r, s = _fn_name(reward), _fn_name(state)
+        if r not in REWARD_KINDS or s not in STATE_KINDS:
+            raise EngineError(f"no fused device implementation for reward={r!r} / state={s!r}")
+        self.reward_name, self.state_name = r, s
+        d = _lib.Dims(self.E, topo.C, topo.Tr, topo.T, topo.timescale, topo.dr_steps_ahead, REWARD_KINDS[r],
+                      STATE_KINDS[s], float(topo.tr_voltage))
+        self._keep = [topo.cs_n_ports, topo.cs_tr, topo.cs_phases, topo.cs_imax, topo.cs_imin, topo.cs_imax_dis,
+                      topo.cs_imin_dis, topo.cs_voltage]
+        tv = _lib.TopologyView(*[a.ctypes.data_as(t) for a, (_, t) in zip(self._keep, _lib.TopologyView._fields_)])
+        h = C.c_void_p()
+        rc = self.L.ev2b_create(C.byref(d), C.byref(tv), self.device, C.byref(h))
+        if rc != 0:
+            raise EngineError(f"ev2b_create failed ({rc}): {self.L.ev2b_last_error(None).decode()}")
+        self.h = h
+        self.P, self.C_, self.Tr, self.T = topo.P, topo.C, topo.Tr, topo.T
+        self.D = self.L.ev2b_obs_dim(self.h)
+        self.dev = torch.device("cuda", self.device)
+        self.out: Dict[str, "torch.Tensor"] = {}
+        self._so = _lib.StepOut()
+        self.set_outputs(outputs)
+        self.n_scenarios = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self.L.ev2b_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ev2b_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_outputs(self, names: Iterable[str]):
+        torch = self.torch
+        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P}
+        self.out = {}
+        self._so = _lib.StepOut()
+        for n in names:
+            if n == "obs" and self.D == 0:
+                continue
+            dt, shp = _OUT_SPECS[n]
+            t = torch.zeros((self.E,) + tuple(dims[k] for k in shp), dtype=getattr(torch, dt), device=self.dev)
+            self.out[n] = t
+            setattr(self._so, n, t.data_ptr())
+
+    def _stream(self) -> int:
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    # ------------------------------------------------------------------------------------------
+    def load_scenarios(self, scenarios: Sequence[Scenario]):
+        """Upload a scenario bank (replaces the previous one; every env must be reset afterwards)."""
+        n = len(scenarios)
+        T, Tr = self.T, self.Tr
+        for sc in scenarios:
+            sc.normalise()
+            if sc.charge_price.shape != (T,) or sc.tr_infl.shape != (Tr, T):
+                raise EngineError("scenario shape does not match the engine's topology")
+        v = _lib.ScenariosView()
+        keep = []
+
+        def put(name, arr, ptr_t):
+            arr = np.ascontiguousarray(arr)
+            keep.append(arr)
+            setattr(v, name, arr.ctypes.data_as(ptr_t))
+
+        v.n = n
+        ndr = max(int(sc.dr_start.shape[1]) for sc in scenarios)
+        v.n_dr, v.lut_len = ndr, LUT_LEN
+
+        def pad_dr(a, fill=0):
+            out = np.full((Tr, ndr), fill, dtype=a.dtype)
+            out[:, :a.shape[1]] = a
+            return out
+
+        for k in _lib._SCN_F64:
+            put(k, np.stack([getattr(sc, k) for sc in scenarios]).astype(np.float64), _lib._pd)
+        put("dr_start", np.stack([pad_dr(sc.dr_start) for sc in scenarios]).astype(np.int32), _lib._pi)
+        put("dr_end", np.stack([pad_dr(sc.dr_end) for sc in scenarios]).astype(np.int32), _lib._pi)
+        put("dr_cap", np.stack([pad_dr(sc.dr_cap) for sc in scenarios]).astype(np.float64), _lib._pd)
+        put("dr_count", np.stack([sc.dr_count for sc in scenarios]).astype(np.int32), _lib._pi)
+        s_off = np.zeros(n + 1, dtype=np.int64)
+        l_off = np.zeros(n + 1, dtype=np.int64)
+        for i, sc in enumerate(scenarios):
+            s_off[i + 1] = s_off[i] + sc.n_sessions
+            l_off[i + 1] = l_off[i] + sc.luts_c.shape[0]
+        put("sess_off", s_off, _lib._pl)
+        put("lut_off", l_off, _lib._pl)
+        for k in SESSION_INT_FIELDS:
+            put("s_" + k, np.concatenate([sc.sessions[k] for sc in scenarios]).astype(np.int32), _lib._pi)
+        for k in SESSION_F64_FIELDS:
+            put("s_" + k, np.concatenate([sc.sessions[k] for sc in scenarios]).astype(np.float64), _lib._pd)
+        put("luts_c", np.concatenate([sc.luts_c.reshape(-1) for sc in scenarios] + [np.zeros(0)]), _lib._pd)
+        put("luts_d", np.concatenate([sc.luts_d.reshape(-1) for sc in scenarios] + [np.zeros(0)]), _lib._pd)
+        self._check(self.L.ev2b_load_scenarios(self.h, C.byref(v)), "ev2b_load_scenarios")
+        self.n_scenarios = n
+
+    def reset(self, env_lo: int = 0, env_hi: Optional[int] = None, scn_ids: Optional[Sequence[int]] = None):
+        """Reset envs [env_lo, env_hi); returns the observation tensor [E,D] (rows of that range refreshed)."""
+        env_hi = self.E if env_hi is None else env_hi
+        ids = None
+        if scn_ids is not None:
+            ids_np = np.ascontiguousarray(scn_ids, dtype=np.int32)
+            assert ids_np.shape == (env_hi - env_lo,)
+            ids = ids_np.ctypes.data_as(_lib._pi)
+        obs = self.out.get("obs")
+        self._check(self.L.ev2b_reset(self.h, env_lo, env_hi, ids, obs.data_ptr() if obs is not None else None,
+                                      self._stream()), "ev2b_reset")
+        return obs
+
+    def reset_done(self):
+        obs = self.out.get("obs")
+        self._check(self.L.ev2b_reset_done(self.h, obs.data_ptr() if obs is not None else None, self._stream()),
+                    "ev2b_reset_done")
+        return obs
+
+    def step(self, actions) -> Dict[str, "torch.Tensor"]:
+        """One fused kernel launch advancing all E envs.  actions: cuda tensor [E,P], float32 or float64."""
+        torch = self.torch
+        if actions.device != self.dev or tuple(actions.shape) != (self.E, self.P) or not actions.is_contiguous():
+            raise EngineError(f"actions must be a contiguous cuda tensor of shape {(self.E, self.P)} on {self.dev}")
+        if actions.dtype == torch.float32:
+            dt = 0
+        elif actions.dtype == torch.float64:
+            dt = 1
+        else:
+            raise EngineError("actions must be float32 or float64")
+        self._check(self.L.ev2b_step(self.h, actions.data_ptr(), dt, C.byref(self._so), self._stream()), "ev2b_step")
+        return self.out
+
+    def step_host(self, actions: np.ndarray, reward: np.ndarray, status: np.ndarray, obs: Optional[np.ndarray] = None):
+        """End-to-end step with HOST buffers (H2D actions, kernel, D2H reward/status[/obs], sync)."""
+        dt = {np.dtype("float32"): 0, np.dtype("float64"): 1}[actions.dtype]
+        assert actions.shape == (self.E, self.P) and actions.flags.c_contiguous
+        self._check(self.L.ev2b_step_host(self.h, actions.ctypes.data, dt, reward.ctypes.data, status.ctypes.data,
+                                          obs.ctypes.data if obs is not None else None, self._stream()),
+                    "ev2b_step_host")
+
+    # ------------------------------------------------------------------------------------------
+    def state_tensors(self) -> Dict[str, "torch.Tensor"]:
+        """Zero-copy torch views of the SoA state (valid until the engine is closed)."""
+        torch = self.torch
+        sv = _lib.StateView()
+        self._check(self.L.ev2b_state_view_get(self.h, C.byref(sv)), "ev2b_state_view_get")
+        E, P = self.E, self.P
+
+        def view(ptr, shape, typestr):
+            return torch.as_tensor(_CudaView(ptr, shape, typestr, self), device=self.dev)
+        return {
+            "port_cap": view(sv.port_cap, (E, P), "<f8"), "port_exch": view(sv.port_exch, (E, P), "<f4"),
+            "port_hot": view(sv.port_hot, (E, P, 4), "<i4"), "env_step": view(sv.env_step, (E,), "<i4"),
+            "env_scn": view(sv.env_scn, (E,), "<i4"), "env_potential": view(sv.env_potential, (E,), "<f8"),
+            "env_usage": view(sv.env_usage, (E,), "<f8"), "env_kpi": view(sv.env_kpi, (E, sv.n_kpi), "<f8"),
+        }
+
+    def kpis(self) -> Dict[str, np.ndarray]:
+        k = self.state_tensors()["env_kpi"].cpu().numpy()
+        return {n: k[:, i].copy() for i, n in enumerate(KPI_NAMES)}
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.ev2b_launch_count(self.h))
+
+    @staticmethod
+    def decode_hot(hot: np.ndarray) -> Dict[str, np.ndarray]:
+        """Unpack the [.,4] int32 hot words into t_arr / t_dep / next_arr / spec fields."""
+        w = hot.astype(np.int64) & 0xFFFFFFFF
+        i16 = lambda x: ((x & 0xFFFF) ^ 0x8000) - 0x8000
+        return {"t_arr": i16(w[..., 0]), "t_dep": i16(w[..., 0] >> 16), "next_arr": i16(w[..., 1]),
+                "cursor": (w[..., 1] >> 16) & 0xFF, "spec": w[..., 2] & 0xFFFF, "ts_milli": w[..., 2] >> 16}

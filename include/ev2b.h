@@ -1,0 +1,188 @@
+/*
+ * ev2b.h -- C ABI of the B200-native batched EV2Gym environment-step engine (libev2b.so).
+ *
+ * The reference (StavrosOrf/EV2Gym) has NO FFI on this path: its boundary is the Python call
+ * convention of `EV2Gym.reset()/step()` (ev2gym/models/ev2gym_env.py:243-331, 333-447).  This
+ * header is the C surface a binding for that boundary binds instead;
+ * each entry point names the reference code it replaces.  Plain pointers and sizes only: no
+ * torch / C++ types cross this boundary.  The Python facade (ev2gym_b200/env.py) and the
+ * ctypes stub shown in INTEGRATION.md sit directly on top of it.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; ev2b_last_error() gives the text
+ *   - one handle per GPU, not thread-safe (the reference env is not re-entrant either)
+ *   - `stream` is a cudaStream_t passed as void*; all device work is stream-ordered,
+ *     nothing synchronises the host unless documented (ev2b_step_host, ev2b_read_*)
+ *   - "env" = one replica of the reference's EV2Gym object; "port" index is charger-major,
+ *     i.e. the reference's action order (ev2gym_env.py:363-385)
+ *   - arithmetic: float64, same operation order as the reference, FMA contraction off
+ *     (battery level carries a ceil(x*100)/100 every active step, ev2gym/models/ev.py:183)
+ */
+#ifndef EV2B_H
+#define EV2B_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EV2B_ABI_VERSION 1
+
+/* reward_function / state_function fused on the device (ev2gym/rl_agent/reward.py, state.py). */
+enum ev2b_reward_kind {
+    EV2B_REWARD_NONE = 0,                 /* reward output = 0 (caller computes its own)            */
+    EV2B_REWARD_SQ_TRACKING = 1,          /* SquaredTrackingErrorReward            reward.py:7-14   */
+    EV2B_REWARD_PROFIT_TR_USER = 2,       /* ProfitMax_TrPenalty_UserIncentives    reward.py:34-44  */
+    EV2B_REWARD_PROFIT_MAX = 3            /* profit_maximization                   reward.py:78-87  */
+};
+enum ev2b_state_kind {
+    EV2B_STATE_NONE = 0,
+    EV2B_STATE_PUBLIC_PST = 1,            /* PublicPST            state.py:6-63    D = 3 + 3P        */
+    EV2B_STATE_V2G_PROFIT_MAX = 2,        /* V2G_profit_max       state.py:65-106  D = 22 + 2P       */
+    EV2B_STATE_V2G_PROFIT_MAX_LOADS = 3   /* V2G_profit_max_loads state.py:108-155 D = 22 + 40Tr + 2P */
+};
+enum ev2b_action_dtype { EV2B_F32 = 0, EV2B_F64 = 1 };
+
+/* error codes */
+enum {
+    EV2B_OK = 0, EV2B_E_ARG = -1, EV2B_E_CUDA = -2, EV2B_E_STATE = -3, EV2B_E_SCENARIO = -4,
+    EV2B_E_LIMIT = -5
+};
+
+/* per-env status bits written by the step kernel (ev2b_step_out.status) */
+#define EV2B_ST_DONE          1u   /* current_step >= simulation_length       ev2gym_env.py:460        */
+#define EV2B_ST_AMPS_OVERFLOW 2u   /* the reference would `raise Exception`   ev_charger.py:203-205    */
+#define EV2B_ST_WAS_DONE      4u   /* step() on a finished env (reference: AssertionError, :343)       */
+
+typedef struct ev2b_handle ev2b_handle;
+
+/* Problem sizes; replaces the size-bearing part of the YAML config (ev2gym_env.py:78-128). */
+typedef struct {
+    int32_t n_envs;            /* E  env replicas resident on this GPU                        */
+    int32_t n_chargers;        /* C  number_of_charging_stations                              */
+    int32_t n_transformers;    /* Tr                                                          */
+    int32_t sim_length;        /* T  simulation_length                                        */
+    int32_t timescale;         /* minutes per step                                            */
+    int32_t dr_steps_ahead;    /* notification_of_event_minutes // timescale (transformer.py:69) */
+    int32_t reward_kind;       /* enum ev2b_reward_kind                                       */
+    int32_t state_kind;        /* enum ev2b_state_kind                                        */
+    double  tr_voltage;        /* voltage*sqrt(phases) of the config   (transformer.py:39-40) */
+} ev2b_dims;
+
+/* Static charger layout, HOST pointers; replaces load_ev_charger_profiles / cs_transformers
+ * (ev2gym/utilities/loaders.py:299-365, 495-498).  Arrays have n_chargers entries. */
+typedef struct {
+    const int32_t *cs_n_ports;     /* n_ports                      */
+    const int32_t *cs_tr;          /* connected_transformer        */
+    const int32_t *cs_phases;      /* phases (1..3)                */
+    const double  *cs_imax;        /* max_charge_current           */
+    const double  *cs_imin;        /* min_charge_current           */
+    const double  *cs_imax_dis;    /* max_discharge_current (<=0)  */
+    const double  *cs_imin_dis;    /* min_discharge_current        */
+    const double  *cs_voltage;     /* voltage                      */
+} ev2b_topology;
+
+/* A bank of n pre-sampled episodes ("scenarios"), HOST pointers, plain float64/int32 exactly as
+ * the reference objects hold them after reset() (ev2gym_env.py:293-296).  The library replays
+ * the first-free-port rule (ev_charger.py:273), de-duplicates EV specs / efficiency tables and
+ * packs everything for the device.  Sessions of scenario i are rows sess_off[i]..sess_off[i+1]
+ * (arrival-sorted, = env.EVs_profiles order); its efficiency tables are rows
+ * lut_off[i]..lut_off[i+1] of luts_c/luts_d and s_lut indexes them locally (-1 = scalar). */
+typedef struct {
+    int32_t n;                                     /* scenarios in this call                       */
+    int32_t n_dr;                                  /* DR events stored per transformer (padded)    */
+    int32_t lut_len;                               /* entries per efficiency table (101)           */
+    const double *charge_price, *discharge_price;  /* [n*T]      loaders.py:439-460 (row 0)        */
+    const double *setpoint;                        /* [n*T]      power_setpoints                   */
+    const double *tr_infl, *tr_solar;              /* [n*Tr*T]   inflexible_load, solar_power (<=0)*/
+    const double *tr_max_power, *tr_min_power;     /* [n*Tr*T]   after DR events                   */
+    const double *tr_load_fc, *tr_pv_fc;           /* [n*Tr*T]   forecasts                         */
+    const int32_t *dr_start, *dr_end;              /* [n*Tr*n_dr]                                  */
+    const double  *dr_cap;                         /* [n*Tr*n_dr] capacity_percentage              */
+    const int32_t *dr_count;                       /* [n*Tr]                                       */
+    const int64_t *sess_off;                       /* [n+1]                                        */
+    const int32_t *s_loc, *s_t_arr, *s_t_dep, *s_ev_phases, *s_lut;
+    const double  *s_cap0, *s_B, *s_pmax_ac, *s_pmin_ac, *s_pmax_dis, *s_pmin_dis, *s_bmin, *s_bmin_em,
+                  *s_desired, *s_ts, *s_mult, *s_eta_c, *s_eta_d;
+    const int64_t *lut_off;                        /* [n+1]                                        */
+    const double  *luts_c, *luts_d;                /* [lut_off[n]*lut_len] percent                 */
+} ev2b_scenarios;
+
+/* Per-step outputs, DEVICE pointers owned by the caller; any pointer may be NULL (= not wanted).
+ * Replaces the 5-tuple of EV2Gym.step plus the attributes rewards/states/agents read afterwards. */
+typedef struct {
+    double   *reward;        /* [E]     reward of this step                  ev2gym_env.py:430-432 */
+    uint32_t *status;        /* [E]     EV2B_ST_* bits (done etc.)           ev2gym_env.py:460     */
+    float    *obs;           /* [E,D]   state_function(env), float32         ev2gym_env.py:563-565 */
+    float    *cs_power;      /* [E,C]   cs.current_power_output (kW)         ev_charger.py:180,196 */
+    float    *cs_current;    /* [E,C]   cs.current_total_amps (A)            ev_charger.py:181,197 */
+    double   *tr_power;      /* [E,Tr]  tr.current_power                     transformer.py:264-274 */
+    double   *tr_overload;   /* [E,Tr]  tr.get_how_overloaded()              transformer.py:292-302 */
+    double   *total_costs;   /* [E]     sum of charger profits (`total_costs`) ev2gym_env.py:381   */
+    uint8_t  *action_mask;   /* [E,P]   1 if an EV is connected after the step ev2gym_env.py:452-457 */
+    float    *dep_sat;       /* [E,P]   user satisfaction of the EV that left this port this step, NaN otherwise */
+    float    *port_energy;   /* [E,P]   ev.current_energy of this step (kWh)                       */
+} ev2b_step_out;
+
+/* Raw DEVICE pointers into the struct-of-arrays state, for zero-copy tensor views. */
+typedef struct {
+    int32_t n_envs, n_ports, n_chargers, n_transformers, obs_dim, n_kpi;
+    double   *port_cap;        /* [E,P] current_capacity (kWh), float64                             */
+    float    *port_exch;       /* [E,P] total_energy_exchanged                                     */
+    uint32_t *port_hot;        /* [E,P,4] packed session words, see DESIGN.md                      */
+    int32_t  *env_step;        /* [E]   current_step                                               */
+    int32_t  *env_scn;         /* [E]   scenario id in the bank                                    */
+    double   *env_potential;   /* [E]   charge_power_potential[current_step]                       */
+    double   *env_usage;       /* [E]   current_power_usage[current_step-1]                        */
+    double   *env_kpi;         /* [E,n_kpi] running KPI sums, see enum ev2b_kpi                    */
+} ev2b_state_view;
+
+enum ev2b_kpi {
+    EV2B_KPI_TOTAL_REWARD = 0, EV2B_KPI_TOTAL_PROFITS, EV2B_KPI_ENERGY_CHARGED, EV2B_KPI_ENERGY_DISCHARGED,
+    EV2B_KPI_TR_OVERLOAD, EV2B_KPI_EVS_SERVED, EV2B_KPI_SAT_SUM, EV2B_KPI_TRACKING_ERROR,
+    EV2B_KPI_ENERGY_TRACKING_ERROR, EV2B_KPI_TRACKER_VIOLATION, EV2B_KPI_EVS_SPAWNED, EV2B_KPI_INVALID_ACTIONS,
+    EV2B_KPI_STEPS, EV2B_KPI_COUNT
+};
+
+int         ev2b_abi_version(void);
+const char *ev2b_last_error(const ev2b_handle *h);   /* h may be NULL: error of the last failed create */
+
+/* EV2Gym.__init__ (sizes + topology only)            ev2gym_env.py:38-241 */
+int  ev2b_create(const ev2b_dims *dims, const ev2b_topology *topo, int device, ev2b_handle **out);
+void ev2b_destroy(ev2b_handle *h);
+int  ev2b_obs_dim(const ev2b_handle *h);
+int  ev2b_n_ports(const ev2b_handle *h);
+
+/* The scenario part of reset(): load_transformers / load_ev_profiles / load_electricity_prices /
+ * load_power_setpoints outputs (ev2gym_env.py:293-296).  Replaces the whole bank. Synchronous. */
+int  ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *bank);
+int  ev2b_n_scenarios(const ev2b_handle *h);
+
+/* The state part of reset() for envs [env_lo, env_hi): init_statistic_variables + charger /
+ * transformer resets + first observation (ev2gym_env.py:298-331).  scn_ids: HOST array of
+ * env_hi-env_lo bank indices, or NULL for (env index mod bank size).  obs0: DEVICE [E,D] or NULL
+ * (rows env_lo..env_hi are written). */
+int  ev2b_reset(ev2b_handle *h, int env_lo, int env_hi, const int32_t *scn_ids, float *obs0, void *stream);
+
+/* EV2Gym.step for all E envs: one fused kernel launch.   ev2gym_env.py:333-447
+ * actions: DEVICE [E,P] float32 or float64, in [-1,1]; never written. */
+int  ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, void *stream);
+
+/* Same, with HOST buffers (pinned for full speed): H2D(actions) -> kernel -> D2H(reward,status[,obs]),
+ * then waits for completion.  This is the call a host-resident agent makes (end-to-end path). */
+int  ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype,
+                    double *reward_host, uint32_t *status_host, float *obs_host, void *stream);
+
+/* Device-side auto-reset of every env whose episode is over: next scenario id =
+ * (current id + n_envs) mod bank size.  For vectorised RL rollouts. */
+int  ev2b_reset_done(ev2b_handle *h, float *obs0, void *stream);
+
+int  ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *out);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t ev2b_launch_count(const ev2b_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EV2B_H */

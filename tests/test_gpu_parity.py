@@ -1,0 +1,184 @@
+"""GPU parity: the CUDA step engine (through the C ABI, libev2b.so) against
+  (1) traces recorded from the Python reference (tests/golden), and
+  (2) the C oracle on seeded synthetic scenarios at sizes the oracle finishes in seconds.
+
+Bars (written where they are asserted):
+  - battery level / arrival-departure indexing / action mask / done flags: BIT-EXACT
+  - float64 outputs (reward, total_costs, tr_power, tr_overload): 1e-9 relative
+    (the device sums chargers in a fixed tree order, the reference sequentially)
+  - float32 outputs (obs, cs_power, cs_current): 1e-5 relative (north_star tolerance; fp32 storage)
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(topo, scenarios, n_envs, reward, state, outputs):
+    from ev2gym_b200.engine import BatchedEngine
+    eng = BatchedEngine(topo, n_envs, reward=reward, state=state, outputs=outputs)
+    eng.load_scenarios(scenarios)
+    return eng
+
+
+def _close(a, b, rtol, atol=0.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= atol + rtol * np.abs(b))
+
+
+ALL_OUT = ("reward", "status", "obs", "cs_power", "cs_current", "tr_power", "tr_overload", "total_costs",
+           "action_mask", "dep_sat", "port_energy")
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_cuda_matches_reference_trace(name):
+    import torch
+    from ev2gym_b200.scenario import ScenarioPack
+    pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
+    tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+    topo = pack.topo
+    E = 3                                 # 3 replicas of the same episode: exercises multi-env CTAs
+    eng = _engine(topo, pack.scenarios, E, str(tr["reward_fn"]), str(tr["state_fn"]), ALL_OUT)
+    obs0 = eng.reset().cpu().numpy()
+    assert _close(obs0[0], tr["obs0"], 1e-5, 1e-6) and np.array_equal(obs0[0], obs0[2])
+    st = eng.state_tensors()
+    T = tr["reward"].shape[0]
+    for t in range(T):
+        a = torch.tensor(np.tile(tr["actions"][t], (E, 1)), dtype=torch.float64, device="cuda")
+        out = {k: v.cpu().numpy() for k, v in eng.step(a).items()}
+        for e in (0, E - 1):
+            occ = out["action_mask"][e] > 0
+            assert np.array_equal(occ.astype(np.float64), tr["action_mask"][t]), (t, "mask")
+            cap = st["port_cap"][e].cpu().numpy()
+            # battery level: bit exact (fp64, same operation order, no FMA)
+            assert np.array_equal(cap[occ], tr["cap"][t][occ]), (t, "cap", cap[occ], tr["cap"][t][occ])
+            hot = eng.decode_hot(st["port_hot"][e].cpu().numpy())
+            assert np.array_equal(hot["t_arr"][occ], tr["port_t_arr"][t][occ]), (t, "arrival index")
+            assert _close(out["reward"][e], tr["reward"][t], 1e-9, 1e-9), (t, out["reward"][e], tr["reward"][t])
+            assert _close(out["total_costs"][e], tr["total_costs"][t], 1e-9, 1e-12)
+            assert _close(out["tr_power"][e], tr["tr_power"][t], 1e-9, 1e-9)
+            assert _close(out["tr_overload"][e], tr["tr_overload"][t], 1e-9, 1e-9)
+            assert _close(out["cs_power"][e], tr["cs_power"][t], 1e-5, 1e-6)
+            assert _close(out["cs_current"][e], tr["cs_current"][t], 1e-5, 1e-6)
+            assert _close(out["obs"][e], tr["obs"][t], 1e-5, 1e-5), (t, "obs",
+                                                                     np.abs(out["obs"][e] - tr["obs"][t]).max())
+            assert bool(out["status"][e] & 1) == bool(tr["done"][t])
+            assert np.nansum(out["dep_sat"][e]) == pytest.approx(tr["sat_sum"][t], rel=1e-6, abs=1e-6)
+            assert np.count_nonzero(~np.isnan(out["dep_sat"][e])) == tr["n_departed"][t]
+    k = eng.kpis()
+    assert k["total_reward"][0] == pytest.approx(float(tr["total_reward"]), rel=1e-9, abs=1e-9)
+    assert k["total_ev_served"][0] == float(tr["stat_total_ev_served"])
+    assert k["total_profits"][0] == pytest.approx(float(tr["stat_total_profits"]), rel=1e-9, abs=1e-9)
+    assert k["total_energy_charged"][0] == pytest.approx(float(tr["stat_total_energy_charged"]), rel=1e-9)
+    assert k["total_transformer_overload"][0] == pytest.approx(float(tr["stat_total_transformer_overload"]),
+                                                               rel=1e-9, abs=1e-9)
+    assert k["tracking_error"][0] == pytest.approx(float(tr["stat_tracking_error"]), rel=1e-9, abs=1e-9)
+    # stepping a finished env is a no-op flagged WAS_DONE (reference: AssertionError, ev2gym_env.py:343)
+    out = eng.step(a)
+    assert int(out["status"][0].item()) & 4 and float(out["reward"][0].item()) == 0.0
+
+
+SHAPES = [  # C, n_ports, Tr, E, reward, state, action dtype
+    (25, 1, 1, 37, "SquaredTrackingErrorReward", "PublicPST", "float32"),
+    (100, 2, 5, 9, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", "float32"),
+    (250, 1, 1, 4, "profit_maximization", "V2G_profit_max", "float64"),
+    (7, 3, 2, 50, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", "float64"),
+    (300, 1, 20, 3, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", "float32"),
+]
+
+
+@pytest.mark.parametrize("C,n,Tr,E,reward,state,adt", SHAPES)
+def test_cuda_matches_oracle_on_synthetic(C, n, Tr, E, reward, state, adt):
+    import torch
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    from oracle.oracle import OracleBatch
+    topo = Topology.uniform(C=C, n_ports=n, Tr=Tr, T=64, imin=6.0 if n == 3 else 0.0)
+    bank = sample_bank(topo, 5, seed=C + n, min_stay=5)
+    scn_ids = [(3 * e + 1) % 5 for e in range(E)]
+    eng = _engine(topo, bank, E, reward, state, ALL_OUT)
+    obs0 = eng.reset(scn_ids=scn_ids).cpu().numpy()
+    orc = OracleBatch(topo, [bank[i] for i in scn_ids], reward=reward, state=state)
+    assert _close(obs0, orc.reset(), 1e-5, 1e-5)
+    st = eng.state_tensors()
+    rng = np.random.default_rng(99)
+    for t in range(topo.T):
+        a = rng.uniform(-1, 1, (E, topo.P))
+        a[rng.random((E, topo.P)) < 0.1] = 0.0
+        a = a.astype(adt)
+        out = {k: v.cpu().numpy() for k, v in eng.step(torch.tensor(a, device="cuda")).items()}
+        orc.step(a.astype(np.float64))
+        occ = orc.arr["port_session"] >= 0
+        assert np.array_equal(out["action_mask"] > 0, occ), t
+        cap = st["port_cap"].cpu().numpy()
+        assert np.array_equal(cap[occ], orc.arr["port_cap"][occ]), (t, "cap")            # bit exact
+        assert _close(out["reward"], orc.reward, 1e-9, 1e-9), t
+        assert _close(out["tr_power"], orc.o["tr_power"][:, :Tr], 1e-9, 1e-9), t
+        assert _close(out["tr_overload"], orc.o["tr_overload"][:, :Tr], 1e-9, 1e-9), t
+        assert _close(out["cs_power"], orc.o["cs_power"], 1e-5, 1e-6), t
+        assert _close(out["obs"], orc.o["obs"][:, :eng.D], 1e-5, 1e-5), t
+        assert np.array_equal((out["status"] & 1) > 0, orc.done > 0), t
+        ovf = np.array([o.error == 1 for o in orc.outs])
+        assert np.array_equal((out["status"] & 2) > 0, ovf), (t, "amps overflow flag")
+    assert _close(eng.kpis()["total_reward"], [s.total_reward for s in orc.states], 1e-9, 1e-9)
+
+
+def test_ragged_ports_and_reset_done():
+    """Chargers with different port counts / currents (topology-file style) + device-side auto reset."""
+    import torch
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    from oracle.oracle import OracleBatch
+    topo = Topology(cs_n_ports=[2, 1, 3, 2, 1, 4], cs_tr=[0, 0, 1, 1, 2, 2], cs_imax=[56, 32, 56, 16, 32, 56],
+                    cs_imin=[8, 0, 8, 0, 6, 8], cs_imax_dis=[0, -32, -56, 0, -32, -56], cs_imin_dis=[0] * 6,
+                    cs_voltage=[230, 400, 230, 400, 400, 230], cs_phases=[3, 3, 1, 3, 3, 2], n_transformers=3,
+                    tr_voltage=400 * 3 ** 0.5, timescale=15, sim_length=40, dr_steps_ahead=4)
+    bank = sample_bank(topo, 6, seed=5, min_stay=4)
+    E = 11
+    eng = _engine(topo, bank, E, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", ALL_OUT)
+    eng.reset()
+    ids = [e % 6 for e in range(E)]
+    orc = OracleBatch(topo, [bank[i] for i in ids], reward="ProfitMax_TrPenalty_UserIncentives",
+                      state="V2G_profit_max_loads")
+    orc.reset()
+    rng = np.random.default_rng(3)
+    st = eng.state_tensors()
+    for ep in range(2):
+        for t in range(topo.T):
+            a = rng.uniform(-0.4, 1, (E, topo.P))
+            out = {k: v.cpu().numpy() for k, v in eng.step(torch.tensor(a, device="cuda")).items()}
+            orc.step(a)
+            occ = orc.arr["port_session"] >= 0
+            assert np.array_equal(st["port_cap"].cpu().numpy()[occ], orc.arr["port_cap"][occ])
+            assert _close(out["reward"], orc.reward, 1e-9, 1e-9)
+            assert _close(out["obs"], orc.o["obs"][:, :eng.D], 1e-5, 1e-5)
+        assert np.all(out["status"] & 1)
+        obs = eng.reset_done().cpu().numpy()           # scenario id advances by E modulo the bank size
+        ids = [(i + E) % 6 for i in ids]
+        assert np.array_equal(st["env_scn"].cpu().numpy(), ids)
+        orc = OracleBatch(topo, [bank[i] for i in ids], reward="ProfitMax_TrPenalty_UserIncentives",
+                          state="V2G_profit_max_loads")
+        assert _close(obs, orc.reset(), 1e-5, 1e-5)
+
+
+def test_step_host_matches_device_path():
+    import torch
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    topo = Topology.uniform(C=20, n_ports=2, Tr=2, T=30)
+    bank = sample_bank(topo, 3, seed=8, min_stay=4)
+    E = 16
+    e1 = _engine(topo, bank, E, "profit_maximization", "V2G_profit_max", ("reward", "status", "obs"))
+    e2 = _engine(topo, bank, E, "profit_maximization", "V2G_profit_max", ("reward", "status", "obs"))
+    e1.reset(); e2.reset()
+    rng = np.random.default_rng(1)
+    rew, stt, obs = np.zeros(E), np.zeros(E, dtype=np.uint32), np.zeros((E, e1.D), dtype=np.float32)
+    for t in range(topo.T):
+        a = rng.uniform(-1, 1, (E, topo.P)).astype(np.float32)
+        o1 = e1.step(torch.tensor(a, device="cuda"))
+        e2.step_host(a, rew, stt, obs)
+        assert np.array_equal(o1["reward"].cpu().numpy(), rew)
+        assert np.array_equal(o1["obs"].cpu().numpy(), obs)
+        assert np.array_equal(o1["status"].cpu().numpy().astype(np.uint32), stt)
