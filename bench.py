@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched EV2Gym step engine on B200 (contract: see the task brief).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl reference]
+
+One "step" = one fused-kernel pass advancing one batch of E env replicas by one timestep
+(E x chargers named in config.workload).  Scenarios are banks exported from the reference's own
+reset() (ev2gym_b200/data/*.npz, tools/make_golden.py --packs), tiled over the envs (env e uses
+scenario e mod bank); actions are synthetic uniform fp32 in the action space, resident in HBM.
+
+L2 hygiene: the per-batch state (~25-40 MB) would sit in the 126 MB L2, so the timed loop ROTATES
+over G independent env groups whose total footprint is > 2x L2; every launch finds its data in HBM.
+
+Printed: ONE JSON line (rank 0).  `value` = device-timed whole-job env-steps/s (CUDA events, max over
+ranks); `e2e` = the same through ev2b_step_host with pinned HOST buffers (H2D actions, D2H
+reward+status+obs inside the timed region); `roofline` = algorithmic bytes / measured launch time
+against MEASURED_PEAKS.json; `cpu_baseline` = the C oracle on the host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (pack, E, reward, state, human description)
+    "c2": ("c2_publicpst_c25", 1024, "SquaredTrackingErrorReward", "PublicPST",
+           "PublicPST.yaml, 1024 envs x 25 chargers x 1 port, 1 transformer, uniform actions"),
+    "c3": ("c3_v2gloads_c100n2tr5", 4096, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads",
+           "V2GProfitPlusLoads.yaml, 4096 envs x 100 chargers x 2 ports, 5 transformers, uniform actions"),
+    "c3-1k": ("c3_v2gloads_c100n2tr5", 1024, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads",
+              "V2GProfitPlusLoads.yaml, 1024 envs x 100 chargers x 2 ports, 5 transformers, uniform actions"),
+    "c4": ("c4_v2gprofitmax_c250", 8192, "profit_maximization", "V2G_profit_max",
+           "V2GProfitMax.yaml, 8192 envs x 250 chargers x 1 port, 1 transformer, uniform actions"),
+}
+L2_BYTES = 126e6
+
+
+def load_pack(name):
+    from ev2gym_b200.scenario import ScenarioPack
+    return ScenarioPack.load(os.path.join(ROOT, "ev2gym_b200", "data", name + ".npz"))
+
+
+def algorithmic_bytes_per_env_step(topo, obs_dim):
+    """B_step = 40 P + 8 C + 20 Tr + 16 (+ 4 D with observations)."""
+    return 40 * topo.P + 8 * topo.C + 20 * topo.Tr + 16 + 4 * obs_dim
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(topo, scenarios, reward, state, target_seconds=12.0, threads=0):
+    """The C oracle (a port of the reference step; the reference itself is Python and cannot travel)."""
+    from oracle.oracle import OracleBatch
+    E = 512
+    ob = OracleBatch(topo, [scenarios[e % len(scenarios)] for e in range(E)], reward=reward, state=state,
+                     threads=threads)
+    rng = np.random.default_rng(0)
+    low = -1.0 if topo.v2g_enabled else 0.0
+    acts = [rng.uniform(low, 1.0, (E, topo.P)) for _ in range(4)]
+    ob.reset()
+    for t in range(3):
+        ob.step(acts[t % 4])
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        if ob.states[0].current_step >= topo.T:
+            ob.reset()
+        ob.step(acts[steps % 4])
+        steps += 1
+        if steps % 8 == 0 and time.perf_counter() - t0 > target_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": E * steps / dt, "unit": "env-steps/s", "cores": ob.threads, "kind": "port",
+            "sample": f"C oracle (oracle/ev2o.c, fp64, pthreads), {E} envs x {steps} steps incl. state+reward, "
+                      f"{dt:.1f} s; the Python reference itself measured 330 env-steps/s/core on this shape "
+                      f"(BASELINE.md) and cannot run on the GPU box"}
+
+
+def run_reference(args, wl):
+    """`--impl reference`: the reference's CPU implementation of the path = the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pack_name, E, reward, state, desc = WORKLOADS[wl]
+    pack = load_pack(pack_name)
+    topo = pack.topo
+    from oracle.oracle import OracleBatch
+    Es = 512                                           # bounded sample of the workload's batch per step
+    ob = OracleBatch(topo, [pack.scenarios[e % len(pack)] for e in range(Es)], reward=reward, state=state)
+    rng = np.random.default_rng(0)
+    low = -1.0 if topo.v2g_enabled else 0.0
+    acts = [rng.uniform(low, 1.0, (Es, topo.P)) for _ in range(4)]
+    ob.reset()
+    for w in range(args.warmup):
+        ob.step(acts[w % 4])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        if ob.states[0].current_step >= topo.T:
+            ob.reset()
+        ob.step(acts[k % 4])
+    dt = time.perf_counter() - t0
+    v = Es * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic actions on reference-exported scenarios",
+        "config": {"workload": desc, "sample": f"{Es} of {E} envs per step"},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": ob.threads, "kind": "port",
+                         "sample": f"C oracle, {Es} envs x {args.steps} steps"},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=448)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-obs", action="store_true", help="do not produce observations (heuristic-driven runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args, args.workload)
+
+    import torch
+    import torch.distributed as dist
+    from ev2gym_b200.engine import BatchedEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    pack_name, E, reward, state, desc = WORKLOADS[args.workload]
+    pack = load_pack(pack_name)
+    topo = pack.topo
+    outputs = ("reward", "status") if args.no_obs else ("reward", "status", "obs")
+    probe = BatchedEngine(topo, 1, reward=reward, state=state, device=local, outputs=outputs)
+    D = 0 if args.no_obs else probe.D
+    probe.close()
+    bytes_env_step = algorithmic_bytes_per_env_step(topo, D)
+    state_bytes = E * (28 * topo.P + 4 * topo.P + 4 * D + 150)       # hot+cap+exch, actions, obs, per-env
+    G = max(2, int(np.ceil(2.2 * L2_BYTES / state_bytes)))
+
+    engines = []
+    for g in range(G):
+        eng = BatchedEngine(topo, E, reward=reward, state=state, device=local, outputs=outputs)
+        eng.load_scenarios(pack.scenarios)
+        eng.reset(scn_ids=[(rank * E * G + g * E + e) % len(pack) for e in range(E)])
+        engines.append(eng)
+    low = -1.0 if topo.v2g_enabled else 0.0
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = [torch.rand((E, topo.P), device=dev, generator=gen) * (1.0 - low) + low for _ in range(G)]
+    T = topo.T
+
+    # every group advances one step per "round"; all envs of a group finish together every T rounds
+    def round_(r):
+        for g in range(G):
+            engines[g].step(actions[(g + r) % G])
+
+    def reset_all():
+        for g in range(G):
+            engines[g].reset()
+
+    R = 4                                                            # rounds per graph replay (T % R == 0)
+    rounds_done = 0
+    n_warm_rounds = max(R, (args.warmup + G - 1) // G // R * R)
+    for r in range(n_warm_rounds):
+        round_(rounds_done); rounds_done += 1
+    torch.cuda.synchronize(dev)
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):                                # capture only: nothing executes here
+            for r in range(R):
+                round_(r)
+    torch.cuda.synchronize(dev)
+
+    n_replays = max(1, args.steps // (G * R))
+    K = n_replays * G * R                                            # exactly K timed steps
+    launches0 = sum(e.launch_count for e in engines)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    resets = 0
+    ev0.record()
+    for it in range(n_replays):
+        if rounds_done % T == 0:
+            reset_all(); resets += 1                                 # a new episode for every env (inside the timed region)
+        if graph is not None:
+            graph.replay()
+        else:
+            for r in range(R):
+                round_(rounds_done + r)
+        rounds_done += R
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    gpu_launches = K + resets * 2 * G
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * E * K / (elapsed_ms * 1e-3)
+
+    # aggregate KPIs: the path's only collective: one small all-reduce(sum)
+    kpi = sum(e.state_tensors()["env_kpi"].sum(dim=0) for e in engines)
+    if world > 1:
+        dist.all_reduce(kpi, op=dist.ReduceOp.SUM)
+
+    # ---- end to end through the host-buffer API --------------------------------------------------
+    eng = engines[0]
+    eng.reset()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    h_act = [pin((E, topo.P), torch.float32) for _ in range(2)]
+    for a in h_act:
+        a[:] = np.random.default_rng(5).uniform(low, 1.0, a.shape)
+    h_rew, h_st = pin((E,), torch.float64), pin((E,), torch.int32).view(np.uint32)
+    h_obs = pin((E, D), torch.float32) if D else None
+    n_e2e = min(T - 4, max(8, args.steps // 8))
+    for w in range(3):
+        eng.step_host(h_act[w % 2], h_rew, h_st, h_obs)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        eng.step_host(h_act[k % 2], h_rew, h_st, h_obs)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * n_e2e / float(te.item())
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        launch_ms = elapsed_ms / K
+        achieved = bytes_env_step * E / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": n_warm_rounds * G, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (uniform fp32 actions on scenario banks exported "
+                                                         "from the reference's reset())",
+            "config": {"workload": desc, "envs_per_gpu": E, "chargers": topo.C, "ports": topo.P,
+                       "transformers": topo.Tr, "obs_dim": D, "reward": reward, "state": state,
+                       "l2": f"rotating {G} independent env groups, {G * state_bytes / 1e6:.0f} MB total > 126 MB L2",
+                       "cuda_graph": graph is not None, "parallelism": f"env-sharded x{world}"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": E * topo.P * 4,
+                    "d2h_bytes_per_step": E * (8 + 4 + 4 * D), "steps": n_e2e,
+                    "what": "ev2b_step_host: pinned host actions -> H2D -> fused kernel -> D2H reward+status+obs -> sync"},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": bytes_env_step,
+                         "kernel": "ev2b::step_kernel", "launch_ms": launch_ms},
+            "kpi_allreduce": {"total_reward": float(kpi[0].item()), "total_evs_served": float(kpi[5].item())},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(topo, pack.scenarios, reward, state if D else None)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,7 @@ struct DevBuf {
 struct ev2b_handle {
     ev2b_dims dims{};
     int device = 0;
-    int C = 0, P = 0, Tr = 0, T = 0, E = 0, D = 0, EPB = 1, block = 32, n_cls = 1, np_uniform = 0;
+    int C = 0, P = 0, Tr = 0, T = 0, E = 0, D = 0, EPB = 1, block = 32, n_cls = 1, np_uniform = 0, cs_uniform = 0;
     size_t smem = 0;
     std::string err;
     int64_t launches = 0;
@@ -80,6 +80,8 @@ struct ev2b_handle {
         p.reward_kind = dims.reward_kind; p.state_kind = dims.state_kind; p.dr_steps_ahead = dims.dr_steps_ahead;
         p.c60 = 60.0 / (double)dims.timescale; p.p60 = (double)dims.timescale / 60.0; p.period = (double)dims.timescale;
         p.tr_voltage = dims.tr_voltage;
+        p.c_magic = C > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)C) + 1u : 0u;
+        p.cs_uniform = cs_uniform; p.cs0 = cs_h.empty() ? CsStatic{} : cs_h[0];
         p.cs = cs.p; p.tr_cs_off = tr_cs_off.p; p.tr_cs_idx = tr_cs_idx.p; p.obs_slot = obs_slot.p; p.tr_obs_off = tr_obs_off.p;
         p.env_t = env_t.p; p.tr_t = tr_t.p; p.sess = sess.p; p.spec = spec.p; p.luts_c = luts_c.p; p.luts_d = luts_d.p;
         p.pot_kw = pot_kw.p; p.trA = trA.p; p.trF = trF.p; p.tr_limit = tr_limit.p; p.dr = dr.p; p.dr_count = dr_count.p;
@@ -116,13 +118,13 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
         return cudaGetLastError();
     };
     if (h->block <= 256) {
-        if (h->np_uniform == 1) return go(step_kernel<ActT, 1, 256>);
-        if (h->np_uniform == 2) return go(step_kernel<ActT, 2, 256>);
-        return go(step_kernel<ActT, 0, 256>);
+        if (h->np_uniform == 1) return go(step_kernel<ActT, 1, 256, 4>);
+        if (h->np_uniform == 2) return go(step_kernel<ActT, 2, 256, 4>);
+        return go(step_kernel<ActT, 0, 256, 4>);
     }
-    if (h->np_uniform == 1) return go(step_kernel<ActT, 1, kMaxThreads>);
-    if (h->np_uniform == 2) return go(step_kernel<ActT, 2, kMaxThreads>);
-    return go(step_kernel<ActT, 0, kMaxThreads>);
+    if (h->np_uniform == 1) return go(step_kernel<ActT, 1, kMaxThreads, 1>);
+    if (h->np_uniform == 2) return go(step_kernel<ActT, 2, kMaxThreads, 1>);
+    return go(step_kernel<ActT, 0, kMaxThreads, 1>);
 }
 
 extern "C" {
@@ -186,6 +188,11 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     h->P = off;
     h->n_cls = (int)cls_of.size();
     h->np_uniform = uniform_ports ? h->cs_h[0].n_ports : 0;
+    h->cs_uniform = (uniform_ports && h->n_cls == 1) ? 1 : 0;
+    for (int c = 1; c < C && h->cs_uniform; ++c) {
+        const CsStatic &a0 = h->cs_h[0], &b0 = h->cs_h[c];
+        if (a0.imin != b0.imin || a0.imax_dis_abs != b0.imax_dis_abs || a0.imin_dis != b0.imin_dis) h->cs_uniform = 0;
+    }
     h->D = obs_dim_for(d->state_kind, h->P, h->Tr);
     // transformer -> chargers CSR (id order)
     std::vector<int> tr_off(h->Tr + 1, 0), tr_idx(C);

@@ -65,6 +65,9 @@ struct Params {
     double p60;        // timescale / 60          ev.py:355
     double period;     // timescale
     double tr_voltage;
+    unsigned c_magic;  // ceil(2^32 / C): tid / C == __umulhi(tid, c_magic)
+    int cs_uniform;    // all chargers identical: read the layout from cs0 (constant bank) instead of global memory
+    CsStatic cs0;
     // static
     const CsStatic *cs; const int *tr_cs_off; const int *tr_cs_idx; const int *obs_slot; const int *tr_obs_off;
     // scenario bank
@@ -193,9 +196,164 @@ __device__ __forceinline__ float obs_series_value(const Params &p, int s, int tq
 }
 
 // ---- the fused step kernel --------------------------------------------------------------------
+__device__ __forceinline__ const CsStatic &cs_of(const Params &p, int c) { return p.cs_uniform ? p.cs0 : p.cs[c]; }
+
+// One port of one charger: EV.step + departure + arrival + potential + obs tuple.
+// Accumulates into the charger's partial sums (acc) in the reference's port order.
+struct ChargerAcc { double P, A, profit, satexp, pot, ch, dis, sat; int cnt; bool overflow; };
+
+template <typename ActT>
+__device__ __forceinline__ void process_port(const Params &p, const CsStatic &cs, const int t, const int s,
+                                             const size_t ip, const int port, uint4 h, double a, const double sum,
+                                             const double cp, const double dp, ChargerAcc &acc, float *obs_row,
+                                             const bool want_obs) {
+    const int tq = t + 1;
+    bool occ = hot_t_arr(h) <= t && t <= hot_t_dep(h);
+    if (!occ) a = 0.0;
+    if (sum > 1.0) a = a / sum; else if (sum < -1.0) a = -a / sum;                    // ev_charger.py:143-149
+    const double action = (a == 0.0) ? 0.0 : rint(a * 100000.0) / 100000.0;           // round(action, 5)  :157
+    const EvSpec *sp = p.spec + hot_spec(h);
+    double capv = 0.0, energy = 0.0;
+    float exch_new = 0.f;
+    bool exch_valid = false;
+    if (occ) capv = p.cap[ip];
+    if (occ && action != 0.0) {
+        double amps, act_amps = 0.0;
+        const double veff_cs = cs.veff[cs.phases];
+        if (action > 0.0) {                                                            // :167-170
+            amps = action * cs.imax;
+            if (amps < cs.imin - 0.01) amps = 0.0;
+            const double pmin = __ldg(&sp->pmin_ac);
+            if (amps > 0.0 && pmin != 0.0 && amps < pmin * 1000.0 / veff_cs) amps = 0.0;   // ev.py:151-152
+        } else {                                                                       // :183-186
+            amps = action * cs.imax_dis_abs;
+            if (amps > cs.imin_dis - 0.01) amps = cs.imin_dis;
+            const double pmin = __ldg(&sp->pmin_dis);
+            if (amps > 0.0) {                                                          // only if imin_dis > 0
+                const double pm = __ldg(&sp->pmin_ac);
+                if (amps < pm * 1000.0 / veff_cs) amps = 0.0;
+            } else if (amps < 0.0 && pmin != 0.0 && amps > pmin * 1000.0 / veff_cs) amps = 0.0;  // ev.py:153-154
+        }
+        if (amps != 0.0) {
+            const int evph = __ldg(&sp->ev_phases);
+            const double veff = cs.veff[cs.phases < evph ? cs.phases : evph];            // ev.py:169
+            const int lut = __ldg(&sp->lut);
+            const double B = __ldg(&sp->B);
+            if (amps > 0.0) {                                                          // EV._charge  ev.py:240-355
+                double eta;
+                const unsigned tsm = h.z >> 16, ecm = h.w & 0xFFFFu;
+                if (lut >= 0) eta = lut_get(p.luts_c + (size_t)lut * p.lut_len, p.lut_len, rint(amps)) / 100.0;
+                else eta = (ecm == 0xFFFFu) ? __ldg(&sp->eta_c) : (double)ecm / 1000.0;
+                const double ts = (tsm == 0xFFFFu) ? __ldg(&sp->ts) : (double)tsm / 1000.0;
+                const double pmax = __ldg(&sp->pmax_ac);
+                double pilot = eta * amps * veff / 1000.0 / B / p.c60;                 // :295-296
+                const double maxd = eta * pmax / B / p.c60;                            // :297-298
+                if (pilot > maxd) pilot = maxd;                                        // :300-301
+                const double soc = capv / B;
+                double curr;
+                if (ts == 1.0) {                                                       // :303-306
+                    curr = pilot + soc;
+                    if (curr > 1.0) curr = 1.0;
+                } else {
+                    const double pts = ts + (pilot - maxd) / maxd * (ts - 1.0);        // :312-314
+                    double nsoc;
+                    if (soc < pts) {
+                        if (1.0 <= (pts - soc) / pilot) nsoc = pilot + soc;            // :323-324
+                        else nsoc = 1.0 + exp(__ldg(&sp->mult) * (pilot + soc - pts) / (pts - 1.0)) * (pts - 1.0);
+                    } else {
+                        nsoc = 1.0 + exp(__ldg(&sp->mult) * pilot / (pts - 1.0)) * (soc - 1.0);   // :332-334
+                    }
+                    const double lim = (maxd > pilot) ? pilot : maxd;                  // :336-339
+                    curr = (nsoc - soc > lim) ? lim + soc : nsoc;                      // :341-344
+                }
+                capv = curr * B;                                                       // :348
+                energy = (curr - soc) * B;                                             // :346,352
+                act_amps = energy / p.p60 * 1000.0 / veff;                             // :355
+            } else {                                                                   // EV._discharge  ev.py:357-405
+                double eta;
+                const unsigned edm = h.w >> 16;
+                if (lut >= 0) eta = lut_get(p.luts_d + (size_t)lut * p.lut_len, p.lut_len, fabs(rint(amps))) / 100.0;
+                else eta = (edm == 0xFFFFu) ? __ldg(&sp->eta_d) : (double)edm / 1000.0;
+                const double pmd = __ldg(&sp->pmax_dis), bmin = __ldg(&sp->bmin);
+                double given_power = amps * veff / 1000.0;                             // :367
+                if (fabs(given_power) > fabs(pmd)) given_power = pmd;                  // :370-371
+                double given_energy = given_power * eta * p.period / 60.0;             // :381
+                if (capv + given_energy < bmin) {                                      // :382-393
+                    if (capv > bmin) { energy = -(capv - bmin); given_energy = energy; }
+                    else { energy = 0.0; given_energy = 0.0; }
+                    capv = bmin;
+                } else {
+                    energy = given_energy;
+                    capv += given_energy;
+                }
+                act_amps = given_energy * 60.0 / p.period * 1000.0 / veff;             // :405
+            }
+            capv = ceil(capv * 100.0) / 100.0;                                         // my_ceil  ev.py:183
+            p.cap[ip] = capv;
+            exch_new = p.exch[ip] + (float)energy;                                     // total_energy_exchanged ev.py:178
+            exch_valid = true;
+            p.exch[ip] = exch_new;
+        }
+        const double ae = fabs(energy);
+        if (action > 0.0) { acc.profit += ae * cp; acc.ch += ae; }                     // :178-179
+        else              { acc.profit += ae * dp; acc.dis += ae; }                    // :194-195
+        acc.P += energy * 60.0 / p.period;                                             // :180,196
+        acc.A += act_amps;                                                             // :181,197
+    }
+    if (acc.A - 0.0001 > cs.imax) acc.overflow = true;                                 // :203-205
+    if (p.out.port_energy) p.out.port_energy[ip] = (float)energy;
+
+    // departure (charger step counter == t)        ev_charger.py:209-224, ev.py:199-214
+    float dsat = __int_as_float(0x7fc00000);
+    if (occ && t >= hot_t_dep(h)) {
+        const double des = __ldg(&sp->desired);
+        const double sat = (capv < des - 0.001) ? capv / des : 1.0;
+        acc.satexp += 100.0 * exp(-10.0 * sat);                                        // reward.py:42,85
+        acc.sat += sat;
+        acc.cnt += 1 << 10;
+        dsat = (float)sat;
+    }
+    if (p.out.dep_sat) p.out.dep_sat[ip] = dsat;
+
+    // arrival of the next session at t+1            ev2gym_env.py:399-417, ev_charger.py:266-285
+    if (hot_next_arr(h) == tq) {
+        const SessRec r = p.sess[((size_t)s * p.P + port) * p.Smax + hot_cursor(h)];
+        h = r.hot;
+        capv = r.cap0;
+        p.hot[ip] = h;
+        p.cap[ip] = capv;
+        p.exch[ip] = 0.f;
+        exch_new = 0.f; exch_valid = true;
+        sp = p.spec + hot_spec(h);
+        acc.cnt += 1 << 20;
+    }
+    const bool occ_after = hot_t_arr(h) <= tq && tq <= hot_t_dep(h);
+    if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;                 // ev2gym_env.py:452-457
+    if (occ_after) {
+        const double B = __ldg(&sp->B);
+        // charge power potential for step t+1            utils.py:766-777
+        if (capv < B && hot_t_dep(h) > tq) acc.pot += __ldg(&p.pot_kw[hot_spec(h) * p.n_cls + cs.cls]);
+        if (want_obs) {       // observation tuple (transformer-major slot)   state.py:37-57, 85-102, 137-151
+            float *o = obs_row + p.obs_slot[port];
+            if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
+                o[0] = (capv == B) ? 1.f : 0.5f;
+                o[1] = exch_valid ? exch_new : p.exch[ip];
+                o[2] = (float)(tq - hot_t_arr(h));
+            } else {
+                o[0] = (float)(capv / B);
+                o[1] = (float)(hot_t_dep(h) - tq);
+            }
+        }
+    } else if (want_obs) {
+        float *o = obs_row + p.obs_slot[port];
+        o[0] = 0.f; o[1] = 0.f;
+        if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
+    }
+}
+
 // ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = read from CsStatic.
-template <typename ActT, int NP, int MAXT>
-__global__ void __launch_bounds__(MAXT) step_kernel(const Params p) {
+template <typename ActT, int NP, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
     double *red   = reinterpret_cast<double *>(smem_raw);                 // [kNRed][NT]
@@ -206,14 +364,16 @@ __global__ void __launch_bounds__(MAXT) step_kernel(const Params p) {
     float  *obs_s = reinterpret_cast<float *>(envi + (size_t)p.EPB * 4);  // [EPB][D]
 
     const int tid = threadIdx.x;
-    const int el = tid / p.C, c = tid - el * p.C;
+    const int el = p.C == 1 ? tid : (int)__umulhi((unsigned)tid, p.c_magic);   // tid / C
+    const int c = tid - el * p.C;
     const int e = blockIdx.x * p.EPB + el;
     const bool valid = (el < p.EPB) && (e < p.E);
     const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
 
-    double rP = 0, rA = 0, rProfit = 0, rSatExp = 0, rPot = 0, rCh = 0, rDis = 0, rSat = 0;
-    int rCnt = 0;
+    ChargerAcc acc;
+    acc.P = acc.A = acc.profit = acc.satexp = acc.pot = acc.ch = acc.dis = acc.sat = 0.0;
+    acc.cnt = 0; acc.overflow = false;
     int t = 0, s = 0;
     bool live = false;
     if (valid) {
@@ -224,133 +384,53 @@ __global__ void __launch_bounds__(MAXT) step_kernel(const Params p) {
     }
 
     if (valid && live) {
-        const CsStatic cs = p.cs[c];
-        const EnvT et = p.env_t[(size_t)s * p.T + t];
+        const CsStatic &cs = cs_of(p, c);
+        const int port0 = p.cs_uniform ? c * (NP > 0 ? NP : p.cs0.n_ports) : cs.port_off;
         const int n = NP > 0 ? NP : cs.n_ports;
-        const size_t pbase = (size_t)e * p.P + cs.port_off;
-        const int tq = t + 1;
-        bool overflow = false;
-
-        // pass 1: empty-port zeroing + python sum()      ev_charger.py:137-149
-        double sum = 0.0;
-        int invalid = 0;
-        for (int j = 0; j < n; ++j) {
-            const uint4 h = p.hot[pbase + j];
-            const bool occ = hot_t_arr(h) <= t && t <= hot_t_dep(h);
-            double a = occ ? (double)actions[pbase + j] : 0.0;
-            invalid += occ ? 0 : 1;
-            sum = sum + a;
-        }
-        // pass 2: per port                                 ev_charger.py:155-231
-        for (int j = 0; j < n; ++j) {
-            const size_t ip = pbase + j;
-            uint4 h = p.hot[ip];
-            bool occ = hot_t_arr(h) <= t && t <= hot_t_dep(h);
-            double a = occ ? (double)actions[ip] : 0.0;
-            if (sum > 1.0) a = a / sum; else if (sum < -1.0) a = -a / sum;
-            const double action = (a == 0.0) ? 0.0 : rint(a * 100000.0) / 100000.0;   // round(action, 5)  :157
-            double capv = 0.0, energy = 0.0, act_amps = 0.0;
-            EvSpec sp;
-            if (occ) { capv = p.cap[ip]; sp = p.spec[hot_spec(h)]; }
-            if (occ && action != 0.0) {
-                double amps;
-                const double veff_cs = cs.veff[cs.phases];
-                if (action > 0.0) {                                                    // :167-170
-                    amps = action * cs.imax;
-                    if (amps < cs.imin - 0.01) amps = 0.0;
-                } else {                                                               // :183-186
-                    amps = action * cs.imax_dis_abs;
-                    if (amps > cs.imin_dis - 0.01) amps = cs.imin_dis;
-                }
-                if (amps > 0.0 && amps < sp.pmin_ac * 1000.0 / veff_cs) amps = 0.0;       // ev.py:151-152
-                else if (amps < 0.0 && amps > sp.pmin_dis * 1000.0 / veff_cs) amps = 0.0; // ev.py:153-154
-                if (amps != 0.0) {
-                    const int ph = cs.phases < sp.ev_phases ? cs.phases : sp.ev_phases;   // ev.py:169
-                    const double veff = cs.veff[ph];
-                    const unsigned tsm = h.z >> 16, ecm = h.w & 0xFFFFu, edm = h.w >> 16;
-                    if (amps > 0.0) {
-                        double eta;
-                        if (sp.lut >= 0) eta = lut_get(p.luts_c + (size_t)sp.lut * p.lut_len, p.lut_len, rint(amps)) / 100.0;
-                        else eta = (ecm == 0xFFFFu) ? sp.eta_c : (double)ecm / 1000.0;
-                        const double ts = (tsm == 0xFFFFu) ? sp.ts : (double)tsm / 1000.0;
-                        act_amps = ev_charge(sp, ts, eta, capv, amps, veff, p, energy);
-                    } else {
-                        double eta;
-                        if (sp.lut >= 0) eta = lut_get(p.luts_d + (size_t)sp.lut * p.lut_len, p.lut_len, fabs(rint(amps))) / 100.0;
-                        else eta = (edm == 0xFFFFu) ? sp.eta_d : (double)edm / 1000.0;
-                        act_amps = ev_discharge(sp, eta, capv, amps, veff, p, energy);
-                    }
-                    capv = ceil(capv * 100.0) / 100.0;                                 // my_ceil  ev.py:183
-                    p.cap[ip] = capv;
-                    p.exch[ip] = p.exch[ip] + (float)energy;                           // total_energy_exchanged ev.py:178
-                }
-                const double ae = fabs(energy);
-                if (action > 0.0) { rProfit += ae * et.cp; rCh += ae; }                // :178-179
-                else              { rProfit += ae * et.dp; rDis += ae; }               // :194-195
-                rP += energy * 60.0 / p.period;                                        // :180,196
-                rA += act_amps;                                                        // :181,197
+        const size_t pbase = (size_t)e * p.P + port0;
+        float *obs_row = obs_s + (size_t)el * p.D;
+        if (NP > 0) {
+            // issue every independent load of this charger up front
+            uint4 h[NP > 0 ? NP : 1];
+            double a[NP > 0 ? NP : 1];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { h[j] = p.hot[pbase + j]; a[j] = (double)actions[pbase + j]; }
+            const EnvT et = p.env_t[(size_t)s * p.T + t];
+            double sum = 0.0;                                       // python sum(): left to right  ev_charger.py:143
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const bool occ = hot_t_arr(h[j]) <= t && t <= hot_t_dep(h[j]);
+                acc.cnt += occ ? 0 : 1;                             // invalid_action_punishment  :137-140
+                sum = sum + (occ ? a[j] : 0.0);
             }
-            if (rA - 0.0001 > cs.imax) overflow = true;                                // :203-205
-            if (p.out.port_energy) p.out.port_energy[ip] = (float)energy;
-
-            // departure (charger step counter == t)        ev_charger.py:209-224, ev.py:199-214
-            float dsat = __int_as_float(0x7fc00000);
-            if (occ && t >= hot_t_dep(h)) {
-                const double sat = (capv < sp.desired - 0.001) ? capv / sp.desired : 1.0;
-                rSatExp += 100.0 * exp(-10.0 * sat);                                   // reward.py:42,85
-                rSat += sat;
-                rCnt += 1 << 10;
-                dsat = (float)sat;
-                occ = false;
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+                process_port<ActT>(p, cs, t, s, pbase + j, port0 + j, h[j], a[j], sum, et.cp, et.dp, acc, obs_row, want_obs);
+        } else {
+            const EnvT et = p.env_t[(size_t)s * p.T + t];
+            double sum = 0.0;
+            for (int j = 0; j < n; ++j) {
+                const uint4 h = p.hot[pbase + j];
+                const bool occ = hot_t_arr(h) <= t && t <= hot_t_dep(h);
+                acc.cnt += occ ? 0 : 1;
+                sum = sum + (occ ? (double)actions[pbase + j] : 0.0);
             }
-            if (p.out.dep_sat) p.out.dep_sat[ip] = dsat;
-
-            // arrival of the next session at t+1            ev2gym_env.py:399-417, ev_charger.py:266-285
-            if (hot_next_arr(h) == tq) {
-                const SessRec r = p.sess[((size_t)s * p.P + cs.port_off + j) * p.Smax + hot_cursor(h)];
-                h = r.hot;
-                capv = r.cap0;
-                p.hot[ip] = h;
-                p.cap[ip] = capv;
-                p.exch[ip] = 0.f;
-                sp = p.spec[hot_spec(h)];
-                rCnt += 1 << 20;
-            }
-            const bool occ_after = hot_t_arr(h) <= tq && tq <= hot_t_dep(h);
-            if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;         // ev2gym_env.py:452-457
-
-            // charge power potential for step t+1            utils.py:766-777
-            if (occ_after && capv < sp.B && hot_t_dep(h) > tq)
-                rPot += p.pot_kw[hot_spec(h) * p.n_cls + cs.cls];
-
-            // observation tuple of this port (transformer-major slot)   state.py:37-57, 85-102, 137-151
-            if (want_obs) {
-                float *o = obs_s + (size_t)el * p.D + p.obs_slot[cs.port_off + j];
-                if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
-                    if (occ_after) {
-                        o[0] = (capv == sp.B) ? 1.f : 0.5f;
-                        o[1] = (hot_t_arr(h) == tq) ? 0.f : p.exch[ip];
-                        o[2] = (float)(tq - hot_t_arr(h));
-                    } else { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
-                } else {
-                    if (occ_after) { o[0] = (float)(capv / sp.B); o[1] = (float)(hot_t_dep(h) - tq); }
-                    else { o[0] = 0.f; o[1] = 0.f; }
-                }
-            }
+            for (int j = 0; j < n; ++j)
+                process_port<ActT>(p, cs, t, s, pbase + j, port0 + j, p.hot[pbase + j], (double)actions[pbase + j], sum,
+                                   et.cp, et.dp, acc, obs_row, want_obs);
         }
         // clamp the charger's potential                      utils.py:779-789
-        if (rPot > cs.max_power) rPot = cs.max_power;
-        else if (rPot < cs.min_power) rPot = 0.0;
-        rCnt += invalid;
-        if (overflow) atomicOr(&envi[el * 4 + 3], (int)EV2B_ST_AMPS_OVERFLOW);
-        if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
-        if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
+        if (acc.pot > cs.max_power) acc.pot = cs.max_power;
+        else if (acc.pot < cs.min_power) acc.pot = 0.0;
+        if (acc.overflow) atomicOr(&envi[el * 4 + 3], (int)EV2B_ST_AMPS_OVERFLOW);
+        if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = (float)acc.P;
+        if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = (float)acc.A;
     }
-    red[RedP * NT + tid] = rP;           red[RedA * NT + tid] = rA;
-    red[RedProfit * NT + tid] = rProfit; red[RedSatExp * NT + tid] = rSatExp;
-    red[RedPot * NT + tid] = rPot;       red[RedCharged * NT + tid] = rCh;
-    red[RedDischarged * NT + tid] = rDis; red[RedSatSum * NT + tid] = rSat;
-    cnt[tid] = rCnt;
+    red[RedP * NT + tid] = acc.P;             red[RedProfit * NT + tid] = acc.profit;
+    red[RedSatExp * NT + tid] = acc.satexp;   red[RedPot * NT + tid] = acc.pot;
+    red[RedCharged * NT + tid] = acc.ch;      red[RedDischarged * NT + tid] = acc.dis;
+    red[RedSatSum * NT + tid] = acc.sat;
+    cnt[tid] = acc.cnt;
     __syncthreads();
 
     // ---- phase B: fixed-order reductions (warp per job) + series part of the observation -------
@@ -364,13 +444,10 @@ __global__ void __launch_bounds__(MAXT) step_kernel(const Params p) {
             const int jt = envi[jel * 4 + 0], js = envi[jel * 4 + 1];
             if (jt >= p.T) continue;
             if (k < p.Tr) {       // transformer k: Transformer.step accumulation   transformer.py:269-274
-                double sp_ = 0, sa_ = 0;
-                for (int i = p.tr_cs_off[k] + lane; i < p.tr_cs_off[k + 1]; i += 32) {
-                    const int cc = jel * p.C + p.tr_cs_idx[i];
-                    sp_ += red[RedP * NT + cc];
-                    sa_ += red[RedA * NT + cc];
-                }
-                sp_ = warp_sum(sp_); sa_ = warp_sum(sa_);
+                double sp_ = 0;
+                for (int i = p.tr_cs_off[k] + lane; i < p.tr_cs_off[k + 1]; i += 32)
+                    sp_ += red[RedP * NT + jel * p.C + p.tr_cs_idx[i]];
+                sp_ = warp_sum(sp_);
                 if (lane == 0) {
                     const TrT tt = p.tr_t[((size_t)js * p.T + jt) * p.Tr + k];
                     const double base = tt.infl + tt.solar;                       // transformer.py:264-265
@@ -380,7 +457,6 @@ __global__ void __launch_bounds__(MAXT) step_kernel(const Params p) {
                     trov[jel * p.Tr + k] = ov;
                     if (p.out.tr_power)    p.out.tr_power[(size_t)je * p.Tr + k] = ptot;
                     if (p.out.tr_overload) p.out.tr_overload[(size_t)je * p.Tr + k] = ov;
-                    (void)sa_;
                 }
             } else {              // env-level sums
                 double v[kNRed];
@@ -390,12 +466,12 @@ __global__ void __launch_bounds__(MAXT) step_kernel(const Params p) {
                 for (int i = lane; i < p.C; i += 32) {
                     const int cc = jel * p.C + i;
 #pragma unroll
-                    for (int q = 0; q < kNRed; ++q) v[q] += red[q * NT + cc];
+                    for (int q = 0; q < kNRed; ++q) if (q != RedA) v[q] += red[q * NT + cc];
                     const int w = cnt[cc];
                     ci += w & 1023; cd += (w >> 10) & 1023; ca += (w >> 20) & 1023;
                 }
 #pragma unroll
-                for (int q = 0; q < kNRed; ++q) v[q] = warp_sum(v[q]);
+                for (int q = 0; q < kNRed; ++q) if (q != RedA) v[q] = warp_sum(v[q]);
                 ci = warp_sum_i(ci); cd = warp_sum_i(cd); ca = warp_sum_i(ca);
                 if (lane == 0) {
 #pragma unroll
@@ -406,15 +482,17 @@ __global__ void __launch_bounds__(MAXT) step_kernel(const Params p) {
         }
         if (want_obs && p.state_kind != EV2B_STATE_PUBLIC_PST) {
             const int per_env = 20 + (p.state_kind == EV2B_STATE_V2G_PROFIT_MAX_LOADS ? p.Tr * 40 : 0);
-            for (int i = tid; i < p.EPB * per_env; i += NT) {
-                const int jel = i / per_env, ii = i - jel * per_env;
+            for (int jel = 0; jel < p.EPB; ++jel) {
                 const int je = blockIdx.x * p.EPB + jel;
-                if (je >= p.E) continue;
+                if (je >= p.E) break;
                 const int jt = envi[jel * 4 + 0];
                 if (jt >= p.T) continue;
-                int off;
-                const float v = obs_series_value(p, envi[jel * 4 + 1], jt + 1, ii, &off);
-                obs_s[(size_t)jel * p.D + off] = v;
+                const int js = envi[jel * 4 + 1];
+                for (int i = tid; i < per_env; i += NT) {
+                    int off;
+                    const float v = obs_series_value(p, js, jt + 1, i, &off);
+                    obs_s[(size_t)jel * p.D + off] = v;
+                }
             }
         }
     }
@@ -474,10 +552,13 @@ __global__ void __launch_bounds__(MAXT) step_kernel(const Params p) {
     }
     if (want_obs) {
         __syncthreads();
-        for (int i = tid; i < p.EPB * p.D; i += NT) {
-            const int jel = i / p.D;
+        for (int jel = 0; jel < p.EPB; ++jel) {
             const int je = blockIdx.x * p.EPB + jel;
-            if (je < p.E && envi[jel * 4 + 0] < p.T) p.out.obs[(size_t)blockIdx.x * p.EPB * p.D + i] = obs_s[i];
+            if (je >= p.E) break;
+            if (envi[jel * 4 + 0] >= p.T) continue;
+            float *dst = p.out.obs + (size_t)je * p.D;
+            const float *src = obs_s + (size_t)jel * p.D;
+            for (int i = tid; i < p.D; i += NT) dst[i] = src[i];
         }
     }
 }
