@@ -55,11 +55,12 @@ struct ev2b_handle {
     std::vector<double> cls_imax;       // per charger class
     std::vector<std::array<double, 4>> cls_veff;
     // device: static
-    DevBuf<CsStatic> cs; DevBuf<int> tr_cs_off, tr_cs_idx, obs_slot, tr_obs_off;
+    DevBuf<CsStatic> cs; DevBuf<int> tr_cs_off, tr_cs_idx, obs_slot, tr_obs_off, port_cs_d, series_off;
+    int W = 0;                          // (scenario, time)-only observation values per env
     // device: bank
     int S = 0, Smax = 1, n_dr = 1, lut_len = 101;
     DevBuf<EnvT> env_t; DevBuf<TrT> tr_t; DevBuf<SessRec> sess; DevBuf<EvSpec> spec;
-    DevBuf<double> luts_c, luts_d, pot_kw; DevBuf<float> trA, trF, tr_limit; DevBuf<DrEv> dr; DevBuf<uint8_t> dr_count;
+    DevBuf<double> luts_c, luts_d, pot_kw; DevBuf<float> trA, trF, tr_limit, obs_static; DevBuf<DrEv> dr; DevBuf<uint8_t> dr_count;
     // device: state
     DevBuf<uint4> hot; DevBuf<double> cap; DevBuf<float> exch; DevBuf<int> env_step, env_scn;
     DevBuf<double> env_pot, env_usage, env_kpi;
@@ -76,12 +77,14 @@ struct ev2b_handle {
     Params params() const {
         Params p{};
         p.E = E; p.C = C; p.P = P; p.Tr = Tr; p.T = T; p.D = D; p.EPB = EPB; p.n_dr = n_dr; p.lut_len = lut_len;
-        p.Smax = Smax; p.S = S; p.n_cls = n_cls;
+        p.Smax = Smax; p.S = S; p.n_cls = n_cls; p.W = W;
         p.reward_kind = dims.reward_kind; p.state_kind = dims.state_kind; p.dr_steps_ahead = dims.dr_steps_ahead;
         p.c60 = 60.0 / (double)dims.timescale; p.p60 = (double)dims.timescale / 60.0; p.period = (double)dims.timescale;
-        p.tr_voltage = dims.tr_voltage;
+        p.rc60 = 1.0 / p.c60; p.rp60 = 1.0 / p.p60; p.rperiod = 1.0 / p.period;
+        p.p_magic = P > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)P) + 1u : 0u;
         p.c_magic = C > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)C) + 1u : 0u;
         p.cs_uniform = cs_uniform; p.cs0 = cs_h.empty() ? CsStatic{} : cs_h[0];
+        p.port_cs = port_cs_d.p; p.series_off = series_off.p; p.obs_static = obs_static.p;
         p.cs = cs.p; p.tr_cs_off = tr_cs_off.p; p.tr_cs_idx = tr_cs_idx.p; p.obs_slot = obs_slot.p; p.tr_obs_off = tr_obs_off.p;
         p.env_t = env_t.p; p.tr_t = tr_t.p; p.sess = sess.p; p.spec = spec.p; p.luts_c = luts_c.p; p.luts_d = luts_d.p;
         p.pot_kw = pot_kw.p; p.trA = trA.p; p.trF = trF.p; p.tr_limit = tr_limit.p; p.dr = dr.p; p.dr_count = dr_count.p;
@@ -169,7 +172,11 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         s.imax_dis_abs = std::fabs(tp->cs_imax_dis[c]);          // ev_charger.py:184
         s.imin_dis = tp->cs_imin_dis[c];
         s.veff[0] = 0.0;
-        for (int k = 1; k <= 3; ++k) s.veff[k] = tp->cs_voltage[c] * std::sqrt((double)k);   // ev.py:279
+        s.rveff[0] = 0.0;
+        for (int k = 1; k <= 3; ++k) {
+            s.veff[k] = tp->cs_voltage[c] * std::sqrt((double)k);   // ev.py:279
+            s.rveff[k] = 1.0 / s.veff[k];
+        }
         s.max_power = std::sqrt((double)ph) * tp->cs_voltage[c] * s.imax / 1000.0;           // utils.py:779-780
         s.min_power = std::sqrt((double)ph) * tp->cs_voltage[c] * s.imin / 1000.0;           // utils.py:781-782
         s.port_off = off; s.n_ports = tp->cs_n_ports[c]; s.tr = tp->cs_tr[c]; s.phases = ph;
@@ -214,6 +221,14 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
             }
         }
     }
+    // destination offsets of the (scenario, time)-only observation values: [20 prices][Tr x 40]
+    std::vector<int> series_off_h;
+    if (d->state_kind == EV2B_STATE_V2G_PROFIT_MAX || d->state_kind == EV2B_STATE_V2G_PROFIT_MAX_LOADS) {
+        for (int i = 0; i < 20; ++i) series_off_h.push_back(2 + i);
+        if (d->state_kind == EV2B_STATE_V2G_PROFIT_MAX_LOADS)
+            for (int k = 0; k < h->Tr; ++k) for (int j = 0; j < 40; ++j) series_off_h.push_back(tr_obs[k] + j);
+    }
+    h->W = (int)series_off_h.size();
     // launch shape: a CTA owns EPB whole envs, one thread per (env, charger)
     {
         int best_epb = 1; double best_u = -1;
@@ -227,8 +242,10 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         }
         h->EPB = best_epb;
         h->block = std::max(32, (best_epb * C + 31) / 32 * 32);
-        h->smem = sizeof(double) * ((size_t)kNRed * h->block + (size_t)h->EPB * h->Tr + (size_t)h->EPB * kNRed) +
-                  sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4) + sizeof(float) * (size_t)h->EPB * h->D;
+        const size_t PP = (size_t)h->EPB * h->P;
+        h->smem = sizeof(double) * ((size_t)kNRed * h->block + 3 * PP + (size_t)h->EPB * h->Tr + (size_t)h->EPB * kNRed) +
+                  sizeof(uint2) * PP + sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4 + PP + 4) +
+                  sizeof(float) * (size_t)h->EPB * h->D + PP + 16;
     }
 #define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
         g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e); delete h; return EV2B_E_CUDA; } } while (0)
@@ -237,6 +254,8 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     CREATE_TRY(h->tr_cs_idx.upload(tr_idx));
     CREATE_TRY(h->obs_slot.upload(slot));
     CREATE_TRY(h->tr_obs_off.upload(tr_obs));
+    CREATE_TRY(h->port_cs_d.upload(h->port_cs));
+    CREATE_TRY(h->series_off.upload(series_off_h));
     const size_t EP = (size_t)h->E * h->P;
     CREATE_TRY(h->hot.alloc(EP)); CREATE_TRY(h->cap.alloc(EP)); CREATE_TRY(h->exch.alloc(EP));
     CREATE_TRY(h->env_step.alloc(h->E)); CREATE_TRY(h->env_scn.alloc(h->E));
@@ -349,6 +368,7 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
             sp.pmax_dis = b->s_pmax_dis[r]; sp.pmin_dis = b->s_pmin_dis[r]; sp.bmin = b->s_bmin[r];
             sp.bmin_em = b->s_bmin_em[r]; sp.desired = b->s_desired[r]; sp.mult = b->s_mult[r];
             sp.ev_phases = b->s_ev_phases[r];
+            sp.rB = 1.0 / sp.B;
             if (sp.ev_phases < 1 || sp.ev_phases > 3) return h->fail(EV2B_E_SCENARIO, "scenario %d: ev_phases must be 1..3", i);
             sp.lut = b->s_lut[r] >= 0 ? lut_global[b->lut_off[i] + b->s_lut[r]] : -1;
             unsigned tsm = 0xFFFFu, ecm = 0xFFFFu, edm = 0xFFFFu;
@@ -438,6 +458,21 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
     CUDA_TRY(h, h->pot_kw.upload(pot_kw)); CUDA_TRY(h, h->trA.upload(trA)); CUDA_TRY(h, h->trF.upload(trF));
     CUDA_TRY(h, h->tr_limit.upload(tr_limit)); CUDA_TRY(h, h->dr.upload(dr)); CUDA_TRY(h, h->dr_count.upload(dr_count));
     h->S = S; h->Smax = Smax; h->n_dr = n_dr; h->lut_len = lut_len;
+    h->obs_static.release();
+    if (h->W > 0) {   // precompute the (scenario, time)-only observation values when the table is small enough
+        const size_t n = (size_t)S * (T + 1) * h->W;
+        if (n * sizeof(float) <= ((size_t)1 << 31)) {
+            DevBuf<float> tab;
+            CUDA_TRY(h, tab.alloc(n));
+            Params p = h->params();
+            p.obs_static = nullptr;
+            obs_static_kernel<<<1024, 256>>>(p, tab.p);
+            CUDA_TRY(h, cudaGetLastError());
+            CUDA_TRY(h, cudaDeviceSynchronize());
+            h->obs_static.p = tab.p; h->obs_static.n = tab.n; tab.p = nullptr; tab.n = 0;
+            h->launches += 1;
+        }
+    }
     {   // a new bank invalidates every running episode
         std::vector<int> st(h->E, h->T);
         CUDA_TRY(h, cudaMemcpy(h->env_step.p, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice));

@@ -7,28 +7,37 @@
 //   calculate_charge_power_potential (utils.py:760-791), the three stock rewards (reward.py) and the
 //   three stock state functions (state.py), for E env replicas at once.
 //
-// Mapping: ONE THREAD PER (env, charger).  A CTA owns EPB whole envs (EPB*C threads) so that the
-// per-transformer and per-env reductions stay inside the CTA (shared memory + warp shuffles, fixed
-// order => bitwise reproducible).  All per-port arrays are [E,P] struct-of-arrays: consecutive
-// threads touch consecutive addresses.  Arithmetic is IEEE float64 in the reference's operation
-// order; this translation unit is compiled with -fmad=false so no multiply-add is contracted.
-// No tensor cores: the path is elementwise + segmented reduce (HBM-bound).
+// Kernel structure (one CTA owns EPB whole envs, so every reduction stays inside the CTA):
+//   A1  thread per (env, charger): coalesced loads of the per-port state, empty-port masking,
+//       action normalisation; ports that will actually move energy are COMPACTED into a shared
+//       memory work list (mid-episode only a few % of ports are active: running the float64
+//       battery model per lane would leave ~30 of 32 lanes idle).
+//   A2  thread per work item (dense warps): EV.step -- the float64 battery model.
+//   A3  thread per (env, charger): charger accounting in port order, departures, arrivals,
+//       potential, observation tuples; coalesced stores of the updated state.
+//   B   warp per (env, transformer) / per env: fixed-order shared-memory + shuffle reductions.
+//   C   thread per env: reward, KPI sums, step counter.   D: coalesced observation rows.
+// Arithmetic is IEEE float64 in the reference's operation order; this translation unit is
+// compiled with -fmad=false so no multiply-add is contracted (the only FMAs are the explicit ones
+// of the exact constant division, ev2b_math.h).  No tensor cores: elementwise + segmented reduce.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/ev2b.h"
+#include "ev2b_math.h"
 
 namespace ev2b {
 
 constexpr int   kNoArrival = 32767;   // "no (further) session on this port"
 constexpr int   kMaxThreads = 1024;
-constexpr int   kNRed = 8;            // float64 partials per charger, see Red* below
-enum { RedP = 0, RedA, RedProfit, RedSatExp, RedPot, RedCharged, RedDischarged, RedSatSum };
+constexpr int   kNRed = 7;            // float64 partials per charger, see Red* below
+enum { RedP = 0, RedProfit, RedSatExp, RedPot, RedCharged, RedDischarged, RedSatSum };
 
 // ---- static tables -------------------------------------------------------------------------
 struct CsStatic {            // one per charger; ev_charger.py:41-75 + derived constants
     double imax, imin, imax_dis_abs, imin_dis;
     double veff[4];          // voltage*sqrt(phases) for phases = 1..3 (index 0 unused)  ev.py:279,365
+    double rveff[4];         // RN(1/veff[k])
     double max_power;        // sqrt(ph)*V*Imax/1000   utils.py:779-780
     double min_power;        // sqrt(ph)*V*Imin/1000   utils.py:781-782
     int    port_off, n_ports, tr, phases;
@@ -39,7 +48,8 @@ struct EvSpec {              // de-duplicated EV model; ev.py:45-113
     double B, pmax_ac, pmin_ac, pmax_dis, pmin_dis, bmin, bmin_em, desired, mult;
     double ts, eta_c, eta_d; // used when the per-session milli encodings are 0xFFFF
     int    ev_phases, lut;   // lut < 0: scalar efficiencies
-    double pad[3];
+    double rB;               // RN(1/B)
+    double pad[2];
 };
 static_assert(sizeof(EvSpec) == 128, "EvSpec must be 128 B");
 
@@ -59,21 +69,23 @@ struct DrEv { int16_t start, end; float value; };         // value = limit - lim
 
 struct Params {
     // sizes
-    int E, C, P, Tr, T, D, EPB, n_dr, lut_len, Smax, S, n_cls;
+    int E, C, P, Tr, T, D, EPB, n_dr, lut_len, Smax, S, n_cls, W;
     int reward_kind, state_kind, dr_steps_ahead;
-    double c60;        // 60 / timescale          ev.py:296
-    double p60;        // timescale / 60          ev.py:355
-    double period;     // timescale
-    double tr_voltage;
-    unsigned c_magic;  // ceil(2^32 / C): tid / C == __umulhi(tid, c_magic)
-    int cs_uniform;    // all chargers identical: read the layout from cs0 (constant bank) instead of global memory
+    double c60, rc60;        // 60 / timescale (ev.py:296) and its reciprocal
+    double p60, rp60;        // timescale / 60 (ev.py:355)
+    double period, rperiod;  // timescale
+    unsigned c_magic;        // ceil(2^32 / C): tid / C == __umulhi(tid, c_magic)
+    unsigned p_magic;        // ceil(2^32 / P)
+    int cs_uniform;          // all chargers identical: read the layout from cs0 (constant bank)
     CsStatic cs0;
     // static
-    const CsStatic *cs; const int *tr_cs_off; const int *tr_cs_idx; const int *obs_slot; const int *tr_obs_off;
+    const CsStatic *cs; const int *port_cs; const int *tr_cs_off; const int *tr_cs_idx; const int *obs_slot;
+    const int *tr_obs_off; const int *series_off;
     // scenario bank
     const EnvT *env_t; const TrT *tr_t; const SessRec *sess; const EvSpec *spec;
     const double *luts_c, *luts_d; const double *pot_kw;
     const float *trA, *trF, *tr_limit; const DrEv *dr; const uint8_t *dr_count;
+    const float *obs_static;   // [S][T+1][W] precomputed price window + forecast/limit blocks, or null
     // state
     uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;
     double *env_kpi;
@@ -94,52 +106,6 @@ __device__ __forceinline__ double lut_get(const double *lut, int lut_len, double
     return 1.0;
 }
 
-// EV._charge  ev.py:240-355
-__device__ __forceinline__ double ev_charge(const EvSpec &sp, double ts, double eta, double &cap, double amps,
-                                            double veff, const Params &p, double &energy) {
-    double pilot = eta * amps * veff / 1000.0 / sp.B / p.c60;      // :295-296
-    const double maxd = eta * sp.pmax_ac / sp.B / p.c60;           // :297-298
-    if (pilot > maxd) pilot = maxd;                                // :300-301
-    const double soc = cap / sp.B;
-    double curr;
-    if (ts == 1.0) {                                               // :303-306
-        curr = pilot + soc;
-        if (curr > 1.0) curr = 1.0;
-    } else {
-        const double pts = ts + (pilot - maxd) / maxd * (ts - 1.0);    // :312-314
-        double nsoc;
-        if (soc < pts) {
-            if (1.0 <= (pts - soc) / pilot) nsoc = pilot + soc;        // :323-324
-            else nsoc = 1.0 + exp(sp.mult * (pilot + soc - pts) / (pts - 1.0)) * (pts - 1.0);  // :326-330
-        } else {
-            nsoc = 1.0 + exp(sp.mult * pilot / (pts - 1.0)) * (soc - 1.0);                     // :332-334
-        }
-        const double lim = (maxd > pilot) ? pilot : maxd;              // :336-339
-        curr = (nsoc - soc > lim) ? lim + soc : nsoc;                  // :341-344
-    }
-    const double dsoc = curr - soc;
-    cap = curr * sp.B;                                             // :348
-    energy = dsoc * sp.B;                                          // :352
-    return energy / p.p60 * 1000.0 / veff;                         // :355
-}
-
-// EV._discharge  ev.py:357-405
-__device__ __forceinline__ double ev_discharge(const EvSpec &sp, double eta, double &cap, double amps,
-                                               double veff, const Params &p, double &energy) {
-    double given_power = amps * veff / 1000.0;                     // :367
-    if (fabs(given_power) > fabs(sp.pmax_dis)) given_power = sp.pmax_dis;   // :370-371
-    double given_energy = given_power * eta * p.period / 60.0;     // :381
-    if (cap + given_energy < sp.bmin) {                            // :382-393
-        if (cap > sp.bmin) { energy = -(cap - sp.bmin); given_energy = energy; }
-        else { energy = 0.0; given_energy = 0.0; }
-        cap = sp.bmin;
-    } else {
-        energy = given_energy;
-        cap += given_energy;
-    }
-    return given_energy * 60.0 / p.period * 1000.0 / veff;         // :405
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -150,6 +116,8 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+__device__ __forceinline__ const CsStatic &cs_of(const Params &p, int c) { return p.cs_uniform ? p.cs0 : p.cs[c]; }
 
 // ---- observation pieces shared by the step and reset kernels --------------------------------
 // Header of the stock state functions at observation time tq (= current_step after the increment).
@@ -163,16 +131,13 @@ __device__ __forceinline__ void obs_header(const Params &p, float *row, int s, i
         row[1] = (float)prev_usage;
     }
 }
-// One value of the header price window / per-transformer forecast + limit blocks.  i indexes the
-// flat list [20 prices][Tr * 40]; returns the obs offset through *off.
-__device__ __forceinline__ float obs_series_value(const Params &p, int s, int tq, int i, int *off) {
-    if (i < 20) {                                                   // abs(charge_prices[0, t:t+20]), zero padded
-        *off = 2 + i;
+// One value of the (scenario, time)-only part of the observation: i indexes the flat list
+// [20 prices][Tr * (20 load-pv forecast + 20 power limits)].
+__device__ __forceinline__ float obs_series_value(const Params &p, int s, int tq, int i) {
+    if (i < 20)                                                     // abs(charge_prices[0, t:t+20]), zero padded
         return (tq + i < p.T) ? (float)fabs(p.env_t[(size_t)s * p.T + tq + i].cp) : 0.f;
-    }
     i -= 20;
     const int k = i / 40, j = i - k * 40;
-    *off = p.tr_obs_off[k] + j;
     const size_t base = ((size_t)s * p.Tr + k) * p.T;
     if (j < 20) {                                                   // loads - pv   transformer.py:173-188
         const int idx = tq + j;
@@ -194,174 +159,125 @@ __device__ __forceinline__ float obs_series_value(const Params &p, int s, int tq
     }
     return v;
 }
-
-// ---- the fused step kernel --------------------------------------------------------------------
-__device__ __forceinline__ const CsStatic &cs_of(const Params &p, int c) { return p.cs_uniform ? p.cs0 : p.cs[c]; }
-
-// One port of one charger: EV.step + departure + arrival + potential + obs tuple.
-// Accumulates into the charger's partial sums (acc) in the reference's port order.
-struct ChargerAcc { double P, A, profit, satexp, pot, ch, dis, sat; int cnt; bool overflow; };
-
-template <typename ActT>
-__device__ __forceinline__ void process_port(const Params &p, const CsStatic &cs, const int t, const int s,
-                                             const size_t ip, const int port, uint4 h, double a, const double sum,
-                                             const double cp, const double dp, ChargerAcc &acc, float *obs_row,
-                                             const bool want_obs) {
-    const int tq = t + 1;
-    bool occ = hot_t_arr(h) <= t && t <= hot_t_dep(h);
-    if (!occ) a = 0.0;
-    if (sum > 1.0) a = a / sum; else if (sum < -1.0) a = -a / sum;                    // ev_charger.py:143-149
-    const double action = (a == 0.0) ? 0.0 : rint(a * 100000.0) / 100000.0;           // round(action, 5)  :157
-    const EvSpec *sp = p.spec + hot_spec(h);
-    double capv = 0.0, energy = 0.0;
-    float exch_new = 0.f;
-    bool exch_valid = false;
-    if (occ) capv = p.cap[ip];
-    if (occ && action != 0.0) {
-        double amps, act_amps = 0.0;
-        const double veff_cs = cs.veff[cs.phases];
-        if (action > 0.0) {                                                            // :167-170
-            amps = action * cs.imax;
-            if (amps < cs.imin - 0.01) amps = 0.0;
-            const double pmin = __ldg(&sp->pmin_ac);
-            if (amps > 0.0 && pmin != 0.0 && amps < pmin * 1000.0 / veff_cs) amps = 0.0;   // ev.py:151-152
-        } else {                                                                       // :183-186
-            amps = action * cs.imax_dis_abs;
-            if (amps > cs.imin_dis - 0.01) amps = cs.imin_dis;
-            const double pmin = __ldg(&sp->pmin_dis);
-            if (amps > 0.0) {                                                          // only if imin_dis > 0
-                const double pm = __ldg(&sp->pmin_ac);
-                if (amps < pm * 1000.0 / veff_cs) amps = 0.0;
-            } else if (amps < 0.0 && pmin != 0.0 && amps > pmin * 1000.0 / veff_cs) amps = 0.0;  // ev.py:153-154
-        }
-        if (amps != 0.0) {
-            const int evph = __ldg(&sp->ev_phases);
-            const double veff = cs.veff[cs.phases < evph ? cs.phases : evph];            // ev.py:169
-            const int lut = __ldg(&sp->lut);
-            const double B = __ldg(&sp->B);
-            if (amps > 0.0) {                                                          // EV._charge  ev.py:240-355
-                double eta;
-                const unsigned tsm = h.z >> 16, ecm = h.w & 0xFFFFu;
-                if (lut >= 0) eta = lut_get(p.luts_c + (size_t)lut * p.lut_len, p.lut_len, rint(amps)) / 100.0;
-                else eta = (ecm == 0xFFFFu) ? __ldg(&sp->eta_c) : (double)ecm / 1000.0;
-                const double ts = (tsm == 0xFFFFu) ? __ldg(&sp->ts) : (double)tsm / 1000.0;
-                const double pmax = __ldg(&sp->pmax_ac);
-                double pilot = eta * amps * veff / 1000.0 / B / p.c60;                 // :295-296
-                const double maxd = eta * pmax / B / p.c60;                            // :297-298
-                if (pilot > maxd) pilot = maxd;                                        // :300-301
-                const double soc = capv / B;
-                double curr;
-                if (ts == 1.0) {                                                       // :303-306
-                    curr = pilot + soc;
-                    if (curr > 1.0) curr = 1.0;
-                } else {
-                    const double pts = ts + (pilot - maxd) / maxd * (ts - 1.0);        // :312-314
-                    double nsoc;
-                    if (soc < pts) {
-                        if (1.0 <= (pts - soc) / pilot) nsoc = pilot + soc;            // :323-324
-                        else nsoc = 1.0 + exp(__ldg(&sp->mult) * (pilot + soc - pts) / (pts - 1.0)) * (pts - 1.0);
-                    } else {
-                        nsoc = 1.0 + exp(__ldg(&sp->mult) * pilot / (pts - 1.0)) * (soc - 1.0);   // :332-334
-                    }
-                    const double lim = (maxd > pilot) ? pilot : maxd;                  // :336-339
-                    curr = (nsoc - soc > lim) ? lim + soc : nsoc;                      // :341-344
-                }
-                capv = curr * B;                                                       // :348
-                energy = (curr - soc) * B;                                             // :346,352
-                act_amps = energy / p.p60 * 1000.0 / veff;                             // :355
-            } else {                                                                   // EV._discharge  ev.py:357-405
-                double eta;
-                const unsigned edm = h.w >> 16;
-                if (lut >= 0) eta = lut_get(p.luts_d + (size_t)lut * p.lut_len, p.lut_len, fabs(rint(amps))) / 100.0;
-                else eta = (edm == 0xFFFFu) ? __ldg(&sp->eta_d) : (double)edm / 1000.0;
-                const double pmd = __ldg(&sp->pmax_dis), bmin = __ldg(&sp->bmin);
-                double given_power = amps * veff / 1000.0;                             // :367
-                if (fabs(given_power) > fabs(pmd)) given_power = pmd;                  // :370-371
-                double given_energy = given_power * eta * p.period / 60.0;             // :381
-                if (capv + given_energy < bmin) {                                      // :382-393
-                    if (capv > bmin) { energy = -(capv - bmin); given_energy = energy; }
-                    else { energy = 0.0; given_energy = 0.0; }
-                    capv = bmin;
-                } else {
-                    energy = given_energy;
-                    capv += given_energy;
-                }
-                act_amps = given_energy * 60.0 / p.period * 1000.0 / veff;             // :405
-            }
-            capv = ceil(capv * 100.0) / 100.0;                                         // my_ceil  ev.py:183
-            p.cap[ip] = capv;
-            exch_new = p.exch[ip] + (float)energy;                                     // total_energy_exchanged ev.py:178
-            exch_valid = true;
-            p.exch[ip] = exch_new;
-        }
-        const double ae = fabs(energy);
-        if (action > 0.0) { acc.profit += ae * cp; acc.ch += ae; }                     // :178-179
-        else              { acc.profit += ae * dp; acc.dis += ae; }                    // :194-195
-        acc.P += energy * 60.0 / p.period;                                             // :180,196
-        acc.A += act_amps;                                                             // :181,197
-    }
-    if (acc.A - 0.0001 > cs.imax) acc.overflow = true;                                 // :203-205
-    if (p.out.port_energy) p.out.port_energy[ip] = (float)energy;
-
-    // departure (charger step counter == t)        ev_charger.py:209-224, ev.py:199-214
-    float dsat = __int_as_float(0x7fc00000);
-    if (occ && t >= hot_t_dep(h)) {
-        const double des = __ldg(&sp->desired);
-        const double sat = (capv < des - 0.001) ? capv / des : 1.0;
-        acc.satexp += 100.0 * exp(-10.0 * sat);                                        // reward.py:42,85
-        acc.sat += sat;
-        acc.cnt += 1 << 10;
-        dsat = (float)sat;
-    }
-    if (p.out.dep_sat) p.out.dep_sat[ip] = dsat;
-
-    // arrival of the next session at t+1            ev2gym_env.py:399-417, ev_charger.py:266-285
-    if (hot_next_arr(h) == tq) {
-        const SessRec r = p.sess[((size_t)s * p.P + port) * p.Smax + hot_cursor(h)];
-        h = r.hot;
-        capv = r.cap0;
-        p.hot[ip] = h;
-        p.cap[ip] = capv;
-        p.exch[ip] = 0.f;
-        exch_new = 0.f; exch_valid = true;
-        sp = p.spec + hot_spec(h);
-        acc.cnt += 1 << 20;
-    }
-    const bool occ_after = hot_t_arr(h) <= tq && tq <= hot_t_dep(h);
-    if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;                 // ev2gym_env.py:452-457
-    if (occ_after) {
-        const double B = __ldg(&sp->B);
-        // charge power potential for step t+1            utils.py:766-777
-        if (capv < B && hot_t_dep(h) > tq) acc.pot += __ldg(&p.pot_kw[hot_spec(h) * p.n_cls + cs.cls]);
-        if (want_obs) {       // observation tuple (transformer-major slot)   state.py:37-57, 85-102, 137-151
-            float *o = obs_row + p.obs_slot[port];
-            if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
-                o[0] = (capv == B) ? 1.f : 0.5f;
-                o[1] = exch_valid ? exch_new : p.exch[ip];
-                o[2] = (float)(tq - hot_t_arr(h));
-            } else {
-                o[0] = (float)(capv / B);
-                o[1] = (float)(hot_t_dep(h) - tq);
-            }
-        }
-    } else if (want_obs) {
-        float *o = obs_row + p.obs_slot[port];
-        o[0] = 0.f; o[1] = 0.f;
-        if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
+__device__ __forceinline__ float obs_series_fetch(const Params &p, int s, int tq, int i) {
+    if (p.obs_static) return __ldg(p.obs_static + ((size_t)s * (p.T + 1) + tq) * p.W + i);
+    return obs_series_value(p, s, tq, i);
+}
+// Fills obs_static[s][tq][0..W) for every scenario and observation time (run once per bank).
+__global__ void obs_static_kernel(const Params p, float *table) {
+    const size_t n = (size_t)p.S * (p.T + 1) * p.W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % p.W);
+        const size_t r = i / p.W;
+        table[i] = obs_series_value(p, (int)(r / (p.T + 1)), (int)(r % (p.T + 1)), w);
     }
 }
 
-// ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = read from CsStatic.
+// ---- A2: EV.step for one work item ------------------------------------------------------------
+// a = normalised action (non-zero), cap = battery level, hz/hw = hot words z/w of the session.
+// Returns through (energy, act_amps, cap); result = the EV saw non-zero amps (ev.py:158).
+__device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs, const unsigned hz, const unsigned hw,
+                                             const double a, double &cap, double &energy, double &act_amps) {
+    energy = 0.0; act_amps = 0.0;
+    const double action = ev2b_div_c(rint(a * 100000.0), 100000.0, 1e-5);          // round(action, 5)  ev_charger.py:157
+    if (action == 0.0) return false;
+    const EvSpec *sp = p.spec + (hz & 0xFFFFu);
+    const double veff_cs = cs.veff[cs.phases];
+    double amps;
+    if (action > 0.0) {                                                            // ev_charger.py:167-170
+        amps = action * cs.imax;
+        if (amps < cs.imin - 0.01) amps = 0.0;
+    } else {                                                                       // ev_charger.py:183-186
+        amps = action * cs.imax_dis_abs;
+        if (amps > cs.imin_dis - 0.01) amps = cs.imin_dis;
+    }
+    if (amps > 0.0) {                                                              // ev.py:151-152
+        const double pmin = __ldg(&sp->pmin_ac);
+        if (pmin != 0.0 && amps < pmin * 1000.0 / veff_cs) amps = 0.0;
+    } else if (amps < 0.0) {                                                       // ev.py:153-154
+        const double pmin = __ldg(&sp->pmin_dis);
+        if (pmin != 0.0 && amps > pmin * 1000.0 / veff_cs) amps = 0.0;
+    }
+    if (amps == 0.0) return false;
+    const int evph = __ldg(&sp->ev_phases);
+    const int ph = cs.phases < evph ? cs.phases : evph;                            // ev.py:169
+    const double veff = cs.veff[ph], rveff = cs.rveff[ph];
+    const int lut = __ldg(&sp->lut);
+    const double B = __ldg(&sp->B), rB = __ldg(&sp->rB);
+    if (amps > 0.0) {                                                              // EV._charge  ev.py:240-355
+        double eta;
+        const unsigned tsm = hz >> 16, ecm = hw & 0xFFFFu;
+        if (lut >= 0) eta = ev2b_div_c(lut_get(p.luts_c + (size_t)lut * p.lut_len, p.lut_len, rint(amps)), 100.0, 0.01);
+        else eta = (ecm == 0xFFFFu) ? __ldg(&sp->eta_c) : ev2b_div_c((double)ecm, 1000.0, 0.001);
+        const double ts = (tsm == 0xFFFFu) ? __ldg(&sp->ts) : ev2b_div_c((double)tsm, 1000.0, 0.001);
+        const double pmax = __ldg(&sp->pmax_ac);
+        // pilot_dsoc = eta*amps*voltage/1000/B/(60/period)                            :295-296
+        double pilot = ev2b_div_c(ev2b_div_c(ev2b_div_c(eta * amps * veff, 1000.0, 0.001), B, rB), p.c60, p.rc60);
+        const double maxd = ev2b_div_c(ev2b_div_c(eta * pmax, B, rB), p.c60, p.rc60);  // :297-298
+        if (pilot > maxd) pilot = maxd;                                            // :300-301
+        const double soc = ev2b_div_c(cap, B, rB);
+        double curr;
+        if (ts == 1.0) {                                                           // :303-306
+            curr = pilot + soc;
+            if (curr > 1.0) curr = 1.0;
+        } else {
+            const double pts = ts + (pilot - maxd) / maxd * (ts - 1.0);            // :312-314
+            double nsoc;
+            if (soc < pts) {
+                if (1.0 <= (pts - soc) / pilot) nsoc = pilot + soc;                // :323-324
+                else nsoc = 1.0 + exp(__ldg(&sp->mult) * (pilot + soc - pts) / (pts - 1.0)) * (pts - 1.0);  // :326-330
+            } else {
+                nsoc = 1.0 + exp(__ldg(&sp->mult) * pilot / (pts - 1.0)) * (soc - 1.0);                     // :332-334
+            }
+            const double lim = (maxd > pilot) ? pilot : maxd;                      // :336-339
+            curr = (nsoc - soc > lim) ? lim + soc : nsoc;                          // :341-344
+        }
+        cap = curr * B;                                                            // :348
+        energy = (curr - soc) * B;                                                 // :346,352
+        act_amps = ev2b_div_c(ev2b_div_c(energy, p.p60, p.rp60) * 1000.0, veff, rveff);   // :355
+    } else {                                                                       // EV._discharge  ev.py:357-405
+        double eta;
+        const unsigned edm = hw >> 16;
+        if (lut >= 0) eta = ev2b_div_c(lut_get(p.luts_d + (size_t)lut * p.lut_len, p.lut_len, fabs(rint(amps))), 100.0, 0.01);
+        else eta = (edm == 0xFFFFu) ? __ldg(&sp->eta_d) : ev2b_div_c((double)edm, 1000.0, 0.001);
+        const double pmd = __ldg(&sp->pmax_dis), bmin = __ldg(&sp->bmin);
+        double given_power = ev2b_div_c(amps * veff, 1000.0, 0.001);               // :367
+        if (fabs(given_power) > fabs(pmd)) given_power = pmd;                      // :370-371
+        double given_energy = ev2b_div_c(given_power * eta * p.period, 60.0, 1.0 / 60.0);   // :381
+        if (cap + given_energy < bmin) {                                           // :382-393
+            if (cap > bmin) { energy = -(cap - bmin); given_energy = energy; }
+            else { energy = 0.0; given_energy = 0.0; }
+            cap = bmin;
+        } else {
+            energy = given_energy;
+            cap += given_energy;
+        }
+        act_amps = ev2b_div_c(ev2b_div_c(given_energy * 60.0, p.period, p.rperiod) * 1000.0, veff, rveff);   // :405
+    }
+    cap = ev2b_div_c(ceil(cap * 100.0), 100.0, 0.01);                              // my_ceil  ev.py:183,188-189
+    return true;
+}
+
+// ---- the fused step kernel --------------------------------------------------------------------
+// ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = ragged (CsStatic).
 template <typename ActT, int NP, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
+    const int PP = p.EPB * p.P;
     double *red   = reinterpret_cast<double *>(smem_raw);                 // [kNRed][NT]
-    double *trov  = red + (size_t)kNRed * NT;                             // [EPB*Tr] overload per transformer
+    double *resE  = red + (size_t)kNRed * NT;                             // [PP] action in, energy out
+    double *resA  = resE + PP;                                            // [PP] actual amps out
+    double *resC  = resA + PP;                                            // [PP] battery level in/out (-1: EV inactive)
+    double *trov  = resC + PP;                                            // [EPB*Tr] overload per transformer
     double *envs  = trov + (size_t)p.EPB * p.Tr;                          // [EPB][kNRed]
-    int    *cnt   = reinterpret_cast<int *>(envs + (size_t)p.EPB * kNRed);// [NT] invalid | dep<<10 | arr<<20
+    uint2  *whot  = reinterpret_cast<uint2 *>(envs + (size_t)p.EPB * kNRed);   // [PP] hot words z, w of work items
+    int    *cnt   = reinterpret_cast<int *>(whot + PP);                   // [NT] invalid | dep<<10 | arr<<20
     int    *envi  = cnt + NT;                                             // [EPB][4] t, scn, cnt, flags
-    float  *obs_s = reinterpret_cast<float *>(envi + (size_t)p.EPB * 4);  // [EPB][D]
+    int    *wl    = envi + (size_t)p.EPB * 4;                             // [PP] work list (port_local)
+    int    *wcnt  = wl + PP;                                              // [1] (+3 pad)
+    float  *obs_s = reinterpret_cast<float *>(wcnt + 4);                  // [EPB][D]
+    signed char *pflag = reinterpret_cast<signed char *>(obs_s + (size_t)p.EPB * p.D);   // [PP] ragged path only
 
     const int tid = threadIdx.x;
     const int el = p.C == 1 ? tid : (int)__umulhi((unsigned)tid, p.c_magic);   // tid / C
@@ -370,10 +286,9 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     const bool valid = (el < p.EPB) && (e < p.E);
     const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
+    constexpr int NPR = NP > 0 ? NP : 1;
 
-    ChargerAcc acc;
-    acc.P = acc.A = acc.profit = acc.satexp = acc.pot = acc.ch = acc.dis = acc.sat = 0.0;
-    acc.cnt = 0; acc.overflow = false;
+    if (tid == 0) *wcnt = 0;
     int t = 0, s = 0;
     bool live = false;
     if (valid) {
@@ -382,123 +297,255 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         live = t < p.T;
         if (c == 0) { envi[el * 4 + 0] = t; envi[el * 4 + 1] = s; envi[el * 4 + 3] = 0; }
     }
+    __syncthreads();
 
+    // ---- A1: per charger: loads, empty-port masking, normalisation, work-list compaction -------
+    uint4 h[NPR];
+    double capv[NPR];
+    unsigned pushed = 0, asign = 0;      // bit j: port j is a work item / its action is > 0
+    int invalid = 0;
+    int port0 = 0, n = 0;
     if (valid && live) {
         const CsStatic &cs = cs_of(p, c);
-        const int port0 = p.cs_uniform ? c * (NP > 0 ? NP : p.cs0.n_ports) : cs.port_off;
-        const int n = NP > 0 ? NP : cs.n_ports;
+        port0 = p.cs_uniform ? c * (NP > 0 ? NP : p.cs0.n_ports) : cs.port_off;
+        n = NP > 0 ? NP : cs.n_ports;
         const size_t pbase = (size_t)e * p.P + port0;
-        float *obs_row = obs_s + (size_t)el * p.D;
+        double sum = 0.0;
         if (NP > 0) {
-            // issue every independent load of this charger up front
-            uint4 h[NP > 0 ? NP : 1];
-            double a[NP > 0 ? NP : 1];
+            double a[NPR];
 #pragma unroll
             for (int j = 0; j < NP; ++j) { h[j] = p.hot[pbase + j]; a[j] = (double)actions[pbase + j]; }
-            const EnvT et = p.env_t[(size_t)s * p.T + t];
-            double sum = 0.0;                                       // python sum(): left to right  ev_charger.py:143
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const bool occ = hot_t_arr(h[j]) <= t && t <= hot_t_dep(h[j]);
-                acc.cnt += occ ? 0 : 1;                             // invalid_action_punishment  :137-140
-                sum = sum + (occ ? a[j] : 0.0);
+                capv[j] = occ ? p.cap[pbase + j] : 0.0;
+                if (!occ) { a[j] = 0.0; ++invalid; }                     // ev_charger.py:137-140
+                sum = sum + a[j];                                        // python sum(), left to right  :143
             }
 #pragma unroll
-            for (int j = 0; j < NP; ++j)
-                process_port<ActT>(p, cs, t, s, pbase + j, port0 + j, h[j], a[j], sum, et.cp, et.dp, acc, obs_row, want_obs);
+            for (int j = 0; j < NP; ++j) {
+                double an = a[j];
+                if (sum > 1.0) an = an / sum; else if (sum < -1.0) an = -an / sum;     // :143-149
+                if (an != 0.0) {                                         // occupied and a non-zero request
+                    const int pl = el * p.P + port0 + j;
+                    const int slot = atomicAdd(wcnt, 1);
+                    wl[slot] = pl;
+                    resE[pl] = an; resC[pl] = capv[j]; whot[pl] = make_uint2(h[j].z, h[j].w);
+                    pushed |= 1u << j;
+                    if (an > 0.0) asign |= 1u << j;
+                }
+            }
         } else {
-            const EnvT et = p.env_t[(size_t)s * p.T + t];
-            double sum = 0.0;
             for (int j = 0; j < n; ++j) {
-                const uint4 h = p.hot[pbase + j];
-                const bool occ = hot_t_arr(h) <= t && t <= hot_t_dep(h);
-                acc.cnt += occ ? 0 : 1;
+                const uint4 hj = p.hot[pbase + j];
+                const bool occ = hot_t_arr(hj) <= t && t <= hot_t_dep(hj);
+                if (!occ) ++invalid;
                 sum = sum + (occ ? (double)actions[pbase + j] : 0.0);
             }
-            for (int j = 0; j < n; ++j)
-                process_port<ActT>(p, cs, t, s, pbase + j, port0 + j, p.hot[pbase + j], (double)actions[pbase + j], sum,
-                                   et.cp, et.dp, acc, obs_row, want_obs);
+            for (int j = 0; j < n; ++j) {
+                const uint4 hj = p.hot[pbase + j];
+                const bool occ = hot_t_arr(hj) <= t && t <= hot_t_dep(hj);
+                double an = occ ? (double)actions[pbase + j] : 0.0;
+                if (sum > 1.0) an = an / sum; else if (sum < -1.0) an = -an / sum;
+                const int pl = el * p.P + port0 + j;
+                signed char f = 0;
+                if (an != 0.0) {
+                    const int slot = atomicAdd(wcnt, 1);
+                    wl[slot] = pl;
+                    resE[pl] = an; resC[pl] = p.cap[pbase + j]; whot[pl] = make_uint2(hj.z, hj.w);
+                    f = an > 0.0 ? 1 : -1;
+                }
+                pflag[pl] = f;
+            }
+        }
+    }
+    // (scenario, time)-only part of the observation: price window + forecast / limit blocks
+    if (want_obs && p.W > 0) {
+        for (int jel = 0; jel < p.EPB; ++jel) {
+            const int je = blockIdx.x * p.EPB + jel;
+            if (je >= p.E) break;
+            const int jt = envi[jel * 4 + 0];
+            if (jt >= p.T) continue;
+            const int js = envi[jel * 4 + 1];
+            for (int i = tid; i < p.W; i += NT)
+                obs_s[(size_t)jel * p.D + p.series_off[i]] = obs_series_fetch(p, js, jt + 1, i);
+        }
+    }
+    __syncthreads();
+
+    // ---- A2: the float64 battery model on the compacted work list (dense warps) ----------------
+    {
+        const int nw = *wcnt;
+        for (int i = tid; i < nw; i += NT) {
+            const int pl = wl[i];
+            const int port = p.EPB == 1 ? pl : pl - (int)__umulhi((unsigned)pl, p.p_magic) * p.P;
+            const CsStatic &cs = cs_of(p, p.cs_uniform ? 0 : p.port_cs[port]);
+            const uint2 hw = whot[pl];
+            double cap = resC[pl], energy, amps;
+            const bool active = ev_step_item(p, cs, hw.x, hw.y, resE[pl], cap, energy, amps);
+            resE[pl] = energy; resA[pl] = amps;
+            resC[pl] = active ? cap : -1.0;                              // EV saw amps == 0: nothing changes (ev.py:158-163)
+        }
+    }
+    __syncthreads();
+
+    // ---- A3: charger accounting in port order, departures, arrivals, potential, obs tuples -----
+    double rP = 0, rA = 0, rProfit = 0, rSatExp = 0, rPot = 0, rCh = 0, rDis = 0, rSat = 0;
+    int rCnt = invalid;
+    if (valid && live) {
+        const CsStatic &cs = cs_of(p, c);
+        const EnvT et = p.env_t[(size_t)s * p.T + t];
+        const size_t pbase = (size_t)e * p.P + port0;
+        const int tq = t + 1;
+        float *obs_row = obs_s + (size_t)el * p.D;
+        bool overflow = false;
+#pragma unroll
+        for (int j = 0; j < (NP > 0 ? NP : n); ++j) {
+            const size_t ip = pbase + j;
+            const int pl = el * p.P + port0 + j;
+            uint4 hj; double cv; bool was_item, apos;
+            if (NP > 0) { hj = h[j]; cv = capv[j]; was_item = (pushed >> j) & 1u; apos = (asign >> j) & 1u; }
+            else {
+                hj = p.hot[ip];
+                const signed char f = pflag[pl];
+                was_item = f != 0; apos = f > 0;
+                cv = (hot_t_arr(hj) <= t && t <= hot_t_dep(hj)) ? p.cap[ip] : 0.0;
+            }
+            const bool occ = hot_t_arr(hj) <= t && t <= hot_t_dep(hj);
+            double energy = 0.0;
+            float exch_new = 0.f; bool exch_valid = false;
+            if (was_item) {
+                energy = resE[pl];
+                const double cnew = resC[pl];
+                if (cnew >= 0.0) {                                        // the EV was active this step
+                    cv = cnew;
+                    p.cap[ip] = cv;
+                    exch_new = p.exch[ip] + (float)energy;                // total_energy_exchanged  ev.py:178
+                    exch_valid = true;
+                    p.exch[ip] = exch_new;
+                }
+                const double ae = fabs(energy);
+                if (apos) { rProfit += ae * et.cp; rCh += ae; }           // ev_charger.py:178-179
+                else      { rProfit += ae * et.dp; rDis += ae; }          // ev_charger.py:194-195
+                rP += ev2b_div_c(energy * 60.0, p.period, p.rperiod);     // :180,196
+                rA += resA[pl];                                           // :181,197
+            }
+            if (rA - 0.0001 > cs.imax) overflow = true;                   // :203-205
+            if (p.out.port_energy) p.out.port_energy[ip] = (float)energy;
+
+            // departure (charger step counter == t)        ev_charger.py:209-224, ev.py:199-214
+            float dsat = __int_as_float(0x7fc00000);
+            if (occ && t >= hot_t_dep(hj)) {
+                const double des = __ldg(&p.spec[hot_spec(hj)].desired);
+                const double sat = (cv < des - 0.001) ? cv / des : 1.0;
+                rSatExp += 100.0 * exp(-10.0 * sat);                      // reward.py:42,85
+                rSat += sat;
+                rCnt += 1 << 10;
+                dsat = (float)sat;
+            }
+            if (p.out.dep_sat) p.out.dep_sat[ip] = dsat;
+
+            // arrival of the next session at t+1            ev2gym_env.py:399-417, ev_charger.py:266-285
+            if (hot_next_arr(hj) == tq) {
+                const SessRec r = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj)];
+                hj = r.hot;
+                cv = r.cap0;
+                p.hot[ip] = hj;
+                p.cap[ip] = cv;
+                p.exch[ip] = 0.f;
+                exch_new = 0.f; exch_valid = true;
+                rCnt += 1 << 20;
+            }
+            const bool occ_after = hot_t_arr(hj) <= tq && tq <= hot_t_dep(hj);
+            if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;          // ev2gym_env.py:452-457
+            if (occ_after) {
+                const EvSpec *sp = p.spec + hot_spec(hj);
+                const double B = __ldg(&sp->B);
+                // charge power potential for step t+1            utils.py:766-777
+                if (cv < B && hot_t_dep(hj) > tq) rPot += __ldg(&p.pot_kw[hot_spec(hj) * p.n_cls + cs.cls]);
+                if (want_obs) {       // observation tuple (transformer-major slot)   state.py:37-57, 85-102, 137-151
+                    float *o = obs_row + p.obs_slot[port0 + j];
+                    if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
+                        o[0] = (cv == B) ? 1.f : 0.5f;
+                        o[1] = exch_valid ? exch_new : p.exch[ip];
+                        o[2] = (float)(tq - hot_t_arr(hj));
+                    } else {
+                        o[0] = (float)ev2b_div_c(cv, B, __ldg(&sp->rB));
+                        o[1] = (float)(hot_t_dep(hj) - tq);
+                    }
+                }
+            } else if (want_obs) {
+                float *o = obs_row + p.obs_slot[port0 + j];
+                o[0] = 0.f; o[1] = 0.f;
+                if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
+            }
         }
         // clamp the charger's potential                      utils.py:779-789
-        if (acc.pot > cs.max_power) acc.pot = cs.max_power;
-        else if (acc.pot < cs.min_power) acc.pot = 0.0;
-        if (acc.overflow) atomicOr(&envi[el * 4 + 3], (int)EV2B_ST_AMPS_OVERFLOW);
-        if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = (float)acc.P;
-        if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = (float)acc.A;
+        if (rPot > cs.max_power) rPot = cs.max_power;
+        else if (rPot < cs.min_power) rPot = 0.0;
+        if (overflow) atomicOr(&envi[el * 4 + 3], (int)EV2B_ST_AMPS_OVERFLOW);
+        if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
+        if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
     }
-    red[RedP * NT + tid] = acc.P;             red[RedProfit * NT + tid] = acc.profit;
-    red[RedSatExp * NT + tid] = acc.satexp;   red[RedPot * NT + tid] = acc.pot;
-    red[RedCharged * NT + tid] = acc.ch;      red[RedDischarged * NT + tid] = acc.dis;
-    red[RedSatSum * NT + tid] = acc.sat;
-    cnt[tid] = acc.cnt;
+    red[RedP * NT + tid] = rP;             red[RedProfit * NT + tid] = rProfit;
+    red[RedSatExp * NT + tid] = rSatExp;   red[RedPot * NT + tid] = rPot;
+    red[RedCharged * NT + tid] = rCh;      red[RedDischarged * NT + tid] = rDis;
+    red[RedSatSum * NT + tid] = rSat;
+    cnt[tid] = rCnt;
     __syncthreads();
 
-    // ---- phase B: fixed-order reductions (warp per job) + series part of the observation -------
+    // ---- B: fixed-order reductions: warp per (env, transformer) and per env ---------------------
     {
         const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
-        const int njobs = p.EPB * (p.Tr + 1);
-        for (int job = warp; job < njobs; job += nwarps) {
-            const int jel = job / (p.Tr + 1), k = job - jel * (p.Tr + 1);
+        for (int jel = 0; jel < p.EPB; ++jel) {
             const int je = blockIdx.x * p.EPB + jel;
-            if (je >= p.E) continue;
-            const int jt = envi[jel * 4 + 0], js = envi[jel * 4 + 1];
+            if (je >= p.E) break;
+            const int jt = envi[jel * 4 + 0];
             if (jt >= p.T) continue;
-            if (k < p.Tr) {       // transformer k: Transformer.step accumulation   transformer.py:269-274
-                double sp_ = 0;
-                for (int i = p.tr_cs_off[k] + lane; i < p.tr_cs_off[k + 1]; i += 32)
-                    sp_ += red[RedP * NT + jel * p.C + p.tr_cs_idx[i]];
-                sp_ = warp_sum(sp_);
-                if (lane == 0) {
-                    const TrT tt = p.tr_t[((size_t)js * p.T + jt) * p.Tr + k];
-                    const double base = tt.infl + tt.solar;                       // transformer.py:264-265
-                    const double ptot = base + sp_;
-                    double ov = 0.0;                                              // transformer.py:284-302
-                    if (ptot > tt.maxp + 0.0001 || ptot < tt.minp - 0.0001) ov = fabs(ptot - tt.maxp);
-                    trov[jel * p.Tr + k] = ov;
-                    if (p.out.tr_power)    p.out.tr_power[(size_t)je * p.Tr + k] = ptot;
-                    if (p.out.tr_overload) p.out.tr_overload[(size_t)je * p.Tr + k] = ov;
-                }
-            } else {              // env-level sums
-                double v[kNRed];
+            const int js = envi[jel * 4 + 1];
+            for (int k = warp; k <= p.Tr; k += nwarps) {
+                if (k < p.Tr) {       // transformer k: Transformer.step accumulation   transformer.py:269-274
+                    double sp_ = 0;
+                    const int i1 = p.tr_cs_off[k + 1];
+                    for (int i = p.tr_cs_off[k] + lane; i < i1; i += 32)
+                        sp_ += red[RedP * NT + jel * p.C + p.tr_cs_idx[i]];
+                    sp_ = warp_sum(sp_);
+                    if (lane == 0) {
+                        const TrT tt = p.tr_t[((size_t)js * p.T + jt) * p.Tr + k];
+                        const double ptot = (tt.infl + tt.solar) + sp_;               // transformer.py:264-265
+                        double ov = 0.0;                                              // transformer.py:284-302
+                        if (ptot > tt.maxp + 0.0001 || ptot < tt.minp - 0.0001) ov = fabs(ptot - tt.maxp);
+                        trov[jel * p.Tr + k] = ov;
+                        if (p.out.tr_power)    p.out.tr_power[(size_t)je * p.Tr + k] = ptot;
+                        if (p.out.tr_overload) p.out.tr_overload[(size_t)je * p.Tr + k] = ov;
+                    }
+                } else {              // env-level sums
+                    double v[kNRed];
 #pragma unroll
-                for (int q = 0; q < kNRed; ++q) v[q] = 0.0;
-                int ci = 0, cd = 0, ca = 0;
-                for (int i = lane; i < p.C; i += 32) {
-                    const int cc = jel * p.C + i;
+                    for (int q = 0; q < kNRed; ++q) v[q] = 0.0;
+                    int ci = 0, cd = 0, ca = 0;
+                    for (int i = lane; i < p.C; i += 32) {
+                        const int cc = jel * p.C + i;
 #pragma unroll
-                    for (int q = 0; q < kNRed; ++q) if (q != RedA) v[q] += red[q * NT + cc];
-                    const int w = cnt[cc];
-                    ci += w & 1023; cd += (w >> 10) & 1023; ca += (w >> 20) & 1023;
-                }
+                        for (int q = 0; q < kNRed; ++q) v[q] += red[q * NT + cc];
+                        const int w = cnt[cc];
+                        ci += w & 1023; cd += (w >> 10) & 1023; ca += (w >> 20) & 1023;
+                    }
 #pragma unroll
-                for (int q = 0; q < kNRed; ++q) if (q != RedA) v[q] = warp_sum(v[q]);
-                ci = warp_sum_i(ci); cd = warp_sum_i(cd); ca = warp_sum_i(ca);
-                if (lane == 0) {
+                    for (int q = 0; q < kNRed; ++q) v[q] = warp_sum(v[q]);
+                    ci = warp_sum_i(ci); cd = warp_sum_i(cd); ca = warp_sum_i(ca);
+                    if (lane == 0) {
 #pragma unroll
-                    for (int q = 0; q < kNRed; ++q) envs[jel * kNRed + q] = v[q];
-                    envi[jel * 4 + 2] = ci | (cd << 10) | (ca << 20);
-                }
-            }
-        }
-        if (want_obs && p.state_kind != EV2B_STATE_PUBLIC_PST) {
-            const int per_env = 20 + (p.state_kind == EV2B_STATE_V2G_PROFIT_MAX_LOADS ? p.Tr * 40 : 0);
-            for (int jel = 0; jel < p.EPB; ++jel) {
-                const int je = blockIdx.x * p.EPB + jel;
-                if (je >= p.E) break;
-                const int jt = envi[jel * 4 + 0];
-                if (jt >= p.T) continue;
-                const int js = envi[jel * 4 + 1];
-                for (int i = tid; i < per_env; i += NT) {
-                    int off;
-                    const float v = obs_series_value(p, js, jt + 1, i, &off);
-                    obs_s[(size_t)jel * p.D + off] = v;
+                        for (int q = 0; q < kNRed; ++q) envs[jel * kNRed + q] = v[q];
+                        envi[jel * 4 + 2] = ci | (cd << 10) | (ca << 20);
+                    }
                 }
             }
         }
     }
     __syncthreads();
 
-    // ---- phase C: one thread per env: reward, KPIs, step counter -------------------------------
+    // ---- C: one thread per env: reward, KPIs, step counter ---------------------------------------
     if (tid < p.EPB) {
         const int je = blockIdx.x * p.EPB + tid;
         if (je < p.E) {
@@ -550,6 +597,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             if (p.out.status) p.out.status[je] = status;
         }
     }
+    // ---- D: coalesced observation rows -----------------------------------------------------------
     if (want_obs) {
         __syncthreads();
         for (int jel = 0; jel < p.EPB; ++jel) {
@@ -611,14 +659,7 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
         for (int i = threadIdx.x; i < p.D; i += blockDim.x) row[i] = 0.f;   // no EV is connected at t = 0
         __syncthreads();
         if (threadIdx.x == 0) obs_header(p, row, s, 0, 0.0);
-        if (p.state_kind != EV2B_STATE_PUBLIC_PST) {
-            const int per_env = 20 + (p.state_kind == EV2B_STATE_V2G_PROFIT_MAX_LOADS ? p.Tr * 40 : 0);
-            for (int i = threadIdx.x; i < per_env; i += blockDim.x) {
-                int off;
-                const float v = obs_series_value(p, s, 0, i, &off);
-                row[off] = v;
-            }
-        }
+        for (int i = threadIdx.x; i < p.W; i += blockDim.x) row[p.series_off[i]] = obs_series_fetch(p, s, 0, i);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
