@@ -434,16 +434,17 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             if (p.out.port_energy) p.out.port_energy[ip] = (float)energy;
 
             // departure (charger step counter == t)        ev_charger.py:209-224, ev.py:199-214
-            float dsat = __int_as_float(0x7fc00000);
+            double dsat = __longlong_as_double(0x7ff8000000000000LL), dcap = dsat;
             if (occ && t >= hot_t_dep(hj)) {
                 const double des = __ldg(&p.spec[hot_spec(hj)].desired);
                 const double sat = (cv < des - 0.001) ? cv / des : 1.0;
                 rSatExp += 100.0 * exp(-10.0 * sat);                      // reward.py:42,85
                 rSat += sat;
                 rCnt += 1 << 10;
-                dsat = (float)sat;
+                dsat = sat; dcap = cv;
             }
             if (p.out.dep_sat) p.out.dep_sat[ip] = dsat;
+            if (p.out.dep_cap) p.out.dep_cap[ip] = dcap;
 
             // arrival of the next session at t+1            ev2gym_env.py:399-417, ev_charger.py:266-285
             if (hot_next_arr(hj) == tq) {

@@ -28,7 +28,8 @@ _OUT_SPECS = {  # name -> (dtype, per-env shape key)
     "reward": ("float64", ()), "status": ("int32", ()), "obs": ("float32", ("D",)),
     "cs_power": ("float32", ("C",)), "cs_current": ("float32", ("C",)),
     "tr_power": ("float64", ("Tr",)), "tr_overload": ("float64", ("Tr",)), "total_costs": ("float64", ()),
-    "action_mask": ("uint8", ("P",)), "dep_sat": ("float32", ("P",)), "port_energy": ("float32", ("P",)),
+    "action_mask": ("uint8", ("P",)), "dep_sat": ("float64", ("P",)), "dep_cap": ("float64", ("P",)),
+    "port_energy": ("float32", ("P",)),
 }
 
 

@@ -121,7 +121,8 @@ typedef struct {
     double   *tr_overload;   /* [E,Tr]  tr.get_how_overloaded()              transformer.py:292-302 */
     double   *total_costs;   /* [E]     sum of charger profits (`total_costs`) ev2gym_env.py:381   */
     uint8_t  *action_mask;   /* [E,P]   1 if an EV is connected after the step ev2gym_env.py:452-457 */
-    float    *dep_sat;       /* [E,P]   user satisfaction of the EV that left this port this step, NaN otherwise */
+    double   *dep_sat;       /* [E,P]   user satisfaction of the EV that left this port this step, NaN otherwise */
+    double   *dep_cap;       /* [E,P]   its final battery level (kWh), NaN otherwise  (env.departing_evs)         */
     float    *port_energy;   /* [E,P]   ev.current_energy of this step (kWh)                       */
 } ev2b_step_out;
 
