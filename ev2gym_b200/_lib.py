@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libev2b.so")
+LIB_PATH = os.environ.get("EV2B_LIB") or os.path.join(CSRC, "libev2b.so")   # EV2B_LIB: A/B-test another build
 SOURCES = [os.path.join(CSRC, f) for f in ("ev2b.cu", "ev2b_device.cuh")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "ev2b.h")]
 

@@ -120,10 +120,13 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
         kern<<<grid, h->block, h->smem, st>>>(p);
         return cudaGetLastError();
     };
+#ifndef EV2B_MINB
+#define EV2B_MINB 4
+#endif
     if (h->block <= 256) {
-        if (h->np_uniform == 1) return go(step_kernel<ActT, 1, 256, 4>);
-        if (h->np_uniform == 2) return go(step_kernel<ActT, 2, 256, 4>);
-        return go(step_kernel<ActT, 0, 256, 4>);
+        if (h->np_uniform == 1) return go(step_kernel<ActT, 1, 256, EV2B_MINB>);
+        if (h->np_uniform == 2) return go(step_kernel<ActT, 2, 256, EV2B_MINB>);
+        return go(step_kernel<ActT, 0, 256, EV2B_MINB>);
     }
     if (h->np_uniform == 1) return go(step_kernel<ActT, 1, kMaxThreads, 1>);
     if (h->np_uniform == 2) return go(step_kernel<ActT, 2, kMaxThreads, 1>);
@@ -244,7 +247,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         h->block = std::max(32, (best_epb * C + 31) / 32 * 32);
         const size_t PP = (size_t)h->EPB * h->P;
         h->smem = sizeof(double) * ((size_t)kNRed * h->block + 3 * PP + (size_t)h->EPB * h->Tr + (size_t)h->EPB * kNRed) +
-                  sizeof(uint2) * PP + sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4 + PP + 4) +
+                  sizeof(uint2) * PP + sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4 + PP + 4 + 1) +
                   sizeof(float) * (size_t)h->EPB * h->D + PP + 16;
     }
 #define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \

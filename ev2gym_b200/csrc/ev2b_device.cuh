@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     int    *envi  = cnt + NT;                                             // [EPB][4] t, scn, cnt, flags
     int    *wl    = envi + (size_t)p.EPB * 4;                             // [PP] work list (port_local)
     int    *wcnt  = wl + PP;                                              // [1] (+3 pad)
-    float  *obs_s = reinterpret_cast<float *>(wcnt + 4);                  // [EPB][D]
+    float  *obs_s = reinterpret_cast<float *>(wcnt + 4 + ((NT + PP) & 1));   // [EPB][D], 8-byte aligned
     signed char *pflag = reinterpret_cast<signed char *>(obs_s + (size_t)p.EPB * p.D);   // [PP] ragged path only
 
     const int tid = threadIdx.x;
@@ -291,30 +291,38 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     if (tid == 0) *wcnt = 0;
     int t = 0, s = 0;
     bool live = false;
-    if (valid) {
-        t = p.env_step[e];
-        s = p.env_scn[e];
-        live = t < p.T;
-        if (c == 0) { envi[el * 4 + 0] = t; envi[el * 4 + 1] = s; envi[el * 4 + 3] = 0; }
-    }
-    __syncthreads();
-
     // ---- A1: per charger: loads, empty-port masking, normalisation, work-list compaction -------
+    // Every independent global load of this thread is issued BEFORE the first barrier.
     uint4 h[NPR];
+    ActT araw[NPR];
     double capv[NPR];
     unsigned pushed = 0, asign = 0;      // bit j: port j is a work item / its action is > 0
     int invalid = 0;
     int port0 = 0, n = 0;
+    if (valid) {
+        t = p.env_step[e];
+        s = p.env_scn[e];
+        if (NP > 0) {
+            port0 = p.cs_uniform ? c * NP : p.cs[c].port_off;
+            const size_t pb = (size_t)e * p.P + port0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { h[j] = p.hot[pb + j]; araw[j] = actions[pb + j]; }
+        }
+        live = t < p.T;
+        if (c == 0) { envi[el * 4 + 0] = t; envi[el * 4 + 1] = s; envi[el * 4 + 2] = 0; envi[el * 4 + 3] = 0; }
+    }
+    __syncthreads();
+
     if (valid && live) {
         const CsStatic &cs = cs_of(p, c);
-        port0 = p.cs_uniform ? c * (NP > 0 ? NP : p.cs0.n_ports) : cs.port_off;
+        if (NP == 0) port0 = p.cs_uniform ? c * p.cs0.n_ports : cs.port_off;
         n = NP > 0 ? NP : cs.n_ports;
         const size_t pbase = (size_t)e * p.P + port0;
         double sum = 0.0;
         if (NP > 0) {
             double a[NPR];
 #pragma unroll
-            for (int j = 0; j < NP; ++j) { h[j] = p.hot[pbase + j]; a[j] = (double)actions[pbase + j]; }
+            for (int j = 0; j < NP; ++j) a[j] = (double)araw[j];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const bool occ = hot_t_arr(h[j]) <= t && t <= hot_t_dep(h[j]);
@@ -495,52 +503,85 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     cnt[tid] = rCnt;
     __syncthreads();
 
-    // ---- B: fixed-order reductions: warp per (env, transformer) and per env ---------------------
+    // ---- B: fixed-order reductions.  Three small warp jobs per env, every lane busy: lanes are split
+    //      into (quantity, segment) pairs, each lane sums its segment serially, then a short xor tree.
     {
         const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
-        for (int jel = 0; jel < p.EPB; ++jel) {
+        for (int job = warp; job < 3 * p.EPB; job += nwarps) {
+            const int jel = job / 3, kind = job - jel * 3;
             const int je = blockIdx.x * p.EPB + jel;
-            if (je >= p.E) break;
+            if (je >= p.E) continue;
             const int jt = envi[jel * 4 + 0];
             if (jt >= p.T) continue;
-            const int js = envi[jel * 4 + 1];
-            for (int k = warp; k <= p.Tr; k += nwarps) {
-                if (k < p.Tr) {       // transformer k: Transformer.step accumulation   transformer.py:269-274
-                    double sp_ = 0;
-                    const int i1 = p.tr_cs_off[k + 1];
-                    for (int i = p.tr_cs_off[k] + lane; i < i1; i += 32)
-                        sp_ += red[RedP * NT + jel * p.C + p.tr_cs_idx[i]];
-                    sp_ = warp_sum(sp_);
-                    if (lane == 0) {
+            if (kind == 0) {          // Transformer.step accumulation + overload   transformer.py:264-302
+                const int js = envi[jel * 4 + 1];
+                int nseg = 1;
+                while (nseg * 2 * p.Tr <= 32) nseg *= 2;
+                const int per = 32 / nseg;                              // transformers per pass
+                for (int k0 = 0; k0 < p.Tr; k0 += per) {
+                    const int k = k0 + lane / nseg, seg = lane & (nseg - 1);
+                    double sp_ = 0.0;
+                    if (k < p.Tr && lane / nseg < per) {
+                        const int i0 = p.tr_cs_off[k], n_k = p.tr_cs_off[k + 1] - i0;
+                        const int chunk = (n_k + nseg - 1) / nseg;
+                        const int lo = seg * chunk, hi = min(n_k, lo + chunk);
+                        for (int i = lo; i < hi; ++i) sp_ += red[RedP * NT + jel * p.C + p.tr_cs_idx[i0 + i]];
+                    }
+                    for (int o = nseg >> 1; o > 0; o >>= 1) sp_ += __shfl_xor_sync(0xffffffffu, sp_, o);
+                    if (seg == 0 && k < p.Tr && lane / nseg < per) {
                         const TrT tt = p.tr_t[((size_t)js * p.T + jt) * p.Tr + k];
-                        const double ptot = (tt.infl + tt.solar) + sp_;               // transformer.py:264-265
-                        double ov = 0.0;                                              // transformer.py:284-302
+                        const double ptot = (tt.infl + tt.solar) + sp_;
+                        double ov = 0.0;
                         if (ptot > tt.maxp + 0.0001 || ptot < tt.minp - 0.0001) ov = fabs(ptot - tt.maxp);
                         trov[jel * p.Tr + k] = ov;
                         if (p.out.tr_power)    p.out.tr_power[(size_t)je * p.Tr + k] = ptot;
                         if (p.out.tr_overload) p.out.tr_overload[(size_t)je * p.Tr + k] = ov;
                     }
-                } else {              // env-level sums
-                    double v[kNRed];
-#pragma unroll
-                    for (int q = 0; q < kNRed; ++q) v[q] = 0.0;
-                    int ci = 0, cd = 0, ca = 0;
-                    for (int i = lane; i < p.C; i += 32) {
-                        const int cc = jel * p.C + i;
-#pragma unroll
-                        for (int q = 0; q < kNRed; ++q) v[q] += red[q * NT + cc];
-                        const int w = cnt[cc];
-                        ci += w & 1023; cd += (w >> 10) & 1023; ca += (w >> 20) & 1023;
-                    }
-#pragma unroll
-                    for (int q = 0; q < kNRed; ++q) v[q] = warp_sum(v[q]);
-                    ci = warp_sum_i(ci); cd = warp_sum_i(cd); ca = warp_sum_i(ca);
-                    if (lane == 0) {
-#pragma unroll
-                        for (int q = 0; q < kNRed; ++q) envs[jel * kNRed + q] = v[q];
-                        envi[jel * 4 + 2] = ci | (cd << 10) | (ca << 20);
-                    }
                 }
+            } else if (kind == 1) {   // env-level float64 sums: 7 quantities x 4 segments = 28 lanes
+                const int q = lane >> 2, seg = lane & 3;
+                double v = 0.0;
+                if (q < kNRed) {
+                    const int chunk = (p.C + 3) >> 2;
+                    const int lo = seg * chunk, hi = min(p.C, lo + chunk);
+                    const double *r = red + q * NT + jel * p.C;
+                    for (int i = lo; i < hi; ++i) v += r[i];
+                }
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (q < kNRed && seg == 0) envs[jel * kNRed + q] = v;
+            } else {                  // env-level integer counts: 3 fields x 8 segments = 24 lanes
+                const int q = lane >> 3, seg = lane & 7;
+                int v = 0;
+                if (q < 3) {
+                    const int chunk = (p.C + 7) >> 3;
+                    const int lo = seg * chunk, hi = min(p.C, lo + chunk);
+                    for (int i = lo; i < hi; ++i) v += (cnt[jel * p.C + i] >> (10 * q)) & 1023;
+                }
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (q < 3 && seg == 0) atomicOr(&envi[jel * 4 + 2], v << (10 * q));
+            }
+        }
+    }
+    // ---- D (overlapped with B): coalesced copy-out of the observation rows, header excluded --------
+    const int hdr = p.state_kind == EV2B_STATE_PUBLIC_PST ? 3 : 2;
+    if (want_obs) {
+        for (int jel = 0; jel < p.EPB; ++jel) {
+            const int je = blockIdx.x * p.EPB + jel;
+            if (je >= p.E) break;
+            if (envi[jel * 4 + 0] >= p.T) continue;
+            float *dst = p.out.obs + (size_t)je * p.D;
+            const float *src = obs_s + (size_t)jel * p.D;
+            if ((p.D & 1) == 0) {                 // rows are 8-byte aligned: float2 body, scalar edges
+                const int b0 = (hdr + 1) & ~1;
+                if (tid == 0 && b0 > hdr) dst[hdr] = src[hdr];
+                const float2 *s2 = reinterpret_cast<const float2 *>(src);
+                float2 *d2 = reinterpret_cast<float2 *>(dst);
+                for (int i = (b0 >> 1) + tid; i < (p.D >> 1); i += NT) d2[i] = s2[i];
+            } else {
+                for (int i = hdr + tid; i < p.D; i += NT) dst[i] = src[i];
             }
         }
     }
@@ -589,25 +630,13 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 p.env_usage[je] = usage;
                 p.env_step[je] = jt + 1;
                 if (jt + 1 >= p.T) status |= EV2B_ST_DONE;                     // ev2gym_env.py:460
-                if (want_obs) obs_header(p, obs_s + (size_t)tid * p.D, js, jt + 1, usage);
+                if (want_obs) obs_header(p, p.out.obs + (size_t)je * p.D, js, jt + 1, usage);
             } else {
                 status |= EV2B_ST_DONE | EV2B_ST_WAS_DONE;                     // ev2gym_env.py:343
             }
             if (p.out.reward) p.out.reward[je] = reward;
             if (p.out.total_costs) p.out.total_costs[je] = costs;
             if (p.out.status) p.out.status[je] = status;
-        }
-    }
-    // ---- D: coalesced observation rows -----------------------------------------------------------
-    if (want_obs) {
-        __syncthreads();
-        for (int jel = 0; jel < p.EPB; ++jel) {
-            const int je = blockIdx.x * p.EPB + jel;
-            if (je >= p.E) break;
-            if (envi[jel * 4 + 0] >= p.T) continue;
-            float *dst = p.out.obs + (size_t)je * p.D;
-            const float *src = obs_s + (size_t)jel * p.D;
-            for (int i = tid; i < p.D; i += NT) dst[i] = src[i];
         }
     }
 }
