@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -123,14 +124,18 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
 #ifndef EV2B_MINB
 #define EV2B_MINB 4
 #endif
-    if (h->block <= 256) {
-        if (h->np_uniform == 1) return go(step_kernel<ActT, 1, 256, EV2B_MINB>);
-        if (h->np_uniform == 2) return go(step_kernel<ActT, 2, 256, EV2B_MINB>);
-        return go(step_kernel<ActT, 0, 256, EV2B_MINB>);
-    }
-    if (h->np_uniform == 1) return go(step_kernel<ActT, 1, kMaxThreads, 1>);
-    if (h->np_uniform == 2) return go(step_kernel<ActT, 2, kMaxThreads, 1>);
-    return go(step_kernel<ActT, 0, kMaxThreads, 1>);
+    // uniform charger layout + 1 or 2 ports: the YAML case; everything else takes the generic variant
+    const int np = (h->cs_uniform && (h->np_uniform == 1 || h->np_uniform == 2)) ? h->np_uniform : 0;
+#define EV2B_DISPATCH(MAXT, MINB)                                               \
+    do {                                                                        \
+        if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB>);         \
+        if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB>);         \
+        return go(step_kernel<ActT, 0, false, MAXT, MINB>);                     \
+    } while (0)
+    if (h->block <= 256) EV2B_DISPATCH(256, EV2B_MINB);
+    if (h->block <= 512) EV2B_DISPATCH(512, 2);
+    EV2B_DISPATCH(kMaxThreads, 1);
+#undef EV2B_DISPATCH
 }
 
 extern "C" {
@@ -235,13 +240,17 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     // launch shape: a CTA owns EPB whole envs, one thread per (env, charger)
     {
         int best_epb = 1; double best_u = -1;
-        const int cap_thr = C > 256 ? kMaxThreads : 256;
+        const int cap_thr = C > 256 ? kMaxThreads : (C > 128 ? 256 : 128);   // small CTAs: less barrier skew (measured)
         for (int epb = 1; epb <= 64 && epb <= h->E; ++epb) {
             const int thr = epb * C;
             if (thr > cap_thr) break;
             const int blk = (thr + 31) / 32 * 32;
             const double u = (double)thr / blk;
             if (u > best_u + 1e-9) { best_u = u; best_epb = epb; }
+        }
+        if (const char *ov = getenv("EV2B_EPB")) {          // tuning override (benchmarks only)
+            const int v = atoi(ov);
+            if (v >= 1 && v <= h->E && v * C <= kMaxThreads) best_epb = v;
         }
         h->EPB = best_epb;
         h->block = std::max(32, (best_epb * C + 31) / 32 * 32);

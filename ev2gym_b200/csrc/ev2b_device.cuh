@@ -117,7 +117,11 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
-__device__ __forceinline__ const CsStatic &cs_of(const Params &p, int c) { return p.cs_uniform ? p.cs0 : p.cs[c]; }
+template <bool UNI>
+__device__ __forceinline__ const CsStatic &cs_of(const Params &p, int c) {
+    if (UNI) return p.cs0;          // kernel-parameter constant bank: fields become immediate operands
+    return p.cs[c];
+}
 
 // ---- observation pieces shared by the step and reset kernels --------------------------------
 // Header of the stock state functions at observation time tq (= current_step after the increment).
@@ -260,7 +264,7 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
 
 // ---- the fused step kernel --------------------------------------------------------------------
 // ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = ragged (CsStatic).
-template <typename ActT, int NP, int MAXT, int MINB>
+template <typename ActT, int NP, bool UNI, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         t = p.env_step[e];
         s = p.env_scn[e];
         if (NP > 0) {
-            port0 = p.cs_uniform ? c * NP : p.cs[c].port_off;
+            port0 = UNI ? c * NP : p.cs[c].port_off;
             const size_t pb = (size_t)e * p.P + port0;
 #pragma unroll
             for (int j = 0; j < NP; ++j) { h[j] = p.hot[pb + j]; araw[j] = actions[pb + j]; }
@@ -314,8 +318,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     __syncthreads();
 
     if (valid && live) {
-        const CsStatic &cs = cs_of(p, c);
-        if (NP == 0) port0 = p.cs_uniform ? c * p.cs0.n_ports : cs.port_off;
+        const CsStatic &cs = cs_of<UNI>(p, c);
+        if (NP == 0) port0 = cs.port_off;
         n = NP > 0 ? NP : cs.n_ports;
         const size_t pbase = (size_t)e * p.P + port0;
         double sum = 0.0;
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         for (int i = tid; i < nw; i += NT) {
             const int pl = wl[i];
             const int port = p.EPB == 1 ? pl : pl - (int)__umulhi((unsigned)pl, p.p_magic) * p.P;
-            const CsStatic &cs = cs_of(p, p.cs_uniform ? 0 : p.port_cs[port]);
+            const CsStatic &cs = cs_of<UNI>(p, UNI ? 0 : p.port_cs[port]);
             const uint2 hw = whot[pl];
             double cap = resC[pl], energy, amps;
             const bool active = ev_step_item(p, cs, hw.x, hw.y, resE[pl], cap, energy, amps);
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     double rP = 0, rA = 0, rProfit = 0, rSatExp = 0, rPot = 0, rCh = 0, rDis = 0, rSat = 0;
     int rCnt = invalid;
     if (valid && live) {
-        const CsStatic &cs = cs_of(p, c);
+        const CsStatic &cs = cs_of<UNI>(p, c);
         const EnvT et = p.env_t[(size_t)s * p.T + t];
         const size_t pbase = (size_t)e * p.P + port0;
         const int tq = t + 1;
