@@ -91,10 +91,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(topo, scenarios, reward, state, target_seconds=12.0, threads=0):
+def cpu_baseline(topo, scenarios, reward, state, E, target_seconds=12.0, threads=0):
     """The C oracle (a port of the reference step; the reference itself is Python and cannot travel)."""
     from oracle.oracle import OracleBatch
-    E = 512
     ob = OracleBatch(topo, [scenarios[e % len(scenarios)] for e in range(E)], reward=reward, state=state,
                      threads=threads)
     rng = np.random.default_rng(0)
@@ -109,7 +108,7 @@ def cpu_baseline(topo, scenarios, reward, state, target_seconds=12.0, threads=0)
             ob.reset()
         ob.step(acts[steps % 4])
         steps += 1
-        if steps % 8 == 0 and time.perf_counter() - t0 > target_seconds:
+        if time.perf_counter() - t0 > target_seconds:
             break
     dt = time.perf_counter() - t0
     return {"value": E * steps / dt, "unit": "env-steps/s", "cores": ob.threads, "kind": "port",
@@ -127,7 +126,7 @@ def run_reference(args, wl):
     pack = load_pack(pack_name)
     topo = pack.topo
     from oracle.oracle import OracleBatch
-    Es = 512                                           # bounded sample of the workload's batch per step
+    Es = E                                             # one step = the workload's full batch, as on the GPU
     ob = OracleBatch(topo, [pack.scenarios[e % len(pack)] for e in range(Es)], reward=reward, state=state)
     rng = np.random.default_rng(0)
     low = -1.0 if topo.v2g_enabled else 0.0
@@ -146,7 +145,7 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic actions on reference-exported scenarios",
-        "config": {"workload": desc, "sample": f"{Es} of {E} envs per step"},
+        "config": {"workload": desc, "sample": f"full batch of {Es} envs per step, {args.steps} steps"},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": ob.threads, "kind": "port",
                          "sample": f"C oracle, {Es} envs x {args.steps} steps"},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -297,6 +296,12 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         launch_ms = elapsed_ms / K
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)).get(args.workload)
+            if tj:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         achieved = bytes_env_step * E / (launch_ms * 1e-3) / 1e9
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
@@ -313,13 +318,13 @@ def main():
                     "what": "ev2b_step_host: pinned host actions -> H2D -> fused kernel -> D2H reward+status+obs -> sync"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_env_step,
                          "kernel": "ev2b::step_kernel", "launch_ms": launch_ms},
             "kpi_allreduce": {"total_reward": float(kpi[0].item()), "total_evs_served": float(kpi[5].item())},
         }
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(topo, pack.scenarios, reward, state if D else None)
+            line["cpu_baseline"] = cpu_baseline(topo, pack.scenarios, reward, state if D else None, E)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
