@@ -132,6 +132,10 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
         if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB>);         \
         return go(step_kernel<ActT, 0, false, MAXT, MINB>);                     \
     } while (0)
+#ifndef EV2B_MINB128
+#define EV2B_MINB128 8
+#endif
+    if (h->block <= 128) EV2B_DISPATCH(128, EV2B_MINB128);
     if (h->block <= 256) EV2B_DISPATCH(256, EV2B_MINB);
     if (h->block <= 512) EV2B_DISPATCH(512, 2);
     EV2B_DISPATCH(kMaxThreads, 1);

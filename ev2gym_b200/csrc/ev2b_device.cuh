@@ -28,6 +28,11 @@
 
 namespace ev2b {
 
+#ifndef EV2B_LEAN
+#define EV2B_LEAN 0
+#endif
+#define EV2B_OPT(ptr) (!EV2B_LEAN && (ptr))
+
 constexpr int   kNoArrival = 32767;   // "no (further) session on this port"
 constexpr int   kMaxThreads = 1024;
 constexpr int   kNRed = 7;            // float64 partials per charger, see Red* below
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
     constexpr int NPR = NP > 0 ? NP : 1;
 
-    if (tid == 0) *wcnt = 0;
+    if (tid == 0) { wcnt[0] = 0; wcnt[1] = 0; }   // charge items fill wl from the front, discharge items from the back
     int t = 0, s = 0;
     bool live = false;
     // ---- A1: per charger: loads, empty-port masking, normalisation, work-list compaction -------
@@ -340,8 +345,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 if (sum > 1.0) an = an / sum; else if (sum < -1.0) an = -an / sum;     // :143-149
                 if (an != 0.0) {                                         // occupied and a non-zero request
                     const int pl = el * p.P + port0 + j;
-                    const int slot = atomicAdd(wcnt, 1);
-                    wl[slot] = pl;
+                    if (an > 0.0) wl[atomicAdd(&wcnt[0], 1)] = pl;
+                    else          wl[PP - 1 - atomicAdd(&wcnt[1], 1)] = pl;
                     resE[pl] = an; resC[pl] = capv[j]; whot[pl] = make_uint2(h[j].z, h[j].w);
                     pushed |= 1u << j;
                     if (an > 0.0) asign |= 1u << j;
@@ -362,8 +367,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 const int pl = el * p.P + port0 + j;
                 signed char f = 0;
                 if (an != 0.0) {
-                    const int slot = atomicAdd(wcnt, 1);
-                    wl[slot] = pl;
+                    if (an > 0.0) wl[atomicAdd(&wcnt[0], 1)] = pl;
+                    else          wl[PP - 1 - atomicAdd(&wcnt[1], 1)] = pl;
                     resE[pl] = an; resC[pl] = p.cap[pbase + j]; whot[pl] = make_uint2(hj.z, hj.w);
                     f = an > 0.0 ? 1 : -1;
                 }
@@ -387,9 +392,12 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
 
     // ---- A2: the float64 battery model on the compacted work list (dense warps) ----------------
     {
-        const int nw = *wcnt;
-        for (int i = tid; i < nw; i += NT) {
-            const int pl = wl[i];
+        // two passes so that a warp runs either the charge or the discharge model, not both
+        const int n_ch = wcnt[0], n_dis = wcnt[1];
+        const int n_ch_pad = (n_ch + 31) & ~31;                        // discharge items start on a warp boundary
+        for (int i = tid; i < n_ch_pad + n_dis; i += NT) {
+            if (i >= n_ch && i < n_ch_pad) continue;
+            const int pl = i < n_ch ? wl[i] : wl[PP - 1 - (i - n_ch_pad)];
             const int port = p.EPB == 1 ? pl : pl - (int)__umulhi((unsigned)pl, p.p_magic) * p.P;
             const CsStatic &cs = cs_of<UNI>(p, UNI ? 0 : p.port_cs[port]);
             const uint2 hw = whot[pl];
@@ -443,7 +451,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 rA += resA[pl];                                           // :181,197
             }
             if (rA - 0.0001 > cs.imax) overflow = true;                   // :203-205
-            if (p.out.port_energy) p.out.port_energy[ip] = (float)energy;
+            if (EV2B_OPT(p.out.port_energy)) p.out.port_energy[ip] = (float)energy;
 
             // departure (charger step counter == t)        ev_charger.py:209-224, ev.py:199-214
             double dsat = __longlong_as_double(0x7ff8000000000000LL), dcap = dsat;
@@ -455,8 +463,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 rCnt += 1 << 10;
                 dsat = sat; dcap = cv;
             }
-            if (p.out.dep_sat) p.out.dep_sat[ip] = dsat;
-            if (p.out.dep_cap) p.out.dep_cap[ip] = dcap;
+            if (EV2B_OPT(p.out.dep_sat)) p.out.dep_sat[ip] = dsat;
+            if (EV2B_OPT(p.out.dep_cap)) p.out.dep_cap[ip] = dcap;
 
             // arrival of the next session at t+1            ev2gym_env.py:399-417, ev_charger.py:266-285
             if (hot_next_arr(hj) == tq) {
@@ -497,8 +505,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         if (rPot > cs.max_power) rPot = cs.max_power;
         else if (rPot < cs.min_power) rPot = 0.0;
         if (overflow) atomicOr(&envi[el * 4 + 3], (int)EV2B_ST_AMPS_OVERFLOW);
-        if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
-        if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
+        if (EV2B_OPT(p.out.cs_power))   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
+        if (EV2B_OPT(p.out.cs_current)) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
     }
     red[RedP * NT + tid] = rP;             red[RedProfit * NT + tid] = rProfit;
     red[RedSatExp * NT + tid] = rSatExp;   red[RedPot * NT + tid] = rPot;
@@ -538,8 +546,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                         double ov = 0.0;
                         if (ptot > tt.maxp + 0.0001 || ptot < tt.minp - 0.0001) ov = fabs(ptot - tt.maxp);
                         trov[jel * p.Tr + k] = ov;
-                        if (p.out.tr_power)    p.out.tr_power[(size_t)je * p.Tr + k] = ptot;
-                        if (p.out.tr_overload) p.out.tr_overload[(size_t)je * p.Tr + k] = ov;
+                        if (EV2B_OPT(p.out.tr_power))    p.out.tr_power[(size_t)je * p.Tr + k] = ptot;
+                        if (EV2B_OPT(p.out.tr_overload)) p.out.tr_overload[(size_t)je * p.Tr + k] = ov;
                     }
                 }
             } else if (kind == 1) {   // env-level float64 sums: 7 quantities x 4 segments = 28 lanes
@@ -639,7 +647,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 status |= EV2B_ST_DONE | EV2B_ST_WAS_DONE;                     // ev2gym_env.py:343
             }
             if (p.out.reward) p.out.reward[je] = reward;
-            if (p.out.total_costs) p.out.total_costs[je] = costs;
+            if (EV2B_OPT(p.out.total_costs)) p.out.total_costs[je] = costs;
             if (p.out.status) p.out.status[je] = status;
         }
     }
