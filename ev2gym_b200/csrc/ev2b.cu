@@ -50,6 +50,7 @@ struct ev2b_handle {
     size_t smem = 0;
     std::string err;
     int64_t launches = 0;
+    const float *last_obs = nullptr;    // obs buffer whose rows are known to be current (incremental obs writes)
     // host copies of the static layout (needed to pack scenarios)
     std::vector<CsStatic> cs_h;
     std::vector<int> port_cs;           // port -> charger
@@ -261,7 +262,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         const size_t PP = (size_t)h->EPB * h->P;
         h->smem = sizeof(double) * ((size_t)kNRed * h->block + 3 * PP + (size_t)h->EPB * h->Tr + (size_t)h->EPB * kNRed) +
                   sizeof(uint2) * PP + sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4 + PP + 4 + 1) +
-                  sizeof(float) * (size_t)h->EPB * h->D + PP + 16;
+                  PP + 16;
     }
 #define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
         g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e); delete h; return EV2B_E_CUDA; } } while (0)
@@ -474,6 +475,7 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
     CUDA_TRY(h, h->pot_kw.upload(pot_kw)); CUDA_TRY(h, h->trA.upload(trA)); CUDA_TRY(h, h->trF.upload(trF));
     CUDA_TRY(h, h->tr_limit.upload(tr_limit)); CUDA_TRY(h, h->dr.upload(dr)); CUDA_TRY(h, h->dr_count.upload(dr_count));
     h->S = S; h->Smax = Smax; h->n_dr = n_dr; h->lut_len = lut_len;
+    h->last_obs = nullptr;
     h->obs_static.release();
     if (h->W > 0) {   // precompute the (scenario, time)-only observation values when the table is small enough
         const size_t n = (size_t)S * (T + 1) * h->W;
@@ -522,6 +524,8 @@ int ev2b_reset(ev2b_handle *h, int env_lo, int env_hi, const int32_t *scn_ids, f
         CUDA_TRY(h, cudaStreamSynchronize(st));   // scn_ids is a caller-owned (possibly pageable) host buffer
         scn_dev = h->st_scn.p;
     }
+    if (obs0 == nullptr || obs0 != h->last_obs) h->last_obs = nullptr;   // rows of this buffer are not all current
+    if (obs0 != nullptr && env_lo == 0 && env_hi == h->E) h->last_obs = obs0;
     return launch_reset(h, env_lo, env_hi, scn_dev, 0, obs0, st);
 }
 
@@ -529,6 +533,7 @@ int ev2b_reset_done(ev2b_handle *h, float *obs0, void *stream) {
     if (!h) return EV2B_E_ARG;
     if (h->S == 0) return h->fail(EV2B_E_STATE, "reset_done: no scenario bank loaded");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    if (obs0 == nullptr || obs0 != h->last_obs) h->last_obs = nullptr;
     return launch_reset(h, 0, h->E, nullptr, 1, obs0, (cudaStream_t)stream);
 }
 
@@ -538,6 +543,8 @@ int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_
     Params p = h->params();
     p.actions = actions;
     if (out) p.out = *out;
+    p.obs_full = (p.out.obs != h->last_obs) ? 1 : 0;
+    h->last_obs = p.out.obs;
     cudaError_t e;
     if (action_dtype == EV2B_F32) e = launch_step<float>(h, p, (cudaStream_t)stream);
     else if (action_dtype == EV2B_F64) e = launch_step<double>(h, p, (cudaStream_t)stream);

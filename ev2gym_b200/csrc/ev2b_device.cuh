@@ -76,6 +76,8 @@ struct Params {
     // sizes
     int E, C, P, Tr, T, D, EPB, n_dr, lut_len, Smax, S, n_cls, W;
     int reward_kind, state_kind, dr_steps_ahead;
+    int obs_full;            // 1: rewrite every observation entry; 0: the caller's obs buffer still holds last step's
+                             //    rows, only entries that can change are written (occupied ports, header, series)
     double c60, rc60;        // 60 / timescale (ev.py:296) and its reciprocal
     double p60, rp60;        // timescale / 60 (ev.py:355)
     double period, rperiod;  // timescale
@@ -285,8 +287,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     int    *envi  = cnt + NT;                                             // [EPB][4] t, scn, cnt, flags
     int    *wl    = envi + (size_t)p.EPB * 4;                             // [PP] work list (port_local)
     int    *wcnt  = wl + PP;                                              // [1] (+3 pad)
-    float  *obs_s = reinterpret_cast<float *>(wcnt + 4 + ((NT + PP) & 1));   // [EPB][D], 8-byte aligned
-    signed char *pflag = reinterpret_cast<signed char *>(obs_s + (size_t)p.EPB * p.D);   // [PP] ragged path only
+    signed char *pflag = reinterpret_cast<signed char *>(wcnt + 4);       // [PP] ragged path only
 
     const int tid = threadIdx.x;
     const int el = p.C == 1 ? tid : (int)__umulhi((unsigned)tid, p.c_magic);   // tid / C
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             if (jt >= p.T) continue;
             const int js = envi[jel * 4 + 1];
             for (int i = tid; i < p.W; i += NT)
-                obs_s[(size_t)jel * p.D + p.series_off[i]] = obs_series_fetch(p, js, jt + 1, i);
+                p.out.obs[(size_t)je * p.D + p.series_off[i]] = obs_series_fetch(p, js, jt + 1, i);
         }
     }
     __syncthreads();
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         const EnvT et = p.env_t[(size_t)s * p.T + t];
         const size_t pbase = (size_t)e * p.P + port0;
         const int tq = t + 1;
-        float *obs_row = obs_s + (size_t)el * p.D;
+        float *obs_row = p.out.obs + (size_t)e * p.D;      // observation rows live in the caller's buffer across steps
         bool overflow = false;
 #pragma unroll
         for (int j = 0; j < (NP > 0 ? NP : n); ++j) {
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                         o[1] = (float)(hot_t_dep(hj) - tq);
                     }
                 }
-            } else if (want_obs) {
+            } else if (want_obs && (occ || p.obs_full)) {     // the port just emptied (or a full rewrite was asked for)
                 float *o = obs_row + p.obs_slot[port0 + j];
                 o[0] = 0.f; o[1] = 0.f;
                 if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
@@ -574,26 +575,6 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 if (q < 3 && seg == 0) atomicOr(&envi[jel * 4 + 2], v << (10 * q));
-            }
-        }
-    }
-    // ---- D (overlapped with B): coalesced copy-out of the observation rows, header excluded --------
-    const int hdr = p.state_kind == EV2B_STATE_PUBLIC_PST ? 3 : 2;
-    if (want_obs) {
-        for (int jel = 0; jel < p.EPB; ++jel) {
-            const int je = blockIdx.x * p.EPB + jel;
-            if (je >= p.E) break;
-            if (envi[jel * 4 + 0] >= p.T) continue;
-            float *dst = p.out.obs + (size_t)je * p.D;
-            const float *src = obs_s + (size_t)jel * p.D;
-            if ((p.D & 1) == 0) {                 // rows are 8-byte aligned: float2 body, scalar edges
-                const int b0 = (hdr + 1) & ~1;
-                if (tid == 0 && b0 > hdr) dst[hdr] = src[hdr];
-                const float2 *s2 = reinterpret_cast<const float2 *>(src);
-                float2 *d2 = reinterpret_cast<float2 *>(dst);
-                for (int i = (b0 >> 1) + tid; i < (p.D >> 1); i += NT) d2[i] = s2[i];
-            } else {
-                for (int i = hdr + tid; i < p.D; i += NT) dst[i] = src[i];
             }
         }
     }
