@@ -26,7 +26,8 @@ _pl, _pu, _pb = C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8
 class Dims(C.Structure):
     _fields_ = [("n_envs", C.c_int32), ("n_chargers", C.c_int32), ("n_transformers", C.c_int32),
                 ("sim_length", C.c_int32), ("timescale", C.c_int32), ("dr_steps_ahead", C.c_int32),
-                ("reward_kind", C.c_int32), ("state_kind", C.c_int32), ("tr_voltage", C.c_double)]
+                ("reward_kind", C.c_int32), ("state_kind", C.c_int32), ("tr_voltage", C.c_double),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class TopologyView(C.Structure):
@@ -66,7 +67,7 @@ class StateView(C.Structure):
 
 EXPORTS = ("ev2b_abi_version", "ev2b_last_error", "ev2b_create", "ev2b_destroy", "ev2b_obs_dim", "ev2b_n_ports",
            "ev2b_load_scenarios", "ev2b_n_scenarios", "ev2b_reset", "ev2b_step", "ev2b_step_host",
-           "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count")
+           "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count", "ev2b_episode_stats")
 
 
 def needs_build() -> bool:
@@ -127,6 +128,8 @@ def load():
     L.ev2b_reset_done.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ev2b_state_view_get.restype = C.c_int
     L.ev2b_state_view_get.argtypes = [C.c_void_p, C.POINTER(StateView)]
+    L.ev2b_episode_stats.restype = C.c_int
+    L.ev2b_episode_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ev2b_launch_count.restype = C.c_int64
     L.ev2b_launch_count.argtypes = [C.c_void_p]
     if L.ev2b_abi_version() != 1:

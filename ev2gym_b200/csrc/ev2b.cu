@@ -66,6 +66,10 @@ struct ev2b_handle {
     // device: state
     DevBuf<uint4> hot; DevBuf<double> cap; DevBuf<float> exch; DevBuf<int> env_step, env_scn;
     DevBuf<double> env_pot, env_usage, env_kpi;
+    // device: statistics mode
+    int L = 1;
+    DevBuf<double> st_soc_sum, st_abs_e, st_act, st_r, cs_sat_sum, cs_dcal, cs_dcyc;
+    DevBuf<int> st_cnt, st_nfin, cs_served, cs_em;
     // e2e staging (ev2b_step_host)
     DevBuf<unsigned char> st_actions; DevBuf<double> st_reward; DevBuf<uint32_t> st_status; DevBuf<float> st_obs;
     DevBuf<int> st_scn;
@@ -86,6 +90,16 @@ struct ev2b_handle {
         p.p_magic = P > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)P) + 1u : 0u;
         p.c_magic = C > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)C) + 1u : 0u;
         p.cs_uniform = cs_uniform; p.cs0 = cs_h.empty() ? CsStatic{} : cs_h[0];
+        p.stats = (dims.flags & EV2B_F_STATS) ? 1 : 0; p.L = L;
+        {   // ev.py:456-516 constants
+            const double b_age = 2 * 365, d_dist = 15000, Gk = 0.186, b_cap_ah = 2.05, b_cap_kwh = 78;
+            const double q_acc = 2 * (b_age * (d_dist / 365) * Gk * b_cap_ah) / b_cap_kwh;
+            p.k_cal = 0.75 / std::pow(b_age, 0.25); p.k_exp = std::exp(-6976.0 / 298.15);
+            p.k_cyc = 0.5 * b_cap_ah / std::pow(q_acc, 0.5);
+        }
+        p.st_soc_sum = st_soc_sum.p; p.st_abs_e = st_abs_e.p; p.st_act = st_act.p; p.st_r = st_r.p;
+        p.st_cnt = st_cnt.p; p.st_nfin = st_nfin.p; p.cs_sat_sum = cs_sat_sum.p; p.cs_dcal = cs_dcal.p;
+        p.cs_dcyc = cs_dcyc.p; p.cs_served = cs_served.p; p.cs_em = cs_em.p;
         p.port_cs = port_cs_d.p; p.series_off = series_off.p; p.obs_static = obs_static.p;
         p.cs = cs.p; p.tr_cs_off = tr_cs_off.p; p.tr_cs_idx = tr_cs_idx.p; p.obs_slot = obs_slot.p; p.tr_obs_off = tr_obs_off.p;
         p.env_t = env_t.p; p.tr_t = tr_t.p; p.sess = sess.p; p.spec = spec.p; p.luts_c = luts_c.p; p.luts_d = luts_d.p;
@@ -127,12 +141,18 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
 #endif
     // uniform charger layout + 1 or 2 ports: the YAML case; everything else takes the generic variant
     const int np = (h->cs_uniform && (h->np_uniform == 1 || h->np_uniform == 2)) ? h->np_uniform : 0;
-#define EV2B_DISPATCH(MAXT, MINB)                                               \
-    do {                                                                        \
-        if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB>);         \
-        if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB>);         \
-        return go(step_kernel<ActT, 0, false, MAXT, MINB>);                     \
+#define EV2B_DISPATCH(MAXT, MINB)                                                       \
+    do {                                                                                \
+        if (stats) {                                                                    \
+            if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB, true>);       \
+            if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, true>);       \
+            return go(step_kernel<ActT, 0, false, MAXT, MINB, true>);                   \
+        }                                                                               \
+        if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB, false>);          \
+        if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, false>);          \
+        return go(step_kernel<ActT, 0, false, MAXT, MINB, false>);                      \
     } while (0)
+    const bool stats = (h->dims.flags & EV2B_F_STATS) != 0;
 #ifndef EV2B_MINB128
 #define EV2B_MINB128 8
 #endif
@@ -370,6 +390,7 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
         }
     }
     if (Smax > 255) return h->fail(EV2B_E_LIMIT, "more than 255 sessions on one port");
+    int Lmax = 2;
     SessRec empty{};
     empty.hot.x = ((unsigned)kNoArrival & 0xFFFFu) | (0xFFFFu << 16);
     empty.hot.y = (unsigned)kNoArrival & 0xFFFFu;
@@ -411,6 +432,25 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
             rec.hot.z = (unsigned)it->second | (tsm << 16);
             rec.hot.w = ecm | (edm << 16);
             rec.cap0 = b->s_cap0[r];
+            {   // EV.calculate_max_energy_with_AFAP(cs.get_max_power())   ev.py:407-440, ev_charger.py:251-252,279
+                const CsStatic &cs = h->cs_h[b->s_loc[r]];
+                const double max_cs_power = cs.imax * (cs.veff[1]) * std::sqrt((double)cs.phases) / 1000.0;
+                const double max_power = std::fabs(max_cs_power) > std::fabs(sp.pmax_ac) ? sp.pmax_ac : max_cs_power;
+                double eff = b->s_eta_c[r];
+                if (b->s_lut[r] >= 0) {
+                    const double *l = b->luts_c + (b->lut_off[i] + b->s_lut[r]) * lut_len;
+                    double m = 0; for (int q = 0; q < lut_len; ++q) m = std::max(m, l[q]);
+                    eff = m / 100.0;
+                }
+                double afap = b->s_cap0[r];
+                for (int q = b->s_t_arr[r]; q < b->s_t_dep[r] + 1; ++q) {
+                    afap += max_power * eff * (double)h->dims.timescale / 60.0;
+                    afap = std::ceil(afap * 100.0) / 100.0;
+                    if (afap > sp.B) { afap = sp.B; break; }
+                }
+                rec.afap = afap;
+                Lmax = std::max(Lmax, std::min(td, T) - ta + 3);
+            }
             if (last_of_port[pl.port] >= 0) {
                 SessRec &prev = sess[((size_t)i * P + pl.port) * Smax + last_of_port[pl.port]];
                 prev.hot.y = (prev.hot.y & 0xFFFF0000u) | ((unsigned)ta & 0xFFFFu);
@@ -476,6 +516,16 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
     CUDA_TRY(h, h->tr_limit.upload(tr_limit)); CUDA_TRY(h, h->dr.upload(dr)); CUDA_TRY(h, h->dr_count.upload(dr_count));
     h->S = S; h->Smax = Smax; h->n_dr = n_dr; h->lut_len = lut_len;
     h->last_obs = nullptr;
+    if (h->dims.flags & EV2B_F_STATS) {
+        h->L = std::max(2, std::min(Lmax, T + 2));
+        const size_t EP = (size_t)h->E * P, EC = (size_t)h->E * C;
+        CUDA_TRY(h, h->st_soc_sum.alloc(EP)); CUDA_TRY(h, h->st_abs_e.alloc(EP)); CUDA_TRY(h, h->st_cnt.alloc(EP));
+        CUDA_TRY(h, h->st_nfin.alloc(EP)); CUDA_TRY(h, h->st_act.alloc(EP * h->L)); CUDA_TRY(h, h->st_r.alloc(EP * Smax));
+        CUDA_TRY(h, h->cs_sat_sum.alloc(EC)); CUDA_TRY(h, h->cs_dcal.alloc(EC)); CUDA_TRY(h, h->cs_dcyc.alloc(EC));
+        CUDA_TRY(h, h->cs_served.alloc(EC)); CUDA_TRY(h, h->cs_em.alloc(EC));
+        CUDA_TRY(h, cudaMemset(h->st_cnt.p, 0, EP * sizeof(int))); CUDA_TRY(h, cudaMemset(h->st_nfin.p, 0, EP * sizeof(int)));
+        CUDA_TRY(h, cudaMemset(h->cs_served.p, 0, EC * sizeof(int))); CUDA_TRY(h, cudaMemset(h->cs_em.p, 0, EC * sizeof(int)));
+    }
     h->obs_static.release();
     if (h->W > 0) {   // precompute the (scenario, time)-only observation values when the table is small enough
         const size_t n = (size_t)S * (T + 1) * h->W;
@@ -574,6 +624,17 @@ int ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype, d
     if (status_host) CUDA_TRY(h, cudaMemcpyAsync(status_host, h->st_status.p, sizeof(uint32_t) * h->E, cudaMemcpyDeviceToHost, st));
     if (out.obs) CUDA_TRY(h, cudaMemcpyAsync(obs_host, h->st_obs.p, sizeof(float) * (size_t)h->E * h->D, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    return EV2B_OK;
+}
+
+int ev2b_episode_stats(ev2b_handle *h, double *out, void *stream) {
+    if (!h || !out) return h ? h->fail(EV2B_E_ARG, "episode_stats: null output") : EV2B_E_ARG;
+    if (!(h->dims.flags & EV2B_F_STATS)) return h->fail(EV2B_E_STATE, "episode_stats: handle was created without EV2B_F_STATS");
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "episode_stats: no scenario bank loaded");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    episode_stats_kernel<<<h->E, 32, 0, (cudaStream_t)stream>>>(h->params(), out);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
     return EV2B_OK;
 }
 

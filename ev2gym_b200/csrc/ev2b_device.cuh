@@ -65,7 +65,7 @@ static_assert(sizeof(EvSpec) == 128, "EvSpec must be 128 B");
 //   w.w = eta_c_milli (u16) | eta_d_milli (u16) << 16
 // A port is occupied at step t iff t_arr <= t <= t_dep (the EV is charged in step t_dep and then
 // leaves, ev_charger.py:209-224).
-struct SessRec { uint4 hot; double cap0; double pad; };   // cold table, read once per arrival
+struct SessRec { uint4 hot; double cap0; double afap; };  // cold table, read once per arrival; afap: ev.py:407-440
 static_assert(sizeof(SessRec) == 32, "SessRec must be 32 B");
 
 struct EnvT { double cp, dp, setpoint, pad; };            // per (scenario, t)
@@ -93,6 +93,12 @@ struct Params {
     const double *luts_c, *luts_d; const double *pot_kw;
     const float *trA, *trF, *tr_limit; const DrEv *dr; const uint8_t *dr_count;
     const float *obs_static;   // [S][T+1][W] precomputed price window + forecast/limit blocks, or null
+    // statistics mode (EV2B_F_STATS): per-EV histories for get_statistics  utils.py:12-123, ev.py:442-521
+    int stats, L;              // L: trace slots per port (longest session + 2)
+    double k_cal, k_exp, k_cyc; // 0.75/730^0.25, exp(-e2/theta), 0.5*(2.05/78)/sqrt(Q_acc)
+    double *st_soc_sum, *st_abs_e, *st_act, *st_r;   // [E,P], [E,P], [E,P,L], [E,P,Smax]
+    int *st_cnt, *st_nfin;     // [E,P] n_hist | n_act << 16 ; finalised sessions on the port
+    double *cs_sat_sum, *cs_dcal, *cs_dcyc; int *cs_served, *cs_em;   // [E,C]
     // state
     uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;
     double *env_kpi;
@@ -187,9 +193,11 @@ __global__ void obs_static_kernel(const Params p, float *table) {
 // ---- A2: EV.step for one work item ------------------------------------------------------------
 // a = normalised action (non-zero), cap = battery level, hz/hw = hot words z/w of the session.
 // Returns through (energy, act_amps, cap); result = the EV saw non-zero amps (ev.py:158).
+template <bool STATS>
 __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs, const unsigned hz, const unsigned hw,
-                                             const double a, double &cap, double &energy, double &act_amps) {
-    energy = 0.0; act_amps = 0.0;
+                                             const double a, double &cap, double &energy, double &act_amps,
+                                             bool &em_cross) {
+    energy = 0.0; act_amps = 0.0; em_cross = false;
     const double action = ev2b_div_c(rint(a * 100000.0), 100000.0, 1e-5);          // round(action, 5)  ev_charger.py:157
     if (action == 0.0) return false;
     const EvSpec *sp = p.spec + (hz & 0xFFFFu);
@@ -255,6 +263,7 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
         double given_power = ev2b_div_c(amps * veff, 1000.0, 0.001);               // :367
         if (fabs(given_power) > fabs(pmd)) given_power = pmd;                      // :370-371
         double given_energy = ev2b_div_c(given_power * eta * p.period, 60.0, 1.0 / 60.0);   // :381
+        const double prev_cap = cap;
         if (cap + given_energy < bmin) {                                           // :382-393
             if (cap > bmin) { energy = -(cap - bmin); given_energy = energy; }
             else { energy = 0.0; given_energy = 0.0; }
@@ -263,15 +272,46 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
             energy = given_energy;
             cap += given_energy;
         }
+        if (STATS) { const double be = __ldg(&sp->bmin_em); em_cross = prev_cap > be && cap < be; }   // :401-402
         act_amps = ev2b_div_c(ev2b_div_c(given_energy * 60.0, p.period, p.rperiod) * 1000.0, veff, rveff);   // :405
     }
     cap = ev2b_div_c(ceil(cap * 100.0), 100.0, 0.01);                              // my_ceil  ev.py:183,188-189
     return true;
 }
 
+// ---- statistics mode: what EV.get_battery_degradation / get_statistics need of one EV ----------
+// Called when the EV leaves (or at the last step for EVs still connected).  ev.py:442-521, utils.py:49-63
+__device__ __noinline__ void finalize_ev(const Params &p, size_t ip, int e_c, const EvSpec *sp, double afap,
+                                         int t_arr, int t_dep, double cap_final) {
+    const double e0 = 7.543e6, e1 = 23.75e6, z0 = 7.348e-3, z1 = 3.667, z2 = 7.6e-4, z3 = 4.081e-3;
+    const double k = 0.8263, v_min = 3.3324, b_cap_kwh = 78;
+    const double B = __ldg(&sp->B);
+    const double final_soc = cap_final / B;
+    const int cnt = p.st_cnt[ip], n_hist = cnt & 0xFFFF, n_act = cnt >> 16;
+    const double T_sim = (double)(t_dep - t_arr + 1) * p.period / (60.0 * 24.0);
+    const double avg_soc = (p.st_soc_sum[ip] + final_soc) / (double)(n_hist + 1);
+    const double alpha = (e0 * (v_min + k * avg_soc) - e1) * p.k_exp;
+    const double d_cal = alpha * T_sim * p.k_cal;
+    const double *f = p.st_act + ip * (size_t)p.L;
+    double fsum = final_soc;
+    for (int j = 0; j < n_act; ++j) fsum += f[j];
+    const double avg_f = fsum / (double)(n_act + 1);
+    double dev = fabs(avg_f - final_soc);
+    for (int j = 0; j < n_act; ++j) dev += fabs(avg_f - f[j]);
+    const double delta_dod = 2.0 * (dev / (double)(n_act + 1));
+    const double v_half = v_min + k * 0.5;
+    const double beta = z0 * (v_half - z1) * (v_half - z1) + z2 + z3 * delta_dod;
+    const double d_cyc = beta * (p.st_abs_e[ip] / b_cap_kwh) * p.k_cyc;
+    p.cs_dcal[e_c] += d_cal;
+    p.cs_dcyc[e_c] += d_cyc;
+    const int k_fin = p.st_nfin[ip];
+    p.st_r[ip * (size_t)p.Smax + k_fin] = (cap_final / afap) * 100.0;      // utils.py:59-62
+    p.st_nfin[ip] = k_fin + 1;
+}
+
 // ---- the fused step kernel --------------------------------------------------------------------
 // ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = ragged (CsStatic).
-template <typename ActT, int NP, bool UNI, int MAXT, int MINB>
+template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool STATS>
 __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
@@ -403,7 +443,12 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             const CsStatic &cs = cs_of<UNI>(p, UNI ? 0 : p.port_cs[port]);
             const uint2 hw = whot[pl];
             double cap = resC[pl], energy, amps;
-            const bool active = ev_step_item(p, cs, hw.x, hw.y, resE[pl], cap, energy, amps);
+            bool em_cross;
+            const bool active = ev_step_item<STATS>(p, cs, hw.x, hw.y, resE[pl], cap, energy, amps, em_cross);
+            if (STATS && em_cross) {   // min_emergency_battery_capacity_metric  ev.py:401-402 (integer atomics: order-free)
+                const int jel = p.EPB == 1 ? 0 : (int)__umulhi((unsigned)pl, p.p_magic);
+                atomicAdd(&p.cs_em[(size_t)(blockIdx.x * p.EPB + jel) * p.C + p.port_cs[port]], 1);
+            }
             resE[pl] = energy; resA[pl] = amps;
             resC[pl] = active ? cap : -1.0;                              // EV saw amps == 0: nothing changes (ev.py:158-163)
         }
@@ -433,7 +478,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 cv = (hot_t_arr(hj) <= t && t <= hot_t_dep(hj)) ? p.cap[ip] : 0.0;
             }
             const bool occ = hot_t_arr(hj) <= t && t <= hot_t_dep(hj);
-            double energy = 0.0;
+            double energy = 0.0, act_amps = 0.0;
+            const double cv_old = cv;
             float exch_new = 0.f; bool exch_valid = false;
             if (was_item) {
                 energy = resE[pl];
@@ -449,9 +495,22 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 if (apos) { rProfit += ae * et.cp; rCh += ae; }           // ev_charger.py:178-179
                 else      { rProfit += ae * et.dp; rDis += ae; }          // ev_charger.py:194-195
                 rP += ev2b_div_c(energy * 60.0, p.period, p.rperiod);     // :180,196
-                rA += resA[pl];                                           // :181,197
+                act_amps = resA[pl];
+                rA += act_amps;                                           // :181,197
             }
             if (rA - 0.0001 > cs.imax) overflow = true;                   // :203-205
+            if (STATS && occ) {      // EV.step bookkeeping: historic_soc / active_steps / |energy|  ev.py:156,178-185
+                const EvSpec *sq = p.spec + hot_spec(hj);
+                const double soc0 = ev2b_div_c(cv_old, __ldg(&sq->B), __ldg(&sq->rB));
+                int cn = p.st_cnt[ip];
+                p.st_soc_sum[ip] += soc0;
+                if (was_item && act_amps != 0.0) {
+                    p.st_act[ip * (size_t)p.L + (cn >> 16)] = soc0;
+                    cn += 1 << 16;
+                }
+                if (was_item) p.st_abs_e[ip] += fabs(energy);
+                p.st_cnt[ip] = cn + 1;
+            }
             if (EV2B_OPT(p.out.port_energy)) p.out.port_energy[ip] = (float)energy;
 
             // departure (charger step counter == t)        ev_charger.py:209-224, ev.py:199-214
@@ -463,6 +522,12 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 rSat += sat;
                 rCnt += 1 << 10;
                 dsat = sat; dcap = cv;
+                if (STATS) {
+                    const size_t ec = (size_t)e * p.C + c;
+                    p.cs_sat_sum[ec] += sat; p.cs_served[ec] += 1;          // ev_charger.py:218-220
+                    const SessRec r0 = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj) - 1];
+                    finalize_ev(p, ip, (int)ec, p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj), hot_t_dep(hj), cv);
+                }
             }
             if (EV2B_OPT(p.out.dep_sat)) p.out.dep_sat[ip] = dsat;
             if (EV2B_OPT(p.out.dep_cap)) p.out.dep_cap[ip] = dcap;
@@ -477,9 +542,15 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 p.exch[ip] = 0.f;
                 exch_new = 0.f; exch_valid = true;
                 rCnt += 1 << 20;
+                if (STATS) { p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0; }
             }
             const bool occ_after = hot_t_arr(hj) <= tq && tq <= hot_t_dep(hj);
             if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;          // ev2gym_env.py:452-457
+            if (STATS && occ_after && tq >= p.T) {   // episode over: EVs still connected count too (env.EVs)
+                const SessRec r0 = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj) - 1];
+                finalize_ev(p, ip, (int)((size_t)e * p.C + c), p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj),
+                            hot_t_dep(hj), cv);
+            }
             if (occ_after) {
                 const EvSpec *sp = p.spec + hot_spec(hj);
                 const double B = __ldg(&sp->B);
@@ -657,6 +728,10 @@ __global__ void reset_ports_kernel(const Params p, int lo, int hi, const int *sc
     p.hot[(size_t)e * p.P + port] = h;
     p.cap[(size_t)e * p.P + port] = 0.0;
     p.exch[(size_t)e * p.P + port] = 0.f;
+    if (p.stats) {
+        const size_t ip = (size_t)e * p.P + port;
+        p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0; p.st_nfin[ip] = 0;
+    }
 }
 
 // Per-env part of reset() + first observation.  Must run AFTER reset_ports_kernel (same stream).
@@ -689,6 +764,50 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
         p.env_step[e] = 0; p.env_scn[e] = s; p.env_pot[e] = 0.0; p.env_usage[e] = 0.0;
         for (int k = 0; k < EV2B_KPI_COUNT; ++k) p.env_kpi[(size_t)e * EV2B_KPI_COUNT + k] = 0.0;
     }
+    if (p.stats)
+        for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+            const size_t ec = (size_t)e * p.C + c;
+            p.cs_sat_sum[ec] = 0.0; p.cs_dcal[ec] = 0.0; p.cs_dcyc[ec] = 0.0; p.cs_served[ec] = 0; p.cs_em[ec] = 0;
+        }
+}
+
+// ---- get_statistics(env)  utils.py:12-123: one CTA per env, fixed-order sums by thread 0 ----------
+__global__ void episode_stats_kernel(const Params p, double *out) {
+    const int e = blockIdx.x;
+    if (e >= p.E || threadIdx.x != 0) return;
+    const double *kpi = p.env_kpi + (size_t)e * EV2B_KPI_COUNT;
+    double *o = out + (size_t)e * EV2B_STAT_COUNT;
+    double avg_sum = 0, dcal = 0, dcyc = 0; int n_cs = 0, em = 0;
+    for (int c = 0; c < p.C; ++c) {
+        const size_t ec = (size_t)e * p.C + c;
+        if (p.cs_served[ec] > 0) { avg_sum += p.cs_sat_sum[ec] / (double)p.cs_served[ec]; ++n_cs; }   // utils.py:21-23
+        dcal += p.cs_dcal[ec]; dcyc += p.cs_dcyc[ec]; em += p.cs_em[ec];
+    }
+    double rsum = 0, rmin = __longlong_as_double(0x7ff0000000000000LL); int n = 0;
+    for (int port = 0; port < p.P; ++port) {
+        const size_t ip = (size_t)e * p.P + port;
+        for (int k = 0; k < p.st_nfin[ip]; ++k) { const double r = p.st_r[ip * p.Smax + k]; rsum += r; rmin = fmin(rmin, r); ++n; }
+    }
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double rmean = n ? rsum / n : nan;
+    double var = 0;
+    for (int port = 0; port < p.P; ++port) {
+        const size_t ip = (size_t)e * p.P + port;
+        for (int k = 0; k < p.st_nfin[ip]; ++k) { const double d = p.st_r[ip * p.Smax + k] - rmean; var += d * d; }
+    }
+    o[EV2B_STAT_EV_SERVED] = kpi[EV2B_KPI_EVS_SERVED];           o[EV2B_STAT_PROFITS] = kpi[EV2B_KPI_TOTAL_PROFITS];
+    o[EV2B_STAT_ENERGY_CHARGED] = kpi[EV2B_KPI_ENERGY_CHARGED];  o[EV2B_STAT_ENERGY_DISCHARGED] = kpi[EV2B_KPI_ENERGY_DISCHARGED];
+    o[EV2B_STAT_AVG_USER_SAT] = n_cs ? avg_sum / n_cs : nan;
+    o[EV2B_STAT_TRACKER_VIOLATION] = kpi[EV2B_KPI_TRACKER_VIOLATION];
+    o[EV2B_STAT_TRACKING_ERROR] = kpi[EV2B_KPI_TRACKING_ERROR];
+    o[EV2B_STAT_ENERGY_TRACKING_ERROR] = kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] * p.period / 60.0;   // utils.py:46
+    o[EV2B_STAT_ENERGY_USER_SAT] = rmean;
+    o[EV2B_STAT_STD_ENERGY_USER_SAT] = n ? sqrt(var / n) : nan;
+    o[EV2B_STAT_MIN_ENERGY_USER_SAT] = n ? rmin : nan;
+    o[EV2B_STAT_EMERGENCY_STEPS] = (double)em;
+    o[EV2B_STAT_TR_OVERLOAD] = kpi[EV2B_KPI_TR_OVERLOAD];
+    o[EV2B_STAT_DEGRADATION] = dcal + dcyc; o[EV2B_STAT_DEGRADATION_CAL] = dcal; o[EV2B_STAT_DEGRADATION_CYC] = dcyc;
+    o[EV2B_STAT_TOTAL_REWARD] = kpi[EV2B_KPI_TOTAL_REWARD];
 }
 
 }  // namespace ev2b

@@ -24,6 +24,12 @@ KPI_NAMES = ("total_reward", "total_profits", "total_energy_charged", "total_ene
              "energy_tracking_error_steps", "power_tracker_violation", "total_evs_spawned", "invalid_actions",
              "steps")
 
+STAT_NAMES = ("total_ev_served", "total_profits", "total_energy_charged", "total_energy_discharged",
+              "average_user_satisfaction", "power_tracker_violation", "tracking_error", "energy_tracking_error",
+              "energy_user_satisfaction", "std_energy_user_satisfaction", "min_energy_user_satisfaction",
+              "total_steps_min_emergency_battery_capacity_violation", "total_transformer_overload",
+              "battery_degradation", "battery_degradation_calendar", "battery_degradation_cycling", "total_reward")
+
 _OUT_SPECS = {  # name -> (dtype, per-env shape key)
     "reward": ("float64", ()), "status": ("int32", ()), "obs": ("float32", ("D",)),
     "cs_power": ("float32", ("C",)), "cs_current": ("float32", ("C",)),
@@ -54,7 +60,7 @@ class _CudaView:
 
 class BatchedEngine:
     def __init__(self, topo: Topology, n_envs: int, reward=None, state=None, device: int = 0,
-                 outputs: Iterable[str] = ("reward", "status", "obs")):
+                 outputs: Iterable[str] = ("reward", "status", "obs"), stats: bool = False):
         import torch  # plumbing only
         if not torch.cuda.is_available():
             raise EngineError("ev2gym_b200 needs a CUDA device: there is no CPU fallback in the product path")
@@ -66,7 +72,8 @@ class BatchedEngine:
             raise EngineError(f"no fused device implementation for reward={r!r} / state={s!r}")
         self.reward_name, self.state_name = r, s
         d = _lib.Dims(self.E, topo.C, topo.Tr, topo.T, topo.timescale, topo.dr_steps_ahead, REWARD_KINDS[r],
-                      STATE_KINDS[s], float(topo.tr_voltage))
+                      STATE_KINDS[s], float(topo.tr_voltage), 1 if stats else 0, 0)
+        self.stats = bool(stats)
         self._keep = [topo.cs_n_ports, topo.cs_tr, topo.cs_phases, topo.cs_imax, topo.cs_imin, topo.cs_imax_dis,
                       topo.cs_imin_dis, topo.cs_voltage]
         tv = _lib.TopologyView(*[a.ctypes.data_as(t) for a, (_, t) in zip(self._keep, _lib.TopologyView._fields_)])
@@ -220,6 +227,14 @@ class BatchedEngine:
             "env_scn": view(sv.env_scn, (E,), "<i4"), "env_potential": view(sv.env_potential, (E,), "<f8"),
             "env_usage": view(sv.env_usage, (E,), "<f8"), "env_kpi": view(sv.env_kpi, (E, sv.n_kpi), "<f8"),
         }
+
+    def episode_stats(self) -> Dict[str, np.ndarray]:
+        """get_statistics(env) of every env (ev2gym/utilities/utils.py:12-123); needs stats=True."""
+        torch = self.torch
+        out = torch.zeros((self.E, len(STAT_NAMES)), dtype=torch.float64, device=self.dev)
+        self._check(self.L.ev2b_episode_stats(self.h, out.data_ptr(), self._stream()), "ev2b_episode_stats")
+        o = out.cpu().numpy()
+        return {n: o[:, i].copy() for i, n in enumerate(STAT_NAMES)}
 
     def kpis(self) -> Dict[str, np.ndarray]:
         k = self.state_tensors()["env_kpi"].cpu().numpy()

@@ -118,7 +118,7 @@ class EV2GymB200:
         self._fused_reward = _fn_name(reward_function) in REWARD_KINDS and _fn_name(reward_function) is not None
         self._engine = BatchedEngine(topo, 1, reward=reward_function if self._fused_reward else None,
                                      state=state_function if self._fused_state else None, device=device,
-                                     outputs=_FACADE_OUTPUTS)
+                                     outputs=_FACADE_OUTPUTS, stats=True)
         self._port_off = topo.cs_port_off
         self.done = False
         high = np.ones(self.number_of_ports)
@@ -292,18 +292,15 @@ class EV2GymB200:
         return obs, reward, False, False, {"cost": cost, "action_mask": self._mask.copy()}
 
     def _statistics(self) -> dict:
-        """The subset of get_statistics (ev2gym/utilities/utils.py:12-123) the step path maintains."""
-        k = {n: float(v[0]) for n, v in self._engine.kpis().items()}
-        served = [cs for cs in self.charging_stations if cs.total_evs_served > 0]
-        return {
-            "total_ev_served": int(k["total_ev_served"]), "total_profits": k["total_profits"],
-            "total_energy_charged": k["total_energy_charged"], "total_energy_discharged": k["total_energy_discharged"],
-            "average_user_satisfaction": float(np.mean([cs.get_avg_user_satisfaction() for cs in served])) if served
-            else float("nan"),
-            "power_tracker_violation": k["power_tracker_violation"], "tracking_error": k["tracking_error"],
-            "energy_tracking_error": k["energy_tracking_error_steps"] * self.timescale / 60,
-            "total_transformer_overload": k["total_transformer_overload"], "total_reward": self.total_reward,
-        }
+        """get_statistics (ev2gym/utilities/utils.py:12-123), computed on the device (ev2b_episode_stats)."""
+        st = {k: float(v[0]) for k, v in self._engine.episode_stats().items()}
+        st["total_ev_served"] = int(st["total_ev_served"])
+        st["total_steps_min_emergency_battery_capacity_violation"] = int(
+            st["total_steps_min_emergency_battery_capacity_violation"])
+        st["total_reward"] = self.total_reward
+        st.update(saved_grid_energy=0, voltage_violation=0, voltage_violation_counter=0,
+                  voltage_violation_counter_per_step=0)                              # utils.py:108-112
+        return st
 
     def set_cost_function(self, cost_function):
         self.cost_function = cost_function

@@ -68,7 +68,11 @@ typedef struct {
     int32_t reward_kind;       /* enum ev2b_reward_kind                                       */
     int32_t state_kind;        /* enum ev2b_state_kind                                        */
     double  tr_voltage;        /* voltage*sqrt(phases) of the config   (transformer.py:39-40) */
+    int32_t flags;             /* EV2B_F_* */
+    int32_t reserved;
 } ev2b_dims;
+
+#define EV2B_F_STATS 1         /* keep the per-EV histories get_statistics() needs (utils.py:12-123, ev.py:442-521) */
 
 /* Static charger layout, HOST pointers; replaces load_ev_charger_profiles / cs_transformers
  * (ev2gym/utilities/loaders.py:299-365, 495-498).  Arrays have n_chargers entries. */
@@ -146,6 +150,14 @@ enum ev2b_kpi {
     EV2B_KPI_STEPS, EV2B_KPI_COUNT
 };
 
+enum ev2b_stat {
+    EV2B_STAT_EV_SERVED = 0, EV2B_STAT_PROFITS, EV2B_STAT_ENERGY_CHARGED, EV2B_STAT_ENERGY_DISCHARGED,
+    EV2B_STAT_AVG_USER_SAT, EV2B_STAT_TRACKER_VIOLATION, EV2B_STAT_TRACKING_ERROR, EV2B_STAT_ENERGY_TRACKING_ERROR,
+    EV2B_STAT_ENERGY_USER_SAT, EV2B_STAT_STD_ENERGY_USER_SAT, EV2B_STAT_MIN_ENERGY_USER_SAT,
+    EV2B_STAT_EMERGENCY_STEPS, EV2B_STAT_TR_OVERLOAD, EV2B_STAT_DEGRADATION, EV2B_STAT_DEGRADATION_CAL,
+    EV2B_STAT_DEGRADATION_CYC, EV2B_STAT_TOTAL_REWARD, EV2B_STAT_COUNT
+};
+
 int         ev2b_abi_version(void);
 const char *ev2b_last_error(const ev2b_handle *h);   /* h may be NULL: error of the last failed create */
 
@@ -180,6 +192,12 @@ int  ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype,
 int  ev2b_reset_done(ev2b_handle *h, float *obs0, void *stream);
 
 int  ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *out);
+
+/* get_statistics(env) for every env (ev2gym/utilities/utils.py:12-123, incl. EV.get_battery_degradation
+ * ev.py:442-521 and the AFAP bound ev.py:407-440).  Needs EV2B_F_STATS.  out: DEVICE [E, EV2B_STAT_COUNT]
+ * float64, columns in enum ev2b_stat order.  Meaningful once an env is done (or at any time for the
+ * EVs that already left). */
+int  ev2b_episode_stats(ev2b_handle *h, double *out, void *stream);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t ev2b_launch_count(const ev2b_handle *h);
 

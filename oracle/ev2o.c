@@ -261,6 +261,10 @@ void ev2o_reset(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st
     memset(st->tr_overload_hist, 0, sizeof(double) * Tr * T);
     memset(st->cs_power_hist, 0, sizeof(double) * C * T);
     memset(st->cs_current_hist, 0, sizeof(double) * C * T);
+    for (int i = 0; i < sc->n_sessions; ++i) {
+        st->ev_spawned[i] = 0; st->ev_final_cap[i] = 0; st->ev_afap[i] = 0; st->ev_soc_sum[i] = 0; st->ev_n_hist[i] = 0;
+        st->ev_abs_energy[i] = 0; st->ev_em_metric[i] = 0; st->ev_n_act[i] = 0;
+    }
     memcpy(st->load_fc_live, sc->tr_load_fc, sizeof(double) * Tr * T);
     memcpy(st->pv_fc_live, sc->tr_pv_fc, sizeof(double) * Tr * T);
     write_obs(tp, sc, st, state_kind, obs0);
@@ -332,7 +336,8 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
             double amps = 0, energy = 0, actual = 0;
             int stepped = 0, active = 0, ci = 0, ec = 0;
             ev_params prm;
-            if (s >= 0) session_params(sc, s, &prm);
+            double soc_before = 0;
+            if (s >= 0) { session_params(sc, s, &prm); soc_before = st->port_cap[p] / prm.B; }
             if (action == 0 && s >= 0) {                             /* :162-165  ev.step(0, V) */
                 stepped = 1;
                 active = ev_step(&prm, &st->port_cap[p], 0.0, tp->cs_voltage[c], 1, tp->timescale,
@@ -359,6 +364,9 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
                 total_amps += actual;
             }
             if (stepped) {
+                /* EV.step bookkeeping for get_battery_degradation: historic_soc / active_steps  ev.py:156,162,185 */
+                st->ev_soc_sum[s] += soc_before; st->ev_n_hist[s] += 1;
+                if (active && actual != 0) st->ev_act_soc[(size_t)s * T + st->ev_n_act[s]++] = soc_before;
                 st->port_cur_energy[p] = energy; st->port_cur_amps[p] = actual;
                 if (active) {                                        /* ev.py:166-183 bookkeeping */
                     st->port_cycles[p] += ci;
@@ -366,12 +374,14 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
                     st->port_energy_exch[p] += energy;
                     st->port_abs_energy[p] += fabs(energy);
                     st->port_em_metric[p] += ec;
+                    st->ev_abs_energy[s] += fabs(energy); st->ev_em_metric[s] += ec;
                     if (amps > 0) st->port_required[p] -= energy;    /* ev.py:353 (after gating amps keeps its sign) */
                     else          st->port_required[p] += energy;    /* ev.py:399 */
                 }
             }
             if (total_amps - 0.0001 > tp->cs_imax[c]) out->error = 1;   /* :203-205 raise Exception */
         }
+        for (int j = 0; j < n; ++j) if (st->port_session[lo + j] >= 0) st->ev_final_cap[st->port_session[lo + j]] = st->port_cap[lo + j];
         st->cs_total_profits[c] += profit;                          /* :207 */
         /* departures, with the charger's own step counter == t   :209-231 */
         for (int j = 0; j < n; ++j) {
@@ -412,6 +422,24 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
             st->port_required[idx] = sc->s_B[i] - sc->s_cap0[i];
             st->port_cur_energy[idx] = 0; st->port_cur_amps[idx] = 0;
             st->port_cycles[idx] = 0; st->port_em_metric[idx] = 0;
+            st->ev_spawned[i] = 1; st->ev_final_cap[i] = sc->s_cap0[i];
+            {   /* EV.calculate_max_energy_with_AFAP(cs.get_max_power())  ev.py:407-440, ev_charger.py:251-252,279 */
+                double max_cs_power = tp->cs_imax[c] * tp->cs_voltage[c] * sqrt((double)tp->cs_phases[c]) / 1000.0;
+                double max_power = fabs(max_cs_power) > fabs(sc->s_pmax_ac[i]) ? sc->s_pmax_ac[i] : max_cs_power;
+                double eff = sc->s_eta_c[i];
+                if (sc->s_lut[i] >= 0) {
+                    const double *l = sc->luts_c + (size_t)sc->s_lut[i] * sc->lut_len;
+                    double m = 0; for (int k = 0; k < sc->lut_len; ++k) if (l[k] > m) m = l[k];
+                    eff = m / 100.0;
+                }
+                double afap = sc->s_cap0[i];
+                for (int k = sc->s_t_arr[i]; k < sc->s_t_dep[i] + 1; ++k) {
+                    afap += max_power * eff * (double)tp->timescale / 60.0;
+                    afap = my_ceil2(afap);
+                    if (afap > sc->s_B[i]) { afap = sc->s_B[i]; break; }
+                }
+                st->ev_afap[i] = afap;
+            }
             st->total_evs_spawned++;
             n_arrived++;
         } else if (sc->s_t_arr[i] > t + 1) break;
@@ -472,4 +500,75 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
     out->reward = reward; out->total_costs = total_costs; out->done = st->done;
     out->invalid_actions = total_invalid; out->n_departed = n_departed; out->n_arrived = n_arrived;
     return out->error ? 1 : 0;
+}
+
+
+/* ------------------------------------------------------------------------- */
+/* get_statistics  utils.py:12-123                                           */
+
+static double mean_of(const double *v, int n) { double s = 0; for (int i = 0; i < n; ++i) s += v[i]; return n ? s / n : NAN; }
+
+void ev2o_statistics(const ev2o_topology *tp, const ev2o_scenario *sc, const ev2o_state *st, double *out) {
+    const int C = tp->C, T = tp->T, Tr = tp->Tr;
+    double served = 0, profits = 0, ch = 0, dis = 0, avg_sat_sum = 0; int n_served_cs = 0;
+    for (int c = 0; c < C; ++c) {
+        served += st->cs_total_served[c]; profits += st->cs_total_profits[c];
+        ch += st->cs_total_charged[c]; dis += st->cs_total_discharged[c];
+        if (st->cs_total_served[c] > 0) { avg_sat_sum += st->cs_total_sat[c] / st->cs_total_served[c]; n_served_cs++; }
+    }
+    double tr_ov = 0;
+    for (int i = 0; i < Tr * T; ++i) tr_ov += st->tr_overload_hist[i];
+    double te = 0, ete = 0, viol = 0;                                  /* utils.py:31-46 */
+    for (int t = 0; t < T; ++t) {
+        double d = sc->setpoint[t] - st->usage[t];
+        te += d * d; ete += fabs(d);
+        if (st->usage[t] > sc->setpoint[t]) viol += st->usage[t] - sc->setpoint[t];
+    }
+    ete *= (double)tp->timescale / 60.0;
+    /* per EV: energy user satisfaction + battery degradation (ev.py:442-521) */
+    const double e0 = 7.543e6, e1 = 23.75e6, e2 = 6976, z0 = 7.348e-3, z1 = 3.667, z2 = 7.6e-4, z3 = 4.081e-3;
+    const double b_cap_ah = 2.05, b_cap_kwh = 78, d_dist = 15000, b_age = 2 * 365, G = 0.186;
+    const double theta = 298.15, k = 0.8263, v_min = 3.3324;
+    double dcal = 0, dcyc = 0, eus_sum = 0, eus_sq = 0, eus_min = INFINITY; int n_ev = 0, em = 0;
+    for (int i = 0; i < sc->n_sessions; ++i) {
+        if (!st->ev_spawned[i]) continue;
+        const double B = sc->s_B[i], final_soc = st->ev_final_cap[i] / B;
+        double T_sim = (double)(sc->s_t_dep[i] - sc->s_t_arr[i] + 1) * (double)tp->timescale / (60.0 * 24.0);
+        double avg_soc = (st->ev_soc_sum[i] + final_soc) / (double)(st->ev_n_hist[i] + 1);
+        double v_avg = v_min + k * avg_soc;
+        double alpha = (e0 * v_avg - e1) * exp(-e2 / theta);
+        double d_cal = alpha * 0.75 * T_sim / pow(b_age, 0.25);
+        const double *f = st->ev_act_soc + (size_t)i * T;
+        int nf = st->ev_n_act[i];
+        double fsum = final_soc; for (int j = 0; j < nf; ++j) fsum += f[j];
+        double avg_f = fsum / (double)(nf + 1);
+        double dev = fabs(avg_f - final_soc); for (int j = 0; j < nf; ++j) dev += fabs(avg_f - f[j]);
+        double delta_DoD = 2.0 * (dev / (double)(nf + 1));
+        double v_half = v_min + k * 0.5;
+        double beta = z0 * (v_half - z1) * (v_half - z1) + z2 + z3 * delta_DoD;
+        double Q_sim = (st->ev_abs_energy[i] / b_cap_kwh) * b_cap_ah;
+        double Q_acc = 2 * (b_age * (d_dist / 365) * G * b_cap_ah) / b_cap_kwh;
+        double d_cyc = beta * 0.5 * Q_sim / pow(Q_acc, 0.5);
+        dcal += d_cal; dcyc += d_cyc;
+        double r = (st->ev_final_cap[i] / st->ev_afap[i]) * 100.0;       /* utils.py:59-62 */
+        eus_sum += r; eus_sq += r * r; if (r < eus_min) eus_min = r; n_ev++;
+        em += st->ev_em_metric[i];
+    }
+    double eus_mean = n_ev ? eus_sum / n_ev : NAN;
+    double eus_var = 0;                                                 /* np.std: two-pass population variance */
+    for (int i = 0; i < sc->n_sessions; ++i) {
+        if (!st->ev_spawned[i]) continue;
+        double r = (st->ev_final_cap[i] / st->ev_afap[i]) * 100.0;
+        eus_var += (r - eus_mean) * (r - eus_mean);
+    }
+    eus_var = n_ev ? eus_var / n_ev : NAN;
+    (void)eus_sq;
+    out[EV2O_STAT_EV_SERVED] = served; out[EV2O_STAT_PROFITS] = profits; out[EV2O_STAT_ENERGY_CHARGED] = ch;
+    out[EV2O_STAT_ENERGY_DISCHARGED] = dis; out[EV2O_STAT_AVG_USER_SAT] = n_served_cs ? avg_sat_sum / n_served_cs : NAN;
+    out[EV2O_STAT_TRACKER_VIOLATION] = viol; out[EV2O_STAT_TRACKING_ERROR] = te; out[EV2O_STAT_ENERGY_TRACKING_ERROR] = ete;
+    out[EV2O_STAT_ENERGY_USER_SAT] = eus_mean; out[EV2O_STAT_STD_ENERGY_USER_SAT] = eus_var > 0 ? sqrt(eus_var) : 0.0;
+    out[EV2O_STAT_MIN_ENERGY_USER_SAT] = eus_min; out[EV2O_STAT_EMERGENCY_STEPS] = em; out[EV2O_STAT_TR_OVERLOAD] = tr_ov;
+    out[EV2O_STAT_DEGRADATION] = dcal + dcyc; out[EV2O_STAT_DEGRADATION_CAL] = dcal; out[EV2O_STAT_DEGRADATION_CYC] = dcyc;
+    out[EV2O_STAT_TOTAL_REWARD] = st->total_reward;
+    (void)mean_of;
 }

@@ -86,7 +86,23 @@ typedef struct {
     double *tr_overload_hist;    /* [Tr*T] */
     double *cs_power_hist, *cs_current_hist; /* [C*T] */
     double *load_fc_live, *pv_fc_live;       /* [Tr*T] forecasts incl. the write-through of transformer.py:178-180 */
+    /* per spawned EV (index = session index; env.EVs keeps departed EVs), for get_statistics  utils.py:12-123 */
+    int    *ev_spawned;          /* [S] 1 once spawned */
+    double *ev_final_cap;        /* [S] current_capacity as of now / at departure */
+    double *ev_afap;             /* [S] max_energy_AFAP  ev.py:407-440 */
+    double *ev_soc_sum;          /* [S] sum(historic_soc) */
+    int    *ev_n_hist;           /* [S] len(historic_soc) */
+    double *ev_abs_energy;       /* [S] abs_total_energy_exchanged */
+    int    *ev_em_metric;        /* [S] min_emergency_battery_capacity_metric */
+    int    *ev_n_act;            /* [S] number of steps with actual_current != 0 */
+    double *ev_act_soc;          /* [S*T] historic_soc at those steps */
 } ev2o_state;
+
+enum { EV2O_STAT_EV_SERVED = 0, EV2O_STAT_PROFITS, EV2O_STAT_ENERGY_CHARGED, EV2O_STAT_ENERGY_DISCHARGED,
+       EV2O_STAT_AVG_USER_SAT, EV2O_STAT_TRACKER_VIOLATION, EV2O_STAT_TRACKING_ERROR, EV2O_STAT_ENERGY_TRACKING_ERROR,
+       EV2O_STAT_ENERGY_USER_SAT, EV2O_STAT_STD_ENERGY_USER_SAT, EV2O_STAT_MIN_ENERGY_USER_SAT,
+       EV2O_STAT_EMERGENCY_STEPS, EV2O_STAT_TR_OVERLOAD, EV2O_STAT_DEGRADATION, EV2O_STAT_DEGRADATION_CAL,
+       EV2O_STAT_DEGRADATION_CYC, EV2O_STAT_TOTAL_REWARD, EV2O_STAT_COUNT };
 
 /* Per-step outputs; arrays caller-allocated, any may be NULL. */
 typedef struct {
@@ -110,6 +126,9 @@ int  ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
 /* Micro entry point for the known-answer table: one EV.step (ev.py:138-186) on explicit params.
  * p = {cap, B, pmax_ac, pmin_ac, pmax_dis, pmin_dis, bmin, ts, mult, eta_c, eta_d}; returns new cap,
  * writes energy and amps. */
+/* get_statistics(env)  ev2gym/utilities/utils.py:12-123 (+ EV.get_battery_degradation ev.py:442-521) */
+void ev2o_statistics(const ev2o_topology *tp, const ev2o_scenario *sc, const ev2o_state *st, double *out);
+
 double ev2o_ev_step(const double *p, int ev_phases, double amps, double voltage, int phases,
                     int timescale, double *energy, double *actual_amps);
 

@@ -52,7 +52,10 @@ _STATE_ARRAYS = [("port_session", "i", "P"), ("port_cap", "d", "P"), ("port_ener
                  ("cs_total_sat", "d", "C"), ("cs_total_served", "i", "C"),
                  ("usage", "d", "T"), ("potential", "d", "T"), ("tr_overload_hist", "d", "TrT"),
                  ("cs_power_hist", "d", "CT"), ("cs_current_hist", "d", "CT"),
-                 ("load_fc_live", "d", "TrT"), ("pv_fc_live", "d", "TrT")]
+                 ("load_fc_live", "d", "TrT"), ("pv_fc_live", "d", "TrT"),
+                 ("ev_spawned", "i", "S"), ("ev_final_cap", "d", "S"), ("ev_afap", "d", "S"), ("ev_soc_sum", "d", "S"),
+                 ("ev_n_hist", "i", "S"), ("ev_abs_energy", "d", "S"), ("ev_em_metric", "i", "S"), ("ev_n_act", "i", "S"),
+                 ("ev_act_soc", "d", "ST")]
 
 
 class _State(C.Structure):
@@ -97,6 +100,8 @@ def lib():
                                 C.POINTER(_Out)]
         L.ev2o_ev_step.restype = C.c_double
         L.ev2o_ev_step.argtypes = [_pd, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _pd, _pd]
+        L.ev2o_statistics.restype = None
+        L.ev2o_statistics.argtypes = [C.POINTER(_Topo), C.POINTER(_Scn), C.POINTER(_State), _pd]
         L.ev2o_max_threads.restype = C.c_int
         L.ev2o_step_batch.restype = C.c_int
         L.ev2o_step_batch.argtypes = [C.POINTER(_Topo), C.POINTER(C.POINTER(_Scn)), C.POINTER(_State), C.c_int,
@@ -146,8 +151,16 @@ class _ScnC:
         self.c = s
 
 
-def _sizes(topo, D):
-    return {"P": topo.P, "C": topo.C, "T": topo.T, "Tr": max(topo.Tr, 1), "TrT": max(topo.Tr, 1) * topo.T,
+STAT_NAMES = ("total_ev_served", "total_profits", "total_energy_charged", "total_energy_discharged",
+              "average_user_satisfaction", "power_tracker_violation", "tracking_error", "energy_tracking_error",
+              "energy_user_satisfaction", "std_energy_user_satisfaction", "min_energy_user_satisfaction",
+              "total_steps_min_emergency_battery_capacity_violation", "total_transformer_overload",
+              "battery_degradation", "battery_degradation_calendar", "battery_degradation_cycling", "total_reward")
+
+
+def _sizes(topo, D, S=1):
+    S = max(int(S), 1)
+    return {"S": S, "ST": S * topo.T, "P": topo.P, "C": topo.C, "T": topo.T, "Tr": max(topo.Tr, 1), "TrT": max(topo.Tr, 1) * topo.T,
             "CT": topo.C * topo.T, "D": max(D, 1)}
 
 
@@ -160,7 +173,7 @@ class OracleEnv:
         self.reward_kind, self.state_kind = REWARD_KINDS[reward], STATE_KINDS[state]
         self._t, self._s = _TopoC(topo), _ScnC(scenario)
         self.obs_dim = self.L.ev2o_obs_dim(C.byref(self._t.c), self.state_kind)
-        sz = _sizes(topo, self.obs_dim)
+        sz = _sizes(topo, self.obs_dim, scenario.n_sessions)
         self.state = _State()
         self.arr = {}
         for n, k, dim in _STATE_ARRAYS:
@@ -197,6 +210,11 @@ class OracleEnv:
                  usage=self.arr["usage"].copy())
         return r
 
+    def statistics(self) -> dict:
+        out = np.zeros(len(STAT_NAMES))
+        self.L.ev2o_statistics(C.byref(self._t.c), C.byref(self._s.c), C.byref(self.state), _p(out))
+        return dict(zip(STAT_NAMES, out.tolist()))
+
     @property
     def current_step(self) -> int:
         return self.state.current_step
@@ -225,7 +243,7 @@ class OracleBatch:
             self._scn.append(uniq[id(sc)])
         self._scn_ptrs = (C.POINTER(_Scn) * self.E)(*[C.pointer(s.c) for s in self._scn])
         self.obs_dim = self.L.ev2o_obs_dim(C.byref(self._t.c), self.state_kind)
-        sz = _sizes(topo, self.obs_dim)
+        sz = _sizes(topo, self.obs_dim, max(sc.n_sessions for sc in scenarios))
         self.states = (_State * self.E)()
         self.outs = (_Out * self.E)()
         self.arr = {}
@@ -248,6 +266,12 @@ class OracleBatch:
             self.L.ev2o_reset(C.byref(self._t.c), self._scn_ptrs[e], C.byref(self.states[e]), self.state_kind,
                               _p(self.o["obs"][e]))
         return self.o["obs"][:, :self.obs_dim]
+
+    def statistics(self) -> dict:
+        out = np.zeros((self.E, len(STAT_NAMES)))
+        for e in range(self.E):
+            self.L.ev2o_statistics(C.byref(self._t.c), self._scn_ptrs[e], C.byref(self.states[e]), _p(out[e]))
+        return {n: out[:, i].copy() for i, n in enumerate(STAT_NAMES)}
 
     def step(self, actions: np.ndarray):
         a = np.ascontiguousarray(actions, dtype=np.float64)

@@ -40,7 +40,10 @@ def test_facade_replays_reference_episode(name):
         assert np.array_equal(info["action_mask"], tr["action_mask"][t])
     assert info["total_ev_served"] == int(tr["stat_total_ev_served"])
     for k in ("total_profits", "total_energy_charged", "total_energy_discharged", "total_transformer_overload",
-              "tracking_error", "energy_tracking_error", "power_tracker_violation"):
+              "tracking_error", "energy_tracking_error", "power_tracker_violation", "energy_user_satisfaction",
+              "std_energy_user_satisfaction", "min_energy_user_satisfaction", "battery_degradation",
+              "battery_degradation_calendar", "battery_degradation_cycling", "total_reward",
+              "total_steps_min_emergency_battery_capacity_violation"):
         assert info[k] == pytest.approx(float(tr["stat_" + k]), rel=1e-9, abs=1e-9), k
     if not math.isnan(float(tr["stat_average_user_satisfaction"])):
         assert info["average_user_satisfaction"] == pytest.approx(float(tr["stat_average_user_satisfaction"]), rel=1e-9)

@@ -16,9 +16,9 @@ from conftest import GOLDEN, golden_cases
 pytestmark = pytest.mark.gpu
 
 
-def _engine(topo, scenarios, n_envs, reward, state, outputs):
+def _engine(topo, scenarios, n_envs, reward, state, outputs, stats=False):
     from ev2gym_b200.engine import BatchedEngine
-    eng = BatchedEngine(topo, n_envs, reward=reward, state=state, outputs=outputs)
+    eng = BatchedEngine(topo, n_envs, reward=reward, state=state, outputs=outputs, stats=stats)
     eng.load_scenarios(scenarios)
     return eng
 
@@ -40,7 +40,7 @@ def test_cuda_matches_reference_trace(name):
     tr = np.load(f"{GOLDEN}/{name}.trace.npz")
     topo = pack.topo
     E = 3                                 # 3 replicas of the same episode: exercises multi-env CTAs
-    eng = _engine(topo, pack.scenarios, E, str(tr["reward_fn"]), str(tr["state_fn"]), ALL_OUT)
+    eng = _engine(topo, pack.scenarios, E, str(tr["reward_fn"]), str(tr["state_fn"]), ALL_OUT, stats=True)
     obs0 = eng.reset().cpu().numpy()
     assert _close(obs0[0], tr["obs0"], 1e-5, 1e-6) and np.array_equal(obs0[0], obs0[2])
     st = eng.state_tensors()
@@ -75,6 +75,13 @@ def test_cuda_matches_reference_trace(name):
     assert k["total_transformer_overload"][0] == pytest.approx(float(tr["stat_total_transformer_overload"]),
                                                                rel=1e-9, abs=1e-9)
     assert k["tracking_error"][0] == pytest.approx(float(tr["stat_tracking_error"]), rel=1e-9, abs=1e-9)
+    # get_statistics(env) incl. battery degradation and AFAP-normalised energy satisfaction: 1e-9 relative
+    from ev2gym_b200.engine import STAT_NAMES
+    st = eng.episode_stats()
+    for n in STAT_NAMES:
+        ref = float(tr["stat_" + n])
+        for e in (0, E - 1):
+            assert (np.isnan(ref) and np.isnan(st[n][e])) or st[n][e] == pytest.approx(ref, rel=1e-9, abs=1e-12), n
     # stepping a finished env is a no-op flagged WAS_DONE (reference: AssertionError, ev2gym_env.py:343)
     out = eng.step(a)
     assert int(out["status"][0].item()) & 4 and float(out["reward"][0].item()) == 0.0
@@ -98,7 +105,7 @@ def test_cuda_matches_oracle_on_synthetic(C, n, Tr, E, reward, state, adt):
     topo = Topology.uniform(C=C, n_ports=n, Tr=Tr, T=64, imin=6.0 if n == 3 else 0.0)
     bank = sample_bank(topo, 5, seed=C + n, min_stay=5)
     scn_ids = [(3 * e + 1) % 5 for e in range(E)]
-    eng = _engine(topo, bank, E, reward, state, ALL_OUT)
+    eng = _engine(topo, bank, E, reward, state, ALL_OUT, stats=True)
     obs0 = eng.reset(scn_ids=scn_ids).cpu().numpy()
     orc = OracleBatch(topo, [bank[i] for i in scn_ids], reward=reward, state=state)
     assert _close(obs0, orc.reset(), 1e-5, 1e-5)
@@ -123,6 +130,10 @@ def test_cuda_matches_oracle_on_synthetic(C, n, Tr, E, reward, state, adt):
         ovf = np.array([o.error == 1 for o in orc.outs])
         assert np.array_equal((out["status"] & 2) > 0, ovf), (t, "amps overflow flag")
     assert _close(eng.kpis()["total_reward"], [s.total_reward for s in orc.states], 1e-9, 1e-9)
+    st, ost = eng.episode_stats(), orc.statistics()
+    for n in st:
+        both_nan = np.isnan(st[n]) & np.isnan(ost[n])
+        assert _close(np.where(both_nan, 0, st[n]), np.where(both_nan, 0, ost[n]), 1e-9, 1e-12), n
 
 
 def test_ragged_ports_and_reset_done():

@@ -141,3 +141,21 @@ def test_known_answers_charger():
         caps.append(r["port_cap"][0])
     assert caps == [22.75, 25.5, 28.26] and r["n_departed"] == 1 and r["port_session"][0] == -1
     assert r["dep_sat"][0] == 28.26 / 50
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_statistics_match_reference(name):
+    """get_statistics (utils.py:12-123) incl. battery degradation (ev.py:442-521): 1e-10 relative
+    (numpy sums pairwise, the oracle sequentially); AFAP bounds (ev.py:407-440) bit-exact."""
+    from oracle.oracle import STAT_NAMES
+    pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
+    tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+    env = OracleEnv(pack.topo, pack.scenarios[0], reward=str(tr["reward_fn"]), state=str(tr["state_fn"]))
+    env.reset()
+    for t in range(tr["reward"].shape[0]):
+        env.step(tr["actions"][t])
+    st = env.statistics()
+    for k in STAT_NAMES:
+        ref = float(tr["stat_" + k])
+        assert (np.isnan(ref) and np.isnan(st[k])) or st[k] == pytest.approx(ref, rel=1e-10, abs=1e-12), k
+    assert np.array_equal(env.arr["ev_afap"][env.arr["ev_spawned"] > 0], tr["afap"])

@@ -159,8 +159,12 @@ def record_episode(base, overrides, seed, agent, state=None, reward=None):
     out["total_reward"] = np.array(env.total_reward)
     for k in ("total_ev_served", "total_profits", "total_energy_charged", "total_energy_discharged",
               "average_user_satisfaction", "total_transformer_overload", "tracking_error",
-              "energy_tracking_error", "power_tracker_violation"):
+              "energy_tracking_error", "power_tracker_violation", "energy_user_satisfaction",
+              "std_energy_user_satisfaction", "min_energy_user_satisfaction",
+              "total_steps_min_emergency_battery_capacity_violation", "battery_degradation",
+              "battery_degradation_calendar", "battery_degradation_cycling", "total_reward"):
         out["stat_" + k] = np.array(float(stats[k]))
+    out["afap"] = np.array([ev.max_energy_AFAP for ev in env.EVs], dtype=np.float64)   # ev.py:407-440, spawn order
     out["state_fn"], out["reward_fn"] = np.array(st), np.array(rw)
     out["seed"], out["agent"], out["base"] = np.array(seed), np.array(agent), np.array(base)
     return topo, scn, out
