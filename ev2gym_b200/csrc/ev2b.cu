@@ -73,6 +73,9 @@ struct ev2b_handle {
     // e2e staging (ev2b_step_host)
     DevBuf<unsigned char> st_actions; DevBuf<double> st_reward; DevBuf<uint32_t> st_status; DevBuf<float> st_obs;
     DevBuf<int> st_scn;
+    static constexpr int kChunks = 4;   // ev2b_step_host pipelines H2D / kernel / D2H over env chunks
+    cudaStream_t chunk_stream[kChunks] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t chunk_ev[kChunks] = {nullptr, nullptr, nullptr, nullptr}, start_ev = nullptr;
 
     int fail(int code, const char *fmt, ...) {
         char buf[512];
@@ -83,7 +86,7 @@ struct ev2b_handle {
     Params params() const {
         Params p{};
         p.E = E; p.C = C; p.P = P; p.Tr = Tr; p.T = T; p.D = D; p.EPB = EPB; p.n_dr = n_dr; p.lut_len = lut_len;
-        p.Smax = Smax; p.S = S; p.n_cls = n_cls; p.W = W;
+        p.Smax = Smax; p.S = S; p.n_cls = n_cls; p.W = W; p.env0 = 0; p.env_end = E;
         p.reward_kind = dims.reward_kind; p.state_kind = dims.state_kind; p.dr_steps_ahead = dims.dr_steps_ahead;
         p.c60 = 60.0 / (double)dims.timescale; p.p60 = (double)dims.timescale / 60.0; p.period = (double)dims.timescale;
         p.rc60 = 1.0 / p.c60; p.rp60 = 1.0 / p.p60; p.rperiod = 1.0 / p.period;
@@ -127,7 +130,7 @@ static int obs_dim_for(int kind, int P, int Tr) {
 
 template <typename ActT>
 static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st) {
-    const unsigned grid = (unsigned)((h->E + h->EPB - 1) / h->EPB);
+    const unsigned grid = (unsigned)((p.env_end - p.env0 + h->EPB - 1) / h->EPB);
     auto go = [&](auto kern) -> cudaError_t {
         if (h->smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
@@ -317,6 +320,11 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
 void ev2b_destroy(ev2b_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    for (int i = 0; i < ev2b_handle::kChunks; ++i) {
+        if (h->chunk_stream[i]) cudaStreamDestroy(h->chunk_stream[i]);
+        if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
+    }
+    if (h->start_ev) cudaEventDestroy(h->start_ev);
     delete h;
 }
 
@@ -587,43 +595,80 @@ int ev2b_reset_done(ev2b_handle *h, float *obs0, void *stream) {
     return launch_reset(h, 0, h->E, nullptr, 1, obs0, (cudaStream_t)stream);
 }
 
-int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, void *stream) {
-    if (!h || !actions) return h ? h->fail(EV2B_E_ARG, "step: null actions") : EV2B_E_ARG;
-    if (h->S == 0) return h->fail(EV2B_E_STATE, "step: no scenario bank loaded");
+int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, void *stream);
+
+// Launches the step kernel for envs [lo, hi) on `st` (used by ev2b_step and by the chunked host path).
+static int step_range(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, int lo, int hi,
+                      int obs_full, cudaStream_t st) {
     Params p = h->params();
     p.actions = actions;
     if (out) p.out = *out;
-    p.obs_full = (p.out.obs != h->last_obs) ? 1 : 0;
-    h->last_obs = p.out.obs;
+    p.obs_full = obs_full;
+    p.env0 = lo; p.env_end = hi;
     cudaError_t e;
-    if (action_dtype == EV2B_F32) e = launch_step<float>(h, p, (cudaStream_t)stream);
-    else if (action_dtype == EV2B_F64) e = launch_step<double>(h, p, (cudaStream_t)stream);
+    if (action_dtype == EV2B_F32) e = launch_step<float>(h, p, st);
+    else if (action_dtype == EV2B_F64) e = launch_step<double>(h, p, st);
     else return h->fail(EV2B_E_ARG, "step: unknown action dtype %d", action_dtype);
     if (e != cudaSuccess) return h->fail(EV2B_E_CUDA, "step launch: %s", cudaGetErrorString(e));
     h->launches += 1;
     return EV2B_OK;
 }
 
+int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, void *stream) {
+    if (!h || !actions) return h ? h->fail(EV2B_E_ARG, "step: null actions") : EV2B_E_ARG;
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "step: no scenario bank loaded");
+    const float *obs = out ? out->obs : nullptr;
+    const int obs_full = (obs != h->last_obs) ? 1 : 0;
+    h->last_obs = obs;
+    return step_range(h, actions, action_dtype, out, 0, h->E, obs_full, (cudaStream_t)stream);
+}
+
 int ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype, double *reward_host,
                    uint32_t *status_host, float *obs_host, void *stream) {
     if (!h || !actions_host) return h ? h->fail(EV2B_E_ARG, "step_host: null actions") : EV2B_E_ARG;
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "step_host: no scenario bank loaded");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t user = (cudaStream_t)stream;
     const size_t esz = action_dtype == EV2B_F64 ? 8 : 4;
     const size_t nbytes = (size_t)h->E * h->P * esz;
     if (h->st_actions.n < nbytes) CUDA_TRY(h, h->st_actions.alloc(nbytes));
     if (h->st_reward.n < (size_t)h->E) { CUDA_TRY(h, h->st_reward.alloc(h->E)); CUDA_TRY(h, h->st_status.alloc(h->E)); }
-    if (obs_host && h->D > 0 && h->st_obs.n < (size_t)h->E * h->D) CUDA_TRY(h, h->st_obs.alloc((size_t)h->E * h->D));
-    CUDA_TRY(h, cudaMemcpyAsync(h->st_actions.p, actions_host, nbytes, cudaMemcpyHostToDevice, st));
+    const bool want_obs = obs_host && h->D > 0;
+    if (want_obs && h->st_obs.n < (size_t)h->E * h->D) CUDA_TRY(h, h->st_obs.alloc((size_t)h->E * h->D));
+    if (!h->start_ev) {
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
+        for (int i = 0; i < ev2b_handle::kChunks; ++i) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->chunk_stream[i], cudaStreamNonBlocking));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->chunk_ev[i], cudaEventDisableTiming));
+        }
+    }
     ev2b_step_out out{};
     out.reward = h->st_reward.p; out.status = h->st_status.p;
-    out.obs = (obs_host && h->D > 0) ? h->st_obs.p : nullptr;
-    int rc = ev2b_step(h, h->st_actions.p, action_dtype, &out, stream);
-    if (rc != EV2B_OK) return rc;
-    if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host, h->st_reward.p, sizeof(double) * h->E, cudaMemcpyDeviceToHost, st));
-    if (status_host) CUDA_TRY(h, cudaMemcpyAsync(status_host, h->st_status.p, sizeof(uint32_t) * h->E, cudaMemcpyDeviceToHost, st));
-    if (out.obs) CUDA_TRY(h, cudaMemcpyAsync(obs_host, h->st_obs.p, sizeof(float) * (size_t)h->E * h->D, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaStreamSynchronize(st));
+    out.obs = want_obs ? h->st_obs.p : nullptr;
+    const int obs_full = (out.obs != h->last_obs) ? 1 : 0;
+    h->last_obs = out.obs;
+    // PCIe is full duplex and the copy engines run beside the SMs: split the env range into chunks, each on its
+    // own stream (H2D actions -> kernel -> D2H results), so chunk i's download overlaps chunk i+1's upload/compute.
+    const int per = ((h->E + ev2b_handle::kChunks - 1) / ev2b_handle::kChunks + h->EPB - 1) / h->EPB * h->EPB;
+    CUDA_TRY(h, cudaEventRecord(h->start_ev, user));
+    const unsigned char *ah = static_cast<const unsigned char *>(actions_host);
+    for (int c = 0; c < ev2b_handle::kChunks; ++c) {
+        const int lo = c * per, hi = std::min(h->E, lo + per);
+        if (lo >= hi) break;
+        cudaStream_t st = h->chunk_stream[c];
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->start_ev, 0));
+        const size_t aoff = (size_t)lo * h->P * esz, abytes = (size_t)(hi - lo) * h->P * esz;
+        CUDA_TRY(h, cudaMemcpyAsync(h->st_actions.p + aoff, ah + aoff, abytes, cudaMemcpyHostToDevice, st));
+        int rc = step_range(h, h->st_actions.p, action_dtype, &out, lo, hi, obs_full, st);
+        if (rc != EV2B_OK) return rc;
+        if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host + lo, h->st_reward.p + lo, sizeof(double) * (hi - lo), cudaMemcpyDeviceToHost, st));
+        if (status_host) CUDA_TRY(h, cudaMemcpyAsync(status_host + lo, h->st_status.p + lo, sizeof(uint32_t) * (hi - lo), cudaMemcpyDeviceToHost, st));
+        if (want_obs) CUDA_TRY(h, cudaMemcpyAsync(obs_host + (size_t)lo * h->D, h->st_obs.p + (size_t)lo * h->D,
+                                                  sizeof(float) * (size_t)(hi - lo) * h->D, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(h, cudaEventRecord(h->chunk_ev[c], st));
+        CUDA_TRY(h, cudaStreamWaitEvent(user, h->chunk_ev[c], 0));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(user));
     return EV2B_OK;
 }
 

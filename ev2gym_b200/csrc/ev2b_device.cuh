@@ -76,6 +76,7 @@ struct Params {
     // sizes
     int E, C, P, Tr, T, D, EPB, n_dr, lut_len, Smax, S, n_cls, W;
     int reward_kind, state_kind, dr_steps_ahead;
+    int env0, env_end;       // this launch advances envs [env0, env_end)  (ev2b_step_host pipelines chunks)
     int obs_full;            // 1: rewrite every observation entry; 0: the caller's obs buffer still holds last step's
                              //    rows, only entries that can change are written (occupied ports, header, series)
     double c60, rc60;        // 60 / timescale (ev.py:296) and its reciprocal
@@ -332,8 +333,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     const int tid = threadIdx.x;
     const int el = p.C == 1 ? tid : (int)__umulhi((unsigned)tid, p.c_magic);   // tid / C
     const int c = tid - el * p.C;
-    const int e = blockIdx.x * p.EPB + el;
-    const bool valid = (el < p.EPB) && (e < p.E);
+    const int e = (p.env0 + blockIdx.x * p.EPB) + el;
+    const bool valid = (el < p.EPB) && (e < p.env_end);
     const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
     constexpr int NPR = NP > 0 ? NP : 1;
@@ -420,8 +421,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     // (scenario, time)-only part of the observation: price window + forecast / limit blocks
     if (want_obs && p.W > 0) {
         for (int jel = 0; jel < p.EPB; ++jel) {
-            const int je = blockIdx.x * p.EPB + jel;
-            if (je >= p.E) break;
+            const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
+            if (je >= p.env_end) break;
             const int jt = envi[jel * 4 + 0];
             if (jt >= p.T) continue;
             const int js = envi[jel * 4 + 1];
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             const bool active = ev_step_item<STATS>(p, cs, hw.x, hw.y, resE[pl], cap, energy, amps, em_cross);
             if (STATS && em_cross) {   // min_emergency_battery_capacity_metric  ev.py:401-402 (integer atomics: order-free)
                 const int jel = p.EPB == 1 ? 0 : (int)__umulhi((unsigned)pl, p.p_magic);
-                atomicAdd(&p.cs_em[(size_t)(blockIdx.x * p.EPB + jel) * p.C + p.port_cs[port]], 1);
+                atomicAdd(&p.cs_em[(size_t)((p.env0 + blockIdx.x * p.EPB) + jel) * p.C + p.port_cs[port]], 1);
             }
             resE[pl] = energy; resA[pl] = amps;
             resC[pl] = active ? cap : -1.0;                              // EV saw amps == 0: nothing changes (ev.py:158-163)
@@ -593,8 +594,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
         for (int job = warp; job < 3 * p.EPB; job += nwarps) {
             const int jel = job / 3, kind = job - jel * 3;
-            const int je = blockIdx.x * p.EPB + jel;
-            if (je >= p.E) continue;
+            const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
+            if (je >= p.env_end) continue;
             const int jt = envi[jel * 4 + 0];
             if (jt >= p.T) continue;
             if (kind == 0) {          // Transformer.step accumulation + overload   transformer.py:264-302
@@ -653,8 +654,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
 
     // ---- C: one thread per env: reward, KPIs, step counter ---------------------------------------
     if (tid < p.EPB) {
-        const int je = blockIdx.x * p.EPB + tid;
-        if (je < p.E) {
+        const int je = (p.env0 + blockIdx.x * p.EPB) + tid;
+        if (je < p.env_end) {
             const int jt = envi[tid * 4 + 0], js = envi[tid * 4 + 1];
             unsigned status = (unsigned)envi[tid * 4 + 3];
             double reward = 0.0, costs = 0.0;
