@@ -264,6 +264,22 @@ def main():
     if world > 1:
         dist.all_reduce(kpi, op=dist.ReduceOp.SUM)
 
+    # ---- k-step device-agent rollout (ev2b_step_k): no action tensor, no host round trip -----------------
+    agent_rate = None
+    try:
+        reset_all()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kk = T - 1
+        e0.record()
+        for g in range(G):
+            engines[g].step_k(kk, "uniform", seed=7 + g)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        agent_rate = E * G * kk / (e0.elapsed_time(e1) * 1e-3)
+    except Exception as exc:  # pragma: no cover
+        agent_rate = f"failed: {exc}"
+
     # ---- end to end through the host-buffer API --------------------------------------------------
     eng = engines[0]
     eng.reset()
@@ -322,6 +338,8 @@ def main():
                          "algorithmic_bytes_per_env_step": bytes_env_step,
                          "kernel": "ev2b::step_kernel", "launch_ms": launch_ms},
             "kpi_allreduce": {"total_reward": float(kpi[0].item()), "total_evs_served": float(kpi[5].item())},
+            "device_agent_rollout": {"value": agent_rate, "unit": "env-steps/s per GPU",
+                                     "what": "ev2b_step_k, UNIFORM on-device agent, one call per episode and env group"},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(topo, pack.scenarios, reward, state if D else None, E)

@@ -598,9 +598,13 @@ int ev2b_reset_done(ev2b_handle *h, float *obs0, void *stream) {
 int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, void *stream);
 
 // Launches the step kernel for envs [lo, hi) on `st` (used by ev2b_step and by the chunked host path).
+struct AgentCfg { int kind = EV2B_AGENT_EXTERNAL; uint64_t seed = 0; double low = -1.0; };
+
 static int step_range(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, int lo, int hi,
-                      int obs_full, cudaStream_t st) {
+                      int obs_full, cudaStream_t st, const AgentCfg &ag = AgentCfg()) {
     Params p = h->params();
+    p.agent_kind = ag.kind; p.agent_seed_lo = (unsigned)ag.seed; p.agent_seed_hi = (unsigned)(ag.seed >> 32);
+    p.action_low = ag.low;
     p.actions = actions;
     if (out) p.out = *out;
     p.obs_full = obs_full;
@@ -621,6 +625,30 @@ int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_
     const int obs_full = (obs != h->last_obs) ? 1 : 0;
     h->last_obs = obs;
     return step_range(h, actions, action_dtype, out, 0, h->E, obs_full, (cudaStream_t)stream);
+}
+
+int ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, int action_dtype, uint64_t seed,
+                double action_low, int auto_reset, const ev2b_step_out *out, void *stream) {
+    if (!h) return EV2B_E_ARG;
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "step_k: no scenario bank loaded");
+    if (k < 1) return h->fail(EV2B_E_ARG, "step_k: k must be >= 1");
+    if (agent_kind < EV2B_AGENT_EXTERNAL || agent_kind > EV2B_AGENT_UNIFORM) return h->fail(EV2B_E_ARG, "step_k: unknown agent %d", agent_kind);
+    if (agent_kind == EV2B_AGENT_EXTERNAL && !actions_k) return h->fail(EV2B_E_ARG, "step_k: EXTERNAL agent needs actions_k");
+    AgentCfg ag; ag.kind = agent_kind; ag.seed = seed; ag.low = action_low;
+    const size_t stride = (size_t)h->E * h->P * (action_dtype == EV2B_F64 ? 8 : 4);
+    float *obs = out ? out->obs : nullptr;
+    for (int i = 0; i < k; ++i) {
+        const int obs_full = (obs != h->last_obs) ? 1 : 0;
+        h->last_obs = obs;
+        const void *a = agent_kind == EV2B_AGENT_EXTERNAL ? (const void *)((const unsigned char *)actions_k + stride * i) : (const void *)h->hot.p;
+        int rc = step_range(h, a, action_dtype, out, 0, h->E, obs_full, (cudaStream_t)stream, ag);
+        if (rc != EV2B_OK) return rc;
+        if (auto_reset) {
+            rc = ev2b_reset_done(h, obs, stream);
+            if (rc != EV2B_OK) return rc;
+        }
+    }
+    return EV2B_OK;
 }
 
 int ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype, double *reward_host,

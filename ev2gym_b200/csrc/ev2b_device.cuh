@@ -76,6 +76,8 @@ struct Params {
     // sizes
     int E, C, P, Tr, T, D, EPB, n_dr, lut_len, Smax, S, n_cls, W;
     int reward_kind, state_kind, dr_steps_ahead;
+    int agent_kind;          // enum ev2b_agent_kind; != 0: actions are generated, `actions` is not read
+    unsigned agent_seed_lo, agent_seed_hi; double action_low;
     int env0, env_end;       // this launch advances envs [env0, env_end)  (ev2b_step_host pipelines chunks)
     int obs_full;            // 1: rewrite every observation entry; 0: the caller's obs buffer still holds last step's
                              //    rows, only entries that can change are written (occupied ports, header, series)
@@ -113,6 +115,20 @@ __device__ __forceinline__ int hot_t_dep(const uint4 &h)   { return (int)(int16_
 __device__ __forceinline__ int hot_next_arr(const uint4 &h){ return (int)(int16_t)(h.y & 0xFFFFu); }
 __device__ __forceinline__ int hot_cursor(const uint4 &h)  { return (int)((h.y >> 16) & 0xFFu); }
 __device__ __forceinline__ int hot_spec(const uint4 &h)    { return (int)(h.z & 0xFFFFu); }
+
+// Counter-based RNG of the UNIFORM device agent (documented in include/ev2b.h; mirrored by tests).
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+template <typename ActT>
+__device__ __forceinline__ double agent_action(const Params &p, const ActT *actions, size_t ip, int t) {
+    if (p.agent_kind == EV2B_AGENT_EXTERNAL) return (double)actions[ip];
+    if (p.agent_kind == EV2B_AGENT_AFAP) return 1.0;
+    if (p.agent_kind == EV2B_AGENT_ZERO) return 0.0;
+    const unsigned hsh = mix32(mix32((unsigned)ip ^ p.agent_seed_lo) + (unsigned)t * 0x9E3779B9u + p.agent_seed_hi);
+    return p.action_low + (1.0 - p.action_low) * ((double)(hsh >> 8) * (1.0 / 16777216.0));
+}
 
 __device__ __forceinline__ double lut_get(const double *lut, int lut_len, double key) {
     // dict.get(np.round(amps), 1): integer keys 0..lut_len-1, default 1   ev.py:288,376
@@ -345,11 +361,13 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     // ---- A1: per charger: loads, empty-port masking, normalisation, work-list compaction -------
     // Every independent global load of this thread is issued BEFORE the first barrier.
     uint4 h[NPR];
-    ActT araw[NPR];
+    double araw[NPR];
     double capv[NPR];
     unsigned pushed = 0, asign = 0;      // bit j: port j is a work item / its action is > 0
     int invalid = 0;
     int port0 = 0, n = 0;
+    double pre_cp = 0.0, pre_dp = 0.0;     // prices of this step, fetched before the first barrier
+    float exch0[NPR];
     if (valid) {
         t = p.env_step[e];
         s = p.env_scn[e];
@@ -357,9 +375,10 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             port0 = UNI ? c * NP : p.cs[c].port_off;
             const size_t pb = (size_t)e * p.P + port0;
 #pragma unroll
-            for (int j = 0; j < NP; ++j) { h[j] = p.hot[pb + j]; araw[j] = actions[pb + j]; }
+            for (int j = 0; j < NP; ++j) { h[j] = p.hot[pb + j]; araw[j] = agent_action<ActT>(p, actions, pb + j, t); }
         }
         live = t < p.T;
+        if (live) { const EnvT et0 = p.env_t[(size_t)s * p.T + t]; pre_cp = et0.cp; pre_dp = et0.dp; }
         if (c == 0) { envi[el * 4 + 0] = t; envi[el * 4 + 1] = s; envi[el * 4 + 2] = 0; envi[el * 4 + 3] = 0; }
     }
     __syncthreads();
@@ -373,11 +392,12 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         if (NP > 0) {
             double a[NPR];
 #pragma unroll
-            for (int j = 0; j < NP; ++j) a[j] = (double)araw[j];
+            for (int j = 0; j < NP; ++j) a[j] = araw[j];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const bool occ = hot_t_arr(h[j]) <= t && t <= hot_t_dep(h[j]);
                 capv[j] = occ ? p.cap[pbase + j] : 0.0;
+                exch0[j] = occ ? p.exch[pbase + j] : 0.f;
                 if (!occ) { a[j] = 0.0; ++invalid; }                     // ev_charger.py:137-140
                 sum = sum + a[j];                                        // python sum(), left to right  :143
             }
@@ -399,12 +419,12 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 const uint4 hj = p.hot[pbase + j];
                 const bool occ = hot_t_arr(hj) <= t && t <= hot_t_dep(hj);
                 if (!occ) ++invalid;
-                sum = sum + (occ ? (double)actions[pbase + j] : 0.0);
+                sum = sum + (occ ? agent_action<ActT>(p, actions, pbase + j, t) : 0.0);
             }
             for (int j = 0; j < n; ++j) {
                 const uint4 hj = p.hot[pbase + j];
                 const bool occ = hot_t_arr(hj) <= t && t <= hot_t_dep(hj);
-                double an = occ ? (double)actions[pbase + j] : 0.0;
+                double an = occ ? agent_action<ActT>(p, actions, pbase + j, t) : 0.0;
                 if (sum > 1.0) an = an / sum; else if (sum < -1.0) an = -an / sum;
                 const int pl = el * p.P + port0 + j;
                 signed char f = 0;
@@ -461,7 +481,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     int rCnt = invalid;
     if (valid && live) {
         const CsStatic &cs = cs_of<UNI>(p, c);
-        const EnvT et = p.env_t[(size_t)s * p.T + t];
+        EnvT et; et.cp = pre_cp; et.dp = pre_dp;
         const size_t pbase = (size_t)e * p.P + port0;
         const int tq = t + 1;
         float *obs_row = p.out.obs + (size_t)e * p.D;      // observation rows live in the caller's buffer across steps
@@ -488,7 +508,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 if (cnew >= 0.0) {                                        // the EV was active this step
                     cv = cnew;
                     p.cap[ip] = cv;
-                    exch_new = p.exch[ip] + (float)energy;                // total_energy_exchanged  ev.py:178
+                    exch_new = (NP > 0 ? exch0[j] : p.exch[ip]) + (float)energy;   // total_energy_exchanged  ev.py:178
                     exch_valid = true;
                     p.exch[ip] = exch_new;
                 }
@@ -561,7 +581,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                     float *o = obs_row + p.obs_slot[port0 + j];
                     if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
                         o[0] = (cv == B) ? 1.f : 0.5f;
-                        o[1] = exch_valid ? exch_new : p.exch[ip];
+                        o[1] = exch_valid ? exch_new : (NP > 0 ? exch0[j] : p.exch[ip]);
                         o[2] = (float)(tq - hot_t_arr(hj));
                     } else {
                         o[0] = (float)ev2b_div_c(cv, B, __ldg(&sp->rB));

@@ -203,6 +203,36 @@ class BatchedEngine:
         self._check(self.L.ev2b_step(self.h, actions.data_ptr(), dt, C.byref(self._so), self._stream()), "ev2b_step")
         return self.out
 
+    AGENTS = {"external": 0, "afap": 1, "zero": 2, "uniform": 3}
+
+    def step_k(self, k: int, agent: str = "afap", actions_k=None, seed: int = 0, auto_reset: bool = False):
+        """k steps without returning to the host, driven by an on-device agent (or actions_k [k,E,P])."""
+        kind = self.AGENTS[agent]
+        dt, ptr = 0, None
+        if kind == 0:
+            if tuple(actions_k.shape) != (k, self.E, self.P) or not actions_k.is_contiguous():
+                raise EngineError(f"actions_k must be a contiguous cuda tensor of shape {(k, self.E, self.P)}")
+            dt = 1 if actions_k.dtype == self.torch.float64 else 0
+            ptr = actions_k.data_ptr()
+        low = -1.0 if self.topo.v2g_enabled else 0.0
+        self._check(self.L.ev2b_step_k(self.h, int(k), kind, ptr, dt, int(seed) & (2 ** 64 - 1), low, int(auto_reset),
+                                       C.byref(self._so), self._stream()), "ev2b_step_k")
+        return self.out
+
+    @staticmethod
+    def uniform_agent_actions(seed: int, n_envs: int, n_ports: int, t: int, low: float) -> np.ndarray:
+        """Host mirror of the UNIFORM device agent (include/ev2b.h): exactly the float64 actions it draws."""
+        def mix32(x):
+            x = x.astype(np.uint64) & 0xFFFFFFFF
+            x ^= x >> 16; x = (x * 0x7feb352d) & 0xFFFFFFFF; x ^= x >> 15
+            x = (x * 0x846ca68b) & 0xFFFFFFFF; x ^= x >> 16
+            return x
+        ip = np.arange(n_envs * n_ports, dtype=np.uint64)
+        lo, hi = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+        h = mix32((mix32(ip ^ lo) + np.uint64((t * 0x9E3779B9) & 0xFFFFFFFF) + hi) & 0xFFFFFFFF)
+        u = (h >> 8).astype(np.float64) * (1.0 / 16777216.0)
+        return (low + (1.0 - low) * u).reshape(n_envs, n_ports)
+
     def step_host(self, actions: np.ndarray, reward: np.ndarray, status: np.ndarray, obs: Optional[np.ndarray] = None):
         """End-to-end step with HOST buffers (H2D actions, kernel, D2H reward/status[/obs], sync)."""
         dt = {np.dtype("float32"): 0, np.dtype("float64"): 1}[actions.dtype]

@@ -43,6 +43,13 @@ enum ev2b_state_kind {
     EV2B_STATE_V2G_PROFIT_MAX_LOADS = 3   /* V2G_profit_max_loads state.py:108-155 D = 22 + 40Tr + 2P */
 };
 enum ev2b_action_dtype { EV2B_F32 = 0, EV2B_F64 = 1 };
+/* On-device agents for ev2b_step_k (no action tensor is read). */
+enum ev2b_agent_kind {
+    EV2B_AGENT_EXTERNAL = 0,      /* actions_k[k,E,P] supplied by the caller                                   */
+    EV2B_AGENT_AFAP = 1,          /* ChargeAsFastAsPossible: all ones        ev2gym/baselines/heuristics.py:161-166 */
+    EV2B_AGENT_ZERO = 2,          /* DoNothing: all zeros                    heuristics.py (DoNothing)          */
+    EV2B_AGENT_UNIFORM = 3        /* RandomAgent-like: uniform in the action space, counter-based hash RNG      */
+};
 
 /* error codes */
 enum {
@@ -186,6 +193,13 @@ int  ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b
  * then waits for completion.  This is the call a host-resident agent makes (end-to-end path). */
 int  ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype,
                     double *reward_host, uint32_t *status_host, float *obs_host, void *stream);
+
+/* k consecutive steps without returning to the host: `agent_kind` picks an on-device agent (or EXTERNAL with
+ * actions_k = DEVICE [k,E,P]).  Outputs in `out` hold the LAST step; KPI sums cover all k.  With auto_reset != 0
+ * finished envs restart on their next scenario between steps (ev2b_reset_done).  UNIFORM draws
+ * a = low + (1-low) * u, u = (mix32(seed, env*P+port, step) >> 8) * 2^-24, low = -1 if v2g (action_low) else 0. */
+int  ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, int action_dtype, uint64_t seed,
+                 double action_low, int auto_reset, const ev2b_step_out *out, void *stream);
 
 /* Device-side auto-reset of every env whose episode is over: next scenario id =
  * (current id + n_envs) mod bank size.  For vectorised RL rollouts. */

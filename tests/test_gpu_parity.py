@@ -193,3 +193,39 @@ def test_step_host_matches_device_path():
         assert np.array_equal(o1["reward"].cpu().numpy(), rew)
         assert np.array_equal(o1["obs"].cpu().numpy(), obs)
         assert np.array_equal(o1["status"].cpu().numpy().astype(np.uint32), stt)
+
+
+@pytest.mark.parametrize("agent", ["afap", "zero", "uniform", "external"])
+def test_step_k_device_agents(agent):
+    """ev2b_step_k: k steps per call with an on-device agent == stepping the oracle with the same actions."""
+    import torch
+    from ev2gym_b200.engine import BatchedEngine
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    from oracle.oracle import OracleBatch
+    topo = Topology.uniform(C=30, n_ports=2, Tr=3, T=48)
+    bank = sample_bank(topo, 4, seed=21, min_stay=5)
+    E, seed = 13, 0x1234ABCD5678
+    rw, stf = "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads"
+    eng = _engine(topo, bank, E, rw, stf, ("reward", "status", "obs"))
+    eng.reset()
+    orc = OracleBatch(topo, [bank[e % 4] for e in range(E)], reward=rw, state=stf)
+    orc.reset()
+    caps = eng.state_tensors()["port_cap"]
+    rng = np.random.default_rng(2)
+    t = 0
+    for k in (1, 5, 16, 26):
+        ext = rng.uniform(-1, 1, (k, E, topo.P))
+        for i in range(k):
+            a = {"afap": np.ones((E, topo.P)), "zero": np.zeros((E, topo.P)), "external": ext[i],
+                 "uniform": BatchedEngine.uniform_agent_actions(seed, E, topo.P, t + i, -1.0)}[agent]
+            orc.step(a)
+        out = eng.step_k(k, agent, actions_k=torch.tensor(ext, device="cuda") if agent == "external" else None,
+                         seed=seed)
+        t += k
+        occ = orc.arr["port_session"] >= 0
+        assert np.array_equal(caps.cpu().numpy()[occ], orc.arr["port_cap"][occ]), (agent, t)
+        assert _close(out["reward"].cpu().numpy(), orc.reward, 1e-9, 1e-9)
+        assert _close(out["obs"].cpu().numpy(), orc.o["obs"][:, :eng.D], 1e-5, 1e-5)
+    assert t == topo.T and bool((out["status"] & 1).all())
+    assert _close(eng.kpis()["total_reward"], [s.total_reward for s in orc.states], 1e-9, 1e-9)
