@@ -41,7 +41,36 @@ def topology_from_env(env) -> Topology:
         sim_length=int(env.simulation_length),
         dr_steps_ahead=int(cfg["demand_response"]["notification_of_event_minutes"] // env.timescale),
         v2g_enabled=bool(cfg["v2g_enabled"]),
+        **_grid_static(env),
     )
+
+
+def _grid_static(env) -> dict:
+    """K, L of the Laurent power flow (grid_tensor.py:110-118) when `simulate_grid` is on."""
+    grid = getattr(env, "grid", None)
+    if not getattr(env, "simulate_grid", False) or grid is None:
+        return {}
+    net = grid.net
+    return dict(grid_K=np.asarray(net._K_, dtype=np.complex128), grid_L=np.asarray(net._L_, dtype=np.complex128).reshape(-1),
+                grid_s_base=float(net.s_base))
+
+
+def _grid_series(env, T: int):
+    """Base bus powers of steps 0..T exactly as PowerGrid.reset/step derive them (grid.py:109-118, 131-139)."""
+    grid = env.grid
+    nb = grid.node_num
+    act = np.zeros((T + 1, nb - 1))
+    rea = np.zeros((T + 1, nb - 1))
+    # step 0: PowerGrid.reset's `active_power` is a VIEW of load_data[0] and is modified in place (`-= pv`,
+    # grid.py:109-116), so row 0 of load_data no longer holds the raw load: take what reset() left behind.
+    act[0] = np.asarray(grid.active_power, dtype=np.float64).reshape(-1)
+    rea[0] = np.asarray(grid.reactive_power, dtype=np.float64).reshape(-1)
+    for t in range(1, T + 1):
+        a = np.array(grid.load_data[t, 1:nb], dtype=np.float64).reshape(1, -1)
+        r = (a * grid.net.pf).round(1)
+        a = a - np.asarray(grid.pv_data[t, 1:nb], dtype=np.float64).reshape(1, -1)
+        act[t], rea[t] = a[0], r[0]
+    return act, rea
 
 
 def _lut_row(d: dict) -> Tuple[float, ...]:
@@ -102,7 +131,17 @@ def scenario_from_env(env) -> Scenario:
             sess[k].append(v)
     sessions = {k: np.array(v, dtype=np.int32 if k in SESSION_INT_FIELDS else np.float64) for k, v in sess.items()}
 
+    import datetime
+    start = env.sim_starting_date if hasattr(env, "sim_starting_date") else env.sim_date
+    dates = [start + datetime.timedelta(minutes=int(env.timescale) * k) for k in range(T + 1)]
+    date_feat = np.array([[d.weekday() / 7, math.sin(d.hour / 24 * 2 * math.pi), math.cos(d.hour / 24 * 2 * math.pi)]
+                          for d in dates])                                    # state.py:221-225
+    grid_kw = {}
+    if getattr(env, "simulate_grid", False) and getattr(env, "grid", None) is not None:
+        ga, gr = _grid_series(env, T)
+        grid_kw = dict(grid_active=ga, grid_reactive=gr)
     return Scenario(
+        date_feat=date_feat, **grid_kw,
         charge_price=cp[0].copy(), discharge_price=dp[0].copy(),
         setpoint=np.asarray(env.power_setpoints, dtype=np.float64)[:T].copy(),
         tr_infl=series("inflexible_load"), tr_solar=series("solar_power"),

@@ -61,6 +61,10 @@ class Topology:
     sim_length: int             # T
     dr_steps_ahead: int = 0     # notification_of_event_minutes // timescale  transformer.py:69
     v2g_enabled: bool = True
+    # distribution grid (simulate_grid: True): Laurent power flow V <- K conj(S/V) + L   grid_tensor.py:110-118
+    grid_K: Optional[np.ndarray] = None      # [nb-1, nb-1] complex128  (-Ydd^-1)
+    grid_L: Optional[np.ndarray] = None      # [nb-1] complex128        (K @ Yds)
+    grid_s_base: float = 1000.0              # kVA
 
     def __post_init__(self):
         self.cs_n_ports = np.ascontiguousarray(self.cs_n_ports, dtype=np.int32)
@@ -68,6 +72,16 @@ class Topology:
         self.cs_phases = np.ascontiguousarray(self.cs_phases, dtype=np.int32)
         for k in ("cs_imax", "cs_imin", "cs_imax_dis", "cs_imin_dis", "cs_voltage"):
             setattr(self, k, np.ascontiguousarray(getattr(self, k), dtype=np.float64))
+        if self.grid_K is not None and np.size(self.grid_K) > 0:
+            self.grid_K = np.ascontiguousarray(self.grid_K, dtype=np.complex128)
+            self.grid_L = np.ascontiguousarray(self.grid_L, dtype=np.complex128).reshape(-1)
+        else:
+            self.grid_K = self.grid_L = None
+
+    @property
+    def n_bus(self) -> int:
+        """Buses without the slack (= transformers in grid mode, loaders.py:481); 0 when no grid is simulated."""
+        return 0 if self.grid_K is None else int(self.grid_K.shape[0])
 
     @property
     def C(self) -> int:
@@ -108,13 +122,15 @@ class Topology:
             sim_length=T, dr_steps_ahead=dr_steps_ahead, v2g_enabled=v2g_enabled)
 
     def to_dict(self) -> Dict[str, np.ndarray]:
-        d = {f"topo_{k}": np.asarray(v) for k, v in dataclasses.asdict(self).items()}
+        d = {f"topo_{k}": np.asarray(v if v is not None else np.zeros(0)) for k, v in dataclasses.asdict(self).items()}
         return d
 
     @classmethod
     def from_dict(cls, d) -> "Topology":
         kw = {}
         for f in dataclasses.fields(cls):
+            if f"topo_{f.name}" not in d:          # packs written before the field existed: keep the default
+                continue
             v = d[f"topo_{f.name}"]
             if f.name in ("n_transformers", "timescale", "sim_length", "dr_steps_ahead"):
                 v = int(v)
@@ -122,6 +138,10 @@ class Topology:
                 v = float(v)
             elif f.name == "v2g_enabled":
                 v = bool(v)
+            elif f.name == "grid_s_base":
+                v = float(v)
+            elif f.name in ("grid_K", "grid_L"):
+                v = None if np.size(v) == 0 else v
             kw[f.name] = v
         return cls(**kw)
 
@@ -146,6 +166,11 @@ class Scenario:
     luts_c: np.ndarray = field(default_factory=lambda: np.ones((0, LUT_LEN)))  # [L,101] percent
     luts_d: np.ndarray = field(default_factory=lambda: np.ones((0, LUT_LEN)))
     meta: Dict[str, object] = field(default_factory=dict)
+    # grid mode only: base bus powers of steps 0..T (grid.py:98-118,131-139) and calendar features of the
+    # observation times 0..T (state.py:221-225)
+    grid_active: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))    # [T+1, nb-1] kW (load - pv)
+    grid_reactive: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))  # [T+1, nb-1] kVAr
+    date_feat: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))      # [T+1, 3] weekday/7, sin, cos
 
     @property
     def n_sessions(self) -> int:
@@ -160,6 +185,8 @@ class Scenario:
             self.sessions[k] = np.ascontiguousarray(self.sessions[k], dtype=np.int32)
         for k in SESSION_F64_FIELDS:
             self.sessions[k] = np.ascontiguousarray(self.sessions[k], dtype=np.float64)
+        for k in ("grid_active", "grid_reactive", "date_feat"):
+            setattr(self, k, np.ascontiguousarray(getattr(self, k), dtype=np.float64))
         self.luts_c = np.ascontiguousarray(self.luts_c, dtype=np.float64).reshape(-1, LUT_LEN)
         self.luts_d = np.ascontiguousarray(self.luts_d, dtype=np.float64).reshape(-1, LUT_LEN)
         return self
@@ -211,7 +238,7 @@ class ScenarioPack:
         d["n_scenarios"] = np.array(len(self.scenarios))
         sc = self.scenarios
         for k in ("charge_price", "discharge_price", "setpoint", "dr_start", "dr_end", "dr_cap",
-                  "dr_count") + TR_SERIES:
+                  "dr_count", "grid_active", "grid_reactive", "date_feat") + TR_SERIES:
             d[k] = np.stack([getattr(s, k) for s in sc])
         s_off = np.zeros(len(sc) + 1, dtype=np.int64)
         l_off = np.zeros(len(sc) + 1, dtype=np.int64)
@@ -241,6 +268,9 @@ class ScenarioPack:
                 tr_load_fc=z["tr_load_fc"][i], tr_pv_fc=z["tr_pv_fc"][i],
                 dr_start=z["dr_start"][i], dr_end=z["dr_end"][i], dr_cap=z["dr_cap"][i],
                 dr_count=z["dr_count"][i], sessions=sess,
+                grid_active=z["grid_active"][i] if "grid_active" in z else np.zeros((0, 0)),
+                grid_reactive=z["grid_reactive"][i] if "grid_reactive" in z else np.zeros((0, 0)),
+                date_feat=z["date_feat"][i] if "date_feat" in z else np.zeros((0, 3)),
                 luts_c=z["luts_c"][l_off[i]:l_off[i + 1]], luts_d=z["luts_d"][l_off[i]:l_off[i + 1]],
             ).normalise())
         return cls(topo=topo, scenarios=out, config_name=str(z["config_name"]))

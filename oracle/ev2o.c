@@ -156,6 +156,7 @@ int ev2o_obs_dim(const ev2o_topology *tp, int kind) {
     case EV2O_STATE_PUBLIC_PST:            return 3 + 3 * tp->P;               /* state.py:11-57 */
     case EV2O_STATE_V2G_PROFIT_MAX:        return 2 + 20 + 2 * tp->P;          /* state.py:70-102 */
     case EV2O_STATE_V2G_PROFIT_MAX_LOADS:  return 2 + 20 + 40 * tp->Tr + 2 * tp->P; /* state.py:113-151 */
+    case EV2O_STATE_V2G_GRID:              return 6 + 2 * tp->n_bus + 3 * tp->P;    /* state.py:216-278 */
     default: return 0;
     }
 }
@@ -204,6 +205,23 @@ static void write_obs(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_sta
     const int T = tp->T, t = st->current_step;
     int o = 0;
     double prev_usage = st->usage[(t - 1 + T) % T];  /* python negative index at t == 0 */
+    if (kind == EV2O_STATE_V2G_GRID) {                               /* V2G_grid_state  state.py:216-278 */
+        const int n = tp->n_bus;
+        obs[o++] = sc->date_feat[t * 3 + 0]; obs[o++] = sc->date_feat[t * 3 + 1]; obs[o++] = sc->date_feat[t * 3 + 2];
+        obs[o++] = (t < T) ? sc->charge_price[t] : 0.0;              /* charge_prices[0, t:t+1], zero padded */
+        obs[o++] = (t < T) ? sc->setpoint[t] : 0.0;
+        obs[o++] = prev_usage;
+        /* node_active_power[1:, step-1] holds the base powers of step `step` (grid.step returns the NEXT step's) */
+        for (int i = 0; i < n; ++i) obs[o++] = sc->grid_active[(size_t)t * n + i];
+        for (int i = 0; i < n; ++i) obs[o++] = sc->grid_reactive[(size_t)t * n + i];
+        for (int c = 0; c < tp->C; ++c)
+            for (int p = tp->cs_port_off[c]; p < tp->cs_port_off[c + 1]; ++p) {
+                int s = st->port_session[p];
+                if (s >= 0) { obs[o++] = st->port_cap[p]; obs[o++] = (double)(sc->s_t_dep[s] - t + 1); obs[o++] = (double)tp->cs_tr[c]; }
+                else { obs[o++] = 0; obs[o++] = 0; obs[o++] = 0; }
+            }
+        return;
+    }
     if (kind == EV2O_STATE_PUBLIC_PST) {
         obs[o++] = (double)t / (double)T;
         obs[o++] = (t < T) ? sc->setpoint[t] : 0.0;
@@ -265,6 +283,7 @@ void ev2o_reset(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st
         st->ev_spawned[i] = 0; st->ev_final_cap[i] = 0; st->ev_afap[i] = 0; st->ev_soc_sum[i] = 0; st->ev_n_hist[i] = 0;
         st->ev_abs_energy[i] = 0; st->ev_em_metric[i] = 0; st->ev_n_act[i] = 0;
     }
+    if (tp->n_bus > 0) memset(st->node_voltage, 0, sizeof(double) * (tp->n_bus + 1) * T);
     memcpy(st->load_fc_live, sc->tr_load_fc, sizeof(double) * Tr * T);
     memcpy(st->pv_fc_live, sc->tr_pv_fc, sizeof(double) * Tr * T);
     write_obs(tp, sc, st, state_kind, obs0);
@@ -303,6 +322,7 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
     double total_costs = 0;
     int total_invalid = 0, n_departed = 0, n_arrived = 0;
     double sat_exp_sum = 0;      /* sum over departing EVs of exp(-10*score)  reward.py:41-42,83-85 */
+    double user_costs = 0, loss_v = 0;
     double tr_power[Tr > 0 ? Tr : 1], tr_amps[Tr > 0 ? Tr : 1];
     double act[P > 0 ? P : 1];
     memcpy(act, actions_in, sizeof(double) * P);
@@ -394,6 +414,7 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
                 st->cs_total_served[c] += 1;
                 st->cs_total_sat[c] += sat;
                 sat_exp_sum += 100.0 * exp(-10.0 * sat);
+                user_costs += -((capn - des) * (capn - des));            /* reward.py:99-102 */
                 if (out->dep_sat) out->dep_sat[p] = sat;
                 n_departed++;
             }
@@ -407,6 +428,52 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
         if (out->cs_current) out->cs_current[c] = total_amps;
         st->cs_power_hist[(size_t)c * T + t] = power_out;            /* ev2gym_env.py:534-535 */
         st->cs_current_hist[(size_t)c * T + t] = total_amps;
+    }
+
+    /* distribution grid: node_ev_power <- tr.current_power; PowerGrid.step  ev2gym_env.py:387-397, grid.py:120-141 */
+    out->pf_iterations = 0;
+    if (tp->n_bus > 0) {
+        const int n = tp->n_bus;
+        double Sr[n], Si[n], vr[n], vi[n], lr[n], li[n], nr[n], ni[n];
+        for (int i = 0; i < n; ++i) {
+            double act = sc->grid_active[(size_t)t * n + i] + tr_power[i];       /* grid.py:121 */
+            Sr[i] = act / tp->s_base; Si[i] = sc->grid_reactive[(size_t)t * n + i] / tp->s_base;   /* grid_tensor.py:594-598 */
+            vr[i] = 1.0; vi[i] = 0.0;                                            /* flat start */
+        }
+        int it = 0; double tol = INFINITY;
+        while (it < 100 && tol >= 1e-6) {                                        /* numbarize.py:301-315 */
+            for (int i = 0; i < n; ++i) {
+                /* 1 / v0 (numpy complex division, Smith), then S * that, then conj */
+                double a = vr[i], b = vi[i], rr, ri;
+                if (fabs(a) >= fabs(b)) { double rat = b / a, scl = 1.0 / (a + b * rat); rr = (1.0 + 0.0 * rat) * scl; ri = (0.0 - 1.0 * rat) * scl; }
+                else { double rat = a / b, scl = 1.0 / (b + a * rat); rr = (1.0 * rat + 0.0) * scl; ri = (0.0 * rat - 1.0) * scl; }
+                lr[i] = Sr[i] * rr - Si[i] * ri;
+                li[i] = -(Sr[i] * ri + Si[i] * rr);
+            }
+            tol = 0;
+            for (int r = 0; r < n; ++r) {
+                double zr = 0, zi = 0;
+                for (int c2 = 0; c2 < n; ++c2) {
+                    const double kr = tp->grid_K[2 * ((size_t)r * n + c2)], ki = tp->grid_K[2 * ((size_t)r * n + c2) + 1];
+                    zr += kr * lr[c2] - ki * li[c2];
+                    zi += kr * li[c2] + ki * lr[c2];
+                }
+                nr[r] = zr + tp->grid_L[2 * r]; ni[r] = zi + tp->grid_L[2 * r + 1];
+                double d = fabs(hypot(nr[r], ni[r]) - hypot(vr[r], vi[r]));
+                if (d > tol) tol = d;
+            }
+            for (int r = 0; r < n; ++r) { vr[r] = nr[r]; vi[r] = ni[r]; }
+            it++;
+        }
+        out->pf_iterations = it;
+        st->node_voltage[(size_t)0 * T + t] = 1.0;                               /* grid.py:127-129: slack = 1 */
+        for (int i = 0; i < n; ++i) st->node_voltage[(size_t)(i + 1) * T + t] = hypot(vr[i], vi[i]);
+        for (int i = 0; i <= n; ++i) {                                           /* reward.py:107-110 */
+            double vm = st->node_voltage[(size_t)i * T + t];
+            double x = 0.05 - fabs(1.0 - vm);
+            loss_v += x < 0 ? x : 0.0;
+            if (out->node_vm) out->node_vm[i] = vm;
+        }
     }
 
     /* spawn EVs arriving at t+1  ev2gym_env.py:399-417, ev_charger.py:266-285 */
@@ -485,6 +552,8 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
             if (out->dep_sat ? !isnan(out->dep_sat[p]) : 0) reward -= 100.0 * exp(-10.0 * out->dep_sat[p]);
         if (!out->dep_sat) reward -= sat_exp_sum;
     } break;
+    case EV2O_REWARD_GRID_FULL:   reward = total_costs + 1000.0 * loss_v + user_costs; break;   /* reward.py:89-111 */
+    case EV2O_REWARD_GRID_SIMPLE: reward = 1000.0 * loss_v; break;                              /* reward.py:114-121 */
     default: reward = 0;
     }
     (void)overload_sum;

@@ -34,9 +34,9 @@ extern "C" {
 #endif
 
 enum { EV2O_REWARD_NONE = 0, EV2O_REWARD_SQ_TRACKING = 1, EV2O_REWARD_PROFIT_TR_USER = 2,
-       EV2O_REWARD_PROFIT_MAX = 3 };
+       EV2O_REWARD_PROFIT_MAX = 3, EV2O_REWARD_GRID_FULL = 4, EV2O_REWARD_GRID_SIMPLE = 5 };
 enum { EV2O_STATE_NONE = 0, EV2O_STATE_PUBLIC_PST = 1, EV2O_STATE_V2G_PROFIT_MAX = 2,
-       EV2O_STATE_V2G_PROFIT_MAX_LOADS = 3 };
+       EV2O_STATE_V2G_PROFIT_MAX_LOADS = 3, EV2O_STATE_V2G_GRID = 4 };
 
 /* Static layout shared by all envs. */
 typedef struct {
@@ -47,6 +47,11 @@ typedef struct {
     const int    *cs_phases;     /* [C]   */
     const double *cs_imax, *cs_imin, *cs_imax_dis, *cs_imin_dis, *cs_voltage; /* [C] */
     double tr_voltage;           /* voltage*sqrt(phases), transformer.py:39-40 */
+    /* distribution grid (simulate_grid): Laurent power flow  grid.py:120-141, numbarize.py:268-325 */
+    int n_bus;                   /* buses without the slack (== Tr), 0 = no grid */
+    const double *grid_K;        /* [n_bus*n_bus] complex128 row-major as (re,im) pairs */
+    const double *grid_L;        /* [n_bus] complex128 */
+    double s_base;
 } ev2o_topology;
 
 /* One env's pre-sampled episode. */
@@ -63,6 +68,8 @@ typedef struct {
                  *s_bmin, *s_bmin_em, *s_desired, *s_ts, *s_mult, *s_eta_c, *s_eta_d; /* [S] */
     int n_luts, lut_len;
     const double *luts_c, *luts_d;                                     /* [n_luts*lut_len] percent */
+    const double *grid_active, *grid_reactive;                         /* [(T+1)*n_bus] base bus powers of steps 0..T */
+    const double *date_feat;                                           /* [(T+1)*3] weekday/7, sin, cos at obs time */
 } ev2o_scenario;
 
 /* Mutable env state; all arrays are caller-allocated. */
@@ -85,6 +92,7 @@ typedef struct {
     double *potential;           /* [T] charge_power_potential */
     double *tr_overload_hist;    /* [Tr*T] */
     double *cs_power_hist, *cs_current_hist; /* [C*T] */
+    double *node_voltage;        /* [(n_bus+1)*T] |V| per node and step, slack first  ev2gym_env.py:397 */
     double *load_fc_live, *pv_fc_live;       /* [Tr*T] forecasts incl. the write-through of transformer.py:178-180 */
     /* per spawned EV (index = session index; env.EVs keeps departed EVs), for get_statistics  utils.py:12-123 */
     int    *ev_spawned;          /* [S] 1 once spawned */
@@ -114,6 +122,8 @@ typedef struct {
     double *action_mask;                       /* [P] */
     double *obs;                               /* [obs_dim] */
     double *actions_eff;                       /* [P] actions after the empty-port zeroing (ev_charger.py:137-140) */
+    double *node_vm;                           /* [n_bus+1] |V| of this step */
+    int pf_iterations;
 } ev2o_out;
 
 int  ev2o_obs_dim(const ev2o_topology *tp, int state_kind);

@@ -16,8 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libev2oracle.so")
 
 REWARD_KINDS = {None: 0, "none": 0, "SquaredTrackingErrorReward": 1,
-                "ProfitMax_TrPenalty_UserIncentives": 2, "profit_maximization": 3}
-STATE_KINDS = {None: 0, "none": 0, "PublicPST": 1, "V2G_profit_max": 2, "V2G_profit_max_loads": 3}
+                "ProfitMax_TrPenalty_UserIncentives": 2, "profit_maximization": 3, "V2G_grid_full_reward": 4,
+                "V2G_grid_simple_reward": 5}
+STATE_KINDS = {None: 0, "none": 0, "PublicPST": 1, "V2G_profit_max": 2, "V2G_profit_max_loads": 3, "V2G_grid_state": 4}
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int)
@@ -28,7 +29,8 @@ class _Topo(C.Structure):
                 ("dr_steps_ahead", C.c_int),
                 ("cs_n_ports", _pi), ("cs_port_off", _pi), ("cs_tr", _pi), ("cs_phases", _pi),
                 ("cs_imax", _pd), ("cs_imin", _pd), ("cs_imax_dis", _pd), ("cs_imin_dis", _pd),
-                ("cs_voltage", _pd), ("tr_voltage", C.c_double)]
+                ("cs_voltage", _pd), ("tr_voltage", C.c_double),
+                ("n_bus", C.c_int), ("grid_K", _pd), ("grid_L", _pd), ("s_base", C.c_double)]
 
 
 class _Scn(C.Structure):
@@ -41,7 +43,8 @@ class _Scn(C.Structure):
                 ("s_cap0", _pd), ("s_B", _pd), ("s_pmax_ac", _pd), ("s_pmin_ac", _pd), ("s_pmax_dis", _pd),
                 ("s_pmin_dis", _pd), ("s_bmin", _pd), ("s_bmin_em", _pd), ("s_desired", _pd), ("s_ts", _pd),
                 ("s_mult", _pd), ("s_eta_c", _pd), ("s_eta_d", _pd),
-                ("n_luts", C.c_int), ("lut_len", C.c_int), ("luts_c", _pd), ("luts_d", _pd)]
+                ("n_luts", C.c_int), ("lut_len", C.c_int), ("luts_c", _pd), ("luts_d", _pd),
+                ("grid_active", _pd), ("grid_reactive", _pd), ("date_feat", _pd)]
 
 
 _STATE_ARRAYS = [("port_session", "i", "P"), ("port_cap", "d", "P"), ("port_energy_exch", "d", "P"),
@@ -51,7 +54,7 @@ _STATE_ARRAYS = [("port_session", "i", "P"), ("port_cap", "d", "P"), ("port_ener
                  ("cs_total_charged", "d", "C"), ("cs_total_discharged", "d", "C"), ("cs_total_profits", "d", "C"),
                  ("cs_total_sat", "d", "C"), ("cs_total_served", "i", "C"),
                  ("usage", "d", "T"), ("potential", "d", "T"), ("tr_overload_hist", "d", "TrT"),
-                 ("cs_power_hist", "d", "CT"), ("cs_current_hist", "d", "CT"),
+                 ("cs_power_hist", "d", "CT"), ("cs_current_hist", "d", "CT"), ("node_voltage", "d", "NT"),
                  ("load_fc_live", "d", "TrT"), ("pv_fc_live", "d", "TrT"),
                  ("ev_spawned", "i", "S"), ("ev_final_cap", "d", "S"), ("ev_afap", "d", "S"), ("ev_soc_sum", "d", "S"),
                  ("ev_n_hist", "i", "S"), ("ev_abs_energy", "d", "S"), ("ev_em_metric", "i", "S"), ("ev_n_act", "i", "S"),
@@ -65,13 +68,14 @@ class _State(C.Structure):
 
 
 _OUT_ARRAYS = [("cs_power", "C"), ("cs_current", "C"), ("tr_power", "Tr"), ("tr_amps", "Tr"),
-               ("tr_overload", "Tr"), ("dep_sat", "P"), ("action_mask", "P"), ("obs", "D"), ("actions_eff", "P")]
+               ("tr_overload", "Tr"), ("dep_sat", "P"), ("action_mask", "P"), ("obs", "D"), ("actions_eff", "P"),
+               ("node_vm", "N")]
 
 
 class _Out(C.Structure):
     _fields_ = [("reward", C.c_double), ("total_costs", C.c_double), ("done", C.c_int),
                 ("invalid_actions", C.c_int), ("n_departed", C.c_int), ("n_arrived", C.c_int), ("error", C.c_int)] + \
-               [(n, _pd) for n, _ in _OUT_ARRAYS]
+               [(n, _pd) for n, _ in _OUT_ARRAYS] + [("pf_iterations", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -130,6 +134,11 @@ class _TopoC:
         t.cs_imax, t.cs_imin, t.cs_imax_dis, t.cs_imin_dis, t.cs_voltage = _p(topo.cs_imax), _p(topo.cs_imin), \
             _p(topo.cs_imax_dis), _p(topo.cs_imin_dis), _p(topo.cs_voltage)
         t.tr_voltage = float(topo.tr_voltage)
+        t.n_bus = topo.n_bus
+        if topo.n_bus:
+            self._K = np.ascontiguousarray(topo.grid_K).view(np.float64).reshape(-1)
+            self._L = np.ascontiguousarray(topo.grid_L).view(np.float64).reshape(-1)
+            t.grid_K, t.grid_L, t.s_base = _p(self._K), _p(self._L), float(topo.grid_s_base)
         self.c = t
 
 
@@ -148,6 +157,13 @@ class _ScnC:
                 setattr(s, "s_" + k, _p(v))
         s.n_luts, s.lut_len = sc.luts_c.shape[0], sc.luts_c.shape[1]
         s.luts_c, s.luts_d = _p(sc.luts_c), _p(sc.luts_d)
+        self._ga = np.ascontiguousarray(sc.grid_active, dtype=np.float64).reshape(-1)
+        self._gr = np.ascontiguousarray(sc.grid_reactive, dtype=np.float64).reshape(-1)
+        self._df = np.ascontiguousarray(sc.date_feat, dtype=np.float64).reshape(-1)
+        if self._ga.size:
+            s.grid_active, s.grid_reactive = _p(self._ga), _p(self._gr)
+        if self._df.size:
+            s.date_feat = _p(self._df)
         self.c = s
 
 
@@ -160,7 +176,7 @@ STAT_NAMES = ("total_ev_served", "total_profits", "total_energy_charged", "total
 
 def _sizes(topo, D, S=1):
     S = max(int(S), 1)
-    return {"S": S, "ST": S * topo.T, "P": topo.P, "C": topo.C, "T": topo.T, "Tr": max(topo.Tr, 1), "TrT": max(topo.Tr, 1) * topo.T,
+    return {"N": topo.n_bus + 1, "NT": (topo.n_bus + 1) * topo.T, "S": S, "ST": S * topo.T, "P": topo.P, "C": topo.C, "T": topo.T, "Tr": max(topo.Tr, 1), "TrT": max(topo.Tr, 1) * topo.T,
             "CT": topo.C * topo.T, "D": max(D, 1)}
 
 

@@ -25,6 +25,7 @@ def test_oracle_matches_reference_trace_bit_exact(name):
     tr = np.load(f"{GOLDEN}/{name}.trace.npz")
     env = OracleEnv(pack.topo, pack.scenarios[0], reward=str(tr["reward_fn"]), state=str(tr["state_fn"]))
     assert _eq(env.reset(), tr["obs0"])
+    grid = "node_voltage" in tr.files
     T = tr["reward"].shape[0]
     for t in range(T):
         r = env.step(tr["actions"][t])
@@ -32,7 +33,11 @@ def test_oracle_matches_reference_trace_bit_exact(name):
         for k in ("obs", "cs_power", "cs_current", "tr_power", "tr_amps", "tr_overload", "action_mask",
                   "actions_eff"):
             assert _eq(r[k], tr[k][t]), (k, t)
-        assert r["reward"] == tr["reward"][t], t
+        if grid:      # BLAS zgemv sums the 33 products of a power-flow row in its own order: 1e-12, not bit-exact
+            assert r["reward"] == pytest.approx(tr["reward"][t], rel=1e-12, abs=1e-12), t
+            assert np.allclose(r["node_vm"], tr["node_voltage"][:, t], rtol=0, atol=1e-13), t
+        else:
+            assert r["reward"] == tr["reward"][t], t
         assert r["total_costs"] == tr["total_costs"][t], t
         assert r["invalid_actions"] == tr["invalid"][t] and r["n_departed"] == tr["n_departed"][t], t
         occ = r["port_session"] >= 0
@@ -43,7 +48,7 @@ def test_oracle_matches_reference_trace_bit_exact(name):
         assert np.array_equal(sess_arr, tr["port_t_arr"][t]), t
         assert r["done"] == bool(tr["done"][t])
     assert _eq(r["usage"], tr["usage"]) and _eq(r["potential"], tr["potential"])
-    assert env.total_reward == float(tr["total_reward"])
+    assert env.total_reward == pytest.approx(float(tr["total_reward"]), rel=1e-12 if grid else 0, abs=0)
     with pytest.raises(AssertionError):
         env.step(tr["actions"][0])      # ev2gym_env.py:343
 

@@ -44,7 +44,21 @@ from ev2gym.baselines import heuristics as ref_agents  # noqa: E402
 from ev2gym_b200.reference_export import scenario_from_env, topology_from_env  # noqa: E402
 from ev2gym_b200.scenario import ScenarioPack  # noqa: E402
 
+import ev2gym.models.data_augment as _da  # noqa: E402
+
+
+def _synthetic_bus_loads(self, n_buses, n_steps, start_day, start_step):
+    """Stand-in for the un-vendored copula sampler (`multicopula`, data_augment.py:68-92), which only feeds
+    INPUTS (bus load shapes) to the grid path: a deterministic daily sinusoid + noise per bus."""
+    rng = np.random.default_rng(1000 * start_day + start_step)
+    x = np.linspace(0, 2 * np.pi * n_steps / 96, n_steps)[:, None]
+    return 0.5 + 0.3 * np.sin(x + rng.uniform(0, 6, (1, n_buses))) + 0.1 * rng.random((n_steps, n_buses))
+
+
+_da.DataGenerator.sample_data = _synthetic_bus_loads
+
 PAIRS = {  # config -> (state, reward)   train_stable_baselines.py:39-51
+    "V2Ggrid": ("V2G_grid_state", "V2G_grid_full_reward"),
     "PublicPST": ("PublicPST", "SquaredTrackingErrorReward"),
     "V2GProfitMax": ("V2G_profit_max", "profit_maximization"),
     "V2GProfitPlusLoads": ("V2G_profit_max_loads", "ProfitMax_TrPenalty_UserIncentives"),
@@ -100,6 +114,8 @@ def make_actions(kind: str, env, rng) -> np.ndarray:
 
 
 def record_episode(base, overrides, seed, agent, state=None, reward=None):
+    overrides = dict(overrides)
+    reward = overrides.pop("_reward", reward)
     env, st, rw = make_env(base, overrides, seed, state, reward)
     obs0, _ = env.reset(seed=seed)
     topo, scn = topology_from_env(env), scenario_from_env(env)
@@ -165,6 +181,11 @@ def record_episode(base, overrides, seed, agent, state=None, reward=None):
               "battery_degradation_calendar", "battery_degradation_cycling", "total_reward"):
         out["stat_" + k] = np.array(float(stats[k]))
     out["afap"] = np.array([ev.max_energy_AFAP for ev in env.EVs], dtype=np.float64)   # ev.py:407-440, spawn order
+    if env.simulate_grid:
+        out["node_voltage"] = env.node_voltage.copy()                   # [nb, T]
+        out["node_active_power"] = env.node_active_power.copy()
+        out["node_reactive_power"] = env.node_reactive_power.copy()
+        out["node_ev_power"] = env.node_ev_power.copy()
     out["state_fn"], out["reward_fn"] = np.array(st), np.array(rw)
     out["seed"], out["agent"], out["base"] = np.array(seed), np.array(agent), np.array(base)
     return topo, scn, out
@@ -193,6 +214,9 @@ CASES = [
      {"number_of_charging_stations": 6, "number_of_ports_per_cs": 2, "v2g_enabled": True,
       "charging_station": {"min_charge_current": 6, "max_charge_current": 32, "max_discharge_current": -32,
                            "min_discharge_current": -6}}, 8, "mixed"),
+    ("grid_c40_uniform_s3", "V2Ggrid", {"number_of_charging_stations": 40}, 3, "uniform"),          # Laurent power flow
+    ("grid_c20n2_mixed_s5", "V2Ggrid", {"number_of_charging_stations": 20, "number_of_ports_per_cs": 2,
+                                       "_reward": "V2G_grid_simple_reward"}, 5, "mixed"),
     ("ts10_c5_uniform_s10", "V2GProfitMax", {"number_of_charging_stations": 5, "timescale": 10,
                                              "simulation_length": 150}, 10, "uniform"),
 ]
