@@ -39,6 +39,10 @@ WORKLOADS = {
            "V2GProfitPlusLoads.yaml, 4096 envs x 100 chargers x 2 ports, 5 transformers, uniform actions"),
     "c3-1k": ("c3_v2gloads_c100n2tr5", 1024, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads",
               "V2GProfitPlusLoads.yaml, 1024 envs x 100 chargers x 2 ports, 5 transformers, uniform actions"),
+    # BASELINE config 5 names a BusinessPST.yaml that does not exist in the reference and a 20-transformer grid that
+    # matches no shipped network: synthesised here -- 21-bus feeder, 500 chargers, synthetic scenarios.
+    "c5": ("synthetic:grid:C500:Tr20", 2048, "V2G_grid_full_reward", "V2G_grid_state",
+           "synthetic BusinessPST-like + 21-bus Laurent power flow, 2048 envs x 500 chargers x 1 port, 20 transformers"),
     "c4": ("c4_v2gprofitmax_c250", 8192, "profit_maximization", "V2G_profit_max",
            "V2GProfitMax.yaml, 8192 envs x 250 chargers x 1 port, 1 transformer, uniform actions"),
 }
@@ -47,6 +51,13 @@ L2_BYTES = 126e6
 
 def load_pack(name):
     from ev2gym_b200.scenario import ScenarioPack
+    if name.startswith("synthetic:grid"):
+        from ev2gym_b200.scenario import Topology
+        from ev2gym_b200.synthetic import add_grid, sample_bank
+        topo = Topology.uniform(C=500, n_ports=1, Tr=20, T=96, imax=32.0)
+        bank = sample_bank(topo, 16, seed=5, loads=False)
+        add_grid(topo, bank, seed=5)
+        return ScenarioPack(topo, bank, name)
     return ScenarioPack.load(os.path.join(ROOT, "ev2gym_b200", "data", name + ".npz"))
 
 
@@ -158,6 +169,7 @@ def main():
     ap.add_argument("--steps", type=int, default=448)
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--skip-agent-rollout", action="store_true")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
@@ -267,6 +279,8 @@ def main():
     # ---- k-step device-agent rollout (ev2b_step_k): no action tensor, no host round trip -----------------
     agent_rate = None
     try:
+        if args.skip_agent_rollout:
+            raise RuntimeError("skipped")
         reset_all()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -32,7 +32,8 @@ class Dims(C.Structure):
 
 class TopologyView(C.Structure):
     _fields_ = [("cs_n_ports", _pi), ("cs_tr", _pi), ("cs_phases", _pi), ("cs_imax", _pd), ("cs_imin", _pd),
-                ("cs_imax_dis", _pd), ("cs_imin_dis", _pd), ("cs_voltage", _pd)]
+                ("cs_imax_dis", _pd), ("cs_imin_dis", _pd), ("cs_voltage", _pd),
+                ("n_bus", C.c_int32), ("grid_K", _pd), ("grid_L", _pd), ("grid_s_base", C.c_double)]
 
 
 _SCN_F64 = ("charge_price", "discharge_price", "setpoint", "tr_infl", "tr_solar", "tr_max_power", "tr_min_power",
@@ -47,14 +48,15 @@ class ScenariosView(C.Structure):
                [(k, _pd) for k in _SCN_F64] + \
                [("dr_start", _pi), ("dr_end", _pi), ("dr_cap", _pd), ("dr_count", _pi), ("sess_off", _pl)] + \
                [(k, _pi) for k in _SESS_I] + [(k, _pd) for k in _SESS_D] + \
-               [("lut_off", _pl), ("luts_c", _pd), ("luts_d", _pd)]
+               [("lut_off", _pl), ("luts_c", _pd), ("luts_d", _pd), ("grid_active", _pd), ("grid_reactive", _pd),
+                ("date_feat", _pd)]
 
 
 class StepOut(C.Structure):
     _fields_ = [("reward", C.c_void_p), ("status", C.c_void_p), ("obs", C.c_void_p), ("cs_power", C.c_void_p),
                 ("cs_current", C.c_void_p), ("tr_power", C.c_void_p), ("tr_overload", C.c_void_p),
                 ("total_costs", C.c_void_p), ("action_mask", C.c_void_p), ("dep_sat", C.c_void_p),
-                ("dep_cap", C.c_void_p), ("port_energy", C.c_void_p)]
+                ("dep_cap", C.c_void_p), ("port_energy", C.c_void_p), ("node_voltage", C.c_void_p)]
 
 
 class StateView(C.Structure):

@@ -70,6 +70,9 @@ struct ev2b_handle {
     int L = 1;
     DevBuf<double> st_soc_sum, st_abs_e, st_act, st_r, cs_sat_sum, cs_dcal, cs_dcyc;
     DevBuf<int> st_cnt, st_nfin, cs_served, cs_em;
+    // device: distribution grid
+    int n_bus = 0; double s_base = 1000.0;
+    DevBuf<double2> grid_Kt, grid_L; DevBuf<double> grid_act, grid_rea, date_feat;
     // e2e staging (ev2b_step_host)
     DevBuf<unsigned char> st_actions; DevBuf<double> st_reward; DevBuf<uint32_t> st_status; DevBuf<float> st_obs;
     DevBuf<int> st_scn;
@@ -93,6 +96,8 @@ struct ev2b_handle {
         p.p_magic = P > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)P) + 1u : 0u;
         p.c_magic = C > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)C) + 1u : 0u;
         p.cs_uniform = cs_uniform; p.cs0 = cs_h.empty() ? CsStatic{} : cs_h[0];
+        p.n_bus = n_bus; p.s_base = s_base; p.grid_Kt = grid_Kt.p; p.grid_L = grid_L.p; p.grid_act = grid_act.p;
+        p.grid_rea = grid_rea.p; p.date_feat = date_feat.p;
         p.stats = (dims.flags & EV2B_F_STATS) ? 1 : 0; p.L = L;
         {   // ev.py:456-516 constants
             const double b_age = 2 * 365, d_dist = 15000, Gk = 0.186, b_cap_ah = 2.05, b_cap_kwh = 78;
@@ -124,6 +129,7 @@ static int obs_dim_for(int kind, int P, int Tr) {
     case EV2B_STATE_PUBLIC_PST: return 3 + 3 * P;
     case EV2B_STATE_V2G_PROFIT_MAX: return 22 + 2 * P;
     case EV2B_STATE_V2G_PROFIT_MAX_LOADS: return 22 + 40 * Tr + 2 * P;
+    case EV2B_STATE_V2G_GRID: return 6 + 2 * Tr + 3 * P;          // n_bus == Tr in grid mode
     default: return 0;
     }
 }
@@ -155,7 +161,7 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
         if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, false>);          \
         return go(step_kernel<ActT, 0, false, MAXT, MINB, false>);                      \
     } while (0)
-    const bool stats = (h->dims.flags & EV2B_F_STATS) != 0;
+    const bool stats = (h->dims.flags & EV2B_F_STATS) != 0 || h->n_bus > 0;   // the HEAVY instantiation
 #ifndef EV2B_MINB128
 #define EV2B_MINB128 8
 #endif
@@ -229,6 +235,16 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         for (int j = 0; j < s.n_ports; ++j) h->port_cs.push_back(c);
     }
     h->P = off;
+    if (tp->n_bus > 0) {
+        if (tp->n_bus != h->Tr || tp->n_bus > 128 || !tp->grid_K || !tp->grid_L) {
+            delete h; g_create_error = "ev2b_create: grid needs n_bus == n_transformers <= 128 and K, L"; return EV2B_E_ARG;
+        }
+        h->n_bus = tp->n_bus; h->s_base = tp->grid_s_base;
+    }
+    if ((d->reward_kind == EV2B_REWARD_GRID_FULL || d->reward_kind == EV2B_REWARD_GRID_SIMPLE ||
+         d->state_kind == EV2B_STATE_V2G_GRID) && h->n_bus == 0) {
+        delete h; g_create_error = "ev2b_create: grid reward/state functions need a grid (n_bus > 0)"; return EV2B_E_ARG;
+    }
     h->n_cls = (int)cls_of.size();
     h->np_uniform = uniform_ports ? h->cs_h[0].n_ports : 0;
     h->cs_uniform = (uniform_ports && h->n_cls == 1) ? 1 : 0;
@@ -249,6 +265,9 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         const int kind = d->state_kind;
         const int tuple = kind == EV2B_STATE_PUBLIC_PST ? 3 : 2;
         int o = kind == EV2B_STATE_PUBLIC_PST ? 3 : 22;
+        if (kind == EV2B_STATE_V2G_GRID)      // charger-major, 3 values per port  state.py:262-274
+            for (int pp = 0; pp < h->P; ++pp) slot[pp] = 6 + 2 * h->n_bus + 3 * pp;
+        else
         for (int k = 0; k < h->Tr; ++k) {
             if (kind == EV2B_STATE_V2G_PROFIT_MAX_LOADS) { tr_obs[k] = o; o += 40; }
             for (int i = tr_off[k]; i < tr_off[k + 1]; ++i) {
@@ -263,6 +282,10 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         for (int i = 0; i < 20; ++i) series_off_h.push_back(2 + i);
         if (d->state_kind == EV2B_STATE_V2G_PROFIT_MAX_LOADS)
             for (int k = 0; k < h->Tr; ++k) for (int j = 0; j < 40; ++j) series_off_h.push_back(tr_obs[k] + j);
+    }
+    if (d->state_kind == EV2B_STATE_V2G_GRID) {
+        for (int i = 0; i < 5; ++i) series_off_h.push_back(i);
+        for (int i = 0; i < 2 * h->n_bus; ++i) series_off_h.push_back(6 + i);
     }
     h->W = (int)series_off_h.size();
     // launch shape: a CTA owns EPB whole envs, one thread per (env, charger)
@@ -283,7 +306,8 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         h->EPB = best_epb;
         h->block = std::max(32, (best_epb * C + 31) / 32 * 32);
         const size_t PP = (size_t)h->EPB * h->P;
-        h->smem = sizeof(double) * ((size_t)kNRed * h->block + 3 * PP + (size_t)h->EPB * h->Tr + (size_t)h->EPB * kNRed) +
+        h->smem = sizeof(double) * ((size_t)kNRed * h->block + 3 * PP + 2 * (size_t)h->EPB * h->Tr + (size_t)h->EPB + 1 +
+                                    6 * (size_t)h->EPB * h->n_bus + (size_t)h->EPB * kNRed) +
                   sizeof(uint2) * PP + sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4 + PP + 4 + 1) +
                   PP + 16;
     }
@@ -296,6 +320,15 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     CREATE_TRY(h->tr_obs_off.upload(tr_obs));
     CREATE_TRY(h->port_cs_d.upload(h->port_cs));
     CREATE_TRY(h->series_off.upload(series_off_h));
+    if (h->n_bus > 0) {
+        const int n = h->n_bus;
+        std::vector<double2> kt((size_t)n * n), lv(n);
+        for (int r = 0; r < n; ++r) {
+            for (int c2 = 0; c2 < n; ++c2) kt[(size_t)c2 * n + r] = make_double2(tp->grid_K[2 * ((size_t)r * n + c2)], tp->grid_K[2 * ((size_t)r * n + c2) + 1]);
+            lv[r] = make_double2(tp->grid_L[2 * r], tp->grid_L[2 * r + 1]);
+        }
+        CREATE_TRY(h->grid_Kt.upload(kt)); CREATE_TRY(h->grid_L.upload(lv));
+    }
     const size_t EP = (size_t)h->E * h->P;
     CREATE_TRY(h->hot.alloc(EP)); CREATE_TRY(h->cap.alloc(EP)); CREATE_TRY(h->exch.alloc(EP));
     CREATE_TRY(h->env_step.alloc(h->E)); CREATE_TRY(h->env_scn.alloc(h->E));
@@ -514,6 +547,18 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
                 d.end = (int16_t)std::max(-32000, std::min(32000, b->dr_end[di]));
                 d.value = (float)(limit - limit * b->dr_cap[di] / 100.0);   // transformer.py:158-159
             }
+        }
+    }
+    {
+        const size_t nd = (size_t)S * (T + 1) * 3;
+        std::vector<double> df(nd, 0.0);
+        if (b->date_feat) std::copy(b->date_feat, b->date_feat + nd, df.begin());
+        CUDA_TRY(h, h->date_feat.upload(df));
+        if (h->n_bus > 0) {
+            if (!b->grid_active || !b->grid_reactive) return h->fail(EV2B_E_SCENARIO, "grid handle: scenarios need grid_active / grid_reactive");
+            const size_t ng = (size_t)S * (T + 1) * h->n_bus;
+            std::vector<double> ga(b->grid_active, b->grid_active + ng), gr(b->grid_reactive, b->grid_reactive + ng);
+            CUDA_TRY(h, h->grid_act.upload(ga)); CUDA_TRY(h, h->grid_rea.upload(gr));
         }
     }
     if (luts_c.empty()) { luts_c.assign(lut_len, 1.0); luts_d.assign(lut_len, 1.0); }

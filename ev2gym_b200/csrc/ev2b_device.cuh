@@ -96,6 +96,12 @@ struct Params {
     const double *luts_c, *luts_d; const double *pot_kw;
     const float *trA, *trF, *tr_limit; const DrEv *dr; const uint8_t *dr_count;
     const float *obs_static;   // [S][T+1][W] precomputed price window + forecast/limit blocks, or null
+    // distribution grid: Laurent power flow  grid.py:120-141, numbarize.py:268-325
+    int n_bus; double s_base;
+    const double2 *grid_Kt;    // [n_bus][n_bus] K transposed (Kt[c][r] = K[r][c]): lanes read consecutive rows
+    const double2 *grid_L;     // [n_bus]
+    const double *grid_act, *grid_rea;   // [S][T+1][n_bus]
+    const double *date_feat;   // [S][T+1][3]
     // statistics mode (EV2B_F_STATS): per-EV histories for get_statistics  utils.py:12-123, ev.py:442-521
     int stats, L;              // L: trace slots per port (longest session + 2)
     double k_cal, k_exp, k_cyc; // 0.75/730^0.25, exp(-e2/theta), 0.5*(2.05/78)/sqrt(Q_acc)
@@ -156,7 +162,9 @@ __device__ __forceinline__ const CsStatic &cs_of(const Params &p, int c) {
 // ---- observation pieces shared by the step and reset kernels --------------------------------
 // Header of the stock state functions at observation time tq (= current_step after the increment).
 __device__ __forceinline__ void obs_header(const Params &p, float *row, int s, int tq, double prev_usage) {
-    if (p.state_kind == EV2B_STATE_PUBLIC_PST) {                    // state.py:11-34
+    if (p.state_kind == EV2B_STATE_V2G_GRID) {                      // state.py:247 (the rest of the header is static)
+        row[5] = (float)prev_usage;
+    } else if (p.state_kind == EV2B_STATE_PUBLIC_PST) {             // state.py:11-34
         row[0] = (float)((double)tq / (double)p.T);
         row[1] = (tq < p.T) ? (float)p.env_t[(size_t)s * p.T + tq].setpoint : 0.f;
         row[2] = (float)prev_usage;
@@ -168,6 +176,14 @@ __device__ __forceinline__ void obs_header(const Params &p, float *row, int s, i
 // One value of the (scenario, time)-only part of the observation: i indexes the flat list
 // [20 prices][Tr * (20 load-pv forecast + 20 power limits)].
 __device__ __forceinline__ float obs_series_value(const Params &p, int s, int tq, int i) {
+    if (p.state_kind == EV2B_STATE_V2G_GRID) {                      // V2G_grid_state  state.py:221-255
+        if (i < 3) return (float)p.date_feat[((size_t)s * (p.T + 1) + tq) * 3 + i];
+        if (i == 3) return (tq < p.T) ? (float)p.env_t[(size_t)s * p.T + tq].cp : 0.f;        // charge_prices[0, t:t+1]
+        if (i == 4) return (tq < p.T) ? (float)p.env_t[(size_t)s * p.T + tq].setpoint : 0.f;
+        const int j = i - 5;   // node_active_power[1:, step-1] == base powers of step `step` (grid.step returns the next step's)
+        const size_t base = ((size_t)s * (p.T + 1) + tq) * p.n_bus;
+        return (float)(j < p.n_bus ? p.grid_act[base + j] : p.grid_rea[base + j - p.n_bus]);
+    }
     if (i < 20)                                                     // abs(charge_prices[0, t:t+20]), zero padded
         return (tq + i < p.T) ? (float)fabs(p.env_t[(size_t)s * p.T + tq + i].cp) : 0.f;
     i -= 20;
@@ -289,7 +305,7 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
             energy = given_energy;
             cap += given_energy;
         }
-        if (STATS) { const double be = __ldg(&sp->bmin_em); em_cross = prev_cap > be && cap < be; }   // :401-402
+        if (STATS && p.stats) { const double be = __ldg(&sp->bmin_em); em_cross = prev_cap > be && cap < be; }   // :401-402
         act_amps = ev2b_div_c(ev2b_div_c(given_energy * 60.0, p.period, p.rperiod) * 1000.0, veff, rveff);   // :405
     }
     cap = ev2b_div_c(ceil(cap * 100.0), 100.0, 0.01);                              // my_ceil  ev.py:183,188-189
@@ -326,9 +342,71 @@ __device__ __noinline__ void finalize_ev(const Params &p, size_t ip, int e_c, co
     p.st_nfin[ip] = k_fin + 1;
 }
 
+// ---- B2: Laurent power flow of one env by one warp  (grid.py:120-141, numbarize.py:268-325) ----------
+// S/V/Lm: shared scratch [n_bus] each; trp_env: transformer (= bus) EV power of this env.  Returns the
+// voltage-band loss sum(min(0, 0.05 - |1 - vm|)) (reward.py:107-110) in every lane.
+__device__ __forceinline__ double power_flow_env(const Params &p, double2 *S, const double *trp_env, int js, int jt, int je,
+                                              int lane) {
+    const int n = p.n_bus;
+    double2 *V = S + n, *Lm = V + n;
+            const size_t gb = ((size_t)js * (p.T + 1) + jt) * n;
+    for (int r = lane; r < n; r += 32) {                     // S = (P + jQ) / s_base, flat start  grid_tensor.py:594-630
+        S[r] = make_double2((p.grid_act[gb + r] + trp_env[r]) / p.s_base, p.grid_rea[gb + r] / p.s_base);
+        V[r] = make_double2(1.0, 0.0);
+    }
+    __syncwarp();
+    int it = 0; double tol = 1e300;
+    while (it < 100 && tol >= 1e-6) {
+        for (int r = lane; r < n; r += 32) {                 // lambda = conj(S * (1 / v0))   numbarize.py:304
+            const double a = V[r].x, b = V[r].y;
+            double rr, ri;                                   // numpy complex reciprocal (Smith)
+            if (fabs(a) >= fabs(b)) { const double rat = b / a, scl = 1.0 / (a + b * rat); rr = scl; ri = (0.0 - rat) * scl; }
+            else { const double rat = a / b, scl = 1.0 / (b + a * rat); rr = rat * scl; ri = (0.0 - 1.0) * scl; }
+            Lm[r] = make_double2(S[r].x * rr - S[r].y * ri, -(S[r].x * ri + S[r].y * rr));
+        }
+        __syncwarp();
+        double dmax = 0.0;
+        double2 nv[4];                                       // rows lane, lane+32, ... (n_bus <= 128)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = lane + 32 * q;
+            nv[q] = make_double2(0.0, 0.0);
+            if (r < n) {
+                double zr = 0.0, zi = 0.0;
+                for (int c2 = 0; c2 < n; ++c2) {             // Z = K @ lambda   numbarize.py:305
+                    const double2 kk = __ldg(&p.grid_Kt[(size_t)c2 * n + r]);
+                    const double2 lm = Lm[c2];
+                    zr += kk.x * lm.x - kk.y * lm.y;
+                    zi += kk.x * lm.y + kk.y * lm.x;
+                }
+                const double2 ll = __ldg(&p.grid_L[r]);
+                nv[q] = make_double2(zr + ll.x, zi + ll.y);  // voltage_k = Z + L
+                dmax = fmax(dmax, fabs(hypot(nv[q].x, nv[q].y) - hypot(V[r].x, V[r].y)));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        tol = dmax;                                          // numbarize.py:308
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int r = lane + 32 * q; if (r < n) V[r] = nv[q]; }
+        __syncwarp();
+        ++it;
+    }
+    double lv = 0.0;                                         // sum(min(0, 0.05 - |1 - vm|)) incl. the slack (vm = 1)
+    for (int r = lane; r < n; r += 32) {
+        const double vm = hypot(V[r].x, V[r].y);
+        const double x = 0.05 - fabs(1.0 - vm);
+        lv += x < 0.0 ? x : 0.0;
+        if (p.out.node_voltage) p.out.node_voltage[(size_t)je * (n + 1) + r + 1] = vm;
+    }
+    lv = warp_sum(lv);
+    return lv;
+}
+
 // ---- the fused step kernel --------------------------------------------------------------------
 // ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = ragged (CsStatic).
-template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool STATS>
+template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool HEAVY>   // HEAVY: statistics mode and/or distribution grid compiled in
 __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
@@ -338,7 +416,10 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     double *resA  = resE + PP;                                            // [PP] actual amps out
     double *resC  = resA + PP;                                            // [PP] battery level in/out (-1: EV inactive)
     double *trov  = resC + PP;                                            // [EPB*Tr] overload per transformer
-    double *envs  = trov + (size_t)p.EPB * p.Tr;                          // [EPB][kNRed]
+    double *trp   = trov + (size_t)p.EPB * p.Tr;                          // [EPB*Tr] transformer power (grid: bus EV power)
+    double *lossv = trp + (size_t)p.EPB * p.Tr;                           // [EPB] voltage-band loss  reward.py:107-110
+    double2 *pfv  = reinterpret_cast<double2 *>(lossv + p.EPB + (p.EPB & 1));   // [EPB][3][n_bus] S, V, lambda
+    double *envs  = reinterpret_cast<double *>(pfv + (size_t)p.EPB * 3 * p.n_bus);   // [EPB][kNRed]
     uint2  *whot  = reinterpret_cast<uint2 *>(envs + (size_t)p.EPB * kNRed);   // [PP] hot words z, w of work items
     int    *cnt   = reinterpret_cast<int *>(whot + PP);                   // [NT] invalid | dep<<10 | arr<<20
     int    *envi  = cnt + NT;                                             // [EPB][4] t, scn, cnt, flags
@@ -465,8 +546,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             const uint2 hw = whot[pl];
             double cap = resC[pl], energy, amps;
             bool em_cross;
-            const bool active = ev_step_item<STATS>(p, cs, hw.x, hw.y, resE[pl], cap, energy, amps, em_cross);
-            if (STATS && em_cross) {   // min_emergency_battery_capacity_metric  ev.py:401-402 (integer atomics: order-free)
+            const bool active = ev_step_item<HEAVY>(p, cs, hw.x, hw.y, resE[pl], cap, energy, amps, em_cross);
+            if (HEAVY && p.stats && em_cross) {   // min_emergency_battery_capacity_metric  ev.py:401-402 (integer atomics: order-free)
                 const int jel = p.EPB == 1 ? 0 : (int)__umulhi((unsigned)pl, p.p_magic);
                 atomicAdd(&p.cs_em[(size_t)((p.env0 + blockIdx.x * p.EPB) + jel) * p.C + p.port_cs[port]], 1);
             }
@@ -520,7 +601,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 rA += act_amps;                                           // :181,197
             }
             if (rA - 0.0001 > cs.imax) overflow = true;                   // :203-205
-            if (STATS && occ) {      // EV.step bookkeeping: historic_soc / active_steps / |energy|  ev.py:156,178-185
+            if (HEAVY && p.stats && occ) {      // EV.step bookkeeping: historic_soc / active_steps / |energy|  ev.py:156,178-185
                 const EvSpec *sq = p.spec + hot_spec(hj);
                 const double soc0 = ev2b_div_c(cv_old, __ldg(&sq->B), __ldg(&sq->rB));
                 int cn = p.st_cnt[ip];
@@ -539,11 +620,14 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             if (occ && t >= hot_t_dep(hj)) {
                 const double des = __ldg(&p.spec[hot_spec(hj)].desired);
                 const double sat = (cv < des - 0.001) ? cv / des : 1.0;
-                rSatExp += 100.0 * exp(-10.0 * sat);                      // reward.py:42,85
+                if (p.reward_kind == EV2B_REWARD_GRID_FULL || p.reward_kind == EV2B_REWARD_GRID_SIMPLE)
+                    rSatExp += (cv - des) * (cv - des);                   // -user_costs  reward.py:99-102
+                else
+                    rSatExp += 100.0 * exp(-10.0 * sat);                  // reward.py:42,85
                 rSat += sat;
                 rCnt += 1 << 10;
                 dsat = sat; dcap = cv;
-                if (STATS) {
+                if (HEAVY && p.stats) {
                     const size_t ec = (size_t)e * p.C + c;
                     p.cs_sat_sum[ec] += sat; p.cs_served[ec] += 1;          // ev_charger.py:218-220
                     const SessRec r0 = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj) - 1];
@@ -563,11 +647,11 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 p.exch[ip] = 0.f;
                 exch_new = 0.f; exch_valid = true;
                 rCnt += 1 << 20;
-                if (STATS) { p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0; }
+                if (HEAVY && p.stats) { p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0; }
             }
             const bool occ_after = hot_t_arr(hj) <= tq && tq <= hot_t_dep(hj);
             if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;          // ev2gym_env.py:452-457
-            if (STATS && occ_after && tq >= p.T) {   // episode over: EVs still connected count too (env.EVs)
+            if (HEAVY && p.stats && occ_after && tq >= p.T) {   // episode over: EVs still connected count too (env.EVs)
                 const SessRec r0 = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj) - 1];
                 finalize_ev(p, ip, (int)((size_t)e * p.C + c), p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj),
                             hot_t_dep(hj), cv);
@@ -579,7 +663,11 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 if (cv < B && hot_t_dep(hj) > tq) rPot += __ldg(&p.pot_kw[hot_spec(hj) * p.n_cls + cs.cls]);
                 if (want_obs) {       // observation tuple (transformer-major slot)   state.py:37-57, 85-102, 137-151
                     float *o = obs_row + p.obs_slot[port0 + j];
-                    if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
+                    if (p.state_kind == EV2B_STATE_V2G_GRID) {          // state.py:262-270
+                        o[0] = (float)cv;
+                        o[1] = (float)(hot_t_dep(hj) - tq + 1);
+                        o[2] = (float)cs.tr;
+                    } else if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
                         o[0] = (cv == B) ? 1.f : 0.5f;
                         o[1] = exch_valid ? exch_new : (NP > 0 ? exch0[j] : p.exch[ip]);
                         o[2] = (float)(tq - hot_t_arr(hj));
@@ -591,7 +679,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             } else if (want_obs && (occ || p.obs_full)) {     // the port just emptied (or a full rewrite was asked for)
                 float *o = obs_row + p.obs_slot[port0 + j];
                 o[0] = 0.f; o[1] = 0.f;
-                if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
+                if (p.state_kind == EV2B_STATE_PUBLIC_PST || p.state_kind == EV2B_STATE_V2G_GRID) o[2] = 0.f;
             }
         }
         // clamp the charger's potential                      utils.py:779-789
@@ -639,6 +727,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                         double ov = 0.0;
                         if (ptot > tt.maxp + 0.0001 || ptot < tt.minp - 0.0001) ov = fabs(ptot - tt.maxp);
                         trov[jel * p.Tr + k] = ov;
+                        trp[jel * p.Tr + k] = ptot;
                         if (EV2B_OPT(p.out.tr_power))    p.out.tr_power[(size_t)je * p.Tr + k] = ptot;
                         if (EV2B_OPT(p.out.tr_overload)) p.out.tr_overload[(size_t)je * p.Tr + k] = ov;
                     }
@@ -672,6 +761,20 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     }
     __syncthreads();
 
+    // ---- B2: distribution grid: Laurent power flow, one warp per env ------------------------------------
+    if (HEAVY && p.n_bus > 0) {
+        const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5, n = p.n_bus;
+        for (int jel = warp; jel < p.EPB; jel += nwarps) {
+            const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
+            if (je >= p.env_end) continue;
+            const int jt = envi[jel * 4 + 0];
+            if (jt >= p.T) continue;
+            const double lv = power_flow_env(p, pfv + (size_t)jel * 3 * n, trp + jel * p.Tr, envi[jel * 4 + 1], jt, je, lane);
+            if (lane == 0) { lossv[jel] = lv; if (p.out.node_voltage) p.out.node_voltage[(size_t)je * (n + 1)] = 1.0; }
+        }
+        __syncthreads();
+    }
+
     // ---- C: one thread per env: reward, KPIs, step counter ---------------------------------------
     if (tid < p.EPB) {
         const int je = (p.env0 + blockIdx.x * p.EPB) + tid;
@@ -695,6 +798,10 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                     reward = costs - 100.0 * ovsum - v[RedSatExp];
                 } else if (p.reward_kind == EV2B_REWARD_PROFIT_MAX) {          // reward.py:81-87
                     reward = costs - v[RedSatExp];
+                } else if (p.reward_kind == EV2B_REWARD_GRID_FULL) {           // reward.py:89-111
+                    reward = costs + 1000.0 * lossv[tid] - v[RedSatExp];
+                } else if (p.reward_kind == EV2B_REWARD_GRID_SIMPLE) {         // reward.py:114-121
+                    reward = 1000.0 * lossv[tid];
                 }
                 double *kpi = p.env_kpi + (size_t)je * EV2B_KPI_COUNT;
                 kpi[EV2B_KPI_TOTAL_REWARD] += reward;

@@ -15,8 +15,9 @@ from . import _lib
 from .scenario import LUT_LEN, SESSION_F64_FIELDS, SESSION_INT_FIELDS, Scenario, Topology
 
 REWARD_KINDS = {None: 0, "none": 0, "SquaredTrackingErrorReward": 1,
-                "ProfitMax_TrPenalty_UserIncentives": 2, "profit_maximization": 3}
-STATE_KINDS = {None: 0, "none": 0, "PublicPST": 1, "V2G_profit_max": 2, "V2G_profit_max_loads": 3}
+                "ProfitMax_TrPenalty_UserIncentives": 2, "profit_maximization": 3, "V2G_grid_full_reward": 4,
+                "V2G_grid_simple_reward": 5}
+STATE_KINDS = {None: 0, "none": 0, "PublicPST": 1, "V2G_profit_max": 2, "V2G_profit_max_loads": 3, "V2G_grid_state": 4}
 
 ST_DONE, ST_AMPS_OVERFLOW, ST_WAS_DONE = 1, 2, 4
 KPI_NAMES = ("total_reward", "total_profits", "total_energy_charged", "total_energy_discharged",
@@ -35,7 +36,7 @@ _OUT_SPECS = {  # name -> (dtype, per-env shape key)
     "cs_power": ("float32", ("C",)), "cs_current": ("float32", ("C",)),
     "tr_power": ("float64", ("Tr",)), "tr_overload": ("float64", ("Tr",)), "total_costs": ("float64", ()),
     "action_mask": ("uint8", ("P",)), "dep_sat": ("float64", ("P",)), "dep_cap": ("float64", ("P",)),
-    "port_energy": ("float32", ("P",)),
+    "port_energy": ("float32", ("P",)), "node_voltage": ("float64", ("N",)),
 }
 
 
@@ -77,6 +78,11 @@ class BatchedEngine:
         self._keep = [topo.cs_n_ports, topo.cs_tr, topo.cs_phases, topo.cs_imax, topo.cs_imin, topo.cs_imax_dis,
                       topo.cs_imin_dis, topo.cs_voltage]
         tv = _lib.TopologyView(*[a.ctypes.data_as(t) for a, (_, t) in zip(self._keep, _lib.TopologyView._fields_)])
+        if topo.n_bus:
+            self._gk = np.ascontiguousarray(topo.grid_K).view(np.float64).reshape(-1)
+            self._gl = np.ascontiguousarray(topo.grid_L).view(np.float64).reshape(-1)
+            tv.n_bus, tv.grid_s_base = topo.n_bus, float(topo.grid_s_base)
+            tv.grid_K, tv.grid_L = self._gk.ctypes.data_as(_lib._pd), self._gl.ctypes.data_as(_lib._pd)
         h = C.c_void_p()
         rc = self.L.ev2b_create(C.byref(d), C.byref(tv), self.device, C.byref(h))
         if rc != 0:
@@ -108,7 +114,7 @@ class BatchedEngine:
 
     def set_outputs(self, names: Iterable[str]):
         torch = self.torch
-        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P}
+        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P, "N": self.topo.n_bus + 1}
         self.out = {}
         self._so = _lib.StepOut()
         for n in names:
@@ -167,6 +173,14 @@ class BatchedEngine:
             put("s_" + k, np.concatenate([sc.sessions[k] for sc in scenarios]).astype(np.float64), _lib._pd)
         put("luts_c", np.concatenate([sc.luts_c.reshape(-1) for sc in scenarios] + [np.zeros(0)]), _lib._pd)
         put("luts_d", np.concatenate([sc.luts_d.reshape(-1) for sc in scenarios] + [np.zeros(0)]), _lib._pd)
+        if all(sc.date_feat.shape == (T + 1, 3) for sc in scenarios):
+            put("date_feat", np.stack([sc.date_feat for sc in scenarios]).astype(np.float64), _lib._pd)
+        if self.topo.n_bus:
+            nb = self.topo.n_bus
+            if not all(sc.grid_active.shape == (T + 1, nb) for sc in scenarios):
+                raise EngineError("grid topology: every scenario needs grid_active / grid_reactive of shape (T+1, n_bus)")
+            put("grid_active", np.stack([sc.grid_active for sc in scenarios]).astype(np.float64), _lib._pd)
+            put("grid_reactive", np.stack([sc.grid_reactive for sc in scenarios]).astype(np.float64), _lib._pd)
         self._check(self.L.ev2b_load_scenarios(self.h, C.byref(v)), "ev2b_load_scenarios")
         self.n_scenarios = n
 

@@ -28,6 +28,7 @@ from .compat import ChargerView, EVView, TransformerView
 from .engine import REWARD_KINDS, STATE_KINDS, BatchedEngine, EngineError, _fn_name
 from .scenario import Scenario, ScenarioPack, Topology, assign_ports
 
+_FACADE_OUTPUTS_GRID = ("node_voltage",)
 _FACADE_OUTPUTS = ("reward", "status", "obs", "cs_power", "cs_current", "tr_power", "tr_overload", "total_costs",
                    "action_mask", "dep_sat", "dep_cap", "port_energy")
 
@@ -118,7 +119,7 @@ class EV2GymB200:
         self._fused_reward = _fn_name(reward_function) in REWARD_KINDS and _fn_name(reward_function) is not None
         self._engine = BatchedEngine(topo, 1, reward=reward_function if self._fused_reward else None,
                                      state=state_function if self._fused_state else None, device=device,
-                                     outputs=_FACADE_OUTPUTS, stats=True)
+                                     outputs=_FACADE_OUTPUTS + (_FACADE_OUTPUTS_GRID if topo.n_bus else ()), stats=True)
         self._port_off = topo.cs_port_off
         self.done = False
         high = np.ones(self.number_of_ports)
@@ -167,8 +168,13 @@ class EV2GymB200:
         self.cs_power, self.cs_current = np.zeros((topo.C, T)), np.zeros((topo.C, T))
         self.tr_overload = np.zeros((topo.Tr, T))
         self.tr_inflexible_loads, self.tr_solar_power = sc.tr_infl.copy(), sc.tr_solar.copy()
-        self.node_active_power = np.zeros((34, T))
-        self.node_reactive_power = np.zeros((34, T))
+        nb = topo.n_bus + 1 if topo.n_bus else 34
+        self.simulate_grid = topo.n_bus > 0
+        self.node_active_power = np.zeros((nb, T))                      # ev2gym_env.py:321-327, 395-396
+        self.node_reactive_power = np.zeros((nb, T))
+        self.node_voltage = np.zeros((nb, T))
+        if self.simulate_grid:
+            self.node_active_power[1:, 0], self.node_reactive_power[1:, 0] = sc.grid_active[0], sc.grid_reactive[0]
         self.departing_evs: List[EVView] = []
         self.EVs: List[EVView] = []
         self.EVs_profiles = [EVView(sc, i, 0, s["cap0"][i], 0.0, 0.0, 0.0, topo.timescale) for i in range(sc.n_sessions)]
@@ -263,6 +269,10 @@ class EV2GymB200:
         self.current_power_usage[t] = float(st["env_usage"][0].item())
         self.cs_power[:, t], self.cs_current[:, t] = out["cs_power"], out["cs_current"]
         self.tr_overload[:, t] = out["tr_overload"]
+        if self.simulate_grid:                                           # ev2gym_env.py:392-397
+            self.node_voltage[:, t] = out["node_voltage"]
+            self.node_active_power[1:, t] = self._sc.grid_active[t + 1]
+            self.node_reactive_power[1:, t] = self._sc.grid_reactive[t + 1]
         sat_list = self._refresh_views(out, cap, exch, hot, t)
         self.current_ev_departed = len(sat_list)
         self.total_evs_spawned += self.current_ev_arrived

@@ -102,6 +102,24 @@ def sample_scenario(topo: Topology, rng: np.random.Generator, occupancy: float =
                     dr_count=dr_count, sessions=sess, luts_c=luts, luts_d=luts.copy()).normalise()
 
 
+def add_grid(topo: Topology, scenarios: List[Scenario], seed: int = 0) -> Topology:
+    """Attach a synthetic radial feeder (one bus per transformer) to `topo` and base bus powers / calendar features
+    to every scenario: a diagonally dominant K and L = 1 give a well-conditioned Laurent iteration."""
+    rng = np.random.default_rng(seed)
+    n, T = topo.Tr, topo.T
+    path = np.abs(np.subtract.outer(np.arange(n), np.arange(n)))
+    K = -(0.02 + 0.01 * rng.random((n, n))) * np.exp(-0.15 * path) * (1 + 0.6j)
+    topo.grid_K, topo.grid_L, topo.grid_s_base = K.astype(np.complex128), np.ones(n, dtype=np.complex128), 1000.0
+    for sc in scenarios:
+        x = np.linspace(0, 2 * np.pi, T + 1)[:, None]
+        sc.grid_active = np.round(120 + 80 * np.sin(x + rng.uniform(0, 6, (1, n))) + 20 * rng.random((T + 1, n)), 1)
+        sc.grid_reactive = np.round(0.4 * sc.grid_active, 1)
+        hours = (5 + np.arange(T + 1) * topo.timescale // 60) % 24
+        sc.date_feat = np.stack([np.full(T + 1, 2 / 7), np.sin(hours / 24 * 2 * np.pi), np.cos(hours / 24 * 2 * np.pi)], 1)
+        sc.normalise()
+    return topo
+
+
 def sample_bank(topo: Topology, n: int, seed: int = 0, **kw) -> List[Scenario]:
     rng = np.random.default_rng(seed)
     return [sample_scenario(topo, rng, **kw) for _ in range(n)]

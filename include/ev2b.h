@@ -34,13 +34,16 @@ enum ev2b_reward_kind {
     EV2B_REWARD_NONE = 0,                 /* reward output = 0 (caller computes its own)            */
     EV2B_REWARD_SQ_TRACKING = 1,          /* SquaredTrackingErrorReward            reward.py:7-14   */
     EV2B_REWARD_PROFIT_TR_USER = 2,       /* ProfitMax_TrPenalty_UserIncentives    reward.py:34-44  */
-    EV2B_REWARD_PROFIT_MAX = 3            /* profit_maximization                   reward.py:78-87  */
+    EV2B_REWARD_PROFIT_MAX = 3,           /* profit_maximization                   reward.py:78-87  */
+    EV2B_REWARD_GRID_FULL = 4,            /* V2G_grid_full_reward   (needs a grid) reward.py:89-111 */
+    EV2B_REWARD_GRID_SIMPLE = 5           /* V2G_grid_simple_reward (needs a grid) reward.py:114-121 */
 };
 enum ev2b_state_kind {
     EV2B_STATE_NONE = 0,
     EV2B_STATE_PUBLIC_PST = 1,            /* PublicPST            state.py:6-63    D = 3 + 3P        */
     EV2B_STATE_V2G_PROFIT_MAX = 2,        /* V2G_profit_max       state.py:65-106  D = 22 + 2P       */
-    EV2B_STATE_V2G_PROFIT_MAX_LOADS = 3   /* V2G_profit_max_loads state.py:108-155 D = 22 + 40Tr + 2P */
+    EV2B_STATE_V2G_PROFIT_MAX_LOADS = 3,  /* V2G_profit_max_loads state.py:108-155 D = 22 + 40Tr + 2P */
+    EV2B_STATE_V2G_GRID = 4               /* V2G_grid_state       state.py:216-278 D = 6 + 2(nb-1) + 3P */
 };
 enum ev2b_action_dtype { EV2B_F32 = 0, EV2B_F64 = 1 };
 /* On-device agents for ev2b_step_k (no action tensor is read). */
@@ -92,6 +95,13 @@ typedef struct {
     const double  *cs_imax_dis;    /* max_discharge_current (<=0)  */
     const double  *cs_imin_dis;    /* min_discharge_current        */
     const double  *cs_voltage;     /* voltage                      */
+    /* distribution grid (simulate_grid: True): Laurent power flow V <- K conj(S/V) + L per env and step
+     * (ev2gym/models/grid.py:120-141, grid_utility/numbarize.py:268-325, K/L: grid_tensor.py:110-118).
+     * n_bus = buses without the slack; must equal n_transformers (loaders.py:481).  0 = no grid. */
+    int32_t        n_bus;
+    const double  *grid_K;         /* [n_bus*n_bus] complex128 row-major as (re,im) pairs */
+    const double  *grid_L;         /* [n_bus] complex128 */
+    double         grid_s_base;    /* kVA */
 } ev2b_topology;
 
 /* A bank of n pre-sampled episodes ("scenarios"), HOST pointers, plain float64/int32 exactly as
@@ -118,6 +128,8 @@ typedef struct {
                   *s_desired, *s_ts, *s_mult, *s_eta_c, *s_eta_d;
     const int64_t *lut_off;                        /* [n+1]                                        */
     const double  *luts_c, *luts_d;                /* [lut_off[n]*lut_len] percent                 */
+    const double  *grid_active, *grid_reactive;    /* [n*(T+1)*n_bus] base bus powers of steps 0..T (grid.py:109-118,131-139) or NULL */
+    const double  *date_feat;                      /* [n*(T+1)*3] weekday/7, sin, cos of the observation times (state.py:221-225) or NULL */
 } ev2b_scenarios;
 
 /* Per-step outputs, DEVICE pointers owned by the caller; any pointer may be NULL (= not wanted).
@@ -135,6 +147,7 @@ typedef struct {
     double   *dep_sat;       /* [E,P]   user satisfaction of the EV that left this port this step, NaN otherwise */
     double   *dep_cap;       /* [E,P]   its final battery level (kWh), NaN otherwise  (env.departing_evs)         */
     float    *port_energy;   /* [E,P]   ev.current_energy of this step (kWh)                       */
+    double   *node_voltage;  /* [E,n_bus+1] |V| per node, slack first   env.node_voltage[:, t]  ev2gym_env.py:397 */
 } ev2b_step_out;
 
 /* Raw DEVICE pointers into the struct-of-arrays state, for zero-copy tensor views. */

@@ -10,7 +10,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 CASES = ["c1_afap_s42", "pst25_uniform_s3", "loads_c20n2tr3_mixed_s11", "profitmax_c25_mixed_s9",
-         "mincur_c6n2_mixed_s8"]
+         "mincur_c6n2_mixed_s8", "grid_c40_uniform_s3"]
 
 
 def _env(name, **kw):

@@ -40,7 +40,9 @@ def test_cuda_matches_reference_trace(name):
     tr = np.load(f"{GOLDEN}/{name}.trace.npz")
     topo = pack.topo
     E = 3                                 # 3 replicas of the same episode: exercises multi-env CTAs
-    eng = _engine(topo, pack.scenarios, E, str(tr["reward_fn"]), str(tr["state_fn"]), ALL_OUT, stats=True)
+    grid = topo.n_bus > 0
+    eng = _engine(topo, pack.scenarios, E, str(tr["reward_fn"]), str(tr["state_fn"]),
+                  ALL_OUT + (("node_voltage",) if grid else ()), stats=True)
     obs0 = eng.reset().cpu().numpy()
     assert _close(obs0[0], tr["obs0"], 1e-5, 1e-6) and np.array_equal(obs0[0], obs0[2])
     st = eng.state_tensors()
@@ -64,6 +66,8 @@ def test_cuda_matches_reference_trace(name):
             assert _close(out["cs_current"][e], tr["cs_current"][t], 1e-5, 1e-6)
             assert _close(out["obs"][e], tr["obs"][t], 1e-5, 1e-5), (t, "obs",
                                                                      np.abs(out["obs"][e] - tr["obs"][t]).max())
+            if grid:      # Laurent power flow: |V| per node, slack first (ev2gym_env.py:397)
+                assert _close(out["node_voltage"][e], tr["node_voltage"][:, t], 1e-9, 1e-12), (t, "node voltage")
             assert bool(out["status"][e] & 1) == bool(tr["done"][t])
             assert np.nansum(out["dep_sat"][e]) == pytest.approx(tr["sat_sum"][t], rel=1e-6, abs=1e-6)
             assert np.count_nonzero(~np.isnan(out["dep_sat"][e])) == tr["n_departed"][t]
@@ -229,3 +233,29 @@ def test_step_k_device_agents(agent):
         assert _close(out["obs"].cpu().numpy(), orc.o["obs"][:, :eng.D], 1e-5, 1e-5)
     assert t == topo.T and bool((out["status"] & 1).all())
     assert _close(eng.kpis()["total_reward"], [s.total_reward for s in orc.states], 1e-9, 1e-9)
+
+
+def test_grid_power_flow_matches_oracle_on_synthetic():
+    """Synthetic 20-bus feeder, 2 ports per charger, several envs per CTA: voltages / grid rewards / grid state."""
+    import torch
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import add_grid, sample_bank
+    from oracle.oracle import OracleBatch
+    topo = Topology.uniform(C=50, n_ports=2, Tr=20, T=40)
+    bank = sample_bank(topo, 3, seed=31, min_stay=4, loads=False)
+    add_grid(topo, bank, seed=1)
+    E = 7
+    for rw in ("V2G_grid_full_reward", "V2G_grid_simple_reward"):
+        eng = _engine(topo, bank, E, rw, "V2G_grid_state", ("reward", "status", "obs", "node_voltage"))
+        obs0 = eng.reset().cpu().numpy()
+        orc = OracleBatch(topo, [bank[e % 3] for e in range(E)], reward=rw, state="V2G_grid_state")
+        assert _close(obs0, orc.reset(), 1e-5, 1e-5)
+        rng = np.random.default_rng(4)
+        for t in range(topo.T):
+            a = rng.uniform(-1, 1, (E, topo.P))
+            out = {k: v.cpu().numpy() for k, v in eng.step(torch.tensor(a, device="cuda")).items()}
+            orc.step(a)
+            assert _close(out["node_voltage"], orc.o["node_vm"], 1e-9, 1e-12), t
+            assert _close(out["reward"], orc.reward, 1e-9, 1e-9), t
+            assert _close(out["obs"], orc.o["obs"][:, :eng.D], 1e-5, 1e-5), t
+        eng.close()
