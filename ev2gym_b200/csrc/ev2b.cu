@@ -57,7 +57,7 @@ struct ev2b_handle {
     std::vector<double> cls_imax;       // per charger class
     std::vector<std::array<double, 4>> cls_veff;
     // device: static
-    DevBuf<CsStatic> cs; DevBuf<int> tr_cs_off, tr_cs_idx, obs_slot, tr_obs_off, port_cs_d, series_off;
+    DevBuf<CsStatic> cs; DevBuf<int> cs_tr_d; DevBuf<int> tr_cs_off, tr_cs_idx, obs_slot, tr_obs_off, port_cs_d, series_off;
     int W = 0;                          // (scenario, time)-only observation values per env
     // device: bank
     int S = 0, Smax = 1, n_dr = 1, lut_len = 101;
@@ -108,6 +108,7 @@ struct ev2b_handle {
         p.st_soc_sum = st_soc_sum.p; p.st_abs_e = st_abs_e.p; p.st_act = st_act.p; p.st_r = st_r.p;
         p.st_cnt = st_cnt.p; p.st_nfin = st_nfin.p; p.cs_sat_sum = cs_sat_sum.p; p.cs_dcal = cs_dcal.p;
         p.cs_dcyc = cs_dcyc.p; p.cs_served = cs_served.p; p.cs_em = cs_em.p;
+        p.cs_tr = cs_tr_d.p;
         p.port_cs = port_cs_d.p; p.series_off = series_off.p; p.obs_static = obs_static.p;
         p.cs = cs.p; p.tr_cs_off = tr_cs_off.p; p.tr_cs_idx = tr_cs_idx.p; p.obs_slot = obs_slot.p; p.tr_obs_off = tr_obs_off.p;
         p.env_t = env_t.p; p.tr_t = tr_t.p; p.sess = sess.p; p.spec = spec.p; p.luts_c = luts_c.p; p.luts_d = luts_d.p;
@@ -319,6 +320,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     CREATE_TRY(h->obs_slot.upload(slot));
     CREATE_TRY(h->tr_obs_off.upload(tr_obs));
     CREATE_TRY(h->port_cs_d.upload(h->port_cs));
+    { std::vector<int> ct(C); for (int c = 0; c < C; ++c) ct[c] = h->cs_h[c].tr; CREATE_TRY(h->cs_tr_d.upload(ct)); }
     CREATE_TRY(h->series_off.upload(series_off_h));
     if (h->n_bus > 0) {
         const int n = h->n_bus;

@@ -89,7 +89,7 @@ struct Params {
     int cs_uniform;          // all chargers identical: read the layout from cs0 (constant bank)
     CsStatic cs0;
     // static
-    const CsStatic *cs; const int *port_cs; const int *tr_cs_off; const int *tr_cs_idx; const int *obs_slot;
+    const CsStatic *cs; const int *cs_tr; const int *port_cs; const int *tr_cs_off; const int *tr_cs_idx; const int *obs_slot;
     const int *tr_obs_off; const int *series_off;
     // scenario bank
     const EnvT *env_t; const TrT *tr_t; const SessRec *sess; const EvSpec *spec;
@@ -376,12 +376,12 @@ __device__ __forceinline__ double power_flow_env(const Params &p, double2 *S, co
                 for (int c2 = 0; c2 < n; ++c2) {             // Z = K @ lambda   numbarize.py:305
                     const double2 kk = __ldg(&p.grid_Kt[(size_t)c2 * n + r]);
                     const double2 lm = Lm[c2];
-                    zr += kk.x * lm.x - kk.y * lm.y;
-                    zi += kk.x * lm.y + kk.y * lm.x;
+                    zr = fma(kk.x, lm.x, fma(-kk.y, lm.y, zr));     // voltages carry a 1e-6 solver tolerance: FMA is fine here
+                    zi = fma(kk.x, lm.y, fma(kk.y, lm.x, zi));
                 }
                 const double2 ll = __ldg(&p.grid_L[r]);
                 nv[q] = make_double2(zr + ll.x, zi + ll.y);  // voltage_k = Z + L
-                dmax = fmax(dmax, fabs(hypot(nv[q].x, nv[q].y) - hypot(V[r].x, V[r].y)));
+                dmax = fmax(dmax, fabs(sqrt(nv[q].x * nv[q].x + nv[q].y * nv[q].y) - sqrt(V[r].x * V[r].x + V[r].y * V[r].y)));
             }
         }
 #pragma unroll
@@ -395,7 +395,7 @@ __device__ __forceinline__ double power_flow_env(const Params &p, double2 *S, co
     }
     double lv = 0.0;                                         // sum(min(0, 0.05 - |1 - vm|)) incl. the slack (vm = 1)
     for (int r = lane; r < n; r += 32) {
-        const double vm = hypot(V[r].x, V[r].y);
+        const double vm = sqrt(V[r].x * V[r].x + V[r].y * V[r].y);
         const double x = 0.05 - fabs(1.0 - vm);
         lv += x < 0.0 ? x : 0.0;
         if (p.out.node_voltage) p.out.node_voltage[(size_t)je * (n + 1) + r + 1] = vm;
@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                     if (p.state_kind == EV2B_STATE_V2G_GRID) {          // state.py:262-270
                         o[0] = (float)cv;
                         o[1] = (float)(hot_t_dep(hj) - tq + 1);
-                        o[2] = (float)cs.tr;
+                        o[2] = (float)__ldg(&p.cs_tr[c]);     // cs.connected_bus (cs0 is shared in the uniform layout)
                     } else if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
                         o[0] = (cv == B) ? 1.f : 0.5f;
                         o[1] = exch_valid ? exch_new : (NP > 0 ? exch0[j] : p.exch[ip]);
