@@ -163,21 +163,6 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
         return go(step_kernel<ActT, 0, false, MAXT, MINB, false>);                      \
     } while (0)
     const bool stats = (h->dims.flags & EV2B_F_STATS) != 0 || h->n_bus > 0;   // the HEAVY instantiation
-    // persistent TMA variant: uniform layout, 1-2 ports, every per-env slab a multiple of 16 bytes, <= 128 threads
-    static const bool persist_env = getenv("EV2B_PERSIST") ? atoi(getenv("EV2B_PERSIST")) != 0 : false;
-    if (persist_env && !stats && np > 0 && h->block <= 128 && (h->P % 4) == 0) {
-        const size_t PPs = (size_t)h->EPB * h->P;
-        const size_t smem_p = ((h->smem + 15) & ~(size_t)15) + 2 * PPs * (16 + 8 + sizeof(ActT) + 4) + 16 + 16;
-        auto kern = np == 1 ? step_kernel<ActT, 1, true, 128, 8, false, true> : step_kernel<ActT, 2, true, 128, 8, false, true>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0, n_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, h->block, smem_p);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
-        const unsigned pgrid = std::min<unsigned>(grid, (unsigned)std::max(1, per_sm * n_sm));
-        kern<<<pgrid, h->block, smem_p, st>>>(p);
-        return cudaGetLastError();
-    }
 #ifndef EV2B_MINB128
 #define EV2B_MINB128 8
 #endif

@@ -404,29 +404,9 @@ __device__ __forceinline__ double power_flow_env(const Params &p, double2 *S, co
     return lv;
 }
 
-// ---- TMA bulk copies + mbarrier (persistent variant stages each env group's state slab in shared memory) ----
-__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
-    asm volatile(
-        "{\n .reg .pred P1;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra WAIT_LOOP;\n DONE:\n }"
-        ::"r"(smem_u32(bar)), "r"(phase) : "memory");
-}
-
 // ---- the fused step kernel --------------------------------------------------------------------
 // ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = ragged (CsStatic).
-// PERSIST: one CTA per SM slot loops over env groups; the next group's hot/action/cap/exch slab is fetched by TMA
-// (cp.async.bulk + mbarrier) while the current group is processed.
-template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool HEAVY, bool PERSIST = false>   // HEAVY: statistics mode and/or distribution grid compiled in
+template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool HEAVY>   // HEAVY: statistics mode and/or distribution grid compiled in
 __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
@@ -446,55 +426,15 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     int    *wl    = envi + (size_t)p.EPB * 4;                             // [PP] work list (port_local)
     int    *wcnt  = wl + PP;                                              // [1] (+3 pad)
     signed char *pflag = reinterpret_cast<signed char *>(wcnt + 4);       // [PP] ragged path only
-    // persistent variant: two staging buffers {hot, cap, action, exch} + one mbarrier each
-    unsigned char *stage0 = reinterpret_cast<unsigned char *>(((uintptr_t)(pflag + PP) + 15) & ~(uintptr_t)15);
-    const size_t stage_bytes = (size_t)PP * (16 + 8 + sizeof(ActT) + 4);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(stage0 + 2 * stage_bytes);
 
     const int tid = threadIdx.x;
     const int el = p.C == 1 ? tid : (int)__umulhi((unsigned)tid, p.c_magic);   // tid / C
     const int c = tid - el * p.C;
+    const int e = (p.env0 + blockIdx.x * p.EPB) + el;
+    const bool valid = (el < p.EPB) && (e < p.env_end);
     const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
     constexpr int NPR = NP > 0 ? NP : 1;
-    const int n_groups = (p.env_end - p.env0 + p.EPB - 1) / p.EPB;
-    // issue the TMA loads of env group g into staging buffer b (thread 0 only)
-    auto stage_issue = [&](int g, int b) {
-        const int e0 = p.env0 + g * p.EPB;
-        const unsigned ne = (unsigned)min(p.EPB, p.env_end - e0) * (unsigned)p.P;
-        unsigned char *d = stage0 + (size_t)b * stage_bytes;
-        const size_t off = (size_t)e0 * p.P;
-        const bool act = p.agent_kind == EV2B_AGENT_EXTERNAL;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&bars[b], ne * (16 + 8 + 4 + (act ? (unsigned)sizeof(ActT) : 0u)));
-        tma_load_1d(d, p.hot + off, ne * 16, &bars[b]);
-        tma_load_1d(d + (size_t)PP * 16, p.cap + off, ne * 8, &bars[b]);
-        tma_load_1d(d + (size_t)PP * 24, p.exch + off, ne * 4, &bars[b]);
-        if (act) tma_load_1d(d + (size_t)PP * 28, actions + off, ne * (unsigned)sizeof(ActT), &bars[b]);
-    };
-    unsigned ph0 = 0, ph1 = 0;
-    int buf = 0;
-    if (PERSIST) {
-        if (tid == 0) {
-            mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0 && (int)blockIdx.x < n_groups) stage_issue(blockIdx.x, 0);
-    }
-    for (int blk = blockIdx.x; blk < n_groups; blk += (PERSIST ? (int)gridDim.x : n_groups)) {
-    const int e = (p.env0 + blk * p.EPB) + el;
-    const bool valid = (el < p.EPB) && (e < p.env_end);
-    const uint4 *s_hot = reinterpret_cast<const uint4 *>(stage0 + (size_t)buf * stage_bytes);
-    const double *s_cap = reinterpret_cast<const double *>(stage0 + (size_t)buf * stage_bytes + (size_t)PP * 16);
-    const float *s_exch = reinterpret_cast<const float *>(stage0 + (size_t)buf * stage_bytes + (size_t)PP * 24);
-    const ActT *s_act = reinterpret_cast<const ActT *>(stage0 + (size_t)buf * stage_bytes + (size_t)PP * 28);
-    if (PERSIST) {
-        const int nxt = blk + (int)gridDim.x;
-        if (tid == 0 && nxt < n_groups) stage_issue(nxt, buf ^ 1);     // prefetch the next group while this one runs
-        mbar_wait(&bars[buf], buf ? ph1 : ph0);
-        if (buf) ph1 ^= 1; else ph0 ^= 1;
-    }
 
     if (tid == 0) { wcnt[0] = 0; wcnt[1] = 0; }   // charge items fill wl from the front, discharge items from the back
     int t = 0, s = 0;
@@ -516,13 +456,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             port0 = UNI ? c * NP : p.cs[c].port_off;
             const size_t pb = (size_t)e * p.P + port0;
 #pragma unroll
-            for (int j = 0; j < NP; ++j) {
-                if (PERSIST) {
-                    const int pl0 = el * p.P + port0 + j;
-                    h[j] = s_hot[pl0];
-                    araw[j] = p.agent_kind == EV2B_AGENT_EXTERNAL ? (double)s_act[pl0] : agent_action<ActT>(p, actions, pb + j, t);
-                } else { h[j] = p.hot[pb + j]; araw[j] = agent_action<ActT>(p, actions, pb + j, t); }
-            }
+            for (int j = 0; j < NP; ++j) { h[j] = p.hot[pb + j]; araw[j] = agent_action<ActT>(p, actions, pb + j, t); }
         }
         live = t < p.T;
         if (live) { const EnvT et0 = p.env_t[(size_t)s * p.T + t]; pre_cp = et0.cp; pre_dp = et0.dp; }
@@ -543,8 +477,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const bool occ = hot_t_arr(h[j]) <= t && t <= hot_t_dep(h[j]);
-                capv[j] = occ ? (PERSIST ? s_cap[el * p.P + port0 + j] : p.cap[pbase + j]) : 0.0;
-                exch0[j] = occ ? (PERSIST ? s_exch[el * p.P + port0 + j] : p.exch[pbase + j]) : 0.f;
+                capv[j] = occ ? p.cap[pbase + j] : 0.0;
+                exch0[j] = occ ? p.exch[pbase + j] : 0.f;
                 if (!occ) { a[j] = 0.0; ++invalid; }                     // ev_charger.py:137-140
                 sum = sum + a[j];                                        // python sum(), left to right  :143
             }
@@ -588,7 +522,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     // (scenario, time)-only part of the observation: price window + forecast / limit blocks
     if (want_obs && p.W > 0) {
         for (int jel = 0; jel < p.EPB; ++jel) {
-            const int je = (p.env0 + blk * p.EPB) + jel;
+            const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
             if (je >= p.env_end) break;
             const int jt = envi[jel * 4 + 0];
             if (jt >= p.T) continue;
@@ -615,7 +549,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             const bool active = ev_step_item<HEAVY>(p, cs, hw.x, hw.y, resE[pl], cap, energy, amps, em_cross);
             if (HEAVY && p.stats && em_cross) {   // min_emergency_battery_capacity_metric  ev.py:401-402 (integer atomics: order-free)
                 const int jel = p.EPB == 1 ? 0 : (int)__umulhi((unsigned)pl, p.p_magic);
-                atomicAdd(&p.cs_em[(size_t)((p.env0 + blk * p.EPB) + jel) * p.C + p.port_cs[port]], 1);
+                atomicAdd(&p.cs_em[(size_t)((p.env0 + blockIdx.x * p.EPB) + jel) * p.C + p.port_cs[port]], 1);
             }
             resE[pl] = energy; resA[pl] = amps;
             resC[pl] = active ? cap : -1.0;                              // EV saw amps == 0: nothing changes (ev.py:158-163)
@@ -768,7 +702,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
         for (int job = warp; job < 3 * p.EPB; job += nwarps) {
             const int jel = job / 3, kind = job - jel * 3;
-            const int je = (p.env0 + blk * p.EPB) + jel;
+            const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
             if (je >= p.env_end) continue;
             const int jt = envi[jel * 4 + 0];
             if (jt >= p.T) continue;
@@ -831,7 +765,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     if (HEAVY && p.n_bus > 0) {
         const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5, n = p.n_bus;
         for (int jel = warp; jel < p.EPB; jel += nwarps) {
-            const int je = (p.env0 + blk * p.EPB) + jel;
+            const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
             if (je >= p.env_end) continue;
             const int jt = envi[jel * 4 + 0];
             if (jt >= p.T) continue;
@@ -843,7 +777,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
 
     // ---- C: one thread per env: reward, KPIs, step counter ---------------------------------------
     if (tid < p.EPB) {
-        const int je = (p.env0 + blk * p.EPB) + tid;
+        const int je = (p.env0 + blockIdx.x * p.EPB) + tid;
         if (je < p.env_end) {
             const int jt = envi[tid * 4 + 0], js = envi[tid * 4 + 1];
             unsigned status = (unsigned)envi[tid * 4 + 3];
@@ -897,8 +831,6 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             if (p.out.status) p.out.status[je] = status;
         }
     }
-    if (PERSIST) { __syncthreads(); buf ^= 1; }
-    }   // env-group loop
 }
 
 // ---- reset ------------------------------------------------------------------------------------
