@@ -66,7 +66,6 @@ struct ev2b_handle {
     // device: state
     DevBuf<uint4> hot; DevBuf<double> cap; DevBuf<float> exch; DevBuf<int> env_step, env_scn;
     DevBuf<double> env_pot, env_usage, env_kpi;
-    DevBuf<unsigned> occ_bits, arr_bits; int WB = 1;
     // device: statistics mode
     int L = 1;
     DevBuf<double> st_soc_sum, st_abs_e, st_act, st_r, cs_sat_sum, cs_dcal, cs_dcyc;
@@ -114,7 +113,6 @@ struct ev2b_handle {
         p.cs = cs.p; p.tr_cs_off = tr_cs_off.p; p.tr_cs_idx = tr_cs_idx.p; p.obs_slot = obs_slot.p; p.tr_obs_off = tr_obs_off.p;
         p.env_t = env_t.p; p.tr_t = tr_t.p; p.sess = sess.p; p.spec = spec.p; p.luts_c = luts_c.p; p.luts_d = luts_d.p;
         p.pot_kw = pot_kw.p; p.trA = trA.p; p.trF = trF.p; p.tr_limit = tr_limit.p; p.dr = dr.p; p.dr_count = dr_count.p;
-        p.occ_bits = occ_bits.p; p.arr_bits = arr_bits.p; p.WB = WB;
         p.hot = hot.p; p.cap = cap.p; p.exch = exch.p; p.env_step = env_step.p; p.env_scn = env_scn.p;
         p.env_pot = env_pot.p; p.env_usage = env_usage.p; p.env_kpi = env_kpi.p;
         return p;
@@ -312,8 +310,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         h->smem = sizeof(double) * ((size_t)kNRed * h->block + 3 * PP + 2 * (size_t)h->EPB * h->Tr + (size_t)h->EPB + 1 +
                                     6 * (size_t)h->EPB * h->n_bus + (size_t)h->EPB * kNRed) +
                   sizeof(uint2) * PP + sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4 + PP + 4 + 1) +
-                  PP + 16 + sizeof(unsigned) * 2 * (size_t)h->EPB * ((h->P + 31) / 32) + sizeof(int) * 2 * (size_t)h->EPB +
-                  sizeof(short) * 2 * (size_t)h->block + 8;
+                  PP + 16;
     }
 #define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
         g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e); delete h; return EV2B_E_CUDA; } } while (0)
@@ -335,9 +332,6 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         CREATE_TRY(h->grid_Kt.upload(kt)); CREATE_TRY(h->grid_L.upload(lv));
     }
     const size_t EP = (size_t)h->E * h->P;
-    h->WB = (h->P + 31) / 32;
-    CREATE_TRY(h->occ_bits.alloc((size_t)h->E * h->WB));
-    CREATE_TRY(cudaMemset(h->occ_bits.p, 0, (size_t)h->E * h->WB * sizeof(unsigned)));
     CREATE_TRY(h->hot.alloc(EP)); CREATE_TRY(h->cap.alloc(EP)); CREATE_TRY(h->exch.alloc(EP));
     CREATE_TRY(h->env_step.alloc(h->E)); CREATE_TRY(h->env_scn.alloc(h->E));
     CREATE_TRY(h->env_pot.alloc(h->E)); CREATE_TRY(h->env_usage.alloc(h->E));
@@ -506,16 +500,6 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
             }
             last_of_port[pl.port] = k;
         }
-    }
-    {   // arrival bitmaps: bit (port) of word [s][t_arr][port/32]; the kernel ORs them into the busy-charger list
-        const int WB = (P + 31) / 32;
-        std::vector<unsigned> ab((size_t)S * (T + 1) * WB, 0u);
-        for (int i = 0; i < S; ++i)
-            for (const Placed &pl : placed[i]) {
-                const int ta = b->s_t_arr[pl.row];
-                if (ta >= 0 && ta <= T) ab[((size_t)i * (T + 1) + ta) * WB + (pl.port >> 5)] |= 1u << (pl.port & 31);
-            }
-        CUDA_TRY(h, h->arr_bits.upload(ab));
     }
     // potential contribution per (spec, charger class)          utils.py:772-777
     std::vector<double> pot_kw(specs.size() * h->n_cls);

@@ -109,9 +109,6 @@ struct Params {
     int *st_cnt, *st_nfin;     // [E,P] n_hist | n_act << 16 ; finalised sessions on the port
     double *cs_sat_sum, *cs_dcal, *cs_dcyc; int *cs_served, *cs_em;   // [E,C]
     // state
-    unsigned *occ_bits;        // [E][WB] bit per port: an EV is connected (uniform layouts; drives the busy-charger list)
-    const unsigned *arr_bits;  // [S][T+1][WB] bit per port: a session arrives at that step
-    int WB;                    // words per env = ceil(P / 32)
     uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;
     double *env_kpi;
     // io
@@ -429,19 +426,12 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     int    *wl    = envi + (size_t)p.EPB * 4;                             // [PP] work list (port_local)
     int    *wcnt  = wl + PP;                                              // [1] (+3 pad)
     signed char *pflag = reinterpret_cast<signed char *>(wcnt + 4);       // [PP] ragged path only
-    // busy-charger compaction (uniform layouts): occupancy words, busy-charger words, slot -> charger / transformer
-    unsigned *bits  = reinterpret_cast<unsigned *>(((uintptr_t)(pflag + PP) + 3) & ~(uintptr_t)3);   // [EPB][WB] (updated in A3)
-    unsigned *busyw = bits + (size_t)p.EPB * p.WB;                        // [EPB][WB]
-    int *nbusy = reinterpret_cast<int *>(busyw + (size_t)p.EPB * p.WB);   // [EPB] busy chargers, [EPB] connected EVs
-    short *cid = reinterpret_cast<short *>(nbusy + 2 * p.EPB);            // [NT] charger of this slot
-    short *ctr = cid + NT;                                                // [NT] its transformer
-    constexpr bool COMPACT = UNI && NP > 0;
 
     const int tid = threadIdx.x;
     const int el = p.C == 1 ? tid : (int)__umulhi((unsigned)tid, p.c_magic);   // tid / C
-    int c = tid - el * p.C;               // slot; identity = charger id unless COMPACT re-maps it below
+    const int c = tid - el * p.C;
     const int e = (p.env0 + blockIdx.x * p.EPB) + el;
-    bool valid = (el < p.EPB) && (e < p.env_end);
+    const bool valid = (el < p.EPB) && (e < p.env_end);
     const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
     constexpr int NPR = NP > 0 ? NP : 1;
@@ -462,8 +452,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     if (valid) {
         t = p.env_step[e];
         s = p.env_scn[e];
-        if (NP > 0 && !COMPACT) {
-            port0 = p.cs[c].port_off;
+        if (NP > 0) {
+            port0 = UNI ? c * NP : p.cs[c].port_off;
             const size_t pb = (size_t)e * p.P + port0;
 #pragma unroll
             for (int j = 0; j < NP; ++j) { h[j] = p.hot[pb + j]; araw[j] = agent_action<ActT>(p, actions, pb + j, t); }
@@ -471,59 +461,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
         live = t < p.T;
         if (live) { const EnvT et0 = p.env_t[(size_t)s * p.T + t]; pre_cp = et0.cp; pre_dp = et0.dp; }
         if (c == 0) { envi[el * 4 + 0] = t; envi[el * 4 + 1] = s; envi[el * 4 + 2] = 0; envi[el * 4 + 3] = 0; }
-        if (COMPACT && c < p.WB) {         // NP <= 2 => WB <= C: one word per thread
-            const unsigned occw = p.occ_bits[(size_t)e * p.WB + c];
-            const unsigned any = occw | (live ? __ldg(&p.arr_bits[((size_t)s * (p.T + 1) + t + 1) * p.WB + c]) : 0u);
-            bits[el * p.WB + c] = occw;
-            busyw[el * p.WB + c] = live ? (NP == 2 ? ((any | (any >> 1)) & 0x55555555u) : any) : 0u;
-        }
-    }
-    if (COMPACT) {
-        // optional per-port / per-charger outputs and (on a full rewrite) observation tuples of chargers that are not
-        // visited this step are filled here; busy chargers overwrite theirs two barriers later
-        for (int jel = 0; jel < p.EPB; ++jel) {
-            const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
-            if (je >= p.env_end) break;
-            if (EV2B_OPT(p.out.cs_power))   for (int i = tid; i < p.C; i += NT) p.out.cs_power[(size_t)je * p.C + i] = 0.f;
-            if (EV2B_OPT(p.out.cs_current)) for (int i = tid; i < p.C; i += NT) p.out.cs_current[(size_t)je * p.C + i] = 0.f;
-            if (EV2B_OPT(p.out.port_energy)) for (int i = tid; i < p.P; i += NT) p.out.port_energy[(size_t)je * p.P + i] = 0.f;
-            if (EV2B_OPT(p.out.dep_sat)) for (int i = tid; i < p.P; i += NT) p.out.dep_sat[(size_t)je * p.P + i] = __longlong_as_double(0x7ff8000000000000LL);
-            if (EV2B_OPT(p.out.dep_cap)) for (int i = tid; i < p.P; i += NT) p.out.dep_cap[(size_t)je * p.P + i] = __longlong_as_double(0x7ff8000000000000LL);
-            if (want_obs && p.obs_full) {
-                const int tup = (p.state_kind == EV2B_STATE_PUBLIC_PST || p.state_kind == EV2B_STATE_V2G_GRID) ? 3 : 2;
-                for (int i = tid; i < p.P; i += NT) {
-                    float *o = p.out.obs + (size_t)je * p.D + p.obs_slot[i];
-                    o[0] = 0.f; o[1] = 0.f; if (tup == 3) o[2] = 0.f;
-                }
-            }
-        }
     }
     __syncthreads();
-    if (COMPACT) {        // slot -> busy charger: the slot-th set bit of this env's busy words
-        bool mine = false;
-        if (valid) {
-            int acc = 0, w_hit = -1, k_hit = 0, nocc = 0;
-            for (int w = 0; w < p.WB; ++w) {
-                const int pc = __popc(busyw[el * p.WB + w]);
-                if (w_hit < 0 && c < acc + pc) { w_hit = w; k_hit = c - acc; }
-                acc += pc;
-                nocc += __popc(bits[el * p.WB + w]);
-            }
-            if (c == 0) { nbusy[el] = acc; nbusy[p.EPB + el] = nocc; }
-            if (w_hit >= 0) {
-                port0 = w_hit * 32 + (int)__fns(busyw[el * p.WB + w_hit], 0, k_hit + 1);
-                c = NP == 2 ? port0 >> 1 : port0;
-                mine = true;
-            }
-        }
-        valid = mine;
-        if (valid) {
-            const size_t pb = (size_t)e * p.P + port0;
-#pragma unroll
-            for (int j = 0; j < NP; ++j) { h[j] = p.hot[pb + j]; araw[j] = agent_action<ActT>(p, actions, pb + j, t); }
-            cid[tid] = (short)c; ctr[tid] = (short)__ldg(&p.cs_tr[c]);
-        }
-    }
 
     if (valid && live) {
         const CsStatic &cs = cs_of<UNI>(p, c);
@@ -540,7 +479,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 const bool occ = hot_t_arr(h[j]) <= t && t <= hot_t_dep(h[j]);
                 capv[j] = occ ? p.cap[pbase + j] : 0.0;
                 exch0[j] = occ ? p.exch[pbase + j] : 0.f;
-                if (!occ) { a[j] = 0.0; if (!COMPACT) ++invalid; }       // ev_charger.py:137-140 (COMPACT: counted from the bitmap)
+                if (!occ) { a[j] = 0.0; ++invalid; }                     // ev_charger.py:137-140
                 sum = sum + a[j];                                        // python sum(), left to right  :143
             }
 #pragma unroll
@@ -711,9 +650,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 if (HEAVY && p.stats) { p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0; }
             }
             const bool occ_after = hot_t_arr(hj) <= tq && tq <= hot_t_dep(hj);
-            if (COMPACT) {            // keep the occupancy bitmap current; the action mask is expanded from it below
-                if (occ_after != occ) atomicXor(&bits[el * p.WB + ((port0 + j) >> 5)], 1u << ((port0 + j) & 31));
-            } else if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;   // ev2gym_env.py:452-457
+            if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;          // ev2gym_env.py:452-457
             if (HEAVY && p.stats && occ_after && tq >= p.T) {   // episode over: EVs still connected count too (env.EVs)
                 const SessRec r0 = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj) - 1];
                 finalize_ev(p, ip, (int)((size_t)e * p.C + c), p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj),
@@ -758,17 +695,6 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     red[RedSatSum * NT + tid] = rSat;
     cnt[tid] = rCnt;
     __syncthreads();
-    if (COMPACT) {
-        for (int jel = 0; jel < p.EPB; ++jel) {
-            const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
-            if (je >= p.env_end) break;
-            if (envi[jel * 4 + 0] >= p.T) continue;
-            for (int w = tid; w < p.WB; w += NT) p.occ_bits[(size_t)je * p.WB + w] = bits[jel * p.WB + w];
-            if (p.out.action_mask)                                       // ev2gym_env.py:452-457
-                for (int i = tid; i < p.P; i += NT)
-                    p.out.action_mask[(size_t)je * p.P + i] = (bits[jel * p.WB + (i >> 5)] >> (i & 31)) & 1u;
-        }
-    }
 
     // ---- B: fixed-order reductions.  Three small warp jobs per env, every lane busy: lanes are split
     //      into (quantity, segment) pairs, each lane sums its segment serially, then a short xor tree.
@@ -789,18 +715,10 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                     const int k = k0 + lane / nseg, seg = lane & (nseg - 1);
                     double sp_ = 0.0;
                     if (k < p.Tr && lane / nseg < per) {
-                        if (COMPACT) {        // dense busy list: pick this transformer's chargers by their tag
-                            const int nb = nbusy[jel];
-                            const int chunk = (nb + nseg - 1) / nseg;
-                            const int lo = seg * chunk, hi = min(nb, lo + chunk);
-                            for (int i = lo; i < hi; ++i)
-                                if (ctr[jel * p.C + i] == k) sp_ += red[RedP * NT + jel * p.C + i];
-                        } else {
-                            const int i0 = p.tr_cs_off[k], n_k = p.tr_cs_off[k + 1] - i0;
-                            const int chunk = (n_k + nseg - 1) / nseg;
-                            const int lo = seg * chunk, hi = min(n_k, lo + chunk);
-                            for (int i = lo; i < hi; ++i) sp_ += red[RedP * NT + jel * p.C + p.tr_cs_idx[i0 + i]];
-                        }
+                        const int i0 = p.tr_cs_off[k], n_k = p.tr_cs_off[k + 1] - i0;
+                        const int chunk = (n_k + nseg - 1) / nseg;
+                        const int lo = seg * chunk, hi = min(n_k, lo + chunk);
+                        for (int i = lo; i < hi; ++i) sp_ += red[RedP * NT + jel * p.C + p.tr_cs_idx[i0 + i]];
                     }
                     for (int o = nseg >> 1; o > 0; o >>= 1) sp_ += __shfl_xor_sync(0xffffffffu, sp_, o);
                     if (seg == 0 && k < p.Tr && lane / nseg < per) {
@@ -818,9 +736,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 const int q = lane >> 2, seg = lane & 3;
                 double v = 0.0;
                 if (q < kNRed) {
-                    const int nsl = COMPACT ? nbusy[jel] : p.C;           // slots that hold a charger
-                    const int chunk = (nsl + 3) >> 2;
-                    const int lo = seg * chunk, hi = min(nsl, lo + chunk);
+                    const int chunk = (p.C + 3) >> 2;
+                    const int lo = seg * chunk, hi = min(p.C, lo + chunk);
                     const double *r = red + q * NT + jel * p.C;
                     for (int i = lo; i < hi; ++i) v += r[i];
                 }
@@ -831,9 +748,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 const int q = lane >> 3, seg = lane & 7;
                 int v = 0;
                 if (q < 3) {
-                    const int nsl = COMPACT ? nbusy[jel] : p.C;
-                    const int chunk = (nsl + 7) >> 3;
-                    const int lo = seg * chunk, hi = min(nsl, lo + chunk);
+                    const int chunk = (p.C + 7) >> 3;
+                    const int lo = seg * chunk, hi = min(p.C, lo + chunk);
                     for (int i = lo; i < hi; ++i) v += (cnt[jel * p.C + i] >> (10 * q)) & 1023;
                 }
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -900,7 +816,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] += fabs(d);
                 if (usage > et.setpoint) kpi[EV2B_KPI_TRACKER_VIOLATION] += usage - et.setpoint;
                 kpi[EV2B_KPI_EVS_SPAWNED] += (double)((w >> 20) & 1023);
-                kpi[EV2B_KPI_INVALID_ACTIONS] += COMPACT ? (double)(p.P - nbusy[p.EPB + tid]) : (double)(w & 1023);
+                kpi[EV2B_KPI_INVALID_ACTIONS] += (double)(w & 1023);
                 kpi[EV2B_KPI_STEPS] += 1.0;
                 p.env_pot[je] = (jt + 1 < p.T) ? v[RedPot] : 0.0;              // ev2gym_env.py:424-426
                 p.env_usage[je] = usage;
@@ -974,7 +890,6 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
     __syncthreads();
     if (threadIdx.x == 0) {
         p.env_step[e] = 0; p.env_scn[e] = s; p.env_pot[e] = 0.0; p.env_usage[e] = 0.0;
-        for (int w = 0; w < p.WB; ++w) p.occ_bits[(size_t)e * p.WB + w] = 0u;
         for (int k = 0; k < EV2B_KPI_COUNT; ++k) p.env_kpi[(size_t)e * EV2B_KPI_COUNT + k] = 0.0;
     }
     if (p.stats)
