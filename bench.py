@@ -318,6 +318,24 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * E * n_e2e / float(te.item())
+    e2e_step_ms = float(te.item()) / n_e2e * 1e3
+
+    # PCIe floor of one e2e step: the same bytes as plain pinned copies, each direction alone (the link is full duplex)
+    def copy_ms(dst, src, n=20):
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        c0.record()
+        for _ in range(n):
+            dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        return c0.elapsed_time(c1) / n
+    d2h_bytes, h2d_bytes = E * (8 + 4 + 4 * D), E * topo.P * 4
+    dbuf, hbuf = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev), torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
+    d2h_ms = copy_ms(hbuf, dbuf)
+    h2d_ms = copy_ms(dbuf[:h2d_bytes], hbuf[:h2d_bytes])
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -344,7 +362,10 @@ def main():
                        "cuda_graph": graph is not None, "parallelism": f"env-sharded x{world}"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": E * topo.P * 4,
-                    "d2h_bytes_per_step": E * (8 + 4 + 4 * D), "steps": n_e2e,
+                    "d2h_bytes_per_step": E * (8 + 4 + 4 * D), "steps": n_e2e, "ms_per_step": e2e_step_ms,
+                    "pcie_floor": {"d2h_ms": d2h_ms, "h2d_ms": h2d_ms, "d2h_gbs": d2h_bytes / d2h_ms / 1e6,
+                                   "h2d_gbs": h2d_bytes / h2d_ms / 1e6, "frac": max(d2h_ms, h2d_ms) / e2e_step_ms,
+                                   "what": "the step's bytes as bare pinned cudaMemcpyAsync, each direction alone"},
                     "what": "ev2b_step_host: pinned host actions -> H2D -> fused kernel -> D2H reward+status+obs -> sync"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -69,7 +69,8 @@ class StateView(C.Structure):
 
 EXPORTS = ("ev2b_abi_version", "ev2b_last_error", "ev2b_create", "ev2b_destroy", "ev2b_obs_dim", "ev2b_n_ports",
            "ev2b_load_scenarios", "ev2b_n_scenarios", "ev2b_reset", "ev2b_step", "ev2b_step_host",
-           "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count", "ev2b_episode_stats", "ev2b_step_k")
+           "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count", "ev2b_episode_stats", "ev2b_step_k",
+           "ev2b_agent_actions")
 
 
 def needs_build() -> bool:
@@ -130,6 +131,8 @@ def load():
     L.ev2b_reset_done.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ev2b_state_view_get.restype = C.c_int
     L.ev2b_state_view_get.argtypes = [C.c_void_p, C.POINTER(StateView)]
+    L.ev2b_agent_actions.restype = C.c_int
+    L.ev2b_agent_actions.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ev2b_step_k.restype = C.c_int
     L.ev2b_step_k.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_double, C.c_int,
                               C.POINTER(StepOut), C.c_void_p]

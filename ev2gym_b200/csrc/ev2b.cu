@@ -73,13 +73,17 @@ struct ev2b_handle {
     // device: distribution grid
     int n_bus = 0; double s_base = 1000.0;
     DevBuf<double2> grid_Kt, grid_L; DevBuf<double> grid_act, grid_rea, date_feat;
+    // stock heuristic agents (ev2b_agent_actions): RoundRobin queue state, action scratch of ev2b_step_k
+    double rr_avg_power = 1.0, rr_share = 1.0;
+    DevBuf<int> rr_key, rr_fb; DevBuf<double> agent_act;
     // e2e staging (ev2b_step_host)
     DevBuf<unsigned char> st_actions; DevBuf<double> st_reward; DevBuf<uint32_t> st_status; DevBuf<float> st_obs;
     DevBuf<int> st_scn;
-    static constexpr int kChunks = 4;   // ev2b_step_host pipelines H2D / kernel / D2H over env chunks
-    cudaStream_t chunk_stream[kChunks] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t chunk_ev[kChunks] = {nullptr, nullptr, nullptr, nullptr}, start_ev = nullptr;
-
+    static constexpr int kChunks = 8;   // ev2b_step_host pipelines H2D / kernel / D2H over up to kChunks env chunks
+    int n_chunks = 2;                   // chunks in use (measured: 2 -> 285 us, 4 -> 297 us, 8 -> 342 us per c3 step;
+                                        // EV2B_HOST_CHUNKS overrides, tuning only)
+    cudaStream_t chunk_stream[kChunks] = {};
+    cudaEvent_t chunk_ev[kChunks] = {}, start_ev = nullptr;
     int fail(int code, const char *fmt, ...) {
         char buf[512];
         va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -115,6 +119,7 @@ struct ev2b_handle {
         p.pot_kw = pot_kw.p; p.trA = trA.p; p.trF = trF.p; p.tr_limit = tr_limit.p; p.dr = dr.p; p.dr_count = dr_count.p;
         p.hot = hot.p; p.cap = cap.p; p.exch = exch.p; p.env_step = env_step.p; p.env_scn = env_scn.p;
         p.env_pot = env_pot.p; p.env_usage = env_usage.p; p.env_kpi = env_kpi.p;
+        p.rr_key = rr_key.p; p.rr_fb = rr_fb.p; p.rr_avg_power = rr_avg_power; p.rr_share = rr_share;
         return p;
     }
 };
@@ -203,6 +208,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     int off = 0;
     bool uniform_ports = true;
     std::map<std::array<double, 3>, int> cls_of;
+    double rr_acc = 0.0;
     for (int c = 0; c < C; ++c) {
         CsStatic &s = h->cs_h[c];
         const int ph = tp->cs_phases[c];
@@ -222,6 +228,8 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         }
         s.max_power = std::sqrt((double)ph) * tp->cs_voltage[c] * s.imax / 1000.0;           // utils.py:779-780
         s.min_power = std::sqrt((double)ph) * tp->cs_voltage[c] * s.imin / 1000.0;           // utils.py:781-782
+        s.calap_kw = s.imax * tp->cs_voltage[c] * std::sqrt((double)ph) / 1000.0;              // heuristics.py:120-121
+        rr_acc += s.imax * tp->cs_voltage[c] * std::sqrt((double)ph) / (double)tp->cs_n_ports[c];   // heuristics.py:20-23
         s.port_off = off; s.n_ports = tp->cs_n_ports[c]; s.tr = tp->cs_tr[c]; s.phases = ph;
         std::array<double, 3> key{s.imax, tp->cs_voltage[c], (double)ph};
         auto it = cls_of.find(key);
@@ -236,6 +244,8 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         for (int j = 0; j < s.n_ports; ++j) h->port_cs.push_back(c);
     }
     h->P = off;
+    h->rr_avg_power = rr_acc / (double)C;
+    h->rr_share = 1.0 / (double)tp->cs_n_ports[0];                 // 1 / env.number_of_ports_per_cs  heuristics.py:84
     if (tp->n_bus > 0) {
         if (tp->n_bus != h->Tr || tp->n_bus > 128 || !tp->grid_K || !tp->grid_L) {
             delete h; g_create_error = "ev2b_create: grid needs n_bus == n_transformers <= 128 and K, L"; return EV2B_E_ARG;
@@ -674,12 +684,38 @@ int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_
     return step_range(h, actions, action_dtype, out, 0, h->E, obs_full, (cudaStream_t)stream);
 }
 
+int ev2b_agent_actions(ev2b_handle *h, int agent_kind, double *actions_out, void *stream) {
+    if (!h || !actions_out) return h ? h->fail(EV2B_E_ARG, "agent_actions: null output") : EV2B_E_ARG;
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "agent_actions: no scenario bank loaded");
+    if (agent_kind != EV2B_AGENT_AFAP && agent_kind != EV2B_AGENT_ZERO && agent_kind != EV2B_AGENT_ROUNDROBIN &&
+        agent_kind != EV2B_AGENT_CALAP)
+        return h->fail(EV2B_E_ARG, "agent_actions: agent %d has no action tensor (AFAP, ZERO, ROUNDROBIN, CALAP)", agent_kind);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (agent_kind == EV2B_AGENT_ROUNDROBIN && !h->rr_key.p) {      // first use: every env starts with an empty queue
+        std::vector<int> keys((size_t)h->E * h->P, kRrAbsent), fb((size_t)h->E * 2);
+        for (int e = 0; e < h->E; ++e) { fb[2 * e] = 0; fb[2 * e + 1] = 1; }
+        CUDA_TRY(h, h->rr_key.upload(keys));
+        CUDA_TRY(h, h->rr_fb.upload(fb));
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+    }
+    const int thr = std::min(kMaxThreads, std::max(32, (h->P + 31) / 32 * 32));
+    const size_t sm = (size_t)h->P * 5 + 16;
+    if (sm > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(agent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    agent_kernel<<<h->E, thr, sm, st>>>(h->params(), agent_kind, actions_out);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return EV2B_OK;
+}
+
 int ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, int action_dtype, uint64_t seed,
                 double action_low, int auto_reset, const ev2b_step_out *out, void *stream) {
     if (!h) return EV2B_E_ARG;
     if (h->S == 0) return h->fail(EV2B_E_STATE, "step_k: no scenario bank loaded");
     if (k < 1) return h->fail(EV2B_E_ARG, "step_k: k must be >= 1");
-    if (agent_kind < EV2B_AGENT_EXTERNAL || agent_kind > EV2B_AGENT_UNIFORM) return h->fail(EV2B_E_ARG, "step_k: unknown agent %d", agent_kind);
+    if (agent_kind < EV2B_AGENT_EXTERNAL || agent_kind > EV2B_AGENT_CALAP) return h->fail(EV2B_E_ARG, "step_k: unknown agent %d", agent_kind);
+    const bool tensor_agent = agent_kind == EV2B_AGENT_ROUNDROBIN || agent_kind == EV2B_AGENT_CALAP;   // needs the whole env's state
+    if (tensor_agent && h->agent_act.n < (size_t)h->E * h->P) CUDA_TRY(h, h->agent_act.alloc((size_t)h->E * h->P));
     if (agent_kind == EV2B_AGENT_EXTERNAL && !actions_k) return h->fail(EV2B_E_ARG, "step_k: EXTERNAL agent needs actions_k");
     AgentCfg ag; ag.kind = agent_kind; ag.seed = seed; ag.low = action_low;
     const size_t stride = (size_t)h->E * h->P * (action_dtype == EV2B_F64 ? 8 : 4);
@@ -688,7 +724,14 @@ int ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, in
         const int obs_full = (obs != h->last_obs) ? 1 : 0;
         h->last_obs = obs;
         const void *a = agent_kind == EV2B_AGENT_EXTERNAL ? (const void *)((const unsigned char *)actions_k + stride * i) : (const void *)h->hot.p;
-        int rc = step_range(h, a, action_dtype, out, 0, h->E, obs_full, (cudaStream_t)stream, ag);
+        int rc;
+        if (tensor_agent) {
+            rc = ev2b_agent_actions(h, agent_kind, h->agent_act.p, stream);
+            if (rc != EV2B_OK) return rc;
+            rc = step_range(h, h->agent_act.p, EV2B_F64, out, 0, h->E, obs_full, (cudaStream_t)stream);
+        } else {
+            rc = step_range(h, a, action_dtype, out, 0, h->E, obs_full, (cudaStream_t)stream, ag);
+        }
         if (rc != EV2B_OK) return rc;
         if (auto_reset) {
             rc = ev2b_reset_done(h, obs, stream);
@@ -711,6 +754,7 @@ int ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype, d
     const bool want_obs = obs_host && h->D > 0;
     if (want_obs && h->st_obs.n < (size_t)h->E * h->D) CUDA_TRY(h, h->st_obs.alloc((size_t)h->E * h->D));
     if (!h->start_ev) {
+        if (const char *ov = getenv("EV2B_HOST_CHUNKS")) h->n_chunks = std::min(ev2b_handle::kChunks, std::max(1, atoi(ov)));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
         for (int i = 0; i < ev2b_handle::kChunks; ++i) {
             CUDA_TRY(h, cudaStreamCreateWithFlags(&h->chunk_stream[i], cudaStreamNonBlocking));
@@ -724,25 +768,31 @@ int ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype, d
     h->last_obs = out.obs;
     // PCIe is full duplex and the copy engines run beside the SMs: split the env range into chunks, each on its
     // own stream (H2D actions -> kernel -> D2H results), so chunk i's download overlaps chunk i+1's upload/compute.
-    const int per = ((h->E + ev2b_handle::kChunks - 1) / ev2b_handle::kChunks + h->EPB - 1) / h->EPB * h->EPB;
-    CUDA_TRY(h, cudaEventRecord(h->start_ev, user));
+    const int per = ((h->E + h->n_chunks - 1) / h->n_chunks + h->EPB - 1) / h->EPB * h->EPB;
     const unsigned char *ah = static_cast<const unsigned char *>(actions_host);
-    for (int c = 0; c < ev2b_handle::kChunks; ++c) {
-        const int lo = c * per, hi = std::min(h->E, lo + per);
-        if (lo >= hi) break;
-        cudaStream_t st = h->chunk_stream[c];
-        CUDA_TRY(h, cudaStreamWaitEvent(st, h->start_ev, 0));
-        const size_t aoff = (size_t)lo * h->P * esz, abytes = (size_t)(hi - lo) * h->P * esz;
-        CUDA_TRY(h, cudaMemcpyAsync(h->st_actions.p + aoff, ah + aoff, abytes, cudaMemcpyHostToDevice, st));
-        int rc = step_range(h, h->st_actions.p, action_dtype, &out, lo, hi, obs_full, st);
-        if (rc != EV2B_OK) return rc;
-        if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host + lo, h->st_reward.p + lo, sizeof(double) * (hi - lo), cudaMemcpyDeviceToHost, st));
-        if (status_host) CUDA_TRY(h, cudaMemcpyAsync(status_host + lo, h->st_status.p + lo, sizeof(uint32_t) * (hi - lo), cudaMemcpyDeviceToHost, st));
-        if (want_obs) CUDA_TRY(h, cudaMemcpyAsync(obs_host + (size_t)lo * h->D, h->st_obs.p + (size_t)lo * h->D,
-                                                  sizeof(float) * (size_t)(hi - lo) * h->D, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(h, cudaEventRecord(h->chunk_ev[c], st));
-        CUDA_TRY(h, cudaStreamWaitEvent(user, h->chunk_ev[c], 0));
-    }
+    auto issue = [&](cudaStream_t root) -> int {
+        CUDA_TRY(h, cudaEventRecord(h->start_ev, root));
+        for (int c = 0; c < h->n_chunks; ++c) {
+            const int lo = c * per, hi = std::min(h->E, lo + per);
+            if (lo >= hi) break;
+            cudaStream_t st = h->chunk_stream[c];
+            CUDA_TRY(h, cudaStreamWaitEvent(st, h->start_ev, 0));
+            const size_t aoff = (size_t)lo * h->P * esz, abytes = (size_t)(hi - lo) * h->P * esz;
+            CUDA_TRY(h, cudaMemcpyAsync(h->st_actions.p + aoff, ah + aoff, abytes, cudaMemcpyHostToDevice, st));
+            int rc = step_range(h, h->st_actions.p, action_dtype, &out, lo, hi, obs_full, st);
+            if (rc != EV2B_OK) return rc;
+            if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host + lo, h->st_reward.p + lo, sizeof(double) * (hi - lo), cudaMemcpyDeviceToHost, st));
+            if (status_host) CUDA_TRY(h, cudaMemcpyAsync(status_host + lo, h->st_status.p + lo, sizeof(uint32_t) * (hi - lo), cudaMemcpyDeviceToHost, st));
+            if (want_obs) CUDA_TRY(h, cudaMemcpyAsync(obs_host + (size_t)lo * h->D, h->st_obs.p + (size_t)lo * h->D,
+                                                      sizeof(float) * (size_t)(hi - lo) * h->D, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(h, cudaEventRecord(h->chunk_ev[c], st));
+            CUDA_TRY(h, cudaStreamWaitEvent(root, h->chunk_ev[c], 0));
+        }
+        return EV2B_OK;
+    };
+    h->host_direct += 1;
+    const int rc = issue(user);
+    if (rc != EV2B_OK) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(user));
     return EV2B_OK;
 }

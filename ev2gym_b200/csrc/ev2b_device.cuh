@@ -35,6 +35,7 @@ namespace ev2b {
 
 constexpr int   kNoArrival = 32767;   // "no (further) session on this port"
 constexpr int   kMaxThreads = 1024;
+constexpr int   kRrAbsent = 0x7fffffff;
 constexpr int   kNRed = 7;            // float64 partials per charger, see Red* below
 enum { RedP = 0, RedProfit, RedSatExp, RedPot, RedCharged, RedDischarged, RedSatSum };
 
@@ -47,6 +48,8 @@ struct CsStatic {            // one per charger; ev_charger.py:41-75 + derived c
     double min_power;        // sqrt(ph)*V*Imin/1000   utils.py:781-782
     int    port_off, n_ports, tr, phases;
     int    cls, pad0, pad1, pad2;   // charger class (distinct imax/voltage/phases) for the potential table
+    double calap_kw;         // imax*V*sqrt(ph)/1000 in the operation order of heuristics.py:120-121
+    double pad3;
 };
 
 struct EvSpec {              // de-duplicated EV model; ev.py:45-113
@@ -108,6 +111,9 @@ struct Params {
     double *st_soc_sum, *st_abs_e, *st_act, *st_r;   // [E,P], [E,P], [E,P,L], [E,P,Smax]
     int *st_cnt, *st_nfin;     // [E,P] n_hist | n_act << 16 ; finalised sessions on the port
     double *cs_sat_sum, *cs_dcal, *cs_dcyc; int *cs_served, *cs_em;   // [E,C]
+    // RoundRobin agent queue (heuristics.py:29,33-52): sort key per port (kRrAbsent = not queued) + front/back counters
+    int *rr_key; int *rr_fb;   // [E,P], [E,2]; null until the agent is first used
+    double rr_avg_power, rr_share;   // heuristics.py:19-23 ; 1 / number_of_ports_per_cs
     // state
     uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;
     double *env_kpi;
@@ -856,6 +862,10 @@ __global__ void reset_ports_kernel(const Params p, int lo, int hi, const int *sc
     p.hot[(size_t)e * p.P + port] = h;
     p.cap[(size_t)e * p.P + port] = 0.0;
     p.exch[(size_t)e * p.P + port] = 0.f;
+    if (p.rr_key) {                       // a new episode starts with a fresh agent: empty queue
+        p.rr_key[(size_t)e * p.P + port] = kRrAbsent;
+        if (port == 0) { p.rr_fb[2 * e] = 0; p.rr_fb[2 * e + 1] = 1; }
+    }
     if (p.stats) {
         const size_t ip = (size_t)e * p.P + port;
         p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0; p.st_nfin[ip] = 0;
@@ -897,6 +907,93 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
             const size_t ec = (size_t)e * p.C + c;
             p.cs_sat_sum[ec] = 0.0; p.cs_dcal[ec] = 0.0; p.cs_dcyc[ec] = 0.0; p.cs_served[ec] = 0; p.cs_em[ec] = 0;
         }
+}
+
+// ---- stock heuristic agents: agent.get_action(env) for every env, one CTA per env -------------------------
+// ROUNDROBIN (heuristics.py:7-95).  The reference keeps an ordered list of waiting ports: newly waiting EVs are
+// inserted at the FRONT while the ports are scanned in ascending order, EVs that are full or gone are removed, the first
+// k = min(ceil(setpoint / average port power), len) entries are served and moved, in order, to the BACK.  Restated with
+// one integer sort key per port (queue order == ascending key): a new port takes `front - 1 - (#new ports before it)`
+// (so later ports end up nearer the front, as repeated insert(0, .) does), served ports take `back + rank`.  A port's
+// position in the queue is the number of queued ports with a smaller key -- an O(P) shared-memory scan per port instead of
+// the reference's O(P) list searches per port.
+// CALAP (heuristics.py:98-150): per-port, stateless.
+__global__ void agent_kernel(const Params p, int kind, double *act) {
+    extern __shared__ int a_sm[];                 // [P] keys, then [P] bytes: bit0 queued, bit1 new
+    int *skey = a_sm;
+    unsigned char *sflag = reinterpret_cast<unsigned char *>(a_sm + p.P);
+    __shared__ int s_new, s_len;
+    const int e = blockIdx.x;
+    const int t = p.env_step[e], s = p.env_scn[e];
+    double *arow = act + (size_t)e * p.P;
+    if (t >= p.T || kind == EV2B_AGENT_ZERO || kind == EV2B_AGENT_AFAP) {
+        const double v = (t < p.T && kind == EV2B_AGENT_AFAP) ? 1.0 : 0.0;     // heuristics.py:161-166
+        for (int i = threadIdx.x; i < p.P; i += blockDim.x) arow[i] = v;
+        return;
+    }
+    if (kind == EV2B_AGENT_CALAP) {
+        for (int i = threadIdx.x; i < p.P; i += blockDim.x) {
+            const size_t ip = (size_t)e * p.P + i;
+            const uint4 h = p.hot[ip];
+            double a = 0.0;
+            if (hot_t_arr(h) <= t && t <= hot_t_dep(h)) {
+                const CsStatic &cs = p.cs[p.port_cs[i]];
+                const EvSpec *sp = p.spec + hot_spec(h);
+                const double pmax = sp->pmax_ac;
+                const double kw = pmax < cs.calap_kw ? pmax : cs.calap_kw;                            // min(cs, ev)  :123-124
+                const double soc = p.cap[ip] / sp->B;
+                const double steps = ceil((1.0 - soc) / (kw * p.period / 60.0 / sp->B));                          // :127-128
+                if (soc < 1.0 && (double)hot_t_dep(h) - steps <= (double)t) a = 1.0;                               // :130-132
+            }
+            arow[i] = a;
+        }
+        return;
+    }
+    // ---- ROUNDROBIN
+    if (threadIdx.x == 0) { s_new = 0; s_len = 0; }
+    __syncthreads();
+    int *gkey = p.rr_key + (size_t)e * p.P;
+    const int front = p.rr_fb[2 * e], back = p.rr_fb[2 * e + 1];
+    for (int i = threadIdx.x; i < p.P; i += blockDim.x) {                          // update_ev_buffer :33-52
+        const size_t ip = (size_t)e * p.P + i;
+        const uint4 h = p.hot[ip];
+        bool waiting = false;
+        if (hot_t_arr(h) <= t && t <= hot_t_dep(h)) waiting = p.cap[ip] / p.spec[hot_spec(h)].B < 1.0;   // get_soc() < 1
+        const int key = gkey[i];
+        const bool fresh = waiting && key == kRrAbsent;
+        skey[i] = waiting ? key : kRrAbsent;
+        sflag[i] = (unsigned char)((waiting ? 1 : 0) | (fresh ? 2 : 0));
+        if (fresh) atomicAdd(&s_new, 1);
+        if (waiting) atomicAdd(&s_len, 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.P; i += blockDim.x) {
+        if (!(sflag[i] & 2)) continue;
+        int before = 0;
+        for (int j = 0; j < i; ++j) before += (sflag[j] >> 1) & 1;
+        skey[i] = front - 1 - before;
+    }
+    __syncthreads();
+    const double want = p.env_t[(size_t)s * p.T + t].setpoint * 1000.0 / p.rr_avg_power;   // :58-60
+    const double cw = ceil(want);
+    const int len = s_len;
+    const int k = cw < (double)len ? (int)cw : len;                                // min(int(ceil(.)), len(buffer))
+    for (int i = threadIdx.x; i < p.P; i += blockDim.x) {
+        double a = 0.0;
+        int key = skey[i];
+        if (sflag[i] & 1) {
+            int rank = 0;
+            for (int j = 0; j < p.P; ++j) rank += ((sflag[j] & 1) && skey[j] < key) ? 1 : 0;
+            if (rank < k) {
+                a = p.rr_share;                                                    // :84
+                if (rank == k - 1 && want < (double)k) a = want - (double)rank;    // :85-86
+                key = back + rank;                                                 // served EVs go to the back, in order
+            }
+        }
+        arow[i] = a;
+        gkey[i] = key;
+    }
+    if (threadIdx.x == 0) { p.rr_fb[2 * e] = front - s_new; p.rr_fb[2 * e + 1] = back + (k > 0 ? k : 0); }
 }
 
 // ---- get_statistics(env)  utils.py:12-123: one CTA per env, fixed-order sums by thread 0 ----------

@@ -217,7 +217,20 @@ class BatchedEngine:
         self._check(self.L.ev2b_step(self.h, actions.data_ptr(), dt, C.byref(self._so), self._stream()), "ev2b_step")
         return self.out
 
-    AGENTS = {"external": 0, "afap": 1, "zero": 2, "uniform": 3}
+    AGENTS = {"external": 0, "afap": 1, "zero": 2, "uniform": 3, "roundrobin": 4, "calap": 5}
+
+    def agent_actions(self, agent: str, out=None):
+        """`agent.get_action(env)` of a stock heuristic (ev2gym/baselines/heuristics.py) for every env's current state:
+        float64 cuda tensor [E,P] to pass to `step`.  "afap", "zero", "roundrobin" (stateful: one call == one
+        get_action; the per-env queue empties when the env is reset), "calap"."""
+        torch = self.torch
+        if out is None:
+            out = torch.empty((self.E, self.P), dtype=torch.float64, device=self.dev)
+        if out.dtype != torch.float64 or tuple(out.shape) != (self.E, self.P) or not out.is_contiguous() or not out.is_cuda:
+            raise EngineError(f"out must be a contiguous float64 cuda tensor of shape {(self.E, self.P)}")
+        self._check(self.L.ev2b_agent_actions(self.h, self.AGENTS[agent], out.data_ptr(), self._stream()),
+                    "ev2b_agent_actions")
+        return out
 
     def step_k(self, k: int, agent: str = "afap", actions_k=None, seed: int = 0, auto_reset: bool = False):
         """k steps without returning to the host, driven by an on-device agent (or actions_k [k,E,P])."""

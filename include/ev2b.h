@@ -51,7 +51,9 @@ enum ev2b_agent_kind {
     EV2B_AGENT_EXTERNAL = 0,      /* actions_k[k,E,P] supplied by the caller                                   */
     EV2B_AGENT_AFAP = 1,          /* ChargeAsFastAsPossible: all ones        ev2gym/baselines/heuristics.py:161-166 */
     EV2B_AGENT_ZERO = 2,          /* DoNothing: all zeros                    heuristics.py (DoNothing)          */
-    EV2B_AGENT_UNIFORM = 3        /* RandomAgent-like: uniform in the action space, counter-based hash RNG      */
+    EV2B_AGENT_UNIFORM = 3,       /* RandomAgent-like: uniform in the action space, counter-based hash RNG      */
+    EV2B_AGENT_ROUNDROBIN = 4,    /* RoundRobin: setpoint-sized rotating queue of waiting EVs   heuristics.py:7-95    */
+    EV2B_AGENT_CALAP = 5          /* ChargeAsLateAsPossible                                     heuristics.py:98-150  */
 };
 
 /* error codes */
@@ -213,6 +215,14 @@ int  ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype,
  * a = low + (1-low) * u, u = (mix32(seed, env*P+port, step) >> 8) * 2^-24, low = -1 if v2g (action_low) else 0. */
 int  ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, int action_dtype, uint64_t seed,
                  double action_low, int auto_reset, const ev2b_step_out *out, void *stream);
+
+/* agent.get_action(env) of a stock heuristic for the CURRENT state of every env  (ev2gym/baselines/heuristics.py):
+ * actions_out = DEVICE [E,P] float64 (the reference's agents return float64 arrays), ready for ev2b_step(..., EV2B_F64).
+ * AFAP / ZERO / ROUNDROBIN / CALAP.  ROUNDROBIN keeps the reference's per-agent queue (`ev_buffer`) per env inside the
+ * handle: every call is one get_action (it rotates the queue), and ev2b_reset / ev2b_reset_done empty the queue of the
+ * envs they reset (the reference's scripts build a fresh agent per episode).  Finished envs get zeros.
+ * ev2b_step_k accepts the same kinds and calls this before every step. */
+int  ev2b_agent_actions(ev2b_handle *h, int agent_kind, double *actions_out, void *stream);
 
 /* Device-side auto-reset of every env whose episode is over: next scenario id =
  * (current id + n_envs) mod bank size.  For vectorised RL rollouts. */

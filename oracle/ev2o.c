@@ -15,6 +15,13 @@
 #include <stddef.h>
 #include <string.h>
 
+/* The reference squares Python/numpy float64 SCALARS with `x**2` (reward.py:12,102; utils.py:38; ev.py:508), which
+ * calls libm pow(x, 2.0).  glibc's pow is not correctly rounded: about 0.1 % of arguments come out 1 ulp away from
+ * x*x.  To restate the reference literally the oracle calls the same libm function; the Makefile passes
+ * -fno-builtin-pow because gcc otherwise folds pow(x, 2.0) into x*x.  (The CUDA path uses the correctly rounded
+ * x*x, see DESIGN.md "known deviations".) */
+static double py_sq(double x) { return pow(x, 2.0); }
+
 /* ------------------------------------------------------------------------- */
 /* helpers                                                                   */
 
@@ -414,7 +421,7 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
                 st->cs_total_served[c] += 1;
                 st->cs_total_sat[c] += sat;
                 sat_exp_sum += 100.0 * exp(-10.0 * sat);
-                user_costs += -((capn - des) * (capn - des));            /* reward.py:99-102 */
+                user_costs += -py_sq(capn - des);                        /* reward.py:99-102 */
                 if (out->dep_sat) out->dep_sat[p] = sat;
                 n_departed++;
             }
@@ -537,7 +544,7 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
     case EV2O_REWARD_SQ_TRACKING: {                                  /* reward.py:11-12 */
         double m = sc->setpoint[tm1] < st->potential[tm1] ? sc->setpoint[tm1] : st->potential[tm1];
         double d = m - st->usage[tm1];
-        reward = -(d * d);
+        reward = -py_sq(d);
     } break;
     case EV2O_REWARD_PROFIT_TR_USER: {                               /* reward.py:36-44: costs, then -= per tr, then -= per EV */
         reward = total_costs;
@@ -590,7 +597,7 @@ void ev2o_statistics(const ev2o_topology *tp, const ev2o_scenario *sc, const ev2
     double te = 0, ete = 0, viol = 0;                                  /* utils.py:31-46 */
     for (int t = 0; t < T; ++t) {
         double d = sc->setpoint[t] - st->usage[t];
-        te += d * d; ete += fabs(d);
+        te += py_sq(d); ete += fabs(d);                                /* utils.py:37-38 */
         if (st->usage[t] > sc->setpoint[t]) viol += st->usage[t] - sc->setpoint[t];
     }
     ete *= (double)tp->timescale / 60.0;
@@ -614,7 +621,7 @@ void ev2o_statistics(const ev2o_topology *tp, const ev2o_scenario *sc, const ev2
         double dev = fabs(avg_f - final_soc); for (int j = 0; j < nf; ++j) dev += fabs(avg_f - f[j]);
         double delta_DoD = 2.0 * (dev / (double)(nf + 1));
         double v_half = v_min + k * 0.5;
-        double beta = z0 * (v_half - z1) * (v_half - z1) + z2 + z3 * delta_DoD;
+        double beta = z0 * py_sq(v_half - z1) + z2 + z3 * delta_DoD;          /* ev.py:508 */
         double Q_sim = (st->ev_abs_energy[i] / b_cap_kwh) * b_cap_ah;
         double Q_acc = 2 * (b_age * (d_dist / 365) * G * b_cap_ah) / b_cap_kwh;
         double d_cyc = beta * 0.5 * Q_sim / pow(Q_acc, 0.5);

@@ -251,6 +251,7 @@ class OracleBatch:
         self.threads = threads if threads > 0 else self.L.ev2o_max_threads()
         self.reward_kind, self.state_kind = REWARD_KINDS[reward], STATE_KINDS[state]
         self._t = _TopoC(topo)
+        self._scenarios = list(scenarios)
         uniq = {}
         self._scn = []
         for sc in scenarios:           # scenarios may repeat (tiling): share the C view
@@ -288,6 +289,20 @@ class OracleBatch:
         for e in range(self.E):
             self.L.ev2o_statistics(C.byref(self._t.c), self._scn_ptrs[e], C.byref(self.states[e]), _p(out[e]))
         return {n: out[:, i].copy() for i, n in enumerate(STAT_NAMES)}
+
+    def env_view(self, e: int):
+        """What oracle/agents.py reads of one env (same attribute names as OracleEnv), live views of env `e`."""
+        batch = self
+
+        class _View:
+            topo = batch.topo
+            scenario = batch._scenarios[e]
+            arr = {k: v[e] for k, v in batch.arr.items()}
+
+            @property
+            def current_step(self):
+                return batch.states[e].current_step
+        return _View()
 
     def step(self, actions: np.ndarray):
         a = np.ascontiguousarray(actions, dtype=np.float64)

@@ -178,7 +178,10 @@ def test_ragged_ports_and_reset_done():
         assert _close(obs, orc.reset(), 1e-5, 1e-5)
 
 
-def test_step_host_matches_device_path():
+@pytest.mark.parametrize("pinned", [False, True])
+def test_step_host_matches_device_path(pinned):
+    """ev2b_step_host == ev2b_step, with pageable host arrays (plain stream calls) and with pinned ones (the call is
+    replayed from a captured graph keyed by the buffer addresses; two action buffers alternate)."""
     import torch
     from ev2gym_b200.scenario import Topology
     from ev2gym_b200.synthetic import sample_bank
@@ -189,9 +192,21 @@ def test_step_host_matches_device_path():
     e2 = _engine(topo, bank, E, "profit_maximization", "V2G_profit_max", ("reward", "status", "obs"))
     e1.reset(); e2.reset()
     rng = np.random.default_rng(1)
-    rew, stt, obs = np.zeros(E), np.zeros(E, dtype=np.uint32), np.zeros((E, e1.D), dtype=np.float32)
+    if pinned:
+        keep = [torch.zeros(E, dtype=torch.float64).pin_memory(), torch.zeros(E, dtype=torch.int32).pin_memory(),
+                torch.zeros((E, e1.D), dtype=torch.float32).pin_memory(),
+                torch.zeros((E, topo.P), dtype=torch.float32).pin_memory(), torch.zeros((E, topo.P), dtype=torch.float32).pin_memory()]
+        rew, stt, obs = keep[0].numpy(), keep[1].numpy().view(np.uint32), keep[2].numpy()
+        abuf = [keep[3].numpy(), keep[4].numpy()]
+    else:
+        rew, stt, obs = np.zeros(E), np.zeros(E, dtype=np.uint32), np.zeros((E, e1.D), dtype=np.float32)
     for t in range(topo.T):
         a = rng.uniform(-1, 1, (E, topo.P)).astype(np.float32)
+        if pinned:
+            abuf[t % 2][...] = a
+            a = abuf[t % 2]
+        if t == 17:                      # a reset in the middle must not be hidden by the replayed graphs
+            e1.reset(); e2.reset()
         o1 = e1.step(torch.tensor(a, device="cuda"))
         e2.step_host(a, rew, stt, obs)
         assert np.array_equal(o1["reward"].cpu().numpy(), rew)
@@ -259,3 +274,62 @@ def test_grid_power_flow_matches_oracle_on_synthetic():
             assert _close(out["reward"], orc.reward, 1e-9, 1e-9), t
             assert _close(out["obs"], orc.o["obs"][:, :eng.D], 1e-5, 1e-5), t
         eng.close()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if "roundrobin" in n or "calap" in n])
+def test_device_agents_match_reference_agents(name):
+    """ev2b_agent_actions == the action vector the reference's RoundRobin / ChargeAsLateAsPossible emitted at every step
+    of the recorded episode (float64, bit-exact: queue order, fractional last EV, CALAP's ceil)."""
+    from ev2gym_b200.scenario import ScenarioPack
+    pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
+    tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+    E = 3
+    eng = _engine(pack.topo, pack.scenarios, E, str(tr["reward_fn"]), str(tr["state_fn"]), ("reward", "status"))
+    eng.reset()
+    kind = "roundrobin" if "roundrobin" in name else "calap"
+    for t in range(tr["reward"].shape[0]):
+        a = eng.agent_actions(kind)
+        got = a.cpu().numpy()
+        assert np.array_equal(got[0], tr["actions"][t]) and np.array_equal(got[E - 1], tr["actions"][t]), t
+        out = eng.step(a)
+        assert _close(out["reward"][0].item(), tr["reward"][t], 1e-9, 1e-9), t
+    assert bool((out["status"] & 1).all())
+    assert not eng.agent_actions(kind).any()            # finished envs: zeros
+
+
+@pytest.mark.parametrize("agent,C,n", [("roundrobin", 30, 2), ("calap", 30, 2), ("roundrobin", 17, 3), ("roundrobin", 600, 2)])
+def test_step_k_tensor_agents(agent, C, n):
+    """ev2b_step_k with the queue-based / whole-env agents == oracle env driven by oracle/agents.py, including the
+    queue reset at ev2b_reset and ports beyond one CTA pass (P = 1200)."""
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    from oracle.agents import OracleChargeAsLateAsPossible, OracleRoundRobin
+    from oracle.oracle import OracleBatch
+    T = 12 if C > 100 else 40
+    topo = Topology.uniform(C=C, n_ports=n, Tr=2, T=T, v2g_enabled=False)
+    bank = sample_bank(topo, 3, seed=33, min_stay=4, occupancy=0.8)
+    for sc in bank:                       # setpoints that serve a fraction of the waiting EVs (fractional last share)
+        sc.setpoint = np.round(sc.setpoint * (0.02 if C > 100 else 0.35), 3)
+        sc.normalise()
+    E = 4 if C > 100 else 7
+    rw, stf = "SquaredTrackingErrorReward", "PublicPST"
+    eng = _engine(topo, bank, E, rw, stf, ("reward", "status", "obs"))
+    orc = OracleBatch(topo, [bank[e % 3] for e in range(E)], reward=rw, state=stf)
+    caps = eng.state_tensors()["port_cap"]
+    for episode in range(2):
+        eng.reset(); orc.reset()
+        views = [orc.env_view(e) for e in range(E)]
+        agents = [OracleRoundRobin(v) if agent == "roundrobin" else OracleChargeAsLateAsPossible() for v in views]
+        t, served = 0, 0
+        for k in ((3, 9) if C > 100 else (1, 7, 20, 12)):
+            for i in range(k):
+                a = np.stack([ag.get_action(v) for ag, v in zip(agents, views)])
+                served += int(np.count_nonzero(a))
+                orc.step(a)
+            out = eng.step_k(k, agent)
+            t += k
+            occ = orc.arr["port_session"] >= 0
+            assert np.array_equal(caps.cpu().numpy()[occ], orc.arr["port_cap"][occ]), (agent, episode, t)
+            assert _close(out["reward"].cpu().numpy(), orc.reward, 1e-9, 1e-9)
+            assert _close(out["obs"].cpu().numpy(), orc.o["obs"][:, :eng.D], 1e-5, 1e-5)
+        assert t == topo.T and served > 0

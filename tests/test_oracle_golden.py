@@ -164,3 +164,22 @@ def test_oracle_statistics_match_reference(name):
         ref = float(tr["stat_" + k])
         assert (np.isnan(ref) and np.isnan(st[k])) or st[k] == pytest.approx(ref, rel=1e-10, abs=1e-12), k
     assert np.array_equal(env.arr["ev_afap"][env.arr["ev_spawned"] > 0], tr["afap"])
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if "roundrobin" in n or "calap" in n])
+def test_oracle_agents_match_reference_agents(name):
+    """oracle/agents.py emits, step by step, exactly the action vector the reference's RoundRobin /
+    ChargeAsLateAsPossible (heuristics.py:7-150) produced on the same episode (bit-exact float64)."""
+    from oracle.agents import OracleChargeAsLateAsPossible, OracleRoundRobin
+    pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
+    tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+    env = OracleEnv(pack.topo, pack.scenarios[0], reward=str(tr["reward_fn"]), state=str(tr["state_fn"]))
+    env.reset()
+    agent = OracleRoundRobin(env) if "roundrobin" in name else OracleChargeAsLateAsPossible()
+    nonzero = 0
+    for t in range(tr["reward"].shape[0]):
+        a = agent.get_action(env)
+        assert np.array_equal(a, tr["actions"][t]), t
+        nonzero += int(np.count_nonzero(a))
+        env.step(a)
+    assert nonzero > 0

@@ -121,7 +121,8 @@ def record_episode(base, overrides, seed, agent, state=None, reward=None):
     topo, scn = topology_from_env(env), scenario_from_env(env)
     T, P, C, Tr = env.simulation_length, env.number_of_ports, env.cs, len(env.transformers)
     rng = np.random.default_rng(seed + 7919)
-    rr = ref_agents.RoundRobin(env) if agent == "roundrobin" else None
+    rr = ref_agents.RoundRobin(env) if agent == "roundrobin" else \
+        ref_agents.ChargeAsLateAsPossible() if agent == "calap" else None
 
     captured = {}
     inner = env.reward_function
@@ -217,6 +218,11 @@ CASES = [
     ("grid_c40_uniform_s3", "V2Ggrid", {"number_of_charging_stations": 40}, 3, "uniform"),          # Laurent power flow
     ("grid_c20n2_mixed_s5", "V2Ggrid", {"number_of_charging_stations": 20, "number_of_ports_per_cs": 2,
                                        "_reward": "V2G_grid_simple_reward"}, 5, "mixed"),
+    ("pst12n2_roundrobin_s12", "PublicPST", {"number_of_charging_stations": 12, "number_of_ports_per_cs": 2}, 12,
+     "roundrobin"),                                                                                  # fractional last EV, 1/n_ports
+    ("pst25_calap_s6", "PublicPST", {"number_of_charging_stations": 25}, 6, "calap"),
+    ("loads_c10n2_calap_s13", "V2GProfitPlusLoads",
+     {"number_of_charging_stations": 10, "number_of_ports_per_cs": 2, "number_of_transformers": 2}, 13, "calap"),
     ("ts10_c5_uniform_s10", "V2GProfitMax", {"number_of_charging_stations": 5, "timescale": 10,
                                              "simulation_length": 150}, 10, "uniform"),
 ]
