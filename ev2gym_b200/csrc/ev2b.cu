@@ -790,7 +790,6 @@ int ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype, d
         }
         return EV2B_OK;
     };
-    h->host_direct += 1;
     const int rc = issue(user);
     if (rc != EV2B_OK) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(user));

@@ -181,7 +181,7 @@ def test_ragged_ports_and_reset_done():
 @pytest.mark.parametrize("pinned", [False, True])
 def test_step_host_matches_device_path(pinned):
     """ev2b_step_host == ev2b_step, with pageable host arrays (plain stream calls) and with pinned ones (the call is
-    replayed from a captured graph keyed by the buffer addresses; two action buffers alternate)."""
+    same path, the copies then run at full PCIe rate; two action buffers alternate)."""
     import torch
     from ev2gym_b200.scenario import Topology
     from ev2gym_b200.synthetic import sample_bank
