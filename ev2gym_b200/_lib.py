@@ -76,6 +76,8 @@ EXPORTS = ("ev2b_abi_version", "ev2b_last_error", "ev2b_create", "ev2b_destroy",
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
+    if os.environ.get("EV2B_LIB"):       # an explicitly chosen build is used as it is, never rebuilt from the sources
+        return False
     t = os.path.getmtime(LIB_PATH)
     return any(os.path.exists(s) and os.path.getmtime(s) > t for s in SOURCES)
 

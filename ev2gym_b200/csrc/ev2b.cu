@@ -84,6 +84,24 @@ struct ev2b_handle {
                                         // EV2B_HOST_CHUNKS overrides, tuning only)
     cudaStream_t chunk_stream[kChunks] = {};
     cudaEvent_t chunk_ev[kChunks] = {}, start_ev = nullptr;
+    // shared-memory map of step_kernel: byte offsets handed to the kernel through Params (constant bank)
+    int so[15] = {0}, pre_stride = 0;
+    void layout_smem() {
+        const size_t PP = (size_t)EPB * P, nt = (size_t)block, epb = (size_t)EPB;
+        size_t off = 0;
+        auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; const size_t at = off; off += bytes; return (int)at; };
+        pre_stride = kPreTr + 4 * Tr;
+        take(8 * kNRed * nt, 16);                                  // red
+        so[0] = take(8 * PP, 8); so[1] = take(8 * PP, 8); so[2] = take(8 * PP, 8);          // resE, resA, resC
+        so[3] = take(8 * epb * Tr, 8); so[4] = take(8 * epb * Tr, 8); so[5] = take(8 * epb, 8);   // trov, trp, lossv
+        so[6] = take(16 * epb * 3 * n_bus, 16);                    // pfv
+        so[7] = take(8 * epb * kNRed, 8);                          // envs
+        so[14] = take(8 * epb * pre_stride, 16);                   // pre
+        so[8] = take(8 * PP, 8);                                   // whot
+        so[9] = take(4 * nt, 4); so[10] = take(16 * epb, 4); so[11] = take(4 * PP, 4); so[12] = take(16, 4);   // cnt, envi, wl, wcnt
+        so[13] = take(PP, 1);                                      // pflag
+        smem = off;
+    }
     int fail(int code, const char *fmt, ...) {
         char buf[512];
         va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -100,6 +118,9 @@ struct ev2b_handle {
         p.p_magic = P > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)P) + 1u : 0u;
         p.c_magic = C > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)C) + 1u : 0u;
         p.cs_uniform = cs_uniform; p.cs0 = cs_h.empty() ? CsStatic{} : cs_h[0];
+        p.o_resE = so[0]; p.o_resA = so[1]; p.o_resC = so[2]; p.o_trov = so[3]; p.o_trp = so[4]; p.o_lossv = so[5];
+        p.o_pfv = so[6]; p.o_envs = so[7]; p.o_whot = so[8]; p.o_cnt = so[9]; p.o_envi = so[10]; p.o_wl = so[11];
+        p.o_wcnt = so[12]; p.o_pflag = so[13]; p.o_pre = so[14]; p.pre_stride = pre_stride;
         p.n_bus = n_bus; p.s_base = s_base; p.grid_Kt = grid_Kt.p; p.grid_L = grid_L.p; p.grid_act = grid_act.p;
         p.grid_rea = grid_rea.p; p.date_feat = date_feat.p;
         p.stats = (dims.flags & EV2B_F_STATS) ? 1 : 0; p.L = L;
@@ -316,11 +337,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         }
         h->EPB = best_epb;
         h->block = std::max(32, (best_epb * C + 31) / 32 * 32);
-        const size_t PP = (size_t)h->EPB * h->P;
-        h->smem = sizeof(double) * ((size_t)kNRed * h->block + 3 * PP + 2 * (size_t)h->EPB * h->Tr + (size_t)h->EPB + 1 +
-                                    6 * (size_t)h->EPB * h->n_bus + (size_t)h->EPB * kNRed) +
-                  sizeof(uint2) * PP + sizeof(int) * ((size_t)h->block + (size_t)h->EPB * 4 + PP + 4 + 1) +
-                  PP + 16;
+        h->layout_smem();
     }
 #define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
         g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e); delete h; return EV2B_E_CUDA; } } while (0)

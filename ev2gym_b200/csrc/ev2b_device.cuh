@@ -36,6 +36,10 @@ namespace ev2b {
 constexpr int   kNoArrival = 32767;   // "no (further) session on this port"
 constexpr int   kMaxThreads = 1024;
 constexpr int   kRrAbsent = 0x7fffffff;
+// Per-env records every step needs late (phase B / C) are fetched into shared memory with cp.async before the first
+// barrier, so the single-thread tail of a CTA never waits on a global load:
+//   [0,13) KPI sums   [13] charge_power_potential[t]   [14] setpoint[t]   [15] setpoint[t+1]   [16 + 4k, +4) TrT of transformer k
+constexpr int   kPrePot = 13, kPreSet = 14, kPreSetNext = 15, kPreTr = 16;
 constexpr int   kNRed = 7;            // float64 partials per charger, see Red* below
 enum { RedP = 0, RedProfit, RedSatExp, RedPot, RedCharged, RedDischarged, RedSatSum };
 
@@ -90,6 +94,9 @@ struct Params {
     unsigned c_magic;        // ceil(2^32 / C): tid / C == __umulhi(tid, c_magic)
     unsigned p_magic;        // ceil(2^32 / P)
     int cs_uniform;          // all chargers identical: read the layout from cs0 (constant bank)
+    // byte offsets of the step kernel's shared-memory arrays (computed once on the host: ev2b_handle::layout_smem)
+    int o_resE, o_resA, o_resC, o_trov, o_trp, o_lossv, o_pfv, o_envs, o_whot, o_cnt, o_envi, o_wl, o_wcnt, o_pflag, o_pre;
+    int pre_stride;          // doubles per env in the prefetch area: kPreTr + 4 * Tr
     CsStatic cs0;
     // static
     const CsStatic *cs; const int *cs_tr; const int *port_cs; const int *tr_cs_off; const int *tr_cs_idx; const int *obs_slot;
@@ -148,6 +155,14 @@ __device__ __forceinline__ double lut_get(const double *lut, int lut_len, double
     return 1.0;
 }
 
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -167,12 +182,12 @@ __device__ __forceinline__ const CsStatic &cs_of(const Params &p, int c) {
 
 // ---- observation pieces shared by the step and reset kernels --------------------------------
 // Header of the stock state functions at observation time tq (= current_step after the increment).
-__device__ __forceinline__ void obs_header(const Params &p, float *row, int s, int tq, double prev_usage) {
+__device__ __forceinline__ void obs_header(const Params &p, float *row, int s, int tq, double prev_usage, double setpoint_tq) {
     if (p.state_kind == EV2B_STATE_V2G_GRID) {                      // state.py:247 (the rest of the header is static)
         row[5] = (float)prev_usage;
     } else if (p.state_kind == EV2B_STATE_PUBLIC_PST) {             // state.py:11-34
         row[0] = (float)((double)tq / (double)p.T);
-        row[1] = (tq < p.T) ? (float)p.env_t[(size_t)s * p.T + tq].setpoint : 0.f;
+        row[1] = (tq < p.T) ? (float)setpoint_tq : 0.f;        // power_setpoints[current_step]
         row[2] = (float)prev_usage;
     } else {                                                        // state.py:70-82, 113-125
         row[0] = (float)tq;
@@ -281,11 +296,17 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
         } else {
             const double pts = ts + (pilot - maxd) / maxd * (ts - 1.0);            // :312-314
             double nsoc;
-            if (soc < pts) {
-                if (1.0 <= (pts - soc) / pilot) nsoc = pilot + soc;                // :323-324
-                else nsoc = 1.0 + exp(__ldg(&sp->mult) * (pilot + soc - pts) / (pts - 1.0)) * (pts - 1.0);  // :326-330
+            if (soc < pts && 1.0 <= (pts - soc) / pilot) {
+                nsoc = pilot + soc;                                                // constant-current stage  :323-324
             } else {
-                nsoc = 1.0 + exp(__ldg(&sp->mult) * pilot / (pts - 1.0)) * (soc - 1.0);                     // :332-334
+                // the two constant-voltage expressions differ only in their operands; selecting the operands first lets
+                // the lanes of a warp share one exp / one division instead of running both branches in turn
+                //   soc <  pts: 1 + exp(mult * (pilot + soc - pts) / (pts - 1)) * (pts - 1)      :326-330
+                //   soc >= pts: 1 + exp(mult * pilot / (pts - 1)) * (soc - 1)                    :332-334
+                const bool below = soc < pts;
+                const double x = below ? pilot + soc - pts : pilot;
+                const double y = below ? pts - 1.0 : soc - 1.0;
+                nsoc = 1.0 + exp(__ldg(&sp->mult) * x / (pts - 1.0)) * y;
             }
             const double lim = (maxd > pilot) ? pilot : maxd;                      // :336-339
             curr = (nsoc - soc > lim) ? lim + soc : nsoc;                          // :341-344
@@ -418,20 +439,21 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     const int NT = blockDim.x;
     const int PP = p.EPB * p.P;
     double *red   = reinterpret_cast<double *>(smem_raw);                 // [kNRed][NT]
-    double *resE  = red + (size_t)kNRed * NT;                             // [PP] action in, energy out
-    double *resA  = resE + PP;                                            // [PP] actual amps out
-    double *resC  = resA + PP;                                            // [PP] battery level in/out (-1: EV inactive)
-    double *trov  = resC + PP;                                            // [EPB*Tr] overload per transformer
-    double *trp   = trov + (size_t)p.EPB * p.Tr;                          // [EPB*Tr] transformer power (grid: bus EV power)
-    double *lossv = trp + (size_t)p.EPB * p.Tr;                           // [EPB] voltage-band loss  reward.py:107-110
-    double2 *pfv  = reinterpret_cast<double2 *>(lossv + p.EPB + (p.EPB & 1));   // [EPB][3][n_bus] S, V, lambda
-    double *envs  = reinterpret_cast<double *>(pfv + (size_t)p.EPB * 3 * p.n_bus);   // [EPB][kNRed]
-    uint2  *whot  = reinterpret_cast<uint2 *>(envs + (size_t)p.EPB * kNRed);   // [PP] hot words z, w of work items
-    int    *cnt   = reinterpret_cast<int *>(whot + PP);                   // [NT] invalid | dep<<10 | arr<<20
-    int    *envi  = cnt + NT;                                             // [EPB][4] t, scn, cnt, flags
-    int    *wl    = envi + (size_t)p.EPB * 4;                             // [PP] work list (port_local)
-    int    *wcnt  = wl + PP;                                              // [1] (+3 pad)
-    signed char *pflag = reinterpret_cast<signed char *>(wcnt + 4);       // [PP] ragged path only
+    double *resE  = reinterpret_cast<double *>(smem_raw + p.o_resE);      // [PP] action in, energy out
+    double *resA  = reinterpret_cast<double *>(smem_raw + p.o_resA);      // [PP] actual amps out
+    double *resC  = reinterpret_cast<double *>(smem_raw + p.o_resC);      // [PP] battery level in/out (-1: EV inactive)
+    double *trov  = reinterpret_cast<double *>(smem_raw + p.o_trov);      // [EPB*Tr] overload per transformer
+    double *trp   = reinterpret_cast<double *>(smem_raw + p.o_trp);       // [EPB*Tr] transformer power (grid: bus EV power)
+    double *lossv = reinterpret_cast<double *>(smem_raw + p.o_lossv);     // [EPB] voltage-band loss  reward.py:107-110
+    double2 *pfv  = reinterpret_cast<double2 *>(smem_raw + p.o_pfv);      // [EPB][3][n_bus] S, V, lambda
+    double *envs  = reinterpret_cast<double *>(smem_raw + p.o_envs);      // [EPB][kNRed]
+    double *pre   = reinterpret_cast<double *>(smem_raw + p.o_pre);       // [EPB][pre_stride] prefetched per-env records
+    uint2  *whot  = reinterpret_cast<uint2 *>(smem_raw + p.o_whot);       // [PP] hot words z, w of work items
+    int    *cnt   = reinterpret_cast<int *>(smem_raw + p.o_cnt);          // [NT] invalid | dep<<10 | arr<<20
+    int    *envi  = reinterpret_cast<int *>(smem_raw + p.o_envi);         // [EPB][4] t, scn, cnt, flags
+    int    *wl    = reinterpret_cast<int *>(smem_raw + p.o_wl);           // [PP] work list (port_local)
+    int    *wcnt  = reinterpret_cast<int *>(smem_raw + p.o_wcnt);         // [1] (+3 pad)
+    signed char *pflag = reinterpret_cast<signed char *>(smem_raw + p.o_pflag);   // [PP] ragged path only
 
     const int tid = threadIdx.x;
     const int el = p.C == 1 ? tid : (int)__umulhi((unsigned)tid, p.c_magic);   // tid / C
@@ -458,6 +480,9 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     if (valid) {
         t = p.env_step[e];
         s = p.env_scn[e];
+        double *pe = pre + el * p.pre_stride;
+        for (int i = c; i <= kPrePot; i += p.C)                 // KPI sums and the potential of this step: need only e
+            cp_async8(pe + i, i < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + i : p.env_pot + e);
         if (NP > 0) {
             port0 = UNI ? c * NP : p.cs[c].port_off;
             const size_t pb = (size_t)e * p.P + port0;
@@ -465,7 +490,14 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             for (int j = 0; j < NP; ++j) { h[j] = p.hot[pb + j]; araw[j] = agent_action<ActT>(p, actions, pb + j, t); }
         }
         live = t < p.T;
-        if (live) { const EnvT et0 = p.env_t[(size_t)s * p.T + t]; pre_cp = et0.cp; pre_dp = et0.dp; }
+        if (live) {
+            const EnvT et0 = p.env_t[(size_t)s * p.T + t]; pre_cp = et0.cp; pre_dp = et0.dp;
+            for (int i = c; i < 2 + 2 * p.Tr; i += p.C) {        // setpoint[t], setpoint[t+1], TrT rows (two 16 B halves each)
+                if (i < 2) { if (t + i < p.T) cp_async8(pe + kPreSet + i, &p.env_t[(size_t)s * p.T + t + i].setpoint); }
+                else cp_async16(pe + kPreTr + 2 * (i - 2),
+                                reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * (i - 2));
+            }
+        }
         if (c == 0) { envi[el * 4 + 0] = t; envi[el * 4 + 1] = s; envi[el * 4 + 2] = 0; envi[el * 4 + 3] = 0; }
     }
     __syncthreads();
@@ -700,6 +732,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
     red[RedCharged * NT + tid] = rCh;      red[RedDischarged * NT + tid] = rDis;
     red[RedSatSum * NT + tid] = rSat;
     cnt[tid] = rCnt;
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- B: fixed-order reductions.  Three small warp jobs per env, every lane busy: lanes are split
@@ -713,7 +746,6 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             const int jt = envi[jel * 4 + 0];
             if (jt >= p.T) continue;
             if (kind == 0) {          // Transformer.step accumulation + overload   transformer.py:264-302
-                const int js = envi[jel * 4 + 1];
                 int nseg = 1;
                 while (nseg * 2 * p.Tr <= 32) nseg *= 2;
                 const int per = 32 / nseg;                              // transformers per pass
@@ -728,7 +760,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                     }
                     for (int o = nseg >> 1; o > 0; o >>= 1) sp_ += __shfl_xor_sync(0xffffffffu, sp_, o);
                     if (seg == 0 && k < p.Tr && lane / nseg < per) {
-                        const TrT tt = p.tr_t[((size_t)js * p.T + jt) * p.Tr + k];
+                        const double *tq4 = pre + jel * p.pre_stride + kPreTr + 4 * k;
+                        TrT tt; tt.infl = tq4[0]; tt.solar = tq4[1]; tt.maxp = tq4[2]; tt.minp = tq4[3];
                         const double ptot = (tt.infl + tt.solar) + sp_;
                         double ov = 0.0;
                         if (ptot > tt.maxp + 0.0001 || ptot < tt.minp - 0.0001) ov = fabs(ptot - tt.maxp);
@@ -791,13 +824,14 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             if (jt < p.T) {
                 const double *v = envs + tid * kNRed;
                 const int w = envi[tid * 4 + 2];
-                const EnvT et = p.env_t[(size_t)js * p.T + jt];
+                const double *pe = pre + tid * p.pre_stride;
+                EnvT et; et.setpoint = pe[kPreSet];
                 const double usage = v[RedP];                                  // current_power_usage[t]  ev2gym_env.py:375
                 costs = v[RedProfit];
                 double ovsum = 0.0;
                 for (int k = 0; k < p.Tr; ++k) ovsum += trov[tid * p.Tr + k];
                 if (p.reward_kind == EV2B_REWARD_SQ_TRACKING) {                // reward.py:11-12
-                    const double pot = p.env_pot[je];
+                    const double pot = pe[kPrePot];
                     const double m = et.setpoint < pot ? et.setpoint : pot;
                     reward = -((m - usage) * (m - usage));
                 } else if (p.reward_kind == EV2B_REWARD_PROFIT_TR_USER) {      // reward.py:36-44
@@ -809,26 +843,26 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 } else if (p.reward_kind == EV2B_REWARD_GRID_SIMPLE) {         // reward.py:114-121
                     reward = 1000.0 * lossv[tid];
                 }
-                double *kpi = p.env_kpi + (size_t)je * EV2B_KPI_COUNT;
-                kpi[EV2B_KPI_TOTAL_REWARD] += reward;
-                kpi[EV2B_KPI_TOTAL_PROFITS] += costs;
-                kpi[EV2B_KPI_ENERGY_CHARGED] += v[RedCharged];
-                kpi[EV2B_KPI_ENERGY_DISCHARGED] += v[RedDischarged];
-                kpi[EV2B_KPI_TR_OVERLOAD] += ovsum;
-                kpi[EV2B_KPI_EVS_SERVED] += (double)((w >> 10) & 1023);
-                kpi[EV2B_KPI_SAT_SUM] += v[RedSatSum];
+                double *kpi = p.env_kpi + (size_t)je * EV2B_KPI_COUNT;      // old sums come from the prefetch area
+                kpi[EV2B_KPI_TOTAL_REWARD] = pe[EV2B_KPI_TOTAL_REWARD] + reward;
+                kpi[EV2B_KPI_TOTAL_PROFITS] = pe[EV2B_KPI_TOTAL_PROFITS] + costs;
+                kpi[EV2B_KPI_ENERGY_CHARGED] = pe[EV2B_KPI_ENERGY_CHARGED] + v[RedCharged];
+                kpi[EV2B_KPI_ENERGY_DISCHARGED] = pe[EV2B_KPI_ENERGY_DISCHARGED] + v[RedDischarged];
+                kpi[EV2B_KPI_TR_OVERLOAD] = pe[EV2B_KPI_TR_OVERLOAD] + ovsum;
+                kpi[EV2B_KPI_EVS_SERVED] = pe[EV2B_KPI_EVS_SERVED] + (double)((w >> 10) & 1023);
+                kpi[EV2B_KPI_SAT_SUM] = pe[EV2B_KPI_SAT_SUM] + v[RedSatSum];
                 const double d = et.setpoint - usage;                          // utils.py:37-44
-                kpi[EV2B_KPI_TRACKING_ERROR] += d * d;
-                kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] += fabs(d);
-                if (usage > et.setpoint) kpi[EV2B_KPI_TRACKER_VIOLATION] += usage - et.setpoint;
-                kpi[EV2B_KPI_EVS_SPAWNED] += (double)((w >> 20) & 1023);
-                kpi[EV2B_KPI_INVALID_ACTIONS] += (double)(w & 1023);
-                kpi[EV2B_KPI_STEPS] += 1.0;
+                kpi[EV2B_KPI_TRACKING_ERROR] = pe[EV2B_KPI_TRACKING_ERROR] + d * d;
+                kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] = pe[EV2B_KPI_ENERGY_TRACKING_ERROR] + fabs(d);
+                if (usage > et.setpoint) kpi[EV2B_KPI_TRACKER_VIOLATION] = pe[EV2B_KPI_TRACKER_VIOLATION] + (usage - et.setpoint);
+                kpi[EV2B_KPI_EVS_SPAWNED] = pe[EV2B_KPI_EVS_SPAWNED] + (double)((w >> 20) & 1023);
+                kpi[EV2B_KPI_INVALID_ACTIONS] = pe[EV2B_KPI_INVALID_ACTIONS] + (double)(w & 1023);
+                kpi[EV2B_KPI_STEPS] = pe[EV2B_KPI_STEPS] + 1.0;
                 p.env_pot[je] = (jt + 1 < p.T) ? v[RedPot] : 0.0;              // ev2gym_env.py:424-426
                 p.env_usage[je] = usage;
                 p.env_step[je] = jt + 1;
                 if (jt + 1 >= p.T) status |= EV2B_ST_DONE;                     // ev2gym_env.py:460
-                if (want_obs) obs_header(p, p.out.obs + (size_t)je * p.D, js, jt + 1, usage);
+                if (want_obs) obs_header(p, p.out.obs + (size_t)je * p.D, js, jt + 1, usage, pe[kPreSetNext]);
             } else {
                 status |= EV2B_ST_DONE | EV2B_ST_WAS_DONE;                     // ev2gym_env.py:343
             }
@@ -894,7 +928,7 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
         float *row = obs0 + (size_t)e * p.D;
         for (int i = threadIdx.x; i < p.D; i += blockDim.x) row[i] = 0.f;   // no EV is connected at t = 0
         __syncthreads();
-        if (threadIdx.x == 0) obs_header(p, row, s, 0, 0.0);
+        if (threadIdx.x == 0) obs_header(p, row, s, 0, 0.0, p.env_t[(size_t)s * p.T].setpoint);
         for (int i = threadIdx.x; i < p.W; i += blockDim.x) row[p.series_off[i]] = obs_series_fetch(p, s, 0, i);
     }
     __syncthreads();
