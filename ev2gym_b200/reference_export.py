@@ -73,6 +73,37 @@ def _grid_series(env, T: int):
     return act, rea
 
 
+class _ReplayAsEnv:
+    """Presents an `EvCityReplay` (ev2gym/models/replay.py:10-182) under the attribute names `topology_from_env` /
+    `scenario_from_env` read -- the same objects `EV2Gym(load_from_replay_path=...)` hands to its loaders
+    (loaders.py:97-98, 235-236, 307-308, 389, 400-401)."""
+
+    def __init__(self, replay, config: dict):
+        if getattr(replay, "simulate_grid", False):
+            raise NotImplementedError("grid replays are not imported: PowerGrid.reset modifies load_data[0] in place "
+                                      "(grid.py:109-116), so a saved grid replay no longer holds the raw step-0 loads")
+        self.charging_stations, self.transformers = replay.charging_stations, replay.transformers
+        self.EVs_profiles = replay.EVs
+        self.charge_prices, self.discharge_prices = replay.charge_prices, replay.discharge_prices
+        self.power_setpoints = replay.power_setpoints
+        self.simulation_length, self.timescale = replay.sim_length, replay.timescale
+        self.sim_starting_date = self.sim_date = replay.sim_date
+        self.simulate_grid, self.grid = False, None
+        self.config = config
+        self.seed = None
+
+
+def topology_from_replay(replay, config: dict) -> Topology:
+    """Topology of a saved reference episode.  `config` is the YAML dict the reference would be constructed with
+    (ev2gym_env.py:64-65): the replay does not store `v2g_enabled` or the demand-response notification time."""
+    return topology_from_env(_ReplayAsEnv(replay, config))
+
+
+def scenario_from_replay(replay, config: dict) -> Scenario:
+    """Scenario of a saved reference episode: what `EV2Gym(load_from_replay_path=...)` would re-run."""
+    return scenario_from_env(_ReplayAsEnv(replay, config))
+
+
 def _lut_row(d: dict) -> Tuple[float, ...]:
     """`dict.get(k, 1)` for k = 0..100, the only keys `np.round(amps)` can hit within LUT_LEN
     (ev.py:287-288; the dict is dense over 0..100 after utils.py:282-288)."""

@@ -233,6 +233,10 @@ class ScenarioPack:
         return len(self.scenarios)
 
     def save(self, path: str) -> None:
+        np.savez_compressed(path, **self.to_dict())
+
+    def to_dict(self) -> Dict[str, np.ndarray]:
+        """Flat name -> array form of the whole pack (what `save` writes)."""
         d = dict(self.topo.to_dict())
         d["config_name"] = np.array(self.config_name)
         d["n_scenarios"] = np.array(len(self.scenarios))
@@ -250,7 +254,7 @@ class ScenarioPack:
             d["s_" + k] = np.concatenate([s.sessions[k] for s in sc])
         d["luts_c"] = np.concatenate([s.luts_c for s in sc]).reshape(-1, LUT_LEN)
         d["luts_d"] = np.concatenate([s.luts_d for s in sc]).reshape(-1, LUT_LEN)
-        np.savez_compressed(path, **d)
+        return d
 
     @classmethod
     def load(cls, path: str) -> "ScenarioPack":

@@ -100,3 +100,17 @@ def test_kpi_allreduce_gloo_world2():
     [p.join(60) for p in ps]
     for _, k in res:
         assert k["total_reward"] == float(sum(range(10))) and k["steps"] == 10.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ev2gym"), reason="needs the reference checkout (build container only)")
+def test_replay_pickle_import_round_trip():
+    """EvCityReplay import (ev2gym/models/replay.py): `scenario_from_replay` == exporting the env the reference builds
+    from the same pickle, and the oracle on it reproduces the reference's re-run bit for bit.  Runs the reference in a
+    subprocess (tools/make_golden.py --replay-check changes directory and imports the stubs)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "make_golden.py"), "--replay-check"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rewards bit-equal" in r.stdout

@@ -228,11 +228,66 @@ CASES = [
 ]
 
 
+def replay_check() -> int:
+    """Round trip of the reference's replay pickle (ev2gym/models/replay.py): save an episode, then
+    (a) let the reference re-load it (`load_from_replay_path`) and export that env, (b) import the pickle directly with
+    `scenario_from_replay`; both must give the same tensors, and the oracle fed with (b) must reproduce, bit for bit, the
+    rewards of the reference re-running the replay."""
+    import pickle
+    import shutil
+    from ev2gym_b200.reference_export import scenario_from_replay, topology_from_replay
+    from oracle.oracle import OracleEnv
+    ov = {"number_of_charging_stations": 6, "number_of_ports_per_cs": 2, "number_of_transformers": 2}
+    st, rw = PAIRS["V2GProfitPlusLoads"]
+    path = make_config("V2GProfitPlusLoads", ov)
+    cfg = yaml.safe_load(open(path))
+    tmp = tempfile.mkdtemp()
+    try:
+        env = EV2Gym(config_file=path, seed=21, save_replay=True, replay_save_path=tmp + "/",
+                     state_function=getattr(ref_state, st), reward_function=getattr(ref_reward, rw))
+        env.reset(seed=21)
+        rng = np.random.default_rng(3)
+        acts = [rng.uniform(-1, 1, env.number_of_ports) for _ in range(env.simulation_length)]
+        for t, a in enumerate(acts):
+            if t == env.simulation_length - 1:
+                os.chdir(tmp)                    # EvCityReplay.__init__ creates ./replay (replay.py:19-20)
+            env.step(a.copy())
+        os.chdir(REF)
+        files = [f for f in os.listdir(tmp) if f.endswith(".pkl")]
+        assert len(files) == 1, files
+        rp = os.path.join(tmp, files[0])
+        env2 = EV2Gym(config_file=path, seed=5, load_from_replay_path=rp,
+                      state_function=getattr(ref_state, st), reward_function=getattr(ref_reward, rw))
+        env2.reset()
+        topo_a, scn_a = topology_from_env(env2), scenario_from_env(env2)
+        replay = pickle.load(open(rp, "rb"))
+        topo_b, scn_b = topology_from_replay(replay, cfg), scenario_from_replay(replay, cfg)
+        da, db = ScenarioPack(topo_a, [scn_a], "a").to_dict(), ScenarioPack(topo_b, [scn_b], "b").to_dict()
+        bad = [k for k in da if k not in ("config_name",) and not k.endswith("meta") and
+               not np.array_equal(np.asarray(da[k]), np.asarray(db[k]), equal_nan=np.asarray(da[k]).dtype.kind == "f")]
+        assert not bad, bad
+        orc = OracleEnv(topo_b, scn_b, reward=rw, state=st)
+        orc.reset()
+        for t, a in enumerate(acts):
+            _, r, done, _, _ = env2.step(a.copy())
+            assert orc.step(a)["reward"] == float(r), t
+        assert done
+        print(f"replay check: {len(da)} tensors equal, {len(acts)} rewards bit-equal, sessions={scn_b.n_sessions}")
+        return 0
+    finally:
+        os.chdir(REF)
+        shutil.rmtree(tmp, ignore_errors=True)
+        os.unlink(path)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--replay-check", action="store_true", help="round-trip a reference replay pickle (no files written)")
     ap.add_argument("--packs", action="store_true", help="write the scenario banks used by bench.py")
     ap.add_argument("--only", default=None)
     args = ap.parse_args()
+    if args.replay_check:
+        sys.exit(replay_check())
     if args.packs:
         out_dir = os.path.join(REPO, "ev2gym_b200", "data")
         os.makedirs(out_dir, exist_ok=True)

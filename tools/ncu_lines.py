@@ -30,9 +30,9 @@ def main():
             continue
         if not on:
             continue
-        m = re.search(r'//## File ".*?", line (\d+)', ln)
+        m = re.search(r'//## File "(.*?)", line (\d+)', ln)
         if m:
-            cur = int(m.group(1))
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
         if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
             lines.append(cur)
@@ -48,13 +48,17 @@ def main():
     inst, smp, thr = collections.Counter(), collections.Counter(), collections.Counter()
     for r, l in zip(body, lines):
         inst[l] += int(r[ci] or 0); smp[l] += int(r[si] or 0); thr[l] += int(r[ti] or 0)
-    src = open(os.path.join(os.path.dirname(os.path.abspath(so)), "ev2b_device.cuh")).read().splitlines()
+    srcdir = os.path.dirname(os.path.abspath(so))
+    srcs = {f: open(os.path.join(srcdir, f)).read().splitlines() for f in ("ev2b_device.cuh", "ev2b_math.h", "ev2b.cu")
+            if os.path.exists(os.path.join(srcdir, f))}
     ti_, ts_ = sum(inst.values()), sum(smp.values())
     print(f"total warp-instructions {ti_}, stall samples {ts_}")
-    print("  line   inst%  smp%  thr/inst  source")
+    print("  file:line               inst%  smp%  thr/inst  source")
     for l, n in inst.most_common(top):
-        text = src[l - 1].strip()[:95] if l and l <= len(src) else "?"
-        print(f"{l!s:>6} {100 * n / ti_:6.2f} {100 * smp[l] / max(ts_, 1):5.1f} {thr[l] / max(n, 1):8.1f}  {text}")
+        f, no = l if l else ("?", 0)
+        src = srcs.get(f)
+        text = src[no - 1].strip()[:90] if src and 0 < no <= len(src) else "(CUDA header)"
+        print(f"{f[:16] + ':' + str(no):>22} {100 * n / ti_:6.2f} {100 * smp[l] / max(ts_, 1):5.1f} {thr[l] / max(n, 1):8.1f}  {text}")
 
 
 if __name__ == "__main__":
