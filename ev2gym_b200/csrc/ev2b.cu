@@ -188,7 +188,8 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
         if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, false>);          \
         return go(step_kernel<ActT, 0, false, MAXT, MINB, false>);                      \
     } while (0)
-    const bool stats = (h->dims.flags & EV2B_F_STATS) != 0 || h->n_bus > 0;   // the HEAVY instantiation
+    const bool stats = (h->dims.flags & EV2B_F_STATS) != 0 || h->n_bus > 0 ||   // the HEAVY instantiation
+                       h->dims.reward_kind >= EV2B_REWARD_SQTR_TR_USER;
 #ifndef EV2B_MINB128
 #define EV2B_MINB128 8
 #endif
@@ -273,7 +274,11 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         }
         h->n_bus = tp->n_bus; h->s_base = tp->grid_s_base;
     }
+    if (d->reward_kind < EV2B_REWARD_NONE || d->reward_kind > EV2B_REWARD_PST_PROFITMAX_V2) {
+        delete h; g_create_error = "ev2b_create: unknown reward kind"; return EV2B_E_ARG;
+    }
     if ((d->reward_kind == EV2B_REWARD_GRID_FULL || d->reward_kind == EV2B_REWARD_GRID_SIMPLE ||
+         d->reward_kind == EV2B_REWARD_GRID_PROFITMAX_V2 ||
          d->state_kind == EV2B_STATE_V2G_GRID) && h->n_bus == 0) {
         delete h; g_create_error = "ev2b_create: grid reward/state functions need a grid (n_bus > 0)"; return EV2B_E_ARG;
     }

@@ -660,7 +660,11 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                 const double sat = (cv < des - 0.001) ? cv / des : 1.0;
                 if (p.reward_kind == EV2B_REWARD_GRID_FULL || p.reward_kind == EV2B_REWARD_GRID_SIMPLE)
                     rSatExp += (cv - des) * (cv - des);                   // -user_costs  reward.py:99-102
-                else
+                else if (HEAVY && p.reward_kind >= EV2B_REWARD_SQTR_TR_USER) {   // per-departure penalty of the other stock rewards
+                    if (p.reward_kind == EV2B_REWARD_SQTR_TR_USER) rSatExp += 1000.0 * (1.0 - sat);                // reward.py:29-30
+                    else if (p.reward_kind == EV2B_REWARD_V2G_PROFITMAX) { if (des > cv) rSatExp += 100.0 * (des - cv); }   // :136-138
+                    else if (p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX_V2) { if (des > cv) rSatExp += 0.05 * ((des - cv) * (des - cv)); }   // :199-207
+                } else
                     rSatExp += 100.0 * exp(-10.0 * sat);                  // reward.py:42,85
                 rSat += sat;
                 rCnt += 1 << 10;
@@ -697,6 +701,15 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
             if (occ_after) {
                 const EvSpec *sp = p.spec + hot_spec(hj);
                 const double B = __ldg(&sp->B);
+                if (HEAVY && p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX_V2) {   // V2G_profitmaxV2 family: EVs that can no longer
+                    const double des = __ldg(&sp->desired), pmax = __ldg(&sp->pmax_ac);   // reach their desired level  reward.py:172-190
+                    const double min_steps = (des - cv) / (pmax / p.c60);
+                    const int dstep = hot_t_dep(hj) - tq;
+                    if (min_steps > (double)dstep) {
+                        const double gap = (des - ((double)(dstep + 1) * pmax / p.c60)) - cv;
+                        rSatExp += 0.05 * (gap * gap);
+                    }
+                }
                 // charge power potential for step t+1            utils.py:766-777
                 if (cv < B && hot_t_dep(hj) > tq) rPot += __ldg(&p.pot_kw[hot_spec(hj) * p.n_cls + cs.cls]);
                 if (want_obs) {       // observation tuple (transformer-major slot)   state.py:37-57, 85-102, 137-151
@@ -842,6 +855,22 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
                     reward = costs + 1000.0 * lossv[tid] - v[RedSatExp];
                 } else if (p.reward_kind == EV2B_REWARD_GRID_SIMPLE) {         // reward.py:114-121
                     reward = 1000.0 * lossv[tid];
+                } else if (HEAVY && p.reward_kind == EV2B_REWARD_SQTR_TR_USER) {   // reward.py:16-32
+                    double m = et.setpoint < pe[kPrePot] ? et.setpoint : pe[kPrePot];
+                    const double lim = pe[kPreTr + 2];                         // transformers[0].max_power[t]
+                    if (lim < m) m = lim;
+                    reward = -((m - usage) * (m - usage)) - 100.0 * ovsum - v[RedSatExp];
+                } else if (HEAVY && p.reward_kind == EV2B_REWARD_SIMPLE) {         // reward.py:60-65
+                    reward = -((et.setpoint - usage) * (et.setpoint - usage));
+                } else if (HEAVY && p.reward_kind == EV2B_REWARD_MIN_TRACKER_SURPLUS) {   // reward.py:67-76
+                    if (et.setpoint < usage) reward -= (usage - et.setpoint) * (usage - et.setpoint);
+                    reward += usage;
+                } else if (HEAVY && p.reward_kind == EV2B_REWARD_V2G_COSTS_SIMPLE) {   // reward.py:150-153
+                    reward = costs;
+                } else if (HEAVY && p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX) {      // V2G_profitmax, V2G_profitmaxV2 (+ grid / pst)
+                    reward = costs - v[RedSatExp];
+                    if (p.reward_kind == EV2B_REWARD_GRID_PROFITMAX_V2) reward += 50000.0 * lossv[tid];       // reward.py:274-279
+                    if (p.reward_kind == EV2B_REWARD_PST_PROFITMAX_V2 && et.setpoint < usage) reward += 1000.0 * (et.setpoint - usage);   // :333-339
                 }
                 double *kpi = p.env_kpi + (size_t)je * EV2B_KPI_COUNT;      // old sums come from the prefetch area
                 kpi[EV2B_KPI_TOTAL_REWARD] = pe[EV2B_KPI_TOTAL_REWARD] + reward;

@@ -36,7 +36,16 @@ enum ev2b_reward_kind {
     EV2B_REWARD_PROFIT_TR_USER = 2,       /* ProfitMax_TrPenalty_UserIncentives    reward.py:34-44  */
     EV2B_REWARD_PROFIT_MAX = 3,           /* profit_maximization                   reward.py:78-87  */
     EV2B_REWARD_GRID_FULL = 4,            /* V2G_grid_full_reward   (needs a grid) reward.py:89-111 */
-    EV2B_REWARD_GRID_SIMPLE = 5           /* V2G_grid_simple_reward (needs a grid) reward.py:114-121 */
+    EV2B_REWARD_GRID_SIMPLE = 5,          /* V2G_grid_simple_reward (needs a grid) reward.py:114-121 */
+    /* the remaining stock rewards run in the kernel's full-featured instantiation (same as statistics mode) */
+    EV2B_REWARD_SQTR_TR_USER = 6,         /* SqTrError_TrPenalty_UserIncentives    reward.py:16-32   */
+    EV2B_REWARD_SIMPLE = 7,               /* SimpleReward                          reward.py:60-65   */
+    EV2B_REWARD_MIN_TRACKER_SURPLUS = 8,  /* MinimizeTrackerSurplusWithChargeRewards reward.py:67-76 */
+    EV2B_REWARD_V2G_PROFITMAX = 9,        /* V2G_profitmax                         reward.py:123-148 */
+    EV2B_REWARD_V2G_COSTS_SIMPLE = 10,    /* V2G_costs_simple                      reward.py:150-153 */
+    EV2B_REWARD_V2G_PROFITMAX_V2 = 11,    /* V2G_profitmaxV2                       reward.py:155-213 */
+    EV2B_REWARD_GRID_PROFITMAX_V2 = 12,   /* Grid_V2G_profitmaxV2 (needs a grid)   reward.py:215-279 */
+    EV2B_REWARD_PST_PROFITMAX_V2 = 13     /* pst_V2G_profitmaxV2                   reward.py:281-339 */
 };
 enum ev2b_state_kind {
     EV2B_STATE_NONE = 0,

@@ -330,6 +330,8 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
     int total_invalid = 0, n_departed = 0, n_arrived = 0;
     double sat_exp_sum = 0;      /* sum over departing EVs of exp(-10*score)  reward.py:41-42,83-85 */
     double user_costs = 0, loss_v = 0;
+    double dep_score[P > 0 ? P : 1], dep_capv[P > 0 ? P : 1], dep_des[P > 0 ? P : 1];   /* env.departing_evs of this step, in order */
+    int n_dep_rec = 0;
     double tr_power[Tr > 0 ? Tr : 1], tr_amps[Tr > 0 ? Tr : 1];
     double act[P > 0 ? P : 1];
     memcpy(act, actions_in, sizeof(double) * P);
@@ -422,6 +424,7 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
                 st->cs_total_sat[c] += sat;
                 sat_exp_sum += 100.0 * exp(-10.0 * sat);
                 user_costs += -py_sq(capn - des);                        /* reward.py:99-102 */
+                dep_score[n_dep_rec] = sat; dep_capv[n_dep_rec] = capn; dep_des[n_dep_rec] = des; n_dep_rec++;   /* env.departing_evs order */
                 if (out->dep_sat) out->dep_sat[p] = sat;
                 n_departed++;
             }
@@ -561,6 +564,52 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
     } break;
     case EV2O_REWARD_GRID_FULL:   reward = total_costs + 1000.0 * loss_v + user_costs; break;   /* reward.py:89-111 */
     case EV2O_REWARD_GRID_SIMPLE: reward = 1000.0 * loss_v; break;                              /* reward.py:114-121 */
+    case EV2O_REWARD_SQTR_TR_USER: {                                 /* reward.py:16-32 */
+        double m = sc->setpoint[tm1];
+        if (st->potential[tm1] < m) m = st->potential[tm1];
+        if (sc->tr_max_power[tm1] < m) m = sc->tr_max_power[tm1];   /* transformers[0].max_power[t] */
+        reward = -py_sq(m - st->usage[tm1]);
+        for (int k = 0; k < Tr; ++k) reward -= 100.0 * st->tr_overload_hist[(size_t)k * T + tm1];
+        for (int i = 0; i < n_dep_rec; ++i) reward -= 1000.0 * (1.0 - dep_score[i]);
+    } break;
+    case EV2O_REWARD_SIMPLE:                                         /* reward.py:60-65 */
+        reward = -py_sq(sc->setpoint[tm1] - st->usage[tm1]);
+        break;
+    case EV2O_REWARD_MIN_TRACKER_SURPLUS:                            /* reward.py:67-76 */
+        reward = 0;
+        if (sc->setpoint[tm1] < st->usage[tm1]) reward -= py_sq(st->usage[tm1] - sc->setpoint[tm1]);
+        reward += st->usage[tm1];
+        break;
+    case EV2O_REWARD_V2G_PROFITMAX: {                                /* reward.py:123-148 */
+        double uc = 0;
+        for (int i = 0; i < n_dep_rec; ++i) if (dep_des[i] > dep_capv[i]) uc += -100.0 * (dep_des[i] - dep_capv[i]);
+        reward = total_costs + uc;
+    } break;
+    case EV2O_REWARD_V2G_COSTS_SIMPLE: reward = total_costs; break;  /* reward.py:150-153 */
+    case EV2O_REWARD_V2G_PROFITMAX_V2: case EV2O_REWARD_GRID_PROFITMAX_V2: case EV2O_REWARD_PST_PROFITMAX_V2: {
+        /* reward.py:155-213 (and the grid / pst variants :215-339): EVs that can no longer reach their desired level */
+        double uc = 0;
+        const double mult = 0.05, per_hour = 60.0 / (double)tp->timescale;
+        for (int p = 0; p < P; ++p) {                                /* connected EVs, incl. the ones that just arrived */
+            const int s = st->port_session[p];
+            if (s < 0) continue;
+            const double des = sc->s_desired[s], capn = st->port_cap[p], pmax = sc->s_pmax_ac[s];
+            const double min_steps = (des - capn) / (pmax / per_hour);
+            const int departing_step = sc->s_t_dep[s] - st->current_step;
+            if (min_steps > (double)departing_step) {
+                const double min_cap = des - ((double)(departing_step + 1) * pmax / per_hour);
+                uc += -(mult * py_sq(min_cap - capn));
+            }
+        }
+        for (int i = 0; i < n_dep_rec; ++i)
+            if (dep_des[i] > dep_capv[i]) uc += -mult * py_sq(dep_des[i] - dep_capv[i]);
+        if (reward_kind == EV2O_REWARD_GRID_PROFITMAX_V2) reward = total_costs + uc + 50000.0 * loss_v;
+        else if (reward_kind == EV2O_REWARD_PST_PROFITMAX_V2) {
+            double viol = 0;
+            if (sc->setpoint[tm1] < st->usage[tm1]) viol += sc->setpoint[tm1] - st->usage[tm1];
+            reward = total_costs + uc + 1000.0 * viol;
+        } else reward = total_costs + uc;
+    } break;
     default: reward = 0;
     }
     (void)overload_sum;

@@ -34,7 +34,15 @@ extern "C" {
 #endif
 
 enum { EV2O_REWARD_NONE = 0, EV2O_REWARD_SQ_TRACKING = 1, EV2O_REWARD_PROFIT_TR_USER = 2,
-       EV2O_REWARD_PROFIT_MAX = 3, EV2O_REWARD_GRID_FULL = 4, EV2O_REWARD_GRID_SIMPLE = 5 };
+       EV2O_REWARD_PROFIT_MAX = 3, EV2O_REWARD_GRID_FULL = 4, EV2O_REWARD_GRID_SIMPLE = 5,
+       EV2O_REWARD_SQTR_TR_USER = 6,       /* SqTrError_TrPenalty_UserIncentives       reward.py:16-32   */
+       EV2O_REWARD_SIMPLE = 7,             /* SimpleReward                             reward.py:60-65   */
+       EV2O_REWARD_MIN_TRACKER_SURPLUS = 8,/* MinimizeTrackerSurplusWithChargeRewards  reward.py:67-76   */
+       EV2O_REWARD_V2G_PROFITMAX = 9,      /* V2G_profitmax                            reward.py:123-148 */
+       EV2O_REWARD_V2G_COSTS_SIMPLE = 10,  /* V2G_costs_simple                         reward.py:150-153 */
+       EV2O_REWARD_V2G_PROFITMAX_V2 = 11,  /* V2G_profitmaxV2                          reward.py:155-213 */
+       EV2O_REWARD_GRID_PROFITMAX_V2 = 12, /* Grid_V2G_profitmaxV2                     reward.py:215-279 */
+       EV2O_REWARD_PST_PROFITMAX_V2 = 13   /* pst_V2G_profitmaxV2                      reward.py:281-339 */ };
 enum { EV2O_STATE_NONE = 0, EV2O_STATE_PUBLIC_PST = 1, EV2O_STATE_V2G_PROFIT_MAX = 2,
        EV2O_STATE_V2G_PROFIT_MAX_LOADS = 3, EV2O_STATE_V2G_GRID = 4 };
 

@@ -223,6 +223,21 @@ CASES = [
     ("pst25_calap_s6", "PublicPST", {"number_of_charging_stations": 25}, 6, "calap"),
     ("loads_c10n2_calap_s13", "V2GProfitPlusLoads",
      {"number_of_charging_stations": 10, "number_of_ports_per_cs": 2, "number_of_transformers": 2}, 13, "calap"),
+    # the remaining stock reward functions (reward.py), one episode each
+    ("pst25_sqtr_s14", "PublicPST", {"number_of_charging_stations": 25, "_reward": "SqTrError_TrPenalty_UserIncentives"},
+     14, "uniform"),
+    ("pst10_simple_s15", "PublicPST", {"number_of_charging_stations": 10, "_reward": "SimpleReward"}, 15, "uniform"),
+    ("pst10_mintracker_s16", "PublicPST",
+     {"number_of_charging_stations": 10, "_reward": "MinimizeTrackerSurplusWithChargeRewards"}, 16, "uniform"),
+    ("profitmax_c12_v2gprofitmax_s17", "V2GProfitMax", {"number_of_charging_stations": 12, "_reward": "V2G_profitmax"},
+     17, "mixed"),
+    ("profitmax_c8_costs_s18", "V2GProfitMax", {"number_of_charging_stations": 8, "_reward": "V2G_costs_simple"}, 18, "mixed"),
+    ("loads_c12n2tr2_v2_s19", "V2GProfitPlusLoads",
+     {"number_of_charging_stations": 12, "number_of_ports_per_cs": 2, "number_of_transformers": 2,
+      "_reward": "V2G_profitmaxV2"}, 19, "mixed"),
+    ("grid_c16_v2_s20", "V2Ggrid", {"number_of_charging_stations": 16, "_reward": "Grid_V2G_profitmaxV2"}, 20, "mixed"),
+    ("pst8n2_pstv2_s21", "PublicPST", {"number_of_charging_stations": 8, "number_of_ports_per_cs": 2, "v2g_enabled": True,
+                                       "_reward": "pst_V2G_profitmaxV2"}, 21, "mixed"),
     ("ts10_c5_uniform_s10", "V2GProfitMax", {"number_of_charging_stations": 5, "timescale": 10,
                                              "simulation_length": 150}, 10, "uniform"),
 ]
