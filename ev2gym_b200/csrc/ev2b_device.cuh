@@ -434,7 +434,7 @@ __device__ __forceinline__ double power_flow_env(const Params &p, double2 *S, co
 // ---- the fused step kernel --------------------------------------------------------------------
 // ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = ragged (CsStatic).
 template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool HEAVY>   // HEAVY: statistics mode and/or distribution grid compiled in
-__global__ void __launch_bounds__(MAXT, MINB) step_kernel(const Params p) {
+__global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant__ Params p) {   // __grid_constant__: &p may be passed to finalize_ev without a per-thread copy
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
     const int PP = p.EPB * p.P;
