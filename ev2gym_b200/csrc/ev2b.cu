@@ -180,19 +180,27 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
 #define EV2B_DISPATCH(MAXT, MINB)                                                       \
     do {                                                                                \
         if (stats) {                                                                    \
-            if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB, true>);       \
-            if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, true>);       \
-            return go(step_kernel<ActT, 0, false, MAXT, MINB, true>);                   \
+            if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB, true, true>);  \
+            if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, true, true>);  \
+            return go(step_kernel<ActT, 0, false, MAXT, MINB, true, true>);              \
         }                                                                               \
-        if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB, false>);          \
-        if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, false>);          \
-        return go(step_kernel<ActT, 0, false, MAXT, MINB, false>);                      \
+        if (opt) {                                                                      \
+            if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB, false, true>); \
+            if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, false, true>); \
+            return go(step_kernel<ActT, 0, false, MAXT, MINB, false, true>);             \
+        }                                                                               \
+        if (np == 1) return go(step_kernel<ActT, 1, true, MAXT, MINB, false, false>);   \
+        if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, false, false>);   \
+        return go(step_kernel<ActT, 0, false, MAXT, MINB, false, false>);               \
     } while (0)
     const bool stats = (h->dims.flags & EV2B_F_STATS) != 0 || h->n_bus > 0 ||   // the HEAVY instantiation
                        h->dims.reward_kind >= EV2B_REWARD_SQTR_TR_USER;
 #ifndef EV2B_MINB128
 #define EV2B_MINB128 8
 #endif
+    const ev2b_step_out &o = p.out;    // any optional output requested?  (reward / status / obs are always compiled in)
+    const bool opt = o.cs_power || o.cs_current || o.tr_power || o.tr_overload || o.total_costs || o.action_mask ||
+                     o.dep_sat || o.dep_cap || o.port_energy || o.node_voltage;
     if (h->block <= 128) EV2B_DISPATCH(128, EV2B_MINB128);
     if (h->block <= 256) EV2B_DISPATCH(256, EV2B_MINB);
     if (h->block <= 512) EV2B_DISPATCH(512, 2);

@@ -28,10 +28,9 @@
 
 namespace ev2b {
 
-#ifndef EV2B_LEAN
-#define EV2B_LEAN 0
-#endif
-#define EV2B_OPT(ptr) (!EV2B_LEAN && (ptr))
+// optional per-step outputs (everything but reward / status / obs): the OPTOUT = false instantiation of the step kernel,
+// launched when the caller asked for none of them, has no code for them at all
+#define EV2B_OPT(ptr) (OPTOUT && (ptr))
 
 constexpr int   kNoArrival = 32767;   // "no (further) session on this port"
 constexpr int   kMaxThreads = 1024;
@@ -433,7 +432,7 @@ __device__ __forceinline__ double power_flow_env(const Params &p, double2 *S, co
 
 // ---- the fused step kernel --------------------------------------------------------------------
 // ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = ragged (CsStatic).
-template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool HEAVY>   // HEAVY: statistics mode and/or distribution grid compiled in
+template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool HEAVY, bool OPTOUT>   // HEAVY: statistics mode and/or distribution grid compiled in
 __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant__ Params p) {   // __grid_constant__: &p may be passed to finalize_ev without a per-thread copy
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x;
@@ -692,7 +691,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                 if (HEAVY && p.stats) { p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0; }
             }
             const bool occ_after = hot_t_arr(hj) <= tq && tq <= hot_t_dep(hj);
-            if (p.out.action_mask) p.out.action_mask[ip] = occ_after ? 1 : 0;          // ev2gym_env.py:452-457
+            if (EV2B_OPT(p.out.action_mask)) p.out.action_mask[ip] = occ_after ? 1 : 0;          // ev2gym_env.py:452-457
             if (HEAVY && p.stats && occ_after && tq >= p.T) {   // episode over: EVs still connected count too (env.EVs)
                 const SessRec r0 = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj) - 1];
                 finalize_ev(p, ip, (int)((size_t)e * p.C + c), p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj),
