@@ -65,7 +65,7 @@ struct ev2b_handle {
     DevBuf<double> luts_c, luts_d, pot_kw; DevBuf<float> trA, trF, tr_limit, obs_static; DevBuf<DrEv> dr; DevBuf<uint8_t> dr_count;
     // device: state
     DevBuf<uint4> hot; DevBuf<double> cap; DevBuf<float> exch; DevBuf<int> env_step, env_scn;
-    DevBuf<double> env_pot, env_usage, env_kpi;
+    DevBuf<double> env_pot, env_usage, env_kpi, env_pot_prev;
     // device: statistics mode
     int L = 1;
     DevBuf<double> st_soc_sum, st_abs_e, st_act, st_r, cs_sat_sum, cs_dcal, cs_dcyc;
@@ -139,7 +139,7 @@ struct ev2b_handle {
         p.env_t = env_t.p; p.tr_t = tr_t.p; p.sess = sess.p; p.spec = spec.p; p.luts_c = luts_c.p; p.luts_d = luts_d.p;
         p.pot_kw = pot_kw.p; p.trA = trA.p; p.trF = trF.p; p.tr_limit = tr_limit.p; p.dr = dr.p; p.dr_count = dr_count.p;
         p.hot = hot.p; p.cap = cap.p; p.exch = exch.p; p.env_step = env_step.p; p.env_scn = env_scn.p;
-        p.env_pot = env_pot.p; p.env_usage = env_usage.p; p.env_kpi = env_kpi.p;
+        p.env_pot = env_pot.p; p.env_usage = env_usage.p; p.env_kpi = env_kpi.p; p.env_pot_prev = env_pot_prev.p;
         p.rr_key = rr_key.p; p.rr_fb = rr_fb.p; p.rr_avg_power = rr_avg_power; p.rr_share = rr_share;
         return p;
     }
@@ -282,7 +282,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         }
         h->n_bus = tp->n_bus; h->s_base = tp->grid_s_base;
     }
-    if (d->reward_kind < EV2B_REWARD_NONE || d->reward_kind > EV2B_REWARD_PST_PROFITMAX_V2) {
+    if (d->reward_kind < EV2B_REWARD_NONE || d->reward_kind > EV2B_REWARD_SQ_TRACKING_PENALTY) {
         delete h; g_create_error = "ev2b_create: unknown reward kind"; return EV2B_E_ARG;
     }
     if ((d->reward_kind == EV2B_REWARD_GRID_FULL || d->reward_kind == EV2B_REWARD_GRID_SIMPLE ||
@@ -374,7 +374,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     const size_t EP = (size_t)h->E * h->P;
     CREATE_TRY(h->hot.alloc(EP)); CREATE_TRY(h->cap.alloc(EP)); CREATE_TRY(h->exch.alloc(EP));
     CREATE_TRY(h->env_step.alloc(h->E)); CREATE_TRY(h->env_scn.alloc(h->E));
-    CREATE_TRY(h->env_pot.alloc(h->E)); CREATE_TRY(h->env_usage.alloc(h->E));
+    CREATE_TRY(h->env_pot.alloc(h->E)); CREATE_TRY(h->env_usage.alloc(h->E)); CREATE_TRY(h->env_pot_prev.alloc(h->E));
     CREATE_TRY(h->env_kpi.alloc((size_t)h->E * EV2B_KPI_COUNT));
     CREATE_TRY(cudaMemset(h->hot.p, 0, EP * sizeof(uint4)));
     CREATE_TRY(cudaMemset(h->cap.p, 0, EP * sizeof(double)));

@@ -122,6 +122,7 @@ struct Params {
     double rr_avg_power, rr_share;   // heuristics.py:19-23 ; 1 / number_of_ports_per_cs
     // state
     uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;
+    double *env_pot_prev;      // charge_power_potential[t-1], kept only for SquaredTrackingErrorRewardWithPenalty (reward.py:50)
     double *env_kpi;
     // io
     const void *actions;
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                 else if (HEAVY && p.reward_kind >= EV2B_REWARD_SQTR_TR_USER) {   // per-departure penalty of the other stock rewards
                     if (p.reward_kind == EV2B_REWARD_SQTR_TR_USER) rSatExp += 1000.0 * (1.0 - sat);                // reward.py:29-30
                     else if (p.reward_kind == EV2B_REWARD_V2G_PROFITMAX) { if (des > cv) rSatExp += 100.0 * (des - cv); }   // :136-138
-                    else if (p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX_V2) { if (des > cv) rSatExp += 0.05 * ((des - cv) * (des - cv)); }   // :199-207
+                    else if (p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX_V2 && p.reward_kind <= EV2B_REWARD_PST_PROFITMAX_V2) { if (des > cv) rSatExp += 0.05 * ((des - cv) * (des - cv)); }   // :199-207
                 } else
                     rSatExp += 100.0 * exp(-10.0 * sat);                  // reward.py:42,85
                 rSat += sat;
@@ -700,7 +701,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
             if (occ_after) {
                 const EvSpec *sp = p.spec + hot_spec(hj);
                 const double B = __ldg(&sp->B);
-                if (HEAVY && p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX_V2) {   // V2G_profitmaxV2 family: EVs that can no longer
+                if (HEAVY && p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX_V2 && p.reward_kind <= EV2B_REWARD_PST_PROFITMAX_V2) {   // V2G_profitmaxV2 family: EVs that can no longer
                     const double des = __ldg(&sp->desired), pmax = __ldg(&sp->pmax_ac);   // reach their desired level  reward.py:172-190
                     const double min_steps = (des - cv) / (pmax / p.c60);
                     const int dstep = hot_t_dep(hj) - tq;
@@ -859,6 +860,12 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                     const double lim = pe[kPreTr + 2];                         // transformers[0].max_power[t]
                     if (lim < m) m = lim;
                     reward = -((m - usage) * (m - usage)) - 100.0 * ovsum - v[RedSatExp];
+                } else if (HEAVY && p.reward_kind == EV2B_REWARD_SQ_TRACKING_PENALTY) {   // reward.py:46-58
+                    const double pot = pe[kPrePot];
+                    const double m = et.setpoint < pot ? et.setpoint : pot;
+                    reward = -((m - usage) * (m - usage));
+                    if (usage == 0.0 && p.env_pot_prev[je] != 0.0) reward = reward - 100.0;   // potential[current_step-2]; 0 at t = 0
+                    p.env_pot_prev[je] = pot;
                 } else if (HEAVY && p.reward_kind == EV2B_REWARD_SIMPLE) {         // reward.py:60-65
                     reward = -((et.setpoint - usage) * (et.setpoint - usage));
                 } else if (HEAVY && p.reward_kind == EV2B_REWARD_MIN_TRACKER_SURPLUS) {   // reward.py:67-76
@@ -866,7 +873,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                     reward += usage;
                 } else if (HEAVY && p.reward_kind == EV2B_REWARD_V2G_COSTS_SIMPLE) {   // reward.py:150-153
                     reward = costs;
-                } else if (HEAVY && p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX) {      // V2G_profitmax, V2G_profitmaxV2 (+ grid / pst)
+                } else if (HEAVY && p.reward_kind >= EV2B_REWARD_V2G_PROFITMAX && p.reward_kind <= EV2B_REWARD_PST_PROFITMAX_V2) {   // V2G_profitmax, V2G_profitmaxV2 (+ grid / pst)
                     reward = costs - v[RedSatExp];
                     if (p.reward_kind == EV2B_REWARD_GRID_PROFITMAX_V2) reward += 50000.0 * lossv[tid];       // reward.py:274-279
                     if (p.reward_kind == EV2B_REWARD_PST_PROFITMAX_V2 && et.setpoint < usage) reward += 1000.0 * (et.setpoint - usage);   // :333-339
@@ -961,7 +968,7 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        p.env_step[e] = 0; p.env_scn[e] = s; p.env_pot[e] = 0.0; p.env_usage[e] = 0.0;
+        p.env_step[e] = 0; p.env_scn[e] = s; p.env_pot[e] = 0.0; p.env_usage[e] = 0.0; p.env_pot_prev[e] = 0.0;
         for (int k = 0; k < EV2B_KPI_COUNT; ++k) p.env_kpi[(size_t)e * EV2B_KPI_COUNT + k] = 0.0;
     }
     if (p.stats)

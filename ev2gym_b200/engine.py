@@ -18,7 +18,8 @@ REWARD_KINDS = {None: 0, "none": 0, "SquaredTrackingErrorReward": 1,
                 "ProfitMax_TrPenalty_UserIncentives": 2, "profit_maximization": 3, "V2G_grid_full_reward": 4,
                 "V2G_grid_simple_reward": 5, "SqTrError_TrPenalty_UserIncentives": 6, "SimpleReward": 7,
                 "MinimizeTrackerSurplusWithChargeRewards": 8, "V2G_profitmax": 9, "V2G_costs_simple": 10,
-                "V2G_profitmaxV2": 11, "Grid_V2G_profitmaxV2": 12, "pst_V2G_profitmaxV2": 13}
+                "V2G_profitmaxV2": 11, "Grid_V2G_profitmaxV2": 12, "pst_V2G_profitmaxV2": 13,
+                "SquaredTrackingErrorRewardWithPenalty": 14}
 STATE_KINDS = {None: 0, "none": 0, "PublicPST": 1, "V2G_profit_max": 2, "V2G_profit_max_loads": 3, "V2G_grid_state": 4}
 
 ST_DONE, ST_AMPS_OVERFLOW, ST_WAS_DONE = 1, 2, 4

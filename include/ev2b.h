@@ -45,7 +45,8 @@ enum ev2b_reward_kind {
     EV2B_REWARD_V2G_COSTS_SIMPLE = 10,    /* V2G_costs_simple                      reward.py:150-153 */
     EV2B_REWARD_V2G_PROFITMAX_V2 = 11,    /* V2G_profitmaxV2                       reward.py:155-213 */
     EV2B_REWARD_GRID_PROFITMAX_V2 = 12,   /* Grid_V2G_profitmaxV2 (needs a grid)   reward.py:215-279 */
-    EV2B_REWARD_PST_PROFITMAX_V2 = 13     /* pst_V2G_profitmaxV2                   reward.py:281-339 */
+    EV2B_REWARD_PST_PROFITMAX_V2 = 13,    /* pst_V2G_profitmaxV2                   reward.py:281-339 */
+    EV2B_REWARD_SQ_TRACKING_PENALTY = 14  /* SquaredTrackingErrorRewardWithPenalty reward.py:46-58   */
 };
 enum ev2b_state_kind {
     EV2B_STATE_NONE = 0,

@@ -572,6 +572,13 @@ int ev2o_step(const ev2o_topology *tp, const ev2o_scenario *sc, ev2o_state *st,
         for (int k = 0; k < Tr; ++k) reward -= 100.0 * st->tr_overload_hist[(size_t)k * T + tm1];
         for (int i = 0; i < n_dep_rec; ++i) reward -= 1000.0 * (1.0 - dep_score[i]);
     } break;
+    case EV2O_REWARD_SQ_TRACKING_PENALTY: {                          /* reward.py:46-58 */
+        double m = sc->setpoint[tm1] < st->potential[tm1] ? sc->setpoint[tm1] : st->potential[tm1];
+        int prev = st->current_step - 2;                             /* python index: -1 wraps to the last entry */
+        if (prev < 0) prev += T;
+        reward = -py_sq(m - st->usage[tm1]);
+        if (st->usage[tm1] == 0 && st->potential[prev] != 0) reward = reward - 100;
+    } break;
     case EV2O_REWARD_SIMPLE:                                         /* reward.py:60-65 */
         reward = -py_sq(sc->setpoint[tm1] - st->usage[tm1]);
         break;

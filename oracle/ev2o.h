@@ -42,7 +42,8 @@ enum { EV2O_REWARD_NONE = 0, EV2O_REWARD_SQ_TRACKING = 1, EV2O_REWARD_PROFIT_TR_
        EV2O_REWARD_V2G_COSTS_SIMPLE = 10,  /* V2G_costs_simple                         reward.py:150-153 */
        EV2O_REWARD_V2G_PROFITMAX_V2 = 11,  /* V2G_profitmaxV2                          reward.py:155-213 */
        EV2O_REWARD_GRID_PROFITMAX_V2 = 12, /* Grid_V2G_profitmaxV2                     reward.py:215-279 */
-       EV2O_REWARD_PST_PROFITMAX_V2 = 13   /* pst_V2G_profitmaxV2                      reward.py:281-339 */ };
+       EV2O_REWARD_PST_PROFITMAX_V2 = 13,  /* pst_V2G_profitmaxV2                      reward.py:281-339 */
+       EV2O_REWARD_SQ_TRACKING_PENALTY = 14 /* SquaredTrackingErrorRewardWithPenalty   reward.py:46-58   */ };
 enum { EV2O_STATE_NONE = 0, EV2O_STATE_PUBLIC_PST = 1, EV2O_STATE_V2G_PROFIT_MAX = 2,
        EV2O_STATE_V2G_PROFIT_MAX_LOADS = 3, EV2O_STATE_V2G_GRID = 4 };
 

@@ -238,6 +238,8 @@ CASES = [
     ("grid_c16_v2_s20", "V2Ggrid", {"number_of_charging_stations": 16, "_reward": "Grid_V2G_profitmaxV2"}, 20, "mixed"),
     ("pst8n2_pstv2_s21", "PublicPST", {"number_of_charging_stations": 8, "number_of_ports_per_cs": 2, "v2g_enabled": True,
                                        "_reward": "pst_V2G_profitmaxV2"}, 21, "mixed"),
+    ("pst4_sqpenalty_s22", "PublicPST", {"number_of_charging_stations": 4,
+                                         "_reward": "SquaredTrackingErrorRewardWithPenalty"}, 22, "mixed"),
     ("ts10_c5_uniform_s10", "V2GProfitMax", {"number_of_charging_stations": 5, "timescale": 10,
                                              "simulation_length": 150}, 10, "uniform"),
 ]
