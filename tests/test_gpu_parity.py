@@ -32,9 +32,12 @@ ALL_OUT = ("reward", "status", "obs", "cs_power", "cs_current", "tr_power", "tr_
            "action_mask", "dep_sat", "port_energy")
 
 
+@pytest.mark.parametrize("epb", [0, 3])
 @pytest.mark.parametrize("name", golden_cases())
-def test_cuda_matches_reference_trace(name):
+def test_cuda_matches_reference_trace(name, epb, monkeypatch):
     import torch
+    if epb:                               # small batches get one env per CTA by default: force the multi-env CTA layout too
+        monkeypatch.setenv("EV2B_EPB", str(epb))
     from ev2gym_b200.scenario import ScenarioPack
     pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
     tr = np.load(f"{GOLDEN}/{name}.trace.npz")
@@ -101,7 +104,9 @@ SHAPES = [  # C, n_ports, Tr, E, reward, state, action dtype
 
 
 @pytest.mark.parametrize("C,n,Tr,E,reward,state,adt", SHAPES)
-def test_cuda_matches_oracle_on_synthetic(C, n, Tr, E, reward, state, adt):
+def test_cuda_matches_oracle_on_synthetic(C, n, Tr, E, reward, state, adt, monkeypatch):
+    if C * 4 <= 1024:
+        monkeypatch.setenv("EV2B_EPB", "4")   # several envs per CTA (the default for big batches of small envs)
     import torch
     from ev2gym_b200.scenario import Topology
     from ev2gym_b200.synthetic import sample_bank
@@ -250,7 +255,8 @@ def test_step_k_device_agents(agent):
     assert _close(eng.kpis()["total_reward"], [s.total_reward for s in orc.states], 1e-9, 1e-9)
 
 
-def test_grid_power_flow_matches_oracle_on_synthetic():
+def test_grid_power_flow_matches_oracle_on_synthetic(monkeypatch):
+    monkeypatch.setenv("EV2B_EPB", "3")
     """Synthetic 20-bus feeder, 2 ports per charger, several envs per CTA: voltages / grid rewards / grid state."""
     import torch
     from ev2gym_b200.scenario import Topology
