@@ -355,3 +355,92 @@ class EV2GymB200Vec:
 
     def state_tensors(self):
         return self.engine.state_tensors()
+
+
+class EV2GymB200SB3Vec:
+    """The same batch behind the VecEnv call convention of stable-baselines3 (duck-typed: SB3 is not imported): numpy in /
+    numpy out, `step_async` + `step_wait`, auto-reset with `terminal_observation`, one info dict per env.  This is the
+    surface the reference's SB3 scripts drive through `DummyVecEnv` / `SubprocVecEnv` around E separate `EV2Gym`
+    processes (train_stable_baselines.py:139-175); here all E envs are one `ev2b_step_host` call with pinned buffers.
+
+    Differences a caller can see: observations are float32 (SB3 casts to float32 anyway); `get_attr` / `env_method`
+    serve only what is meaningful for a batch (`simulation_length`, `number_of_ports`, ...)."""
+
+    def __init__(self, topo: Topology, scenarios: Sequence[Scenario], num_envs: int, state_function="V2G_profit_max",
+                 reward_function="profit_maximization", device: int = 0, rank: int = 0):
+        import torch
+        self.topo, self.num_envs = topo, int(num_envs)
+        self.engine = BatchedEngine(topo, num_envs, reward=reward_function, state=state_function, device=device,
+                                    outputs=("reward", "status", "obs"))
+        self.engine.load_scenarios(scenarios)
+        self._first = [(rank * num_envs + e) % len(scenarios) for e in range(num_envs)]
+        E, P, D = self.num_envs, topo.P, self.engine.D
+        low = -1.0 if topo.v2g_enabled else 0.0
+        self.action_space = Box(low * np.ones(P), np.ones(P), dtype=np.float32)                       # ev2gym_env.py:225-231
+        self.observation_space = Box(-np.inf * np.ones(D), np.inf * np.ones(D), dtype=np.float32)
+        self.render_mode = None
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        self._keep = [pin((E, P), torch.float32), pin((E,), torch.float64), pin((E,), torch.int32), pin((E, D), torch.float32)]
+        self._act, self._rew, self._st, self._obs = (t.numpy() for t in self._keep)
+        self._st = self._st.view(np.uint32)
+        self._ep_ret, self._ep_len = np.zeros(E), np.zeros(E, dtype=np.int64)
+        self._pending = False
+
+    def reset(self):
+        self._ep_ret[:], self._ep_len[:] = 0.0, 0
+        return self.engine.reset(scn_ids=self._first).cpu().numpy().copy()
+
+    def step_async(self, actions):
+        a = np.asarray(actions)
+        if a.shape != self._act.shape:
+            raise ValueError(f"actions must have shape {self._act.shape}")
+        self._act[...] = a                           # SB3 hands over float32 arrays; the kernel widens them to float64
+        self._pending = True
+
+    def step_wait(self):
+        assert self._pending, "step_async must be called first"
+        self._pending = False
+        self.engine.step_host(self._act, self._rew, self._st, self._obs)
+        obs, rew = self._obs.copy(), self._rew.astype(np.float32)
+        if (self._st & 2).any():
+            raise Exception("sum of amps is higher than max charge current")         # ev_charger.py:203-205
+        done = (self._st & 1).astype(bool)
+        self._ep_ret += self._rew
+        self._ep_len += 1
+        infos = [{} for _ in range(self.num_envs)]
+        if done.any():
+            idx = np.nonzero(done)[0]
+            first = self.engine.reset_done().index_select(0, self.engine.torch.as_tensor(idx, device=self.engine.dev)).cpu().numpy()
+            for k, e in enumerate(idx):
+                infos[e] = {"terminal_observation": obs[e].copy(), "TimeLimit.truncated": False,
+                            "episode": {"r": float(self._ep_ret[e]), "l": int(self._ep_len[e])}}
+                obs[e] = first[k]
+            self._ep_ret[idx], self._ep_len[idx] = 0.0, 0
+        return obs, rew, done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.engine.close()
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs                # step() consumes no randomness; scenarios are fixed by the bank
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * self.num_envs
+
+    def get_attr(self, name, indices=None):
+        vals = {"simulation_length": self.topo.T, "number_of_ports": self.topo.P, "cs": self.topo.C,
+                "number_of_transformers": self.topo.Tr, "timescale": self.topo.timescale, "render_mode": None}
+        if name not in vals:
+            raise AttributeError(f"{name!r} is not available on the batched env")
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [vals[name]] * n
+
+    def set_attr(self, name, value, indices=None):
+        raise AttributeError("the batched env has no per-env Python attributes to set")
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        raise AttributeError(f"{method_name!r}: per-env Python methods do not exist on the batched env")

@@ -114,3 +114,40 @@ def test_vec_env_auto_reset():
         if done.any():
             assert float(obs[done][:, 0].max()) == 0.0          # already the first observation of the next episode
     assert n_done == 64 and int(vec.state_tensors()["env_step"][0]) == 2
+
+
+def test_sb3_style_vec_env_replays_reference_episode():
+    """EV2GymB200SB3Vec (numpy VecEnv convention: step_async / step_wait, auto reset, terminal_observation) on a
+    recorded ChargeAsFastAsPossible episode: per-step obs / reward / done, the terminal observation and the episode
+    return equal the reference's; after the last step every env already shows the first observation of its next episode."""
+    from ev2gym_b200.env import EV2GymB200SB3Vec
+    from ev2gym_b200.scenario import ScenarioPack
+    name = "c1_afap_s42"
+    pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
+    tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+    E = 5
+    venv = EV2GymB200SB3Vec(pack.topo, pack.scenarios, E, state_function=str(tr["state_fn"]),
+                            reward_function=str(tr["reward_fn"]))
+    assert venv.num_envs == E and venv.action_space.shape == (pack.topo.P,)
+    obs = venv.reset()
+    assert obs.shape == (E,) + venv.observation_space.shape and obs.dtype == np.float32
+    assert np.allclose(obs[0], tr["obs0"], rtol=1e-5, atol=1e-5)
+    T = tr["reward"].shape[0]
+    for t in range(T):
+        venv.step_async(np.ones((E, pack.topo.P), dtype=np.float32))
+        obs, rew, done, infos = venv.step_wait()
+        assert rew.dtype == np.float32 and done.dtype == bool and len(infos) == E
+        assert np.allclose(rew, tr["reward"][t], rtol=1e-5, atol=1e-5), t
+        assert bool(done.all()) == bool(tr["done"][t])
+        if t < T - 1:
+            assert np.allclose(obs[E - 1], tr["obs"][t], rtol=1e-5, atol=1e-5), t
+            assert infos[0] == {}
+    for e in (0, E - 1):
+        assert np.allclose(infos[e]["terminal_observation"], tr["obs"][T - 1], rtol=1e-5, atol=1e-5)
+        assert infos[e]["episode"]["l"] == T
+        assert infos[e]["episode"]["r"] == pytest.approx(float(tr["total_reward"]), rel=1e-9)
+        assert np.allclose(obs[e], tr["obs0"], rtol=1e-5, atol=1e-5)          # bank of one scenario: the same episode restarts
+    obs2, rew2, done2, _ = venv.step(np.ones((E, pack.topo.P), dtype=np.float32))   # and it runs on
+    assert np.allclose(rew2, tr["reward"][0], rtol=1e-5, atol=1e-5) and not done2.any()
+    assert venv.get_attr("simulation_length") == [T] * E
+    venv.close()
