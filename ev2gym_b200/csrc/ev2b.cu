@@ -169,7 +169,7 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<grid, h->block, h->smem, st>>>(p);
+        EV2B_LAUNCH(kern, grid, h->block, h->smem, st, p);
         return cudaGetLastError();
     };
 #ifndef EV2B_MINB
@@ -634,7 +634,7 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
             CUDA_TRY(h, tab.alloc(n));
             Params p = h->params();
             p.obs_static = nullptr;
-            obs_static_kernel<<<1024, 256>>>(p, tab.p);
+            EV2B_LAUNCH(obs_static_kernel, (unsigned)std::min<size_t>(1024, (n + 255) / 256), 256, 0, (cudaStream_t)0, p, tab.p);
             CUDA_TRY(h, cudaGetLastError());
             CUDA_TRY(h, cudaDeviceSynchronize());
             h->obs_static.p = tab.p; h->obs_static.n = tab.n; tab.p = nullptr; tab.n = 0;
@@ -652,8 +652,8 @@ static int launch_reset(ev2b_handle *h, int lo, int hi, const int *scn_dev, int 
     const Params p = h->params();
     const size_t n = (size_t)(hi - lo) * h->P;
     const int blk = 256;
-    reset_ports_kernel<<<(unsigned)((n + blk - 1) / blk), blk, 0, st>>>(p, lo, hi, scn_dev, mode);
-    reset_envs_kernel<<<hi - lo, 128, 0, st>>>(p, lo, hi, scn_dev, mode, obs0);
+    EV2B_LAUNCH(reset_ports_kernel, (unsigned)((n + blk - 1) / blk), blk, 0, st, p, lo, hi, scn_dev, mode);
+    EV2B_LAUNCH(reset_envs_kernel, hi - lo, 128, 0, st, p, lo, hi, scn_dev, mode, obs0);
     h->launches += 2;
     CUDA_TRY(h, cudaGetLastError());
     return EV2B_OK;
@@ -737,7 +737,7 @@ int ev2b_agent_actions(ev2b_handle *h, int agent_kind, double *actions_out, void
     const int thr = std::min(kMaxThreads, std::max(32, (h->P + 31) / 32 * 32));
     const size_t sm = (size_t)h->P * 5 + 16;
     if (sm > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(agent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    agent_kernel<<<h->E, thr, sm, st>>>(h->params(), agent_kind, actions_out);
+    EV2B_LAUNCH(agent_kernel, h->E, thr, sm, st, h->params(), agent_kind, actions_out);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return EV2B_OK;
@@ -836,7 +836,7 @@ int ev2b_episode_stats(ev2b_handle *h, double *out, void *stream) {
     if (!(h->dims.flags & EV2B_F_STATS)) return h->fail(EV2B_E_STATE, "episode_stats: handle was created without EV2B_F_STATS");
     if (h->S == 0) return h->fail(EV2B_E_STATE, "episode_stats: no scenario bank loaded");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    episode_stats_kernel<<<h->E, 32, 0, (cudaStream_t)stream>>>(h->params(), out);
+    EV2B_LAUNCH(episode_stats_kernel, h->E, 32, 0, (cudaStream_t)stream, h->params(), out);
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
     return EV2B_OK;

@@ -21,7 +21,15 @@
 // compiled with -fmad=false so no multiply-add is contracted (the only FMAs are the explicit ones
 // of the exact constant division, ev2b_math.h).  No tensor cores: elementwise + segmented reduce.
 #pragma once
+#ifdef EV2B_SIMT_EMU
+// tests/simt_emu: the same sources compiled by g++ and run on a fiber-based SIMT emulator (test infrastructure only)
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
+#define EV2B_NOINLINE __noinline__
+#define EV2B_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define EV2B_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 #include <stdint.h>
 #include "../../include/ev2b.h"
 #include "ev2b_math.h"
@@ -155,6 +163,11 @@ __device__ __forceinline__ double lut_get(const double *lut, int lut_len, double
     return 1.0;
 }
 
+#ifdef EV2B_SIMT_EMU
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) { simt::cp_async(smem_dst, gmem_src, 8); }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) { simt::cp_async(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async_wait_all() { simt::cp_async_wait_all(); }
+#else
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -162,6 +175,7 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -341,7 +355,7 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
 
 // ---- statistics mode: what EV.get_battery_degradation / get_statistics need of one EV ----------
 // Called when the EV leaves (or at the last step for EVs still connected).  ev.py:442-521, utils.py:49-63
-__device__ __noinline__ void finalize_ev(const Params &p, size_t ip, int e_c, const EvSpec *sp, double afap,
+__device__ EV2B_NOINLINE void finalize_ev(const Params &p, size_t ip, int e_c, const EvSpec *sp, double afap,
                                          int t_arr, int t_dep, double cap_final) {
     const double e0 = 7.543e6, e1 = 23.75e6, z0 = 7.348e-3, z1 = 3.667, z2 = 7.6e-4, z3 = 4.081e-3;
     const double k = 0.8263, v_min = 3.3324, b_cap_kwh = 78;
@@ -435,7 +449,7 @@ __device__ __forceinline__ double power_flow_env(const Params &p, double2 *S, co
 // ActT: float or double actions.  NP: ports per charger when uniform (1, 2), 0 = ragged (CsStatic).
 template <typename ActT, int NP, bool UNI, int MAXT, int MINB, bool HEAVY, bool OPTOUT>   // HEAVY: statistics mode and/or distribution grid compiled in
 __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant__ Params p) {   // __grid_constant__: &p may be passed to finalize_ev without a per-thread copy
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EV2B_DYNAMIC_SMEM(smem_raw);
     const int NT = blockDim.x;
     const int PP = p.EPB * p.P;
     double *red   = reinterpret_cast<double *>(smem_raw);                 // [kNRed][NT]
@@ -988,7 +1002,8 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
 // the reference's O(P) list searches per port.
 // CALAP (heuristics.py:98-150): per-port, stateless.
 __global__ void agent_kernel(const Params p, int kind, double *act) {
-    extern __shared__ int a_sm[];                 // [P] keys, then [P] bytes: bit0 queued, bit1 new
+    EV2B_DYNAMIC_SMEM(a_raw);                     // [P] keys, then [P] bytes: bit0 queued, bit1 new
+    int *a_sm = reinterpret_cast<int *>(a_raw);
     int *skey = a_sm;
     unsigned char *sflag = reinterpret_cast<unsigned char *>(a_sm + p.P);
     __shared__ int s_new, s_len;

@@ -53,6 +53,75 @@ def _fn_name(f) -> Optional[str]:
     return getattr(f, "__name__", None)
 
 
+def topology_view(topo: Topology):
+    """`ev2b_topology` (include/ev2b.h) over the arrays of a Topology; returns (view, arrays to keep alive)."""
+    keep = [topo.cs_n_ports, topo.cs_tr, topo.cs_phases, topo.cs_imax, topo.cs_imin, topo.cs_imax_dis,
+            topo.cs_imin_dis, topo.cs_voltage]
+    tv = _lib.TopologyView(*[a.ctypes.data_as(t) for a, (_, t) in zip(keep, _lib.TopologyView._fields_)])
+    if topo.n_bus:
+        gk = np.ascontiguousarray(topo.grid_K).view(np.float64).reshape(-1)
+        gl = np.ascontiguousarray(topo.grid_L).view(np.float64).reshape(-1)
+        keep += [gk, gl]
+        tv.n_bus, tv.grid_s_base = topo.n_bus, float(topo.grid_s_base)
+        tv.grid_K, tv.grid_L = gk.ctypes.data_as(_lib._pd), gl.ctypes.data_as(_lib._pd)
+    return tv, keep
+
+
+def scenarios_view(topo: Topology, scenarios: Sequence[Scenario]):
+    """`ev2b_scenarios` (include/ev2b.h) over a bank of Scenario objects; returns (view, arrays to keep alive)."""
+    n = len(scenarios)
+    T, Tr = topo.T, topo.Tr
+    for sc in scenarios:
+        sc.normalise()
+        if sc.charge_price.shape != (T,) or sc.tr_infl.shape != (Tr, T):
+            raise EngineError("scenario shape does not match the engine's topology")
+    v = _lib.ScenariosView()
+    keep = []
+
+    def put(name, arr, ptr_t):
+        arr = np.ascontiguousarray(arr)
+        keep.append(arr)
+        setattr(v, name, arr.ctypes.data_as(ptr_t))
+
+    v.n = n
+    ndr = max(int(sc.dr_start.shape[1]) for sc in scenarios)
+    v.n_dr, v.lut_len = ndr, LUT_LEN
+
+    def pad_dr(a, fill=0):
+        out = np.full((Tr, ndr), fill, dtype=a.dtype)
+        out[:, :a.shape[1]] = a
+        return out
+
+    for k in _lib._SCN_F64:
+        put(k, np.stack([getattr(sc, k) for sc in scenarios]).astype(np.float64), _lib._pd)
+    put("dr_start", np.stack([pad_dr(sc.dr_start) for sc in scenarios]).astype(np.int32), _lib._pi)
+    put("dr_end", np.stack([pad_dr(sc.dr_end) for sc in scenarios]).astype(np.int32), _lib._pi)
+    put("dr_cap", np.stack([pad_dr(sc.dr_cap) for sc in scenarios]).astype(np.float64), _lib._pd)
+    put("dr_count", np.stack([sc.dr_count for sc in scenarios]).astype(np.int32), _lib._pi)
+    s_off = np.zeros(n + 1, dtype=np.int64)
+    l_off = np.zeros(n + 1, dtype=np.int64)
+    for i, sc in enumerate(scenarios):
+        s_off[i + 1] = s_off[i] + sc.n_sessions
+        l_off[i + 1] = l_off[i] + sc.luts_c.shape[0]
+    put("sess_off", s_off, _lib._pl)
+    put("lut_off", l_off, _lib._pl)
+    for k in SESSION_INT_FIELDS:
+        put("s_" + k, np.concatenate([sc.sessions[k] for sc in scenarios]).astype(np.int32), _lib._pi)
+    for k in SESSION_F64_FIELDS:
+        put("s_" + k, np.concatenate([sc.sessions[k] for sc in scenarios]).astype(np.float64), _lib._pd)
+    put("luts_c", np.concatenate([sc.luts_c.reshape(-1) for sc in scenarios] + [np.zeros(0)]), _lib._pd)
+    put("luts_d", np.concatenate([sc.luts_d.reshape(-1) for sc in scenarios] + [np.zeros(0)]), _lib._pd)
+    if all(sc.date_feat.shape == (T + 1, 3) for sc in scenarios):
+        put("date_feat", np.stack([sc.date_feat for sc in scenarios]).astype(np.float64), _lib._pd)
+    if topo.n_bus:
+        nb = topo.n_bus
+        if not all(sc.grid_active.shape == (T + 1, nb) for sc in scenarios):
+            raise EngineError("grid topology: every scenario needs grid_active / grid_reactive of shape (T+1, n_bus)")
+        put("grid_active", np.stack([sc.grid_active for sc in scenarios]).astype(np.float64), _lib._pd)
+        put("grid_reactive", np.stack([sc.grid_reactive for sc in scenarios]).astype(np.float64), _lib._pd)
+    return v, keep
+
+
 class _CudaView:
     """Minimal __cuda_array_interface__ carrier so torch can wrap a raw device pointer zero-copy."""
 
@@ -78,14 +147,7 @@ class BatchedEngine:
         d = _lib.Dims(self.E, topo.C, topo.Tr, topo.T, topo.timescale, topo.dr_steps_ahead, REWARD_KINDS[r],
                       STATE_KINDS[s], float(topo.tr_voltage), 1 if stats else 0, 0)
         self.stats = bool(stats)
-        self._keep = [topo.cs_n_ports, topo.cs_tr, topo.cs_phases, topo.cs_imax, topo.cs_imin, topo.cs_imax_dis,
-                      topo.cs_imin_dis, topo.cs_voltage]
-        tv = _lib.TopologyView(*[a.ctypes.data_as(t) for a, (_, t) in zip(self._keep, _lib.TopologyView._fields_)])
-        if topo.n_bus:
-            self._gk = np.ascontiguousarray(topo.grid_K).view(np.float64).reshape(-1)
-            self._gl = np.ascontiguousarray(topo.grid_L).view(np.float64).reshape(-1)
-            tv.n_bus, tv.grid_s_base = topo.n_bus, float(topo.grid_s_base)
-            tv.grid_K, tv.grid_L = self._gk.ctypes.data_as(_lib._pd), self._gl.ctypes.data_as(_lib._pd)
+        tv, self._keep = topology_view(topo)
         h = C.c_void_p()
         rc = self.L.ev2b_create(C.byref(d), C.byref(tv), self.device, C.byref(h))
         if rc != 0:
@@ -134,58 +196,9 @@ class BatchedEngine:
     # ------------------------------------------------------------------------------------------
     def load_scenarios(self, scenarios: Sequence[Scenario]):
         """Upload a scenario bank (replaces the previous one; every env must be reset afterwards)."""
-        n = len(scenarios)
-        T, Tr = self.T, self.Tr
-        for sc in scenarios:
-            sc.normalise()
-            if sc.charge_price.shape != (T,) or sc.tr_infl.shape != (Tr, T):
-                raise EngineError("scenario shape does not match the engine's topology")
-        v = _lib.ScenariosView()
-        keep = []
-
-        def put(name, arr, ptr_t):
-            arr = np.ascontiguousarray(arr)
-            keep.append(arr)
-            setattr(v, name, arr.ctypes.data_as(ptr_t))
-
-        v.n = n
-        ndr = max(int(sc.dr_start.shape[1]) for sc in scenarios)
-        v.n_dr, v.lut_len = ndr, LUT_LEN
-
-        def pad_dr(a, fill=0):
-            out = np.full((Tr, ndr), fill, dtype=a.dtype)
-            out[:, :a.shape[1]] = a
-            return out
-
-        for k in _lib._SCN_F64:
-            put(k, np.stack([getattr(sc, k) for sc in scenarios]).astype(np.float64), _lib._pd)
-        put("dr_start", np.stack([pad_dr(sc.dr_start) for sc in scenarios]).astype(np.int32), _lib._pi)
-        put("dr_end", np.stack([pad_dr(sc.dr_end) for sc in scenarios]).astype(np.int32), _lib._pi)
-        put("dr_cap", np.stack([pad_dr(sc.dr_cap) for sc in scenarios]).astype(np.float64), _lib._pd)
-        put("dr_count", np.stack([sc.dr_count for sc in scenarios]).astype(np.int32), _lib._pi)
-        s_off = np.zeros(n + 1, dtype=np.int64)
-        l_off = np.zeros(n + 1, dtype=np.int64)
-        for i, sc in enumerate(scenarios):
-            s_off[i + 1] = s_off[i] + sc.n_sessions
-            l_off[i + 1] = l_off[i] + sc.luts_c.shape[0]
-        put("sess_off", s_off, _lib._pl)
-        put("lut_off", l_off, _lib._pl)
-        for k in SESSION_INT_FIELDS:
-            put("s_" + k, np.concatenate([sc.sessions[k] for sc in scenarios]).astype(np.int32), _lib._pi)
-        for k in SESSION_F64_FIELDS:
-            put("s_" + k, np.concatenate([sc.sessions[k] for sc in scenarios]).astype(np.float64), _lib._pd)
-        put("luts_c", np.concatenate([sc.luts_c.reshape(-1) for sc in scenarios] + [np.zeros(0)]), _lib._pd)
-        put("luts_d", np.concatenate([sc.luts_d.reshape(-1) for sc in scenarios] + [np.zeros(0)]), _lib._pd)
-        if all(sc.date_feat.shape == (T + 1, 3) for sc in scenarios):
-            put("date_feat", np.stack([sc.date_feat for sc in scenarios]).astype(np.float64), _lib._pd)
-        if self.topo.n_bus:
-            nb = self.topo.n_bus
-            if not all(sc.grid_active.shape == (T + 1, nb) for sc in scenarios):
-                raise EngineError("grid topology: every scenario needs grid_active / grid_reactive of shape (T+1, n_bus)")
-            put("grid_active", np.stack([sc.grid_active for sc in scenarios]).astype(np.float64), _lib._pd)
-            put("grid_reactive", np.stack([sc.grid_reactive for sc in scenarios]).astype(np.float64), _lib._pd)
+        v, _keep = scenarios_view(self.topo, scenarios)
         self._check(self.L.ev2b_load_scenarios(self.h, C.byref(v)), "ev2b_load_scenarios")
-        self.n_scenarios = n
+        self.n_scenarios = len(scenarios)
 
     def reset(self, env_lo: int = 0, env_hi: Optional[int] = None, scn_ids: Optional[Sequence[int]] = None):
         """Reset envs [env_lo, env_hi); returns the observation tensor [E,D] (rows of that range refreshed)."""
