@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("EV2B_LIB") or os.path.join(CSRC, "libev2b.so")   # EV2B_LIB: A/B-test another build
-SOURCES = [os.path.join(CSRC, f) for f in ("ev2b.cu", "ev2b_device.cuh")] + \
+SOURCES = [os.path.join(CSRC, f) for f in ("ev2b.cu", "ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_math.h")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "ev2b.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
@@ -70,7 +70,7 @@ class StateView(C.Structure):
 EXPORTS = ("ev2b_abi_version", "ev2b_last_error", "ev2b_create", "ev2b_destroy", "ev2b_obs_dim", "ev2b_n_ports",
            "ev2b_load_scenarios", "ev2b_n_scenarios", "ev2b_reset", "ev2b_step", "ev2b_step_host",
            "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count", "ev2b_episode_stats", "ev2b_step_k",
-           "ev2b_agent_actions")
+           "ev2b_agent_actions", "ev2b_kernel_launches")
 
 
 def needs_build() -> bool:
@@ -142,6 +142,8 @@ def load():
     L.ev2b_episode_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ev2b_launch_count.restype = C.c_int64
     L.ev2b_launch_count.argtypes = [C.c_void_p]
+    L.ev2b_kernel_launches.restype = C.c_int64
+    L.ev2b_kernel_launches.argtypes = [C.c_void_p, C.c_int]
     if L.ev2b_abi_version() != 1:
         raise RuntimeError("libev2b.so ABI version mismatch")
     _lib = L

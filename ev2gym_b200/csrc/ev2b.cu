@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 // (-fmad=false: the battery update must round like the reference's float64 Python arithmetic.)
 #include "ev2b_device.cuh"
+#include "ev2b_evlist.cuh"
 
 #include <algorithm>
 #include <array>
@@ -50,6 +51,7 @@ struct ev2b_handle {
     size_t smem = 0;
     std::string err;
     int64_t launches = 0;
+    int64_t launches_by[3] = {0, 0, 0};   // step_kernel, evl_step_kernel, evl_rebuild_kernel (ev2b_kernel_launches)
     const float *last_obs = nullptr;    // obs buffer whose rows are known to be current (incremental obs writes)
     // host copies of the static layout (needed to pack scenarios)
     std::vector<CsStatic> cs_h;
@@ -84,6 +86,25 @@ struct ev2b_handle {
                                         // EV2B_HOST_CHUNKS overrides, tuning only)
     cudaStream_t chunk_stream[kChunks] = {};
     cudaEvent_t chunk_ev[kChunks] = {}, start_ev = nullptr;
+    // event-driven step kernel (ev2b_evlist.cuh); chosen per handle by EV2B_KERNEL=evlist, used for the launches it covers
+    bool evl = false;                   // lists allocated, schedule built
+    bool list_valid = true;             // occ_list / occ_n agree with the hot words of every env
+    int evl_G = 4, evl_o[9] = {0};      // warps per env; smem map (v_stride, v_amp, ...)
+    size_t evl_smem = 0;
+    DevBuf<uint16_t> occ_list; DevBuf<int> occ_n, arr_off; DevBuf<unsigned> arr_list;
+    void layout_evl() {
+        size_t off = 0;
+        auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; const size_t at = off; off += bytes; return (int)at; };
+        take(8 * (size_t)P, 16);                                   // pw
+        evl_o[1] = take(8 * (size_t)P, 8); evl_o[2] = take(8 * (size_t)P, 8); evl_o[3] = take(8 * (size_t)C, 8);   // amp, pot, csP
+        evl_o[4] = take(8 * (size_t)(kPreTr + 4 * Tr), 16);        // pre (cp.async 16 B destinations)
+        evl_o[5] = take(8 * (size_t)(EvlNSum + 1) * evl_G, 8);     // wsum
+        evl_o[6] = take(8 * (size_t)Tr, 8);                        // trov
+        evl_o[7] = take(2 * (size_t)P, 4);                         // stage
+        evl_o[8] = take(((size_t)P + 3) / 4 * 4, 4);               // occ
+        evl_o[0] = (int)((off + 15) / 16 * 16);                    // stride
+        evl_smem = (size_t)evl_o[0] * (kEvlThreads / (32 * evl_G));
+    }
     // shared-memory map of step_kernel: byte offsets handed to the kernel through Params (constant bank)
     int so[15] = {0}, pre_stride = 0;
     void layout_smem() {
@@ -140,6 +161,9 @@ struct ev2b_handle {
         p.pot_kw = pot_kw.p; p.trA = trA.p; p.trF = trF.p; p.tr_limit = tr_limit.p; p.dr = dr.p; p.dr_count = dr_count.p;
         p.hot = hot.p; p.cap = cap.p; p.exch = exch.p; p.env_step = env_step.p; p.env_scn = env_scn.p;
         p.env_pot = env_pot.p; p.env_usage = env_usage.p; p.env_kpi = env_kpi.p; p.env_pot_prev = env_pot_prev.p;
+        p.occ_list = occ_list.p; p.occ_n = occ_n.p; p.arr_off = arr_off.p; p.arr_list = arr_list.p;
+        p.v_stride = evl_o[0]; p.v_amp = evl_o[1]; p.v_pot = evl_o[2]; p.v_csP = evl_o[3]; p.v_pre = evl_o[4];
+        p.v_wsum = evl_o[5]; p.v_trov = evl_o[6]; p.v_stage = evl_o[7]; p.v_occ = evl_o[8];
         p.rr_key = rr_key.p; p.rr_fb = rr_fb.p; p.rr_avg_power = rr_avg_power; p.rr_share = rr_share;
         return p;
     }
@@ -159,6 +183,52 @@ static int obs_dim_for(int kind, int P, int Tr) {
     case EV2B_STATE_V2G_GRID: return 6 + 2 * Tr + 3 * P;          // n_bus == Tr in grid mode
     default: return 0;
     }
+}
+
+// The full-featured (HEAVY) instantiation: statistics mode, distribution grid, the less common rewards.
+static bool needs_heavy(const ev2b_handle *h) {
+    return (h->dims.flags & EV2B_F_STATS) != 0 || h->n_bus > 0 || h->dims.reward_kind >= EV2B_REWARD_SQTR_TR_USER;
+}
+// Does the event-driven kernel cover a launch with these outputs?  (it has no per-port optional outputs)
+static bool evl_covers(const ev2b_handle *h, const ev2b_step_out *o) {
+    if (!h->evl) return false;
+    return !o || !(o->action_mask || o->dep_sat || o->dep_cap || o->port_energy || o->node_voltage);
+}
+
+template <typename ActT>
+static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st) {
+    const int epb = kEvlThreads / (32 * h->evl_G);
+    const unsigned grid = (unsigned)((p.env_end - p.env0 + epb - 1) / epb);
+    auto go = [&](auto kern) -> cudaError_t {
+        if (h->evl_smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->evl_smem);
+            if (e != cudaSuccess) return e;
+        }
+        EV2B_LAUNCH(kern, grid, kEvlThreads, h->evl_smem, st, p);
+        return cudaGetLastError();
+    };
+    const int np = (h->cs_uniform && (h->np_uniform == 1 || h->np_uniform == 2)) ? h->np_uniform : 0;
+#define EV2B_EVL_DISPATCH(G)                                                   \
+    do {                                                                       \
+        if (np == 1) return go(evl_step_kernel<ActT, 1, true, G>);             \
+        if (np == 2) return go(evl_step_kernel<ActT, 2, true, G>);             \
+        return go(evl_step_kernel<ActT, 0, false, G>);                         \
+    } while (0)
+    if (h->evl_G == 1) EV2B_EVL_DISPATCH(1);
+    if (h->evl_G == 2) EV2B_EVL_DISPATCH(2);
+    EV2B_EVL_DISPATCH(4);
+#undef EV2B_EVL_DISPATCH
+}
+
+// Brings occ_list / occ_n back in line with the hot words after step_kernel advanced some envs (all envs, on `st`).
+static int ensure_list(ev2b_handle *h, cudaStream_t st) {
+    if (!h->evl || h->list_valid) return EV2B_OK;
+    const int wpb = 4;
+    EV2B_LAUNCH(evl_rebuild_kernel, (unsigned)((h->E + wpb - 1) / wpb), 32 * wpb, 0, st, h->params(), 0, h->E);
+    h->launches += 1; h->launches_by[2] += 1;
+    if (cudaGetLastError() != cudaSuccess) return h->fail(EV2B_E_CUDA, "evl_rebuild_kernel launch failed");
+    h->list_valid = true;
+    return EV2B_OK;
 }
 
 template <typename ActT>
@@ -193,8 +263,7 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
         if (np == 2) return go(step_kernel<ActT, 2, true, MAXT, MINB, false, false>);   \
         return go(step_kernel<ActT, 0, false, MAXT, MINB, false, false>);               \
     } while (0)
-    const bool stats = (h->dims.flags & EV2B_F_STATS) != 0 || h->n_bus > 0 ||   // the HEAVY instantiation
-                       h->dims.reward_kind >= EV2B_REWARD_SQTR_TR_USER;
+    const bool stats = needs_heavy(h);   // the HEAVY instantiation
 #ifndef EV2B_MINB128
 #define EV2B_MINB128 8
 #endif
@@ -357,6 +426,19 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         h->block = std::max(32, (best_epb * C + 31) / 32 * 32);
         h->layout_smem();
     }
+    // event-driven kernel (ev2b_evlist.cuh): EV2B_KERNEL=evlist opts a handle in; EV2B_EVL_G = warps per env (1, 2, 4)
+    {
+        const char *kv = getenv("EV2B_KERNEL");
+        const bool want = kv && (!strcmp(kv, "evlist") || !strcmp(kv, "evl"));
+        if (want && !needs_heavy(h) && h->P < 65535) {
+            h->evl = true;
+            h->evl_G = h->P <= 48 ? 1 : (h->P <= 160 ? 2 : 4);
+            if (const char *gv = getenv("EV2B_EVL_G")) { const int v = atoi(gv); if (v == 1 || v == 2 || v == 4) h->evl_G = v; }
+            h->layout_evl();
+            if (h->evl_smem > 200 * 1024) { h->evl_G = 4; h->layout_evl(); }
+            if (h->evl_smem > 200 * 1024) h->evl = false;          // does not fit: step_kernel takes every launch
+        }
+    }
 #define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
         g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e); delete h; return EV2B_E_CUDA; } } while (0)
     CREATE_TRY(h->cs.upload(h->cs_h));
@@ -381,6 +463,11 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     CREATE_TRY(h->env_step.alloc(h->E)); CREATE_TRY(h->env_scn.alloc(h->E));
     CREATE_TRY(h->env_pot.alloc(h->E)); CREATE_TRY(h->env_usage.alloc(h->E)); CREATE_TRY(h->env_pot_prev.alloc(h->E));
     CREATE_TRY(h->env_kpi.alloc((size_t)h->E * EV2B_KPI_COUNT));
+    if (h->evl) {
+        CREATE_TRY(h->occ_list.alloc(2 * EP)); CREATE_TRY(h->occ_n.alloc(h->E));
+        CREATE_TRY(cudaMemset(h->occ_list.p, 0, 2 * EP * sizeof(uint16_t)));
+        CREATE_TRY(cudaMemset(h->occ_n.p, 0, h->E * sizeof(int)));
+    }
     CREATE_TRY(cudaMemset(h->hot.p, 0, EP * sizeof(uint4)));
     CREATE_TRY(cudaMemset(h->cap.p, 0, EP * sizeof(double)));
     CREATE_TRY(cudaMemset(h->exch.p, 0, EP * sizeof(float)));
@@ -412,6 +499,7 @@ int ev2b_obs_dim(const ev2b_handle *h) { return h ? h->D : 0; }
 int ev2b_n_ports(const ev2b_handle *h) { return h ? h->P : 0; }
 int ev2b_n_scenarios(const ev2b_handle *h) { return h ? h->S : 0; }
 int64_t ev2b_launch_count(const ev2b_handle *h) { return h ? h->launches : 0; }
+int64_t ev2b_kernel_launches(const ev2b_handle *h, int which) { return (h && which >= 0 && which < 3) ? h->launches_by[which] : 0; }
 
 // k/1000.0 == v  <=>  v is what np.round(x, 3) produces (utils.py:293-296, 309-310)
 static bool milli(double v, unsigned *k) {
@@ -484,9 +572,13 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
     empty.hot.y = (unsigned)kNoArrival & 0xFFFFu;
     std::vector<SessRec> sess((size_t)S * P * Smax, empty);
     std::vector<int> last_of_port(P);
+    // arrival schedule of the event-driven kernel: sessions of scenario i arriving at step q (q <= T), in session order
+    std::vector<int> arr_off_h((size_t)S * (T + 2), 0);
+    std::vector<unsigned> arr_list_h;
     for (int i = 0; i < S; ++i) {
         std::fill(per_port.begin(), per_port.end(), 0);
         std::fill(last_of_port.begin(), last_of_port.end(), -1);
+        const size_t arr_base = arr_list_h.size();
         for (const Placed &pl : placed[i]) {
             const int64_t r = pl.row;
             EvSpec sp{};
@@ -544,7 +636,15 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
                 prev.hot.y = (prev.hot.y & 0xFFFF0000u) | ((unsigned)ta & 0xFFFFu);
             }
             last_of_port[pl.port] = k;
+            if (b->s_t_arr[r] <= T) {           // placed[] is arrival-sorted: the list comes out bucketed by step
+                arr_list_h.push_back((unsigned)pl.port | ((unsigned)k << 16));
+                arr_off_h[(size_t)i * (T + 2) + b->s_t_arr[r] + 1] += 1;
+            }
         }
+        int *ao = arr_off_h.data() + (size_t)i * (T + 2);        // ao[q + 1] holds the count of step q: prefix-sum into offsets
+        int acc = (int)arr_base;
+        ao[0] = acc;
+        for (int q = 1; q <= T + 1; ++q) { acc += ao[q]; ao[q] = acc; }
     }
     // potential contribution per (spec, charger class)          utils.py:772-777
     std::vector<double> pot_kw(specs.size() * h->n_cls);
@@ -614,6 +714,11 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
     CUDA_TRY(h, h->spec.upload(specs)); CUDA_TRY(h, h->luts_c.upload(luts_c)); CUDA_TRY(h, h->luts_d.upload(luts_d));
     CUDA_TRY(h, h->pot_kw.upload(pot_kw)); CUDA_TRY(h, h->trA.upload(trA)); CUDA_TRY(h, h->trF.upload(trF));
     CUDA_TRY(h, h->tr_limit.upload(tr_limit)); CUDA_TRY(h, h->dr.upload(dr)); CUDA_TRY(h, h->dr_count.upload(dr_count));
+    if (h->evl) {
+        if (arr_list_h.empty()) arr_list_h.push_back(0u);
+        CUDA_TRY(h, h->arr_off.upload(arr_off_h)); CUDA_TRY(h, h->arr_list.upload(arr_list_h));
+        h->list_valid = true;            // every env reads as done until it is reset, and reset empties its list
+    }
     h->S = S; h->Smax = Smax; h->n_dr = n_dr; h->lut_len = lut_len;
     h->last_obs = nullptr;
     if (h->dims.flags & EV2B_F_STATS) {
@@ -702,9 +807,16 @@ static int step_range(ev2b_handle *h, const void *actions, int action_dtype, con
     p.obs_full = obs_full;
     p.env0 = lo; p.env_end = hi;
     cudaError_t e;
-    if (action_dtype == EV2B_F32) e = launch_step<float>(h, p, st);
-    else if (action_dtype == EV2B_F64) e = launch_step<double>(h, p, st);
-    else return h->fail(EV2B_E_ARG, "step: unknown action dtype %d", action_dtype);
+    if (action_dtype != EV2B_F32 && action_dtype != EV2B_F64) return h->fail(EV2B_E_ARG, "step: unknown action dtype %d", action_dtype);
+    if (evl_covers(h, out)) {            // callers ran ensure_list() on a stream this launch is ordered after
+        if (!h->list_valid) return h->fail(EV2B_E_STATE, "step: connected-EV list is stale (internal error)");
+        e = action_dtype == EV2B_F32 ? launch_evl<float>(h, p, st) : launch_evl<double>(h, p, st);
+        h->launches_by[1] += 1;
+    } else {
+        if (h->evl) h->list_valid = false;
+        h->launches_by[0] += 1;
+        e = action_dtype == EV2B_F32 ? launch_step<float>(h, p, st) : launch_step<double>(h, p, st);
+    }
     if (e != cudaSuccess) return h->fail(EV2B_E_CUDA, "step launch: %s", cudaGetErrorString(e));
     h->launches += 1;
     return EV2B_OK;
@@ -716,6 +828,7 @@ int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_
     const float *obs = out ? out->obs : nullptr;
     const int obs_full = (obs != h->last_obs) ? 1 : 0;
     h->last_obs = obs;
+    if (evl_covers(h, out)) { const int rc = ensure_list(h, (cudaStream_t)stream); if (rc != EV2B_OK) return rc; }
     return step_range(h, actions, action_dtype, out, 0, h->E, obs_full, (cudaStream_t)stream);
 }
 
@@ -760,6 +873,7 @@ int ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, in
         h->last_obs = obs;
         const void *a = agent_kind == EV2B_AGENT_EXTERNAL ? (const void *)((const unsigned char *)actions_k + stride * i) : (const void *)h->hot.p;
         int rc;
+        if (evl_covers(h, out)) { rc = ensure_list(h, (cudaStream_t)stream); if (rc != EV2B_OK) return rc; }
         if (tensor_agent) {
             rc = ev2b_agent_actions(h, agent_kind, h->agent_act.p, stream);
             if (rc != EV2B_OK) return rc;
@@ -801,6 +915,7 @@ int ev2b_step_host(ev2b_handle *h, const void *actions_host, int action_dtype, d
     out.obs = want_obs ? h->st_obs.p : nullptr;
     const int obs_full = (out.obs != h->last_obs) ? 1 : 0;
     h->last_obs = out.obs;
+    if (evl_covers(h, &out)) { const int rc = ensure_list(h, user); if (rc != EV2B_OK) return rc; }   // before start_ev: every chunk stream waits on it
     // PCIe is full duplex and the copy engines run beside the SMs: split the env range into chunks, each on its
     // own stream (H2D actions -> kernel -> D2H results), so chunk i's download overlaps chunk i+1's upload/compute.
     const int per = ((h->E + h->n_chunks - 1) / h->n_chunks + h->EPB - 1) / h->EPB * h->EPB;
@@ -841,6 +956,16 @@ int ev2b_episode_stats(ev2b_handle *h, double *out, void *stream) {
     CUDA_TRY(h, cudaGetLastError());
     return EV2B_OK;
 }
+
+#ifdef EV2B_SIMT_EMU
+// emulator builds only (tests/test_emu_kernels.py): the connected-EV list of env e, current half of the ping-pong
+int ev2b_debug_list(ev2b_handle *h, int e, uint16_t *out) {
+    if (!h || !h->evl || e < 0 || e >= h->E) return -1;
+    const int t = h->env_step.p[e], n = h->occ_n.p[e];
+    memcpy(out, h->occ_list.p + ((size_t)(t & 1) * h->E + e) * h->P, sizeof(uint16_t) * (size_t)n);
+    return n;
+}
+#endif
 
 int ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *v) {
     if (!h || !v) return EV2B_E_ARG;

@@ -128,6 +128,12 @@ struct Params {
     // RoundRobin agent queue (heuristics.py:29,33-52): sort key per port (kRrAbsent = not queued) + front/back counters
     int *rr_key; int *rr_fb;   // [E,P], [E,2]; null until the agent is first used
     double rr_avg_power, rr_share;   // heuristics.py:19-23 ; 1 / number_of_ports_per_cs
+    // event-driven step kernel (ev2b_evlist.cuh): connected-EV list per env, arrival schedule per scenario, smem map
+    uint16_t *occ_list;        // [2][E][P] ports holding an EV, buffer (env_step & 1) is current; null: kernel not in use
+    int *occ_n;                // [E]
+    const int *arr_off;        // [S][T+2]: the sessions arriving at step q are arr_list[arr_off[s][q] .. arr_off[s][q+1])
+    const unsigned *arr_list;  // port | session index on that port << 16, arrival-sorted
+    int v_stride, v_amp, v_pot, v_csP, v_pre, v_wsum, v_trov, v_stage, v_occ;   // byte offsets inside one env's block
     // state
     uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;
     double *env_pot_prev;      // charge_power_potential[t-1], kept only for SquaredTrackingErrorRewardWithPenalty (reward.py:50)
@@ -983,6 +989,7 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
     __syncthreads();
     if (threadIdx.x == 0) {
         p.env_step[e] = 0; p.env_scn[e] = s; p.env_pot[e] = 0.0; p.env_usage[e] = 0.0; p.env_pot_prev[e] = 0.0;
+        if (p.occ_n) p.occ_n[e] = 0;          // no EV is connected at t = 0 (ev2b_evlist.cuh)
         for (int k = 0; k < EV2B_KPI_COUNT; ++k) p.env_kpi[(size_t)e * EV2B_KPI_COUNT + k] = 0.0;
     }
     if (p.stats)

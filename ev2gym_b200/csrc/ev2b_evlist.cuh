@@ -1,0 +1,386 @@
+// ev2b_evlist.cuh -- the event-driven step kernel: visits CONNECTED EVs instead of ports.
+//
+// step_kernel (ev2b_device.cuh) runs one thread per (env, charger) and touches every port every step although
+// 65-80 % of the ports are empty mid-episode; it is instruction-issue bound, not HBM bound.
+// This kernel keeps, per env, the list of ports that currently hold an EV (`occ_list`, ping-pong by step parity) and
+// a per-scenario arrival schedule (`arr_list` bucketed by step), and does the reference's work in that order:
+//
+//   P0  prefetch of the per-env records (cp.async), (scenario, time)-only observation values
+//   EV  one thread per CONNECTED EV (dense lanes): loads, Sigma-normalisation with the charger's other ports,
+//       EV.step (the float64 battery model, ev_step_item), charger accounting, departure, observation tuple,
+//       potential; per-port results go to shared memory                        ev_charger.py:114-233, ev.py:138-405
+//   AR  one thread per ARRIVAL of step t+1 (from the schedule)                  ev2gym_env.py:399-417
+//   CS  one thread per charger: power / amps / potential in port order, clamp   transformer.py:264-274, utils.py:779-789
+//   TR  warp 0: transformer sums (CSR) + overload; reward, KPI sums, step counter (same code path as step_kernel C)
+//   LS  last warp: stable compaction of the kept EVs + arrivals into the other half of the ping-pong list
+//
+// An env is owned by a GROUP of G warps (G = 1, 2, 4; a 128-thread CTA holds 4 / G envs), so every barrier is a
+// warp barrier (G = 1), a named barrier (G = 2) or __syncthreads (G = 4), and no phase leaves more than one warp of
+// a group running alone for long.  The state arrays (hot / cap / exch) are exactly step_kernel's: the two kernels are
+// interchangeable launch by launch (evl_rebuild_kernel re-derives the list from the hot words after step_kernel ran).
+// Handles: the lean instantiation's scope (no statistics mode, no grid, the stock rewards 0-3), without the
+// per-port optional outputs (action_mask, dep_sat, dep_cap, port_energy); everything else takes step_kernel.
+// Sums are formed in a different (still fixed) order than step_kernel's, so float64 outputs agree to ~1e-15
+// relative, not bitwise; battery levels, indices, counts and flags are identical.
+#pragma once
+#include "ev2b_device.cuh"
+
+namespace ev2b {
+
+constexpr int kEvlThreads = 128;
+constexpr unsigned kEvlGone = 0xFFFFu;       // staging mark: this EV left during the step
+enum { EvlProfit = 0, EvlSatExp, EvlCharged, EvlDischarged, EvlSatSum, EvlUsage, EvlPot, EvlNSum };
+
+__device__ __forceinline__ void evl_bar_sync(int id, int nthreads) {
+#ifdef EV2B_SIMT_EMU
+    simt::bar_sync(id, nthreads);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+template <int G>
+__device__ __forceinline__ void evl_group_sync(int g) {
+    if (G == 1) __syncwarp();
+    else if (G * 32 == kEvlThreads) __syncthreads();
+    else evl_bar_sync(1 + g, G * 32);
+}
+
+// Rebuilds occ_list / occ_n of envs [lo, hi) from the hot words (one warp per env): ports in ascending order.
+__global__ void evl_rebuild_kernel(const Params p, int lo, int hi) {
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
+    const int e = lo + warp;
+    if (e >= hi) return;
+    const int t = p.env_step[e];
+    uint16_t *lst = p.occ_list + ((size_t)(t & 1) * p.E + e) * p.P;
+    int base = 0;
+    for (int p0 = 0; p0 < p.P; p0 += 32) {
+        const int port = p0 + lane;
+        bool occ = false;
+        if (port < p.P && t < p.T) {
+            const unsigned hx = p.hot[(size_t)e * p.P + port].x;
+            occ = (int)(int16_t)(hx & 0xFFFFu) <= t && t <= (int)(int16_t)(hx >> 16);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, occ);
+        if (occ) lst[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)port;
+        base += __popc(m);
+    }
+    if (lane == 0) p.occ_n[e] = base;
+}
+
+template <typename ActT, int NP, bool UNI, int G>
+__global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_constant__ Params p) {
+    EV2B_DYNAMIC_SMEM(smem_raw);
+    constexpr int GT = 32 * G, EPB = kEvlThreads / GT;
+    const int tid = threadIdx.x;
+    const int g = tid / GT, gtid = tid - g * GT, lane = tid & 31, gw = gtid >> 5;
+    const int e = p.env0 + (int)blockIdx.x * EPB + g;
+    if (e >= p.env_end) return;                       // whole group: its barriers are its own
+
+    unsigned char *sm = smem_raw + (size_t)g * p.v_stride;
+    double *pw    = reinterpret_cast<double *>(sm);                  // [P] charger power contribution of the port's EV (kW)
+    double *amp   = reinterpret_cast<double *>(sm + p.v_amp);        // [P] its actual current (A)
+    double *pot   = reinterpret_cast<double *>(sm + p.v_pot);        // [P] its charge-power potential for step t+1
+    double *csP   = reinterpret_cast<double *>(sm + p.v_csP);        // [C] charger power, for the transformer sums
+    double *pre   = reinterpret_cast<double *>(sm + p.v_pre);        // [pre_stride] prefetched per-env records (kPre*)
+    double *wsum  = reinterpret_cast<double *>(sm + p.v_wsum);       // [G][EvlNSum + 1] per-warp partial sums, counts
+    double *trov  = reinterpret_cast<double *>(sm + p.v_trov);       // [Tr] overload per transformer
+    uint16_t *stage = reinterpret_cast<uint16_t *>(sm + p.v_stage);  // [P] by list position: port, or kEvlGone
+    unsigned char *occ = sm + p.v_occ;                               // [P] the port holds per-port results this step
+
+    const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
+    const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
+    const int t = p.env_step[e];
+    if (t >= p.T) {                                   // step() on a finished env   ev2gym_env.py:343
+        if (gtid == 0) {
+            if (p.out.reward) p.out.reward[e] = 0.0;
+            if (p.out.total_costs) p.out.total_costs[e] = 0.0;
+            if (p.out.status) p.out.status[e] = EV2B_ST_DONE | EV2B_ST_WAS_DONE;
+        }
+        return;
+    }
+    const int s = p.env_scn[e];
+    const int n_old = p.occ_n[e];
+    const int tq = t + 1;
+    float *obs_row = p.out.obs + (size_t)e * p.D;
+
+    // ---- P0: prefetch, zero the per-port flags, (scenario, time)-only observation values ----------------------
+    for (int i = gtid; i <= kPrePot; i += GT)
+        cp_async8(pre + i, i < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + i : p.env_pot + e);
+    for (int i = gtid; i < 2 + 2 * p.Tr; i += GT) {
+        if (i < 2) { if (t + i < p.T) cp_async8(pre + kPreSet + i, &p.env_t[(size_t)s * p.T + t + i].setpoint); }
+        else cp_async16(pre + kPreTr + 2 * (i - 2), reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * (i - 2));
+    }
+    const EnvT et0 = p.env_t[(size_t)s * p.T + t];
+    const int a0 = p.arr_off[(size_t)s * (p.T + 2) + tq], a1 = p.arr_off[(size_t)s * (p.T + 2) + tq + 1];
+    for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
+    if (want_obs) {
+        for (int i = gtid; i < p.W; i += GT) obs_row[p.series_off[i]] = obs_series_fetch(p, s, tq, i);
+        if (p.obs_full) {                             // the caller's buffer does not hold last step's rows: clear every tuple
+            const bool three = p.state_kind == EV2B_STATE_PUBLIC_PST;
+            for (int i = gtid; i < p.P; i += GT) {
+                float *o = obs_row + p.obs_slot[i];
+                o[0] = 0.f; o[1] = 0.f;
+                if (three) o[2] = 0.f;
+            }
+        }
+    }
+    evl_group_sync<G>(g);
+
+    // ---- EV: one thread per connected EV ------------------------------------------------------------------------
+    double aProfit = 0, aSatExp = 0, aCh = 0, aDis = 0, aSat = 0;
+    int nDep = 0;
+    const bool sat_exp = p.reward_kind == EV2B_REWARD_PROFIT_TR_USER || p.reward_kind == EV2B_REWARD_PROFIT_MAX;
+    const uint16_t *lst = p.occ_list + ((size_t)(t & 1) * p.E + e) * p.P;
+    for (int i = gtid; i < n_old; i += GT) {
+        const int port = lst[i];
+        const size_t ip = (size_t)e * p.P + port;
+        const uint4 h = p.hot[ip];
+        double cv = p.cap[ip];
+        float exch_new = p.exch[ip];
+        const double a = agent_action<ActT>(p, actions, ip, t);
+        const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
+        const CsStatic &cs = cs_of<UNI>(p, c);
+        // Sigma over the charger's occupied ports, in port order (python sum())   ev_charger.py:137-149
+        double sum = 0.0;
+        if (NP == 1) {
+            sum = sum + a;
+        } else if (NP == 2) {
+            const size_t im = ip ^ 1;                 // P is even and port offsets are 2c: the other port of this charger
+            const unsigned hx = p.hot[im].x;
+            const bool occ_m = (int)(int16_t)(hx & 0xFFFFu) <= t && t <= (int)(int16_t)(hx >> 16);
+            const double am = occ_m ? agent_action<ActT>(p, actions, im, t) : 0.0;
+            sum = sum + ((port & 1) ? am : a);
+            sum = sum + ((port & 1) ? a : am);
+        } else {
+            const int p0 = cs.port_off, n = cs.n_ports;
+            for (int j = 0; j < n; ++j) {
+                double aj = a;
+                if (p0 + j != port) {
+                    const size_t ij = (size_t)e * p.P + p0 + j;
+                    const unsigned hx = p.hot[ij].x;
+                    const bool occ_j = (int)(int16_t)(hx & 0xFFFFu) <= t && t <= (int)(int16_t)(hx >> 16);
+                    aj = occ_j ? agent_action<ActT>(p, actions, ij, t) : 0.0;
+                }
+                sum = sum + aj;
+            }
+        }
+        double an = a;
+        if (sum > 1.0) an = an / sum; else if (sum < -1.0) an = -an / sum;
+        double energy = 0.0, act_amps = 0.0, pwv = 0.0;
+        if (an != 0.0) {
+            double cap = cv;
+            bool em_cross;
+            const bool active = ev_step_item<false>(p, cs, h.z, h.w, an, cap, energy, act_amps, em_cross);
+            if (active) {                                                 // amps == 0: nothing changes  ev.py:158-163
+                cv = cap;
+                p.cap[ip] = cv;
+                exch_new = exch_new + (float)energy;                     // total_energy_exchanged  ev.py:178
+                p.exch[ip] = exch_new;
+            }
+            const double ae = fabs(energy);
+            if (an > 0.0) { aProfit += ae * et0.cp; aCh += ae; }          // ev_charger.py:178-179
+            else          { aProfit += ae * et0.dp; aDis += ae; }         // ev_charger.py:194-195
+            pwv = ev2b_div_c(energy * 60.0, p.period, p.rperiod);         // :180,196
+        }
+        pw[port] = pwv; amp[port] = act_amps;
+        double potv = 0.0;
+        if (t >= hot_t_dep(h)) {                                          // departure  ev_charger.py:209-224, ev.py:199-214
+            const double des = __ldg(&p.spec[hot_spec(h)].desired);
+            const double sat = (cv < des - 0.001) ? cv / des : 1.0;
+            if (sat_exp) aSatExp += 100.0 * exp(-10.0 * sat);             // reward.py:42,85
+            aSat += sat;
+            ++nDep;
+            stage[i] = (uint16_t)kEvlGone;
+            if (want_obs) {
+                float *o = obs_row + p.obs_slot[port];
+                o[0] = 0.f; o[1] = 0.f;
+                if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
+            }
+        } else {
+            stage[i] = (uint16_t)port;
+            const EvSpec *sp = p.spec + hot_spec(h);
+            const double B = __ldg(&sp->B);
+            if (cv < B && hot_t_dep(h) > tq) potv = __ldg(&p.pot_kw[hot_spec(h) * p.n_cls + cs.cls]);   // utils.py:766-777
+            if (want_obs) {                                               // state.py:37-57, 85-102, 137-151
+                float *o = obs_row + p.obs_slot[port];
+                if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
+                    o[0] = (cv == B) ? 1.f : 0.5f;
+                    o[1] = exch_new;
+                    o[2] = (float)(tq - hot_t_arr(h));
+                } else {
+                    o[0] = (float)ev2b_div_c(cv, B, __ldg(&sp->rB));
+                    o[1] = (float)(hot_t_dep(h) - tq);
+                }
+            }
+        }
+        pot[port] = potv;
+        occ[port] = 1;
+    }
+    evl_group_sync<G>(g);
+
+    // ---- AR: arrivals of step t+1, one thread each (the highest threads: they had the least EV work) ---------
+    const int nArr = a1 - a0;
+    for (int k = GT - 1 - gtid; k < nArr; k += GT) {                      // ev2gym_env.py:399-417, ev_charger.py:266-285
+        const unsigned u = p.arr_list[a0 + k];
+        const int port = (int)(u & 0xFFFFu), cur = (int)(u >> 16);
+        const size_t ip = (size_t)e * p.P + port;
+        const SessRec r = p.sess[((size_t)s * p.P + port) * p.Smax + cur];
+        p.hot[ip] = r.hot;
+        p.cap[ip] = r.cap0;
+        p.exch[ip] = 0.f;
+        const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
+        const CsStatic &cs = cs_of<UNI>(p, c);
+        const EvSpec *sp = p.spec + hot_spec(r.hot);
+        const double B = __ldg(&sp->B);
+        double potv = 0.0;
+        if (r.cap0 < B && hot_t_dep(r.hot) > tq) potv = __ldg(&p.pot_kw[hot_spec(r.hot) * p.n_cls + cs.cls]);
+        if (!occ[port]) { pw[port] = 0.0; amp[port] = 0.0; }             // (an EV may have left this very port in step t)
+        pot[port] = potv;
+        occ[port] = 1;
+        if (want_obs) {
+            float *o = obs_row + p.obs_slot[port];
+            if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
+                o[0] = (r.cap0 == B) ? 1.f : 0.5f;
+                o[1] = 0.f;
+                o[2] = (float)(tq - hot_t_arr(r.hot));
+            } else {
+                o[0] = (float)ev2b_div_c(r.cap0, B, __ldg(&sp->rB));
+                o[1] = (float)(hot_t_dep(r.hot) - tq);
+            }
+        }
+    }
+    evl_group_sync<G>(g);
+
+    // ---- CS: one thread per charger, ports in order -------------------------------------------------------------
+    double aUsage = 0, aPot = 0;
+    bool overflow = false;
+    for (int c = gtid; c < p.C; c += GT) {
+        const CsStatic &cs = cs_of<UNI>(p, c);
+        const int p0 = NP > 0 ? c * NP : cs.port_off, n = NP > 0 ? NP : cs.n_ports;
+        double rP = 0, rA = 0, rPot = 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            if (occ[p0 + j]) { rP += pw[p0 + j]; rA += amp[p0 + j]; rPot += pot[p0 + j]; }
+            if (rA - 0.0001 > cs.imax) overflow = true;                   // ev_charger.py:203-205
+        }
+        if (rPot > cs.max_power) rPot = cs.max_power;                     // utils.py:779-789
+        else if (rPot < cs.min_power) rPot = 0.0;
+        csP[c] = rP;
+        aUsage += rP; aPot += rPot;
+        if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
+        if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
+    }
+    // per-warp partial sums (fixed xor tree); the group total is formed warp by warp below
+    double q[EvlNSum] = {aProfit, aSatExp, aCh, aDis, aSat, aUsage, aPot};
+#pragma unroll
+    for (int k = 0; k < EvlNSum; ++k) q[k] = warp_sum(q[k]);
+    int cnts = warp_sum_i(nDep | (overflow ? 1 << 20 : 0));               // departures < 2^20; overflow votes above
+    if (G > 1) {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < EvlNSum; ++k) wsum[gw * (EvlNSum + 1) + k] = q[k];
+            reinterpret_cast<int *>(wsum + gw * (EvlNSum + 1) + EvlNSum)[0] = cnts;
+        }
+    }
+    cp_async_wait_all();
+    evl_group_sync<G>(g);
+
+    // ---- LS: the group's last warp writes next step's list: kept EVs in list order, then the arrivals ----------
+    if (gw == G - 1) {
+        uint16_t *nxt = p.occ_list + ((size_t)(tq & 1) * p.E + e) * p.P;
+        int base = 0;
+        for (int i0 = 0; i0 < n_old; i0 += 32) {
+            const int i = i0 + lane;
+            const unsigned v = i < n_old ? (unsigned)stage[i] : kEvlGone;
+            const unsigned m = __ballot_sync(0xffffffffu, v != kEvlGone);
+            if (v != kEvlGone) nxt[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)v;
+            base += __popc(m);
+        }
+        for (int k = lane; k < nArr; k += 32) nxt[base + k] = (uint16_t)(p.arr_list[a0 + k] & 0xFFFFu);
+        if (lane == 0) p.occ_n[e] = base + nArr;
+    }
+    if (gw != 0) return;
+
+    // ---- TR: transformer sums + overload (warp 0), same lane split as step_kernel's phase B ---------------------
+    if (G > 1) {
+#pragma unroll
+        for (int k = 0; k < EvlNSum; ++k) {
+            double v = wsum[k];
+            for (int w = 1; w < G; ++w) v += wsum[w * (EvlNSum + 1) + k];
+            q[k] = v;
+        }
+        cnts = 0;
+        for (int w = 0; w < G; ++w) cnts += reinterpret_cast<const int *>(wsum + w * (EvlNSum + 1) + EvlNSum)[0];
+    }
+    {
+        int nseg = 1;
+        while (nseg * 2 * p.Tr <= 32) nseg *= 2;
+        const int per = 32 / nseg;
+        for (int k0 = 0; k0 < p.Tr; k0 += per) {
+            const int k = k0 + lane / nseg, seg = lane & (nseg - 1);
+            double sp_ = 0.0;
+            if (k < p.Tr && lane / nseg < per) {
+                const int i0 = p.tr_cs_off[k], n_k = p.tr_cs_off[k + 1] - i0;
+                const int chunk = (n_k + nseg - 1) / nseg;
+                const int lo = seg * chunk, hi = min(n_k, lo + chunk);
+                for (int i = lo; i < hi; ++i) sp_ += csP[p.tr_cs_idx[i0 + i]];
+            }
+            for (int o = nseg >> 1; o > 0; o >>= 1) sp_ += __shfl_xor_sync(0xffffffffu, sp_, o);
+            if (seg == 0 && k < p.Tr && lane / nseg < per) {              // transformer.py:264-302
+                const double *tq4 = pre + kPreTr + 4 * k;
+                const double ptot = (tq4[0] + tq4[1]) + sp_;
+                double ov = 0.0;
+                if (ptot > tq4[2] + 0.0001 || ptot < tq4[3] - 0.0001) ov = fabs(ptot - tq4[2]);
+                trov[k] = ov;
+                if (p.out.tr_power)    p.out.tr_power[(size_t)e * p.Tr + k] = ptot;
+                if (p.out.tr_overload) p.out.tr_overload[(size_t)e * p.Tr + k] = ov;
+            }
+        }
+        __syncwarp();
+    }
+    // ---- reward, KPI sums, step counter: one lane (same statements as step_kernel's phase C) -----------------
+    if (lane == 0) {
+        unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
+        const int n_dep = cnts & 0xFFFFF;
+        const double setpoint = pre[kPreSet];
+        const double usage = q[EvlUsage];                                 // current_power_usage[t]  ev2gym_env.py:375
+        const double costs = q[EvlProfit];
+        double ovsum = 0.0;
+        for (int k = 0; k < p.Tr; ++k) ovsum += trov[k];
+        double reward = 0.0;
+        if (p.reward_kind == EV2B_REWARD_SQ_TRACKING) {                   // reward.py:11-12
+            const double potn = pre[kPrePot];
+            const double m = setpoint < potn ? setpoint : potn;
+            reward = -((m - usage) * (m - usage));
+        } else if (p.reward_kind == EV2B_REWARD_PROFIT_TR_USER) {         // reward.py:36-44
+            reward = costs - 100.0 * ovsum - q[EvlSatExp];
+        } else if (p.reward_kind == EV2B_REWARD_PROFIT_MAX) {             // reward.py:81-87
+            reward = costs - q[EvlSatExp];
+        }
+        double *kpi = p.env_kpi + (size_t)e * EV2B_KPI_COUNT;
+        kpi[EV2B_KPI_TOTAL_REWARD] = pre[EV2B_KPI_TOTAL_REWARD] + reward;
+        kpi[EV2B_KPI_TOTAL_PROFITS] = pre[EV2B_KPI_TOTAL_PROFITS] + costs;
+        kpi[EV2B_KPI_ENERGY_CHARGED] = pre[EV2B_KPI_ENERGY_CHARGED] + q[EvlCharged];
+        kpi[EV2B_KPI_ENERGY_DISCHARGED] = pre[EV2B_KPI_ENERGY_DISCHARGED] + q[EvlDischarged];
+        kpi[EV2B_KPI_TR_OVERLOAD] = pre[EV2B_KPI_TR_OVERLOAD] + ovsum;
+        kpi[EV2B_KPI_EVS_SERVED] = pre[EV2B_KPI_EVS_SERVED] + (double)n_dep;
+        kpi[EV2B_KPI_SAT_SUM] = pre[EV2B_KPI_SAT_SUM] + q[EvlSatSum];
+        const double d = setpoint - usage;                                // utils.py:37-44
+        kpi[EV2B_KPI_TRACKING_ERROR] = pre[EV2B_KPI_TRACKING_ERROR] + d * d;
+        kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] = pre[EV2B_KPI_ENERGY_TRACKING_ERROR] + fabs(d);
+        if (usage > setpoint) kpi[EV2B_KPI_TRACKER_VIOLATION] = pre[EV2B_KPI_TRACKER_VIOLATION] + (usage - setpoint);
+        kpi[EV2B_KPI_EVS_SPAWNED] = pre[EV2B_KPI_EVS_SPAWNED] + (double)nArr;
+        kpi[EV2B_KPI_INVALID_ACTIONS] = pre[EV2B_KPI_INVALID_ACTIONS] + (double)(p.P - n_old);   // every empty port  ev_charger.py:137-140
+        kpi[EV2B_KPI_STEPS] = pre[EV2B_KPI_STEPS] + 1.0;
+        p.env_pot[e] = (tq < p.T) ? q[EvlPot] : 0.0;                      // ev2gym_env.py:424-426
+        p.env_usage[e] = usage;
+        p.env_step[e] = tq;
+        if (tq >= p.T) status |= EV2B_ST_DONE;                            // ev2gym_env.py:460
+        if (want_obs) obs_header(p, obs_row, s, tq, usage, pre[kPreSetNext]);
+        if (p.out.reward) p.out.reward[e] = reward;
+        if (p.out.total_costs) p.out.total_costs[e] = costs;
+        if (p.out.status) p.out.status[e] = status;
+    }
+}
+
+}  // namespace ev2b

@@ -317,6 +317,10 @@ class BatchedEngine:
     def launch_count(self) -> int:
         return int(self.L.ev2b_launch_count(self.h))
 
+    def kernel_launches(self):
+        """Step launches by kernel: (step_kernel, evl_step_kernel, evl_rebuild_kernel)  -- include/ev2b.h."""
+        return tuple(int(self.L.ev2b_kernel_launches(self.h, k)) for k in range(3))
+
     @staticmethod
     def decode_hot(hot: np.ndarray) -> Dict[str, np.ndarray]:
         """Unpack the [.,4] int32 hot words into t_arr / t_dep / next_arr / spec fields."""

@@ -247,6 +247,9 @@ int  ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *out);
 int  ev2b_episode_stats(ev2b_handle *h, double *out, void *stream);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t ev2b_launch_count(const ev2b_handle *h);
+/* step launches by kernel: which = 0 step_kernel (thread per charger), 1 evl_step_kernel (thread per connected EV,
+ * handles created under EV2B_KERNEL=evlist, see ev2b_evlist.cuh), 2 evl_rebuild_kernel (list re-derivation) */
+int64_t ev2b_kernel_launches(const ev2b_handle *h, int which);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,8 @@ def lib():
                                   C.POINTER(_lib.StepOut), C.c_void_p]
         L.ev2b_launch_count.restype = C.c_int64
         L.ev2b_launch_count.argtypes = [C.c_void_p]
+        L.ev2b_kernel_launches.restype = C.c_int64
+        L.ev2b_kernel_launches.argtypes = [C.c_void_p, C.c_int]
         _L = L
     return _L
 
@@ -153,6 +155,10 @@ class EmuEngine:
         self._check(self.L.ev2b_step_k(self.h, int(k), kind, ptr, dt, int(seed), low, int(auto_reset),
                                        C.byref(self._so), None), "ev2b_step_k")
         return self.out
+
+    def kernel_launches(self):
+        """(step_kernel, evl_step_kernel, evl_rebuild_kernel) launches of this handle."""
+        return tuple(int(self.L.ev2b_kernel_launches(self.h, k)) for k in range(3))
 
     def state(self) -> Dict[str, np.ndarray]:
         sv = self._lib.StateView()

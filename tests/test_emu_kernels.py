@@ -1,0 +1,298 @@
+"""CPU-side checks of the CUDA kernels' LOGIC: ev2gym_b200/csrc compiled by g++ against the SIMT emulator in
+tests/simt_emu (every CUDA thread a fiber; barriers, warp collectives, deferred cp.async, guard pages) and driven
+through the same C ABI as libev2b.so, against the C oracle and the recorded reference traces.
+
+This is test infrastructure: it proves indexing / barrier placement / list maintenance of the device code without a
+GPU.  The parity tests proper are the `-m gpu` ones (tests/test_gpu_*.py); nothing in the product imports this.
+
+Bars: battery level, list contents, counts, flags: bit-exact; float64 outputs 1e-9 relative; float32 outputs 1e-5.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt_emu"))
+
+LEAN_REWARDS = ("SquaredTrackingErrorReward", "ProfitMax_TrPenalty_UserIncentives", "profit_maximization", "none", "None")
+OUT = ("reward", "status", "obs", "tr_power", "tr_overload", "cs_power", "cs_current", "total_costs")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu_engine
+    emu_engine.build()
+    return emu_engine
+
+
+def _close(a, b, rtol, atol=0.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= atol + rtol * np.abs(b))
+
+
+def _occupied_ports(eng, e):
+    st = eng.state()
+    from ev2gym_b200.engine import BatchedEngine
+    hot = BatchedEngine.decode_hot(st["port_hot"][e])
+    t = int(st["env_step"][e])
+    return np.nonzero((hot["t_arr"] <= t) & (t <= hot["t_dep"]))[0]
+
+
+def _run_vs_oracle(emu, topo, bank, E, reward, state, adt, kernel, G=None, outputs=OUT, steps=None, switch=None,
+                   monkeypatch=None):
+    """Steps an emulated engine and the oracle side by side; `switch(t)` -> True asks for a per-port output on step t
+    (which the event-driven kernel does not cover: that launch takes step_kernel and the list must be rebuilt)."""
+    from oracle.oracle import OracleBatch
+    monkeypatch.setenv("EV2B_KERNEL", kernel)
+    if G:
+        monkeypatch.setenv("EV2B_EVL_G", str(G))
+    eng = emu.EmuEngine(topo, E, reward=reward, state=state, outputs=outputs)
+    eng.load_scenarios(bank)
+    scn_ids = [(3 * e + 1) % len(bank) for e in range(E)]
+    obs0 = eng.reset(scn_ids=scn_ids)
+    orc = OracleBatch(topo, [bank[i] for i in scn_ids], reward=reward, state=state)
+    o0 = orc.reset()
+    if eng.D:
+        assert _close(obs0, o0, 1e-5, 1e-5)
+    caps = eng.state()["port_cap"]
+    rng = np.random.default_rng(99)
+    Tr = topo.Tr
+    for t in range(steps or topo.T):
+        a = rng.uniform(-1, 1, (E, topo.P))
+        a[rng.random((E, topo.P)) < 0.1] = 0.0
+        if t % 9 == 4:
+            a[:] = 1.0                      # everybody saturates: sum > 1 on shared chargers
+        a = np.ascontiguousarray(a.astype(adt))
+        if switch is not None:
+            eng.set_outputs(outputs + (("action_mask",) if switch(t) else ()))
+        out = eng.step(a)
+        orc.step(a.astype(np.float64))
+        occ = orc.arr["port_session"] >= 0
+        assert np.array_equal(caps[occ], orc.arr["port_cap"][occ]), (t, "battery level")       # bit exact
+        assert _close(out["reward"], orc.reward, 1e-9, 1e-9), (t, "reward", out["reward"], orc.reward)
+        assert _close(out["total_costs"], [o.total_costs for o in orc.outs], 1e-9, 1e-12), (t, "costs")
+        assert _close(out["tr_power"], orc.o["tr_power"][:, :Tr], 1e-9, 1e-9), (t, "tr_power")
+        assert _close(out["tr_overload"], orc.o["tr_overload"][:, :Tr], 1e-9, 1e-9), (t, "tr_overload")
+        assert _close(out["cs_power"], orc.o["cs_power"], 1e-5, 1e-6), (t, "cs_power")
+        assert _close(out["cs_current"], orc.o["cs_current"], 1e-5, 1e-6), (t, "cs_current")
+        if eng.D and (switch is None):      # (a fresh obs tensor every step would force full rewrites: checked separately)
+            assert _close(out["obs"], orc.o["obs"][:, :eng.D], 1e-5, 1e-5), (t, "obs")
+        assert np.array_equal((out["status"] & 1) > 0, orc.done > 0), (t, "done")
+        ovf = np.array([o.error == 1 for o in orc.outs])
+        assert np.array_equal((out["status"] & 2) > 0, ovf), (t, "amps overflow flag")
+        for e in (0, E - 1):                # the engine's own occupancy (hot words) agrees with the oracle's
+            if not orc.done[e]:
+                assert np.array_equal(_occupied_ports(eng, e), np.nonzero(occ[e])[0]), (t, e, "occupancy")
+    kpi = eng.state()["env_kpi"]
+    from ev2gym_b200.engine import KPI_NAMES
+    k = {n: kpi[:, i] for i, n in enumerate(KPI_NAMES)}
+    assert _close(k["total_reward"], [s.total_reward for s in orc.states], 1e-9, 1e-9)
+    assert np.array_equal(k["total_evs_spawned"], [float(s.total_evs_spawned) for s in orc.states])
+    return eng, orc
+
+
+SHAPES = [  # C, n_ports, Tr, E, reward, state, action dtype
+    (25, 1, 1, 7, "SquaredTrackingErrorReward", "PublicPST", "float32"),
+    (40, 2, 5, 5, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", "float32"),
+    (150, 1, 1, 3, "profit_maximization", "V2G_profit_max", "float64"),
+    (7, 3, 2, 9, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", "float64"),
+]
+
+
+def _bank(C, n, Tr, T=48, n_scn=5):
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    topo = Topology.uniform(C=C, n_ports=n, Tr=Tr, T=T, imin=6.0 if n == 3 else 0.0)
+    return topo, sample_bank(topo, n_scn, seed=C + n, min_stay=5)
+
+
+def test_emulator_runs_step_kernel_like_the_gpu(emu, monkeypatch):
+    """The emulator itself: step_kernel (GPU-verified) must reproduce the oracle under emulation too."""
+    topo, bank = _bank(40, 2, 5)
+    eng, _ = _run_vs_oracle(emu, topo, bank, 5, SHAPES[1][4], SHAPES[1][5], "float32", "percharger", monkeypatch=monkeypatch)
+    assert eng.kernel_launches() == (topo.T, 0, 0)
+    eng.close()
+
+
+@pytest.mark.parametrize("G", [1, 2, 4])
+@pytest.mark.parametrize("C,n,Tr,E,reward,state,adt", SHAPES)
+def test_evlist_kernel_matches_oracle(emu, C, n, Tr, E, reward, state, adt, G, monkeypatch):
+    topo, bank = _bank(C, n, Tr)
+    eng, _ = _run_vs_oracle(emu, topo, bank, E, reward, state, adt, "evlist", G=G, monkeypatch=monkeypatch)
+    assert eng.kernel_launches() == (0, topo.T, 0)          # every launch took the event-driven kernel
+    eng.close()
+
+
+def test_evlist_random_thread_schedule(emu, monkeypatch):
+    """Same run with the emulator resuming threads in a seeded random order at every barrier round."""
+    monkeypatch.setenv("SIMT_EMU_SEED", "5")
+    topo, bank = _bank(40, 2, 5)
+    eng, _ = _run_vs_oracle(emu, topo, bank, 5, SHAPES[1][4], SHAPES[1][5], "float32", "evlist", G=2, monkeypatch=monkeypatch)
+    eng.close()
+
+
+@pytest.mark.parametrize("G", [1, 4])
+def test_evlist_list_is_the_set_of_connected_ports(emu, G, monkeypatch):
+    """occ_list / occ_n after every step == the ports whose hot words say an EV is connected (stable order: EVs that
+    stay keep their relative order, arrivals are appended in schedule order)."""
+    import ctypes as C
+    from ev2gym_b200.engine import BatchedEngine
+    topo, bank = _bank(40, 2, 5)
+    monkeypatch.setenv("EV2B_KERNEL", "evlist")
+    monkeypatch.setenv("EV2B_EVL_G", str(G))
+    E = 4
+    eng = emu.EmuEngine(topo, E, reward="profit_maximization", state="V2G_profit_max", outputs=("reward", "status"))
+    eng.load_scenarios(bank)
+    eng.reset()
+    rng = np.random.default_rng(3)
+    L = eng.L
+    L.ev2b_debug_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.ev2b_debug_list.restype = C.c_int
+    prev = [[] for _ in range(E)]
+    for t in range(topo.T - 1):
+        eng.step(np.ascontiguousarray(rng.uniform(-1, 1, (E, topo.P)).astype(np.float32)))
+        for e in range(E):
+            buf = np.zeros(topo.P, dtype=np.uint16)
+            n = L.ev2b_debug_list(eng.h, e, buf.ctypes.data)
+            got = [int(x) for x in buf[:n]]
+            want = set(int(x) for x in _occupied_ports(eng, e))
+            assert set(got) == want and len(got) == len(want), (t, e)
+            t_arr = BatchedEngine.decode_hot(eng.state()["port_hot"][e])["t_arr"]
+            ident = [(x, int(t_arr[x])) for x in got]                    # (port, arrival step) names a session
+            kept = [x for x in prev[e] if x in ident]
+            assert ident[:len(kept)] == kept, (t, e, "EVs that stay keep their order")
+            assert all(ta == t + 1 for _, ta in ident[len(kept):]), (t, e, "then this step's arrivals")
+            prev[e] = ident
+    eng.close()
+
+
+def test_evlist_and_step_kernel_interleave(emu, monkeypatch):
+    """Launches that ask for a per-port output take step_kernel; the next event-driven launch re-derives the list."""
+    topo, bank = _bank(40, 2, 5)
+    eng, _ = _run_vs_oracle(emu, topo, bank, 5, SHAPES[1][4], SHAPES[1][5], "float32", "evlist", G=2,
+                            switch=lambda t: t % 5 in (1, 2), monkeypatch=monkeypatch)
+    a, b, c = eng.kernel_launches()
+    assert a > 0 and b > 0 and c > 0 and a + b == topo.T
+    eng.close()
+
+
+@pytest.mark.parametrize("kernel", ["percharger", "evlist"])
+def test_emulated_kernels_agree_bitwise_on_state(emu, kernel, monkeypatch):
+    """Both kernels leave identical hot / cap / exch arrays (they are interchangeable launch by launch)."""
+    topo, bank = _bank(30, 2, 3)
+    states = {}
+    for kn in ("percharger", kernel):
+        monkeypatch.setenv("EV2B_KERNEL", kn)
+        eng = emu.EmuEngine(topo, 4, reward="ProfitMax_TrPenalty_UserIncentives", state="V2G_profit_max_loads")
+        eng.load_scenarios(bank)
+        eng.reset()
+        rng = np.random.default_rng(1)
+        obs = []
+        for t in range(topo.T):
+            out = eng.step(np.ascontiguousarray(rng.uniform(-1, 1, (4, topo.P)).astype(np.float32)))
+            obs.append(out["obs"].copy())
+        st = eng.state()
+        states[kn] = (st["port_hot"].copy(), st["port_cap"].copy(), st["port_exch"].copy(), np.stack(obs),
+                      st["env_kpi"].copy())
+        eng.close()
+    a, b = states["percharger"], states[kernel]
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(x, y)
+    assert _close(a[4], b[4], 1e-12, 1e-12)
+
+
+def test_evlist_auto_reset_step_k_and_host_chunks(emu, monkeypatch):
+    """ev2b_step_k with the on-device UNIFORM agent + auto reset, and ev2b_step_host (two env chunks), on the
+    event-driven kernel, against the same calls on step_kernel."""
+    topo, bank = _bank(30, 2, 3, T=24)
+    res = {}
+    for kn in ("percharger", "evlist"):
+        monkeypatch.setenv("EV2B_KERNEL", kn)
+        monkeypatch.setenv("EV2B_EVL_G", "2")
+        eng = emu.EmuEngine(topo, 6, reward="ProfitMax_TrPenalty_UserIncentives", state="V2G_profit_max_loads")
+        eng.load_scenarios(bank)
+        eng.reset()
+        eng.step_k(40, agent="uniform", seed=11, auto_reset=True)        # crosses an episode boundary (T = 24)
+        st = eng.state()
+        snap = [st["port_hot"].copy(), st["port_cap"].copy(), st["env_step"].copy(), st["env_scn"].copy(),
+                eng.out["obs"].copy()]
+        rng = np.random.default_rng(4)
+        rew, stat, obs = np.zeros(6), np.zeros(6, dtype=np.uint32), np.zeros((6, eng.D), dtype=np.float32)
+        for t in range(5):
+            eng.step_host(np.ascontiguousarray(rng.uniform(-1, 1, (6, topo.P))), rew, stat, obs)
+        snap += [st["port_cap"].copy(), rew.copy(), stat.copy(), obs.copy()]
+        res[kn] = snap
+        if kn == "evlist":
+            assert eng.kernel_launches()[0] == 0
+        eng.close()
+    for i, (x, y) in enumerate(zip(res["percharger"], res["evlist"])):
+        if x.dtype.kind == "f" and i in (4, 6, 8):
+            assert _close(x, y, 1e-6, 1e-6), i
+        else:
+            assert np.array_equal(x, y), i
+
+
+def test_evlist_ragged_chargers(emu, monkeypatch):
+    """Chargers with different port counts and ratings (topology-JSON case): the generic instantiation."""
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    topo = Topology.uniform(C=12, n_ports=2, Tr=3, T=40)
+    topo.cs_n_ports[:] = [1, 3, 2, 2, 4, 1, 2, 3, 1, 2, 2, 1]
+    topo.cs_imax[::2] = 16.0
+    bank = sample_bank(topo, 4, seed=5, min_stay=5)
+    eng, _ = _run_vs_oracle(emu, topo, bank, 5, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", "float64",
+                            "evlist", G=1, monkeypatch=monkeypatch)
+    assert eng.kernel_launches() == (0, topo.T, 0)
+    eng.close()
+
+
+def _lean_golden():
+    out = []
+    for name in golden_cases():
+        tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+        if str(tr["reward_fn"]) in LEAN_REWARDS and not name.startswith("grid"):
+            out.append(name)
+    return out
+
+
+@pytest.mark.parametrize("name", _lean_golden())
+def test_evlist_kernel_matches_reference_trace(emu, name, monkeypatch):
+    """The recorded episodes of the Python reference (tests/golden) through the event-driven kernel."""
+    from ev2gym_b200.scenario import ScenarioPack
+    monkeypatch.setenv("EV2B_KERNEL", "evlist")
+    pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
+    tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+    topo = pack.topo
+    E = 3
+    eng = emu.EmuEngine(topo, E, reward=str(tr["reward_fn"]), state=str(tr["state_fn"]), outputs=OUT)
+    eng.load_scenarios(pack.scenarios)
+    obs0 = eng.reset()
+    assert _close(obs0[0], tr["obs0"], 1e-5, 1e-6)
+    st = eng.state()
+    T = tr["reward"].shape[0]
+    for t in range(T):
+        out = eng.step(np.ascontiguousarray(np.tile(tr["actions"][t], (E, 1)).astype(np.float64)))
+        for e in (0, E - 1):
+            occ = tr["action_mask"][t] > 0
+            assert np.array_equal(_occupied_ports(eng, e), np.nonzero(occ)[0]) or bool(tr["done"][t]), (t, "occupancy")
+            assert np.array_equal(st["port_cap"][e][occ], tr["cap"][t][occ]), (t, "cap")
+            assert _close(out["reward"][e], tr["reward"][t], 1e-9, 1e-9), (t, out["reward"][e], tr["reward"][t])
+            assert _close(out["total_costs"][e], tr["total_costs"][t], 1e-9, 1e-12)
+            assert _close(out["tr_power"][e], tr["tr_power"][t], 1e-9, 1e-9)
+            assert _close(out["tr_overload"][e], tr["tr_overload"][t], 1e-9, 1e-9)
+            assert _close(out["cs_power"][e], tr["cs_power"][t], 1e-5, 1e-6)
+            assert _close(out["cs_current"][e], tr["cs_current"][t], 1e-5, 1e-6)
+            assert _close(out["obs"][e], tr["obs"][t], 1e-5, 1e-5), (t, "obs")
+            assert bool(out["status"][e] & 1) == bool(tr["done"][t])
+    from ev2gym_b200.engine import KPI_NAMES
+    k = {n: st["env_kpi"][:, i] for i, n in enumerate(KPI_NAMES)}
+    assert k["total_reward"][0] == pytest.approx(float(tr["total_reward"]), rel=1e-9, abs=1e-9)
+    assert k["total_ev_served"][0] == float(tr["stat_total_ev_served"])
+    assert k["total_energy_charged"][0] == pytest.approx(float(tr["stat_total_energy_charged"]), rel=1e-9)
+    assert eng.kernel_launches() == (0, T, 0)
+    out = eng.step(np.zeros((E, topo.P)))      # stepping a finished env: WAS_DONE, reward 0 (ev2gym_env.py:343)
+    assert int(out["status"][0]) & 4 and float(out["reward"][0]) == 0.0
+    eng.close()
