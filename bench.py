@@ -396,7 +396,10 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_env_step,
-                         "kernel": "ev2b::step_kernel", "launch_ms": launch_ms},
+                         "kernel": "ev2b::evl_step_kernel" if engines[0].kernel_launches()[1] else "ev2b::step_kernel",
+                         "kernel_launches": dict(zip(("step_kernel", "evl_step_kernel", "evl_rebuild_kernel"),
+                                                     engines[0].kernel_launches())),
+                         "launch_ms": launch_ms},
             "kpi_allreduce": {"total_reward": float(kpi[0].item()), "total_evs_served": float(kpi[5].item())},
             "device_agent_rollout": {"value": agent_rate, "unit": "env-steps/s per GPU",
                                      "what": "ev2b_step_k, UNIFORM on-device agent, one call per episode and env group"},

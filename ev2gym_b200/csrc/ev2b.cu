@@ -98,7 +98,7 @@ struct ev2b_handle {
         take(8 * (size_t)P, 16);                                   // pw
         evl_o[1] = take(8 * (size_t)P, 8); evl_o[2] = take(8 * (size_t)P, 8); evl_o[3] = take(8 * (size_t)C, 8);   // amp, pot, csP
         evl_o[4] = take(8 * (size_t)(kPreTr + 4 * Tr), 16);        // pre (cp.async 16 B destinations)
-        evl_o[5] = take(8 * (size_t)(EvlNSum + 1) * evl_G, 8);     // wsum
+        evl_o[5] = take(8 * (size_t)EvlNSum * evl_G, 8);           // wsum
         evl_o[6] = take(8 * (size_t)Tr, 8);                        // trov
         evl_o[7] = take(2 * (size_t)P, 4);                         // stage
         evl_o[8] = take(((size_t)P + 3) / 4 * 4, 4);               // occ

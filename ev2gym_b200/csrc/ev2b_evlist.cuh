@@ -29,7 +29,31 @@ namespace ev2b {
 
 constexpr int kEvlThreads = 128;
 constexpr unsigned kEvlGone = 0xFFFFu;       // staging mark: this EV left during the step
-enum { EvlProfit = 0, EvlSatExp, EvlCharged, EvlDischarged, EvlSatSum, EvlUsage, EvlPot, EvlNSum };
+enum { EvlProfit = 0, EvlSatExp, EvlCharged, EvlDischarged, EvlSatSum, EvlUsage, EvlPot, EvlCounts, EvlNSum };
+static_assert(EvlNSum == 8, "warp_sum8 reduces exactly 8 quantities");
+
+// Warp totals of 8 per-lane values in 9 exchanges instead of 40 (a reduce-scatter butterfly: at distance 16 every lane
+// keeps 4 of the 8 quantities and hands the other 4 to its partner, at 8 it keeps 2, at 4 one; distances 2 and 1 are
+// plain).  Returns, in lane L, the total of quantity 4*bit4(L) + 2*bit3(L) + bit2(L); the order of additions is fixed.
+__device__ __forceinline__ double warp_sum8(const double (&q)[8], int lane) {
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    double a[4], b[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double send = h16 ? q[j] : q[j + 4], keep = h16 ? q[j + 4] : q[j];
+        a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const double send = h8 ? a[j] : a[j + 2], keep = h8 ? a[j + 2] : a[j];
+        b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const double send = h4 ? b[0] : b[1], keep = h4 ? b[1] : b[0];
+    double c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
 
 __device__ __forceinline__ void evl_bar_sync(int id, int nthreads) {
 #ifdef EV2B_SIMT_EMU
@@ -82,7 +106,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     double *pot   = reinterpret_cast<double *>(sm + p.v_pot);        // [P] its charge-power potential for step t+1
     double *csP   = reinterpret_cast<double *>(sm + p.v_csP);        // [C] charger power, for the transformer sums
     double *pre   = reinterpret_cast<double *>(sm + p.v_pre);        // [pre_stride] prefetched per-env records (kPre*)
-    double *wsum  = reinterpret_cast<double *>(sm + p.v_wsum);       // [G][EvlNSum + 1] per-warp partial sums, counts
+    double *wsum  = reinterpret_cast<double *>(sm + p.v_wsum);       // [G][EvlNSum] per-warp partial sums (the last one holds counts)
     double *trov  = reinterpret_cast<double *>(sm + p.v_trov);       // [Tr] overload per transformer
     uint16_t *stage = reinterpret_cast<uint16_t *>(sm + p.v_stage);  // [P] by list position: port, or kEvlGone
     unsigned char *occ = sm + p.v_occ;                               // [P] the port holds per-port results this step
@@ -104,19 +128,23 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     float *obs_row = p.out.obs + (size_t)e * p.D;
 
     // ---- P0: prefetch, zero the per-port flags, (scenario, time)-only observation values ----------------------
+#pragma unroll 1
     for (int i = gtid; i <= kPrePot; i += GT)
         cp_async8(pre + i, i < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + i : p.env_pot + e);
+#pragma unroll 1
     for (int i = gtid; i < 2 + 2 * p.Tr; i += GT) {
         if (i < 2) { if (t + i < p.T) cp_async8(pre + kPreSet + i, &p.env_t[(size_t)s * p.T + t + i].setpoint); }
         else cp_async16(pre + kPreTr + 2 * (i - 2), reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * (i - 2));
     }
     const EnvT et0 = p.env_t[(size_t)s * p.T + t];
     const int a0 = p.arr_off[(size_t)s * (p.T + 2) + tq], a1 = p.arr_off[(size_t)s * (p.T + 2) + tq + 1];
+#pragma unroll 1
     for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
     if (want_obs) {
         for (int i = gtid; i < p.W; i += GT) obs_row[p.series_off[i]] = obs_series_fetch(p, s, tq, i);
         if (p.obs_full) {                             // the caller's buffer does not hold last step's rows: clear every tuple
             const bool three = p.state_kind == EV2B_STATE_PUBLIC_PST;
+#pragma unroll 1
             for (int i = gtid; i < p.P; i += GT) {
                 float *o = obs_row + p.obs_slot[i];
                 o[0] = 0.f; o[1] = 0.f;
@@ -131,6 +159,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     int nDep = 0;
     const bool sat_exp = p.reward_kind == EV2B_REWARD_PROFIT_TR_USER || p.reward_kind == EV2B_REWARD_PROFIT_MAX;
     const uint16_t *lst = p.occ_list + ((size_t)(t & 1) * p.E + e) * p.P;
+#pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
         const int port = lst[i];
         const size_t ip = (size_t)e * p.P + port;
@@ -220,6 +249,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
 
     // ---- AR: arrivals of step t+1, one thread each (the highest threads: they had the least EV work) ---------
     const int nArr = a1 - a0;
+#pragma unroll 1
     for (int k = GT - 1 - gtid; k < nArr; k += GT) {                      // ev2gym_env.py:399-417, ev_charger.py:266-285
         const unsigned u = p.arr_list[a0 + k];
         const int port = (int)(u & 0xFFFFu), cur = (int)(u >> 16);
@@ -254,6 +284,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     // ---- CS: one thread per charger, ports in order -------------------------------------------------------------
     double aUsage = 0, aPot = 0;
     bool overflow = false;
+#pragma unroll 1
     for (int c = gtid; c < p.C; c += GT) {
         const CsStatic &cs = cs_of<UNI>(p, c);
         const int p0 = NP > 0 ? c * NP : cs.port_off, n = NP > 0 ? NP : cs.n_ports;
@@ -270,17 +301,12 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
         if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
     }
-    // per-warp partial sums (fixed xor tree); the group total is formed warp by warp below
-    double q[EvlNSum] = {aProfit, aSatExp, aCh, aDis, aSat, aUsage, aPot};
-#pragma unroll
-    for (int k = 0; k < EvlNSum; ++k) q[k] = warp_sum(q[k]);
-    int cnts = warp_sum_i(nDep | (overflow ? 1 << 20 : 0));               // departures < 2^20; overflow votes above
-    if (G > 1) {
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < EvlNSum; ++k) wsum[gw * (EvlNSum + 1) + k] = q[k];
-            reinterpret_cast<int *>(wsum + gw * (EvlNSum + 1) + EvlNSum)[0] = cnts;
-        }
+    // per-warp partial sums (fixed butterfly); the group total is formed warp by warp in the reward phase
+    {
+        const double q[EvlNSum] = {aProfit, aSatExp, aCh, aDis, aSat, aUsage, aPot,
+                                   (double)nDep + (overflow ? 1048576.0 : 0.0)};   // departures < 2^20; overflow votes above
+        const double tot = warp_sum8(q, lane);
+        if ((lane & 3) == 0) wsum[gw * EvlNSum + (lane >> 2)] = tot;
     }
     cp_async_wait_all();
     evl_group_sync<G>(g);
@@ -289,6 +315,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     if (gw == G - 1) {
         uint16_t *nxt = p.occ_list + ((size_t)(tq & 1) * p.E + e) * p.P;
         int base = 0;
+#pragma unroll 1
         for (int i0 = 0; i0 < n_old; i0 += 32) {
             const int i = i0 + lane;
             const unsigned v = i < n_old ? (unsigned)stage[i] : kEvlGone;
@@ -296,22 +323,13 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             if (v != kEvlGone) nxt[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)v;
             base += __popc(m);
         }
+#pragma unroll 1
         for (int k = lane; k < nArr; k += 32) nxt[base + k] = (uint16_t)(p.arr_list[a0 + k] & 0xFFFFu);
         if (lane == 0) p.occ_n[e] = base + nArr;
     }
     if (gw != 0) return;
 
     // ---- TR: transformer sums + overload (warp 0), same lane split as step_kernel's phase B ---------------------
-    if (G > 1) {
-#pragma unroll
-        for (int k = 0; k < EvlNSum; ++k) {
-            double v = wsum[k];
-            for (int w = 1; w < G; ++w) v += wsum[w * (EvlNSum + 1) + k];
-            q[k] = v;
-        }
-        cnts = 0;
-        for (int w = 0; w < G; ++w) cnts += reinterpret_cast<const int *>(wsum + w * (EvlNSum + 1) + EvlNSum)[0];
-    }
     {
         int nseg = 1;
         while (nseg * 2 * p.Tr <= 32) nseg *= 2;
@@ -340,6 +358,14 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     }
     // ---- reward, KPI sums, step counter: one lane (same statements as step_kernel's phase C) -----------------
     if (lane == 0) {
+        double q[EvlNSum];
+#pragma unroll
+        for (int k = 0; k < EvlNSum; ++k) {
+            double v = wsum[k];
+            for (int w = 1; w < G; ++w) v += wsum[w * EvlNSum + k];
+            q[k] = v;
+        }
+        const int cnts = (int)q[EvlCounts];
         unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
         const int n_dep = cnts & 0xFFFFF;
         const double setpoint = pre[kPreSet];
