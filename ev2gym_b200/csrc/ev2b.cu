@@ -426,13 +426,22 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         h->block = std::max(32, (best_epb * C + 31) / 32 * 32);
         h->layout_smem();
     }
-    // event-driven kernel (ev2b_evlist.cuh): EV2B_KERNEL=evlist opts a handle in; EV2B_EVL_G = warps per env (1, 2, 4)
+    // Which step kernel serves this handle (ev2b_evlist.cuh).  The event-driven kernel wins once the batch fills the
+    // machine (B200, mid-episode, us per launch: c3 4096 envs 33.0 vs 37.8; c4 8192 envs 57.1 vs 100.2) and loses below
+    // that (c3 at 1024 envs: 15.7 vs 13.6), so it is the default from 2048 envs up.  EV2B_KERNEL=percharger|evlist forces
+    // one, EV2B_EVL_G = warps per env (1, 2, 4) overrides the group size (tuning / tests).
     {
         const char *kv = getenv("EV2B_KERNEL");
-        const bool want = kv && (!strcmp(kv, "evlist") || !strcmp(kv, "evl"));
+        const bool force_on = kv && (!strcmp(kv, "evlist") || !strcmp(kv, "evl"));
+        const bool force_off = kv && !strcmp(kv, "percharger");
+        const bool want = force_on || (!force_off && h->E >= 2048);
         if (want && !needs_heavy(h) && h->P < 65535) {
             h->evl = true;
-            h->evl_G = h->P <= 48 ? 1 : (h->P <= 160 ? 2 : 4);
+            // one warp per env keeps every resident warp busy, but needs >= ~4096 envs to fill 148 SMs and room for 8 CTAs
+            // (= 32 envs) of shared memory per SM; otherwise the whole CTA works on one env
+            h->evl_G = 1; h->layout_evl();
+            if (h->E < 4096 || 8 * (h->evl_smem + 1024) > 227 * 1024) h->evl_G = 4;
+            if (force_on && h->E < 2048) h->evl_G = h->P <= 48 ? 1 : (h->P <= 160 ? 2 : 4);   // small (test) batches: by env size
             if (const char *gv = getenv("EV2B_EVL_G")) { const int v = atoi(gv); if (v == 1 || v == 2 || v == 4) h->evl_G = v; }
             h->layout_evl();
             if (h->evl_smem > 200 * 1024) { h->evl_G = 4; h->layout_evl(); }

@@ -55,18 +55,22 @@ __device__ __forceinline__ double warp_sum8(const double (&q)[8], int lane) {
     return c;
 }
 
-__device__ __forceinline__ void evl_bar_sync(int id, int nthreads) {
+// Named barrier 1 + g of the CTA for the 64 threads of group g.  The id is a literal: with the id in a register ptxas
+// reserves all 16 barriers for the CTA, which capped the SM at 3 resident CTAs (ncu: 21 % warps active).
+__device__ __forceinline__ void evl_bar_sync64(int g) {
 #ifdef EV2B_SIMT_EMU
-    simt::bar_sync(id, nthreads);
+    simt::bar_sync(1 + g, 64);
 #else
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    if (g == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else        asm volatile("bar.sync 2, 64;" ::: "memory");
 #endif
 }
 template <int G>
 __device__ __forceinline__ void evl_group_sync(int g) {
+    static_assert(G == 1 || G == 2 || G * 32 == kEvlThreads, "group sizes: one warp, two warps, or the whole CTA");
     if (G == 1) __syncwarp();
     else if (G * 32 == kEvlThreads) __syncthreads();
-    else evl_bar_sync(1 + g, G * 32);
+    else evl_bar_sync64(g);
 }
 
 // Rebuilds occ_list / occ_n of envs [lo, hi) from the hot words (one warp per env): ports in ascending order.
@@ -128,6 +132,19 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     float *obs_row = p.out.obs + (size_t)e * p.D;
 
     // ---- P0: prefetch, zero the per-port flags, (scenario, time)-only observation values ----------------------
+    // The loads of this thread's FIRST EV are issued before anything else (with one warp per env the EV loop is a chain of
+    // dependent global loads: list -> hot words -> spec; ncu: 9.3 warps per issue stalled on long scoreboard), the whole
+    // list is staged in shared memory, and inside the loop the loads of the next EV are issued before the model runs.
+    const uint16_t *lst = p.occ_list + ((size_t)(t & 1) * p.E + e) * p.P;
+    int port_n = 0; uint4 h_n = make_uint4(0u, 0u, 0u, 0u); double cv_n = 0.0, a_n = 0.0; float ex_n = 0.f; unsigned hxm_n = 0u;
+    if (gtid < n_old) {
+        port_n = lst[gtid];
+        const size_t ipn = (size_t)e * p.P + port_n;
+        h_n = p.hot[ipn]; cv_n = p.cap[ipn]; ex_n = p.exch[ipn]; a_n = agent_action<ActT>(p, actions, ipn, t);
+        if (NP == 2) hxm_n = p.hot[ipn ^ 1].x;
+    }
+#pragma unroll 1
+    for (int i = gtid; i < n_old; i += GT) stage[i] = lst[i];
 #pragma unroll 1
     for (int i = gtid; i <= kPrePot; i += GT)
         cp_async8(pre + i, i < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + i : p.env_pot + e);
@@ -158,15 +175,21 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     double aProfit = 0, aSatExp = 0, aCh = 0, aDis = 0, aSat = 0;
     int nDep = 0;
     const bool sat_exp = p.reward_kind == EV2B_REWARD_PROFIT_TR_USER || p.reward_kind == EV2B_REWARD_PROFIT_MAX;
-    const uint16_t *lst = p.occ_list + ((size_t)(t & 1) * p.E + e) * p.P;
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
-        const int port = lst[i];
+        const int port = port_n;
         const size_t ip = (size_t)e * p.P + port;
-        const uint4 h = p.hot[ip];
-        double cv = p.cap[ip];
-        float exch_new = p.exch[ip];
-        const double a = agent_action<ActT>(p, actions, ip, t);
+        const uint4 h = h_n;
+        double cv = cv_n;
+        float exch_new = ex_n;
+        const double a = a_n;
+        const unsigned hx = hxm_n;
+        if (i + GT < n_old) {                         // next EV of this thread: loads in flight while this one is computed
+            port_n = stage[i + GT];
+            const size_t ipn = (size_t)e * p.P + port_n;
+            h_n = p.hot[ipn]; cv_n = p.cap[ipn]; ex_n = p.exch[ipn]; a_n = agent_action<ActT>(p, actions, ipn, t);
+            if (NP == 2) hxm_n = p.hot[ipn ^ 1].x;
+        }
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
         const CsStatic &cs = cs_of<UNI>(p, c);
         // Sigma over the charger's occupied ports, in port order (python sum())   ev_charger.py:137-149
@@ -175,7 +198,6 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             sum = sum + a;
         } else if (NP == 2) {
             const size_t im = ip ^ 1;                 // P is even and port offsets are 2c: the other port of this charger
-            const unsigned hx = p.hot[im].x;
             const bool occ_m = (int)(int16_t)(hx & 0xFFFFu) <= t && t <= (int)(int16_t)(hx >> 16);
             const double am = occ_m ? agent_action<ActT>(p, actions, im, t) : 0.0;
             sum = sum + ((port & 1) ? am : a);
@@ -194,7 +216,10 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             }
         }
         double an = a;
-        if (sum > 1.0) an = an / sum; else if (sum < -1.0) an = -an / sum;
+        {   // if sum > 1: a / sum; if sum < -1: -a / sum  (:143-149) -- one division for both branches
+            const bool over = sum > 1.0, under = sum < -1.0;
+            if (over || under) an = (over ? an : -an) / sum;
+        }
         double energy = 0.0, act_amps = 0.0, pwv = 0.0;
         if (an != 0.0) {
             double cap = cv;
@@ -219,14 +244,13 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             if (sat_exp) aSatExp += 100.0 * exp(-10.0 * sat);             // reward.py:42,85
             aSat += sat;
             ++nDep;
-            stage[i] = (uint16_t)kEvlGone;
+            stage[i] = (uint16_t)kEvlGone;                                // (stage[i] already holds the port of an EV that stays)
             if (want_obs) {
                 float *o = obs_row + p.obs_slot[port];
                 o[0] = 0.f; o[1] = 0.f;
                 if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
             }
         } else {
-            stage[i] = (uint16_t)port;
             const EvSpec *sp = p.spec + hot_spec(h);
             const double B = __ldg(&sp->B);
             if (cv < B && hot_t_dep(h) > tq) potv = __ldg(&p.pot_kw[hot_spec(h) * p.n_cls + cs.cls]);   // utils.py:766-777
