@@ -427,7 +427,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         h->layout_smem();
     }
     // Which step kernel serves this handle (ev2b_evlist.cuh).  The event-driven kernel wins once the batch fills the
-    // machine (B200, mid-episode, us per launch: c3 4096 envs 33.0 vs 37.8; c4 8192 envs 57.1 vs 100.2) and loses below
+    // machine (B200, mid-episode, us per launch: c3 4096 envs 31.7 vs 37.8; c4 8192 envs 50.2 vs 100.2) and loses below
     // that (c3 at 1024 envs: 15.7 vs 13.6), so it is the default from 2048 envs up.  EV2B_KERNEL=percharger|evlist forces
     // one, EV2B_EVL_G = warps per env (1, 2, 4) overrides the group size (tuning / tests).
     {
@@ -437,11 +437,9 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         const bool want = force_on || (!force_off && h->E >= 2048);
         if (want && !needs_heavy(h) && h->P < 65535) {
             h->evl = true;
-            // one warp per env keeps every resident warp busy, but needs >= ~4096 envs to fill 148 SMs and room for 8 CTAs
-            // (= 32 envs) of shared memory per SM; otherwise the whole CTA works on one env
-            h->evl_G = 1; h->layout_evl();
-            if (h->E < 4096 || 8 * (h->evl_smem + 1024) > 227 * 1024) h->evl_G = 4;
-            if (force_on && h->E < 2048) h->evl_G = h->P <= 48 ? 1 : (h->P <= 160 ? 2 : 4);   // small (test) batches: by env size
+            // warps per env: two for the stock env sizes (B200, us per launch, G = 1 / 2 / 4: c3 34.3 / 31.7 / 38.4,
+            // c4 64.8 / 50.2 / 59.7), one for small envs (a warp already covers every connected EV), four for very large ones
+            h->evl_G = h->P <= 64 ? 1 : (h->P <= 512 ? 2 : 4);
             if (const char *gv = getenv("EV2B_EVL_G")) { const int v = atoi(gv); if (v == 1 || v == 2 || v == 4) h->evl_G = v; }
             h->layout_evl();
             if (h->evl_smem > 200 * 1024) { h->evl_G = 4; h->layout_evl(); }

@@ -25,6 +25,10 @@
 #pragma once
 #include "ev2b_device.cuh"
 
+#ifndef EV2B_EVL_PIPELINE
+#define EV2B_EVL_PIPELINE 0     // 1: register-prefetch the next EV's state inside the EV loop (A/B on B200: see DESIGN.md)
+#endif
+
 namespace ev2b {
 
 constexpr int kEvlThreads = 128;
@@ -132,17 +136,19 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     float *obs_row = p.out.obs + (size_t)e * p.D;
 
     // ---- P0: prefetch, zero the per-port flags, (scenario, time)-only observation values ----------------------
-    // The loads of this thread's FIRST EV are issued before anything else (with one warp per env the EV loop is a chain of
-    // dependent global loads: list -> hot words -> spec; ncu: 9.3 warps per issue stalled on long scoreboard), the whole
-    // list is staged in shared memory, and inside the loop the loads of the next EV are issued before the model runs.
     const uint16_t *lst = p.occ_list + ((size_t)(t & 1) * p.E + e) * p.P;
-    int port_n = 0; uint4 h_n = make_uint4(0u, 0u, 0u, 0u); double cv_n = 0.0, a_n = 0.0; float ex_n = 0.f; unsigned hxm_n = 0u;
+#if EV2B_EVL_PIPELINE
+    // The loads of this thread's FIRST EV are issued before anything else, the whole list is staged in shared memory, and
+    // inside the loop the loads of the next EV are issued before the model runs (with one warp per env the EV loop is a
+    // chain of dependent global loads: list -> hot words / action -> spec; ncu: 9.3 warps per issue on long scoreboard).
+    int port_n = 0; uint4 h_n = make_uint4(0u, 0u, 0u, 0u); double cv_n = 0.0, a_n = 0.0, am_n = 0.0; float ex_n = 0.f; unsigned hxm_n = 0u;
     if (gtid < n_old) {
         port_n = lst[gtid];
         const size_t ipn = (size_t)e * p.P + port_n;
         h_n = p.hot[ipn]; cv_n = p.cap[ipn]; ex_n = p.exch[ipn]; a_n = agent_action<ActT>(p, actions, ipn, t);
-        if (NP == 2) hxm_n = p.hot[ipn ^ 1].x;
+        if (NP == 2) { hxm_n = p.hot[ipn ^ 1].x; am_n = agent_action<ActT>(p, actions, ipn ^ 1, t); }
     }
+#endif
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) stage[i] = lst[i];
 #pragma unroll 1
@@ -177,19 +183,30 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     const bool sat_exp = p.reward_kind == EV2B_REWARD_PROFIT_TR_USER || p.reward_kind == EV2B_REWARD_PROFIT_MAX;
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
+#if EV2B_EVL_PIPELINE
         const int port = port_n;
         const size_t ip = (size_t)e * p.P + port;
         const uint4 h = h_n;
         double cv = cv_n;
         float exch_new = ex_n;
-        const double a = a_n;
+        const double a = a_n, am_raw = am_n;
         const unsigned hx = hxm_n;
         if (i + GT < n_old) {                         // next EV of this thread: loads in flight while this one is computed
             port_n = stage[i + GT];
             const size_t ipn = (size_t)e * p.P + port_n;
             h_n = p.hot[ipn]; cv_n = p.cap[ipn]; ex_n = p.exch[ipn]; a_n = agent_action<ActT>(p, actions, ipn, t);
-            if (NP == 2) hxm_n = p.hot[ipn ^ 1].x;
+            if (NP == 2) { hxm_n = p.hot[ipn ^ 1].x; am_n = agent_action<ActT>(p, actions, ipn ^ 1, t); }
         }
+#else
+        const int port = stage[i];
+        const size_t ip = (size_t)e * p.P + port;
+        const uint4 h = p.hot[ip];
+        double cv = p.cap[ip];
+        float exch_new = p.exch[ip];
+        const double a = agent_action<ActT>(p, actions, ip, t);
+        const unsigned hx = NP == 2 ? p.hot[ip ^ 1].x : 0u;
+        const double am_raw = NP == 2 ? agent_action<ActT>(p, actions, ip ^ 1, t) : 0.0;   // same 32 B sector as `a`
+#endif
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
         const CsStatic &cs = cs_of<UNI>(p, c);
         // Sigma over the charger's occupied ports, in port order (python sum())   ev_charger.py:137-149
@@ -197,9 +214,9 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         if (NP == 1) {
             sum = sum + a;
         } else if (NP == 2) {
-            const size_t im = ip ^ 1;                 // P is even and port offsets are 2c: the other port of this charger
+            // the other port of this charger is ip ^ 1 (P is even and port offsets are 2c); its action was loaded with ours
             const bool occ_m = (int)(int16_t)(hx & 0xFFFFu) <= t && t <= (int)(int16_t)(hx >> 16);
-            const double am = occ_m ? agent_action<ActT>(p, actions, im, t) : 0.0;
+            const double am = occ_m ? am_raw : 0.0;
             sum = sum + ((port & 1) ? am : a);
             sum = sum + ((port & 1) ? a : am);
         } else {

@@ -13,7 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _BUILD = os.path.join(_HERE, "_build")
-LIB_PATH = os.path.join(_BUILD, "libev2b_emu.so")
+_EXTRA = os.environ.get("EV2B_EMU_CXXFLAGS", "").split()          # e.g. -DEV2B_EVL_PIPELINE=1: emulate a build variant
+LIB_PATH = os.path.join(_BUILD, "libev2b_emu%s.so" % ("_" + "".join(c for c in "".join(_EXTRA) if c.isalnum()) if _EXTRA else ""))
 _CSRC = os.path.join(_ROOT, "ev2gym_b200", "csrc")
 _SOURCES = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", ".h"))] + \
            [os.path.join(_HERE, f) for f in ("simt_emu.h", "simt_emu.cc")] + [os.path.join(_ROOT, "include", "ev2b.h")]
@@ -23,7 +24,7 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in _SOURCES):
         return LIB_PATH
     os.makedirs(_BUILD, exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-DEV2B_SIMT_EMU", "-I", _HERE,
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-DEV2B_SIMT_EMU", "-I", _HERE] + _EXTRA + [
            "-x", "c++", os.path.join(_CSRC, "ev2b.cu"), os.path.join(_HERE, "simt_emu.cc"), "-o", LIB_PATH]
     subprocess.check_call(cmd)
     return LIB_PATH

@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--workloads", default="c3,c2,c4")
     ap.add_argument("--steps", type=int, default=448)
     ap.add_argument("--out", default="")
+    ap.add_argument("--variants", default="percharger:0,evlist:1,evlist:2,evlist:4", help="kernel:G,... (G = warps per env)")
     args = ap.parse_args()
     import torch
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -90,7 +91,7 @@ def main():
         pack = load_pack(pack_name)
         topo = pack.topo
         ref = None
-        for kernel, G in (("percharger", 0), ("evlist", 1), ("evlist", 2), ("evlist", 4)):
+        for kernel, G in [(v.split(":")[0], int(v.split(":")[1])) for v in args.variants.split(",")]:
             try:
                 us, K, D, caps, rew, kl = time_variant(torch, topo, pack, E, reward, state, kernel, G, args.steps)
             except Exception as exc:  # keep going: one variant failing must not lose the others' numbers
@@ -99,7 +100,8 @@ def main():
                 print(json.dumps(line), flush=True)
                 continue
             b = algorithmic_bytes_per_env_step(topo, D)
-            line = {"workload": wl, "kernel": kernel, "G": G, "us_per_launch": us, "launches": K, "envs": E,
+            line = {"workload": wl, "kernel": kernel, "G": G, "lib": os.path.basename(os.environ.get("EV2B_LIB", "libev2b.so")),
+                    "us_per_launch": us, "launches": K, "envs": E,
                     "env_steps_per_s": E / (us * 1e-6), "algorithmic_GBps": b * E / (us * 1e-6) / 1e9,
                     "roofline_frac": b * E / (us * 1e-6) / 1e9 / peak, "kernel_launches": kl}
             if ref is None:
