@@ -163,6 +163,7 @@ struct ev2b_handle {
         p.env_pot = env_pot.p; p.env_usage = env_usage.p; p.env_kpi = env_kpi.p; p.env_pot_prev = env_pot_prev.p;
         p.occ_list = occ_list.p; p.occ_n = occ_n.p; p.arr_off = arr_off.p; p.arr_list = arr_list.p;
         p.v_stride = evl_o[0]; p.v_amp = evl_o[1]; p.v_pot = evl_o[2]; p.v_csP = evl_o[3]; p.v_pre = evl_o[4];
+        { int lg = 0; while ((2 << lg) * Tr <= 32) ++lg; p.tr_lg = lg; }
         p.v_wsum = evl_o[5]; p.v_trov = evl_o[6]; p.v_stage = evl_o[7]; p.v_occ = evl_o[8];
         p.rr_key = rr_key.p; p.rr_fb = rr_fb.p; p.rr_avg_power = rr_avg_power; p.rr_share = rr_share;
         return p;
@@ -471,8 +472,8 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     CREATE_TRY(h->env_pot.alloc(h->E)); CREATE_TRY(h->env_usage.alloc(h->E)); CREATE_TRY(h->env_pot_prev.alloc(h->E));
     CREATE_TRY(h->env_kpi.alloc((size_t)h->E * EV2B_KPI_COUNT));
     if (h->evl) {
-        CREATE_TRY(h->occ_list.alloc(2 * EP)); CREATE_TRY(h->occ_n.alloc(h->E));
-        CREATE_TRY(cudaMemset(h->occ_list.p, 0, 2 * EP * sizeof(uint16_t)));
+        CREATE_TRY(h->occ_list.alloc(EP)); CREATE_TRY(h->occ_n.alloc(h->E));
+        CREATE_TRY(cudaMemset(h->occ_list.p, 0, EP * sizeof(uint16_t)));
         CREATE_TRY(cudaMemset(h->occ_n.p, 0, h->E * sizeof(int)));
     }
     CREATE_TRY(cudaMemset(h->hot.p, 0, EP * sizeof(uint4)));
@@ -965,11 +966,11 @@ int ev2b_episode_stats(ev2b_handle *h, double *out, void *stream) {
 }
 
 #ifdef EV2B_SIMT_EMU
-// emulator builds only (tests/test_emu_kernels.py): the connected-EV list of env e, current half of the ping-pong
+// emulator builds only (tests/test_emu_kernels.py): the connected-EV list of env e
 int ev2b_debug_list(ev2b_handle *h, int e, uint16_t *out) {
     if (!h || !h->evl || e < 0 || e >= h->E) return -1;
-    const int t = h->env_step.p[e], n = h->occ_n.p[e];
-    memcpy(out, h->occ_list.p + ((size_t)(t & 1) * h->E + e) * h->P, sizeof(uint16_t) * (size_t)n);
+    const int n = h->occ_n.p[e];
+    memcpy(out, h->occ_list.p + (size_t)e * h->P, sizeof(uint16_t) * (size_t)n);
     return n;
 }
 #endif

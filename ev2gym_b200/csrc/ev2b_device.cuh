@@ -129,10 +129,11 @@ struct Params {
     int *rr_key; int *rr_fb;   // [E,P], [E,2]; null until the agent is first used
     double rr_avg_power, rr_share;   // heuristics.py:19-23 ; 1 / number_of_ports_per_cs
     // event-driven step kernel (ev2b_evlist.cuh): connected-EV list per env, arrival schedule per scenario, smem map
-    uint16_t *occ_list;        // [2][E][P] ports holding an EV, buffer (env_step & 1) is current; null: kernel not in use
+    uint16_t *occ_list;        // [E][P] ports holding an EV (first occ_n[e] entries); null: kernel not in use
     int *occ_n;                // [E]
     const int *arr_off;        // [S][T+2]: the sessions arriving at step q are arr_list[arr_off[s][q] .. arr_off[s][q+1])
     const unsigned *arr_list;  // port | session index on that port << 16, arrival-sorted
+    int tr_lg;                 // 2^tr_lg lanes share one transformer in the CSR sums (largest with 2^tr_lg * Tr <= 32)
     int v_stride, v_amp, v_pot, v_csP, v_pre, v_wsum, v_trov, v_stage, v_occ;   // byte offsets inside one env's block
     // state
     uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;

@@ -2,7 +2,7 @@
 //
 // step_kernel (ev2b_device.cuh) runs one thread per (env, charger) and touches every port every step although
 // 65-80 % of the ports are empty mid-episode; it is instruction-issue bound, not HBM bound.
-// This kernel keeps, per env, the list of ports that currently hold an EV (`occ_list`, ping-pong by step parity) and
+// This kernel keeps, per env, the list of ports that currently hold an EV (`occ_list`, rewritten in place every step) and
 // a per-scenario arrival schedule (`arr_list` bucketed by step), and does the reference's work in that order:
 //
 //   P0  prefetch of the per-env records (cp.async), (scenario, time)-only observation values
@@ -12,7 +12,7 @@
 //   AR  one thread per ARRIVAL of step t+1 (from the schedule)                  ev2gym_env.py:399-417
 //   CS  one thread per charger: power / amps / potential in port order, clamp   transformer.py:264-274, utils.py:779-789
 //   TR  warp 0: transformer sums (CSR) + overload; reward, KPI sums, step counter (same code path as step_kernel C)
-//   LS  last warp: stable compaction of the kept EVs + arrivals into the other half of the ping-pong list
+//   LS  last warp: stable compaction of the kept EVs + arrivals back into the list (staged in shared memory meanwhile)
 //
 // An env is owned by a GROUP of G warps (G = 1, 2, 4; a 128-thread CTA holds 4 / G envs), so every barrier is a
 // warp barrier (G = 1), a named barrier (G = 2) or __syncthreads (G = 4), and no phase leaves more than one warp of
@@ -24,10 +24,6 @@
 // relative, not bitwise; battery levels, indices, counts and flags are identical.
 #pragma once
 #include "ev2b_device.cuh"
-
-#ifndef EV2B_EVL_PIPELINE
-#define EV2B_EVL_PIPELINE 0     // 1: register-prefetch the next EV's state inside the EV loop (A/B on B200: see DESIGN.md)
-#endif
 
 namespace ev2b {
 
@@ -83,7 +79,7 @@ __global__ void evl_rebuild_kernel(const Params p, int lo, int hi) {
     const int e = lo + warp;
     if (e >= hi) return;
     const int t = p.env_step[e];
-    uint16_t *lst = p.occ_list + ((size_t)(t & 1) * p.E + e) * p.P;
+    uint16_t *lst = p.occ_list + (size_t)e * p.P;
     int base = 0;
     for (int p0 = 0; p0 < p.P; p0 += 32) {
         const int port = p0 + lane;
@@ -121,6 +117,11 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
 
     const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
+    // The EV loop starts with a chain of dependent global loads (occ_n -> list -> hot words -> spec): the list is a
+    // single buffer rewritten in place (phase LS), so its address needs nothing but e and this thread's first entry is
+    // read together with the per-env scalars (entries at or beyond occ_n are stale and never used).
+    const uint16_t *lst = p.occ_list + (size_t)e * p.P;
+    const unsigned first = gtid < p.P ? (unsigned)lst[gtid] : 0u;
     const int t = p.env_step[e];
     if (t >= p.T) {                                   // step() on a finished env   ev2gym_env.py:343
         if (gtid == 0) {
@@ -136,21 +137,9 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     float *obs_row = p.out.obs + (size_t)e * p.D;
 
     // ---- P0: prefetch, zero the per-port flags, (scenario, time)-only observation values ----------------------
-    const uint16_t *lst = p.occ_list + ((size_t)(t & 1) * p.E + e) * p.P;
-#if EV2B_EVL_PIPELINE
-    // The loads of this thread's FIRST EV are issued before anything else, the whole list is staged in shared memory, and
-    // inside the loop the loads of the next EV are issued before the model runs (with one warp per env the EV loop is a
-    // chain of dependent global loads: list -> hot words / action -> spec; ncu: 9.3 warps per issue on long scoreboard).
-    int port_n = 0; uint4 h_n = make_uint4(0u, 0u, 0u, 0u); double cv_n = 0.0, a_n = 0.0, am_n = 0.0; float ex_n = 0.f; unsigned hxm_n = 0u;
-    if (gtid < n_old) {
-        port_n = lst[gtid];
-        const size_t ipn = (size_t)e * p.P + port_n;
-        h_n = p.hot[ipn]; cv_n = p.cap[ipn]; ex_n = p.exch[ipn]; a_n = agent_action<ActT>(p, actions, ipn, t);
-        if (NP == 2) { hxm_n = p.hot[ipn ^ 1].x; am_n = agent_action<ActT>(p, actions, ipn ^ 1, t); }
-    }
-#endif
+    if (gtid < n_old) stage[gtid] = (uint16_t)first;       // the list is staged in shared memory: phase LS rewrites it in place
 #pragma unroll 1
-    for (int i = gtid; i < n_old; i += GT) stage[i] = lst[i];
+    for (int i = gtid + GT; i < n_old; i += GT) stage[i] = lst[i];
 #pragma unroll 1
     for (int i = gtid; i <= kPrePot; i += GT)
         cp_async8(pre + i, i < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + i : p.env_pot + e);
@@ -183,21 +172,6 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     const bool sat_exp = p.reward_kind == EV2B_REWARD_PROFIT_TR_USER || p.reward_kind == EV2B_REWARD_PROFIT_MAX;
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
-#if EV2B_EVL_PIPELINE
-        const int port = port_n;
-        const size_t ip = (size_t)e * p.P + port;
-        const uint4 h = h_n;
-        double cv = cv_n;
-        float exch_new = ex_n;
-        const double a = a_n, am_raw = am_n;
-        const unsigned hx = hxm_n;
-        if (i + GT < n_old) {                         // next EV of this thread: loads in flight while this one is computed
-            port_n = stage[i + GT];
-            const size_t ipn = (size_t)e * p.P + port_n;
-            h_n = p.hot[ipn]; cv_n = p.cap[ipn]; ex_n = p.exch[ipn]; a_n = agent_action<ActT>(p, actions, ipn, t);
-            if (NP == 2) { hxm_n = p.hot[ipn ^ 1].x; am_n = agent_action<ActT>(p, actions, ipn ^ 1, t); }
-        }
-#else
         const int port = stage[i];
         const size_t ip = (size_t)e * p.P + port;
         const uint4 h = p.hot[ip];
@@ -206,7 +180,6 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         const double a = agent_action<ActT>(p, actions, ip, t);
         const unsigned hx = NP == 2 ? p.hot[ip ^ 1].x : 0u;
         const double am_raw = NP == 2 ? agent_action<ActT>(p, actions, ip ^ 1, t) : 0.0;   // same 32 B sector as `a`
-#endif
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
         const CsStatic &cs = cs_of<UNI>(p, c);
         // Sigma over the charger's occupied ports, in port order (python sum())   ev_charger.py:137-149
@@ -354,7 +327,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
 
     // ---- LS: the group's last warp writes next step's list: kept EVs in list order, then the arrivals ----------
     if (gw == G - 1) {
-        uint16_t *nxt = p.occ_list + ((size_t)(tq & 1) * p.E + e) * p.P;
+        uint16_t *nxt = p.occ_list + (size_t)e * p.P;      // in place: every thread staged the old list before the first barrier
         int base = 0;
 #pragma unroll 1
         for (int i0 = 0; i0 < n_old; i0 += 32) {
@@ -372,20 +345,18 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
 
     // ---- TR: transformer sums + overload (warp 0), same lane split as step_kernel's phase B ---------------------
     {
-        int nseg = 1;
-        while (nseg * 2 * p.Tr <= 32) nseg *= 2;
-        const int per = 32 / nseg;
+        const int lg = p.tr_lg, nseg = 1 << lg, per = 32 >> lg;   // 2^lg lanes share one transformer (host: largest with 2^lg * Tr <= 32)
         for (int k0 = 0; k0 < p.Tr; k0 += per) {
-            const int k = k0 + lane / nseg, seg = lane & (nseg - 1);
+            const int k = k0 + (lane >> lg), seg = lane & (nseg - 1);
             double sp_ = 0.0;
-            if (k < p.Tr && lane / nseg < per) {
+            if (k < p.Tr) {
                 const int i0 = p.tr_cs_off[k], n_k = p.tr_cs_off[k + 1] - i0;
-                const int chunk = (n_k + nseg - 1) / nseg;
+                const int chunk = (n_k + nseg - 1) >> lg;
                 const int lo = seg * chunk, hi = min(n_k, lo + chunk);
                 for (int i = lo; i < hi; ++i) sp_ += csP[p.tr_cs_idx[i0 + i]];
             }
             for (int o = nseg >> 1; o > 0; o >>= 1) sp_ += __shfl_xor_sync(0xffffffffu, sp_, o);
-            if (seg == 0 && k < p.Tr && lane / nseg < per) {              // transformer.py:264-302
+            if (seg == 0 && k < p.Tr) {                                   // transformer.py:264-302
                 const double *tq4 = pre + kPreTr + 4 * k;
                 const double ptot = (tq4[0] + tq4[1]) + sp_;
                 double ov = 0.0;
