@@ -89,7 +89,9 @@ struct ev2b_handle {
     // event-driven step kernel (ev2b_evlist.cuh); chosen per handle by EV2B_KERNEL=evlist, used for the launches it covers
     bool evl = false;                   // lists allocated, schedule built
     bool list_valid = true;             // occ_list / occ_n agree with the hot words of every env
-    int evl_G = 4, evl_o[9] = {0};      // warps per env; smem map (v_stride, v_amp, ...)
+    int evl_G = 4, evl_o[13] = {0};     // warps per env; smem map (v_stride, v_amp, ...)
+    bool evl_stage = false;             // EV2B_EVL_STAGE=1: the STG instantiation (EV records staged with cp.async); A/B only
+    int evl_pf = 0, n_sm = 148;         // EV2B_EVL_PREFETCH bits (ev2b_evlist.cuh); A/B only
     size_t evl_smem = 0;
     DevBuf<uint16_t> occ_list; DevBuf<int> occ_n, arr_off; DevBuf<unsigned> arr_list;
     void layout_evl() {
@@ -102,6 +104,10 @@ struct ev2b_handle {
         evl_o[6] = take(8 * (size_t)Tr, 8);                        // trov
         evl_o[7] = take(2 * (size_t)P, 4);                         // stage
         evl_o[8] = take(((size_t)P + 3) / 4 * 4, 4);               // occ
+        if (evl_stage) {
+            evl_o[9] = take(16 * (size_t)P, 16); evl_o[10] = take(8 * (size_t)P, 8);    // s_hot, s_cap
+            evl_o[12] = take(8 * (size_t)P, 8); evl_o[11] = take(4 * (size_t)P, 4);      // s_act, s_exch
+        }
         evl_o[0] = (int)((off + 15) / 16 * 16);                    // stride
         evl_smem = (size_t)evl_o[0] * (kEvlThreads / (32 * evl_G));
     }
@@ -164,6 +170,8 @@ struct ev2b_handle {
         p.occ_list = occ_list.p; p.occ_n = occ_n.p; p.arr_off = arr_off.p; p.arr_list = arr_list.p;
         p.v_stride = evl_o[0]; p.v_amp = evl_o[1]; p.v_pot = evl_o[2]; p.v_csP = evl_o[3]; p.v_pre = evl_o[4];
         { int lg = 0; while ((2 << lg) * Tr <= 32) ++lg; p.tr_lg = lg; }
+        p.v_shot = evl_o[9]; p.v_scap = evl_o[10]; p.v_sexch = evl_o[11]; p.v_sact = evl_o[12];
+        p.evl_pf = evl_pf; p.evl_pf_dist = n_sm * 8 * (kEvlThreads / (32 * evl_G));
         p.v_wsum = evl_o[5]; p.v_trov = evl_o[6]; p.v_stage = evl_o[7]; p.v_occ = evl_o[8];
         p.rr_key = rr_key.p; p.rr_fb = rr_fb.p; p.rr_avg_power = rr_avg_power; p.rr_share = rr_share;
         return p;
@@ -211,9 +219,14 @@ static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st) 
     const int np = (h->cs_uniform && (h->np_uniform == 1 || h->np_uniform == 2)) ? h->np_uniform : 0;
 #define EV2B_EVL_DISPATCH(G)                                                   \
     do {                                                                       \
-        if (np == 1) return go(evl_step_kernel<ActT, 1, true, G>);             \
-        if (np == 2) return go(evl_step_kernel<ActT, 2, true, G>);             \
-        return go(evl_step_kernel<ActT, 0, false, G>);                         \
+        if (h->evl_stage) {                                                    \
+            if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, true>);   \
+            if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, true>);   \
+            return go(evl_step_kernel<ActT, 0, false, G, true>);               \
+        }                                                                      \
+        if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, false>);      \
+        if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, false>);      \
+        return go(evl_step_kernel<ActT, 0, false, G, false>);                  \
     } while (0)
     if (h->evl_G == 1) EV2B_EVL_DISPATCH(1);
     if (h->evl_G == 2) EV2B_EVL_DISPATCH(2);
@@ -442,6 +455,9 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
             // c4 64.8 / 50.2 / 59.7), one for small envs (a warp already covers every connected EV), four for very large ones
             h->evl_G = h->P <= 64 ? 1 : (h->P <= 512 ? 2 : 4);
             if (const char *gv = getenv("EV2B_EVL_G")) { const int v = atoi(gv); if (v == 1 || v == 2 || v == 4) h->evl_G = v; }
+            if (const char *sv = getenv("EV2B_EVL_STAGE")) h->evl_stage = atoi(sv) != 0;          // unmeasured experiments,
+            if (const char *pv = getenv("EV2B_EVL_PREFETCH")) h->evl_pf = atoi(pv) & 3;          // off by default
+            cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
             h->layout_evl();
             if (h->evl_smem > 200 * 1024) { h->evl_G = 4; h->layout_evl(); }
             if (h->evl_smem > 200 * 1024) h->evl = false;          // does not fit: step_kernel takes every launch

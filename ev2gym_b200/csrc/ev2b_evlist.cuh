@@ -55,6 +55,21 @@ __device__ __forceinline__ double warp_sum8(const double (&q)[8], int lane) {
     return c;
 }
 
+__device__ __forceinline__ void evl_prefetch_l2(const void *ptr) {
+#ifndef EV2B_SIMT_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+#ifdef EV2B_SIMT_EMU
+    simt::cp_async(smem_dst, gmem_src, 4);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#endif
+}
+
 // Named barrier 1 + g of the CTA for the 64 threads of group g.  The id is a literal: with the id in a register ptxas
 // reserves all 16 barriers for the CTA, which capped the SM at 3 resident CTAs (ncu: 21 % warps active).
 __device__ __forceinline__ void evl_bar_sync64(int g) {
@@ -95,7 +110,9 @@ __global__ void evl_rebuild_kernel(const Params p, int lo, int hi) {
     if (lane == 0) p.occ_n[e] = base;
 }
 
-template <typename ActT, int NP, bool UNI, int G>
+// STG: every EV record of the env (hot words, battery level, exchanged energy, action) is copied to shared memory with
+// cp.async before the EV loop instead of being loaded inside it (all of an env's DRAM requests in flight at once).
+template <typename ActT, int NP, bool UNI, int G, bool STG>
 __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_constant__ Params p) {
     EV2B_DYNAMIC_SMEM(smem_raw);
     constexpr int GT = 32 * G, EPB = kEvlThreads / GT;
@@ -114,6 +131,10 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     double *trov  = reinterpret_cast<double *>(sm + p.v_trov);       // [Tr] overload per transformer
     uint16_t *stage = reinterpret_cast<uint16_t *>(sm + p.v_stage);  // [P] by list position: port, or kEvlGone
     unsigned char *occ = sm + p.v_occ;                               // [P] the port holds per-port results this step
+    uint4  *s_hot  = reinterpret_cast<uint4 *>(sm + p.v_shot);       // STG only, by list position: [P] hot words,
+    double *s_cap  = reinterpret_cast<double *>(sm + p.v_scap);      //   [P] battery level,
+    float  *s_exch = reinterpret_cast<float *>(sm + p.v_sexch);      //   [P] exchanged energy,
+    ActT   *s_act  = reinterpret_cast<ActT *>(sm + p.v_sact);        //   [P] action (caller-supplied actions only)
 
     const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
@@ -137,9 +158,36 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     float *obs_row = p.out.obs + (size_t)e * p.D;
 
     // ---- P0: prefetch, zero the per-port flags, (scenario, time)-only observation values ----------------------
-    if (gtid < n_old) stage[gtid] = (uint16_t)first;       // the list is staged in shared memory: phase LS rewrites it in place
+    const bool ext_actions = p.agent_kind == EV2B_AGENT_EXTERNAL;
 #pragma unroll 1
-    for (int i = gtid + GT; i < n_old; i += GT) stage[i] = lst[i];
+    for (int i = gtid; i < n_old; i += GT) {               // the list is staged in shared memory: phase LS rewrites it in place
+        const int port = i == gtid ? (int)first : (int)lst[i];
+        stage[i] = (uint16_t)port;
+        const size_t ip = (size_t)e * p.P + port;
+        if (STG) {                                         // this thread consumes exactly the records it requests here
+            cp_async16(s_hot + i, p.hot + ip);
+            cp_async8(s_cap + i, p.cap + ip);
+            cp_async4(s_exch + i, p.exch + ip);
+            if (ext_actions) {
+                if (sizeof(ActT) == 8) cp_async8(s_act + i, actions + ip); else cp_async4(s_act + i, actions + ip);
+            }
+        } else if ((p.evl_pf & 1) && i != gtid) {          // later EVs of this thread: pull their lines into L2 now
+            evl_prefetch_l2(p.hot + ip); evl_prefetch_l2(p.cap + ip); evl_prefetch_l2(p.exch + ip);
+            if (ext_actions) evl_prefetch_l2(actions + ip);
+        }
+    }
+    if (p.evl_pf & 2) {                                    // the env a later CTA of this launch will own: its rows into L2
+        const int e2 = e + p.evl_pf_dist;
+        if (e2 < p.env_end) {
+            const size_t r0 = (size_t)e2 * p.P;
+            for (int o = gtid * 128; o < p.P * 16; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.hot + r0) + o);
+            for (int o = gtid * 128; o < p.P * 8; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.cap + r0) + o);
+            for (int o = gtid * 128; o < p.P * 4; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.exch + r0) + o);
+            if (ext_actions)
+                for (int o = gtid * 128; o < p.P * (int)sizeof(ActT); o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(actions + r0) + o);
+            for (int o = gtid * 128; o < p.P * 2; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.occ_list + r0) + o);
+        }
+    }
 #pragma unroll 1
     for (int i = gtid; i <= kPrePot; i += GT)
         cp_async8(pre + i, i < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + i : p.env_pot + e);
@@ -164,6 +212,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             }
         }
     }
+    if (STG) cp_async_wait_all();                          // (also completes the per-env records requested above)
     evl_group_sync<G>(g);
 
     // ---- EV: one thread per connected EV ------------------------------------------------------------------------
@@ -174,10 +223,10 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     for (int i = gtid; i < n_old; i += GT) {
         const int port = stage[i];
         const size_t ip = (size_t)e * p.P + port;
-        const uint4 h = p.hot[ip];
-        double cv = p.cap[ip];
-        float exch_new = p.exch[ip];
-        const double a = agent_action<ActT>(p, actions, ip, t);
+        const uint4 h = STG ? s_hot[i] : p.hot[ip];
+        double cv = STG ? s_cap[i] : p.cap[ip];
+        float exch_new = STG ? s_exch[i] : p.exch[ip];
+        const double a = (STG && ext_actions) ? (double)s_act[i] : agent_action<ActT>(p, actions, ip, t);
         const unsigned hx = NP == 2 ? p.hot[ip ^ 1].x : 0u;
         const double am_raw = NP == 2 ? agent_action<ActT>(p, actions, ip ^ 1, t) : 0.0;   // same 32 B sector as `a`
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);

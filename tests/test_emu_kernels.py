@@ -126,6 +126,20 @@ def test_evlist_kernel_matches_oracle(emu, C, n, Tr, E, reward, state, adt, G, m
     eng.close()
 
 
+@pytest.mark.parametrize("switch,value", [("EV2B_EVL_STAGE", "1"), ("EV2B_EVL_PREFETCH", "3")])
+@pytest.mark.parametrize("G", [1, 2])
+@pytest.mark.parametrize("shape", [1, 3])
+def test_evlist_experiment_switches(emu, switch, value, G, shape, monkeypatch):
+    """The opt-in build / launch variants kept for A/B on the GPU (EV records staged with cp.async; L2 prefetch) compute
+    the same thing (the emulator defers cp.async copies until cp.async.wait_all, so a missing wait shows up here)."""
+    C, n, Tr, E, reward, state, adt = SHAPES[shape]
+    monkeypatch.setenv(switch, value)
+    topo, bank = _bank(C, n, Tr)
+    eng, _ = _run_vs_oracle(emu, topo, bank, E, reward, state, adt, "evlist", G=G, monkeypatch=monkeypatch)
+    assert eng.kernel_launches() == (0, topo.T, 0)
+    eng.close()
+
+
 def test_evlist_random_thread_schedule(emu, monkeypatch):
     """Same run with the emulator resuming threads in a seeded random order at every barrier round."""
     monkeypatch.setenv("SIMT_EMU_SEED", "5")

@@ -22,9 +22,11 @@ sys.path.insert(0, ROOT)
 from bench import L2_BYTES, WORKLOADS, algorithmic_bytes_per_env_step, load_pack   # noqa: E402
 
 
-def time_variant(torch, topo, pack, E, reward, state, kernel, G, steps):
+def time_variant(torch, topo, pack, E, reward, state, kernel, G, steps, opt=""):
     from ev2gym_b200.engine import BatchedEngine
     os.environ["EV2B_KERNEL"] = kernel
+    os.environ["EV2B_EVL_STAGE"] = "1" if opt == "stage" else "0"          # opt-in experiments of ev2b_evlist.cuh
+    os.environ["EV2B_EVL_PREFETCH"] = opt[2:] if opt.startswith("pf") else "0"
     if G:
         os.environ["EV2B_EVL_G"] = str(G)
     else:
@@ -80,7 +82,8 @@ def main():
     ap.add_argument("--workloads", default="c3,c2,c4")
     ap.add_argument("--steps", type=int, default=448)
     ap.add_argument("--out", default="")
-    ap.add_argument("--variants", default="percharger:0,evlist:1,evlist:2,evlist:4", help="kernel:G,... (G = warps per env)")
+    ap.add_argument("--variants", default="percharger:0,evlist:1,evlist:2,evlist:4",
+                    help="kernel:G[:opt],... (G = warps per env; opt = stage | pf1 | pf2 | pf3, see ev2b_evlist.cuh)")
     args = ap.parse_args()
     import torch
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -91,16 +94,18 @@ def main():
         pack = load_pack(pack_name)
         topo = pack.topo
         ref = None
-        for kernel, G in [(v.split(":")[0], int(v.split(":")[1])) for v in args.variants.split(",")]:
+        for v in args.variants.split(","):
+            kernel, G, opt = (v.split(":") + ["", ""])[:3]
+            G = int(G or 0)
             try:
-                us, K, D, caps, rew, kl = time_variant(torch, topo, pack, E, reward, state, kernel, G, args.steps)
+                us, K, D, caps, rew, kl = time_variant(torch, topo, pack, E, reward, state, kernel, G, args.steps, opt)
             except Exception as exc:  # keep going: one variant failing must not lose the others' numbers
-                line = {"workload": wl, "kernel": kernel, "G": G, "error": repr(exc)}
+                line = {"workload": wl, "kernel": kernel, "G": G, "opt": opt, "error": repr(exc)}
                 lines.append(line)
                 print(json.dumps(line), flush=True)
                 continue
             b = algorithmic_bytes_per_env_step(topo, D)
-            line = {"workload": wl, "kernel": kernel, "G": G, "lib": os.path.basename(os.environ.get("EV2B_LIB", "libev2b.so")),
+            line = {"workload": wl, "kernel": kernel, "G": G, "opt": opt, "lib": os.path.basename(os.environ.get("EV2B_LIB", "libev2b.so")),
                     "us_per_launch": us, "launches": K, "envs": E,
                     "env_steps_per_s": E / (us * 1e-6), "algorithmic_GBps": b * E / (us * 1e-6) / 1e9,
                     "roofline_frac": b * E / (us * 1e-6) / 1e9 / peak, "kernel_launches": kl}

@@ -4,7 +4,7 @@
 # the bench command.  Every step has its own timeout and writes into gpurun_out/; copy what is to be kept to profiles/.
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 150 python tools/ab_kernels.py --workloads c3,c4,c3-1k,c2 --out gpurun_out/ab_kernels.json > gpurun_out/ab.log 2>&1
+timeout 200 python tools/ab_kernels.py --workloads c3,c4,c3-1k,c2 --variants percharger:0,evlist:1,evlist:2,evlist:4,evlist:2:stage,evlist:1:stage,evlist:2:pf1,evlist:2:pf2,evlist:1:pf1 --out gpurun_out/ab_kernels.json > gpurun_out/ab.log 2>&1
 echo "ab rc=$?" >> gpurun_out/steps.log
 timeout 120 python -m pytest tests/test_gpu_evlist.py tests/test_gpu_fullsize.py -x -q > gpurun_out/test_evl.log 2>&1
 echo "test_evl rc=$?" >> gpurun_out/steps.log
