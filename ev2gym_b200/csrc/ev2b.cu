@@ -53,6 +53,7 @@ struct ev2b_handle {
     int64_t launches = 0;
     int64_t launches_by[3] = {0, 0, 0};   // step_kernel, evl_step_kernel, evl_rebuild_kernel (ev2b_kernel_launches)
     const float *last_obs = nullptr;    // obs buffer whose rows are known to be current (incremental obs writes)
+    const uint8_t *last_mask = nullptr; // action_mask buffer whose rows are known to be current (evl_step_kernel)
     // host copies of the static layout (needed to pack scenarios)
     std::vector<CsStatic> cs_h;
     std::vector<int> port_cs;           // port -> charger
@@ -201,7 +202,7 @@ static bool needs_heavy(const ev2b_handle *h) {
 // Does the event-driven kernel cover a launch with these outputs?  (it has no per-port optional outputs)
 static bool evl_covers(const ev2b_handle *h, const ev2b_step_out *o) {
     if (!h->evl) return false;
-    return !o || !(o->action_mask || o->dep_sat || o->dep_cap || o->port_energy || o->node_voltage);
+    return !o || !(o->dep_sat || o->dep_cap || o->port_energy || o->node_voltage);
 }
 
 template <typename ActT>
@@ -829,6 +830,9 @@ static int step_range(ev2b_handle *h, const void *actions, int action_dtype, con
     p.actions = actions;
     if (out) p.out = *out;
     p.obs_full = obs_full;
+    p.mask_full = (p.out.action_mask && p.out.action_mask != h->last_mask) ? 1 : 0;
+    // after this launch the mask buffer is current only if the launch wrote it for every env (both kernels do)
+    h->last_mask = (lo == 0 && hi == h->E) ? p.out.action_mask : nullptr;
     p.env0 = lo; p.env_end = hi;
     cudaError_t e;
     if (action_dtype != EV2B_F32 && action_dtype != EV2B_F64) return h->fail(EV2B_E_ARG, "step: unknown action dtype %d", action_dtype);

@@ -136,6 +136,7 @@ struct Params {
     int tr_lg;                 // 2^tr_lg lanes share one transformer in the CSR sums (largest with 2^tr_lg * Tr <= 32)
     int v_stride, v_amp, v_pot, v_csP, v_pre, v_wsum, v_trov, v_stage, v_occ;   // byte offsets inside one env's block
     int v_shot, v_scap, v_sexch, v_sact;   // staged EV records (evl_step_kernel<..., STG = true>)
+    int mask_full;             // 1: out.action_mask does not hold last step's rows (evl_step_kernel rewrites them)
     int evl_pf, evl_pf_dist;   // L2 prefetch experiments: bit 0 later EVs of the thread, bit 1 the env `evl_pf_dist` envs ahead
     // state
     uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;

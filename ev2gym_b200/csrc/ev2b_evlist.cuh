@@ -19,7 +19,7 @@
 // a group running alone for long.  The state arrays (hot / cap / exch) are exactly step_kernel's: the two kernels are
 // interchangeable launch by launch (evl_rebuild_kernel re-derives the list from the hot words after step_kernel ran).
 // Handles: the lean instantiation's scope (no statistics mode, no grid, the stock rewards 0-3), without the
-// per-port optional outputs (action_mask, dep_sat, dep_cap, port_energy); everything else takes step_kernel.
+// per-port optional outputs dep_sat, dep_cap, port_energy (action_mask is covered); everything else takes step_kernel.
 // Sums are formed in a different (still fixed) order than step_kernel's, so float64 outputs agree to ~1e-15
 // relative, not bitwise; battery levels, indices, counts and flags are identical.
 #pragma once
@@ -212,6 +212,14 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             }
         }
     }
+    // action_mask is maintained incrementally like the observation tuples: the caller's buffer still holds last step's
+    // row, only ports whose EV arrives or leaves change.  A new buffer (mask_full) or a new episode (t == 0: the row may
+    // hold the previous episode's terminal mask) rewrites the row.                                  ev2gym_env.py:452-457
+    uint8_t *mask_row = p.out.action_mask ? p.out.action_mask + (size_t)e * p.P : nullptr;
+    if (mask_row && (p.mask_full || t == 0)) {
+#pragma unroll 1
+        for (int i = gtid; i < p.P; i += GT) mask_row[i] = 0;
+    }
     if (STG) cp_async_wait_all();                          // (also completes the per-env records requested above)
     evl_group_sync<G>(g);
 
@@ -284,12 +292,14 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             aSat += sat;
             ++nDep;
             stage[i] = (uint16_t)kEvlGone;                                // (stage[i] already holds the port of an EV that stays)
+            if (mask_row) mask_row[port] = 0;
             if (want_obs) {
                 float *o = obs_row + p.obs_slot[port];
                 o[0] = 0.f; o[1] = 0.f;
                 if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
             }
         } else {
+            if (mask_row) mask_row[port] = 1;
             const EvSpec *sp = p.spec + hot_spec(h);
             const double B = __ldg(&sp->B);
             if (cv < B && hot_t_dep(h) > tq) potv = __ldg(&p.pot_kw[hot_spec(h) * p.n_cls + cs.cls]);   // utils.py:766-777
@@ -330,6 +340,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         if (!occ[port]) { pw[port] = 0.0; amp[port] = 0.0; }             // (an EV may have left this very port in step t)
         pot[port] = potv;
         occ[port] = 1;
+        if (mask_row) mask_row[port] = 1;
         if (want_obs) {
             float *o = obs_row + p.obs_slot[port];
             if (p.state_kind == EV2B_STATE_PUBLIC_PST) {

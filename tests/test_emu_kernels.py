@@ -18,7 +18,7 @@ from conftest import GOLDEN, golden_cases
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt_emu"))
 
 LEAN_REWARDS = ("SquaredTrackingErrorReward", "ProfitMax_TrPenalty_UserIncentives", "profit_maximization", "none", "None")
-OUT = ("reward", "status", "obs", "tr_power", "tr_overload", "cs_power", "cs_current", "total_costs")
+OUT = ("reward", "status", "obs", "tr_power", "tr_overload", "cs_power", "cs_current", "total_costs", "action_mask")
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +67,7 @@ def _run_vs_oracle(emu, topo, bank, E, reward, state, adt, kernel, G=None, outpu
             a[:] = 1.0                      # everybody saturates: sum > 1 on shared chargers
         a = np.ascontiguousarray(a.astype(adt))
         if switch is not None:
-            eng.set_outputs(outputs + (("action_mask",) if switch(t) else ()))
+            eng.set_outputs(outputs + (("port_energy",) if switch(t) else ()))
         out = eng.step(a)
         orc.step(a.astype(np.float64))
         occ = orc.arr["port_session"] >= 0
@@ -81,6 +81,8 @@ def _run_vs_oracle(emu, topo, bank, E, reward, state, adt, kernel, G=None, outpu
         if eng.D and (switch is None):      # (a fresh obs tensor every step would force full rewrites: checked separately)
             assert _close(out["obs"], orc.o["obs"][:, :eng.D], 1e-5, 1e-5), (t, "obs")
         assert np.array_equal((out["status"] & 1) > 0, orc.done > 0), (t, "done")
+        if "action_mask" in out:
+            assert np.array_equal(out["action_mask"] > 0, occ), (t, "action mask")
         ovf = np.array([o.error == 1 for o in orc.outs])
         assert np.array_equal((out["status"] & 2) > 0, ovf), (t, "amps overflow flag")
         for e in (0, E - 1):                # the engine's own occupancy (hot words) agrees with the oracle's
@@ -180,6 +182,34 @@ def test_evlist_list_is_the_set_of_connected_ports(emu, G, monkeypatch):
             assert ident[:len(kept)] == kept, (t, e, "EVs that stay keep their order")
             assert all(ta == t + 1 for _, ta in ident[len(kept):]), (t, e, "then this step's arrivals")
             prev[e] = ident
+    eng.close()
+
+
+@pytest.mark.parametrize("G", [1, 2])
+def test_evlist_action_mask_incremental(emu, G, monkeypatch):
+    """action_mask from the event-driven kernel: rows are updated in place (arrivals / departures only), rewritten when
+    the caller hands in another buffer or an env starts a new episode (device-side auto reset)."""
+    topo, bank = _bank(40, 2, 5, T=24)
+    eng, orc = _run_vs_oracle(emu, topo, bank, 5, SHAPES[1][4], SHAPES[1][5], "float32", "evlist", G=G,
+                              outputs=OUT, monkeypatch=monkeypatch)
+    assert eng.kernel_launches() == (0, topo.T, 0)
+    rng = np.random.default_rng(8)
+    eng.out["action_mask"][:] = 1                    # stale terminal rows: the first step of the next episode must clear them
+    eng.reset_done()
+    for t in range(topo.T + 6):                      # through a whole episode and into the next one
+        if t == 7:
+            eng.set_outputs(OUT)                     # a fresh buffer mid-episode
+            eng.out["action_mask"][:] = 1
+        out = eng.step(np.ascontiguousarray(rng.uniform(-1, 1, (5, topo.P)).astype(np.float32)))
+        for e in range(5):
+            if not (out["status"][e] & 4):           # (a finished env keeps its last row, like step_kernel)
+                want = np.zeros(topo.P, dtype=bool)
+                if not (out["status"][e] & 1):
+                    want[_occupied_ports(eng, e)] = True
+                assert np.array_equal(out["action_mask"][e] > 0, want), (t, e)
+        if t % 5 == 4:
+            eng.reset_done()
+    assert eng.kernel_launches()[0] == 0
     eng.close()
 
 
@@ -293,6 +323,7 @@ def test_evlist_kernel_matches_reference_trace(emu, name, monkeypatch):
             occ = tr["action_mask"][t] > 0
             assert np.array_equal(_occupied_ports(eng, e), np.nonzero(occ)[0]) or bool(tr["done"][t]), (t, "occupancy")
             assert np.array_equal(st["port_cap"][e][occ], tr["cap"][t][occ]), (t, "cap")
+            assert np.array_equal(out["action_mask"][e] > 0, occ), (t, "action mask")
             assert _close(out["reward"][e], tr["reward"][t], 1e-9, 1e-9), (t, out["reward"][e], tr["reward"][t])
             assert _close(out["total_costs"][e], tr["total_costs"][t], 1e-9, 1e-12)
             assert _close(out["tr_power"][e], tr["tr_power"][t], 1e-9, 1e-9)

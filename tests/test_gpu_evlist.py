@@ -12,7 +12,7 @@ from conftest import GOLDEN, golden_cases
 
 pytestmark = pytest.mark.gpu
 
-OUT = ("reward", "status", "obs", "tr_power", "tr_overload", "cs_power", "cs_current", "total_costs")
+OUT = ("reward", "status", "obs", "tr_power", "tr_overload", "cs_power", "cs_current", "total_costs", "action_mask")
 LEAN_REWARDS = ("SquaredTrackingErrorReward", "ProfitMax_TrPenalty_UserIncentives", "profit_maximization")
 
 
@@ -69,6 +69,7 @@ def test_evlist_matches_oracle_on_synthetic(C, n, Tr, E, reward, state, adt, G, 
         live = orc.done == 0
         occ_dev = (hot["t_arr"] <= t + 1) & (t + 1 <= hot["t_dep"])
         assert np.array_equal(occ_dev[live], occ[live]), (t, "occupancy")
+        assert np.array_equal(out["action_mask"] > 0, occ), (t, "action mask")
         assert _close(out["reward"], orc.reward, 1e-9, 1e-9), t
         assert _close(out["total_costs"], [o.total_costs for o in orc.outs], 1e-9, 1e-12), t
         assert _close(out["tr_power"], orc.o["tr_power"][:, :Tr], 1e-9, 1e-9), t
@@ -116,6 +117,7 @@ def test_evlist_matches_reference_trace(name, monkeypatch):
             occ = tr["action_mask"][t] > 0
             cap = st["port_cap"][e].cpu().numpy()
             assert np.array_equal(cap[occ], tr["cap"][t][occ]), (t, "cap")
+            assert np.array_equal(out["action_mask"][e] > 0, occ), (t, "action mask")
             hot = eng.decode_hot(st["port_hot"][e].cpu().numpy())
             assert np.array_equal(hot["t_arr"][occ], tr["port_t_arr"][t][occ]), (t, "arrival index")
             assert _close(out["reward"][e], tr["reward"][t], 1e-9, 1e-9), (t, out["reward"][e], tr["reward"][t])
@@ -157,7 +159,7 @@ def test_evlist_equals_step_kernel_at_c3_size(G, monkeypatch):
         for t in range(topo.T):
             a = torch.rand((E, topo.P), device="cuda", generator=gen) * 2.0 - 1.0
             if kn == "mixed" and t % 7 in (2, 3):
-                eng.set_outputs(("reward", "status", "obs", "action_mask"))
+                eng.set_outputs(("reward", "status", "obs", "port_energy"))
                 eng.step(a)
                 eng.set_outputs(("reward", "status", "obs"))
                 rew.append(eng.out["reward"].clone() * 0)      # (outputs were re-allocated: rewards of these steps not compared)
