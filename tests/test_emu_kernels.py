@@ -341,3 +341,48 @@ def test_evlist_kernel_matches_reference_trace(emu, name, monkeypatch):
     out = eng.step(np.zeros((E, topo.P)))      # stepping a finished env: WAS_DONE, reward 0 (ev2gym_env.py:343)
     assert int(out["status"][0]) & 4 and float(out["reward"][0]) == 0.0
     eng.close()
+
+
+BENCH_PACKS = [("c2_publicpst_c25", "SquaredTrackingErrorReward", "PublicPST", 1),
+               ("c3_v2gloads_c100n2tr5", "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", 2),
+               ("c4_v2gprofitmax_c250", "profit_maximization", "V2G_profit_max", 2)]
+
+
+@pytest.mark.parametrize("pack_name,reward,state,G", BENCH_PACKS)
+def test_evlist_on_bench_scenario_banks(emu, pack_name, reward, state, G, monkeypatch):
+    """tests/test_gpu_fullsize.py on the emulator, on a sample of the reference-exported banks bench.py uses (16 scenarios
+    x 2 replicas, whole episodes, 70 % of the ports occupied at the busy part): replicas agree bitwise, battery levels
+    and action mask equal the oracle's, reward 1e-9, observation 1e-5."""
+    from ev2gym_b200.scenario import ScenarioPack
+    from oracle.oracle import OracleBatch
+    monkeypatch.setenv("EV2B_KERNEL", "evlist")
+    monkeypatch.setenv("EV2B_EVL_G", str(G))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pack = ScenarioPack.load(os.path.join(root, "ev2gym_b200", "data", pack_name + ".npz"))
+    topo, S = pack.topo, 16
+    scen = pack.scenarios[:S]
+    E = 2 * S
+    eng = emu.EmuEngine(topo, E, reward=reward, state=state, outputs=("reward", "status", "obs", "action_mask"))
+    eng.load_scenarios(scen)
+    obs0 = eng.reset()
+    orc = OracleBatch(topo, scen, reward=reward, state=state)
+    assert _close(obs0[:S], orc.reset(), 1e-5, 1e-5)
+    caps = eng.state()["port_cap"]
+    low = -1.0 if topo.v2g_enabled else 0.0
+    rng = np.random.default_rng(11)
+    for step in range(topo.T):
+        a = rng.uniform(low, 1.0, (S, topo.P))
+        a[rng.random((S, topo.P)) < 0.1] = 0.0
+        out = eng.step(np.ascontiguousarray(np.tile(a, (2, 1)).astype(np.float32)))
+        for k in ("reward", "status", "obs", "action_mask"):
+            v = out[k].reshape((2, S) + out[k].shape[1:])
+            assert (v == v[:1]).all(), (step, k)
+        orc.step(a.astype(np.float32).astype(np.float64))
+        occ = orc.arr["port_session"] >= 0
+        assert np.array_equal(caps[:S][occ], orc.arr["port_cap"][occ]), step
+        assert np.array_equal(out["action_mask"][:S] > 0, occ), (step, "action mask")
+        assert _close(out["reward"][:S], orc.reward, 1e-9, 1e-9), step
+        assert _close(out["obs"][:S], orc.o["obs"][:, :eng.D], 1e-5, 1e-5), step
+        assert np.array_equal((out["status"][:S] & 1).astype(bool), orc.done.astype(bool)), step
+    assert (out["status"] & 1).all() and eng.kernel_launches() == (0, topo.T, 0)
+    eng.close()
