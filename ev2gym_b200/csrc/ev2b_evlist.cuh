@@ -88,6 +88,102 @@ __device__ __forceinline__ void evl_group_sync(int g) {
     else evl_bar_sync64(g);
 }
 
+// Reward, KPI sums, step counter, done flag and observation header of env e (one thread; the same statements as
+// step_kernel's phase C).  old = the env's KPI sums before the step (shared-memory prefetch, or env_kpi itself),
+// q = the step's totals (Evl*), ovsum = sum of the transformers' overloads, pot_now = charge_power_potential[t].
+__device__ __forceinline__ void evl_finish_env(const Params &p, int e, int s, int tq, const double *old, double pot_now,
+                                               double setpoint, double setpoint_next, const double (&q)[EvlNSum],
+                                               double ovsum, int n_arr, int n_connected, bool want_obs) {
+    const int cnts = (int)q[EvlCounts];
+    unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
+    const int n_dep = cnts & 0xFFFFF;
+    const double usage = q[EvlUsage];                                     // current_power_usage[t]  ev2gym_env.py:375
+    const double costs = q[EvlProfit];
+    double reward = 0.0;
+    if (p.reward_kind == EV2B_REWARD_SQ_TRACKING) {                       // reward.py:11-12
+        const double m = setpoint < pot_now ? setpoint : pot_now;
+        reward = -((m - usage) * (m - usage));
+    } else if (p.reward_kind == EV2B_REWARD_PROFIT_TR_USER) {             // reward.py:36-44
+        reward = costs - 100.0 * ovsum - q[EvlSatExp];
+    } else if (p.reward_kind == EV2B_REWARD_PROFIT_MAX) {                 // reward.py:81-87
+        reward = costs - q[EvlSatExp];
+    }
+    double *kpi = p.env_kpi + (size_t)e * EV2B_KPI_COUNT;
+    kpi[EV2B_KPI_TOTAL_REWARD] = old[EV2B_KPI_TOTAL_REWARD] + reward;
+    kpi[EV2B_KPI_TOTAL_PROFITS] = old[EV2B_KPI_TOTAL_PROFITS] + costs;
+    kpi[EV2B_KPI_ENERGY_CHARGED] = old[EV2B_KPI_ENERGY_CHARGED] + q[EvlCharged];
+    kpi[EV2B_KPI_ENERGY_DISCHARGED] = old[EV2B_KPI_ENERGY_DISCHARGED] + q[EvlDischarged];
+    kpi[EV2B_KPI_TR_OVERLOAD] = old[EV2B_KPI_TR_OVERLOAD] + ovsum;
+    kpi[EV2B_KPI_EVS_SERVED] = old[EV2B_KPI_EVS_SERVED] + (double)n_dep;
+    kpi[EV2B_KPI_SAT_SUM] = old[EV2B_KPI_SAT_SUM] + q[EvlSatSum];
+    const double d = setpoint - usage;                                    // utils.py:37-44
+    kpi[EV2B_KPI_TRACKING_ERROR] = old[EV2B_KPI_TRACKING_ERROR] + d * d;
+    kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] = old[EV2B_KPI_ENERGY_TRACKING_ERROR] + fabs(d);
+    if (usage > setpoint) kpi[EV2B_KPI_TRACKER_VIOLATION] = old[EV2B_KPI_TRACKER_VIOLATION] + (usage - setpoint);
+    kpi[EV2B_KPI_EVS_SPAWNED] = old[EV2B_KPI_EVS_SPAWNED] + (double)n_arr;
+    kpi[EV2B_KPI_INVALID_ACTIONS] = old[EV2B_KPI_INVALID_ACTIONS] + (double)(p.P - n_connected);   // every empty port  ev_charger.py:137-140
+    kpi[EV2B_KPI_STEPS] = old[EV2B_KPI_STEPS] + 1.0;
+    p.env_pot[e] = (tq < p.T) ? q[EvlPot] : 0.0;                          // ev2gym_env.py:424-426
+    p.env_usage[e] = usage;
+    p.env_step[e] = tq;
+    if (tq >= p.T) status |= EV2B_ST_DONE;                                // ev2gym_env.py:460
+    if (want_obs) obs_header(p, p.out.obs + (size_t)e * p.D, s, tq, usage, setpoint_next);
+    if (p.out.reward) p.out.reward[e] = reward;
+    if (p.out.total_costs) p.out.total_costs[e] = costs;
+    if (p.out.status) p.out.status[e] = status;
+}
+
+// A step of an env with no EV connected and none arriving (half of the steps of the stock workplace scenarios: the site
+// is empty at night).  Every per-EV and per-charger quantity is zero; what remains is the transformers' base load, the
+// reward, the KPI sums and the observation.  No shared memory; the group's threads share the copies, its first thread
+// does the per-env part straight from global memory -- after a barrier, because it advances env_step, which every thread
+// of the group has just read (the SIMT emulator caught exactly that: a lane that ran ahead saw the next step).
+template <int G>
+__device__ __forceinline__ void evl_idle_step(const Params &p, int e, int t, int s, int g, int gtid, bool want_obs) {
+    constexpr int GT = 32 * G;
+    const int tq = t + 1;
+    evl_group_sync<G>(g);
+    if (want_obs) {
+        float *obs_row = p.out.obs + (size_t)e * p.D;
+        for (int i = gtid; i < p.W; i += GT) obs_row[p.series_off[i]] = obs_series_fetch(p, s, tq, i);
+        if (p.obs_full) {
+            const bool three = p.state_kind == EV2B_STATE_PUBLIC_PST;
+#pragma unroll 1
+            for (int i = gtid; i < p.P; i += GT) {
+                float *o = obs_row + p.obs_slot[i];
+                o[0] = 0.f; o[1] = 0.f;
+                if (three) o[2] = 0.f;
+            }
+        }
+    }
+    if (p.out.action_mask && (p.mask_full || t == 0)) {
+#pragma unroll 1
+        for (int i = gtid; i < p.P; i += GT) p.out.action_mask[(size_t)e * p.P + i] = 0;
+    }
+    if (p.out.cs_power || p.out.cs_current) {
+#pragma unroll 1
+        for (int c = gtid; c < p.C; c += GT) {
+            if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = 0.f;
+            if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = 0.f;
+        }
+    }
+    if (gtid != 0) return;
+    double ovsum = 0.0;
+    for (int k = 0; k < p.Tr; ++k) {                                      // transformer.py:264-302 with no charger load
+        const TrT tt = p.tr_t[((size_t)s * p.T + t) * p.Tr + k];
+        const double ptot = (tt.infl + tt.solar) + 0.0;
+        double ov = 0.0;
+        if (ptot > tt.maxp + 0.0001 || ptot < tt.minp - 0.0001) ov = fabs(ptot - tt.maxp);
+        if (p.out.tr_power)    p.out.tr_power[(size_t)e * p.Tr + k] = ptot;
+        if (p.out.tr_overload) p.out.tr_overload[(size_t)e * p.Tr + k] = ov;
+        ovsum += ov;
+    }
+    const double q[EvlNSum] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const EnvT *et = p.env_t + (size_t)s * p.T + t;
+    evl_finish_env(p, e, s, tq, p.env_kpi + (size_t)e * EV2B_KPI_COUNT, p.env_pot[e], et->setpoint,
+                   tq < p.T ? et[1].setpoint : 0.0, q, ovsum, 0, 0, want_obs);
+}
+
 // Rebuilds occ_list / occ_n of envs [lo, hi) from the hot words (one warp per env): ports in ascending order.
 __global__ void evl_rebuild_kernel(const Params p, int lo, int hi) {
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
@@ -155,6 +251,12 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     const int s = p.env_scn[e];
     const int n_old = p.occ_n[e];
     const int tq = t + 1;
+    const int a0 = p.arr_off[(size_t)s * (p.T + 2) + tq], a1 = p.arr_off[(size_t)s * (p.T + 2) + tq + 1];
+    const int nArr = a1 - a0;
+    if (n_old == 0 && nArr == 0) {                    // nobody connected, nobody arriving: the short path
+        evl_idle_step<G>(p, e, t, s, g, gtid, want_obs);
+        return;
+    }
     float *obs_row = p.out.obs + (size_t)e * p.D;
 
     // ---- P0: prefetch, zero the per-port flags, (scenario, time)-only observation values ----------------------
@@ -197,7 +299,6 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         else cp_async16(pre + kPreTr + 2 * (i - 2), reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * (i - 2));
     }
     const EnvT et0 = p.env_t[(size_t)s * p.T + t];
-    const int a0 = p.arr_off[(size_t)s * (p.T + 2) + tq], a1 = p.arr_off[(size_t)s * (p.T + 2) + tq + 1];
 #pragma unroll 1
     for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
     if (want_obs) {
@@ -321,7 +422,6 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     evl_group_sync<G>(g);
 
     // ---- AR: arrivals of step t+1, one thread each (the highest threads: they had the least EV work) ---------
-    const int nArr = a1 - a0;
 #pragma unroll 1
     for (int k = GT - 1 - gtid; k < nArr; k += GT) {                      // ev2gym_env.py:399-417, ev_charger.py:266-285
         const unsigned u = p.arr_list[a0 + k];
@@ -428,7 +528,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         }
         __syncwarp();
     }
-    // ---- reward, KPI sums, step counter: one lane (same statements as step_kernel's phase C) -----------------
+    // ---- reward, KPI sums, step counter: one lane ------------------------------------------------------------------
     if (lane == 0) {
         double q[EvlNSum];
 #pragma unroll
@@ -437,47 +537,9 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             for (int w = 1; w < G; ++w) v += wsum[w * EvlNSum + k];
             q[k] = v;
         }
-        const int cnts = (int)q[EvlCounts];
-        unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
-        const int n_dep = cnts & 0xFFFFF;
-        const double setpoint = pre[kPreSet];
-        const double usage = q[EvlUsage];                                 // current_power_usage[t]  ev2gym_env.py:375
-        const double costs = q[EvlProfit];
         double ovsum = 0.0;
         for (int k = 0; k < p.Tr; ++k) ovsum += trov[k];
-        double reward = 0.0;
-        if (p.reward_kind == EV2B_REWARD_SQ_TRACKING) {                   // reward.py:11-12
-            const double potn = pre[kPrePot];
-            const double m = setpoint < potn ? setpoint : potn;
-            reward = -((m - usage) * (m - usage));
-        } else if (p.reward_kind == EV2B_REWARD_PROFIT_TR_USER) {         // reward.py:36-44
-            reward = costs - 100.0 * ovsum - q[EvlSatExp];
-        } else if (p.reward_kind == EV2B_REWARD_PROFIT_MAX) {             // reward.py:81-87
-            reward = costs - q[EvlSatExp];
-        }
-        double *kpi = p.env_kpi + (size_t)e * EV2B_KPI_COUNT;
-        kpi[EV2B_KPI_TOTAL_REWARD] = pre[EV2B_KPI_TOTAL_REWARD] + reward;
-        kpi[EV2B_KPI_TOTAL_PROFITS] = pre[EV2B_KPI_TOTAL_PROFITS] + costs;
-        kpi[EV2B_KPI_ENERGY_CHARGED] = pre[EV2B_KPI_ENERGY_CHARGED] + q[EvlCharged];
-        kpi[EV2B_KPI_ENERGY_DISCHARGED] = pre[EV2B_KPI_ENERGY_DISCHARGED] + q[EvlDischarged];
-        kpi[EV2B_KPI_TR_OVERLOAD] = pre[EV2B_KPI_TR_OVERLOAD] + ovsum;
-        kpi[EV2B_KPI_EVS_SERVED] = pre[EV2B_KPI_EVS_SERVED] + (double)n_dep;
-        kpi[EV2B_KPI_SAT_SUM] = pre[EV2B_KPI_SAT_SUM] + q[EvlSatSum];
-        const double d = setpoint - usage;                                // utils.py:37-44
-        kpi[EV2B_KPI_TRACKING_ERROR] = pre[EV2B_KPI_TRACKING_ERROR] + d * d;
-        kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] = pre[EV2B_KPI_ENERGY_TRACKING_ERROR] + fabs(d);
-        if (usage > setpoint) kpi[EV2B_KPI_TRACKER_VIOLATION] = pre[EV2B_KPI_TRACKER_VIOLATION] + (usage - setpoint);
-        kpi[EV2B_KPI_EVS_SPAWNED] = pre[EV2B_KPI_EVS_SPAWNED] + (double)nArr;
-        kpi[EV2B_KPI_INVALID_ACTIONS] = pre[EV2B_KPI_INVALID_ACTIONS] + (double)(p.P - n_old);   // every empty port  ev_charger.py:137-140
-        kpi[EV2B_KPI_STEPS] = pre[EV2B_KPI_STEPS] + 1.0;
-        p.env_pot[e] = (tq < p.T) ? q[EvlPot] : 0.0;                      // ev2gym_env.py:424-426
-        p.env_usage[e] = usage;
-        p.env_step[e] = tq;
-        if (tq >= p.T) status |= EV2B_ST_DONE;                            // ev2gym_env.py:460
-        if (want_obs) obs_header(p, obs_row, s, tq, usage, pre[kPreSetNext]);
-        if (p.out.reward) p.out.reward[e] = reward;
-        if (p.out.total_costs) p.out.total_costs[e] = costs;
-        if (p.out.status) p.out.status[e] = status;
+        evl_finish_env(p, e, s, tq, pre, pre[kPrePot], pre[kPreSet], pre[kPreSetNext], q, ovsum, nArr, n_old, want_obs);
     }
 }
 

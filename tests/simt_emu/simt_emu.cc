@@ -206,7 +206,20 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::functio
                 progress = true;
             }
             if (!any_left) break;
-            if (!progress) { g_cur = nullptr; die("deadlock: every live thread waits on a barrier that cannot complete"); }
+            if (!progress) {                         // say who waits where before giving up
+                for (unsigned t = 0; t < block; ++t) {
+                    const Fiber &f = g_fibers[t];
+                    if (f.done) { fprintf(stderr, "simt_emu:   thread %u exited\n", t); continue; }
+                    int named = -1, warp = -1;
+                    for (int i = 0; i < kNamed; ++i) if (f.wait == &g_named[i]) named = i;
+                    for (size_t w = 0; w < g_warps.size(); ++w) if (f.wait == &g_warps[w].bar) warp = (int)w;
+                    if (named >= 0) fprintf(stderr, "simt_emu:   thread %u waits on CTA barrier %d (%d arrived)\n", t, named, g_named[named].arrived);
+                    else fprintf(stderr, "simt_emu:   thread %u waits on a collective of warp %d (mask %08x, %d arrived)\n", t, warp,
+                                 g_warps[warp < 0 ? 0 : warp].bar_mask, g_warps[warp < 0 ? 0 : warp].bar.arrived);
+                }
+                g_cur = nullptr;
+                die("deadlock: every live thread waits on a barrier that cannot complete");
+            }
         }
     }
     munmap(g_smem_base, g_smem_map);

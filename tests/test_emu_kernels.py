@@ -142,11 +142,13 @@ def test_evlist_experiment_switches(emu, switch, value, G, shape, monkeypatch):
     eng.close()
 
 
-def test_evlist_random_thread_schedule(emu, monkeypatch):
-    """Same run with the emulator resuming threads in a seeded random order at every barrier round."""
-    monkeypatch.setenv("SIMT_EMU_SEED", "5")
+@pytest.mark.parametrize("G", [1, 2, 4])
+def test_evlist_random_thread_schedule(emu, G, monkeypatch):
+    """Same run with the emulator resuming threads in a seeded random order at every barrier round (a thread that runs
+    ahead of its group must not see state another thread of the group is about to change)."""
+    monkeypatch.setenv("SIMT_EMU_SEED", str(4 + G))
     topo, bank = _bank(40, 2, 5)
-    eng, _ = _run_vs_oracle(emu, topo, bank, 5, SHAPES[1][4], SHAPES[1][5], "float32", "evlist", G=2, monkeypatch=monkeypatch)
+    eng, _ = _run_vs_oracle(emu, topo, bank, 5, SHAPES[1][4], SHAPES[1][5], "float32", "evlist", G=G, monkeypatch=monkeypatch)
     eng.close()
 
 
