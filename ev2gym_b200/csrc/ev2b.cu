@@ -98,13 +98,14 @@ struct ev2b_handle {
     void layout_evl() {
         size_t off = 0;
         auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; const size_t at = off; off += bytes; return (int)at; };
-        take(8 * (size_t)P, 16);                                   // pw
-        evl_o[1] = take(8 * (size_t)P, 8); evl_o[2] = take(8 * (size_t)P, 8); evl_o[3] = take(8 * (size_t)C, 8);   // amp, pot, csP
+        const size_t pp = (cs_uniform && np_uniform == 1) ? 0 : (size_t)P;   // one port per charger: no per-port staging
+        take(8 * pp, 16);                                          // pw
+        evl_o[1] = take(8 * pp, 8); evl_o[2] = take(8 * pp, 8); evl_o[3] = take(8 * (size_t)C, 8);   // amp, pot, csP
         evl_o[4] = take(8 * (size_t)(kPreTr + 4 * Tr), 16);        // pre (cp.async 16 B destinations)
         evl_o[5] = take(8 * (size_t)EvlNSum * evl_G, 8);           // wsum
         evl_o[6] = take(8 * (size_t)Tr, 8);                        // trov
         evl_o[7] = take(2 * (size_t)P, 4);                         // stage
-        evl_o[8] = take(((size_t)P + 3) / 4 * 4, 4);               // occ
+        evl_o[8] = take((pp + 3) / 4 * 4, 4);                      // occ
         if (evl_stage) {
             evl_o[9] = take(16 * (size_t)P, 16); evl_o[10] = take(8 * (size_t)P, 8);    // s_hot, s_cap
             evl_o[12] = take(8 * (size_t)P, 8); evl_o[11] = take(4 * (size_t)P, 4);      // s_act, s_exch

@@ -11,6 +11,7 @@
 //       potential; per-port results go to shared memory                        ev_charger.py:114-233, ev.py:138-405
 //   AR  one thread per ARRIVAL of step t+1 (from the schedule)                  ev2gym_env.py:399-417
 //   CS  one thread per charger: power / amps / potential in port order, clamp   transformer.py:264-274, utils.py:779-789
+//       (not with one port per charger: there the EV's own thread does it)
 //   TR  warp 0: transformer sums (CSR) + overload; reward, KPI sums, step counter (same code path as step_kernel C)
 //   LS  last warp: stable compaction of the kept EVs + arrivals back into the list (staged in shared memory meanwhile)
 //
@@ -299,8 +300,17 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         else cp_async16(pre + kPreTr + 2 * (i - 2), reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * (i - 2));
     }
     const EnvT et0 = p.env_t[(size_t)s * p.T + t];
+    if (NP == 1) {                                    // one port per charger: the EV's thread is the charger's thread (no CS phase)
 #pragma unroll 1
-    for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
+        for (int i = gtid; i < p.C; i += GT) {
+            csP[i] = 0.0;
+            if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + i] = 0.f;
+            if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + i] = 0.f;
+        }
+    } else {
+#pragma unroll 1
+        for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
+    }
     if (want_obs) {
         for (int i = gtid; i < p.W; i += GT) obs_row[p.series_off[i]] = obs_series_fetch(p, s, tq, i);
         if (p.obs_full) {                             // the caller's buffer does not hold last step's rows: clear every tuple
@@ -325,8 +335,9 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     evl_group_sync<G>(g);
 
     // ---- EV: one thread per connected EV ------------------------------------------------------------------------
-    double aProfit = 0, aSatExp = 0, aCh = 0, aDis = 0, aSat = 0;
+    double aProfit = 0, aSatExp = 0, aCh = 0, aDis = 0, aSat = 0, aUsage = 0, aPot = 0;
     int nDep = 0;
+    bool overflow = false;
     const bool sat_exp = p.reward_kind == EV2B_REWARD_PROFIT_TR_USER || p.reward_kind == EV2B_REWARD_PROFIT_MAX;
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
@@ -384,7 +395,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             else          { aProfit += ae * et0.dp; aDis += ae; }         // ev_charger.py:194-195
             pwv = ev2b_div_c(energy * 60.0, p.period, p.rperiod);         // :180,196
         }
-        pw[port] = pwv; amp[port] = act_amps;
+        if (NP != 1) { pw[port] = pwv; amp[port] = act_amps; }
         double potv = 0.0;
         if (t >= hot_t_dep(h)) {                                          // departure  ev_charger.py:209-224, ev.py:199-214
             const double des = __ldg(&p.spec[hot_spec(h)].desired);
@@ -416,8 +427,20 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
                 }
             }
         }
-        pot[port] = potv;
-        occ[port] = 1;
+        if (NP == 1) {                                                    // charger == port: accounting in place
+            const double rP = 0.0 + pwv, rA = 0.0 + act_amps;
+            if (rA - 0.0001 > cs.imax) overflow = true;                   // ev_charger.py:203-205
+            double rPot = potv;
+            if (rPot > cs.max_power) rPot = cs.max_power;                 // utils.py:779-789
+            else if (rPot < cs.min_power) rPot = 0.0;
+            csP[port] = rP;
+            aUsage += rP; aPot += rPot;
+            if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + port] = (float)rP;
+            if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + port] = (float)rA;
+        } else {
+            pot[port] = potv;
+            occ[port] = 1;
+        }
     }
     evl_group_sync<G>(g);
 
@@ -437,9 +460,16 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         const double B = __ldg(&sp->B);
         double potv = 0.0;
         if (r.cap0 < B && hot_t_dep(r.hot) > tq) potv = __ldg(&p.pot_kw[hot_spec(r.hot) * p.n_cls + cs.cls]);
-        if (!occ[port]) { pw[port] = 0.0; amp[port] = 0.0; }             // (an EV may have left this very port in step t)
-        pot[port] = potv;
-        occ[port] = 1;
+        if (NP == 1) {                                                    // (an EV that left this very port in step t added 0)
+            double rPot = potv;
+            if (rPot > cs.max_power) rPot = cs.max_power;
+            else if (rPot < cs.min_power) rPot = 0.0;
+            aPot += rPot;
+        } else {
+            if (!occ[port]) { pw[port] = 0.0; amp[port] = 0.0; }         // (an EV may have left this very port in step t)
+            pot[port] = potv;
+            occ[port] = 1;
+        }
         if (mask_row) mask_row[port] = 1;
         if (want_obs) {
             float *o = obs_row + p.obs_slot[port];
@@ -456,10 +486,8 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     evl_group_sync<G>(g);
 
     // ---- CS: one thread per charger, ports in order -------------------------------------------------------------
-    double aUsage = 0, aPot = 0;
-    bool overflow = false;
 #pragma unroll 1
-    for (int c = gtid; c < p.C; c += GT) {
+    for (int c = NP == 1 ? p.C : gtid; c < p.C; c += GT) {
         const CsStatic &cs = cs_of<UNI>(p, c);
         const int p0 = NP > 0 ? c * NP : cs.port_off, n = NP > 0 ? NP : cs.n_ports;
         double rP = 0, rA = 0, rPot = 0;
