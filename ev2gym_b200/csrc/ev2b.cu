@@ -451,7 +451,8 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         const bool force_on = kv && (!strcmp(kv, "evlist") || !strcmp(kv, "evl"));
         const bool force_off = kv && !strcmp(kv, "percharger");
         const bool want = force_on || (!force_off && h->E >= 2048);
-        if (want && !needs_heavy(h) && h->P < 65535) {
+        const bool in_scope = !(h->dims.flags & EV2B_F_STATS) && h->n_bus == 0;   // no statistics mode, no distribution grid
+        if (want && in_scope && h->P < 65535) {
             h->evl = true;
             // warps per env: two for the stock env sizes (B200, us per launch, G = 1 / 2 / 4: c3 34.3 / 31.7 / 38.4,
             // c4 64.8 / 50.2 / 59.7), one for small envs (a warp already covers every connected EV), four for very large ones

@@ -21,8 +21,8 @@
 // warp barrier (G = 1), a named barrier (G = 2) or __syncthreads (G = 4), and no phase leaves more than one warp of
 // a group running alone for long.  The state arrays (hot / cap / exch) are exactly step_kernel's: the two kernels are
 // interchangeable launch by launch (evl_rebuild_kernel re-derives the list from the hot words after step_kernel ran).
-// Handles: the lean instantiation's scope (no statistics mode, no grid, the stock rewards 0-3), without the
-// per-port optional outputs dep_sat, dep_cap, port_energy (action_mask is covered); everything else takes step_kernel.
+// Handles: every stock reward and state function that needs no distribution grid, without statistics mode and without
+// the per-port optional outputs dep_sat, dep_cap, port_energy (action_mask is covered); everything else takes step_kernel.
 // Sums are formed in a different (still fixed) order than step_kernel's, so float64 outputs agree to ~1e-15
 // relative, not bitwise; battery levels, indices, counts and flags are identical.
 #pragma once
@@ -91,12 +91,34 @@ __device__ __forceinline__ void evl_group_sync(int g) {
     else evl_bar_sync64(g);
 }
 
+// What the env's reward function adds per EV that leaves this step (cv = its final battery level, des = the level it
+// asked for, sat = its user satisfaction); summed into EvlSatExp and subtracted by the reward.
+__device__ __forceinline__ double evl_departure_penalty(const Params &p, double cv, double des, double sat) {
+    const int k = p.reward_kind;
+    if (k == EV2B_REWARD_PROFIT_TR_USER || k == EV2B_REWARD_PROFIT_MAX) return 100.0 * exp(-10.0 * sat);   // reward.py:42,85
+    if (k == EV2B_REWARD_SQTR_TR_USER) return 1000.0 * (1.0 - sat);                                         // reward.py:29-30
+    if (k == EV2B_REWARD_V2G_PROFITMAX) return des > cv ? 100.0 * (des - cv) : 0.0;                         // reward.py:136-138
+    if (k == EV2B_REWARD_V2G_PROFITMAX_V2 || k == EV2B_REWARD_PST_PROFITMAX_V2)
+        return des > cv ? 0.05 * ((des - cv) * (des - cv)) : 0.0;                                           // reward.py:199-207
+    return 0.0;
+}
+// V2G_profitmaxV2 family: an EV that stays connected but can no longer reach its desired level   reward.py:172-190
+__device__ __forceinline__ double evl_unreachable_penalty(const Params &p, const EvSpec *sp, double cv, int steps_left) {
+    if (p.reward_kind != EV2B_REWARD_V2G_PROFITMAX_V2 && p.reward_kind != EV2B_REWARD_PST_PROFITMAX_V2) return 0.0;
+    const double des = __ldg(&sp->desired), pmax = __ldg(&sp->pmax_ac);
+    const double min_steps = (des - cv) / (pmax / p.c60);
+    if (!(min_steps > (double)steps_left)) return 0.0;
+    const double gap = (des - ((double)(steps_left + 1) * pmax / p.c60)) - cv;
+    return 0.05 * (gap * gap);
+}
+
 // Reward, KPI sums, step counter, done flag and observation header of env e (one thread; the same statements as
 // step_kernel's phase C).  old = the env's KPI sums before the step (shared-memory prefetch, or env_kpi itself),
 // q = the step's totals (Evl*), ovsum = sum of the transformers' overloads, pot_now = charge_power_potential[t].
 __device__ __forceinline__ void evl_finish_env(const Params &p, int e, int s, int tq, const double *old, double pot_now,
-                                               double setpoint, double setpoint_next, const double (&q)[EvlNSum],
-                                               double ovsum, int n_arr, int n_connected, bool want_obs) {
+                                               double setpoint, double setpoint_next, double tr0_max_power,
+                                               const double (&q)[EvlNSum], double ovsum, int n_arr, int n_connected,
+                                               bool want_obs) {
     const int cnts = (int)q[EvlCounts];
     unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
     const int n_dep = cnts & 0xFFFFF;
@@ -110,6 +132,26 @@ __device__ __forceinline__ void evl_finish_env(const Params &p, int e, int s, in
         reward = costs - 100.0 * ovsum - q[EvlSatExp];
     } else if (p.reward_kind == EV2B_REWARD_PROFIT_MAX) {                 // reward.py:81-87
         reward = costs - q[EvlSatExp];
+    } else if (p.reward_kind == EV2B_REWARD_SQTR_TR_USER) {               // reward.py:16-32
+        double m = setpoint < pot_now ? setpoint : pot_now;
+        if (tr0_max_power < m) m = tr0_max_power;                         // transformers[0].max_power[t]
+        reward = -((m - usage) * (m - usage)) - 100.0 * ovsum - q[EvlSatExp];
+    } else if (p.reward_kind == EV2B_REWARD_SQ_TRACKING_PENALTY) {        // reward.py:46-58
+        const double m = setpoint < pot_now ? setpoint : pot_now;
+        reward = -((m - usage) * (m - usage));
+        if (usage == 0.0 && p.env_pot_prev[e] != 0.0) reward = reward - 100.0;   // potential[current_step-2]; 0 at t = 0
+        p.env_pot_prev[e] = pot_now;
+    } else if (p.reward_kind == EV2B_REWARD_SIMPLE) {                     // reward.py:60-65
+        reward = -((setpoint - usage) * (setpoint - usage));
+    } else if (p.reward_kind == EV2B_REWARD_MIN_TRACKER_SURPLUS) {        // reward.py:67-76
+        if (setpoint < usage) reward -= (usage - setpoint) * (usage - setpoint);
+        reward += usage;
+    } else if (p.reward_kind == EV2B_REWARD_V2G_COSTS_SIMPLE) {           // reward.py:150-153
+        reward = costs;
+    } else if (p.reward_kind == EV2B_REWARD_V2G_PROFITMAX || p.reward_kind == EV2B_REWARD_V2G_PROFITMAX_V2 ||
+               p.reward_kind == EV2B_REWARD_PST_PROFITMAX_V2) {           // reward.py:123-148, 155-213, 281-339
+        reward = costs - q[EvlSatExp];
+        if (p.reward_kind == EV2B_REWARD_PST_PROFITMAX_V2 && setpoint < usage) reward += 1000.0 * (setpoint - usage);
     }
     double *kpi = p.env_kpi + (size_t)e * EV2B_KPI_COUNT;
     kpi[EV2B_KPI_TOTAL_REWARD] = old[EV2B_KPI_TOTAL_REWARD] + reward;
@@ -184,7 +226,7 @@ __device__ __forceinline__ void evl_idle_step(const Params &p, int e, int t, int
     const double q[EvlNSum] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const EnvT *et = p.env_t + (size_t)s * p.T + t;
     evl_finish_env(p, e, s, tq, p.env_kpi + (size_t)e * EV2B_KPI_COUNT, p.env_pot[e], et->setpoint,
-                   tq < p.T ? et[1].setpoint : 0.0, q, ovsum, 0, 0, want_obs);
+                   tq < p.T ? et[1].setpoint : 0.0, p.tr_t[((size_t)s * p.T + t) * p.Tr].maxp, q, ovsum, 0, 0, want_obs);
 }
 
 // Rebuilds occ_list / occ_n of envs [lo, hi) from the hot words (one warp per env): ports in ascending order.
@@ -340,7 +382,6 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     double aProfit = 0, aSatExp = 0, aCh = 0, aDis = 0, aSat = 0, aUsage = 0, aPot = 0;
     int nDep = 0;
     bool overflow = false;
-    const bool sat_exp = p.reward_kind == EV2B_REWARD_PROFIT_TR_USER || p.reward_kind == EV2B_REWARD_PROFIT_MAX;
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
         const int port = stage[i];
@@ -402,7 +443,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         if (t >= hot_t_dep(h)) {                                          // departure  ev_charger.py:209-224, ev.py:199-214
             const double des = __ldg(&p.spec[hot_spec(h)].desired);
             const double sat = (cv < des - 0.001) ? cv / des : 1.0;
-            if (sat_exp) aSatExp += 100.0 * exp(-10.0 * sat);             // reward.py:42,85
+            aSatExp += evl_departure_penalty(p, cv, des, sat);
             aSat += sat;
             ++nDep;
             stage[i] = (uint16_t)kEvlGone;                                // (stage[i] already holds the port of an EV that stays)
@@ -416,6 +457,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             if (mask_row) mask_row[port] = 1;
             const EvSpec *sp = p.spec + hot_spec(h);
             const double B = __ldg(&sp->B);
+            aSatExp += evl_unreachable_penalty(p, sp, cv, hot_t_dep(h) - tq);
             if (cv < B && hot_t_dep(h) > tq) potv = __ldg(&p.pot_kw[hot_spec(h) * p.n_cls + cs.cls]);   // utils.py:766-777
             if (want_obs) {                                               // state.py:37-57, 85-102, 137-151
                 float *o = obs_row + p.obs_slot[port];
@@ -461,6 +503,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         const EvSpec *sp = p.spec + hot_spec(r.hot);
         const double B = __ldg(&sp->B);
         double potv = 0.0;
+        aSatExp += evl_unreachable_penalty(p, sp, r.cap0, hot_t_dep(r.hot) - tq);
         if (r.cap0 < B && hot_t_dep(r.hot) > tq) potv = __ldg(&p.pot_kw[hot_spec(r.hot) * p.n_cls + cs.cls]);
         if (NP == 1) {                                                    // (an EV that left this very port in step t added 0)
             double rPot = potv;
@@ -569,7 +612,8 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         }
         double ovsum = 0.0;
         for (int k = 0; k < p.Tr; ++k) ovsum += trov[k];
-        evl_finish_env(p, e, s, tq, pre, pre[kPrePot], pre[kPreSet], pre[kPreSetNext], q, ovsum, nArr, n_old, want_obs);
+        evl_finish_env(p, e, s, tq, pre, pre[kPrePot], pre[kPreSet], pre[kPreSetNext], pre[kPreTr + 2], q, ovsum, nArr,
+                       n_old, want_obs);
     }
 }
 
