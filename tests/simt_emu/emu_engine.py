@@ -107,7 +107,6 @@ class EmuEngine:
             if n == "obs" and self.D == 0:
                 continue
             dt, shp = _OUT[n]
-            a = np.full((self.E,) + tuple(dims[k] for k in shp), 0x5A, dtype=np.uint8).view(np.uint8)   # placeholder
             a = np.zeros((self.E,) + tuple(dims[k] for k in shp), dtype=dt)
             self.out[n] = a
             setattr(self._so, n, a.ctypes.data)
