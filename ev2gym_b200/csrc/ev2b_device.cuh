@@ -318,7 +318,13 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
             curr = pilot + soc;
             if (curr > 1.0) curr = 1.0;
         } else {
-            const double pts = ts + (pilot - maxd) / maxd * (ts - 1.0);            // :312-314
+            // pts = ts + (pilot - maxd) / maxd * (ts - 1)   :312-314.  A saturated request has pilot == maxd exactly, and a
+            // zero numerator sends the compiler's fp64 division into its out-of-line slow path (ncu: ~270 warp instructions
+            // per env-step); 0 / maxd * (ts - 1) is +-0 and ts + (+-0) == ts, so those lanes skip the division.
+            const double dz = pilot - maxd;
+            double ratio = 0.0;
+            if (dz != 0.0 || maxd == 0.0) ratio = dz / maxd;
+            const double pts = ts + ratio * (ts - 1.0);
             double nsoc;
             if (soc < pts && 1.0 <= (pts - soc) / pilot) {
                 nsoc = pilot + soc;                                                // constant-current stage  :323-324

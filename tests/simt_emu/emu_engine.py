@@ -65,7 +65,8 @@ def lib():
 _OUT = {"reward": (np.float64, ()), "status": (np.uint32, ()), "obs": (np.float32, ("D",)),
         "cs_power": (np.float32, ("C",)), "cs_current": (np.float32, ("C",)), "tr_power": (np.float64, ("Tr",)),
         "tr_overload": (np.float64, ("Tr",)), "total_costs": (np.float64, ()), "action_mask": (np.uint8, ("P",)),
-        "dep_sat": (np.float64, ("P",)), "dep_cap": (np.float64, ("P",)), "port_energy": (np.float32, ("P",))}
+        "dep_sat": (np.float64, ("P",)), "dep_cap": (np.float64, ("P",)), "port_energy": (np.float32, ("P",)),
+        "node_voltage": (np.float64, ("N",))}
 
 
 class EmuEngine:
@@ -100,7 +101,7 @@ class EmuEngine:
             self.h = None
 
     def set_outputs(self, names):
-        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P}
+        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P, "N": self.topo.n_bus + 1}
         self.out: Dict[str, np.ndarray] = {}
         self._so = self._lib.StepOut()
         for n in names:

@@ -391,3 +391,45 @@ def test_evlist_on_bench_scenario_banks(emu, pack_name, reward, state, G, monkey
         assert np.array_equal((out["status"][:S] & 1).astype(bool), orc.done.astype(bool)), step
     assert (out["status"] & 1).all() and eng.kernel_launches() == (0, topo.T, 0)
     eng.close()
+
+
+ALL_OUT = ("reward", "status", "obs", "cs_power", "cs_current", "tr_power", "tr_overload", "total_costs", "action_mask",
+           "dep_sat", "port_energy")
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_step_kernel_matches_reference_trace_on_emulator(emu, name, monkeypatch):
+    """tests/test_gpu_parity.py::test_cuda_matches_reference_trace on the emulator: step_kernel in its full-featured
+    instantiation (statistics mode, every output, the Laurent power flow of the grid episodes) on all recorded reference
+    episodes -- so a change to the shared model code (ev_step_item) is checked here before it reaches a GPU."""
+    from ev2gym_b200.scenario import ScenarioPack
+    monkeypatch.setenv("EV2B_KERNEL", "percharger")
+    pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
+    tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+    topo = pack.topo
+    E, grid = 2, pack.topo.n_bus > 0
+    eng = emu.EmuEngine(topo, E, reward=str(tr["reward_fn"]), state=str(tr["state_fn"]),
+                        outputs=ALL_OUT + (("node_voltage",) if grid else ()), stats=True)
+    eng.load_scenarios(pack.scenarios)
+    obs0 = eng.reset()
+    assert _close(obs0[0], tr["obs0"], 1e-5, 1e-6)
+    st = eng.state()
+    T = tr["reward"].shape[0]
+    for t in range(T):
+        out = eng.step(np.ascontiguousarray(np.tile(tr["actions"][t], (E, 1)).astype(np.float64)))
+        e = E - 1
+        occ = out["action_mask"][e] > 0
+        assert np.array_equal(occ.astype(np.float64), tr["action_mask"][t]), (t, "mask")
+        assert np.array_equal(st["port_cap"][e][occ], tr["cap"][t][occ]), (t, "cap")              # bit exact
+        assert _close(out["reward"][e], tr["reward"][t], 1e-9, 1e-9), (t, "reward")
+        assert _close(out["total_costs"][e], tr["total_costs"][t], 1e-9, 1e-12)
+        assert _close(out["tr_power"][e], tr["tr_power"][t], 1e-9, 1e-9)
+        assert _close(out["tr_overload"][e], tr["tr_overload"][t], 1e-9, 1e-9)
+        assert _close(out["cs_power"][e], tr["cs_power"][t], 1e-5, 1e-6)
+        assert _close(out["obs"][e], tr["obs"][t], 1e-5, 1e-5), (t, "obs")
+        if grid:
+            assert _close(out["node_voltage"][e], tr["node_voltage"][:, t], 1e-9, 1e-12), (t, "node voltage")
+        assert bool(out["status"][e] & 1) == bool(tr["done"][t])
+        assert np.count_nonzero(~np.isnan(out["dep_sat"][e])) == tr["n_departed"][t]
+    assert eng.kernel_launches()[1] == 0
+    eng.close()
