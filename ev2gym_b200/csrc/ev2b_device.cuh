@@ -301,11 +301,18 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
     const double veff = cs.veff[ph], rveff = cs.rveff[ph];
     const int lut = __ldg(&sp->lut);
     const double B = __ldg(&sp->B), rB = __ldg(&sp->rB);
-    if (amps > 0.0) {                                                              // EV._charge  ev.py:240-355
-        double eta;
-        const unsigned tsm = hz >> 16, ecm = hw & 0xFFFFu;
-        if (lut >= 0) eta = ev2b_div_c(lut_get(p.luts_c + (size_t)lut * p.lut_len, p.lut_len, rint(amps)), 100.0, 0.01);
-        else eta = (ecm == 0xFFFFu) ? __ldg(&sp->eta_c) : ev2b_div_c((double)ecm, 1000.0, 0.001);
+    // charge / discharge efficiency: a scalar, or dict.get(np.round(amps), 1) / 100 resp. dict.get(abs(np.round(amps)), 1) / 100
+    // (ev.py:287-290, 375-378).  np.round(amps) >= 0 when charging, so one lookup with |round(amps)| serves both directions:
+    // every lane of the warp does it once instead of the charging and the discharging lanes one after the other.
+    const bool charging = amps > 0.0;
+    double eta;
+    {
+        const unsigned em = charging ? (hw & 0xFFFFu) : (hw >> 16);
+        if (lut >= 0) eta = ev2b_div_c(lut_get((charging ? p.luts_c : p.luts_d) + (size_t)lut * p.lut_len, p.lut_len, fabs(rint(amps))), 100.0, 0.01);
+        else eta = (em == 0xFFFFu) ? __ldg(charging ? &sp->eta_c : &sp->eta_d) : ev2b_div_c((double)em, 1000.0, 0.001);
+    }
+    if (charging) {                                                                // EV._charge  ev.py:240-355
+        const unsigned tsm = hz >> 16;
         const double ts = (tsm == 0xFFFFu) ? __ldg(&sp->ts) : ev2b_div_c((double)tsm, 1000.0, 0.001);
         const double pmax = __ldg(&sp->pmax_ac);
         // pilot_dsoc = eta*amps*voltage/1000/B/(60/period)                            :295-296
@@ -326,7 +333,10 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
             if (dz != 0.0 || maxd == 0.0) ratio = dz / maxd;
             const double pts = ts + ratio * (ts - 1.0);
             double nsoc;
-            if (soc < pts && 1.0 <= (pts - soc) / pilot) {
+            // `1 <= (pts - soc) / pilot`  (:323)  without the division: for 0 < pilot and x = pts - soc > 0, x < pilot
+            // implies x / pilot < 1 - 2^-53 exactly, which rounds below 1, and x >= pilot implies a quotient >= 1 -- so the
+            // float64 comparison of the rounded quotient with 1 is the comparison of x with pilot.
+            if (soc < pts && pilot <= pts - soc) {
                 nsoc = pilot + soc;                                                // constant-current stage  :323-324
             } else {
                 // the two constant-voltage expressions differ only in their operands; selecting the operands first lets
@@ -345,10 +355,6 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
         energy = (curr - soc) * B;                                                 // :346,352
         act_amps = ev2b_div_c(ev2b_div_c(energy, p.p60, p.rp60) * 1000.0, veff, rveff);   // :355
     } else {                                                                       // EV._discharge  ev.py:357-405
-        double eta;
-        const unsigned edm = hw >> 16;
-        if (lut >= 0) eta = ev2b_div_c(lut_get(p.luts_d + (size_t)lut * p.lut_len, p.lut_len, fabs(rint(amps))), 100.0, 0.01);
-        else eta = (edm == 0xFFFFu) ? __ldg(&sp->eta_d) : ev2b_div_c((double)edm, 1000.0, 0.001);
         const double pmd = __ldg(&sp->pmax_dis), bmin = __ldg(&sp->bmin);
         double given_power = ev2b_div_c(amps * veff, 1000.0, 0.001);               // :367
         if (fabs(given_power) > fabs(pmd)) given_power = pmd;                      // :370-371

@@ -23,3 +23,22 @@ def test_div_const_matches_ieee_division():
     out = subprocess.check_output([exe, "2000000"] + [repr(float(d)) for d in divisors], text=True)
     rows = [l.split() for l in out.strip().splitlines()]
     assert len(rows) == len(divisors) and all(int(r[1]) == 0 for r in rows), rows
+
+
+def test_quotient_at_least_one_is_a_plain_comparison():
+    """ev_step_item replaces the reference's `1 <= (pts - soc) / pilot` (ev.py:323) by `pilot <= pts - soc`: for positive
+    float64 operands the rounded quotient is >= 1 exactly when x >= y (x < y gives x / y < 1 - 2^-53, which rounds
+    below 1).  Checked on operands a few ulps around equality and on random ratios, and for a zero numerator of the
+    saturation test `(pilot - maxd) / maxd` (0 / d * (ts - 1) must leave ts unchanged)."""
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    y = np.exp(rng.uniform(-12, 3, n))
+    k = rng.integers(-4, 5, n)
+    x = y.copy()
+    for _ in range(4):
+        x = np.where(k > 0, np.nextafter(x, np.inf), np.where(k < 0, np.nextafter(x, -np.inf), x))
+        k = k - np.sign(k)
+    for xx in (x, y * rng.uniform(0.5, 1.5, n)):
+        assert np.array_equal(1.0 <= xx / y, y <= xx)
+    ts = rng.uniform(0.0, 1.0, n).round(3)
+    assert np.array_equal(ts + (0.0 / y) * (ts - 1.0), ts)
