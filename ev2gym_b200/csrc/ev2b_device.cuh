@@ -220,7 +220,9 @@ __device__ __forceinline__ void obs_header(const Params &p, float *row, int s, i
 }
 // One value of the (scenario, time)-only part of the observation: i indexes the flat list
 // [20 prices][Tr * (20 load-pv forecast + 20 power limits)].
-__device__ __forceinline__ float obs_series_value(const Params &p, int s, int tq, int i) {
+// (out of line: the step kernels only call it when the precomputed table `obs_static` does not exist -- a bank too large
+//  for it -- and inlined it was ~700 instructions at every call site)
+__device__ EV2B_NOINLINE float obs_series_value(const Params &p, int s, int tq, int i) {
     if (p.state_kind == EV2B_STATE_V2G_GRID) {                      // V2G_grid_state  state.py:221-255
         if (i < 3) return (float)p.date_feat[((size_t)s * (p.T + 1) + tq) * 3 + i];
         if (i == 3) return (tq < p.T) ? (float)p.env_t[(size_t)s * p.T + tq].cp : 0.f;        // charge_prices[0, t:t+1]

@@ -115,10 +115,13 @@ __device__ __forceinline__ double evl_unreachable_penalty(const Params &p, const
 // Reward, KPI sums, step counter, done flag and observation header of env e (one thread; the same statements as
 // step_kernel's phase C).  old = the env's KPI sums before the step (shared-memory prefetch, or env_kpi itself),
 // q = the step's totals (Evl*), ovsum = sum of the transformers' overloads, pot_now = charge_power_potential[t].
-__device__ __forceinline__ void evl_finish_env(const Params &p, int e, int s, int tq, const double *old, double pot_now,
-                                               double setpoint, double setpoint_next, double tr0_max_power,
-                                               const double (&q)[EvlNSum], double ovsum, int n_arr, int n_connected,
-                                               bool want_obs) {
+struct EvlTotals {            // the step's totals of one env, indexed by Evl*
+    double v[EvlNSum];
+    __device__ __forceinline__ double operator[](int k) const { return v[k]; }
+};
+__device__ EV2B_NOINLINE void evl_finish_env(const Params &p, int e, int s, int tq, const double *old, double pot_now,
+                                             double setpoint, double setpoint_next, double tr0_max_power,
+                                             const EvlTotals q, double ovsum, int n_arr, int n_connected, bool want_obs) {
     const int cnts = (int)q[EvlCounts];
     unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
     const int n_dep = cnts & 0xFFFFF;
@@ -223,7 +226,7 @@ __device__ __forceinline__ void evl_idle_step(const Params &p, int e, int t, int
         if (p.out.tr_overload) p.out.tr_overload[(size_t)e * p.Tr + k] = ov;
         ovsum += ov;
     }
-    const double q[EvlNSum] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const EvlTotals q = {{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}};
     const EnvT *et = p.env_t + (size_t)s * p.T + t;
     evl_finish_env(p, e, s, tq, p.env_kpi + (size_t)e * EV2B_KPI_COUNT, p.env_pot[e], et->setpoint,
                    tq < p.T ? et[1].setpoint : 0.0, p.tr_t[((size_t)s * p.T + t) * p.Tr].maxp, q, ovsum, 0, 0, want_obs);
@@ -327,11 +330,16 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         const int e2 = e + p.evl_pf_dist;
         if (e2 < p.env_end) {
             const size_t r0 = (size_t)e2 * p.P;
+#pragma unroll 1
             for (int o = gtid * 128; o < p.P * 16; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.hot + r0) + o);
+#pragma unroll 1
             for (int o = gtid * 128; o < p.P * 8; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.cap + r0) + o);
+#pragma unroll 1
             for (int o = gtid * 128; o < p.P * 4; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.exch + r0) + o);
             if (ext_actions)
-                for (int o = gtid * 128; o < p.P * (int)sizeof(ActT); o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(actions + r0) + o);
+    #pragma unroll 1
+            for (int o = gtid * 128; o < p.P * (int)sizeof(ActT); o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(actions + r0) + o);
+#pragma unroll 1
             for (int o = gtid * 128; o < p.P * 2; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.occ_list + r0) + o);
         }
     }
@@ -603,12 +611,12 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     }
     // ---- reward, KPI sums, step counter: one lane ------------------------------------------------------------------
     if (lane == 0) {
-        double q[EvlNSum];
+        EvlTotals q;
 #pragma unroll
         for (int k = 0; k < EvlNSum; ++k) {
             double v = wsum[k];
             for (int w = 1; w < G; ++w) v += wsum[w * EvlNSum + k];
-            q[k] = v;
+            q.v[k] = v;
         }
         double ovsum = 0.0;
         for (int k = 0; k < p.Tr; ++k) ovsum += trov[k];
