@@ -265,6 +265,9 @@ def test_evlist_auto_reset_step_k_and_host_chunks(emu, monkeypatch):
         eng.load_scenarios(bank)
         eng.reset()
         eng.step_k(40, agent="uniform", seed=11, auto_reset=True)        # crosses an episode boundary (T = 24)
+        eng.step_k(9, agent="roundrobin", auto_reset=True)               # agent_kernel reads hot / cap, then a float64 step
+        eng.step_k(9, agent="calap", auto_reset=True)
+        eng.step_k(5, agent="afap", auto_reset=True)
         st = eng.state()
         snap = [st["port_hot"].copy(), st["port_cap"].copy(), st["env_step"].copy(), st["env_scn"].copy(),
                 eng.out["obs"].copy()]
