@@ -114,3 +114,31 @@ def test_replay_pickle_import_round_trip():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "rewards bit-equal" in r.stdout
+
+
+def test_step_kernels_keep_their_register_budget():
+    """Both step kernels are register-limited to 8 CTAs of 128 threads per SM (64 registers per thread) and keep only a
+    few spill slots; the kernel parameter block must fit the 4 KB parameter space.  Read from the built library with
+    cuobjdump (no GPU needed), so an edit that bloats them fails here and not as a slowdown on the GPU box."""
+    import re
+    import shutil
+    import subprocess
+    from ev2gym_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    _lib.load()
+    txt = subprocess.check_output([cuobjdump, "-res-usage", _lib.LIB_PATH], text=True)
+    res = dict(re.findall(r"Function (\S+):\s*\n\s*(REG:\d+ STACK:\d+[^\n]*)", txt))
+    checked = 0
+    for name, usage in res.items():
+        lean_step = "step_kernelIfLi2ELb1ELi128ELi8ELb0ELb0" in name          # c3: float actions, 2 ports, no optional outputs
+        lean_evl = "evl_step_kernelIf" in name and name.endswith("ELb0EEEvNS_6ParamsE")
+        if not (lean_step or lean_evl):
+            continue
+        reg, stack = int(re.search(r"REG:(\d+)", usage).group(1)), int(re.search(r"STACK:(\d+)", usage).group(1))
+        const0 = int(re.search(r"CONSTANT\[0\]:(\d+)", usage).group(1))
+        assert reg <= 64 and stack <= 96, (name, usage)
+        assert const0 <= 4096 + 528, (name, usage)                            # driver area + kernel parameters
+        checked += 1
+    assert checked >= 4
