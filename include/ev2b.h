@@ -145,7 +145,11 @@ typedef struct {
 } ev2b_scenarios;
 
 /* Per-step outputs, DEVICE pointers owned by the caller; any pointer may be NULL (= not wanted).
- * Replaces the 5-tuple of EV2Gym.step plus the attributes rewards/states/agents read afterwards. */
+ * Replaces the 5-tuple of EV2Gym.step plus the attributes rewards/states/agents read afterwards.
+ * `obs` and `action_mask` are updated IN PLACE: when a step is given the same buffer as the previous step (or as the
+ * ev2b_reset before it), only the entries that can have changed are written (ports whose EV stayed, arrived or left,
+ * the header, the price / forecast windows); a different pointer gets every entry rewritten.  So a caller that
+ * overwrites such a buffer between two steps must hand in another buffer (or reset) -- reading it is always fine. */
 typedef struct {
     double   *reward;        /* [E]     reward of this step                  ev2gym_env.py:430-432 */
     uint32_t *status;        /* [E]     EV2B_ST_* bits (done etc.)           ev2gym_env.py:460     */

@@ -93,15 +93,111 @@ def trial(k, rng):
     return desc
 
 
+def stateful_trial(k, rng):
+    """A random sequence of API calls on one handle -- steps with changing output sets (some force step_kernel, so the
+    connected-EV list is re-derived), fresh output buffers (full observation / mask rewrites), partial resets in the middle of
+    an episode, device-side auto reset, ev2b_step_host (two env chunks) -- mirrored on the oracle env by env."""
+    import ctypes as C
+    import emu_engine
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    from oracle.oracle import OracleBatch, _p
+    C_ = int(rng.integers(2, 40))
+    n = int(rng.integers(1, 3))
+    Tr = int(rng.integers(1, min(C_, 4) + 1))
+    T = int(rng.integers(10, 26))
+    S = int(rng.integers(1, 4))
+    E = S * int(rng.integers(1, 4))                  # E % S == 0: the auto reset ((scn + E) mod S) keeps every env on its scenario
+    G = int(rng.choice([1, 2, 4]))
+    reward = REWARDS[rng.integers(len(REWARDS) - 1)]
+    state = STATES[rng.integers(len(STATES) - 1)]
+    os.environ["EV2B_KERNEL"], os.environ["EV2B_EVL_G"], os.environ["EV2B_EVL_STAGE"] = "evlist", str(G), "0"
+    topo = Topology.uniform(C=C_, n_ports=n, Tr=Tr, T=T)
+    bank = sample_bank(topo, S, seed=int(rng.integers(1 << 30)), min_stay=int(rng.integers(1, 6)),
+                       occupancy=float(rng.uniform(0.2, 0.9)))
+    base = ("reward", "status", "obs", "action_mask", "cs_power", "tr_power")
+    eng = emu_engine.EmuEngine(topo, E, reward=reward, state=state, outputs=base)
+    eng.load_scenarios(bank)
+    ids = [e % S for e in range(E)]
+    eng.reset(scn_ids=ids)
+    orc = OracleBatch(topo, [bank[i] for i in ids], reward=reward, state=state)
+    orc.reset()
+    caps = eng.state()["port_cap"]
+    desc = dict(k=k, C=C_, n=n, Tr=Tr, T=T, S=S, E=E, G=G, reward=reward, state=state)
+    graveyard = []
+
+    def oracle_reset(envs):
+        for e in envs:
+            orc.L.ev2o_reset(C.byref(orc._t.c), orc._scn_ptrs[e], C.byref(orc.states[e]), orc.state_kind, _p(orc.o["obs"][e]))
+            orc.done[e] = 0
+
+    def check(out, what, host=False):
+        occ = orc.arr["port_session"] >= 0
+        live = orc.done == 0
+        assert np.array_equal(caps[occ], orc.arr["port_cap"][occ]), (desc, what, "cap")
+        assert close(out["reward"], orc.reward, 1e-9, 1e-9), (desc, what, "reward")
+        assert close(out["obs"], orc.o["obs"][:, :eng.D], 1e-5, 1e-5), (desc, what, "obs")
+        assert np.array_equal((out["status"] & 1) > 0, orc.done > 0), (desc, what, "done")
+        if not host:
+            assert np.array_equal(out["action_mask"] > 0, occ), (desc, what, "mask")
+            assert close(out["cs_power"], orc.o["cs_power"], 1e-5, 1e-6), (desc, what, "cs_power")
+            assert close(out["tr_power"], orc.o["tr_power"][:, :Tr], 1e-9, 1e-9), (desc, what, "tr_power")
+        return live
+
+    for it in range(int(rng.integers(20, 70))):
+        op = rng.choice(["step", "step", "step", "step_v6", "fresh", "partial_reset", "host"])
+        if os.environ.get("FUZZ_TRACE"):
+            print("  op", it, op, flush=True)
+        a = rng.uniform(-1.1, 1.1, (E, topo.P))
+        a[rng.random((E, topo.P)) < 0.15] = 0.0
+        a = np.ascontiguousarray(a.astype(np.float32))
+        if op == "fresh":
+            graveyard.append(eng.out)                # keep the old buffers alive: the new ones must get NEW addresses (the
+            eng.set_outputs(base)                    # library rewrites a buffer in full only when its pointer changes)
+            for v in eng.out.values():
+                v[...] = 1                           # stale content: obs / mask rows must be rewritten in full
+            continue
+        if op == "partial_reset" and E > 1:
+            lo = int(rng.integers(0, E - 1))
+            hi = int(rng.integers(lo + 1, E + 1))
+            eng.reset(lo, hi, scn_ids=ids[lo:hi])
+            oracle_reset(range(lo, hi))
+            continue
+        if op == "host":
+            rew, st = np.zeros(E), np.zeros(E, dtype=np.uint32)
+            obs = np.zeros((E, max(eng.D, 1)), dtype=np.float32)
+            eng.step_host(a, rew, st, obs)
+            orc.step(a.astype(np.float64))
+            check({"reward": rew, "status": st, "obs": obs}, (it, op), host=True)
+            graveyard.append(eng.out)
+            eng.set_outputs(base)                    # (step_host advanced the envs without these buffers: start them afresh)
+        else:
+            if op == "step_v6":
+                graveyard.append(eng.out)
+                eng.set_outputs(base + ("port_energy",))
+            out = eng.step(a)
+            orc.step(a.astype(np.float64))
+            check(out, (it, op))
+            if op == "step_v6":
+                graveyard.append(eng.out)
+                eng.set_outputs(base)
+        if orc.done.any():                           # finished envs restart on their scenario, on both sides
+            eng.reset_done()
+            oracle_reset(np.nonzero(orc.done)[0])
+    eng.close()
+    return desc
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--trials", type=int, default=200)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--stateful", action="store_true", help="random API call sequences instead of plain episodes")
     args = ap.parse_args()
     os.environ.setdefault("SIMT_EMU_SEED", str(1 + args.seed))
     rng = np.random.default_rng(args.seed)
     for k in range(args.trials):
-        d = trial(k, rng)
+        d = (stateful_trial if args.stateful else trial)(k, rng)
         if k % 20 == 0:
             print("ok", d, flush=True)
     print(f"{args.trials} trials passed")
