@@ -1,12 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the batched EV2Gym step engine on B200 (contract: see the task brief).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5|c3-1k] [--impl reference]
 
 One "step" = one fused-kernel pass advancing one batch of E env replicas by one timestep
 (E x chargers named in config.workload).  Scenarios are banks exported from the reference's own
 reset() (ev2gym_b200/data/*.npz, tools/make_golden.py --packs), tiled over the envs (env e uses
 scenario e mod bank); actions are synthetic uniform fp32 in the action space, resident in HBM.
+
+THE TIMED WINDOW IS ALWAYS WHOLE EPISODES.  A stock episode is empty at night (c3: 57 of 112 steps have < 1 EV per
+env, 130 of 200 ports are occupied at the peak), so a window of a few steps measures either the idle path or the
+busy path and not the step path.  Whatever --steps / --warmup say, both arms (this one and --impl reference) and the
+e2e leg time `sweeps` full episodes of every env group, starting at t = 0, resets inside the timed region; --steps
+only sets the MINIMUM number of launches (rounded up to whole sweeps, and up again until the region lasts >= ~1 s of
+device time).  `steps` / `warmup` in the JSON line are the launches actually timed / warmed.
 
 L2 hygiene: the per-batch state (~25-40 MB) would sit in the 126 MB L2, so the timed loop ROTATES
 over G independent env groups whose total footprint is > 2x L2; every launch finds its data in HBM.
@@ -19,6 +26,7 @@ against MEASURED_PEAKS.json; `cpu_baseline` = the C oracle on the host cores (bo
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -47,6 +55,7 @@ WORKLOADS = {
            "V2GProfitMax.yaml, 8192 envs x 250 chargers x 1 port, 1 transformer, uniform actions"),
 }
 L2_BYTES = 126e6
+MIN_TIMED_SECONDS = 1.0
 
 
 def load_pack(name):
@@ -64,6 +73,27 @@ def load_pack(name):
 def algorithmic_bytes_per_env_step(topo, obs_dim):
     """B_step = 40 P + 8 C + 20 Tr + 16 (+ 4 D with observations)."""
     return 40 * topo.P + 8 * topo.C + 20 * topo.Tr + 16 + 4 * obs_dim
+
+
+def occupancy_aware_bytes_per_env_step(topo, obs_dim, series_len, tuple_len, n_connected):
+    """The same count with the per-port terms only for ports that hold an EV: 40 B per CONNECTED EV (hot words 16 R,
+    battery level 8 R + 8 W, exchanged energy 4, action 4) + 8 C + 20 Tr + 16, and of the observation only what a step
+    rewrites: the header, the (scenario, time) series and one tuple per connected EV."""
+    obs = 0
+    if obs_dim:
+        header = obs_dim - series_len - tuple_len * topo.P
+        obs = 4 * (header + series_len + tuple_len * n_connected)
+    return 40 * n_connected + 8 * topo.C + 20 * topo.Tr + 16 + obs
+
+
+def source_sha():
+    """Hash of the CUDA sources the library is built from: stamps profiles (roofline_traffic.json) to a build."""
+    h = hashlib.sha256()
+    for f in ("ev2b.cu", "ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_math.h"):
+        p = os.path.join(ROOT, "ev2gym_b200", "csrc", f)
+        if os.path.exists(p):
+            h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -102,8 +132,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(topo, scenarios, reward, state, E, target_seconds=12.0, threads=0):
-    """The C oracle (a port of the reference step; the reference itself is Python and cannot travel)."""
+def oracle_episodes(topo, scenarios, reward, state, E, n_episodes, warm_steps=3, threads=0, seconds=None):
+    """Whole episodes of E envs on the C oracle (the port of the reference step), all host threads.
+    n_episodes whole episodes, or (seconds given) as many whole episodes as fit, at least one."""
     from oracle.oracle import OracleBatch
     ob = OracleBatch(topo, [scenarios[e % len(scenarios)] for e in range(E)], reward=reward, state=state,
                      threads=threads)
@@ -111,54 +142,56 @@ def cpu_baseline(topo, scenarios, reward, state, E, target_seconds=12.0, threads
     low = -1.0 if topo.v2g_enabled else 0.0
     acts = [rng.uniform(low, 1.0, (E, topo.P)) for _ in range(4)]
     ob.reset()
-    for t in range(3):
+    for t in range(warm_steps):
         ob.step(acts[t % 4])
-    steps, t0 = 0, time.perf_counter()
+    steps, eps, t0 = 0, 0, time.perf_counter()
     while True:
-        if ob.states[0].current_step >= topo.T:
-            ob.reset()
-        ob.step(acts[steps % 4])
-        steps += 1
-        if time.perf_counter() - t0 > target_seconds:
+        ob.reset()                                       # a new episode (inside the timed region, as on the GPU)
+        for t in range(topo.T):
+            ob.step(acts[t % 4])
+        steps += topo.T
+        eps += 1
+        if seconds is None:
+            if eps >= n_episodes:
+                break
+        elif time.perf_counter() - t0 > seconds:
             break
     dt = time.perf_counter() - t0
-    return {"value": E * steps / dt, "unit": "env-steps/s", "cores": ob.threads, "kind": "port",
-            "sample": f"C oracle (oracle/ev2o.c, fp64, pthreads), {E} envs x {steps} steps incl. state+reward, "
-                      f"{dt:.1f} s; the Python reference itself measured 330 env-steps/s/core on this shape "
-                      f"(BASELINE.md) and cannot run on the GPU box"}
+    return E * steps / dt, steps, eps, dt, ob.threads
+
+
+def cpu_baseline(topo, scenarios, reward, state, E, target_seconds=12.0, threads=0):
+    """The C oracle (a port of the reference step; the reference itself is Python and cannot travel)."""
+    v, steps, eps, dt, thr = oracle_episodes(topo, scenarios, reward, state, E, 0, threads=threads,
+                                             seconds=target_seconds)
+    return {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
+            "sample": f"C oracle (oracle/ev2o.c, fp64, pthreads), {E} envs x {eps} whole episodes ({steps} steps) incl. "
+                      f"state+reward, {dt:.1f} s; the Python reference itself measured 330 env-steps/s/core on this "
+                      f"shape (BASELINE.md)"}
 
 
 def run_reference(args, wl):
-    """`--impl reference`: the reference's CPU implementation of the path = the oracle port, all host threads."""
+    """`--impl reference`: the reference's CPU implementation of the path = the oracle port, all host threads,
+    on the same window as the GPU arm: whole episodes of the workload's full batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     pack_name, E, reward, state, desc = WORKLOADS[wl]
     pack = load_pack(pack_name)
     topo = pack.topo
-    from oracle.oracle import OracleBatch
-    Es = E                                             # one step = the workload's full batch, as on the GPU
-    ob = OracleBatch(topo, [pack.scenarios[e % len(pack)] for e in range(Es)], reward=reward, state=state)
-    rng = np.random.default_rng(0)
-    low = -1.0 if topo.v2g_enabled else 0.0
-    acts = [rng.uniform(low, 1.0, (Es, topo.P)) for _ in range(4)]
-    ob.reset()
-    for w in range(args.warmup):
-        ob.step(acts[w % 4])
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        if ob.states[0].current_step >= topo.T:
-            ob.reset()
-        ob.step(acts[k % 4])
-    dt = time.perf_counter() - t0
-    v = Es * args.steps / dt
+    n_eps = max(1, -(-args.steps // topo.T))             # whole episodes covering at least --steps steps
+    v, steps, eps, dt, thr = oracle_episodes(topo, pack.scenarios, reward, state, E, n_eps,
+                                             warm_steps=max(3, args.warmup))
     print(json.dumps({
         "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic actions on reference-exported scenarios",
-        "config": {"workload": desc, "sample": f"full batch of {Es} envs per step, {args.steps} steps"},
-        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": ob.threads, "kind": "port",
-                         "sample": f"C oracle, {Es} envs x {args.steps} steps"},
+        "config": {"workload": desc, "envs_per_gpu": E, "chargers": topo.C, "ports": topo.P, "transformers": topo.Tr,
+                   "reward": reward, "state": state,
+                   "window": f"{eps} whole episodes (t = 0 .. {topo.T}) of the full batch of {E} envs, resets inside",
+                   "sample": f"full batch of {E} envs per step, {steps} steps"},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
+                         "sample": f"C oracle, {E} envs x {eps} whole episodes ({steps} steps)"},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -166,7 +199,7 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=448)
+    ap.add_argument("--steps", type=int, default=448, help="minimum number of timed launches (rounded up to whole episodes)")
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--skip-agent-rollout", action="store_true")
@@ -174,6 +207,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-obs", action="store_true", help="do not produce observations (heuristic-driven runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the distinct-scenario and c3-1k extra measurements")
+    ap.add_argument("--min-seconds", type=float, default=MIN_TIMED_SECONDS)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, args.workload)
@@ -195,86 +230,134 @@ def main():
     pack = load_pack(pack_name)
     topo = pack.topo
     outputs = ("reward", "status") if args.no_obs else ("reward", "status", "obs")
-    probe = BatchedEngine(topo, 1, reward=reward, state=state, device=local, outputs=outputs)
-    D = 0 if args.no_obs else probe.D
-    probe.close()
-    bytes_env_step = algorithmic_bytes_per_env_step(topo, D)
-    state_bytes = E * (28 * topo.P + 4 * topo.P + 4 * D + 150)       # hot+cap+exch, actions, obs, per-env
-    G = max(2, int(np.ceil(2.2 * L2_BYTES / state_bytes)))
-
-    engines = []
-    for g in range(G):
-        eng = BatchedEngine(topo, E, reward=reward, state=state, device=local, outputs=outputs)
-        eng.load_scenarios(pack.scenarios)
-        eng.reset(scn_ids=[(rank * E * G + g * E + e) % len(pack) for e in range(E)])
-        engines.append(eng)
     low = -1.0 if topo.v2g_enabled else 0.0
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    actions = [torch.rand((E, topo.P), device=dev, generator=gen) * (1.0 - low) + low for _ in range(G)]
     T = topo.T
 
-    # every group advances one step per "round"; all envs of a group finish together every T rounds
-    def round_(r):
-        for g in range(G):
-            engines[g].step(actions[(g + r) % G])
+    def build_groups(E_, scenarios, n_groups=None):
+        """G independent env groups (footprint > 2x L2), each with its own action tensor."""
+        probe = BatchedEngine(topo, 1, reward=reward, state=state, device=local, outputs=outputs)
+        D_ = 0 if args.no_obs else probe.D
+        probe.close()
+        state_bytes = E_ * (28 * topo.P + 4 * topo.P + 4 * D_ + 150)     # hot+cap+exch, actions, obs, per-env
+        G_ = n_groups or max(2, int(np.ceil(2.2 * L2_BYTES / state_bytes)))
+        engines_ = []
+        for g in range(G_):
+            eng = BatchedEngine(topo, E_, reward=reward, state=state, device=local, outputs=outputs)
+            eng.load_scenarios(scenarios)
+            engines_.append(eng)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        actions_ = [torch.rand((E_, topo.P), device=dev, generator=gen) * (1.0 - low) + low for _ in range(G_)]
+        # scenario of env e = e mod bank size (ev2b_reset's default: no host id array, so a reset can be graph-captured);
+        # every workload's E is a multiple of its bank size, so every group and rank covers the whole bank
+        return engines_, actions_, D_, state_bytes
 
-    def reset_all():
-        for g in range(G):
-            engines[g].reset()
+    def time_sweeps(engines_, actions_, min_steps, min_seconds, use_graph=True, collective=True):
+        """Times whole-episode sweeps: every group is reset and stepped T times (G * T launches per sweep).
+        Returns (elapsed_ms, n_sweeps, graphed)."""
+        G_ = len(engines_)
 
-    R = 4                                                            # rounds per graph replay (T % R == 0)
-    rounds_done = 0
-    n_warm_rounds = max(R, (args.warmup + G - 1) // G // R * R)
-    for r in range(n_warm_rounds):
-        round_(rounds_done); rounds_done += 1
-    torch.cuda.synchronize(dev)
-    graph = None
-    if not args.no_graph:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):                                # capture only: nothing executes here
-            for r in range(R):
-                round_(r)
-    torch.cuda.synchronize(dev)
+        def sweep():
+            for g in range(G_):
+                engines_[g].reset()
+            for r in range(T):
+                for g in range(G_):
+                    engines_[g].step(actions_[(g + r) % G_])
+        sweep()                                                         # warm-up: one whole episode of every group
+        torch.cuda.synchronize(dev)
+        graph = None
+        if use_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):                               # capture only: nothing executes here
+                sweep()
+        run = graph.replay if graph is not None else sweep
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        ev0.record(); run(); ev1.record()                              # calibration sweep (also warm-up of the graph)
+        torch.cuda.synchronize(dev)
+        one_ms = ev0.elapsed_time(ev1)
+        n = max(1, -(-min_steps // (G_ * T)), int(np.ceil(min_seconds * 1e3 / max(one_ms, 1e-3))))
+        if world > 1 and collective:                                    # every rank times the same number of sweeps
+            tn = torch.tensor([n], device=dev, dtype=torch.int64)
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+            n = int(tn.item())
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        for _ in range(n):
+            run()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1 and collective:
+            dist.barrier()
+        return ev0.elapsed_time(ev1), n, graph is not None
 
-    n_replays = max(1, args.steps // (G * R))
-    K = n_replays * G * R                                            # exactly K timed steps
+    def step_profile(engines_, actions_):
+        """us per launch at every episode step t >= 1: a one-round graph (G launches) replayed T - 1 times, CUDA events
+        between the replays (untimed extra; no collective)."""
+        G_ = len(engines_)
+        for g in range(G_):
+            engines_[g].reset()
+        for g in range(G_):                                             # round 0 eagerly: the capture below must see the
+            engines_[g].step(actions_[g % G_])                          # same obs_full / mask_full host state as later rounds
+        torch.cuda.synchronize(dev)
+        rg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(rg):
+            for g in range(G_):
+                engines_[g].step(actions_[g % G_])
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(T)]
+        evs[0].record()
+        for r in range(1, T):
+            rg.replay()
+            evs[r].record()
+        torch.cuda.synchronize(dev)
+        return [float("nan")] + [evs[r - 1].elapsed_time(evs[r]) * 1e3 / G_ for r in range(1, T)]
+
+    def occupancy_profile(engine):
+        """Mean connected EVs per env BEFORE each step t of an episode (from the hot words; untimed)."""
+        engine.reset()
+        hot = engine.state_tensors()["port_hot"]
+        occ = []
+        gen = torch.Generator(device=dev); gen.manual_seed(99)
+        for t in range(T):
+            w0 = hot[..., 0]
+            t_arr = ((w0 & 0xFFFF) ^ 0x8000) - 0x8000
+            t_dep = (((w0 >> 16) & 0xFFFF) ^ 0x8000) - 0x8000
+            occ.append(float(((t_arr <= t) & (t <= t_dep)).sum().item()) / engine.E)
+            a = torch.rand((engine.E, topo.P), device=dev, generator=gen) * (1.0 - low) + low
+            engine.step(a)
+        return occ
+
+    engines, actions, D, state_bytes = build_groups(E, pack.scenarios)
+    G = len(engines)
+    bytes_env_step = algorithmic_bytes_per_env_step(topo, D)
     launches0 = sum(e.launch_count for e in engines)
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    resets = 0
-    ev0.record()
-    for it in range(n_replays):
-        if rounds_done % T == 0:
-            reset_all(); resets += 1                                 # a new episode for every env (inside the timed region)
-        if graph is not None:
-            graph.replay()
-        else:
-            for r in range(R):
-                round_(rounds_done + r)
-        rounds_done += R
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms, n_sweeps, graphed = time_sweeps(engines, actions, args.steps, args.min_seconds,
+                                                use_graph=not args.no_graph)
     clocks = sampler.stop()
-    gpu_launches = K + resets * 2 * G
+    K = n_sweeps * G * T                                                # step launches inside the timed region
+    gpu_launches = K + n_sweeps * 2 * G                                 # + the two reset kernels per group and sweep
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     value = world * E * K / (elapsed_ms * 1e-3)
 
+    # per-step profile (us per launch at episode step t) and the occupancy it goes with -- rank 0's groups, untimed extras
+    prof = step_profile(engines, actions) if rank == 0 else None
+    occ = occupancy_profile(engines[0]) if rank == 0 else None
+
     # aggregate KPIs: the path's only collective (SURVEY.md section 8e): one small all-reduce(sum)
     kpi = sum(e.state_tensors()["env_kpi"].sum(dim=0) for e in engines)
     if world > 1:
         dist.all_reduce(kpi, op=dist.ReduceOp.SUM)
+
+    def reset_all():
+        for g in range(G):
+            engines[g].reset()
 
     # ---- k-step device-agent rollout (ev2b_step_k): no action tensor, no host round trip -----------------
     agent_rate = None
@@ -282,15 +365,17 @@ def main():
         if args.skip_agent_rollout:
             raise RuntimeError("skipped")
         reset_all()
+        for g in range(G):
+            engines[g].step_k(T, "uniform", seed=7 + g)                 # warm-up episode
+        reset_all()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kk = T - 1
         e0.record()
         for g in range(G):
-            engines[g].step_k(kk, "uniform", seed=7 + g)
+            engines[g].step_k(T, "uniform", seed=7 + g)                 # one call = one whole episode of the group
         e1.record()
         torch.cuda.synchronize(dev)
-        agent_rate = E * G * kk / (e0.elapsed_time(e1) * 1e-3)
+        agent_rate = E * G * T / (e0.elapsed_time(e1) * 1e-3)
     except Exception as exc:  # pragma: no cover
         agent_rate = f"failed: {exc}"
 
@@ -304,46 +389,53 @@ def main():
         actor = torch.nn.Sequential(torch.nn.Linear(D, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
                                     torch.nn.Linear(256, topo.P), torch.nn.Tanh() if low < 0 else torch.nn.Sigmoid()).to(dev)
         e_pol = engines[0]
-        obs = e_pol.reset()
         with torch.no_grad():
-            for _ in range(3):
+            obs = e_pol.reset()
+            for _ in range(T):
                 obs = e_pol.step(actor(obs))["obs"]
+            obs = e_pol.reset()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            kk = T - 8
             e0.record()
-            for _ in range(kk):
+            for _ in range(T):
                 obs = e_pol.step(actor(obs))["obs"]
             e1.record()
         torch.cuda.synchronize(dev)
-        policy_rate = E * kk / (e0.elapsed_time(e1) * 1e-3)
+        policy_rate = E * T / (e0.elapsed_time(e1) * 1e-3)
     except Exception as exc:  # pragma: no cover
         policy_rate = f"failed: {exc}"
 
-    # ---- end to end through the host-buffer API --------------------------------------------------
+    # ---- end to end through the host-buffer API: whole episodes, reset + T x step_host ---------------------
     eng = engines[0]
-    eng.reset()
     pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
     h_act = [pin((E, topo.P), torch.float32) for _ in range(2)]
     for a in h_act:
         a[:] = np.random.default_rng(5).uniform(low, 1.0, a.shape)
     h_rew, h_st = pin((E,), torch.float64), pin((E,), torch.int32).view(np.uint32)
     h_obs = pin((E, D), torch.float32) if D else None
-    n_e2e = min(T - 4, max(8, args.steps // 8))
-    for w in range(3):
-        eng.step_host(h_act[w % 2], h_rew, h_st, h_obs)
+    n_e2e_eps = max(2, -(-args.steps // (8 * T)))
+
+    def e2e_episode():
+        eng.reset()
+        for k in range(T):
+            eng.step_host(h_act[k % 2], h_rew, h_st, h_obs)
+    e2e_episode()                                                       # warm-up episode
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for k in range(n_e2e):
-        eng.step_host(h_act[k % 2], h_rew, h_st, h_obs)
+    for _ in range(n_e2e_eps):
+        e2e_episode()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    n_e2e = n_e2e_eps * T
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * E * n_e2e / float(te.item())
     e2e_step_ms = float(te.item()) / n_e2e * 1e3
+    e2e_bytes = eng.host_step_bytes() if hasattr(eng, "host_step_bytes") else None
+    if e2e_bytes is None:
+        e2e_bytes = {"h2d": E * topo.P * 4, "d2h": E * (8 + 4 + 4 * D)}
 
     # PCIe floor of one e2e step: the same bytes as plain pinned copies, each direction alone (the link is full duplex)
     def copy_ms(dst, src, n=20):
@@ -357,10 +449,45 @@ def main():
         c1.record()
         torch.cuda.synchronize(dev)
         return c0.elapsed_time(c1) / n
-    d2h_bytes, h2d_bytes = E * (8 + 4 + 4 * D), E * topo.P * 4
-    dbuf, hbuf = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev), torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
-    d2h_ms = copy_ms(hbuf, dbuf)
+    d2h_bytes, h2d_bytes = int(e2e_bytes["d2h"]), int(e2e_bytes["h2d"])
+    nb = max(d2h_bytes, h2d_bytes, 1)
+    dbuf, hbuf = torch.empty(nb, dtype=torch.uint8, device=dev), torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    d2h_ms = copy_ms(hbuf[:d2h_bytes], dbuf[:d2h_bytes])
     h2d_ms = copy_ms(dbuf[:h2d_bytes], hbuf[:h2d_bytes])
+
+    # ---- extras (rank 0 only, untimed for the headline): no scenario reuse between envs, and the 1k-env shape ----
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras and args.workload == "c3":
+        for eng_ in engines[1:]:
+            eng_.close()
+        try:   # one scenario per env: the bank is tiled to E physical copies, so no two envs share scenario memory
+            S = len(pack.scenarios)
+            big = [pack.scenarios[i % S] for i in range(E)]
+            engines2, actions2, _, sb2 = build_groups(E, big, n_groups=3)
+            ms2, n2, _ = time_sweeps(engines2, actions2, 1, 0.3, use_graph=not args.no_graph, collective=False)
+            us2 = ms2 * 1e3 / (n2 * 3 * T)
+            extras["distinct_scenarios"] = {
+                "us_per_launch": us2, "env_steps_per_s": E / (us2 * 1e-6), "bank": E,
+                "roofline_frac": bytes_env_step * E / (us2 * 1e-6) / 1e9 / 1.0,   # divided by the peak below
+                "what": f"same workload with one scenario PER ENV (the {S}-scenario bank tiled to {E} physical copies: "
+                        f"scenario rows are never shared between envs), 3 env groups, {n2} whole-episode sweeps"}
+            for e_ in engines2:
+                e_.close()
+        except Exception as exc:  # pragma: no cover
+            extras["distinct_scenarios"] = {"error": repr(exc)}
+        try:   # north_star shape: 1k envs x 100 chargers
+            E1 = 1024
+            engines3, actions3, _, _ = build_groups(E1, pack.scenarios)
+            ms3, n3, _ = time_sweeps(engines3, actions3, 1, 0.3, use_graph=not args.no_graph, collective=False)
+            us3 = ms3 * 1e3 / (n3 * len(engines3) * T)
+            extras["c3_1k"] = {"us_per_launch": us3, "env_steps_per_s": E1 / (us3 * 1e-6), "envs": E1,
+                               "roofline_frac": bytes_env_step * E1 / (us3 * 1e-6) / 1e9 / 1.0,
+                               "what": f"1024 envs x 100 chargers x 2 ports (north_star shape), {len(engines3)} env groups, "
+                                       f"{n3} whole-episode sweeps"}
+            for e_ in engines3:
+                e_.close()
+        except Exception as exc:  # pragma: no cover
+            extras["c3_1k"] = {"error": repr(exc)}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -368,46 +495,71 @@ def main():
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        for x in extras.values():
+            if "roofline_frac" in x:
+                x["roofline_frac"] /= peak
         launch_ms = elapsed_ms / K
-        traffic, traffic_src = None, None
+        sha = source_sha()
+        traffic, traffic_src, traffic_sha = None, None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath)).get(args.workload)
             if tj:
-                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+                traffic, traffic_src, traffic_sha = tj["dram_bytes_per_launch"], tj["source"], tj.get("source_sha")
         achieved = bytes_env_step * E / (launch_ms * 1e-3) / 1e9
+        series_len = {"V2G_profit_max": 20, "V2G_profit_max_loads": 20 + 40 * topo.Tr, "PublicPST": 0,
+                      "V2G_grid_state": 5 + 2 * topo.n_bus}.get(state, 0) if D else 0
+        tuple_len = {"PublicPST": 3, "V2G_grid_state": 3}.get(state, 2) if D else 0
+        occ_mean = float(np.mean(occ))
+        bytes_occ = float(np.mean([occupancy_aware_bytes_per_env_step(topo, D, series_len, tuple_len, n) for n in occ]))
+        achieved_occ = bytes_occ * E / (launch_ms * 1e-3) / 1e9
+        idle = [p for p, n in zip(prof, occ) if n < 1.0 and p == p]
+        busy = [p for p, n in zip(prof, occ) if n >= 1.0 and p == p]
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": n_warm_rounds * G, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": 2 * G * T, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (uniform fp32 actions on scenario banks exported "
                                                          "from the reference's reset())",
             "config": {"workload": desc, "envs_per_gpu": E, "chargers": topo.C, "ports": topo.P,
                        "transformers": topo.Tr, "obs_dim": D, "reward": reward, "state": state,
+                       "window": f"{n_sweeps} sweeps x {G} env groups x whole episodes (t = 0 .. {T}), resets inside "
+                                 f"the timed region; --steps {args.steps} / --warmup {args.warmup} requested",
                        "l2": f"rotating {G} independent env groups, {G * state_bytes / 1e6:.0f} MB total > 126 MB L2",
-                       "cuda_graph": graph is not None, "parallelism": f"env-sharded x{world}"},
+                       "cuda_graph": graphed, "parallelism": f"env-sharded x{world}"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": E * topo.P * 4,
-                    "d2h_bytes_per_step": E * (8 + 4 + 4 * D), "steps": n_e2e, "ms_per_step": e2e_step_ms,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "steps": n_e2e, "ms_per_step": e2e_step_ms,
+                    "window": f"{n_e2e_eps} whole episodes of one env group: reset + {T} x ev2b_step_host",
                     "pcie_floor": {"d2h_ms": d2h_ms, "h2d_ms": h2d_ms, "d2h_gbs": d2h_bytes / d2h_ms / 1e6,
                                    "h2d_gbs": h2d_bytes / h2d_ms / 1e6, "frac": max(d2h_ms, h2d_ms) / e2e_step_ms,
                                    "what": "the step's bytes as bare pinned cudaMemcpyAsync, each direction alone"},
                     "what": "ev2b_step_host: pinned host actions -> H2D -> fused kernel -> D2H reward+status+obs -> sync"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": bytes_env_step,
+                         "traffic": traffic, "traffic_source": traffic_src, "traffic_source_sha": traffic_sha,
+                         "source_sha": sha, "traffic_is_this_build": traffic_sha == sha,
+                         "peak_source": peak_src, "algorithmic_bytes_per_env_step": bytes_env_step,
+                         "occupancy_mean": occ_mean, "occupancy_peak": float(np.max(occ)), "ports": topo.P,
+                         "occupancy_aware_bytes_per_env_step": bytes_occ, "achieved_occupancy_aware": achieved_occ,
+                         "frac_occupancy_aware": achieved_occ / peak,
+                         "idle_step_us": float(np.mean(idle)) if idle else None, "idle_steps": len(idle),
+                         "busy_step_us": float(np.mean(busy)) if busy else None, "busy_steps": len(busy),
+                         "busiest_step_us": float(np.nanmax(prof)),
+                         "us_by_episode_step": [None if p != p else round(p, 2) for p in prof],
+                         "connected_evs_by_episode_step": [round(n, 1) for n in occ],
                          "kernel": "ev2b::evl_step_kernel" if engines[0].kernel_launches()[1] else "ev2b::step_kernel",
                          "kernel_launches": dict(zip(("step_kernel", "evl_step_kernel", "evl_rebuild_kernel"),
                                                      engines[0].kernel_launches())),
                          "launch_ms": launch_ms},
             "kpi_allreduce": {"total_reward": float(kpi[0].item()), "total_evs_served": float(kpi[5].item())},
             "device_agent_rollout": {"value": agent_rate, "unit": "env-steps/s per GPU",
-                                     "what": "ev2b_step_k, UNIFORM on-device agent, one call per episode and env group"},
+                                     "what": "ev2b_step_k, UNIFORM on-device agent, one call per whole episode and env group"},
             "policy_rollout": {"value": policy_rate, "unit": "env-steps/s per GPU",
                                "what": f"obs -> torch MLP actor ({D}-256-256-{topo.P}, fp32) on the GPU -> ev2b_step, one env "
-                                       "group (L2-resident), no host round trip"},
+                                       "group (L2-resident), one whole episode, no host round trip"},
+            "extras": extras,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(topo, pack.scenarios, reward, state if D else None, E)
         print(json.dumps(line))
     if world > 1:

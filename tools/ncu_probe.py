@@ -14,13 +14,14 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bench import WORKLOADS, load_pack   # noqa: E402
+from tools.ab_kernels import set_variant   # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--steps", type=int, default=32)
-    ap.add_argument("--variants", default="percharger:0,evlist:1,evlist:2,evlist:4")
+    ap.add_argument("--variants", default="percharger,evl:G=1,evl:G=2,evl:G=4", help="tools/ab_kernels.py syntax")
     args = ap.parse_args()
     import torch
     from ev2gym_b200.engine import BatchedEngine
@@ -30,9 +31,7 @@ def main():
     dev = torch.device("cuda", 0)
     low = -1.0 if topo.v2g_enabled else 0.0
     for v in args.variants.split(","):
-        kernel, G = v.split(":")
-        os.environ["EV2B_KERNEL"] = kernel
-        os.environ["EV2B_EVL_G"] = G if G != "0" else ""
+        set_variant(v)
         eng = BatchedEngine(topo, E, reward=reward, state=state)
         eng.load_scenarios(pack.scenarios)
         eng.reset()
