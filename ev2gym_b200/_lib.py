@@ -67,6 +67,8 @@ class StateView(C.Structure):
                 ("env_usage", C.c_void_p), ("env_kpi", C.c_void_p)]
 
 
+ABI_VERSION = 2          # EV2B_ABI_VERSION of include/ev2b.h this binding was written against
+
 EXPORTS = ("ev2b_abi_version", "ev2b_last_error", "ev2b_create", "ev2b_destroy", "ev2b_obs_dim", "ev2b_n_ports",
            "ev2b_load_scenarios", "ev2b_n_scenarios", "ev2b_reset", "ev2b_step", "ev2b_step_host",
            "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count", "ev2b_episode_stats", "ev2b_step_k",
@@ -144,7 +146,7 @@ def load():
     L.ev2b_launch_count.argtypes = [C.c_void_p]
     L.ev2b_kernel_launches.restype = C.c_int64
     L.ev2b_kernel_launches.argtypes = [C.c_void_p, C.c_int]
-    if L.ev2b_abi_version() != 1:
+    if L.ev2b_abi_version() != ABI_VERSION:
         raise RuntimeError("libev2b.so ABI version mismatch")
     _lib = L
     return L

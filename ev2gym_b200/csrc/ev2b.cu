@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <numeric>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -67,7 +69,7 @@ struct ev2b_handle {
     DevBuf<EnvT> env_t; DevBuf<TrT> tr_t; DevBuf<SessRec> sess; DevBuf<EvSpec> spec;
     DevBuf<double> luts_c, luts_d, pot_kw; DevBuf<float> trA, trF, tr_limit, obs_static; DevBuf<DrEv> dr; DevBuf<uint8_t> dr_count;
     // device: state
-    DevBuf<uint4> hot; DevBuf<double> cap; DevBuf<float> exch; DevBuf<int> env_step, env_scn;
+    DevBuf<uint4> hot; DevBuf<double> cap, exch; DevBuf<int> env_step, env_scn;
     DevBuf<double> env_pot, env_usage, env_kpi, env_pot_prev;
     // device: statistics mode
     int L = 1;
@@ -91,24 +93,25 @@ struct ev2b_handle {
     bool evl = false;                   // lists allocated, schedule built
     bool list_valid = true;             // occ_list / occ_n agree with the hot words of every env
     int evl_G = 4, evl_o[13] = {0};     // warps per env; smem map (v_stride, v_amp, ...)
-    bool evl_stage = false;             // EV2B_EVL_STAGE=1: the STG instantiation (EV records staged with cp.async); A/B only
-    int evl_pf = 0, n_sm = 148;         // EV2B_EVL_PREFETCH bits (ev2b_evlist.cuh); A/B only
+    int n_sm = 148;
+    bool evl_mix = false;               // EV2B_EVL_MIX=1 (tests): launches that ask for port_energy take step_kernel
     size_t evl_smem = 0;
-    DevBuf<uint16_t> occ_list; DevBuf<int> occ_n, arr_off; DevBuf<unsigned> arr_list;
+    std::set<const void *> smem_opted;  // kernels whose dynamic shared-memory limit has been raised on this device
+    DevBuf<uint16_t> occ_list; DevBuf<int> occ_n; DevBuf<unsigned> arr_list;
+    bool evl_heavy_layout() const { return (dims.flags & EV2B_F_STATS) != 0 || n_bus > 0; }
     void layout_evl() {
         size_t off = 0;
         auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; const size_t at = off; off += bytes; return (int)at; };
         const size_t pp = (cs_uniform && np_uniform == 1) ? 0 : (size_t)P;   // one port per charger: no per-port staging
         take(8 * pp, 16);                                          // pw
         evl_o[1] = take(8 * pp, 8); evl_o[2] = take(8 * pp, 8); evl_o[3] = take(8 * (size_t)C, 8);   // amp, pot, csP
-        evl_o[4] = take(8 * (size_t)(kPreTr + 4 * Tr), 16);        // pre (cp.async 16 B destinations)
+        evl_o[4] = take(8 * (size_t)(kEvlTr + 4 * Tr), 16);        // pre (cp.async 16 B destinations)
         evl_o[5] = take(8 * (size_t)EvlNSum * evl_G, 8);           // wsum
-        evl_o[6] = take(8 * (size_t)Tr, 8);                        // trov
         evl_o[7] = take(2 * (size_t)P, 4);                         // stage
         evl_o[8] = take((pp + 3) / 4 * 4, 4);                      // occ
-        if (evl_stage) {
-            evl_o[9] = take(16 * (size_t)P, 16); evl_o[10] = take(8 * (size_t)P, 8);    // s_hot, s_cap
-            evl_o[12] = take(8 * (size_t)P, 8); evl_o[11] = take(4 * (size_t)P, 4);      // s_act, s_exch
+        if (n_bus > 0) { evl_o[6] = take(8 * (size_t)Tr, 8); evl_o[9] = take(16 * 3 * (size_t)n_bus, 16); }   // trp, pfv
+        if ((dims.flags & EV2B_F_STATS) && pp) {                   // dsat, dcal, dcyc
+            evl_o[10] = take(8 * pp, 8); evl_o[11] = take(8 * pp, 8); evl_o[12] = take(8 * pp, 8);
         }
         evl_o[0] = (int)((off + 15) / 16 * 16);                    // stride
         evl_smem = (size_t)evl_o[0] * (kEvlThreads / (32 * evl_G));
@@ -127,7 +130,7 @@ struct ev2b_handle {
         so[7] = take(8 * epb * kNRed, 8);                          // envs
         so[14] = take(8 * epb * pre_stride, 16);                   // pre
         so[8] = take(8 * PP, 8);                                   // whot
-        so[9] = take(4 * nt, 4); so[10] = take(16 * epb, 4); so[11] = take(4 * PP, 4); so[12] = take(16, 4);   // cnt, envi, wl, wcnt
+        so[9] = take(4 * nt, 4); so[10] = take(32 * epb, 4); so[11] = take(4 * PP, 4); so[12] = take(16, 4);   // cnt, envi, wl, wcnt
         so[13] = take(PP, 1);                                      // pflag
         smem = off;
     }
@@ -169,12 +172,18 @@ struct ev2b_handle {
         p.pot_kw = pot_kw.p; p.trA = trA.p; p.trF = trF.p; p.tr_limit = tr_limit.p; p.dr = dr.p; p.dr_count = dr_count.p;
         p.hot = hot.p; p.cap = cap.p; p.exch = exch.p; p.env_step = env_step.p; p.env_scn = env_scn.p;
         p.env_pot = env_pot.p; p.env_usage = env_usage.p; p.env_kpi = env_kpi.p; p.env_pot_prev = env_pot_prev.p;
-        p.occ_list = occ_list.p; p.occ_n = occ_n.p; p.arr_off = arr_off.p; p.arr_list = arr_list.p;
+        p.occ_list = occ_list.p; p.occ_n = occ_n.p; p.arr_list = arr_list.p;
         p.v_stride = evl_o[0]; p.v_amp = evl_o[1]; p.v_pot = evl_o[2]; p.v_csP = evl_o[3]; p.v_pre = evl_o[4];
         { int lg = 0; while ((2 << lg) * Tr <= 32) ++lg; p.tr_lg = lg; }
-        p.v_shot = evl_o[9]; p.v_scap = evl_o[10]; p.v_sexch = evl_o[11]; p.v_sact = evl_o[12];
-        p.evl_pf = evl_pf; p.evl_pf_dist = n_sm * 8 * (kEvlThreads / (32 * evl_G));
-        p.v_wsum = evl_o[5]; p.v_trov = evl_o[6]; p.v_stage = evl_o[7]; p.v_occ = evl_o[8];
+        p.v_wsum = evl_o[5]; p.v_trp = evl_o[6]; p.v_stage = evl_o[7]; p.v_occ = evl_o[8]; p.v_pfv = evl_o[9];
+        p.v_dsat = evl_o[10]; p.v_dcal = evl_o[11]; p.v_dcyc = evl_o[12];
+        {   // auto-reset stride: E mod S (so that with E < S consecutive episodes walk the bank), made coprime to S --
+            // when E is a multiple of S that is 1: every env visits every scenario instead of replaying its first one
+            int st = S > 0 ? E % S : 0;
+            if (st == 0) st = 1;
+            while (S > 1 && std::gcd(st, S) != 1) ++st;
+            p.scn_stride = st;
+        }
         p.rr_key = rr_key.p; p.rr_fb = rr_fb.p; p.rr_avg_power = rr_avg_power; p.rr_share = rr_share;
         return p;
     }
@@ -200,10 +209,21 @@ static int obs_dim_for(int kind, int P, int Tr) {
 static bool needs_heavy(const ev2b_handle *h) {
     return (h->dims.flags & EV2B_F_STATS) != 0 || h->n_bus > 0 || h->dims.reward_kind >= EV2B_REWARD_SQTR_TR_USER;
 }
-// Does the event-driven kernel cover a launch with these outputs?  (it has no per-port optional outputs)
+// Does the event-driven kernel serve this handle's launches?  (it covers every feature; the choice is made at create time)
 static bool evl_covers(const ev2b_handle *h, const ev2b_step_out *o) {
-    if (!h->evl) return false;
-    return !o || !(o->dep_sat || o->dep_cap || o->port_energy || o->node_voltage);
+    if (h->evl_mix && o && o->port_energy) return false;   // test-only (EV2B_EVL_MIX=1): exercise both kernels on one handle
+    return h->evl;
+}
+
+// Raises a kernel's dynamic shared-memory limit once per handle (not on every launch).
+template <typename K>
+static cudaError_t opt_in_smem(ev2b_handle *h, K kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    const void *key = reinterpret_cast<const void *>(kern);
+    if (h->smem_opted.count(key)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) h->smem_opted.insert(key);
+    return e;
 }
 
 template <typename ActT>
@@ -211,17 +231,17 @@ static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st) 
     const int epb = kEvlThreads / (32 * h->evl_G);
     const unsigned grid = (unsigned)((p.env_end - p.env0 + epb - 1) / epb);
     auto go = [&](auto kern) -> cudaError_t {
-        if (h->evl_smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->evl_smem);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = opt_in_smem(h, kern, h->evl_smem);
+        if (e != cudaSuccess) return e;
         EV2B_LAUNCH(kern, grid, kEvlThreads, h->evl_smem, st, p);
         return cudaGetLastError();
     };
     const int np = (h->cs_uniform && (h->np_uniform == 1 || h->np_uniform == 2)) ? h->np_uniform : 0;
+    // HEAVY: statistics mode, the distribution grid, the dense per-port outputs
+    const bool heavy = h->evl_heavy_layout() || p.out.dep_sat || p.out.dep_cap || p.out.port_energy || p.out.node_voltage;
 #define EV2B_EVL_DISPATCH(G)                                                   \
     do {                                                                       \
-        if (h->evl_stage) {                                                    \
+        if (heavy) {                                                           \
             if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, true>);   \
             if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, true>);   \
             return go(evl_step_kernel<ActT, 0, false, G, true>);               \
@@ -251,10 +271,8 @@ template <typename ActT>
 static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st) {
     const unsigned grid = (unsigned)((p.env_end - p.env0 + h->EPB - 1) / h->EPB);
     auto go = [&](auto kern) -> cudaError_t {
-        if (h->smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = opt_in_smem(h, kern, h->smem);
+        if (e != cudaSuccess) return e;
         EV2B_LAUNCH(kern, grid, h->block, h->smem, st, p);
         return cudaGetLastError();
     };
@@ -306,9 +324,6 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         g_create_error = "ev2b_create: sizes must be >= 1"; return EV2B_E_ARG;
     }
     if (d->sim_length > 32000) { g_create_error = "ev2b_create: sim_length > 32000 (int16 step fields)"; return EV2B_E_LIMIT; }
-    if (d->n_chargers > kMaxThreads) {
-        g_create_error = "ev2b_create: more than 1024 chargers per env is not supported yet"; return EV2B_E_LIMIT;
-    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         g_create_error = "ev2b_create: no CUDA device (this library has no CPU fallback)"; return EV2B_E_CUDA;
@@ -426,7 +441,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         for (int epb = 1; epb <= 64 && epb <= h->E; ++epb) {
             const int thr = epb * C;
-            if (thr > cap_thr) break;
+            if (thr > cap_thr) break;               // (C > 1024: no step_kernel shape; the event-driven kernel serves the handle)
             // packing several small envs into a CTA fills the last warp, but only pays once the grid still has a few
             // CTAs per SM to overlap their serial phases (c2, 1024 x 25: 8.8 us with 1 env per CTA, 10.1 us with 5)
             if (epb > 1 && (h->E + epb - 1) / epb < 4 * n_sm) break;
@@ -439,7 +454,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
             if (v >= 1 && v <= h->E && v * C <= kMaxThreads) best_epb = v;
         }
         h->EPB = best_epb;
-        h->block = std::max(32, (best_epb * C + 31) / 32 * 32);
+        h->block = std::min(kMaxThreads, std::max(32, (best_epb * C + 31) / 32 * 32));
         h->layout_smem();
     }
     // Which step kernel serves this handle (ev2b_evlist.cuh).  The event-driven kernel wins once the batch fills the
@@ -450,20 +465,23 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         const char *kv = getenv("EV2B_KERNEL");
         const bool force_on = kv && (!strcmp(kv, "evlist") || !strcmp(kv, "evl"));
         const bool force_off = kv && !strcmp(kv, "percharger");
-        const bool want = force_on || (!force_off && h->E >= 2048);
-        const bool in_scope = !(h->dims.flags & EV2B_F_STATS) && h->n_bus == 0;   // no statistics mode, no distribution grid
-        if (want && in_scope && h->P < 65535) {
+        const bool big = C > kMaxThreads || h->smem > 200 * 1024;     // beyond step_kernel's one-thread-per-charger shape
+        const bool want = force_on || big || (!force_off && h->E >= 2048);
+        if (want && h->P < 65535) {
             h->evl = true;
             // warps per env: two for the stock env sizes (B200, us per launch, G = 1 / 2 / 4: c3 34.3 / 31.7 / 38.4,
             // c4 64.8 / 50.2 / 59.7), one for small envs (a warp already covers every connected EV), four for very large ones
             h->evl_G = h->P <= 64 ? 1 : (h->P <= 512 ? 2 : 4);
             if (const char *gv = getenv("EV2B_EVL_G")) { const int v = atoi(gv); if (v == 1 || v == 2 || v == 4) h->evl_G = v; }
-            if (const char *sv = getenv("EV2B_EVL_STAGE")) h->evl_stage = atoi(sv) != 0;          // unmeasured experiments,
-            if (const char *pv = getenv("EV2B_EVL_PREFETCH")) h->evl_pf = atoi(pv) & 3;          // off by default
+            if (const char *mv = getenv("EV2B_EVL_MIX")) h->evl_mix = atoi(mv) != 0 && !big;
             cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
             h->layout_evl();
             if (h->evl_smem > 200 * 1024) { h->evl_G = 4; h->layout_evl(); }
             if (h->evl_smem > 200 * 1024) h->evl = false;          // does not fit: step_kernel takes every launch
+        }
+        if (!h->evl && big) {
+            delete h; g_create_error = "ev2b_create: env too large (per-env working set exceeds shared memory, or >= 65535 ports)";
+            return EV2B_E_LIMIT;
         }
     }
 #define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
@@ -497,7 +515,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
     }
     CREATE_TRY(cudaMemset(h->hot.p, 0, EP * sizeof(uint4)));
     CREATE_TRY(cudaMemset(h->cap.p, 0, EP * sizeof(double)));
-    CREATE_TRY(cudaMemset(h->exch.p, 0, EP * sizeof(float)));
+    CREATE_TRY(cudaMemset(h->exch.p, 0, EP * sizeof(double)));
     CREATE_TRY(cudaMemset(h->env_scn.p, 0, h->E * sizeof(int)));
     CREATE_TRY(cudaMemset(h->env_pot.p, 0, h->E * sizeof(double)));
     CREATE_TRY(cudaMemset(h->env_usage.p, 0, h->E * sizeof(double)));
@@ -697,7 +715,9 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
         for (int t = 0; t < T; ++t) {
             EnvT &e = env_t[(size_t)i * T + t];
             e.cp = b->charge_price[(size_t)i * T + t]; e.dp = b->discharge_price[(size_t)i * T + t];
-            e.setpoint = b->setpoint[(size_t)i * T + t]; e.pad = 0;
+            e.setpoint = b->setpoint[(size_t)i * T + t];
+            const int *ao = arr_off_h.data() + (size_t)i * (T + 2);      // the step that starts at t spawns the arrivals of t + 1
+            e.arr0 = ao[t + 1]; e.n_arr = ao[t + 2] - ao[t + 1];
         }
         for (int k = 0; k < Tr; ++k) {
             const size_t base = ((size_t)i * Tr + k) * T;
@@ -743,7 +763,7 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
     CUDA_TRY(h, h->tr_limit.upload(tr_limit)); CUDA_TRY(h, h->dr.upload(dr)); CUDA_TRY(h, h->dr_count.upload(dr_count));
     if (h->evl) {
         if (arr_list_h.empty()) arr_list_h.push_back(0u);
-        CUDA_TRY(h, h->arr_off.upload(arr_off_h)); CUDA_TRY(h, h->arr_list.upload(arr_list_h));
+        CUDA_TRY(h, h->arr_list.upload(arr_list_h));
         h->list_valid = true;            // every env reads as done until it is reset, and reset empties its list
     }
     h->S = S; h->Smax = Smax; h->n_dr = n_dr; h->lut_len = lut_len;
@@ -855,6 +875,7 @@ static int step_range(ev2b_handle *h, const void *actions, int action_dtype, con
 int ev2b_step(ev2b_handle *h, const void *actions, int action_dtype, const ev2b_step_out *out, void *stream) {
     if (!h || !actions) return h ? h->fail(EV2B_E_ARG, "step: null actions") : EV2B_E_ARG;
     if (h->S == 0) return h->fail(EV2B_E_STATE, "step: no scenario bank loaded");
+    CUDA_TRY(h, cudaSetDevice(h->device));
     const float *obs = out ? out->obs : nullptr;
     const int obs_full = (obs != h->last_obs) ? 1 : 0;
     h->last_obs = obs;
@@ -879,7 +900,7 @@ int ev2b_agent_actions(ev2b_handle *h, int agent_kind, double *actions_out, void
     }
     const int thr = std::min(kMaxThreads, std::max(32, (h->P + 31) / 32 * 32));
     const size_t sm = (size_t)h->P * 5 + 16;
-    if (sm > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(agent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CUDA_TRY(h, opt_in_smem(h, agent_kernel, sm));
     EV2B_LAUNCH(agent_kernel, h->E, thr, sm, st, h->params(), agent_kind, actions_out);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
@@ -891,6 +912,7 @@ int ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, in
     if (!h) return EV2B_E_ARG;
     if (h->S == 0) return h->fail(EV2B_E_STATE, "step_k: no scenario bank loaded");
     if (k < 1) return h->fail(EV2B_E_ARG, "step_k: k must be >= 1");
+    CUDA_TRY(h, cudaSetDevice(h->device));
     if (agent_kind < EV2B_AGENT_EXTERNAL || agent_kind > EV2B_AGENT_CALAP) return h->fail(EV2B_E_ARG, "step_k: unknown agent %d", agent_kind);
     const bool tensor_agent = agent_kind == EV2B_AGENT_ROUNDROBIN || agent_kind == EV2B_AGENT_CALAP;   // needs the whole env's state
     if (tensor_agent && h->agent_act.n < (size_t)h->E * h->P) CUDA_TRY(h, h->agent_act.alloc((size_t)h->E * h->P));

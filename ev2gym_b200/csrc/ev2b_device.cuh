@@ -82,7 +82,9 @@ static_assert(sizeof(EvSpec) == 128, "EvSpec must be 128 B");
 struct SessRec { uint4 hot; double cap0; double afap; };  // cold table, read once per arrival; afap: ev.py:407-440
 static_assert(sizeof(SessRec) == 32, "SessRec must be 32 B");
 
-struct EnvT { double cp, dp, setpoint, pad; };            // per (scenario, t)
+struct EnvT { double cp, dp, setpoint; int arr0, n_arr; };  // per (scenario, t); the sessions arriving at step t+1 are
+                                                            // arr_list[arr0 .. arr0 + n_arr)  (ev2b_evlist.cuh)
+static_assert(sizeof(EnvT) == 32, "EnvT must be 32 B");
 struct TrT  { double infl, solar, maxp, minp; };          // per (scenario, t, transformer)
 struct DrEv { int16_t start, end; float value; };         // value = limit - limit*cap/100  transformer.py:158-163
 
@@ -131,15 +133,15 @@ struct Params {
     // event-driven step kernel (ev2b_evlist.cuh): connected-EV list per env, arrival schedule per scenario, smem map
     uint16_t *occ_list;        // [E][P] ports holding an EV (first occ_n[e] entries); null: kernel not in use
     int *occ_n;                // [E]
-    const int *arr_off;        // [S][T+2]: the sessions arriving at step q are arr_list[arr_off[s][q] .. arr_off[s][q+1])
-    const unsigned *arr_list;  // port | session index on that port << 16, arrival-sorted
+    const unsigned *arr_list;  // port | session index on that port << 16, arrival-sorted; bucket of a step: see EnvT
     int tr_lg;                 // 2^tr_lg lanes share one transformer in the CSR sums (largest with 2^tr_lg * Tr <= 32)
-    int v_stride, v_amp, v_pot, v_csP, v_pre, v_wsum, v_trov, v_stage, v_occ;   // byte offsets inside one env's block
-    int v_shot, v_scap, v_sexch, v_sact;   // staged EV records (evl_step_kernel<..., STG = true>)
+    int v_stride, v_amp, v_pot, v_csP, v_pre, v_wsum, v_stage, v_occ;   // byte offsets inside one env's block
+    int v_trp, v_pfv, v_dsat, v_dcal, v_dcyc;   // HEAVY instantiation only (grid / statistics mode)
     int mask_full;             // 1: out.action_mask does not hold last step's rows (evl_step_kernel rewrites them)
-    int evl_pf, evl_pf_dist;   // L2 prefetch experiments: bit 0 later EVs of the thread, bit 1 the env `evl_pf_dist` envs ahead
+    int scn_stride;            // auto-reset: next scenario = (current + scn_stride) mod S, gcd(scn_stride, S) = 1
     // state
-    uint4 *hot; double *cap; float *exch; int *env_step; int *env_scn; double *env_pot; double *env_usage;
+    uint4 *hot; double *cap; double *exch;   // exch: float64 like the reference's total_energy_exchanged (ev.py:178)
+     int *env_step; int *env_scn; double *env_pot; double *env_usage;
     double *env_pot_prev;      // charge_power_potential[t-1], kept only for SquaredTrackingErrorRewardWithPenalty (reward.py:50)
     double *env_kpi;
     // io
@@ -379,8 +381,9 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
 
 // ---- statistics mode: what EV.get_battery_degradation / get_statistics need of one EV ----------
 // Called when the EV leaves (or at the last step for EVs still connected).  ev.py:442-521, utils.py:49-63
-__device__ EV2B_NOINLINE void finalize_ev(const Params &p, size_t ip, int e_c, const EvSpec *sp, double afap,
-                                         int t_arr, int t_dep, double cap_final) {
+// Returns the EV's calendar / cyclic degradation (the caller adds them to its charger's totals, in port order).
+__device__ EV2B_NOINLINE void finalize_ev(const Params &p, size_t ip, const EvSpec *sp, double afap,
+                                         int t_arr, int t_dep, double cap_final, double &d_cal_out, double &d_cyc_out) {
     const double e0 = 7.543e6, e1 = 23.75e6, z0 = 7.348e-3, z1 = 3.667, z2 = 7.6e-4, z3 = 4.081e-3;
     const double k = 0.8263, v_min = 3.3324, b_cap_kwh = 78;
     const double B = __ldg(&sp->B);
@@ -400,8 +403,8 @@ __device__ EV2B_NOINLINE void finalize_ev(const Params &p, size_t ip, int e_c, c
     const double v_half = v_min + k * 0.5;
     const double beta = z0 * (v_half - z1) * (v_half - z1) + z2 + z3 * delta_dod;
     const double d_cyc = beta * (p.st_abs_e[ip] / b_cap_kwh) * p.k_cyc;
-    p.cs_dcal[e_c] += d_cal;
-    p.cs_dcyc[e_c] += d_cyc;
+    d_cal_out = d_cal;
+    d_cyc_out = d_cyc;
     const int k_fin = p.st_nfin[ip];
     p.st_r[ip * (size_t)p.Smax + k_fin] = (cap_final / afap) * 100.0;      // utils.py:59-62
     p.st_nfin[ip] = k_fin + 1;
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
     double *pre   = reinterpret_cast<double *>(smem_raw + p.o_pre);       // [EPB][pre_stride] prefetched per-env records
     uint2  *whot  = reinterpret_cast<uint2 *>(smem_raw + p.o_whot);       // [PP] hot words z, w of work items
     int    *cnt   = reinterpret_cast<int *>(smem_raw + p.o_cnt);          // [NT] invalid | dep<<10 | arr<<20
-    int    *envi  = reinterpret_cast<int *>(smem_raw + p.o_envi);         // [EPB][4] t, scn, cnt, flags
+    int    *envi  = reinterpret_cast<int *>(smem_raw + p.o_envi);         // [EPB][8] t, scn, -, flags, invalid, departures, arrivals, -
     int    *wl    = reinterpret_cast<int *>(smem_raw + p.o_wl);           // [PP] work list (port_local)
     int    *wcnt  = reinterpret_cast<int *>(smem_raw + p.o_wcnt);         // [1] (+3 pad)
     signed char *pflag = reinterpret_cast<signed char *>(smem_raw + p.o_pflag);   // [PP] ragged path only
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
     int invalid = 0;
     int port0 = 0, n = 0;
     double pre_cp = 0.0, pre_dp = 0.0;     // prices of this step, fetched before the first barrier
-    float exch0[NPR];
+    double exch0[NPR];
     if (valid) {
         t = p.env_step[e];
         s = p.env_scn[e];
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                                 reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * (i - 2));
             }
         }
-        if (c == 0) { envi[el * 4 + 0] = t; envi[el * 4 + 1] = s; envi[el * 4 + 2] = 0; envi[el * 4 + 3] = 0; }
+        if (c == 0) { envi[el * 8 + 0] = t; envi[el * 8 + 1] = s; envi[el * 8 + 2] = 0; envi[el * 8 + 3] = 0; }   // [4..6] are written in phase B
     }
     __syncthreads();
 
@@ -554,7 +557,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
             for (int j = 0; j < NP; ++j) {
                 const bool occ = hot_t_arr(h[j]) <= t && t <= hot_t_dep(h[j]);
                 capv[j] = occ ? p.cap[pbase + j] : 0.0;
-                exch0[j] = occ ? p.exch[pbase + j] : 0.f;
+                exch0[j] = occ ? p.exch[pbase + j] : 0.0;
                 if (!occ) { a[j] = 0.0; ++invalid; }                     // ev_charger.py:137-140
                 sum = sum + a[j];                                        // python sum(), left to right  :143
             }
@@ -600,9 +603,9 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
         for (int jel = 0; jel < p.EPB; ++jel) {
             const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
             if (je >= p.env_end) break;
-            const int jt = envi[jel * 4 + 0];
+            const int jt = envi[jel * 8 + 0];
             if (jt >= p.T) continue;
-            const int js = envi[jel * 4 + 1];
+            const int js = envi[jel * 8 + 1];
             for (int i = tid; i < p.W; i += NT)
                 p.out.obs[(size_t)je * p.D + p.series_off[i]] = obs_series_fetch(p, js, jt + 1, i);
         }
@@ -658,14 +661,14 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
             const bool occ = hot_t_arr(hj) <= t && t <= hot_t_dep(hj);
             double energy = 0.0, act_amps = 0.0;
             const double cv_old = cv;
-            float exch_new = 0.f; bool exch_valid = false;
+            double exch_new = 0.0; bool exch_valid = false;
             if (was_item) {
                 energy = resE[pl];
                 const double cnew = resC[pl];
                 if (cnew >= 0.0) {                                        // the EV was active this step
                     cv = cnew;
                     p.cap[ip] = cv;
-                    exch_new = (NP > 0 ? exch0[j] : p.exch[ip]) + (float)energy;   // total_energy_exchanged  ev.py:178
+                    exch_new = (NP > 0 ? exch0[j] : p.exch[ip]) + energy;   // total_energy_exchanged  ev.py:178
                     exch_valid = true;
                     p.exch[ip] = exch_new;
                 }
@@ -711,7 +714,9 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                     const size_t ec = (size_t)e * p.C + c;
                     p.cs_sat_sum[ec] += sat; p.cs_served[ec] += 1;          // ev_charger.py:218-220
                     const SessRec r0 = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj) - 1];
-                    finalize_ev(p, ip, (int)ec, p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj), hot_t_dep(hj), cv);
+                    double d1, d2;
+                    finalize_ev(p, ip, p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj), hot_t_dep(hj), cv, d1, d2);
+                    p.cs_dcal[ec] += d1; p.cs_dcyc[ec] += d2;
                 }
             }
             if (EV2B_OPT(p.out.dep_sat)) p.out.dep_sat[ip] = dsat;
@@ -724,8 +729,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                 cv = r.cap0;
                 p.hot[ip] = hj;
                 p.cap[ip] = cv;
-                p.exch[ip] = 0.f;
-                exch_new = 0.f; exch_valid = true;
+                p.exch[ip] = 0.0;
+                exch_new = 0.0; exch_valid = true;
                 rCnt += 1 << 20;
                 if (HEAVY && p.stats) { p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0; }
             }
@@ -733,8 +738,10 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
             if (EV2B_OPT(p.out.action_mask)) p.out.action_mask[ip] = occ_after ? 1 : 0;          // ev2gym_env.py:452-457
             if (HEAVY && p.stats && occ_after && tq >= p.T) {   // episode over: EVs still connected count too (env.EVs)
                 const SessRec r0 = p.sess[((size_t)s * p.P + port0 + j) * p.Smax + hot_cursor(hj) - 1];
-                finalize_ev(p, ip, (int)((size_t)e * p.C + c), p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj),
-                            hot_t_dep(hj), cv);
+                const size_t ec = (size_t)e * p.C + c;
+                double d1, d2;
+                finalize_ev(p, ip, p.spec + hot_spec(hj), r0.afap, hot_t_arr(hj), hot_t_dep(hj), cv, d1, d2);
+                p.cs_dcal[ec] += d1; p.cs_dcyc[ec] += d2;
             }
             if (occ_after) {
                 const EvSpec *sp = p.spec + hot_spec(hj);
@@ -758,7 +765,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                         o[2] = (float)__ldg(&p.cs_tr[c]);     // cs.connected_bus (cs0 is shared in the uniform layout)
                     } else if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
                         o[0] = (cv == B) ? 1.f : 0.5f;
-                        o[1] = exch_valid ? exch_new : (NP > 0 ? exch0[j] : p.exch[ip]);
+                        o[1] = (float)(exch_valid ? exch_new : (NP > 0 ? exch0[j] : p.exch[ip]));
                         o[2] = (float)(tq - hot_t_arr(hj));
                     } else {
                         o[0] = (float)ev2b_div_c(cv, B, __ldg(&sp->rB));
@@ -774,7 +781,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
         // clamp the charger's potential                      utils.py:779-789
         if (rPot > cs.max_power) rPot = cs.max_power;
         else if (rPot < cs.min_power) rPot = 0.0;
-        if (overflow) atomicOr(&envi[el * 4 + 3], (int)EV2B_ST_AMPS_OVERFLOW);
+        if (overflow) atomicOr(&envi[el * 8 + 3], (int)EV2B_ST_AMPS_OVERFLOW);
         if (EV2B_OPT(p.out.cs_power))   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
         if (EV2B_OPT(p.out.cs_current)) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
     }
@@ -794,7 +801,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
             const int jel = job / 3, kind = job - jel * 3;
             const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
             if (je >= p.env_end) continue;
-            const int jt = envi[jel * 4 + 0];
+            const int jt = envi[jel * 8 + 0];
             if (jt >= p.T) continue;
             if (kind == 0) {          // Transformer.step accumulation + overload   transformer.py:264-302
                 int nseg = 1;
@@ -845,7 +852,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if (q < 3 && seg == 0) atomicOr(&envi[jel * 4 + 2], v << (10 * q));
+                if (q < 3 && seg == 0) envi[jel * 8 + 4 + q] = v;     // (whole ints: the env totals exceed 10 bits for P > 1023)
             }
         }
     }
@@ -857,9 +864,9 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
         for (int jel = warp; jel < p.EPB; jel += nwarps) {
             const int je = (p.env0 + blockIdx.x * p.EPB) + jel;
             if (je >= p.env_end) continue;
-            const int jt = envi[jel * 4 + 0];
+            const int jt = envi[jel * 8 + 0];
             if (jt >= p.T) continue;
-            const double lv = power_flow_env(p, pfv + (size_t)jel * 3 * n, trp + jel * p.Tr, envi[jel * 4 + 1], jt, je, lane);
+            const double lv = power_flow_env(p, pfv + (size_t)jel * 3 * n, trp + jel * p.Tr, envi[jel * 8 + 1], jt, je, lane);
             if (lane == 0) { lossv[jel] = lv; if (p.out.node_voltage) p.out.node_voltage[(size_t)je * (n + 1)] = 1.0; }
         }
         __syncthreads();
@@ -869,12 +876,12 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
     if (tid < p.EPB) {
         const int je = (p.env0 + blockIdx.x * p.EPB) + tid;
         if (je < p.env_end) {
-            const int jt = envi[tid * 4 + 0], js = envi[tid * 4 + 1];
-            unsigned status = (unsigned)envi[tid * 4 + 3];
+            const int jt = envi[tid * 8 + 0], js = envi[tid * 8 + 1];
+            unsigned status = (unsigned)envi[tid * 8 + 3];
             double reward = 0.0, costs = 0.0;
             if (jt < p.T) {
                 const double *v = envs + tid * kNRed;
-                const int w = envi[tid * 4 + 2];
+                const int n_inv = envi[tid * 8 + 4], n_dep = envi[tid * 8 + 5], n_arr = envi[tid * 8 + 6];
                 const double *pe = pre + tid * p.pre_stride;
                 EnvT et; et.setpoint = pe[kPreSet];
                 const double usage = v[RedP];                                  // current_power_usage[t]  ev2gym_env.py:375
@@ -922,14 +929,14 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                 kpi[EV2B_KPI_ENERGY_CHARGED] = pe[EV2B_KPI_ENERGY_CHARGED] + v[RedCharged];
                 kpi[EV2B_KPI_ENERGY_DISCHARGED] = pe[EV2B_KPI_ENERGY_DISCHARGED] + v[RedDischarged];
                 kpi[EV2B_KPI_TR_OVERLOAD] = pe[EV2B_KPI_TR_OVERLOAD] + ovsum;
-                kpi[EV2B_KPI_EVS_SERVED] = pe[EV2B_KPI_EVS_SERVED] + (double)((w >> 10) & 1023);
+                kpi[EV2B_KPI_EVS_SERVED] = pe[EV2B_KPI_EVS_SERVED] + (double)n_dep;
                 kpi[EV2B_KPI_SAT_SUM] = pe[EV2B_KPI_SAT_SUM] + v[RedSatSum];
                 const double d = et.setpoint - usage;                          // utils.py:37-44
                 kpi[EV2B_KPI_TRACKING_ERROR] = pe[EV2B_KPI_TRACKING_ERROR] + d * d;
                 kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] = pe[EV2B_KPI_ENERGY_TRACKING_ERROR] + fabs(d);
                 if (usage > et.setpoint) kpi[EV2B_KPI_TRACKER_VIOLATION] = pe[EV2B_KPI_TRACKER_VIOLATION] + (usage - et.setpoint);
-                kpi[EV2B_KPI_EVS_SPAWNED] = pe[EV2B_KPI_EVS_SPAWNED] + (double)((w >> 20) & 1023);
-                kpi[EV2B_KPI_INVALID_ACTIONS] = pe[EV2B_KPI_INVALID_ACTIONS] + (double)(w & 1023);
+                kpi[EV2B_KPI_EVS_SPAWNED] = pe[EV2B_KPI_EVS_SPAWNED] + (double)n_arr;
+                kpi[EV2B_KPI_INVALID_ACTIONS] = pe[EV2B_KPI_INVALID_ACTIONS] + (double)n_inv;
                 kpi[EV2B_KPI_STEPS] = pe[EV2B_KPI_STEPS] + 1.0;
                 p.env_pot[je] = (jt + 1 < p.T) ? v[RedPot] : 0.0;              // ev2gym_env.py:424-426
                 p.env_usage[je] = usage;
@@ -957,7 +964,7 @@ __global__ void reset_ports_kernel(const Params p, int lo, int hi, const int *sc
     int s;
     if (mode == 1) {
         if (p.env_step[e] < p.T) return;
-        s = (p.env_scn[e] + p.E) % p.S;
+        s = (p.env_scn[e] + p.scn_stride) % p.S;
     } else {
         s = scn_ids ? scn_ids[e - lo] : e % p.S;
     }
@@ -968,7 +975,7 @@ __global__ void reset_ports_kernel(const Params p, int lo, int hi, const int *sc
     h.z = 0; h.w = 0;
     p.hot[(size_t)e * p.P + port] = h;
     p.cap[(size_t)e * p.P + port] = 0.0;
-    p.exch[(size_t)e * p.P + port] = 0.f;
+    p.exch[(size_t)e * p.P + port] = 0.0;
     if (p.rr_key) {                       // a new episode starts with a fresh agent: empty queue
         p.rr_key[(size_t)e * p.P + port] = kRrAbsent;
         if (port == 0) { p.rr_fb[2 * e] = 0; p.rr_fb[2 * e + 1] = 1; }
@@ -988,7 +995,7 @@ __global__ void reset_envs_kernel(const Params p, int lo, int hi, const int *scn
         int go = 1, s;
         if (mode == 1) {
             go = p.env_step[e] >= p.T;
-            s = (p.env_scn[e] + p.E) % p.S;
+            s = (p.env_scn[e] + p.scn_stride) % p.S;
         } else {
             s = scn_ids ? scn_ids[e - lo] : e % p.S;
         }

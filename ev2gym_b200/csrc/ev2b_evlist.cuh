@@ -1,30 +1,35 @@
 // ev2b_evlist.cuh -- the event-driven step kernel: visits CONNECTED EVs instead of ports.
 //
 // step_kernel (ev2b_device.cuh) runs one thread per (env, charger) and touches every port every step although, over an
-// episode of the stock scenarios, 80 % of the ports are empty (30-40 % at the busy part, all of them at night); it is
-// instruction-issue bound, not HBM bound.
+// episode of the stock scenarios, 80 % of the ports are empty (30-40 % at the busy part, all of them at night).
 // This kernel keeps, per env, the list of ports that currently hold an EV (`occ_list`, rewritten in place every step) and
-// a per-scenario arrival schedule (`arr_list` bucketed by step), and does the reference's work in that order:
+// a per-scenario arrival schedule (`arr_list` bucketed by step; the bucket of step t+1 is named by the (scenario, t)
+// record EnvT itself), and does the reference's work in that order:
 //
-//   --  an env with nobody connected and nobody arriving takes evl_idle_step: base load, reward, KPI sums, observation
-//   P0  prefetch of the per-env records (cp.async), (scenario, time)-only observation values
+//   P0  per-env scalars, cp.async prefetch of the per-env records (KPI sums, potential, transformer rows), fills of the
+//       per-step outputs, (scenario, time)-only observation values
 //   EV  one thread per CONNECTED EV (dense lanes): loads, Sigma-normalisation with the charger's other ports,
 //       EV.step (the float64 battery model, ev_step_item), charger accounting, departure, observation tuple,
 //       potential; per-port results go to shared memory                        ev_charger.py:114-233, ev.py:138-405
 //   AR  one thread per ARRIVAL of step t+1 (from the schedule)                  ev2gym_env.py:399-417
 //   CS  one thread per charger: power / amps / potential in port order, clamp   transformer.py:264-274, utils.py:779-789
 //       (not with one port per charger: there the EV's own thread does it)
-//   TR  warp 0: transformer sums (CSR) + overload; reward, KPI sums, step counter (same code path as step_kernel C)
-//   LS  last warp: stable compaction of the kept EVs + arrivals back into the list (staged in shared memory meanwhile)
+//   LS  last warp: stable compaction of the kept EVs + arrivals back into the list
+//   TR  warp 0: transformer sums (CSR) + overload; distribution-grid power flow; then reward, the 13 KPI sums, step
+//       counter, done flag and observation header, ONE LANE PER QUANTITY (lane k owns KPI k: a load, an add, a store --
+//       not thirteen dependent read-modify-writes by one thread)
+//
+// An env with nobody connected and nobody arriving (half of the steps of the stock workplace scenarios: the site is
+// empty at night) runs the same code with the EV / AR / CS / LS phases and their barriers skipped, on warp 0 of the
+// group alone: base load, reward, KPI sums, observation.
 //
 // An env is owned by a GROUP of G warps (G = 1, 2, 4; a 128-thread CTA holds 4 / G envs), so every barrier is a
-// warp barrier (G = 1), a named barrier (G = 2) or __syncthreads (G = 4), and no phase leaves more than one warp of
-// a group running alone for long.  The state arrays (hot / cap / exch) are exactly step_kernel's: the two kernels are
-// interchangeable launch by launch (evl_rebuild_kernel re-derives the list from the hot words after step_kernel ran).
-// Handles: every stock reward and state function that needs no distribution grid, without statistics mode and without
-// the per-port optional outputs dep_sat, dep_cap, port_energy (action_mask is covered); everything else takes step_kernel.
-// Sums are formed in a different (still fixed) order than step_kernel's, so float64 outputs agree to ~1e-15
-// relative, not bitwise; battery levels, indices, counts and flags are identical.
+// warp barrier (G = 1), a named barrier (G = 2) or a CTA barrier (G = 4).  The state arrays (hot / cap / exch) are
+// exactly step_kernel's: the two kernels are interchangeable launch by launch (evl_rebuild_kernel re-derives the list from
+// the hot words after step_kernel ran).  The kernel covers EVERY feature of the C ABI: all stock rewards and state
+// functions, statistics mode, the distribution grid and the per-port optional outputs live in the HEAVY instantiation
+// (so the lean one does not pay for them).  Sums are formed in a different (still fixed) order than step_kernel's, so
+// float64 outputs agree to ~1e-15 relative, not bitwise; battery levels, indices, counts and flags are identical.
 #pragma once
 #include "ev2b_device.cuh"
 
@@ -32,6 +37,10 @@ namespace ev2b {
 
 constexpr int kEvlThreads = 128;
 constexpr unsigned kEvlGone = 0xFFFFu;       // staging mark: this EV left during the step
+// prefetch area of this kernel (doubles): [0,13) KPI sums, [13] charge_power_potential[t] (kPrePot), then
+constexpr int kEvlPotPrev = 14;              // charge_power_potential[t-1]
+constexpr int kEvlSet = 15, kEvlSetNext = 16;   // power_setpoints[t], [t+1]
+constexpr int kEvlTr = 18;                   // [18 + 4k, +4) TrT of transformer k (16 B aligned)
 enum { EvlProfit = 0, EvlSatExp, EvlCharged, EvlDischarged, EvlSatSum, EvlUsage, EvlPot, EvlCounts, EvlNSum };
 static_assert(EvlNSum == 8, "warp_sum8 reduces exactly 8 quantities");
 
@@ -58,178 +67,55 @@ __device__ __forceinline__ double warp_sum8(const double (&q)[8], int lane) {
     return c;
 }
 
-__device__ __forceinline__ void evl_prefetch_l2(const void *ptr) {
-#ifndef EV2B_SIMT_EMU
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-#else
-    (void)ptr;
-#endif
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
-#ifdef EV2B_SIMT_EMU
-    simt::cp_async(smem_dst, gmem_src, 4);
-#else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-#endif
-}
-
-// Named barrier 1 + g of the CTA for the 64 threads of group g.  The id is a literal: with the id in a register ptxas
-// reserves all 16 barriers for the CTA, which capped the SM at 3 resident CTAs (ncu: 21 % warps active).
-__device__ __forceinline__ void evl_bar_sync64(int g) {
-#ifdef EV2B_SIMT_EMU
-    simt::bar_sync(1 + g, 64);
-#else
-    if (g == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-    else        asm volatile("bar.sync 2, 64;" ::: "memory");
-#endif
-}
+// Barriers of a group.  Named barrier ids are literals: with the id in a register ptxas reserves all 16 barriers for
+// the CTA, which capped the SM at 3 resident CTAs (ncu: 21 % warps active).  G = 2: barrier 1 + g, 64 threads; G = 4:
+// barrier 1, the whole CTA.  `arrive` does not wait: the idle path uses it so that warps with nothing to do leave at
+// once while warp 0 still learns that they have read the env's step counter before it advances it.
 template <int G>
 __device__ __forceinline__ void evl_group_sync(int g) {
     static_assert(G == 1 || G == 2 || G * 32 == kEvlThreads, "group sizes: one warp, two warps, or the whole CTA");
-    if (G == 1) __syncwarp();
-    else if (G * 32 == kEvlThreads) __syncthreads();
-    else evl_bar_sync64(g);
+    if (G == 1) { __syncwarp(); return; }
+#ifdef EV2B_SIMT_EMU
+    simt::bar_sync(1 + g, 32 * G);
+#else
+    if (G == 2) { if (g == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory"); }
+    else asm volatile("bar.sync 1, 128;" ::: "memory");
+#endif
+}
+template <int G>
+__device__ __forceinline__ void evl_group_arrive(int g) {
+    if (G == 1) return;
+#ifdef EV2B_SIMT_EMU
+    simt::bar_arrive(1 + g, 32 * G);
+#else
+    if (G == 2) { if (g == 0) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory"); }
+    else asm volatile("bar.arrive 1, 128;" ::: "memory");
+#endif
 }
 
 // What the env's reward function adds per EV that leaves this step (cv = its final battery level, des = the level it
 // asked for, sat = its user satisfaction); summed into EvlSatExp and subtracted by the reward.
+template <bool HEAVY>
 __device__ __forceinline__ double evl_departure_penalty(const Params &p, double cv, double des, double sat) {
     const int k = p.reward_kind;
     if (k == EV2B_REWARD_PROFIT_TR_USER || k == EV2B_REWARD_PROFIT_MAX) return 100.0 * exp(-10.0 * sat);   // reward.py:42,85
     if (k == EV2B_REWARD_SQTR_TR_USER) return 1000.0 * (1.0 - sat);                                         // reward.py:29-30
     if (k == EV2B_REWARD_V2G_PROFITMAX) return des > cv ? 100.0 * (des - cv) : 0.0;                         // reward.py:136-138
-    if (k == EV2B_REWARD_V2G_PROFITMAX_V2 || k == EV2B_REWARD_PST_PROFITMAX_V2)
+    if (k == EV2B_REWARD_V2G_PROFITMAX_V2 || k == EV2B_REWARD_PST_PROFITMAX_V2 || (HEAVY && k == EV2B_REWARD_GRID_PROFITMAX_V2))
         return des > cv ? 0.05 * ((des - cv) * (des - cv)) : 0.0;                                           // reward.py:199-207
+    if (HEAVY && (k == EV2B_REWARD_GRID_FULL || k == EV2B_REWARD_GRID_SIMPLE)) return (cv - des) * (cv - des);   // -user_costs  reward.py:99-102
     return 0.0;
 }
 // V2G_profitmaxV2 family: an EV that stays connected but can no longer reach its desired level   reward.py:172-190
+template <bool HEAVY>
 __device__ __forceinline__ double evl_unreachable_penalty(const Params &p, const EvSpec *sp, double cv, int steps_left) {
-    if (p.reward_kind != EV2B_REWARD_V2G_PROFITMAX_V2 && p.reward_kind != EV2B_REWARD_PST_PROFITMAX_V2) return 0.0;
+    if (p.reward_kind != EV2B_REWARD_V2G_PROFITMAX_V2 && p.reward_kind != EV2B_REWARD_PST_PROFITMAX_V2 &&
+        !(HEAVY && p.reward_kind == EV2B_REWARD_GRID_PROFITMAX_V2)) return 0.0;
     const double des = __ldg(&sp->desired), pmax = __ldg(&sp->pmax_ac);
     const double min_steps = (des - cv) / (pmax / p.c60);
     if (!(min_steps > (double)steps_left)) return 0.0;
     const double gap = (des - ((double)(steps_left + 1) * pmax / p.c60)) - cv;
     return 0.05 * (gap * gap);
-}
-
-// Reward, KPI sums, step counter, done flag and observation header of env e (one thread; the same statements as
-// step_kernel's phase C).  old = the env's KPI sums before the step (shared-memory prefetch, or env_kpi itself),
-// q = the step's totals (Evl*), ovsum = sum of the transformers' overloads, pot_now = charge_power_potential[t].
-struct EvlTotals {            // the step's totals of one env, indexed by Evl*
-    double v[EvlNSum];
-    __device__ __forceinline__ double operator[](int k) const { return v[k]; }
-};
-__device__ EV2B_NOINLINE void evl_finish_env(const Params &p, int e, int s, int tq, const double *old, double pot_now,
-                                             double setpoint, double setpoint_next, double tr0_max_power,
-                                             const EvlTotals q, double ovsum, int n_arr, int n_connected, bool want_obs) {
-    const int cnts = (int)q[EvlCounts];
-    unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
-    const int n_dep = cnts & 0xFFFFF;
-    const double usage = q[EvlUsage];                                     // current_power_usage[t]  ev2gym_env.py:375
-    const double costs = q[EvlProfit];
-    double reward = 0.0;
-    if (p.reward_kind == EV2B_REWARD_SQ_TRACKING) {                       // reward.py:11-12
-        const double m = setpoint < pot_now ? setpoint : pot_now;
-        reward = -((m - usage) * (m - usage));
-    } else if (p.reward_kind == EV2B_REWARD_PROFIT_TR_USER) {             // reward.py:36-44
-        reward = costs - 100.0 * ovsum - q[EvlSatExp];
-    } else if (p.reward_kind == EV2B_REWARD_PROFIT_MAX) {                 // reward.py:81-87
-        reward = costs - q[EvlSatExp];
-    } else if (p.reward_kind == EV2B_REWARD_SQTR_TR_USER) {               // reward.py:16-32
-        double m = setpoint < pot_now ? setpoint : pot_now;
-        if (tr0_max_power < m) m = tr0_max_power;                         // transformers[0].max_power[t]
-        reward = -((m - usage) * (m - usage)) - 100.0 * ovsum - q[EvlSatExp];
-    } else if (p.reward_kind == EV2B_REWARD_SQ_TRACKING_PENALTY) {        // reward.py:46-58
-        const double m = setpoint < pot_now ? setpoint : pot_now;
-        reward = -((m - usage) * (m - usage));
-        if (usage == 0.0 && p.env_pot_prev[e] != 0.0) reward = reward - 100.0;   // potential[current_step-2]; 0 at t = 0
-        p.env_pot_prev[e] = pot_now;
-    } else if (p.reward_kind == EV2B_REWARD_SIMPLE) {                     // reward.py:60-65
-        reward = -((setpoint - usage) * (setpoint - usage));
-    } else if (p.reward_kind == EV2B_REWARD_MIN_TRACKER_SURPLUS) {        // reward.py:67-76
-        if (setpoint < usage) reward -= (usage - setpoint) * (usage - setpoint);
-        reward += usage;
-    } else if (p.reward_kind == EV2B_REWARD_V2G_COSTS_SIMPLE) {           // reward.py:150-153
-        reward = costs;
-    } else if (p.reward_kind == EV2B_REWARD_V2G_PROFITMAX || p.reward_kind == EV2B_REWARD_V2G_PROFITMAX_V2 ||
-               p.reward_kind == EV2B_REWARD_PST_PROFITMAX_V2) {           // reward.py:123-148, 155-213, 281-339
-        reward = costs - q[EvlSatExp];
-        if (p.reward_kind == EV2B_REWARD_PST_PROFITMAX_V2 && setpoint < usage) reward += 1000.0 * (setpoint - usage);
-    }
-    double *kpi = p.env_kpi + (size_t)e * EV2B_KPI_COUNT;
-    kpi[EV2B_KPI_TOTAL_REWARD] = old[EV2B_KPI_TOTAL_REWARD] + reward;
-    kpi[EV2B_KPI_TOTAL_PROFITS] = old[EV2B_KPI_TOTAL_PROFITS] + costs;
-    kpi[EV2B_KPI_ENERGY_CHARGED] = old[EV2B_KPI_ENERGY_CHARGED] + q[EvlCharged];
-    kpi[EV2B_KPI_ENERGY_DISCHARGED] = old[EV2B_KPI_ENERGY_DISCHARGED] + q[EvlDischarged];
-    kpi[EV2B_KPI_TR_OVERLOAD] = old[EV2B_KPI_TR_OVERLOAD] + ovsum;
-    kpi[EV2B_KPI_EVS_SERVED] = old[EV2B_KPI_EVS_SERVED] + (double)n_dep;
-    kpi[EV2B_KPI_SAT_SUM] = old[EV2B_KPI_SAT_SUM] + q[EvlSatSum];
-    const double d = setpoint - usage;                                    // utils.py:37-44
-    kpi[EV2B_KPI_TRACKING_ERROR] = old[EV2B_KPI_TRACKING_ERROR] + d * d;
-    kpi[EV2B_KPI_ENERGY_TRACKING_ERROR] = old[EV2B_KPI_ENERGY_TRACKING_ERROR] + fabs(d);
-    if (usage > setpoint) kpi[EV2B_KPI_TRACKER_VIOLATION] = old[EV2B_KPI_TRACKER_VIOLATION] + (usage - setpoint);
-    kpi[EV2B_KPI_EVS_SPAWNED] = old[EV2B_KPI_EVS_SPAWNED] + (double)n_arr;
-    kpi[EV2B_KPI_INVALID_ACTIONS] = old[EV2B_KPI_INVALID_ACTIONS] + (double)(p.P - n_connected);   // every empty port  ev_charger.py:137-140
-    kpi[EV2B_KPI_STEPS] = old[EV2B_KPI_STEPS] + 1.0;
-    p.env_pot[e] = (tq < p.T) ? q[EvlPot] : 0.0;                          // ev2gym_env.py:424-426
-    p.env_usage[e] = usage;
-    p.env_step[e] = tq;
-    if (tq >= p.T) status |= EV2B_ST_DONE;                                // ev2gym_env.py:460
-    if (want_obs) obs_header(p, p.out.obs + (size_t)e * p.D, s, tq, usage, setpoint_next);
-    if (p.out.reward) p.out.reward[e] = reward;
-    if (p.out.total_costs) p.out.total_costs[e] = costs;
-    if (p.out.status) p.out.status[e] = status;
-}
-
-// A step of an env with no EV connected and none arriving (half of the steps of the stock workplace scenarios: the site
-// is empty at night).  Every per-EV and per-charger quantity is zero; what remains is the transformers' base load, the
-// reward, the KPI sums and the observation.  No shared memory; the group's threads share the copies, its first thread
-// does the per-env part straight from global memory -- after a barrier, because it advances env_step, which every thread
-// of the group has just read (the SIMT emulator caught exactly that: a lane that ran ahead saw the next step).
-template <int G>
-__device__ __forceinline__ void evl_idle_step(const Params &p, int e, int t, int s, int g, int gtid, bool want_obs) {
-    constexpr int GT = 32 * G;
-    const int tq = t + 1;
-    evl_group_sync<G>(g);
-    if (want_obs) {
-        float *obs_row = p.out.obs + (size_t)e * p.D;
-        for (int i = gtid; i < p.W; i += GT) obs_row[p.series_off[i]] = obs_series_fetch(p, s, tq, i);
-        if (p.obs_full) {
-            const bool three = p.state_kind == EV2B_STATE_PUBLIC_PST;
-#pragma unroll 1
-            for (int i = gtid; i < p.P; i += GT) {
-                float *o = obs_row + p.obs_slot[i];
-                o[0] = 0.f; o[1] = 0.f;
-                if (three) o[2] = 0.f;
-            }
-        }
-    }
-    if (p.out.action_mask && (p.mask_full || t == 0)) {
-#pragma unroll 1
-        for (int i = gtid; i < p.P; i += GT) p.out.action_mask[(size_t)e * p.P + i] = 0;
-    }
-    if (p.out.cs_power || p.out.cs_current) {
-#pragma unroll 1
-        for (int c = gtid; c < p.C; c += GT) {
-            if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = 0.f;
-            if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = 0.f;
-        }
-    }
-    if (gtid != 0) return;
-    double ovsum = 0.0;
-    for (int k = 0; k < p.Tr; ++k) {                                      // transformer.py:264-302 with no charger load
-        const TrT tt = p.tr_t[((size_t)s * p.T + t) * p.Tr + k];
-        const double ptot = (tt.infl + tt.solar) + 0.0;
-        double ov = 0.0;
-        if (ptot > tt.maxp + 0.0001 || ptot < tt.minp - 0.0001) ov = fabs(ptot - tt.maxp);
-        if (p.out.tr_power)    p.out.tr_power[(size_t)e * p.Tr + k] = ptot;
-        if (p.out.tr_overload) p.out.tr_overload[(size_t)e * p.Tr + k] = ov;
-        ovsum += ov;
-    }
-    const EvlTotals q = {{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}};
-    const EnvT *et = p.env_t + (size_t)s * p.T + t;
-    evl_finish_env(p, e, s, tq, p.env_kpi + (size_t)e * EV2B_KPI_COUNT, p.env_pot[e], et->setpoint,
-                   tq < p.T ? et[1].setpoint : 0.0, p.tr_t[((size_t)s * p.T + t) * p.Tr].maxp, q, ovsum, 0, 0, want_obs);
 }
 
 // Rebuilds occ_list / occ_n of envs [lo, hi) from the hot words (one warp per env): ports in ascending order.
@@ -254,10 +140,35 @@ __global__ void evl_rebuild_kernel(const Params p, int lo, int hi) {
     if (lane == 0) p.occ_n[e] = base;
 }
 
-// STG: every EV record of the env (hot words, battery level, exchanged energy, action) is copied to shared memory with
-// cp.async before the EV loop instead of being loaded inside it (all of an env's DRAM requests in flight at once).
-template <typename ActT, int NP, bool UNI, int G, bool STG>
-__global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_constant__ Params p) {
+// Observation tuple of the EV on `port` after the step (cv = battery level, h = its hot words)   state.py:37-57, 85-102, 137-151, 262-270
+template <bool HEAVY>
+__device__ __forceinline__ void evl_obs_tuple(const Params &p, float *obs_row, int port, int c, const uint4 &h, double cv,
+                                              double B, const EvSpec *sp, double exch, int tq) {
+    float *o = obs_row + p.obs_slot[port];
+    if (HEAVY && p.state_kind == EV2B_STATE_V2G_GRID) {
+        o[0] = (float)cv;
+        o[1] = (float)(hot_t_dep(h) - tq + 1);
+        o[2] = (float)__ldg(&p.cs_tr[c]);                     // cs.connected_bus
+    } else if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
+        o[0] = (cv == B) ? 1.f : 0.5f;
+        o[1] = (float)exch;
+        o[2] = (float)(tq - hot_t_arr(h));
+    } else {
+        o[0] = (float)ev2b_div_c(cv, B, __ldg(&sp->rB));
+        o[1] = (float)(hot_t_dep(h) - tq);
+    }
+}
+__device__ __forceinline__ void evl_obs_clear(const Params &p, float *obs_row, int port) {
+    float *o = obs_row + p.obs_slot[port];
+    o[0] = 0.f; o[1] = 0.f;
+    if (p.state_kind == EV2B_STATE_PUBLIC_PST || p.state_kind == EV2B_STATE_V2G_GRID) o[2] = 0.f;
+}
+
+#ifndef EV2B_EVL_MINB
+#define EV2B_EVL_MINB 8       // resident CTAs per SM the lean instantiation is compiled for (8 -> 64 registers per thread)
+#endif
+template <typename ActT, int NP, bool UNI, int G, bool HEAVY>
+__global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_step_kernel(const __grid_constant__ Params p) {
     EV2B_DYNAMIC_SMEM(smem_raw);
     constexpr int GT = 32 * G, EPB = kEvlThreads / GT;
     const int tid = threadIdx.x;
@@ -272,132 +183,115 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
     double *csP   = reinterpret_cast<double *>(sm + p.v_csP);        // [C] charger power, for the transformer sums
     double *pre   = reinterpret_cast<double *>(sm + p.v_pre);        // [pre_stride] prefetched per-env records (kPre*)
     double *wsum  = reinterpret_cast<double *>(sm + p.v_wsum);       // [G][EvlNSum] per-warp partial sums (the last one holds counts)
-    double *trov  = reinterpret_cast<double *>(sm + p.v_trov);       // [Tr] overload per transformer
     uint16_t *stage = reinterpret_cast<uint16_t *>(sm + p.v_stage);  // [P] by list position: port, or kEvlGone
-    unsigned char *occ = sm + p.v_occ;                               // [P] the port holds per-port results this step
-    uint4  *s_hot  = reinterpret_cast<uint4 *>(sm + p.v_shot);       // STG only, by list position: [P] hot words,
-    double *s_cap  = reinterpret_cast<double *>(sm + p.v_scap);      //   [P] battery level,
-    float  *s_exch = reinterpret_cast<float *>(sm + p.v_sexch);      //   [P] exchanged energy,
-    ActT   *s_act  = reinterpret_cast<ActT *>(sm + p.v_sact);        //   [P] action (caller-supplied actions only)
+    unsigned char *occ = sm + p.v_occ;                               // [P] bit 0: the port holds per-port results this step;
+                                                                     //     bit 1 / 2 (statistics): an EV left it / was finalised on it
+    double *trp   = reinterpret_cast<double *>(sm + p.v_trp);        // HEAVY: [Tr] transformer power (grid: bus EV power)
+    double2 *pfv  = reinterpret_cast<double2 *>(sm + p.v_pfv);       // HEAVY: [3][n_bus] power-flow scratch S, V, lambda
+    double *dsat  = reinterpret_cast<double *>(sm + p.v_dsat);       // HEAVY statistics, several ports per charger: [P] satisfaction,
+    double *dcal  = reinterpret_cast<double *>(sm + p.v_dcal);       //   calendar and
+    double *dcyc  = reinterpret_cast<double *>(sm + p.v_dcyc);       //   cyclic degradation of the EVs finalised this step
 
     const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
-    // The EV loop starts with a chain of dependent global loads (occ_n -> list -> hot words -> spec): the list is a
-    // single buffer rewritten in place (phase LS), so its address needs nothing but e and this thread's first entry is
-    // read together with the per-env scalars (entries at or beyond occ_n are stale and never used).
+    // The EV loop starts with a chain of dependent global loads (list -> hot words -> spec): the list is a single buffer
+    // rewritten in place (phase LS), so its address needs nothing but e and this thread's first entry is read together
+    // with the per-env scalars (entries at or beyond occ_n are stale and never used).
     const uint16_t *lst = p.occ_list + (size_t)e * p.P;
     const unsigned first = gtid < p.P ? (unsigned)lst[gtid] : 0u;
     const int t = p.env_step[e];
+    const int s = p.env_scn[e];
+    const int n_old = p.occ_n[e];
+    if (gw == 0) {                                     // KPI sums, potential[t], potential[t-1]: need nothing but e
+        if (lane <= kPrePot) cp_async8(pre + lane, lane < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + lane : p.env_pot + e);
+        else if (lane == kEvlPotPrev) cp_async8(pre + lane, p.env_pot_prev + e);
+    }
     if (t >= p.T) {                                   // step() on a finished env   ev2gym_env.py:343
         if (gtid == 0) {
             if (p.out.reward) p.out.reward[e] = 0.0;
             if (p.out.total_costs) p.out.total_costs[e] = 0.0;
             if (p.out.status) p.out.status[e] = EV2B_ST_DONE | EV2B_ST_WAS_DONE;
         }
+        cp_async_wait_all();
         return;
     }
-    const int s = p.env_scn[e];
-    const int n_old = p.occ_n[e];
     const int tq = t + 1;
-    const int a0 = p.arr_off[(size_t)s * (p.T + 2) + tq], a1 = p.arr_off[(size_t)s * (p.T + 2) + tq + 1];
-    const int nArr = a1 - a0;
-    if (n_old == 0 && nArr == 0) {                    // nobody connected, nobody arriving: the short path
-        evl_idle_step<G>(p, e, t, s, g, gtid, want_obs);
-        return;
+    const EnvT *etp = p.env_t + (size_t)s * p.T + t;
+    const double2 price = *reinterpret_cast<const double2 *>(etp);           // cp, dp
+    const int a0 = etp->arr0, nArr = etp->n_arr;                             // the sessions arriving at step t+1
+    const bool idle = n_old == 0 && nArr == 0;        // nobody connected, nobody arriving: warp 0 alone, no barriers
+    if (idle && gw != 0) { evl_group_arrive<G>(g); return; }
+    if (gw == 0) {                                    // setpoints and the transformers' rows of this step (two 16 B halves each)
+        if (lane == kEvlSet) cp_async8(pre + lane, &etp->setpoint);
+        else if (lane == kEvlSetNext) { if (tq < p.T) cp_async8(pre + lane, &etp[1].setpoint); else pre[lane] = 0.0; }
+#pragma unroll 1
+        for (int i = lane; i < 2 * p.Tr; i += 32)
+            cp_async16(pre + kEvlTr + 2 * i, reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * i);
     }
+    const int NT = idle ? 32 : GT;                    // threads that share the fills below
     float *obs_row = p.out.obs + (size_t)e * p.D;
+    uint8_t *mask_row = p.out.action_mask ? p.out.action_mask + (size_t)e * p.P : nullptr;
 
-    // ---- P0: prefetch, zero the per-port flags, (scenario, time)-only observation values ----------------------
-    const bool ext_actions = p.agent_kind == EV2B_AGENT_EXTERNAL;
+    // ---- P0: zero the per-port flags, fill the per-step outputs, (scenario, time)-only observation values ---------
+    if (!idle) {
+        if (NP == 1) {                                // one port per charger: the EV's thread is the charger's thread (no CS phase)
 #pragma unroll 1
-    for (int i = gtid; i < n_old; i += GT) {               // the list is staged in shared memory: phase LS rewrites it in place
-        const int port = i == gtid ? (int)first : (int)lst[i];
-        stage[i] = (uint16_t)port;
-        const size_t ip = (size_t)e * p.P + port;
-        if (STG) {                                         // this thread consumes exactly the records it requests here
-            cp_async16(s_hot + i, p.hot + ip);
-            cp_async8(s_cap + i, p.cap + ip);
-            cp_async4(s_exch + i, p.exch + ip);
-            if (ext_actions) {
-                if (sizeof(ActT) == 8) cp_async8(s_act + i, actions + ip); else cp_async4(s_act + i, actions + ip);
+            for (int i = gtid; i < p.C; i += GT) csP[i] = 0.0;
+        } else {
+#pragma unroll 1
+            for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
+        }
+    }
+    if (NP == 1 || idle) {                            // (with a CS phase the charger's thread writes these)
+        if (p.out.cs_power || p.out.cs_current) {
+#pragma unroll 1
+            for (int c = gtid; c < p.C; c += NT) {
+                if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = 0.f;
+                if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = 0.f;
             }
-        } else if ((p.evl_pf & 1) && i != gtid) {          // later EVs of this thread: pull their lines into L2 now
-            evl_prefetch_l2(p.hot + ip); evl_prefetch_l2(p.cap + ip); evl_prefetch_l2(p.exch + ip);
-            if (ext_actions) evl_prefetch_l2(actions + ip);
         }
-    }
-    if (p.evl_pf & 2) {                                    // the env a later CTA of this launch will own: its rows into L2
-        const int e2 = e + p.evl_pf_dist;
-        if (e2 < p.env_end) {
-            const size_t r0 = (size_t)e2 * p.P;
-#pragma unroll 1
-            for (int o = gtid * 128; o < p.P * 16; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.hot + r0) + o);
-#pragma unroll 1
-            for (int o = gtid * 128; o < p.P * 8; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.cap + r0) + o);
-#pragma unroll 1
-            for (int o = gtid * 128; o < p.P * 4; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.exch + r0) + o);
-            if (ext_actions)
-    #pragma unroll 1
-            for (int o = gtid * 128; o < p.P * (int)sizeof(ActT); o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(actions + r0) + o);
-#pragma unroll 1
-            for (int o = gtid * 128; o < p.P * 2; o += GT * 128) evl_prefetch_l2(reinterpret_cast<const char *>(p.occ_list + r0) + o);
-        }
-    }
-#pragma unroll 1
-    for (int i = gtid; i <= kPrePot; i += GT)
-        cp_async8(pre + i, i < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + i : p.env_pot + e);
-#pragma unroll 1
-    for (int i = gtid; i < 2 + 2 * p.Tr; i += GT) {
-        if (i < 2) { if (t + i < p.T) cp_async8(pre + kPreSet + i, &p.env_t[(size_t)s * p.T + t + i].setpoint); }
-        else cp_async16(pre + kPreTr + 2 * (i - 2), reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * (i - 2));
-    }
-    const EnvT et0 = p.env_t[(size_t)s * p.T + t];
-    if (NP == 1) {                                    // one port per charger: the EV's thread is the charger's thread (no CS phase)
-#pragma unroll 1
-        for (int i = gtid; i < p.C; i += GT) {
-            csP[i] = 0.0;
-            if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + i] = 0.f;
-            if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + i] = 0.f;
-        }
-    } else {
-#pragma unroll 1
-        for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
     }
     if (want_obs) {
-        for (int i = gtid; i < p.W; i += GT) obs_row[p.series_off[i]] = obs_series_fetch(p, s, tq, i);
-        if (p.obs_full) {                             // the caller's buffer does not hold last step's rows: clear every tuple
-            const bool three = p.state_kind == EV2B_STATE_PUBLIC_PST;
 #pragma unroll 1
-            for (int i = gtid; i < p.P; i += GT) {
-                float *o = obs_row + p.obs_slot[i];
-                o[0] = 0.f; o[1] = 0.f;
-                if (three) o[2] = 0.f;
-            }
+        for (int i = gtid; i < p.W; i += NT) obs_row[p.series_off[i]] = obs_series_fetch(p, s, tq, i);
+        if (p.obs_full) {                             // the caller's buffer does not hold last step's rows: clear every tuple
+#pragma unroll 1
+            for (int i = gtid; i < p.P; i += NT) evl_obs_clear(p, obs_row, i);
         }
     }
     // action_mask is maintained incrementally like the observation tuples: the caller's buffer still holds last step's
     // row, only ports whose EV arrives or leaves change.  A new buffer (mask_full) or a new episode (t == 0: the row may
     // hold the previous episode's terminal mask) rewrites the row.                                  ev2gym_env.py:452-457
-    uint8_t *mask_row = p.out.action_mask ? p.out.action_mask + (size_t)e * p.P : nullptr;
     if (mask_row && (p.mask_full || t == 0)) {
 #pragma unroll 1
-        for (int i = gtid; i < p.P; i += GT) mask_row[i] = 0;
+        for (int i = gtid; i < p.P; i += NT) mask_row[i] = 0;
     }
-    if (STG) cp_async_wait_all();                          // (also completes the per-env records requested above)
-    evl_group_sync<G>(g);
+    if (HEAVY && (p.out.port_energy || p.out.dep_sat || p.out.dep_cap)) {   // dense per-port outputs: defaults first
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll 1
+        for (int i = gtid; i < p.P; i += NT) {
+            const size_t ip = (size_t)e * p.P + i;
+            if (p.out.port_energy) p.out.port_energy[ip] = 0.f;
+            if (p.out.dep_sat) p.out.dep_sat[ip] = nan;
+            if (p.out.dep_cap) p.out.dep_cap[ip] = nan;
+        }
+    }
 
-    // ---- EV: one thread per connected EV ------------------------------------------------------------------------
     double aProfit = 0, aSatExp = 0, aCh = 0, aDis = 0, aSat = 0, aUsage = 0, aPot = 0;
     int nDep = 0;
     bool overflow = false;
+    if (!idle) {
+    evl_group_sync<G>(g);
+
+    // ---- EV: one thread per connected EV ------------------------------------------------------------------------
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
-        const int port = stage[i];
+        const int port = i == gtid ? (int)first : (int)lst[i];
         const size_t ip = (size_t)e * p.P + port;
-        const uint4 h = STG ? s_hot[i] : p.hot[ip];
-        double cv = STG ? s_cap[i] : p.cap[ip];
-        float exch_new = STG ? s_exch[i] : p.exch[ip];
-        const double a = (STG && ext_actions) ? (double)s_act[i] : agent_action<ActT>(p, actions, ip, t);
+        const uint4 h = p.hot[ip];
+        double cv = p.cap[ip];
+        double exch_new = p.exch[ip];
+        const double a = agent_action<ActT>(p, actions, ip, t);
         const unsigned hx = NP == 2 ? p.hot[ip ^ 1].x : 0u;
         const double am_raw = NP == 2 ? agent_action<ActT>(p, actions, ip ^ 1, t) : 0.0;   // same 32 B sector as `a`
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
@@ -418,8 +312,8 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
                 double aj = a;
                 if (p0 + j != port) {
                     const size_t ij = (size_t)e * p.P + p0 + j;
-                    const unsigned hx = p.hot[ij].x;
-                    const bool occ_j = (int)(int16_t)(hx & 0xFFFFu) <= t && t <= (int)(int16_t)(hx >> 16);
+                    const unsigned hj = p.hot[ij].x;
+                    const bool occ_j = (int)(int16_t)(hj & 0xFFFFu) <= t && t <= (int)(int16_t)(hj >> 16);
                     aj = occ_j ? agent_action<ActT>(p, actions, ij, t) : 0.0;
                 }
                 sum = sum + aj;
@@ -431,52 +325,72 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             if (over || under) an = (over ? an : -an) / sum;
         }
         double energy = 0.0, act_amps = 0.0, pwv = 0.0;
+        const double cv_old = cv;
         if (an != 0.0) {
             double cap = cv;
             bool em_cross;
-            const bool active = ev_step_item<false>(p, cs, h.z, h.w, an, cap, energy, act_amps, em_cross);
+            const bool active = ev_step_item<HEAVY>(p, cs, h.z, h.w, an, cap, energy, act_amps, em_cross);
             if (active) {                                                 // amps == 0: nothing changes  ev.py:158-163
                 cv = cap;
                 p.cap[ip] = cv;
-                exch_new = exch_new + (float)energy;                     // total_energy_exchanged  ev.py:178
+                exch_new = exch_new + energy;                            // total_energy_exchanged  ev.py:178
                 p.exch[ip] = exch_new;
             }
             const double ae = fabs(energy);
-            if (an > 0.0) { aProfit += ae * et0.cp; aCh += ae; }          // ev_charger.py:178-179
-            else          { aProfit += ae * et0.dp; aDis += ae; }         // ev_charger.py:194-195
+            if (an > 0.0) { aProfit += ae * price.x; aCh += ae; }         // ev_charger.py:178-179
+            else          { aProfit += ae * price.y; aDis += ae; }        // ev_charger.py:194-195
             pwv = ev2b_div_c(energy * 60.0, p.period, p.rperiod);         // :180,196
+            if (HEAVY && p.stats && em_cross) atomicAdd(&p.cs_em[(size_t)e * p.C + c], 1);   // ev.py:401-402 (integer: order-free)
         }
+        if (HEAVY && p.stats) {             // EV.step bookkeeping: historic_soc / active_steps / |energy|  ev.py:156,178-185
+            const EvSpec *sq = p.spec + hot_spec(h);
+            const double soc0 = ev2b_div_c(cv_old, __ldg(&sq->B), __ldg(&sq->rB));
+            int cn = p.st_cnt[ip];
+            p.st_soc_sum[ip] += soc0;
+            if (an != 0.0 && act_amps != 0.0) { p.st_act[ip * (size_t)p.L + (cn >> 16)] = soc0; cn += 1 << 16; }
+            if (an != 0.0) p.st_abs_e[ip] += fabs(energy);
+            p.st_cnt[ip] = cn + 1;
+        }
+        if (HEAVY && p.out.port_energy) p.out.port_energy[ip] = (float)energy;
         if (NP != 1) { pw[port] = pwv; amp[port] = act_amps; }
         double potv = 0.0;
+        unsigned flags = 1u;
+        const EvSpec *sp = p.spec + hot_spec(h);
         if (t >= hot_t_dep(h)) {                                          // departure  ev_charger.py:209-224, ev.py:199-214
-            const double des = __ldg(&p.spec[hot_spec(h)].desired);
+            const double des = __ldg(&sp->desired);
             const double sat = (cv < des - 0.001) ? cv / des : 1.0;
-            aSatExp += evl_departure_penalty(p, cv, des, sat);
+            aSatExp += evl_departure_penalty<HEAVY>(p, cv, des, sat);
             aSat += sat;
             ++nDep;
-            stage[i] = (uint16_t)kEvlGone;                                // (stage[i] already holds the port of an EV that stays)
+            stage[i] = (uint16_t)kEvlGone;
             if (mask_row) mask_row[port] = 0;
-            if (want_obs) {
-                float *o = obs_row + p.obs_slot[port];
-                o[0] = 0.f; o[1] = 0.f;
-                if (p.state_kind == EV2B_STATE_PUBLIC_PST) o[2] = 0.f;
+            if (want_obs) evl_obs_clear(p, obs_row, port);
+            if (HEAVY) {
+                if (p.out.dep_sat) p.out.dep_sat[ip] = sat;
+                if (p.out.dep_cap) p.out.dep_cap[ip] = cv;
+                if (p.stats) {                                            // ev_charger.py:218-220, utils.py:49-63
+                    const SessRec r0 = p.sess[((size_t)s * p.P + port) * p.Smax + hot_cursor(h) - 1];
+                    double d1, d2;
+                    finalize_ev(p, ip, sp, r0.afap, hot_t_arr(h), hot_t_dep(h), cv, d1, d2);
+                    if (NP == 1) {
+                        const size_t ec = (size_t)e * p.C + c;
+                        p.cs_sat_sum[ec] += sat; p.cs_served[ec] += 1; p.cs_dcal[ec] += d1; p.cs_dcyc[ec] += d2;
+                    } else { dsat[port] = sat; dcal[port] = d1; dcyc[port] = d2; flags |= 6u; }
+                }
             }
         } else {
+            stage[i] = (uint16_t)port;
             if (mask_row) mask_row[port] = 1;
-            const EvSpec *sp = p.spec + hot_spec(h);
             const double B = __ldg(&sp->B);
-            aSatExp += evl_unreachable_penalty(p, sp, cv, hot_t_dep(h) - tq);
+            aSatExp += evl_unreachable_penalty<HEAVY>(p, sp, cv, hot_t_dep(h) - tq);
             if (cv < B && hot_t_dep(h) > tq) potv = __ldg(&p.pot_kw[hot_spec(h) * p.n_cls + cs.cls]);   // utils.py:766-777
-            if (want_obs) {                                               // state.py:37-57, 85-102, 137-151
-                float *o = obs_row + p.obs_slot[port];
-                if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
-                    o[0] = (cv == B) ? 1.f : 0.5f;
-                    o[1] = exch_new;
-                    o[2] = (float)(tq - hot_t_arr(h));
-                } else {
-                    o[0] = (float)ev2b_div_c(cv, B, __ldg(&sp->rB));
-                    o[1] = (float)(hot_t_dep(h) - tq);
-                }
+            if (want_obs) evl_obs_tuple<HEAVY>(p, obs_row, port, c, h, cv, B, sp, exch_new, tq);
+            if (HEAVY && p.stats && tq >= p.T) {      // episode over: EVs still connected count too (env.EVs)
+                const SessRec r0 = p.sess[((size_t)s * p.P + port) * p.Smax + hot_cursor(h) - 1];
+                double d1, d2;
+                finalize_ev(p, ip, sp, r0.afap, hot_t_arr(h), hot_t_dep(h), cv, d1, d2);
+                if (NP == 1) { const size_t ec = (size_t)e * p.C + c; p.cs_dcal[ec] += d1; p.cs_dcyc[ec] += d2; }
+                else { dcal[port] = d1; dcyc[port] = d2; flags |= 4u; }
             }
         }
         if (NP == 1) {                                                    // charger == port: accounting in place
@@ -491,7 +405,7 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + port] = (float)rA;
         } else {
             pot[port] = potv;
-            occ[port] = 1;
+            occ[port] = (unsigned char)flags;
         }
     }
     evl_group_sync<G>(g);
@@ -505,36 +419,39 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         const SessRec r = p.sess[((size_t)s * p.P + port) * p.Smax + cur];
         p.hot[ip] = r.hot;
         p.cap[ip] = r.cap0;
-        p.exch[ip] = 0.f;
+        p.exch[ip] = 0.0;
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
         const CsStatic &cs = cs_of<UNI>(p, c);
         const EvSpec *sp = p.spec + hot_spec(r.hot);
         const double B = __ldg(&sp->B);
         double potv = 0.0;
-        aSatExp += evl_unreachable_penalty(p, sp, r.cap0, hot_t_dep(r.hot) - tq);
+        aSatExp += evl_unreachable_penalty<HEAVY>(p, sp, r.cap0, hot_t_dep(r.hot) - tq);
         if (r.cap0 < B && hot_t_dep(r.hot) > tq) potv = __ldg(&p.pot_kw[hot_spec(r.hot) * p.n_cls + cs.cls]);
+        unsigned flags = NP == 1 ? 0u : (unsigned)occ[port];
+        if (HEAVY && p.stats) {
+            p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0;
+            if (tq >= p.T) {                          // arrives as the episode ends: finalised at once (env.EVs)
+                double d1, d2;
+                finalize_ev(p, ip, sp, r.afap, hot_t_arr(r.hot), hot_t_dep(r.hot), r.cap0, d1, d2);
+                if (NP == 1) { const size_t ec = (size_t)e * p.C + c; p.cs_dcal[ec] += d1; p.cs_dcyc[ec] += d2; }
+                else {
+                    if (flags & 4u) { dcal[port] += d1; dcyc[port] += d2; } else { dcal[port] = d1; dcyc[port] = d2; }
+                    flags |= 4u;
+                }
+            }
+        }
         if (NP == 1) {                                                    // (an EV that left this very port in step t added 0)
             double rPot = potv;
             if (rPot > cs.max_power) rPot = cs.max_power;
             else if (rPot < cs.min_power) rPot = 0.0;
             aPot += rPot;
         } else {
-            if (!occ[port]) { pw[port] = 0.0; amp[port] = 0.0; }         // (an EV may have left this very port in step t)
+            if (!(flags & 1u)) { pw[port] = 0.0; amp[port] = 0.0; }      // (an EV may have left this very port in step t)
             pot[port] = potv;
-            occ[port] = 1;
+            occ[port] = (unsigned char)(flags | 1u);
         }
         if (mask_row) mask_row[port] = 1;
-        if (want_obs) {
-            float *o = obs_row + p.obs_slot[port];
-            if (p.state_kind == EV2B_STATE_PUBLIC_PST) {
-                o[0] = (r.cap0 == B) ? 1.f : 0.5f;
-                o[1] = 0.f;
-                o[2] = (float)(tq - hot_t_arr(r.hot));
-            } else {
-                o[0] = (float)ev2b_div_c(r.cap0, B, __ldg(&sp->rB));
-                o[1] = (float)(hot_t_dep(r.hot) - tq);
-            }
-        }
+        if (want_obs) evl_obs_tuple<HEAVY>(p, obs_row, port, c, r.hot, r.cap0, B, sp, 0.0, tq);
     }
     evl_group_sync<G>(g);
 
@@ -546,8 +463,14 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         double rP = 0, rA = 0, rPot = 0;
 #pragma unroll
         for (int j = 0; j < n; ++j) {
-            if (occ[p0 + j]) { rP += pw[p0 + j]; rA += amp[p0 + j]; rPot += pot[p0 + j]; }
+            const unsigned f = occ[p0 + j];
+            if (f & 1u) { rP += pw[p0 + j]; rA += amp[p0 + j]; rPot += pot[p0 + j]; }
             if (rA - 0.0001 > cs.imax) overflow = true;                   // ev_charger.py:203-205
+            if (HEAVY && p.stats && (f & 6u)) {                           // the charger's totals, in port order
+                const size_t ec = (size_t)e * p.C + c;
+                if (f & 2u) { p.cs_sat_sum[ec] += dsat[p0 + j]; p.cs_served[ec] += 1; }
+                p.cs_dcal[ec] += dcal[p0 + j]; p.cs_dcyc[ec] += dcyc[p0 + j];
+            }
         }
         if (rPot > cs.max_power) rPot = cs.max_power;                     // utils.py:779-789
         else if (rPot < cs.min_power) rPot = 0.0;
@@ -563,12 +486,11 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         const double tot = warp_sum8(q, lane);
         if ((lane & 3) == 0) wsum[gw * EvlNSum + (lane >> 2)] = tot;
     }
-    cp_async_wait_all();
     evl_group_sync<G>(g);
 
     // ---- LS: the group's last warp writes next step's list: kept EVs in list order, then the arrivals ----------
     if (gw == G - 1) {
-        uint16_t *nxt = p.occ_list + (size_t)e * p.P;      // in place: every thread staged the old list before the first barrier
+        uint16_t *nxt = p.occ_list + (size_t)e * p.P;      // in place: every thread is past its last read of the old list
         int base = 0;
 #pragma unroll 1
         for (int i0 = 0; i0 < n_old; i0 += 32) {
@@ -583,14 +505,18 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
         if (lane == 0) p.occ_n[e] = base + nArr;
     }
     if (gw != 0) return;
+    }  // !idle
 
-    // ---- TR: transformer sums + overload (warp 0), same lane split as step_kernel's phase B ---------------------
+    // ---- TR (warp 0): transformer sums + overload, same lane split as step_kernel's phase B ---------------------
+    cp_async_wait_all();
+    __syncwarp();
+    double ovsum = 0.0;
     {
         const int lg = p.tr_lg, nseg = 1 << lg, per = 32 >> lg;   // 2^lg lanes share one transformer (host: largest with 2^lg * Tr <= 32)
         for (int k0 = 0; k0 < p.Tr; k0 += per) {
             const int k = k0 + (lane >> lg), seg = lane & (nseg - 1);
             double sp_ = 0.0;
-            if (k < p.Tr) {
+            if (!idle && k < p.Tr) {
                 const int i0 = p.tr_cs_off[k], n_k = p.tr_cs_off[k + 1] - i0;
                 const int chunk = (n_k + nseg - 1) >> lg;
                 const int lo = seg * chunk, hi = min(n_k, lo + chunk);
@@ -598,30 +524,112 @@ __global__ void __launch_bounds__(kEvlThreads, 8) evl_step_kernel(const __grid_c
             }
             for (int o = nseg >> 1; o > 0; o >>= 1) sp_ += __shfl_xor_sync(0xffffffffu, sp_, o);
             if (seg == 0 && k < p.Tr) {                                   // transformer.py:264-302
-                const double *tq4 = pre + kPreTr + 4 * k;
+                const double *tq4 = pre + kEvlTr + 4 * k;
                 const double ptot = (tq4[0] + tq4[1]) + sp_;
                 double ov = 0.0;
                 if (ptot > tq4[2] + 0.0001 || ptot < tq4[3] - 0.0001) ov = fabs(ptot - tq4[2]);
-                trov[k] = ov;
+                ovsum += ov;
+                if (HEAVY && p.n_bus > 0) trp[k] = ptot;
                 if (p.out.tr_power)    p.out.tr_power[(size_t)e * p.Tr + k] = ptot;
                 if (p.out.tr_overload) p.out.tr_overload[(size_t)e * p.Tr + k] = ov;
             }
         }
-        __syncwarp();
+        ovsum = warp_sum(ovsum);
     }
-    // ---- reward, KPI sums, step counter: one lane ------------------------------------------------------------------
-    if (lane == 0) {
-        EvlTotals q;
+    // ---- distribution grid: Laurent power flow of this env (the warp)   grid.py:120-141 -------------------------
+    double lossv = 0.0;
+    if (HEAVY && p.n_bus > 0) {
+        __syncwarp();
+        lossv = power_flow_env(p, pfv, trp, s, t, e, lane);
+        if (lane == 0 && p.out.node_voltage) p.out.node_voltage[(size_t)e * (p.n_bus + 1)] = 1.0;
+    }
+    // ---- reward, KPI sums, step counter: every lane computes the (uniform) reward, lane k stores quantity k ------
+    double q[EvlNSum];
 #pragma unroll
-        for (int k = 0; k < EvlNSum; ++k) {
-            double v = wsum[k];
-            for (int w = 1; w < G; ++w) v += wsum[w * EvlNSum + k];
-            q.v[k] = v;
+    for (int k = 0; k < EvlNSum; ++k) {
+        double v = 0.0;
+        if (!idle) { v = wsum[k]; for (int w = 1; w < G; ++w) v += wsum[w * EvlNSum + k]; }
+        q[k] = v;
+    }
+    const int cnts = (int)q[EvlCounts];
+    const int n_dep = cnts & 0xFFFFF;
+    const double usage = q[EvlUsage];                                     // current_power_usage[t]  ev2gym_env.py:375
+    const double costs = q[EvlProfit];
+    const double pot_now = pre[kPrePot];                                  // charge_power_potential[t]
+    const double setpoint = pre[kEvlSet], setpoint_next = pre[kEvlSetNext];
+    double reward = 0.0;
+    {
+        const int rk = p.reward_kind;
+        if (rk == EV2B_REWARD_SQ_TRACKING) {                              // reward.py:11-12
+            const double m = setpoint < pot_now ? setpoint : pot_now;
+            reward = -((m - usage) * (m - usage));
+        } else if (rk == EV2B_REWARD_PROFIT_TR_USER) {                    // reward.py:36-44
+            reward = costs - 100.0 * ovsum - q[EvlSatExp];
+        } else if (rk == EV2B_REWARD_PROFIT_MAX) {                        // reward.py:81-87
+            reward = costs - q[EvlSatExp];
+        } else if (rk == EV2B_REWARD_SQTR_TR_USER) {                      // reward.py:16-32
+            double m = setpoint < pot_now ? setpoint : pot_now;
+            const double lim = pre[kEvlTr + 2];                           // transformers[0].max_power[t]
+            if (lim < m) m = lim;
+            reward = -((m - usage) * (m - usage)) - 100.0 * ovsum - q[EvlSatExp];
+        } else if (rk == EV2B_REWARD_SQ_TRACKING_PENALTY) {               // reward.py:46-58
+            const double m = setpoint < pot_now ? setpoint : pot_now;
+            reward = -((m - usage) * (m - usage));
+            if (usage == 0.0 && pre[kEvlPotPrev] != 0.0) reward = reward - 100.0;   // potential[current_step-2]; 0 at t = 0
+        } else if (rk == EV2B_REWARD_SIMPLE) {                            // reward.py:60-65
+            reward = -((setpoint - usage) * (setpoint - usage));
+        } else if (rk == EV2B_REWARD_MIN_TRACKER_SURPLUS) {               // reward.py:67-76
+            if (setpoint < usage) reward -= (usage - setpoint) * (usage - setpoint);
+            reward += usage;
+        } else if (rk == EV2B_REWARD_V2G_COSTS_SIMPLE) {                  // reward.py:150-153
+            reward = costs;
+        } else if (rk == EV2B_REWARD_V2G_PROFITMAX || rk == EV2B_REWARD_V2G_PROFITMAX_V2 ||
+                   rk == EV2B_REWARD_PST_PROFITMAX_V2) {                  // reward.py:123-148, 155-213, 281-339
+            reward = costs - q[EvlSatExp];
+            if (rk == EV2B_REWARD_PST_PROFITMAX_V2 && setpoint < usage) reward += 1000.0 * (setpoint - usage);
+        } else if (HEAVY && rk == EV2B_REWARD_GRID_FULL) {                // reward.py:89-111
+            reward = costs + 1000.0 * lossv - q[EvlSatExp];
+        } else if (HEAVY && rk == EV2B_REWARD_GRID_SIMPLE) {              // reward.py:114-121
+            reward = 1000.0 * lossv;
+        } else if (HEAVY && rk == EV2B_REWARD_GRID_PROFITMAX_V2) {        // reward.py:215-279
+            reward = (costs - q[EvlSatExp]) + 50000.0 * lossv;
         }
-        double ovsum = 0.0;
-        for (int k = 0; k < p.Tr; ++k) ovsum += trov[k];
-        evl_finish_env(p, e, s, tq, pre, pre[kPrePot], pre[kPreSet], pre[kPreSetNext], pre[kPreTr + 2], q, ovsum, nArr,
-                       n_old, want_obs);
+    }
+    const double dsp = setpoint - usage;                                  // utils.py:37-44
+    double delta;
+    switch (lane) {
+    case EV2B_KPI_TOTAL_REWARD: delta = reward; break;
+    case EV2B_KPI_TOTAL_PROFITS: delta = costs; break;
+    case EV2B_KPI_ENERGY_CHARGED: delta = q[EvlCharged]; break;
+    case EV2B_KPI_ENERGY_DISCHARGED: delta = q[EvlDischarged]; break;
+    case EV2B_KPI_TR_OVERLOAD: delta = ovsum; break;
+    case EV2B_KPI_EVS_SERVED: delta = (double)n_dep; break;
+    case EV2B_KPI_SAT_SUM: delta = q[EvlSatSum]; break;
+    case EV2B_KPI_TRACKING_ERROR: delta = dsp * dsp; break;
+    case EV2B_KPI_ENERGY_TRACKING_ERROR: delta = fabs(dsp); break;
+    case EV2B_KPI_TRACKER_VIOLATION: delta = usage > setpoint ? usage - setpoint : 0.0; break;
+    case EV2B_KPI_EVS_SPAWNED: delta = (double)nArr; break;
+    case EV2B_KPI_INVALID_ACTIONS: delta = (double)(p.P - n_old); break;   // every empty port  ev_charger.py:137-140
+    default: delta = 1.0; break;                                           // EV2B_KPI_STEPS
+    }
+    if (idle) evl_group_sync<G>(g);                   // the group's other warps have read env_step (they only arrive)
+    if (lane < EV2B_KPI_COUNT) {
+        p.env_kpi[(size_t)e * EV2B_KPI_COUNT + lane] = pre[lane] + delta;
+    } else if (lane == 13) {
+        p.env_pot[e] = (tq < p.T) ? q[EvlPot] : 0.0;                      // ev2gym_env.py:424-426
+    } else if (lane == 14) {
+        p.env_usage[e] = usage;
+        p.env_step[e] = tq;
+    } else if (lane == 15) {
+        unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
+        if (tq >= p.T) status |= EV2B_ST_DONE;                            // ev2gym_env.py:460
+        if (p.out.status) p.out.status[e] = status;
+        if (p.out.reward) p.out.reward[e] = reward;
+    } else if (lane == 16) {
+        if (p.out.total_costs) p.out.total_costs[e] = costs;
+        if (p.reward_kind == EV2B_REWARD_SQ_TRACKING_PENALTY) p.env_pot_prev[e] = pot_now;
+    } else if (lane == 17) {
+        if (want_obs) obs_header(p, obs_row, s, tq, usage, setpoint_next);
     }
 }
 

@@ -295,7 +295,7 @@ class BatchedEngine:
         def view(ptr, shape, typestr):
             return torch.as_tensor(_CudaView(ptr, shape, typestr, self), device=self.dev)
         return {
-            "port_cap": view(sv.port_cap, (E, P), "<f8"), "port_exch": view(sv.port_exch, (E, P), "<f4"),
+            "port_cap": view(sv.port_cap, (E, P), "<f8"), "port_exch": view(sv.port_exch, (E, P), "<f8"),
             "port_hot": view(sv.port_hot, (E, P, 4), "<i4"), "env_step": view(sv.env_step, (E,), "<i4"),
             "env_scn": view(sv.env_scn, (E,), "<i4"), "env_potential": view(sv.env_potential, (E,), "<f8"),
             "env_usage": view(sv.env_usage, (E,), "<f8"), "env_kpi": view(sv.env_kpi, (E, sv.n_kpi), "<f8"),

@@ -19,6 +19,7 @@ Scenario generation (the reference's `reset()` loaders) is out of scope for the 
 """
 from __future__ import annotations
 
+import datetime
 import math
 from typing import Callable, List, Optional, Sequence, Union
 
@@ -27,6 +28,11 @@ import numpy as np
 from .compat import ChargerView, EVView, TransformerView
 from .engine import REWARD_KINDS, STATE_KINDS, BatchedEngine, EngineError, _fn_name
 from .scenario import Scenario, ScenarioPack, Topology, assign_ports
+
+# The engine class the facades instantiate.  The product has exactly one: BatchedEngine (CUDA, raises without a GPU).
+# tests/test_dropin_reference.py points this at an adapter over the SIMT emulator (tests/simt_emu) so that the facade's
+# HOST logic -- views, bookkeeping, plugin calls -- can be checked against the reference in a container without a GPU.
+_ENGINE_CLS = BatchedEngine
 
 _FACADE_OUTPUTS_GRID = ("node_voltage",)
 _FACADE_OUTPUTS = ("reward", "status", "obs", "cs_power", "cs_current", "tr_power", "tr_overload", "total_costs",
@@ -117,7 +123,7 @@ class EV2GymB200:
         self.simulate_grid = False
         self._fused_state = _fn_name(state_function) in STATE_KINDS and _fn_name(state_function) is not None
         self._fused_reward = _fn_name(reward_function) in REWARD_KINDS and _fn_name(reward_function) is not None
-        self._engine = BatchedEngine(topo, 1, reward=reward_function if self._fused_reward else None,
+        self._engine = _ENGINE_CLS(topo, 1, reward=reward_function if self._fused_reward else None,
                                      state=state_function if self._fused_state else None, device=device,
                                      outputs=_FACADE_OUTPUTS + (_FACADE_OUTPUTS_GRID if topo.n_bus else ()), stats=True)
         self._port_off = topo.cs_port_off
@@ -134,10 +140,12 @@ class EV2GymB200:
     def _next_scenario(self, seed) -> Scenario:
         if self._ref is not None:
             self._ref.reset(seed=seed)
-            self.sim_date = self._ref.sim_date
+            self.sim_date = self._ref.sim_date                       # ev2gym_env.py:262-287 (stepped below, :558)
+            self.sim_starting_date = getattr(self._ref, "sim_starting_date", self.sim_date)
             return self._export(self._ref)
         sc = self._scenarios[self._scn_iter % len(self._scenarios)]
         self._scn_iter += 1
+        self.sim_date = self.sim_starting_date = getattr(sc, "sim_date", None)
         return sc
 
     def reset(self, seed=None, options=None, **kwargs):
@@ -277,6 +285,8 @@ class EV2GymB200:
         self.current_ev_departed = len(sat_list)
         self.total_evs_spawned += self.current_ev_arrived
         self.current_step = t + 1
+        if self.sim_date is not None:                                    # _step_date  ev2gym_env.py:422, 558-561
+            self.sim_date = self.sim_date + datetime.timedelta(minutes=self.timescale)
         if self.current_step < self.simulation_length:
             self.charge_power_potential[self.current_step] = float(st["env_potential"][0].item())
         self.current_evs_parked += self.current_ev_arrived - self.current_ev_departed

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define EV2B_ABI_VERSION 1
+#define EV2B_ABI_VERSION 2
 
 /* reward_function / state_function fused on the device (ev2gym/rl_agent/reward.py, state.py). */
 enum ev2b_reward_kind {
@@ -170,7 +170,7 @@ typedef struct {
 typedef struct {
     int32_t n_envs, n_ports, n_chargers, n_transformers, obs_dim, n_kpi;
     double   *port_cap;        /* [E,P] current_capacity (kWh), float64                             */
-    float    *port_exch;       /* [E,P] total_energy_exchanged                                     */
+    double   *port_exch;       /* [E,P] total_energy_exchanged (kWh), float64 like the reference's (ev.py:178)  */
     uint32_t *port_hot;        /* [E,P,4] packed session words, see DESIGN.md                      */
     int32_t  *env_step;        /* [E]   current_step                                               */
     int32_t  *env_scn;         /* [E]   scenario id in the bank                                    */

@@ -157,6 +157,14 @@ class EmuEngine:
                                        C.byref(self._so), None), "ev2b_step_k")
         return self.out
 
+    def episode_stats(self):
+        """get_statistics(env) of every env (needs stats=True), like BatchedEngine.episode_stats."""
+        from ev2gym_b200.engine import STAT_NAMES
+        out = np.zeros((self.E, len(STAT_NAMES)), dtype=np.float64)
+        self.L.ev2b_episode_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self.L.ev2b_episode_stats(self.h, out.ctypes.data, None), "ev2b_episode_stats")
+        return {n: out[:, i].copy() for i, n in enumerate(STAT_NAMES)}
+
     def kernel_launches(self):
         """(step_kernel, evl_step_kernel, evl_rebuild_kernel) launches of this handle."""
         return tuple(int(self.L.ev2b_kernel_launches(self.h, k)) for k in range(3))
@@ -170,7 +178,42 @@ class EmuEngine:
             n = int(np.prod(shape))
             buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
             return np.frombuffer(buf, dtype=dt).reshape(shape)
-        return {"port_cap": view(sv.port_cap, (E, P), np.float64), "port_exch": view(sv.port_exch, (E, P), np.float32),
+        return {"port_cap": view(sv.port_cap, (E, P), np.float64), "port_exch": view(sv.port_exch, (E, P), np.float64),
                 "port_hot": view(sv.port_hot, (E, P, 4), np.int32), "env_step": view(sv.env_step, (E,), np.int32),
                 "env_scn": view(sv.env_scn, (E,), np.int32), "env_potential": view(sv.env_potential, (E,), np.float64),
                 "env_usage": view(sv.env_usage, (E,), np.float64), "env_kpi": view(sv.env_kpi, (E, sv.n_kpi), np.float64)}
+
+
+class EmuTorchEngine(EmuEngine):
+    """EmuEngine behind BatchedEngine's torch-facing surface (CPU tensors), so that the facades of ev2gym_b200.env can be
+    driven without a GPU: tests monkeypatch `ev2gym_b200.env._ENGINE_CLS` with this class.  Test infrastructure only."""
+
+    def __init__(self, topo, n_envs, reward=None, state=None, device=0, outputs=("reward", "status", "obs"), stats=False):
+        import torch
+        from ev2gym_b200.engine import _fn_name
+        self.torch = torch
+        self.dev = torch.device("cpu")
+        self.reward_name, self.state_name = _fn_name(reward), _fn_name(state)
+        super().__init__(topo, n_envs, reward=self.reward_name, state=self.state_name, outputs=outputs, stats=stats)
+
+    def _t(self, d):
+        return {k: self.torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v) for k, v in d.items()}
+
+    def reset(self, env_lo=0, env_hi=None, scn_ids=None):
+        obs = super().reset(env_lo, env_hi, scn_ids)
+        return None if obs is None else self.torch.from_numpy(obs)
+
+    def reset_done(self):
+        obs = super().reset_done()
+        return None if obs is None else self.torch.from_numpy(obs)
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions.detach().cpu().numpy())
+        return self._t(super().step(a))
+
+    def state_tensors(self):
+        return self._t(self.state())
+
+    @property
+    def launch_count(self):
+        return int(self.L.ev2b_launch_count(self.h))

@@ -98,6 +98,15 @@ void bar_sync(int id, int nthreads) {
     arrive(g_named[id], nthreads);
 }
 
+// PTX bar.arrive: counts the thread in, does not wait (the thread may even exit afterwards)
+void bar_arrive(int id, int nthreads) {
+    if (id <= 0 || id >= kNamed) die("bar_arrive: id out of range");
+    if (g_named[id].arrived == 0) g_named_expect[id] = nthreads;
+    else if (g_named_expect[id] != nthreads) die("bar_arrive: threads disagree on the thread count of a named barrier");
+    Bar &b = g_named[id];
+    if (++b.arrived >= nthreads) { b.arrived = 0; ++b.gen; }
+}
+
 static void warp_gather(unsigned mask) {
     Warp &w = g_warps[g_cur->tid >> 5];
     const unsigned lane = g_cur->tid & 31u;

@@ -47,6 +47,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::functio
 unsigned char *dyn_smem();
 void syncthreads();
 void bar_sync(int id, int nthreads);       // PTX bar.sync id, nthreads
+void bar_arrive(int id, int nthreads);     // PTX bar.arrive id, nthreads
 void syncwarp(unsigned mask);
 uint64_t shfl(unsigned mask, uint64_t bits, int src_lane);
 unsigned ballot(unsigned mask, int pred);

@@ -43,7 +43,7 @@ def _occupied_ports(eng, e):
 def _run_vs_oracle(emu, topo, bank, E, reward, state, adt, kernel, G=None, outputs=OUT, steps=None, switch=None,
                    monkeypatch=None):
     """Steps an emulated engine and the oracle side by side; `switch(t)` -> True asks for a per-port output on step t
-    (which the event-driven kernel does not cover: that launch takes step_kernel and the list must be rebuilt)."""
+    (under EV2B_EVL_MIX=1, a test-only knob, such a launch takes step_kernel and the list must be rebuilt afterwards)."""
     from oracle.oracle import OracleBatch
     monkeypatch.setenv("EV2B_KERNEL", kernel)
     if G:
@@ -131,20 +131,6 @@ def test_evlist_kernel_matches_oracle(emu, C, n, Tr, E, reward, state, adt, G, m
     eng.close()
 
 
-@pytest.mark.parametrize("switch,value", [("EV2B_EVL_STAGE", "1"), ("EV2B_EVL_PREFETCH", "3")])
-@pytest.mark.parametrize("G", [1, 2])
-@pytest.mark.parametrize("shape", [1, 3])
-def test_evlist_experiment_switches(emu, switch, value, G, shape, monkeypatch):
-    """The opt-in build / launch variants kept for A/B on the GPU (EV records staged with cp.async; L2 prefetch) compute
-    the same thing (the emulator defers cp.async copies until cp.async.wait_all, so a missing wait shows up here)."""
-    C, n, Tr, E, reward, state, adt = SHAPES[shape]
-    monkeypatch.setenv(switch, value)
-    topo, bank = _bank(C, n, Tr)
-    eng, _ = _run_vs_oracle(emu, topo, bank, E, reward, state, adt, "evlist", G=G, monkeypatch=monkeypatch)
-    assert eng.kernel_launches() == (0, topo.T, 0)
-    eng.close()
-
-
 @pytest.mark.parametrize("G", [1, 2, 4])
 def test_evlist_random_thread_schedule(emu, G, monkeypatch):
     """Same run with the emulator resuming threads in a seeded random order at every barrier round (a thread that runs
@@ -219,7 +205,9 @@ def test_evlist_action_mask_incremental(emu, G, monkeypatch):
 
 
 def test_evlist_and_step_kernel_interleave(emu, monkeypatch):
-    """Launches that ask for a per-port output take step_kernel; the next event-driven launch re-derives the list."""
+    """Both kernels on one handle (EV2B_EVL_MIX=1: launches that ask for port_energy take step_kernel); the next
+    event-driven launch re-derives the list from the hot words."""
+    monkeypatch.setenv("EV2B_EVL_MIX", "1")
     topo, bank = _bank(40, 2, 5)
     eng, _ = _run_vs_oracle(emu, topo, bank, 5, SHAPES[1][4], SHAPES[1][5], "float32", "evlist", G=2,
                             switch=lambda t: t % 5 in (1, 2), monkeypatch=monkeypatch)
@@ -397,16 +385,18 @@ def test_evlist_on_bench_scenario_banks(emu, pack_name, reward, state, G, monkey
 
 
 ALL_OUT = ("reward", "status", "obs", "cs_power", "cs_current", "tr_power", "tr_overload", "total_costs", "action_mask",
-           "dep_sat", "port_energy")
+           "dep_sat", "dep_cap", "port_energy")
 
 
+@pytest.mark.parametrize("kernel", ["percharger", "evlist"])
 @pytest.mark.parametrize("name", golden_cases())
-def test_step_kernel_matches_reference_trace_on_emulator(emu, name, monkeypatch):
-    """tests/test_gpu_parity.py::test_cuda_matches_reference_trace on the emulator: step_kernel in its full-featured
-    instantiation (statistics mode, every output, the Laurent power flow of the grid episodes) on all recorded reference
-    episodes -- so a change to the shared model code (ev_step_item) is checked here before it reaches a GPU."""
+def test_full_featured_kernels_match_reference_trace_on_emulator(emu, name, kernel, monkeypatch):
+    """tests/test_gpu_parity.py::test_cuda_matches_reference_trace on the emulator: both step kernels in their
+    full-featured instantiation (statistics mode, every output, the Laurent power flow of the grid episodes) on all
+    recorded reference episodes, including get_statistics() at the end -- so a change to the shared model code
+    (ev_step_item) is checked here before it reaches a GPU."""
     from ev2gym_b200.scenario import ScenarioPack
-    monkeypatch.setenv("EV2B_KERNEL", "percharger")
+    monkeypatch.setenv("EV2B_KERNEL", kernel)
     pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
     tr = np.load(f"{GOLDEN}/{name}.trace.npz")
     topo = pack.topo
@@ -434,5 +424,14 @@ def test_step_kernel_matches_reference_trace_on_emulator(emu, name, monkeypatch)
             assert _close(out["node_voltage"][e], tr["node_voltage"][:, t], 1e-9, 1e-12), (t, "node voltage")
         assert bool(out["status"][e] & 1) == bool(tr["done"][t])
         assert np.count_nonzero(~np.isnan(out["dep_sat"][e])) == tr["n_departed"][t]
-    assert eng.kernel_launches()[1] == 0
+        assert np.array_equal(np.isnan(out["dep_sat"][e]), np.isnan(out["dep_cap"][e]))
+        if "port_energy" in tr.files:
+            assert _close(out["port_energy"][e], tr["port_energy"][t], 1e-5, 1e-6), (t, "port energy")
+    assert eng.kernel_launches()[1 if kernel == "percharger" else 0] == 0
+    stats = eng.episode_stats()
+    from ev2gym_b200.engine import STAT_NAMES
+    for n in STAT_NAMES:
+        ref = float(tr["stat_" + n])
+        got = float(stats[n][E - 1])
+        assert (np.isnan(ref) and np.isnan(got)) or got == pytest.approx(ref, rel=1e-9, abs=1e-9), (n, got, ref)
     eng.close()

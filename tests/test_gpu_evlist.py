@@ -154,6 +154,7 @@ def test_evlist_equals_step_kernel_at_c3_size(G, monkeypatch):
     for kn in ("percharger", "evlist", "mixed"):
         monkeypatch.setenv("EV2B_KERNEL", "percharger" if kn == "percharger" else "evlist")
         monkeypatch.setenv("EV2B_EVL_G", str(G))
+        monkeypatch.setenv("EV2B_EVL_MIX", "1" if kn == "mixed" else "0")   # test-only: port_energy launches take step_kernel
         eng = _engine(topo, bank, E, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads",
                       outputs=("reward", "status", "obs"))
         eng.reset()

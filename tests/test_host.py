@@ -49,7 +49,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(L, sym), sym
     L.ev2b_abi_version.restype = ctypes.c_int
-    assert L.ev2b_abi_version() == 1
+    assert L.ev2b_abi_version() == _lib.ABI_VERSION
 
 
 def test_no_cpu_fallback():
