@@ -93,7 +93,7 @@ struct ev2b_handle {
     bool evl = false;                   // lists allocated, schedule built
     bool list_valid = true;             // occ_list / occ_n agree with the hot words of every env
     int evl_G = 4, evl_o[13] = {0};     // warps per env; smem map (v_stride, v_amp, ...)
-    int n_sm = 148;
+    int n_sm = 148, n_sm_create = 148;
     bool evl_mix = false;               // EV2B_EVL_MIX=1 (tests): launches that ask for port_energy take step_kernel
     size_t evl_smem = 0;
     std::set<const void *> smem_opted;  // kernels whose dynamic shared-memory limit has been raised on this device
@@ -226,8 +226,9 @@ static cudaError_t opt_in_smem(ev2b_handle *h, K kern, size_t bytes) {
     return e;
 }
 
+// k_steps > 0: the KSTEP instantiation (p.k_steps steps in one launch; lean kernels only, see evl_kstep_ok)
 template <typename ActT>
-static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st) {
+static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st, bool kstep = false) {
     const int epb = kEvlThreads / (32 * h->evl_G);
     const unsigned grid = (unsigned)((p.env_end - p.env0 + epb - 1) / epb);
     auto go = [&](auto kern) -> cudaError_t {
@@ -239,16 +240,22 @@ static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st) 
     const int np = (h->cs_uniform && (h->np_uniform == 1 || h->np_uniform == 2)) ? h->np_uniform : 0;
     // HEAVY: statistics mode, the distribution grid, the dense per-port outputs
     const bool heavy = h->evl_heavy_layout() || p.out.dep_sat || p.out.dep_cap || p.out.port_energy || p.out.node_voltage;
-#define EV2B_EVL_DISPATCH(G)                                                   \
-    do {                                                                       \
-        if (heavy) {                                                           \
-            if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, true>);   \
-            if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, true>);   \
-            return go(evl_step_kernel<ActT, 0, false, G, true>);               \
-        }                                                                      \
-        if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, false>);      \
-        if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, false>);      \
-        return go(evl_step_kernel<ActT, 0, false, G, false>);                  \
+#define EV2B_EVL_DISPATCH(G)                                                          \
+    do {                                                                              \
+        if (heavy) {                                                                  \
+            if (kstep) return cudaErrorInvalidValue;                                  \
+            if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, true, false>);   \
+            if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, true, false>);   \
+            return go(evl_step_kernel<ActT, 0, false, G, true, false>);               \
+        }                                                                             \
+        if (kstep) {                                                                  \
+            if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, false, true>);   \
+            if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, false, true>);   \
+            return go(evl_step_kernel<ActT, 0, false, G, false, true>);               \
+        }                                                                             \
+        if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, false, false>);      \
+        if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, false, false>);      \
+        return go(evl_step_kernel<ActT, 0, false, G, false, false>);                  \
     } while (0)
     if (h->evl_G == 1) EV2B_EVL_DISPATCH(1);
     if (h->evl_G == 2) EV2B_EVL_DISPATCH(2);
@@ -439,6 +446,7 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         const int cap_thr = C > 256 ? kMaxThreads : (C > 128 ? 256 : 128);   // small CTAs: less barrier skew (measured)
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        h->n_sm_create = n_sm;
         for (int epb = 1; epb <= 64 && epb <= h->E; ++epb) {
             const int thr = epb * C;
             if (thr > cap_thr) break;               // (C > 1024: no step_kernel shape; the event-driven kernel serves the handle)
@@ -469,14 +477,18 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         const bool want = force_on || big || (!force_off && h->E >= 2048);
         if (want && h->P < 65535) {
             h->evl = true;
-            // warps per env: two for the stock env sizes (B200, us per launch, G = 1 / 2 / 4: c3 34.3 / 31.7 / 38.4,
-            // c4 64.8 / 50.2 / 59.7), one for small envs (a warp already covers every connected EV), four for very large ones
-            h->evl_G = h->P <= 64 ? 1 : (h->P <= 512 ? 2 : 4);
+            // warps per env: as many as it takes to fill the machine (~28 resident warps per SM of the lean kernel, 16 of the
+            // HEAVY one), at most 4.  B200, whole episodes, us per launch, G = 1 / 2 / 4: c3 (4096 envs) 23.3 / 26.6 / 34.0,
+            // c4 (8192) 46.0 / 53.0 / 59.4, c5 (2048, HEAVY) 74.8 / 86.9; c3 at 1024 envs 17.5 / 12.3 (profiles/r2_ab_*.json)
+            {
+                const int cap_warps = h->n_sm_create * (h->evl_heavy_layout() ? 16 : 28);
+                h->evl_G = h->E >= cap_warps / 2 ? 1 : (h->E >= cap_warps / 4 ? 2 : 4);
+            }
             if (const char *gv = getenv("EV2B_EVL_G")) { const int v = atoi(gv); if (v == 1 || v == 2 || v == 4) h->evl_G = v; }
             if (const char *mv = getenv("EV2B_EVL_MIX")) h->evl_mix = atoi(mv) != 0 && !big;
             cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
             h->layout_evl();
-            if (h->evl_smem > 200 * 1024) { h->evl_G = 4; h->layout_evl(); }
+            while (h->evl_smem > 200 * 1024 && h->evl_G < 4) { h->evl_G *= 2; h->layout_evl(); }   // fewer envs per CTA
             if (h->evl_smem > 200 * 1024) h->evl = false;          // does not fit: step_kernel takes every launch
         }
         if (!h->evl && big) {
@@ -920,6 +932,30 @@ int ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, in
     AgentCfg ag; ag.kind = agent_kind; ag.seed = seed; ag.low = action_low;
     const size_t stride = (size_t)h->E * h->P * (action_dtype == EV2B_F64 ? 8 : 4);
     float *obs = out ? out->obs : nullptr;
+    // Agents that need nothing but the env's own step (an action tensor, AFAP, ZERO, UNIFORM) on the lean event-driven
+    // kernel: ONE launch advances every env k steps (evl_step_kernel<..., KSTEP = true>); EV2B_STEP_K=loop keeps the
+    // launch-per-step path (A/B, tests).
+    const bool heavy_out = out && (out->dep_sat || out->dep_cap || out->port_energy || out->node_voltage);
+    const char *kv = getenv("EV2B_STEP_K");
+    if (!tensor_agent && k > 1 && evl_covers(h, out) && !h->evl_heavy_layout() && !heavy_out && !(kv && !strcmp(kv, "loop"))) {
+        if (action_dtype != EV2B_F32 && action_dtype != EV2B_F64) return h->fail(EV2B_E_ARG, "step_k: unknown action dtype %d", action_dtype);
+        int rc = ensure_list(h, (cudaStream_t)stream);
+        if (rc != EV2B_OK) return rc;
+        Params p = h->params();
+        p.agent_kind = ag.kind; p.agent_seed_lo = (unsigned)ag.seed; p.agent_seed_hi = (unsigned)(ag.seed >> 32);
+        p.action_low = ag.low;
+        p.actions = agent_kind == EV2B_AGENT_EXTERNAL ? actions_k : (const void *)h->hot.p;
+        if (out) p.out = *out;
+        p.obs_full = (obs != h->last_obs) ? 1 : 0;
+        p.mask_full = (p.out.action_mask && p.out.action_mask != h->last_mask) ? 1 : 0;
+        h->last_obs = obs; h->last_mask = p.out.action_mask;
+        p.k_steps = k; p.auto_reset = auto_reset ? 1 : 0;
+        const cudaError_t e = action_dtype == EV2B_F32 ? launch_evl<float>(h, p, (cudaStream_t)stream, true)
+                                                       : launch_evl<double>(h, p, (cudaStream_t)stream, true);
+        if (e != cudaSuccess) return h->fail(EV2B_E_CUDA, "step_k launch: %s", cudaGetErrorString(e));
+        h->launches += 1; h->launches_by[1] += 1;
+        return EV2B_OK;
+    }
     for (int i = 0; i < k; ++i) {
         const int obs_full = (obs != h->last_obs) ? 1 : 0;
         h->last_obs = obs;

@@ -139,6 +139,7 @@ struct Params {
     int v_trp, v_pfv, v_dsat, v_dcal, v_dcyc;   // HEAVY instantiation only (grid / statistics mode)
     int mask_full;             // 1: out.action_mask does not hold last step's rows (evl_step_kernel rewrites them)
     int scn_stride;            // auto-reset: next scenario = (current + scn_stride) mod S, gcd(scn_stride, S) = 1
+    int k_steps, auto_reset;   // evl_step_kernel<..., KSTEP = true>: steps per launch, device-side reset of finished envs
     // state
     uint4 *hot; double *cap; double *exch;   // exch: float64 like the reference's total_energy_exchanged (ev.py:178)
      int *env_step; int *env_scn; double *env_pot; double *env_usage;

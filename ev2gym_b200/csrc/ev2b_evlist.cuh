@@ -67,29 +67,32 @@ __device__ __forceinline__ double warp_sum8(const double (&q)[8], int lane) {
     return c;
 }
 
-// Barriers of a group.  Named barrier ids are literals: with the id in a register ptxas reserves all 16 barriers for
-// the CTA, which capped the SM at 3 resident CTAs (ncu: 21 % warps active).  G = 2: barrier 1 + g, 64 threads; G = 4:
-// barrier 1, the whole CTA.  `arrive` does not wait: the idle path uses it so that warps with nothing to do leave at
-// once while warp 0 still learns that they have read the env's step counter before it advances it.
+// Barriers of a group.  G = 2: named barrier 1 + g, 64 threads (the ids are literals: with the id in a register ptxas
+// reserves all 16 barriers for the CTA, which capped the SM at 3 resident CTAs -- ncu: 21 % warps active).  G = 4: the
+// group is the CTA: __syncthreads.  `arrive` does not wait: the idle path of G = 2 uses it so that the warp with nothing
+// to do leaves at once while warp 0 still learns that it has read the env's step counter before advancing it.  (With
+// G = 4 the other warps wait at the CTA barrier instead: `bar.arrive 1, 128` by three warps that then exit, paired with a
+// `bar.sync 1, 128` of warp 0, passed the emulator and HUNG on the B200 -- round 2, tests/test_gpu_evlist.py.)
 template <int G>
 __device__ __forceinline__ void evl_group_sync(int g) {
     static_assert(G == 1 || G == 2 || G * 32 == kEvlThreads, "group sizes: one warp, two warps, or the whole CTA");
     if (G == 1) { __syncwarp(); return; }
+    if (G * 32 == kEvlThreads) { __syncthreads(); return; }
 #ifdef EV2B_SIMT_EMU
     simt::bar_sync(1 + g, 32 * G);
 #else
-    if (G == 2) { if (g == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory"); }
-    else asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (g == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
 #endif
 }
+// The idle path's "I have read the step counter" of a warp other than warp 0.
 template <int G>
 __device__ __forceinline__ void evl_group_arrive(int g) {
     if (G == 1) return;
+    if (G * 32 == kEvlThreads) { __syncthreads(); return; }
 #ifdef EV2B_SIMT_EMU
     simt::bar_arrive(1 + g, 32 * G);
 #else
-    if (G == 2) { if (g == 0) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory"); }
-    else asm volatile("bar.arrive 1, 128;" ::: "memory");
+    if (g == 0) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory");
 #endif
 }
 
@@ -164,19 +167,16 @@ __device__ __forceinline__ void evl_obs_clear(const Params &p, float *obs_row, i
     if (p.state_kind == EV2B_STATE_PUBLIC_PST || p.state_kind == EV2B_STATE_V2G_GRID) o[2] = 0.f;
 }
 
-#ifndef EV2B_EVL_MINB
-#define EV2B_EVL_MINB 8       // resident CTAs per SM the lean instantiation is compiled for (8 -> 64 registers per thread)
-#endif
-template <typename ActT, int NP, bool UNI, int G, bool HEAVY>
-__global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_step_kernel(const __grid_constant__ Params p) {
-    EV2B_DYNAMIC_SMEM(smem_raw);
-    constexpr int GT = 32 * G, EPB = kEvlThreads / GT;
-    const int tid = threadIdx.x;
-    const int g = tid / GT, gtid = tid - g * GT, lane = tid & 31, gw = gtid >> 5;
-    const int e = p.env0 + (int)blockIdx.x * EPB + g;
-    if (e >= p.env_end) return;                       // whole group: its barriers are its own
-
-    unsigned char *sm = smem_raw + (size_t)g * p.v_stride;
+// One step of env e by its group (g = group in the CTA, sm = the group's shared memory).  KSTEP: called from the k-step
+// loop of evl_step_kernel (every warp of the group meets at a barrier after each call, so the idle path's arrive / wait
+// pair is not needed); `actions` = the action tensor of this step, `first_it` = first step of the launch (only then may
+// the caller's obs / mask buffers need a full rewrite).  Returns the env's step counter after the call (T + 1: the env
+// was already finished).
+template <typename ActT, int NP, bool UNI, int G, bool HEAVY, bool KSTEP>
+__device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, const int e, const int g, const int gtid,
+                                            const ActT *actions, const bool first_it) {
+    constexpr int GT = 32 * G;
+    const int lane = gtid & 31, gw = gtid >> 5;
     double *pw    = reinterpret_cast<double *>(sm);                  // [P] charger power contribution of the port's EV (kW)
     double *amp   = reinterpret_cast<double *>(sm + p.v_amp);        // [P] its actual current (A)
     double *pot   = reinterpret_cast<double *>(sm + p.v_pot);        // [P] its charge-power potential for step t+1
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_st
     double *dcal  = reinterpret_cast<double *>(sm + p.v_dcal);       //   calendar and
     double *dcyc  = reinterpret_cast<double *>(sm + p.v_dcyc);       //   cyclic degradation of the EVs finalised this step
 
-    const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
     const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
+    const bool obs_full = p.obs_full && first_it, mask_full = p.mask_full && first_it;
     // The EV loop starts with a chain of dependent global loads (list -> hot words -> spec): the list is a single buffer
     // rewritten in place (phase LS), so its address needs nothing but e and this thread's first entry is read together
     // with the per-env scalars (entries at or beyond occ_n are stale and never used).
@@ -213,14 +213,14 @@ __global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_st
             if (p.out.status) p.out.status[e] = EV2B_ST_DONE | EV2B_ST_WAS_DONE;
         }
         cp_async_wait_all();
-        return;
+        return p.T + 1;
     }
     const int tq = t + 1;
     const EnvT *etp = p.env_t + (size_t)s * p.T + t;
     const double2 price = *reinterpret_cast<const double2 *>(etp);           // cp, dp
     const int a0 = etp->arr0, nArr = etp->n_arr;                             // the sessions arriving at step t+1
     const bool idle = n_old == 0 && nArr == 0;        // nobody connected, nobody arriving: warp 0 alone, no barriers
-    if (idle && gw != 0) { evl_group_arrive<G>(g); return; }
+    if (idle && gw != 0) { if (!KSTEP) evl_group_arrive<G>(g); return tq; }
     if (gw == 0) {                                    // setpoints and the transformers' rows of this step (two 16 B halves each)
         if (lane == kEvlSet) cp_async8(pre + lane, &etp->setpoint);
         else if (lane == kEvlSetNext) { if (tq < p.T) cp_async8(pre + lane, &etp[1].setpoint); else pre[lane] = 0.0; }
@@ -252,9 +252,20 @@ __global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_st
         }
     }
     if (want_obs) {
+        // batches of 4 values per thread: the loads of a batch are in flight together (an idle env's warp would otherwise
+        // wait out seven dependent L2 round trips, one per value)
 #pragma unroll 1
-        for (int i = gtid; i < p.W; i += NT) obs_row[p.series_off[i]] = obs_series_fetch(p, s, tq, i);
-        if (p.obs_full) {                             // the caller's buffer does not hold last step's rows: clear every tuple
+        for (int i0 = gtid; i0 < p.W; i0 += 4 * NT) {
+            float v[4]; int o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * NT;
+                if (i < p.W) { o[j] = __ldg(&p.series_off[i]); v[j] = obs_series_fetch(p, s, tq, i); }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (i0 + j * NT < p.W) obs_row[o[j]] = v[j];
+        }
+        if (obs_full) {                               // the caller's buffer does not hold last step's rows: clear every tuple
 #pragma unroll 1
             for (int i = gtid; i < p.P; i += NT) evl_obs_clear(p, obs_row, i);
         }
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_st
     // action_mask is maintained incrementally like the observation tuples: the caller's buffer still holds last step's
     // row, only ports whose EV arrives or leaves change.  A new buffer (mask_full) or a new episode (t == 0: the row may
     // hold the previous episode's terminal mask) rewrites the row.                                  ev2gym_env.py:452-457
-    if (mask_row && (p.mask_full || t == 0)) {
+    if (mask_row && (mask_full || t == 0)) {
 #pragma unroll 1
         for (int i = gtid; i < p.P; i += NT) mask_row[i] = 0;
     }
@@ -504,7 +515,7 @@ __global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_st
         for (int k = lane; k < nArr; k += 32) nxt[base + k] = (uint16_t)(p.arr_list[a0 + k] & 0xFFFFu);
         if (lane == 0) p.occ_n[e] = base + nArr;
     }
-    if (gw != 0) return;
+    if (gw != 0) return tq;
     }  // !idle
 
     // ---- TR (warp 0): transformer sums + overload, same lane split as step_kernel's phase B ---------------------
@@ -612,7 +623,7 @@ __global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_st
     case EV2B_KPI_INVALID_ACTIONS: delta = (double)(p.P - n_old); break;   // every empty port  ev_charger.py:137-140
     default: delta = 1.0; break;                                           // EV2B_KPI_STEPS
     }
-    if (idle) evl_group_sync<G>(g);                   // the group's other warps have read env_step (they only arrive)
+    if (idle && !KSTEP) evl_group_sync<G>(g);         // the group's other warps have read env_step (they only arrive)
     if (lane < EV2B_KPI_COUNT) {
         p.env_kpi[(size_t)e * EV2B_KPI_COUNT + lane] = pre[lane] + delta;
     } else if (lane == 13) {
@@ -630,6 +641,77 @@ __global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_st
         if (p.reward_kind == EV2B_REWARD_SQ_TRACKING_PENALTY) p.env_pot_prev[e] = pot_now;
     } else if (lane == 17) {
         if (want_obs) obs_header(p, obs_row, s, tq, usage, setpoint_next);
+    }
+    return tq;
+}
+
+// Device-side reset of env e by its group (the per-env work of reset_ports_kernel + reset_envs_kernel, mode 1): next
+// scenario of the bank, every port empty, counters and KPI sums zero, first observation.      ev2gym_env.py:298-331
+template <int G>
+__device__ __forceinline__ void evl_reset_env(const Params &p, const int e, const int g, const int gtid) {
+    constexpr int GT = 32 * G;
+    const int s = (p.env_scn[e] + p.scn_stride) % p.S;
+    evl_group_sync<G>(g);                             // (every thread has read env_scn before thread 0 replaces it)
+#pragma unroll 1
+    for (int port = gtid; port < p.P; port += GT) {
+        const size_t ip = (size_t)e * p.P + port;
+        uint4 h;
+        h.x = ((unsigned)kNoArrival & 0xFFFFu) | (0xFFFFu << 16);        // t_arr = 32767, t_dep = -1
+        h.y = p.sess[((size_t)s * p.P + port) * p.Smax].hot.x & 0xFFFFu;  // next_arr = first session's t_arr, cursor 0
+        h.z = 0; h.w = 0;
+        p.hot[ip] = h; p.cap[ip] = 0.0; p.exch[ip] = 0.0;
+        if (p.rr_key) p.rr_key[ip] = kRrAbsent;
+    }
+    const bool want_obs = (p.out.obs != nullptr) && (p.state_kind != EV2B_STATE_NONE);
+    if (want_obs) {
+        float *row = p.out.obs + (size_t)e * p.D;
+#pragma unroll 1
+        for (int i = gtid; i < p.D; i += GT) row[i] = 0.f;               // no EV is connected at t = 0
+        evl_group_sync<G>(g);
+        if (gtid == 0) obs_header(p, row, s, 0, 0.0, p.env_t[(size_t)s * p.T].setpoint);
+#pragma unroll 1
+        for (int i = gtid; i < p.W; i += GT) row[p.series_off[i]] = obs_series_fetch(p, s, 0, i);
+    }
+    if (gtid == 0) {
+        p.env_step[e] = 0; p.env_scn[e] = s; p.env_pot[e] = 0.0; p.env_usage[e] = 0.0; p.env_pot_prev[e] = 0.0;
+        p.occ_n[e] = 0;
+        if (p.rr_fb) { p.rr_fb[2 * e] = 0; p.rr_fb[2 * e + 1] = 1; }
+        for (int k = 0; k < EV2B_KPI_COUNT; ++k) p.env_kpi[(size_t)e * EV2B_KPI_COUNT + k] = 0.0;
+    }
+}
+
+// The step kernel.  KSTEP = false: one step per launch (ev2b_step).  KSTEP = true (ev2b_step_k with an agent that needs no
+// other env's state): the group advances ITS env p.k_steps times in one launch -- envs are independent, so no grid-wide
+// synchronisation exists; from the second step on the env's rows are found in L1 / L2 instead of HBM and there is no
+// launch gap between steps.  Finished envs restart on their next scenario when p.auto_reset is set (= ev2b_reset_done).
+#ifndef EV2B_EVL_MINB
+#define EV2B_EVL_MINB 7       // resident CTAs per SM the lean instantiation is compiled for: 7 -> 72 registers per thread.
+                              // B200, c3 whole episodes, one warp per env: 8 (64 regs) 25.8 us, 7 (72) 23.3, 6 (80) 31.4 --
+                              // 4096 envs are 1024 CTAs = 6.9 per SM, so 7 slots still hold the launch in one wave
+#endif
+template <typename ActT, int NP, bool UNI, int G, bool HEAVY, bool KSTEP>
+__global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_step_kernel(const __grid_constant__ Params p) {
+    EV2B_DYNAMIC_SMEM(smem_raw);
+    constexpr int GT = 32 * G, EPB = kEvlThreads / GT;
+    const int tid = threadIdx.x;
+    const int g = tid / GT, gtid = tid - g * GT;
+    const int e = p.env0 + (int)blockIdx.x * EPB + g;
+    if (e >= p.env_end) return;                       // whole group: its barriers are its own
+    unsigned char *sm = smem_raw + (size_t)g * p.v_stride;
+    const ActT *actions = reinterpret_cast<const ActT *>(p.actions);
+    if (!KSTEP) {
+        evl_env_step<ActT, NP, UNI, G, HEAVY, false>(p, sm, e, g, gtid, actions, true);
+        return;
+    }
+    const size_t act_stride = p.agent_kind == EV2B_AGENT_EXTERNAL ? (size_t)p.E * p.P : 0;
+#pragma unroll 1
+    for (int it = 0; it < p.k_steps; ++it) {
+        const int tq = evl_env_step<ActT, NP, UNI, G, HEAVY, true>(p, sm, e, g, gtid, actions + act_stride * it, it == 0);
+        evl_group_sync<G>(g);                         // the step's writes are visible to the whole group before the next one
+        if (p.auto_reset && tq >= p.T) {              // (tq = T + 1: the env was finished before this launch and never reset)
+            evl_reset_env<G>(p, e, g, gtid);
+            evl_group_sync<G>(g);
+        }
     }
 }
 

@@ -353,7 +353,13 @@ class EV2GymB200Vec:
 
     def step(self, actions):
         """actions: cuda tensor [E,P] (fp32/fp64).  Returns (obs, reward, done, info) tensors; with auto_reset
-        the returned obs rows of finished envs are already the first observation of their next episode."""
+        the returned obs rows of finished envs are already the first observation of their next episode (and their
+        action-mask rows are all zero: no EV is connected at t = 0).
+
+        `obs` and `info["action_mask"]` are the engine's LIVE buffers: the next step() updates them in place (only the
+        entries that changed are rewritten, include/ev2b.h), so read them -- or .clone() them -- before stepping again,
+        and do not write into them (e.g. in-place observation normalisation): normalise a copy.  `reward` and `done`
+        are fresh tensors."""
         out = self.engine.step(actions)
         done = (out["status"] & 1).bool()
         reward = out["reward"].clone()
@@ -361,6 +367,7 @@ class EV2GymB200Vec:
         if self.auto_reset:
             info["terminal_obs_overwritten"] = True
             self.engine.reset_done()
+            out["action_mask"].masked_fill_(done.unsqueeze(1), 0)     # the terminal mask of the finished episode
         return out["obs"], reward, done, info
 
     def state_tensors(self):

@@ -19,7 +19,7 @@ from typing import Tuple
 
 import numpy as np
 
-from .scenario import LUT_LEN, SESSION_F64_FIELDS, SESSION_INT_FIELDS, Scenario, Topology
+from .scenario import LUT_LEN, SESSION_F64_FIELDS, SESSION_INT_FIELDS, Scenario, SpawnTables, Topology
 
 
 def topology_from_env(env) -> Topology:
@@ -184,3 +184,63 @@ def scenario_from_env(env) -> Scenario:
         luts_d=np.array(luts_d, dtype=np.float64).reshape(-1, LUT_LEN),
         meta={"sim_date": str(getattr(env, "sim_date", "")), "seed": getattr(env, "seed", None)},
     ).normalise()
+
+
+def spawn_tables_from_env(env, starts=None) -> SpawnTables:
+    """The tables and scalars EV_spawner / spawn_single_EV read from `env` (utils.py:477-557, 177-345), as arrays.
+    `starts`: optional list of sim_date values (one per scenario of the bank the tables go with)."""
+    cfg, scenario = env.config, env.scenario
+    half_hours = [f"{h:02d}:{m:02d}" for h in range(24) for m in (0, 30)]
+
+    def by_arrival(df):
+        col = df.set_index("Arrival Time")[scenario]
+        return np.array([float(col.get(k, 0.0)) for k in half_hours], dtype=np.float64)
+
+    luts, model_lut = [], []
+    if cfg["heterogeneous_ev_specs"]:
+        names = list(env.ev_specs.keys())
+        prob = np.asarray(env.normalized_ev_registrations, dtype=np.float64)
+        B = [env.ev_specs[n]["battery_capacity"] for n in names]
+        pac = [env.ev_specs[n]["max_ac_charge_power"] for n in names]
+        pdis = [-env.ev_specs[n]["max_ac_discharge_power"] for n in names]
+        pmin_ac, pmin_dis, phases = [0.0] * len(names), [0.0] * len(names), [3] * len(names)     # EV() defaults / ev_phases=3
+        for n in names:
+            spec = env.ev_specs[n]
+            if "3ph_ch_efficiency" in spec:                                    # utils.py:273-290
+                eff = dict(zip(spec["ch_current"], spec["3ph_ch_efficiency"]))
+                for i in range(0, 101):
+                    if i not in eff or eff[i] == 0:
+                        nz = [k for k, v in eff.items() if v != 0]
+                        if nz:
+                            eff[i] = eff[min(nz, key=lambda x: abs(x - i))]
+                row = [float(eff.get(i, 1.0)) for i in range(LUT_LEN)]
+                if row not in luts:
+                    luts.append(row)
+                model_lut.append(luts.index(row))
+            else:
+                model_lut.append(-1)
+    else:
+        ev = cfg["ev"]
+        prob, B, pac, pdis = np.ones(1), [ev["battery_capacity"]], [ev["max_ac_charge_power"]], [ev["max_discharge_power"]]
+        pmin_ac, pmin_dis, phases = [ev["min_ac_charge_power"]], [ev["min_discharge_power"]], [ev["ev_phases"]]
+        model_lut = [-1]
+    start = np.array([[d.weekday(), d.hour, d.minute] for d in (starts or [])], dtype=np.int32).reshape(-1, 3)
+    ev = cfg["ev"]
+    return SpawnTables(
+        workplace=int(scenario == "workplace"),
+        arrival_week=np.asarray(env.df_arrival_week[scenario].to_numpy()[:96], dtype=np.float64),
+        arrival_weekend=(np.asarray(env.df_arrival_weekend[scenario].to_numpy()[:96], dtype=np.float64)
+                         if scenario in env.df_arrival_weekend.columns else np.zeros(96)),     # (no weekend column for "workplace": closed)
+        req_energy_mean=by_arrival(env.df_req_energy), stay_mean=by_arrival(env.df_time_of_stay_vs_arrival),
+        spawn_multiplier=float(cfg["spawn_multiplier"]), min_stay_steps=int(ev["min_time_of_stay"] // env.timescale),
+        desired_frac=float(ev["desired_capacity"]), min_battery_capacity=float(ev["min_battery_capacity"]),
+        min_emergency_battery_capacity=float(ev["min_emergency_battery_capacity"]),
+        ts_multiplier=float(ev.get("transition_soc_multiplier", 1)),
+        empty_ports_at_end=int(bool(env.empty_ports_at_end_of_simulation)),
+        heterogeneous=int(bool(cfg["heterogeneous_ev_specs"])),
+        model_prob=prob, model_B=np.array(B, dtype=np.float64), model_pmax_ac=np.array(pac, dtype=np.float64),
+        model_pmax_dis=np.array(pdis, dtype=np.float64), model_pmin_ac=np.array(pmin_ac, dtype=np.float64),
+        model_pmin_dis=np.array(pmin_dis, dtype=np.float64), model_phases=np.array(phases, dtype=np.int32),
+        model_lut=np.array(model_lut, dtype=np.int32), luts=np.array(luts, dtype=np.float64).reshape(-1, LUT_LEN),
+        homog_ts=float(ev.get("transition_soc", 1)), homog_eta_c=float(ev.get("charge_efficiency", 1)),
+        homog_eta_d=float(ev.get("discharge_efficiency", 1)), start=start)

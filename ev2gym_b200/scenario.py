@@ -278,3 +278,55 @@ class ScenarioPack:
                 luts_c=z["luts_c"][l_off[i]:l_off[i + 1]], luts_d=z["luts_d"][l_off[i]:l_off[i + 1]],
             ).normalise())
         return cls(topo=topo, scenarios=out, config_name=str(z["config_name"]))
+
+
+@dataclass
+class SpawnTables:
+    """What `EV_spawner` / `spawn_single_EV` (ev2gym/utilities/utils.py:477-557, 177-345) read besides their random
+    draws: the arrival-rate, required-energy and time-of-stay tables of the config's scenario, the EV model table and a
+    handful of config scalars.  Exported once from a reference env (reference_export.spawn_tables_from_env, stored next
+    to the scenario banks by tools/make_golden.py --spawn-tables) so that the DEVICE sampler (ev2b_resample_sessions)
+    needs neither the reference nor its data files."""
+    workplace: int                  # 1: scenario == "workplace" (closed before 6 h / after 18 h and at weekends, :509-520)
+    arrival_week: np.ndarray        # [96] df_arrival_week[scenario], per quarter of an hour (:515)
+    arrival_weekend: np.ndarray     # [96] df_arrival_weekend[scenario] (:522)
+    req_energy_mean: np.ndarray     # [48] df_req_energy[scenario] by half hour of arrival (:203-205)
+    stay_mean: np.ndarray           # [48] df_time_of_stay_vs_arrival[scenario], hours (:231-234)
+    spawn_multiplier: float         # config["spawn_multiplier"]
+    min_stay_steps: int             # config["ev"]["min_time_of_stay"] // timescale (:495-496)
+    desired_frac: float             # config["ev"]["desired_capacity"]
+    min_battery_capacity: float
+    min_emergency_battery_capacity: float
+    ts_multiplier: float            # transition_soc_multiplier (1 when absent, :263-266)
+    empty_ports_at_end: int         # empty_ports_at_end_of_simulation (:254-256)
+    heterogeneous: int              # heterogeneous_ev_specs
+    model_prob: np.ndarray          # [M] normalized_ev_registrations            (M = 1, prob 1 when homogeneous)
+    model_B: np.ndarray             # [M] battery_capacity
+    model_pmax_ac: np.ndarray       # [M] max_ac_charge_power
+    model_pmax_dis: np.ndarray      # [M] max_discharge_power as the EV stores it (<= 0)
+    model_pmin_ac: np.ndarray       # [M]
+    model_pmin_dis: np.ndarray      # [M]
+    model_phases: np.ndarray        # [M] int32
+    model_lut: np.ndarray           # [M] int32 row of `luts` or -1 (scalar efficiencies drawn per EV, :290-296)
+    luts: np.ndarray                # [L,101] percent; the reference uses the same curve for both directions (:288)
+    homog_ts: float = 1.0           # homogeneous config: transition_soc, charge / discharge efficiency
+    homog_eta_c: float = 1.0
+    homog_eta_d: float = 1.0
+    start: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), dtype=np.int32))   # [n,3] weekday, hour, minute
+                                    # of sim_date at reset() for the scenarios of the bank this file goes with
+
+    _SCALARS = ("workplace", "spawn_multiplier", "min_stay_steps", "desired_frac", "min_battery_capacity",
+                "min_emergency_battery_capacity", "ts_multiplier", "empty_ports_at_end", "heterogeneous", "homog_ts",
+                "homog_eta_c", "homog_eta_d")
+    _ARRAYS = ("arrival_week", "arrival_weekend", "req_energy_mean", "stay_mean", "model_prob", "model_B", "model_pmax_ac",
+               "model_pmax_dis", "model_pmin_ac", "model_pmin_dis", "model_phases", "model_lut", "luts", "start")
+
+    def save(self, path: str) -> None:
+        np.savez_compressed(path, **{k: np.asarray(getattr(self, k)) for k in self._SCALARS + self._ARRAYS})
+
+    @classmethod
+    def load(cls, path: str) -> "SpawnTables":
+        z = np.load(path, allow_pickle=False)
+        kw = {k: z[k].item() for k in cls._SCALARS}
+        kw.update({k: z[k] for k in cls._ARRAYS})
+        return cls(**kw)

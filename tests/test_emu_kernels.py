@@ -435,3 +435,56 @@ def test_full_featured_kernels_match_reference_trace_on_emulator(emu, name, kern
         got = float(stats[n][E - 1])
         assert (np.isnan(ref) and np.isnan(got)) or got == pytest.approx(ref, rel=1e-9, abs=1e-9), (n, got, ref)
     eng.close()
+
+
+@pytest.mark.parametrize("G", [1, 2, 4])
+@pytest.mark.parametrize("agent", ["uniform", "external", "afap"])
+def test_kstep_kernel_equals_launch_per_step(emu, G, agent, monkeypatch):
+    """ev2b_step_k on the event-driven kernel: ONE launch that advances every env k steps (evl_step_kernel<KSTEP>, the
+    group loops over its env; device-side reset of finished envs) leaves exactly the state and outputs of k launches +
+    ev2b_reset_done (EV2B_STEP_K=loop), and the external-action variant equals the oracle stepped with the same tensor."""
+    from oracle.oracle import OracleBatch
+    topo, bank = _bank(30, 2, 3, T=24)
+    E = 7
+    rng = np.random.default_rng(5)
+    ks = (3, 1, 17, 9, 30)                                 # crosses two episode boundaries (T = 24)
+    acts = [np.ascontiguousarray(rng.uniform(-1, 1, (k, E, topo.P)).astype(np.float32)) for k in ks]
+    res = {}
+    for mode in ("loop", "kstep"):
+        monkeypatch.setenv("EV2B_KERNEL", "evlist")
+        monkeypatch.setenv("EV2B_EVL_G", str(G))
+        monkeypatch.setenv("EV2B_STEP_K", "loop" if mode == "loop" else "fused")
+        eng = emu.EmuEngine(topo, E, reward="ProfitMax_TrPenalty_UserIncentives", state="V2G_profit_max_loads",
+                            outputs=("reward", "status", "obs", "action_mask"))
+        eng.load_scenarios(bank)
+        eng.reset()
+        snaps, n0 = [], eng.kernel_launches()[1]
+        for k, a in zip(ks, acts):
+            out = eng.step_k(k, agent=agent, actions_k=a if agent == "external" else None, seed=77, auto_reset=True)
+            st = eng.state()
+            snaps.append([st[n].copy() for n in ("port_hot", "port_cap", "port_exch", "env_step", "env_scn", "env_kpi")] +
+                         [out[n].copy() for n in ("reward", "status", "obs", "action_mask")])
+        n_launch = eng.kernel_launches()[1] - n0
+        assert n_launch == (sum(ks) if mode == "loop" else sum(1 if k > 1 else 1 for k in ks)), (mode, n_launch)
+        res[mode] = snaps
+        eng.close()
+    for a, b in zip(res["loop"], res["kstep"]):
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert np.array_equal(x, y), i
+    if agent == "external":                                # no auto reset here: the oracle has none
+        monkeypatch.setenv("EV2B_STEP_K", "fused")
+        eng = emu.EmuEngine(topo, E, reward="ProfitMax_TrPenalty_UserIncentives", state="V2G_profit_max_loads")
+        eng.load_scenarios(bank)
+        eng.reset()
+        orc = OracleBatch(topo, [bank[e % len(bank)] for e in range(E)], reward="ProfitMax_TrPenalty_UserIncentives",
+                          state="V2G_profit_max_loads")
+        orc.reset()
+        a = np.ascontiguousarray(rng.uniform(-1, 1, (topo.T, E, topo.P)))
+        out = eng.step_k(topo.T, agent="external", actions_k=a)
+        for t in range(topo.T):
+            orc.step(a[t])
+        assert _close(out["reward"], orc.reward, 1e-9, 1e-9) and _close(out["obs"], orc.o["obs"][:, :eng.D], 1e-5, 1e-5)
+        assert (out["status"] & 1).all()
+        kpi = eng.state()["env_kpi"]
+        assert _close(kpi[:, 0], [s.total_reward for s in orc.states], 1e-9, 1e-9)
+        eng.close()

@@ -301,11 +301,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--replay-check", action="store_true", help="round-trip a reference replay pickle (no files written)")
     ap.add_argument("--packs", action="store_true", help="write the scenario banks used by bench.py")
+    ap.add_argument("--spawn-tables", action="store_true",
+                    help="write the EV-spawner tables of those banks (ev2gym_b200/data/spawn_*.npz) for the device sampler")
     ap.add_argument("--only", default=None)
     args = ap.parse_args()
     if args.replay_check:
         sys.exit(replay_check())
-    if args.packs:
+    if args.packs or args.spawn_tables:
         out_dir = os.path.join(REPO, "ev2gym_b200", "data")
         os.makedirs(out_dir, exist_ok=True)
         banks = [
@@ -318,12 +320,19 @@ def main():
             if args.only and args.only not in name:
                 continue
             env, _, _ = make_env(base, ov, 1000)
-            scns = []
+            scns, starts = [], []
             for i in range(n):      # seed = 1000 + i
                 env.reset(seed=1000 + i)
-                scns.append(scenario_from_env(env))
-            ScenarioPack(topology_from_env(env), scns, config_name=name).save(os.path.join(out_dir, name + ".npz"))
-            print("pack", name, n, "scenarios")
+                starts.append(env.sim_date)
+                if args.packs:
+                    scns.append(scenario_from_env(env))
+            if args.packs:
+                ScenarioPack(topology_from_env(env), scns, config_name=name).save(os.path.join(out_dir, name + ".npz"))
+                print("pack", name, n, "scenarios")
+            if args.spawn_tables:
+                from ev2gym_b200.reference_export import spawn_tables_from_env
+                spawn_tables_from_env(env, starts).save(os.path.join(out_dir, "spawn_" + name + ".npz"))
+                print("spawn tables", name, n, "start dates")
         return
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
