@@ -89,7 +89,7 @@ def occupancy_aware_bytes_per_env_step(topo, obs_dim, series_len, tuple_len, n_c
 def source_sha():
     """Hash of the CUDA sources the library is built from: stamps profiles (roofline_traffic.json) to a build."""
     h = hashlib.sha256()
-    for f in ("ev2b.cu", "ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_math.h"):
+    for f in ("ev2b.cu", "ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_spawn.cuh", "ev2b_math.h"):
         p = os.path.join(ROOT, "ev2gym_b200", "csrc", f)
         if os.path.exists(p):
             h.update(open(p, "rb").read())
@@ -475,6 +475,56 @@ def main():
                 e_.close()
         except Exception as exc:  # pragma: no cover
             extras["distinct_scenarios"] = {"error": repr(exc)}
+        try:   # fresh scenarios every episode: the EV sessions of all E scenarios are re-drawn ON THE DEVICE between episodes
+            from ev2gym_b200.scenario import SpawnTables
+            tab = SpawnTables.load(os.path.join(ROOT, "ev2gym_b200", "data", "spawn_" + pack_name + ".npz"))
+            S = len(pack.scenarios)
+            big = [pack.scenarios[i % S] for i in range(E)]
+            eng4 = []
+            for g in range(3):
+                e4 = BatchedEngine(topo, E, reward=reward, state=state, device=local, outputs=outputs)
+                e4.set_spawn_tables(tab)
+                e4.load_scenarios(big)
+                eng4.append(e4)
+            gen = torch.Generator(device=dev); gen.manual_seed(77)
+            act4 = [torch.rand((E, topo.P), device=dev, generator=gen) * (1.0 - low) + low for _ in range(3)]
+
+            def steps_only():
+                for e4 in eng4:
+                    e4.reset()
+                for r in range(T):
+                    for g, e4 in enumerate(eng4):
+                        e4.step(act4[(g + r) % 3])
+            for g, e4 in enumerate(eng4):
+                e4.resample_sessions(seed=g)
+            steps_only()
+            torch.cuda.synchronize(dev)
+            g4 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g4):
+                steps_only()
+            ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            n4, t_res, t_all = 8, 0.0, 0.0
+            torch.cuda.synchronize(dev)
+            for it in range(n4):
+                ev0.record()
+                for g, e4 in enumerate(eng4):
+                    e4.resample_sessions(seed=1000 + 3 * it + g)
+                ev1.record()
+                g4.replay()
+                ev2.record()
+                torch.cuda.synchronize(dev)
+                t_res += ev0.elapsed_time(ev1); t_all += ev0.elapsed_time(ev2)
+            n_sess = float(sum(len(eng4[0].read_sessions(i)["port"]) for i in range(0, E, 64))) / (E // 64)
+            extras["fresh_scenarios"] = {
+                "env_steps_per_s": 3 * E * T * n4 / (t_all * 1e-3), "scenarios_per_s": 3 * E * n4 / (t_res * 1e-3),
+                "resample_ms_per_bank": t_res / (3 * n4), "bank": E, "sessions_per_scenario": n_sess,
+                "what": f"every episode of every env plays a scenario whose EV sessions were just drawn on the device "
+                        f"(ev2b_resample_sessions = EV_spawner + spawn_single_EV, one scenario per env, time series of the "
+                        f"{S}-scenario bank); timed: resample + reset + {T} steps, 3 env groups, {n4} episodes each"}
+            for e_ in eng4:
+                e_.close()
+        except Exception as exc:  # pragma: no cover
+            extras["fresh_scenarios"] = {"error": repr(exc)}
         try:   # north_star shape: 1k envs x 100 chargers
             E1 = 1024
             engines3, actions3, _, _ = build_groups(E1, pack.scenarios)

@@ -13,11 +13,11 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("EV2B_LIB") or os.path.join(CSRC, "libev2b.so")   # EV2B_LIB: A/B-test another build
-SOURCES = [os.path.join(CSRC, f) for f in ("ev2b.cu", "ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_math.h")] + \
+SOURCES = [os.path.join(CSRC, f) for f in ("ev2b.cu", "ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_spawn.cuh", "ev2b_math.h")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "ev2b.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off"]
+              "-split-compile", "0", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off"]
 
 _pd, _pi, _pf = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float)
 _pl, _pu, _pb = C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
@@ -72,7 +72,51 @@ ABI_VERSION = 2          # EV2B_ABI_VERSION of include/ev2b.h this binding was w
 EXPORTS = ("ev2b_abi_version", "ev2b_last_error", "ev2b_create", "ev2b_destroy", "ev2b_obs_dim", "ev2b_n_ports",
            "ev2b_load_scenarios", "ev2b_n_scenarios", "ev2b_reset", "ev2b_step", "ev2b_step_host",
            "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count", "ev2b_episode_stats", "ev2b_step_k",
-           "ev2b_agent_actions", "ev2b_kernel_launches")
+           "ev2b_agent_actions", "ev2b_kernel_launches", "ev2b_set_spawn_tables", "ev2b_resample_sessions",
+           "ev2b_read_sessions")
+
+
+class SpawnTablesView(C.Structure):
+    _fields_ = [("workplace", C.c_int32), ("heterogeneous", C.c_int32), ("empty_ports_at_end", C.c_int32),
+                ("min_stay_steps", C.c_int32), ("n_models", C.c_int32), ("n_luts", C.c_int32),
+                ("spawn_multiplier", C.c_double), ("desired_frac", C.c_double), ("min_battery_capacity", C.c_double),
+                ("min_emergency_battery_capacity", C.c_double), ("ts_multiplier", C.c_double),
+                ("homog_ts", C.c_double), ("homog_eta_c", C.c_double), ("homog_eta_d", C.c_double),
+                ("arrival_week", _pd), ("arrival_weekend", _pd), ("req_energy_mean", _pd), ("stay_mean", _pd),
+                ("model_prob", _pd), ("model_B", _pd), ("model_pmax_ac", _pd), ("model_pmax_dis", _pd),
+                ("model_pmin_ac", _pd), ("model_pmin_dis", _pd), ("model_phases", _pi), ("model_lut", _pi), ("luts", _pd)]
+
+
+def spawn_tables_view(t):
+    """`ev2b_spawn_tables` over a scenario.SpawnTables; returns (view, arrays to keep alive)."""
+    import numpy as np
+    v, keep = SpawnTablesView(), []
+    for k in ("workplace", "heterogeneous", "empty_ports_at_end", "min_stay_steps"):
+        setattr(v, k, int(getattr(t, k)))
+    for k in ("spawn_multiplier", "desired_frac", "min_battery_capacity", "min_emergency_battery_capacity",
+              "ts_multiplier", "homog_ts", "homog_eta_c", "homog_eta_d"):
+        setattr(v, k, float(getattr(t, k)))
+    v.n_models, v.n_luts = int(len(t.model_prob)), int(np.asarray(t.luts).reshape(-1, 101).shape[0])
+    for k, ptr, dt in [("arrival_week", _pd, np.float64), ("arrival_weekend", _pd, np.float64),
+                       ("req_energy_mean", _pd, np.float64), ("stay_mean", _pd, np.float64), ("model_prob", _pd, np.float64),
+                       ("model_B", _pd, np.float64), ("model_pmax_ac", _pd, np.float64), ("model_pmax_dis", _pd, np.float64),
+                       ("model_pmin_ac", _pd, np.float64), ("model_pmin_dis", _pd, np.float64),
+                       ("model_phases", _pi, np.int32), ("model_lut", _pi, np.int32), ("luts", _pd, np.float64)]:
+        a = np.ascontiguousarray(np.asarray(getattr(t, k)).reshape(-1), dtype=dt)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dt)
+        keep.append(a)
+        setattr(v, k, a.ctypes.data_as(ptr))
+    return v, keep
+
+
+def declare_spawn(L):
+    L.ev2b_set_spawn_tables.restype = C.c_int
+    L.ev2b_set_spawn_tables.argtypes = [C.c_void_p, C.POINTER(SpawnTablesView)]
+    L.ev2b_resample_sessions.restype = C.c_int
+    L.ev2b_resample_sessions.argtypes = [C.c_void_p, C.c_uint64, _pi, C.c_void_p]
+    L.ev2b_read_sessions.restype = C.c_int
+    L.ev2b_read_sessions.argtypes = [C.c_void_p, C.c_int, C.c_int, _pi, _pi, _pi, _pi, _pd, _pd, _pd, _pd]
 
 
 def needs_build() -> bool:
@@ -146,6 +190,7 @@ def load():
     L.ev2b_launch_count.argtypes = [C.c_void_p]
     L.ev2b_kernel_launches.restype = C.c_int64
     L.ev2b_kernel_launches.argtypes = [C.c_void_p, C.c_int]
+    declare_spawn(L)
     if L.ev2b_abi_version() != ABI_VERSION:
         raise RuntimeError("libev2b.so ABI version mismatch")
     _lib = L

@@ -4,6 +4,7 @@
 // (-fmad=false: the battery update must round like the reference's float64 Python arithmetic.)
 #include "ev2b_device.cuh"
 #include "ev2b_evlist.cuh"
+#include "ev2b_spawn.cuh"
 
 #include <algorithm>
 #include <array>
@@ -98,6 +99,13 @@ struct ev2b_handle {
     size_t evl_smem = 0;
     std::set<const void *> smem_opted;  // kernels whose dynamic shared-memory limit has been raised on this device
     DevBuf<uint16_t> occ_list; DevBuf<int> occ_n; DevBuf<unsigned> arr_list;
+    // device-side scenario sampling (ev2b_spawn.cuh): tables, scratch, the EV-model spec table that replaces the bank's
+    bool spawn_ready = false, spawn_specs_live = false;
+    int spawn_smax = 0, spawn_M = 0;
+    SpawnParams spawn_p{};
+    DevBuf<double> sp_arr_week, sp_arr_weekend, sp_req, sp_stay, sp_cdf, sp_B, sp_luts, sp_pot_kw;
+    DevBuf<int> sp_lut, sp_start, sp_raw_n, sp_n_sess;
+    DevBuf<SessRec> sp_raw; DevBuf<EvSpec> sp_spec;
     bool evl_heavy_layout() const { return (dims.flags & EV2B_F_STATS) != 0 || n_bus > 0; }
     void layout_evl() {
         size_t off = 0;
@@ -622,6 +630,7 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
             Smax = std::max(Smax, ++per_port[port]);
         }
     }
+    if (h->spawn_ready) Smax = std::max(Smax, h->spawn_smax);       // room for whatever the device sampler can draw
     if (Smax > 255) return h->fail(EV2B_E_LIMIT, "more than 255 sessions on one port");
     int Lmax = 2;
     SessRec empty{};
@@ -775,11 +784,14 @@ int ev2b_load_scenarios(ev2b_handle *h, const ev2b_scenarios *b) {
     CUDA_TRY(h, h->tr_limit.upload(tr_limit)); CUDA_TRY(h, h->dr.upload(dr)); CUDA_TRY(h, h->dr_count.upload(dr_count));
     if (h->evl) {
         if (arr_list_h.empty()) arr_list_h.push_back(0u);
+        if (h->spawn_ready) arr_list_h.resize(std::max(arr_list_h.size(), (size_t)S * P * Smax), 0u);   // a region per scenario
         CUDA_TRY(h, h->arr_list.upload(arr_list_h));
         h->list_valid = true;            // every env reads as done until it is reset, and reset empties its list
     }
     h->S = S; h->Smax = Smax; h->n_dr = n_dr; h->lut_len = lut_len;
     h->last_obs = nullptr;
+    h->spawn_specs_live = false;
+    if (h->spawn_ready && (h->dims.flags & EV2B_F_STATS)) Lmax = T + 2;   // sampled sessions can be as long as the episode
     if (h->dims.flags & EV2B_F_STATS) {
         h->L = std::max(2, std::min(Lmax, T + 2));
         const size_t EP = (size_t)h->E * P, EC = (size_t)h->E * C;
@@ -1054,6 +1066,154 @@ int ev2b_debug_list(ev2b_handle *h, int e, uint16_t *out) {
     return n;
 }
 #endif
+
+int ev2b_set_spawn_tables(ev2b_handle *h, const ev2b_spawn_tables *t) {
+    if (!h || !t) return h ? h->fail(EV2B_E_ARG, "set_spawn_tables: null tables") : EV2B_E_ARG;
+    if (h->S != 0) return h->fail(EV2B_E_STATE, "set_spawn_tables: call before ev2b_load_scenarios");
+    if (!h->evl) return h->fail(EV2B_E_STATE, "set_spawn_tables: the device sampler needs the event-driven kernel (EV2B_KERNEL=evlist)");
+    if (t->n_models < 1 || t->n_models > 65535 || t->min_stay_steps < 0) return h->fail(EV2B_E_ARG, "set_spawn_tables: bad sizes");
+    if (((size_t)(h->T + 2) * ((h->P + 31) / 32) + h->T + 3) * 4 > 200 * 1024)
+        return h->fail(EV2B_E_LIMIT, "set_spawn_tables: too many ports for the arrival-schedule kernel");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int M = t->n_models, LL = 101;
+    auto up = [&](DevBuf<double> &b, const double *src, size_t n) { return b.upload(std::vector<double>(src, src + n)); };
+    CUDA_TRY(h, up(h->sp_arr_week, t->arrival_week, 96)); CUDA_TRY(h, up(h->sp_arr_weekend, t->arrival_weekend, 96));
+    CUDA_TRY(h, up(h->sp_req, t->req_energy_mean, 48)); CUDA_TRY(h, up(h->sp_stay, t->stay_mean, 48));
+    std::vector<double> cdf(M); double acc = 0, tot = 0;
+    for (int i = 0; i < M; ++i) tot += t->model_prob[i];
+    for (int i = 0; i < M; ++i) { acc += t->model_prob[i] / tot; cdf[i] = acc; }
+    CUDA_TRY(h, h->sp_cdf.upload(cdf)); CUDA_TRY(h, up(h->sp_B, t->model_B, M));
+    CUDA_TRY(h, h->sp_lut.upload(std::vector<int>(t->model_lut, t->model_lut + M)));
+    std::vector<double> luts(t->n_luts > 0 ? (size_t)t->n_luts * LL : (size_t)LL, 1.0);
+    if (t->n_luts > 0) std::copy(t->luts, t->luts + (size_t)t->n_luts * LL, luts.begin());
+    CUDA_TRY(h, h->sp_luts.upload(luts));
+    // the EV-model spec table (what ev2b_load_scenarios de-duplicates from a bank's sessions)   ev.py:45-113, utils.py:298-345
+    std::vector<EvSpec> specs(M);
+    for (int i = 0; i < M; ++i) {
+        EvSpec sp{};
+        sp.B = t->model_B[i]; sp.pmax_ac = t->model_pmax_ac[i]; sp.pmin_ac = t->model_pmin_ac[i];
+        sp.pmax_dis = t->model_pmax_dis[i]; sp.pmin_dis = t->model_pmin_dis[i];
+        sp.bmin = t->min_battery_capacity;
+        sp.bmin_em = t->min_emergency_battery_capacity > sp.B ? 0.7 * sp.B : t->min_emergency_battery_capacity;   // utils.py:268-271
+        sp.desired = t->desired_frac * sp.B; sp.mult = t->ts_multiplier;
+        sp.ts = t->homog_ts; sp.eta_c = t->homog_eta_c; sp.eta_d = t->homog_eta_d;
+        sp.ev_phases = t->model_phases[i]; sp.lut = t->model_lut[i];
+        if (sp.ev_phases < 1 || sp.ev_phases > 3 || sp.lut >= t->n_luts) return h->fail(EV2B_E_ARG, "set_spawn_tables: bad model %d", i);
+        sp.rB = 1.0 / sp.B;
+        specs[i] = sp;
+    }
+    CUDA_TRY(h, h->sp_spec.upload(specs));
+    std::vector<double> pot_kw((size_t)M * h->n_cls);
+    {
+        std::vector<int> cls_ph(h->n_cls, 3);
+        for (const CsStatic &c : h->cs_h) cls_ph[c.cls] = c.phases;
+        for (int q = 0; q < M; ++q)
+            for (int k = 0; k < h->n_cls; ++k) {                           // utils.py:772-777
+                const int ph = std::min(cls_ph[k], specs[q].ev_phases);
+                const double sv = h->cls_veff[k][ph];
+                pot_kw[(size_t)q * h->n_cls + k] = sv * std::min(h->cls_imax[k], specs[q].pmax_ac * 1000.0 / sv) / 1000.0;
+            }
+    }
+    CUDA_TRY(h, h->sp_pot_kw.upload(pot_kw));
+    SpawnParams &sp = h->spawn_p;
+    sp = SpawnParams{};
+    sp.arrival_week = h->sp_arr_week.p; sp.arrival_weekend = h->sp_arr_weekend.p; sp.req_energy_mean = h->sp_req.p;
+    sp.stay_mean = h->sp_stay.p; sp.model_cdf = h->sp_cdf.p; sp.model_B = h->sp_B.p; sp.model_lut = h->sp_lut.p;
+    sp.M = M; sp.workplace = t->workplace; sp.heterogeneous = t->heterogeneous; sp.empty_ports_at_end = t->empty_ports_at_end;
+    sp.min_stay_steps = t->min_stay_steps; sp.timescale = h->dims.timescale;
+    sp.spawn_multiplier = t->spawn_multiplier; sp.desired_frac = t->desired_frac; sp.min_battery_capacity = t->min_battery_capacity;
+    unsigned k = 0xFFFFu;
+    sp.homog_ts_milli = milli(t->homog_ts, &k) ? k : 0xFFFFu;
+    sp.homog_eta_c_milli = milli(t->homog_eta_c, &k) ? k : 0xFFFFu;
+    sp.homog_eta_d_milli = milli(t->homog_eta_d, &k) ? k : 0xFFFFu;
+    // a session holds its port for at least min_stay + 2 steps and the port then rests for 2 more   utils.py:534-536, 551-552
+    h->spawn_smax = std::min(255, h->T / std::max(1, t->min_stay_steps + 4) + 2);
+    h->spawn_M = M;
+    h->spawn_ready = true;
+    return EV2B_OK;
+}
+
+int ev2b_resample_sessions(ev2b_handle *h, uint64_t seed, const int32_t *start, void *stream) {
+    if (!h || !start) return h ? h->fail(EV2B_E_ARG, "resample_sessions: null start dates") : EV2B_E_ARG;
+    if (!h->spawn_ready) return h->fail(EV2B_E_STATE, "resample_sessions: ev2b_set_spawn_tables was not called");
+    if (h->S == 0) return h->fail(EV2B_E_STATE, "resample_sessions: no scenario bank loaded");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t SP = (size_t)h->S * h->P;
+    for (int i = 0; i < h->S; ++i)
+        if (start[3 * i] < 0 || start[3 * i] > 6 || start[3 * i + 1] < 0 || start[3 * i + 1] > 23 || start[3 * i + 2] < 0 || start[3 * i + 2] > 59)
+            return h->fail(EV2B_E_ARG, "resample_sessions: bad start date of scenario %d", i);
+    if (h->sp_raw.n < SP * h->Smax) { CUDA_TRY(h, h->sp_raw.alloc(SP * h->Smax)); CUDA_TRY(h, h->sp_raw_n.alloc(SP)); CUDA_TRY(h, h->sp_n_sess.alloc(h->S)); }
+    if (h->sp_start.n < (size_t)3 * h->S) CUDA_TRY(h, h->sp_start.alloc((size_t)3 * h->S));
+    CUDA_TRY(h, cudaMemcpyAsync(h->sp_start.p, start, sizeof(int) * 3 * h->S, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));            // `start` is a caller-owned (possibly pageable) host buffer
+    CUDA_TRY(h, cudaMemsetAsync(h->sp_n_sess.p, 0, sizeof(int) * h->S, st));
+    if (!h->spawn_specs_live) {                        // from now on the bank's sessions name EV models, not the bank's own specs
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        CUDA_TRY(h, h->spec.alloc(h->sp_spec.n));
+        CUDA_TRY(h, cudaMemcpy(h->spec.p, h->sp_spec.p, h->sp_spec.n * sizeof(EvSpec), cudaMemcpyDeviceToDevice));
+        CUDA_TRY(h, h->pot_kw.alloc(h->sp_pot_kw.n));
+        CUDA_TRY(h, cudaMemcpy(h->pot_kw.p, h->sp_pot_kw.p, h->sp_pot_kw.n * sizeof(double), cudaMemcpyDeviceToDevice));
+        CUDA_TRY(h, h->luts_c.alloc(h->sp_luts.n)); CUDA_TRY(h, h->luts_d.alloc(h->sp_luts.n));
+        CUDA_TRY(h, cudaMemcpy(h->luts_c.p, h->sp_luts.p, h->sp_luts.n * sizeof(double), cudaMemcpyDeviceToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->luts_d.p, h->sp_luts.p, h->sp_luts.n * sizeof(double), cudaMemcpyDeviceToDevice));
+        h->lut_len = 101;
+        h->spawn_specs_live = true;
+    }
+    SpawnParams sp = h->spawn_p;
+    sp.start = h->sp_start.p; sp.seed_lo = (unsigned)seed; sp.seed_hi = (unsigned)(seed >> 32);
+    sp.cap_per_scn = h->P * h->Smax;
+    sp.raw = h->sp_raw.p; sp.raw_n = h->sp_raw_n.p; sp.sess = h->sess.p; sp.env_t = h->env_t.p; sp.arr_list = h->arr_list.p;
+    sp.n_sess = h->sp_n_sess.p;
+    const Params p = h->params();
+    const int blk = 128;
+    EV2B_LAUNCH(spawn_sessions_kernel, (unsigned)((SP + blk - 1) / blk), blk, 0, st, p, sp);
+    EV2B_LAUNCH(spawn_assign_kernel, (unsigned)(((size_t)h->S * h->C + blk - 1) / blk), blk, 0, st, p, sp);
+    const size_t sm = ((size_t)(h->T + 2) * ((h->P + 31) / 32) + h->T + 3) * 4;
+    CUDA_TRY(h, opt_in_smem(h, spawn_schedule_kernel, sm));
+    EV2B_LAUNCH(spawn_schedule_kernel, (unsigned)h->S, blk, sm, st, p, sp);
+    EV2B_LAUNCH(spawn_invalidate_envs_kernel, (unsigned)((h->E + blk - 1) / blk), blk, 0, st, p);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 4;
+    h->last_obs = nullptr; h->last_mask = nullptr;
+    return EV2B_OK;
+}
+
+int ev2b_read_sessions(ev2b_handle *h, int scn, int cap, int32_t *port, int32_t *t_arr, int32_t *t_dep, int32_t *model,
+                       double *cap0, double *ts, double *eta_c, double *eta_d) {
+    if (!h) return EV2B_E_ARG;
+    if (h->S == 0 || scn < 0 || scn >= h->S) return h->fail(EV2B_E_ARG, "read_sessions: scenario %d out of range", scn);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    std::vector<SessRec> rec((size_t)h->P * h->Smax);
+    CUDA_TRY(h, cudaMemcpy(rec.data(), h->sess.p + (size_t)scn * h->P * h->Smax, rec.size() * sizeof(SessRec), cudaMemcpyDeviceToHost));
+    struct Row { int ta, port, k; };
+    std::vector<Row> rows;
+    for (int pp = 0; pp < h->P; ++pp)
+        for (int k = 0; k < h->Smax; ++k) {
+            const int ta = (int)(rec[(size_t)pp * h->Smax + k].hot.x & 0xFFFFu);
+            if (ta == kNoArrival) break;
+            rows.push_back({ta, pp, k});
+        }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.ta != b.ta ? a.ta < b.ta : a.port < b.port; });
+    const double nan = std::nan("");
+    int n = 0;
+    for (const Row &r : rows) {
+        if (n >= cap) break;
+        const SessRec &x = rec[(size_t)r.port * h->Smax + r.k];
+        if (port) port[n] = r.port;
+        if (t_arr) t_arr[n] = r.ta;
+        if (t_dep) t_dep[n] = (int)(int16_t)(x.hot.x >> 16);
+        if (model) model[n] = (int)(x.hot.z & 0xFFFFu);
+        if (cap0) cap0[n] = x.cap0;
+        const unsigned tsm = x.hot.z >> 16, ecm = x.hot.w & 0xFFFFu, edm = x.hot.w >> 16;
+        if (ts) ts[n] = tsm == 0xFFFFu ? nan : tsm / 1000.0;
+        if (eta_c) eta_c[n] = (ecm == 0xFFFFu || ecm == 0) ? nan : ecm / 1000.0;
+        if (eta_d) eta_d[n] = (edm == 0xFFFFu || edm == 0) ? nan : edm / 1000.0;
+        ++n;
+    }
+    return (int)rows.size();
+}
 
 int ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *v) {
     if (!h || !v) return EV2B_E_ARG;

@@ -131,7 +131,42 @@ class _CudaView:
         self._owner = owner
 
 
-class BatchedEngine:
+class SpawnMixin:
+    """Device-side scenario sampling (ev2b_set_spawn_tables / ev2b_resample_sessions / ev2b_read_sessions): shared by
+    BatchedEngine and the emulator-backed test engine (same C ABI)."""
+
+    def set_spawn_tables(self, tables):
+        """Register the EV-spawner tables (scenario.SpawnTables).  Call before load_scenarios."""
+        v, keep = _lib.spawn_tables_view(tables)
+        self._check(self.L.ev2b_set_spawn_tables(self.h, C.byref(v)), "ev2b_set_spawn_tables")
+        self._spawn_start = np.ascontiguousarray(tables.start, dtype=np.int32).reshape(-1, 3)
+
+    def resample_sessions(self, seed: int, start=None):
+        """Re-draw the EV sessions of every scenario of the bank on the device (EV_spawner, utils.py:477-557).
+        start: [n_scenarios, 3] weekday / hour / minute of each scenario's sim_date (default: the tables' own, tiled)."""
+        n = self.L.ev2b_n_scenarios(self.h)
+        st = self._spawn_start if start is None else np.asarray(start, dtype=np.int32).reshape(-1, 3)
+        if len(st) == 0:
+            raise EngineError("resample_sessions needs start dates (SpawnTables.start is empty)")
+        st = np.ascontiguousarray(st[np.arange(n) % len(st)], dtype=np.int32)
+        self._check(self.L.ev2b_resample_sessions(self.h, int(seed) & (2 ** 64 - 1), st.ctypes.data_as(_lib._pi),
+                                                  self._stream()), "ev2b_resample_sessions")
+
+    def read_sessions(self, scn: int) -> Dict[str, np.ndarray]:
+        """The sessions of scenario `scn` as the device bank holds them, in arrival order."""
+        cap = self.P * 64
+        i = {k: np.zeros(cap, dtype=np.int32) for k in ("port", "t_arr", "t_dep", "model")}
+        d = {k: np.zeros(cap, dtype=np.float64) for k in ("cap0", "ts", "eta_c", "eta_d")}
+        n = self.L.ev2b_read_sessions(self.h, int(scn), cap, *[i[k].ctypes.data_as(_lib._pi) for k in ("port", "t_arr", "t_dep", "model")],
+                                      *[d[k].ctypes.data_as(_lib._pd) for k in ("cap0", "ts", "eta_c", "eta_d")])
+        if n < 0:
+            self._check(n, "ev2b_read_sessions")
+        out = {k: v[:n].copy() for k, v in i.items()}
+        out.update({k: v[:n].copy() for k, v in d.items()})
+        return out
+
+
+class BatchedEngine(SpawnMixin):
     def __init__(self, topo: Topology, n_envs: int, reward=None, state=None, device: int = 0,
                  outputs: Iterable[str] = ("reward", "status", "obs"), stats: bool = False):
         import torch  # plumbing only

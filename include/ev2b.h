@@ -244,6 +244,41 @@ int  ev2b_reset_done(ev2b_handle *h, float *obs0, void *stream);
 
 int  ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *out);
 
+/* ---- device-side scenario sampling (the EV part of reset(): EV_spawner + spawn_single_EV, utils.py:477-557, 177-345) ----
+ * What the reference's spawner reads besides its random draws, HOST pointers (exported once from a reference env by
+ * ev2gym_b200/reference_export.spawn_tables_from_env; shipped next to the scenario banks as ev2gym_b200/data/spawn_*.npz). */
+typedef struct {
+    int32_t workplace;                 /* scenario == "workplace": closed before 6 h, after 18 h, at weekends  :509-520 */
+    int32_t heterogeneous;             /* heterogeneous_ev_specs                                                      */
+    int32_t empty_ports_at_end;        /* empty_ports_at_end_of_simulation                                 :254-256   */
+    int32_t min_stay_steps;            /* config["ev"]["min_time_of_stay"] // timescale                    :495-496   */
+    int32_t n_models, n_luts;          /* EV models; efficiency curves (lut_len entries each, percent)                */
+    double  spawn_multiplier, desired_frac, min_battery_capacity, min_emergency_battery_capacity, ts_multiplier;
+    double  homog_ts, homog_eta_c, homog_eta_d;   /* homogeneous config: transition_soc, efficiencies                 */
+    const double *arrival_week, *arrival_weekend;  /* [96] percent per quarter of an hour                  :515, 522  */
+    const double *req_energy_mean, *stay_mean;     /* [48] by half hour of arrival (kWh, hours)            :203, 231  */
+    const double *model_prob, *model_B, *model_pmax_ac, *model_pmax_dis, *model_pmin_ac, *model_pmin_dis;   /* [n_models] */
+    const int32_t *model_phases, *model_lut;       /* [n_models]; model_lut: row of luts or -1                        */
+    const double *luts;                            /* [n_luts * 101] the reference uses one curve for both directions  */
+} ev2b_spawn_tables;
+
+/* Registers the tables.  Call BEFORE ev2b_load_scenarios (the session table is sized for what the sampler can draw). */
+int  ev2b_set_spawn_tables(ev2b_handle *h, const ev2b_spawn_tables *tables);
+
+/* Re-draws the EV sessions of EVERY scenario of the loaded bank on the device (counter-based RNG keyed by `seed`,
+ * scenario, port and step: the same seed gives the same sessions on any GPU), keeping each scenario's time series.
+ * start: HOST [n_scenarios][3] weekday (0 = Monday), hour, minute of sim_date at reset() for every scenario.
+ * Afterwards every env reads as finished until it is reset.  Stream-ordered; three small kernels.
+ * power_setpoints are not regenerated (see ev2gym_b200/csrc/ev2b_spawn.cuh). */
+int  ev2b_resample_sessions(ev2b_handle *h, uint64_t seed, const int32_t *start, void *stream);
+
+/* The sessions of scenario `scn` as the bank currently holds them (arrival order), HOST arrays of capacity `cap`:
+ * returns the number of sessions (or < 0).  port = flat port index the EV will occupy; model = index into the spawn
+ * tables' models after ev2b_resample_sessions (the bank's own de-duplicated spec index otherwise); ts / eta_c / eta_d are
+ * NaN where the value comes from an efficiency curve or from the spec.  Synchronous. */
+int  ev2b_read_sessions(ev2b_handle *h, int scn, int cap, int32_t *port, int32_t *t_arr, int32_t *t_dep, int32_t *model,
+                        double *cap0, double *ts, double *eta_c, double *eta_d);
+
 /* get_statistics(env) for every env (ev2gym/utilities/utils.py:12-123, incl. EV.get_battery_degradation
  * ev.py:442-521 and the AFAP bound ev.py:407-440).  Needs EV2B_F_STATS.  out: DEVICE [E, EV2B_STAT_COUNT]
  * float64, columns in enum ev2b_stat order.  Meaningful once an env is done (or at any time for the

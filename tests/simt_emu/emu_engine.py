@@ -58,6 +58,8 @@ def lib():
         L.ev2b_launch_count.argtypes = [C.c_void_p]
         L.ev2b_kernel_launches.restype = C.c_int64
         L.ev2b_kernel_launches.argtypes = [C.c_void_p, C.c_int]
+        L.ev2b_n_scenarios.argtypes = [C.c_void_p]
+        _lib.declare_spawn(L)
         _L = L
     return _L
 
@@ -69,7 +71,12 @@ _OUT = {"reward": (np.float64, ()), "status": (np.uint32, ()), "obs": (np.float3
         "node_voltage": (np.float64, ("N",))}
 
 
-class EmuEngine:
+def _spawn_mixin():
+    from ev2gym_b200.engine import SpawnMixin
+    return SpawnMixin
+
+
+class EmuEngine(_spawn_mixin()):
     """Same call sequence as ev2gym_b200.engine.BatchedEngine, numpy arrays instead of cuda tensors."""
 
     def __init__(self, topo, n_envs: int, reward=None, state=None, outputs: Iterable[str] = ("reward", "status", "obs"),
@@ -94,6 +101,9 @@ class EmuEngine:
     def _check(self, rc, what):
         if rc != 0:
             raise RuntimeError(f"{what} failed ({rc}): {self.L.ev2b_last_error(self.h).decode()}")
+
+    def _stream(self):
+        return None
 
     def close(self):
         if getattr(self, "h", None):

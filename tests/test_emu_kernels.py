@@ -59,6 +59,7 @@ def _run_vs_oracle(emu, topo, bank, E, reward, state, adt, kernel, G=None, outpu
     caps = eng.state()["port_cap"]
     rng = np.random.default_rng(99)
     Tr = topo.Tr
+    n_invalid, n_served = np.zeros(E), np.zeros(E)
     for t in range(steps or topo.T):
         a = rng.uniform(-1, 1, (E, topo.P))
         a[rng.random((E, topo.P)) < 0.1] = 0.0
@@ -84,6 +85,8 @@ def _run_vs_oracle(emu, topo, bank, E, reward, state, adt, kernel, G=None, outpu
             assert np.array_equal(out["action_mask"] > 0, occ), (t, "action mask")
         ovf = np.array([o.error == 1 for o in orc.outs])
         assert np.array_equal((out["status"] & 2) > 0, ovf), (t, "amps overflow flag")
+        n_invalid += [o.invalid_actions for o in orc.outs]
+        n_served += [o.n_departed for o in orc.outs]
         for e in (0, E - 1):                # the engine's own occupancy (hot words) agrees with the oracle's
             if not orc.done[e]:
                 assert np.array_equal(_occupied_ports(eng, e), np.nonzero(occ[e])[0]), (t, e, "occupancy")
@@ -92,6 +95,7 @@ def _run_vs_oracle(emu, topo, bank, E, reward, state, adt, kernel, G=None, outpu
     k = {n: kpi[:, i] for i, n in enumerate(KPI_NAMES)}
     assert _close(k["total_reward"], [s.total_reward for s in orc.states], 1e-9, 1e-9)
     assert np.array_equal(k["total_evs_spawned"], [float(s.total_evs_spawned) for s in orc.states])
+    assert np.array_equal(k["invalid_actions"], n_invalid) and np.array_equal(k["total_ev_served"], n_served)
     return eng, orc
 
 
@@ -488,3 +492,17 @@ def test_kstep_kernel_equals_launch_per_step(emu, G, agent, monkeypatch):
         kpi = eng.state()["env_kpi"]
         assert _close(kpi[:, 0], [s.total_reward for s in orc.states], 1e-9, 1e-9)
         eng.close()
+
+
+@pytest.mark.parametrize("kernel", ["percharger", "evlist"])
+def test_more_than_1023_ports_per_env(emu, kernel, monkeypatch):
+    """600 chargers x 2 ports: the env-level counts (empty ports, departures, arrivals of a step) exceed the 10-bit fields
+    step_kernel used to pack them in (round-1 advisor finding); the KPI sums must still equal the oracle's."""
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    topo = Topology.uniform(C=600, n_ports=2, Tr=3, T=10)
+    bank = sample_bank(topo, 2, seed=3, min_stay=3)
+    eng, orc = _run_vs_oracle(emu, topo, bank, 2, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", "float64",
+                              kernel, G=2, monkeypatch=monkeypatch)
+    assert eng.state()["env_kpi"][:, 11].min() > 1023          # invalid_actions: more than one step's worth of 10 bits
+    eng.close()

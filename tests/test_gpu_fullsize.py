@@ -64,3 +64,85 @@ def test_full_size_replicas_and_sampled_oracle(pack_name, E, reward, state):
     k = eng.kpis()                                                                 # (C)
     assert np.allclose(k["total_reward"], reward_sum.cpu().numpy(), rtol=1e-9, atol=1e-9)
     assert np.allclose(k["total_reward"][:S], [s.total_reward for s in orc.states], rtol=1e-9, atol=1e-9)
+
+
+def test_c5_full_size_grid_replicas_and_sampled_oracle():
+    """BASELINE config 5 at its stated size: 2048 envs x 500 chargers, 20 transformers, Laurent power flow on a 21-bus
+    feeder, V2G_grid_state + V2G_grid_full_reward (the synthetic stand-in of bench.py --workload c5: the BusinessPST.yaml
+    and the 20-transformer network BASELINE.json names do not exist in the reference).  Same properties as
+    above -- bitwise replica consistency over the whole batch, the first bank's worth of envs against the oracle incl. node
+    voltages (1e-9) -- and the launches must have taken the event-driven kernel's HEAVY instantiation."""
+    import torch
+    from bench import WORKLOADS, load_pack
+    from ev2gym_b200.engine import BatchedEngine
+    from oracle.oracle import OracleBatch
+    pack_name, E, reward, state, _ = WORKLOADS["c5"]
+    pack = load_pack(pack_name)
+    topo, S = pack.topo, len(pack)
+    assert (E, topo.C, topo.Tr, topo.n_bus) == (2048, 500, 20, 20) and E % S == 0
+    eng = BatchedEngine(topo, E, reward=reward, state=state, outputs=("reward", "status", "obs", "node_voltage", "tr_power"))
+    eng.load_scenarios(pack.scenarios)
+    obs0 = eng.reset()
+    orc = OracleBatch(topo, pack.scenarios, reward=reward, state=state)
+    o0 = orc.reset()
+    assert np.allclose(obs0[:S].cpu().numpy(), o0, rtol=1e-5, atol=1e-5)
+    caps = eng.state_tensors()["port_cap"]
+    rng = np.random.default_rng(12)
+
+    def same_across_replicas(t):
+        v = t.reshape((E // S, S) + tuple(t.shape[1:]))
+        return bool((v == v[:1]).all())
+
+    for step in range(topo.T):
+        a = rng.uniform(-1.0, 1.0, (S, topo.P))
+        a[rng.random((S, topo.P)) < 0.1] = 0.0
+        out = eng.step(torch.tensor(np.tile(a, (E // S, 1)), dtype=torch.float32, device="cuda"))
+        for k in ("reward", "status", "obs", "node_voltage", "tr_power"):
+            assert same_across_replicas(out[k]), (step, k)
+        assert same_across_replicas(caps), (step, "cap")
+        orc.step(a.astype(np.float32).astype(np.float64))
+        occ = orc.arr["port_session"] >= 0
+        assert np.array_equal(caps[:S].cpu().numpy()[occ], orc.arr["port_cap"][occ]), step
+        r = out["reward"][:S].cpu().numpy()
+        assert np.all(np.abs(r - orc.reward) <= 1e-9 + 1e-9 * np.abs(orc.reward)), step
+        assert np.allclose(out["node_voltage"][:S].cpu().numpy(), orc.o["node_vm"][:, :topo.n_bus + 1], rtol=1e-9, atol=1e-12), step
+        assert np.allclose(out["obs"][:S].cpu().numpy(), orc.o["obs"][:, :eng.D], rtol=1e-5, atol=1e-5), step
+    assert bool((out["status"] & 1).all())
+    assert eng.kernel_launches() == (0, topo.T, 0)          # every launch: evl_step_kernel (HEAVY: grid)
+    assert np.allclose(eng.kpis()["total_reward"][:S], [s.total_reward for s in orc.states], rtol=1e-9, atol=1e-9)
+
+
+def test_more_than_1024_chargers_per_env():
+    """1500 chargers x 2 ports per env (the reference has no size limit, loaders.py:299-365; step_kernel's one thread per
+    charger stops at 1024): served by the event-driven kernel whatever the batch size, checked against the oracle."""
+    import torch
+    from ev2gym_b200.engine import BatchedEngine
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    from oracle.oracle import OracleBatch
+    topo = Topology.uniform(C=1500, n_ports=2, Tr=7, T=30)
+    bank = sample_bank(topo, 2, seed=4, min_stay=4)
+    E = 6
+    rw, stf = "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads"
+    eng = BatchedEngine(topo, E, reward=rw, state=stf, outputs=("reward", "status", "obs", "action_mask"))
+    eng.load_scenarios(bank)
+    eng.reset()
+    orc = OracleBatch(topo, [bank[e % 2] for e in range(E)], reward=rw, state=stf)
+    orc.reset()
+    caps = eng.state_tensors()["port_cap"]
+    rng = np.random.default_rng(9)
+    invalid = np.zeros(E)
+    for step in range(topo.T):
+        a = rng.uniform(-1.0, 1.0, (E, topo.P))
+        invalid += topo.P - (orc.arr["port_session"] >= 0).sum(axis=1)     # every empty port counts  ev_charger.py:137-140
+        out = eng.step(torch.tensor(a, dtype=torch.float64, device="cuda"))
+        orc.step(a)
+        occ = orc.arr["port_session"] >= 0
+        assert np.array_equal(caps.cpu().numpy()[occ], orc.arr["port_cap"][occ]), step
+        assert np.array_equal(out["action_mask"].cpu().numpy() > 0, occ), step
+        r = out["reward"].cpu().numpy()
+        assert np.all(np.abs(r - orc.reward) <= 1e-9 + 1e-9 * np.abs(orc.reward)), step
+        assert np.allclose(out["obs"].cpu().numpy(), orc.o["obs"][:, :eng.D], rtol=1e-5, atol=1e-5), step
+    assert eng.kernel_launches()[0] == 0
+    assert invalid.min() > 1023 * topo.T                   # (totals beyond the 10-bit fields step_kernel once packed them in)
+    assert np.array_equal(eng.kpis()["invalid_actions"], invalid)
