@@ -160,14 +160,29 @@ def oracle_episodes(topo, scenarios, reward, state, E, n_episodes, warm_steps=3,
     return E * steps / dt, steps, eps, dt, ob.threads
 
 
-def cpu_baseline(topo, scenarios, reward, state, E, target_seconds=12.0, threads=0):
-    """The C oracle (a port of the reference step; the reference itself is Python and cannot travel)."""
+def python_reference(workload, seconds=6.0):
+    """The UNMODIFIED Python reference (baseline/_ref, installed by pip from /root/reference; git-ignored, travels to the
+    GPU box) on this box's host cores: one process and one process per host thread (tools/time_python_reference.py)."""
+    if workload not in ("c2", "c3", "c4") or not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "ev2gym")):
+        return {"unavailable": "baseline/_ref not installed (or no shipped config for this workload)"}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_python_reference.py"), "--workload", workload,
+                            "--seconds", str(seconds)], capture_output=True, text=True, timeout=240)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # pragma: no cover
+        return {"unavailable": repr(exc)}
+
+
+def cpu_baseline(topo, scenarios, reward, state, E, target_seconds=12.0, threads=0, workload=None):
+    """The C oracle (a port of the reference step) on all host threads, plus the Python reference itself beside it."""
     v, steps, eps, dt, thr = oracle_episodes(topo, scenarios, reward, state, E, 0, threads=threads,
                                              seconds=target_seconds)
-    return {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
-            "sample": f"C oracle (oracle/ev2o.c, fp64, pthreads), {E} envs x {eps} whole episodes ({steps} steps) incl. "
-                      f"state+reward, {dt:.1f} s; the Python reference itself measured 330 env-steps/s/core on this "
-                      f"shape (BASELINE.md)"}
+    out = {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
+           "sample": f"C oracle (oracle/ev2o.c, fp64, pthreads), {E} envs x {eps} whole episodes ({steps} steps) incl. "
+                     f"state+reward, {dt:.1f} s"}
+    if workload:
+        out["python_reference"] = python_reference(workload)
+    return out
 
 
 def run_reference(args, wl):
@@ -191,7 +206,8 @@ def run_reference(args, wl):
                    "window": f"{eps} whole episodes (t = 0 .. {topo.T}) of the full batch of {E} envs, resets inside",
                    "sample": f"full batch of {E} envs per step, {steps} steps"},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
-                         "sample": f"C oracle, {E} envs x {eps} whole episodes ({steps} steps)"},
+                         "sample": f"C oracle, {E} envs x {eps} whole episodes ({steps} steps)",
+                         "python_reference": python_reference(wl) if args.gpus == 1 else None},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -209,6 +225,9 @@ def main():
     ap.add_argument("--no-obs", action="store_true", help="do not produce observations (heuristic-driven runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the distinct-scenario and c3-1k extra measurements")
     ap.add_argument("--min-seconds", type=float, default=MIN_TIMED_SECONDS)
+    ap.add_argument("--sweeps-only", action="store_true",
+                    help="only the timed whole-episode sweeps, launched eagerly (for `ncu --metrics gpu__time_duration.sum`: "
+                         "the launch list of the timed region without the extras)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, args.workload)
@@ -336,8 +355,13 @@ def main():
     sampler.start()
     time.sleep(0.3)
     elapsed_ms, n_sweeps, graphed = time_sweeps(engines, actions, args.steps, args.min_seconds,
-                                                use_graph=not args.no_graph)
+                                                use_graph=not (args.no_graph or args.sweeps_only))
     clocks = sampler.stop()
+    if args.sweeps_only:
+        if rank == 0:
+            print(json.dumps({"sweeps_only": True, "sweeps": n_sweeps, "groups": G, "T": T, "elapsed_ms": elapsed_ms,
+                              "us_per_launch": elapsed_ms * 1e3 / (n_sweeps * G * T)}))
+        return
     K = n_sweeps * G * T                                                # step launches inside the timed region
     gpu_launches = K + n_sweeps * 2 * G                                 # + the two reset kernels per group and sweep
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
@@ -433,6 +457,19 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * E * n_e2e / float(te.item())
     e2e_step_ms = float(te.item()) / n_e2e * 1e3
+    # the same call without the observation download (obs_host = NULL: open-loop / replayed action sequences, or consumers
+    # that read the state views on demand): H2D actions -> kernel -> D2H reward + status
+    def e2e_episode_no_obs():
+        eng.reset()
+        for k in range(T):
+            eng.step_host(h_act[k % 2], h_rew, h_st, None)
+    e2e_episode_no_obs()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(n_e2e_eps):
+        e2e_episode_no_obs()
+    torch.cuda.synchronize(dev)
+    e2e_noobs_value = E * n_e2e / (time.perf_counter() - t0)
     e2e_bytes = eng.host_step_bytes() if hasattr(eng, "host_step_bytes") else None
     if e2e_bytes is None:
         e2e_bytes = {"h2d": E * topo.P * 4, "d2h": E * (8 + 4 + 4 * D)}
@@ -583,7 +620,9 @@ def main():
                     "pcie_floor": {"d2h_ms": d2h_ms, "h2d_ms": h2d_ms, "d2h_gbs": d2h_bytes / d2h_ms / 1e6,
                                    "h2d_gbs": h2d_bytes / h2d_ms / 1e6, "frac": max(d2h_ms, h2d_ms) / e2e_step_ms,
                                    "what": "the step's bytes as bare pinned cudaMemcpyAsync, each direction alone"},
-                    "what": "ev2b_step_host: pinned host actions -> H2D -> fused kernel -> D2H reward+status+obs -> sync"},
+                    "what": "ev2b_step_host: pinned host actions -> H2D -> fused kernel -> D2H reward+status+obs -> sync",
+                    "without_obs_download": {"value_per_gpu": e2e_noobs_value, "d2h_bytes_per_step": E * 12,
+                                             "what": "same call with obs_host = NULL (reward + status only), this rank"}},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "traffic_source_sha": traffic_sha,
@@ -610,7 +649,8 @@ def main():
             "extras": extras,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(topo, pack.scenarios, reward, state if D else None, E)
+            line["cpu_baseline"] = cpu_baseline(topo, pack.scenarios, reward, state if D else None, E,
+                                                workload=args.workload if args.workload in ("c2", "c3", "c4") else None)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

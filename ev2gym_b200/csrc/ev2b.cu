@@ -65,6 +65,7 @@ struct ev2b_handle {
     // device: static
     DevBuf<CsStatic> cs; DevBuf<int> cs_tr_d; DevBuf<int> tr_cs_off, tr_cs_idx, obs_slot, tr_obs_off, port_cs_d, series_off;
     int W = 0;                          // (scenario, time)-only observation values per env
+    int series_pairs = 0;               // they can be copied two at a time (Params::series_pairs)
     // device: bank
     int S = 0, Smax = 1, n_dr = 1, lut_len = 101;
     DevBuf<EnvT> env_t; DevBuf<TrT> tr_t; DevBuf<SessRec> sess; DevBuf<EvSpec> spec;
@@ -151,7 +152,7 @@ struct ev2b_handle {
     Params params() const {
         Params p{};
         p.E = E; p.C = C; p.P = P; p.Tr = Tr; p.T = T; p.D = D; p.EPB = EPB; p.n_dr = n_dr; p.lut_len = lut_len;
-        p.Smax = Smax; p.S = S; p.n_cls = n_cls; p.W = W; p.env0 = 0; p.env_end = E;
+        p.Smax = Smax; p.S = S; p.n_cls = n_cls; p.W = W; p.env0 = 0; p.env_end = E; p.series_pairs = series_pairs;
         p.reward_kind = dims.reward_kind; p.state_kind = dims.state_kind; p.dr_steps_ahead = dims.dr_steps_ahead;
         p.c60 = 60.0 / (double)dims.timescale; p.p60 = (double)dims.timescale / 60.0; p.period = (double)dims.timescale;
         p.rc60 = 1.0 / p.c60; p.rp60 = 1.0 / p.p60; p.rperiod = 1.0 / p.period;
@@ -448,6 +449,9 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         for (int i = 0; i < 2 * h->n_bus; ++i) series_off_h.push_back(6 + i);
     }
     h->W = (int)series_off_h.size();
+    h->series_pairs = (h->W > 0 && h->W % 2 == 0 && h->D % 2 == 0) ? 1 : 0;
+    for (int i = 0; i + 1 < h->W && h->series_pairs; i += 2)
+        if (series_off_h[i] % 2 != 0 || series_off_h[i + 1] != series_off_h[i] + 1) h->series_pairs = 0;
     // launch shape: a CTA owns EPB whole envs, one thread per (env, charger)
     {
         int best_epb = 1; double best_u = -1;

@@ -140,6 +140,8 @@ struct Params {
     int mask_full;             // 1: out.action_mask does not hold last step's rows (evl_step_kernel rewrites them)
     int scn_stride;            // auto-reset: next scenario = (current + scn_stride) mod S, gcd(scn_stride, S) = 1
     int k_steps, auto_reset;   // evl_step_kernel<..., KSTEP = true>: steps per launch, device-side reset of finished envs
+    int series_pairs;          // 1: W is even, series values 2j / 2j+1 land on neighbouring floats at an even offset and D is
+                               //    even: the (scenario, time) observation values are copied as float2
     // state
     uint4 *hot; double *cap; double *exch;   // exch: float64 like the reference's total_energy_exchanged (ev.py:178)
      int *env_step; int *env_scn; double *env_pot; double *env_usage;
@@ -333,9 +335,14 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
             // pts = ts + (pilot - maxd) / maxd * (ts - 1)   :312-314.  A saturated request has pilot == maxd exactly, and a
             // zero numerator sends the compiler's fp64 division into its out-of-line slow path (ncu: ~270 warp instructions
             // per env-step); 0 / maxd * (ts - 1) is +-0 and ts + (+-0) == ts, so those lanes skip the division.
+            // (round 2: ptxas turned the round-1 `if (dz != 0) ratio = dz / maxd` into a SELECT, so the saturated lanes --
+            //  half of the charging lanes of the bench workload -- still ran the division and 98 % of the warps called its
+            //  slow path, 5.5 % of the kernel's instructions (profiles/r2c_evl_g1_ncu_busy_lines.txt).  Those lanes now
+            //  divide maxd / maxd, which stays on the fast path, and discard the quotient.)
             const double dz = pilot - maxd;
-            double ratio = 0.0;
-            if (dz != 0.0 || maxd == 0.0) ratio = dz / maxd;
+            const bool sat = dz == 0.0 && maxd != 0.0;
+            const double quot = (sat ? maxd : dz) / maxd;
+            const double ratio = sat ? 0.0 : quot;
             const double pts = ts + ratio * (ts - 1.0);
             double nsoc;
             // `1 <= (pts - soc) / pilot`  (:323)  without the division: for 0 < pilot and x = pts - soc > 0, x < pilot

@@ -199,9 +199,12 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     // with the per-env scalars (entries at or beyond occ_n are stale and never used).
     const uint16_t *lst = p.occ_list + (size_t)e * p.P;
     const unsigned first = gtid < p.P ? (unsigned)lst[gtid] : 0u;
-    const int t = p.env_step[e];
-    const int s = p.env_scn[e];
-    const int n_old = p.occ_n[e];
+    // volatile: read exactly once.  Warp 0 uses n_old in the KPI update while the group's last warp is storing the new
+    // occ_n; a plain load may be re-issued by the compiler at that later use (it was, under register pressure, with
+    // G = 4: invalid_actions went wrong on the B200 while every other quantity was right -- round 2, test_gpu_evlist).
+    const int t = *reinterpret_cast<const volatile int *>(p.env_step + e);
+    const int s = *reinterpret_cast<const volatile int *>(p.env_scn + e);
+    const int n_old = *reinterpret_cast<const volatile int *>(p.occ_n + e);
     if (gw == 0) {                                     // KPI sums, potential[t], potential[t-1]: need nothing but e
         if (lane <= kPrePot) cp_async8(pre + lane, lane < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + lane : p.env_pot + e);
         else if (lane == kEvlPotPrev) cp_async8(pre + lane, p.env_pot_prev + e);
@@ -254,6 +257,21 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     if (want_obs) {
         // batches of 4 values per thread: the loads of a batch are in flight together (an idle env's warp would otherwise
         // wait out seven dependent L2 round trips, one per value)
+        if (p.series_pairs && p.obs_static) {         // (the host checked: values 2j, 2j+1 are neighbours at an even offset)
+            const float2 *src = reinterpret_cast<const float2 *>(p.obs_static + ((size_t)s * (p.T + 1) + tq) * p.W);
+            const int W2 = p.W >> 1;
+#pragma unroll 1
+            for (int i0 = gtid; i0 < W2; i0 += 4 * NT) {
+                float2 v[4]; int o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * NT;
+                    if (i < W2) { o[j] = __ldg(&p.series_off[2 * i]); v[j] = __ldg(src + i); }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (i0 + j * NT < W2) *reinterpret_cast<float2 *>(obs_row + o[j]) = v[j];
+            }
+        } else {
 #pragma unroll 1
         for (int i0 = gtid; i0 < p.W; i0 += 4 * NT) {
             float v[4]; int o[4];
@@ -264,6 +282,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (i0 + j * NT < p.W) obs_row[o[j]] = v[j];
+        }
         }
         if (obs_full) {                               // the caller's buffer does not hold last step's rows: clear every tuple
 #pragma unroll 1
@@ -555,11 +574,15 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         if (lane == 0 && p.out.node_voltage) p.out.node_voltage[(size_t)e * (p.n_bus + 1)] = 1.0;
     }
     // ---- reward, KPI sums, step counter: every lane computes the (uniform) reward, lane k stores quantity k ------
+    if (idle) {                                       // every per-EV total is zero (stored so that the reads below are
+        if (lane < EvlNSum) wsum[lane] = 0.0;         //  unconditional: one LDS each instead of eight guarded blocks)
+        __syncwarp();
+    }
     double q[EvlNSum];
 #pragma unroll
     for (int k = 0; k < EvlNSum; ++k) {
-        double v = 0.0;
-        if (!idle) { v = wsum[k]; for (int w = 1; w < G; ++w) v += wsum[w * EvlNSum + k]; }
+        double v = wsum[k];
+        if (!idle) for (int w = 1; w < G; ++w) v += wsum[w * EvlNSum + k];
         q[k] = v;
     }
     const int cnts = (int)q[EvlCounts];

@@ -117,9 +117,11 @@ def test_replay_pickle_import_round_trip():
 
 
 def test_step_kernels_keep_their_register_budget():
-    """Both step kernels are register-limited to 8 CTAs of 128 threads per SM (64 registers per thread) and keep only a
-    few spill slots; the kernel parameter block must fit the 4 KB parameter space.  Read from the built library with
-    cuobjdump (no GPU needed), so an edit that bloats them fails here and not as a slowdown on the GPU box."""
+    """step_kernel is register-limited to 8 CTAs of 128 threads per SM (64 registers per thread), the lean event-driven
+    kernel to 7 (72 registers: measured faster than 64 and 80 on the B200, profiles/r2_ab_registers.jsonl), its HEAVY
+    instantiation (statistics / grid / per-port outputs) to 4 (128); the kernel parameter block must fit the 4 KB
+    parameter space.  Read from the built library with cuobjdump (no GPU needed), so an edit that bloats them fails
+    here and not as a slowdown on the GPU box."""
     import re
     import shutil
     import subprocess
@@ -133,12 +135,13 @@ def test_step_kernels_keep_their_register_budget():
     checked = 0
     for name, usage in res.items():
         lean_step = "step_kernelIfLi2ELb1ELi128ELi8ELb0ELb0" in name          # c3: float actions, 2 ports, no optional outputs
-        lean_evl = "evl_step_kernelIf" in name and name.endswith("ELb0EEEvNS_6ParamsE")
-        if not (lean_step or lean_evl):
+        evl = re.search(r"evl_step_kernelI[fd]Li\dELb[01]ELi\dELb([01])ELb[01]EEEvNS_6ParamsE", name)   # <ActT, NP, UNI, G, HEAVY, KSTEP>
+        if not (lean_step or evl):
             continue
         reg, stack = int(re.search(r"REG:(\d+)", usage).group(1)), int(re.search(r"STACK:(\d+)", usage).group(1))
         const0 = int(re.search(r"CONSTANT\[0\]:(\d+)", usage).group(1))
-        assert reg <= 64 and stack <= 96, (name, usage)
+        limit = 64 if lean_step else (128 if evl.group(1) == "1" else 72)
+        assert reg <= limit and stack <= 256, (name, usage)
         assert const0 <= 4096 + 528, (name, usage)                            # driver area + kernel parameters
         checked += 1
     assert checked >= 4
