@@ -56,7 +56,9 @@ class StepOut(C.Structure):
     _fields_ = [("reward", C.c_void_p), ("status", C.c_void_p), ("obs", C.c_void_p), ("cs_power", C.c_void_p),
                 ("cs_current", C.c_void_p), ("tr_power", C.c_void_p), ("tr_overload", C.c_void_p),
                 ("total_costs", C.c_void_p), ("action_mask", C.c_void_p), ("dep_sat", C.c_void_p),
-                ("dep_cap", C.c_void_p), ("port_energy", C.c_void_p), ("node_voltage", C.c_void_p)]
+                ("dep_cap", C.c_void_p), ("port_energy", C.c_void_p), ("node_voltage", C.c_void_p),
+                ("hist_cs_power", C.c_void_p), ("hist_cs_current", C.c_void_p), ("hist_tr_overload", C.c_void_p),
+                ("hist_usage", C.c_void_p)]
 
 
 class StateView(C.Structure):

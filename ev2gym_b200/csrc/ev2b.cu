@@ -319,7 +319,8 @@ static cudaError_t launch_step(ev2b_handle *h, const Params &p, cudaStream_t st)
 #endif
     const ev2b_step_out &o = p.out;    // any optional output requested?  (reward / status / obs are always compiled in)
     const bool opt = o.cs_power || o.cs_current || o.tr_power || o.tr_overload || o.total_costs || o.action_mask ||
-                     o.dep_sat || o.dep_cap || o.port_energy || o.node_voltage;
+                     o.dep_sat || o.dep_cap || o.port_energy || o.node_voltage || o.hist_cs_power || o.hist_cs_current ||
+                     o.hist_tr_overload || o.hist_usage;
     if (h->block <= 128) EV2B_DISPATCH(128, EV2B_MINB128);
     if (h->block <= 256) EV2B_DISPATCH(256, EV2B_MINB);
     if (h->block <= 512) EV2B_DISPATCH(512, 2);

@@ -792,6 +792,8 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
         if (overflow) atomicOr(&envi[el * 8 + 3], (int)EV2B_ST_AMPS_OVERFLOW);
         if (EV2B_OPT(p.out.cs_power))   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
         if (EV2B_OPT(p.out.cs_current)) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
+        if (EV2B_OPT(p.out.hist_cs_power))   p.out.hist_cs_power[((size_t)e * p.T + t) * p.C + c] = (float)rP;
+        if (EV2B_OPT(p.out.hist_cs_current)) p.out.hist_cs_current[((size_t)e * p.T + t) * p.C + c] = (float)rA;
     }
     red[RedP * NT + tid] = rP;             red[RedProfit * NT + tid] = rProfit;
     red[RedSatExp * NT + tid] = rSatExp;   red[RedPot * NT + tid] = rPot;
@@ -835,6 +837,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                         trp[jel * p.Tr + k] = ptot;
                         if (EV2B_OPT(p.out.tr_power))    p.out.tr_power[(size_t)je * p.Tr + k] = ptot;
                         if (EV2B_OPT(p.out.tr_overload)) p.out.tr_overload[(size_t)je * p.Tr + k] = ov;
+                        if (EV2B_OPT(p.out.hist_tr_overload)) p.out.hist_tr_overload[((size_t)je * p.T + jt) * p.Tr + k] = ov;
                     }
                 }
             } else if (kind == 1) {   // env-level float64 sums: 7 quantities x 4 segments = 28 lanes
@@ -949,6 +952,7 @@ __global__ void __launch_bounds__(MAXT, MINB) step_kernel(const __grid_constant_
                 p.env_pot[je] = (jt + 1 < p.T) ? v[RedPot] : 0.0;              // ev2gym_env.py:424-426
                 p.env_usage[je] = usage;
                 p.env_step[je] = jt + 1;
+                if (EV2B_OPT(p.out.hist_usage)) p.out.hist_usage[(size_t)je * p.T + jt] = usage;
                 if (jt + 1 >= p.T) status |= EV2B_ST_DONE;                     // ev2gym_env.py:460
                 if (want_obs) obs_header(p, p.out.obs + (size_t)je * p.D, js, jt + 1, usage, pe[kPreSetNext]);
             } else {

@@ -222,8 +222,6 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     const EnvT *etp = p.env_t + (size_t)s * p.T + t;
     const double2 price = *reinterpret_cast<const double2 *>(etp);           // cp, dp
     const int a0 = etp->arr0, nArr = etp->n_arr;                             // the sessions arriving at step t+1
-    const bool idle = n_old == 0 && nArr == 0;        // nobody connected, nobody arriving: warp 0 alone, no barriers
-    if (idle && gw != 0) { if (!KSTEP) evl_group_arrive<G>(g); return tq; }
     if (gw == 0) {                                    // setpoints and the transformers' rows of this step (two 16 B halves each)
         if (lane == kEvlSet) cp_async8(pre + lane, &etp->setpoint);
         else if (lane == kEvlSetNext) { if (tq < p.T) cp_async8(pre + lane, &etp[1].setpoint); else pre[lane] = 0.0; }
@@ -231,9 +229,44 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         for (int i = lane; i < 2 * p.Tr; i += 32)
             cp_async16(pre + kEvlTr + 2 * i, reinterpret_cast<const double *>(p.tr_t + ((size_t)s * p.T + t) * p.Tr) + 2 * i);
     }
-    const int NT = idle ? 32 : GT;                    // threads that share the fills below
     float *obs_row = p.out.obs + (size_t)e * p.D;
+    if (want_obs) {                                   // (before the idle decision: these loads travel with the ones above)
+        // batches of 4 values per thread: the loads of a batch are in flight together (an idle env's warp would otherwise
+        // wait out seven dependent L2 round trips, one per value)
+        if (p.series_pairs && p.obs_static) {         // (the host checked: values 2j, 2j+1 are neighbours at an even offset)
+            const float2 *src = reinterpret_cast<const float2 *>(p.obs_static + ((size_t)s * (p.T + 1) + tq) * p.W);
+            const int W2 = p.W >> 1;
+#pragma unroll 1
+            for (int i0 = gtid; i0 < W2; i0 += 4 * GT) {
+                float2 v[4]; int o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * GT;
+                    if (i < W2) { o[j] = __ldg(&p.series_off[2 * i]); v[j] = __ldg(src + i); }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (i0 + j * GT < W2) *reinterpret_cast<float2 *>(obs_row + o[j]) = v[j];
+            }
+        } else {
+#pragma unroll 1
+        for (int i0 = gtid; i0 < p.W; i0 += 4 * GT) {
+            float v[4]; int o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * GT;
+                if (i < p.W) { o[j] = __ldg(&p.series_off[i]); v[j] = obs_series_fetch(p, s, tq, i); }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (i0 + j * GT < p.W) obs_row[o[j]] = v[j];
+        }
+        }
+    }
+    const bool idle = n_old == 0 && nArr == 0;        // nobody connected, nobody arriving: warp 0 alone, no barriers
+    if (idle && gw != 0) { if (!KSTEP) evl_group_arrive<G>(g); return tq; }
+    const int NT = idle ? 32 : GT;                    // threads that share the fills below
     uint8_t *mask_row = p.out.action_mask ? p.out.action_mask + (size_t)e * p.P : nullptr;
+    float *h_csP = p.out.hist_cs_power ? p.out.hist_cs_power + ((size_t)e * p.T + t) * p.C : nullptr;     // row t of the histories
+    float *h_csA = p.out.hist_cs_current ? p.out.hist_cs_current + ((size_t)e * p.T + t) * p.C : nullptr;
 
     // ---- P0: zero the per-port flags, fill the per-step outputs, (scenario, time)-only observation values ---------
     if (!idle) {
@@ -246,44 +279,17 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         }
     }
     if (NP == 1 || idle) {                            // (with a CS phase the charger's thread writes these)
-        if (p.out.cs_power || p.out.cs_current) {
+        if (p.out.cs_power || p.out.cs_current || h_csP || h_csA) {
 #pragma unroll 1
             for (int c = gtid; c < p.C; c += NT) {
                 if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = 0.f;
                 if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = 0.f;
+                if (h_csP) h_csP[c] = 0.f;
+                if (h_csA) h_csA[c] = 0.f;
             }
         }
     }
     if (want_obs) {
-        // batches of 4 values per thread: the loads of a batch are in flight together (an idle env's warp would otherwise
-        // wait out seven dependent L2 round trips, one per value)
-        if (p.series_pairs && p.obs_static) {         // (the host checked: values 2j, 2j+1 are neighbours at an even offset)
-            const float2 *src = reinterpret_cast<const float2 *>(p.obs_static + ((size_t)s * (p.T + 1) + tq) * p.W);
-            const int W2 = p.W >> 1;
-#pragma unroll 1
-            for (int i0 = gtid; i0 < W2; i0 += 4 * NT) {
-                float2 v[4]; int o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + j * NT;
-                    if (i < W2) { o[j] = __ldg(&p.series_off[2 * i]); v[j] = __ldg(src + i); }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (i0 + j * NT < W2) *reinterpret_cast<float2 *>(obs_row + o[j]) = v[j];
-            }
-        } else {
-#pragma unroll 1
-        for (int i0 = gtid; i0 < p.W; i0 += 4 * NT) {
-            float v[4]; int o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = i0 + j * NT;
-                if (i < p.W) { o[j] = __ldg(&p.series_off[i]); v[j] = obs_series_fetch(p, s, tq, i); }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (i0 + j * NT < p.W) obs_row[o[j]] = v[j];
-        }
-        }
         if (obs_full) {                               // the caller's buffer does not hold last step's rows: clear every tuple
 #pragma unroll 1
             for (int i = gtid; i < p.P; i += NT) evl_obs_clear(p, obs_row, i);
@@ -433,6 +439,8 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
             aUsage += rP; aPot += rPot;
             if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + port] = (float)rP;
             if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + port] = (float)rA;
+            if (h_csP) h_csP[port] = (float)rP;
+            if (h_csA) h_csA[port] = (float)rA;
         } else {
             pot[port] = potv;
             occ[port] = (unsigned char)flags;
@@ -508,6 +516,8 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         aUsage += rP; aPot += rPot;
         if (p.out.cs_power)   p.out.cs_power[(size_t)e * p.C + c] = (float)rP;
         if (p.out.cs_current) p.out.cs_current[(size_t)e * p.C + c] = (float)rA;
+        if (h_csP) h_csP[c] = (float)rP;
+        if (h_csA) h_csA[c] = (float)rA;
     }
     // per-warp partial sums (fixed butterfly); the group total is formed warp by warp in the reward phase
     {
@@ -562,6 +572,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
                 if (HEAVY && p.n_bus > 0) trp[k] = ptot;
                 if (p.out.tr_power)    p.out.tr_power[(size_t)e * p.Tr + k] = ptot;
                 if (p.out.tr_overload) p.out.tr_overload[(size_t)e * p.Tr + k] = ov;
+                if (p.out.hist_tr_overload) p.out.hist_tr_overload[((size_t)e * p.T + t) * p.Tr + k] = ov;
             }
         }
         ovsum = warp_sum(ovsum);
@@ -654,6 +665,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     } else if (lane == 14) {
         p.env_usage[e] = usage;
         p.env_step[e] = tq;
+        if (p.out.hist_usage) p.out.hist_usage[(size_t)e * p.T + t] = usage;
     } else if (lane == 15) {
         unsigned status = (cnts >> 20) ? EV2B_ST_AMPS_OVERFLOW : 0u;
         if (tq >= p.T) status |= EV2B_ST_DONE;                            // ev2gym_env.py:460

@@ -40,6 +40,9 @@ _OUT_SPECS = {  # name -> (dtype, per-env shape key)
     "tr_power": ("float64", ("Tr",)), "tr_overload": ("float64", ("Tr",)), "total_costs": ("float64", ()),
     "action_mask": ("uint8", ("P",)), "dep_sat": ("float64", ("P",)), "dep_cap": ("float64", ("P",)),
     "port_energy": ("float32", ("P",)), "node_voltage": ("float64", ("N",)),
+    # per-episode histories, time-major (include/ev2b.h); BatchedEngine.histories() gives the reference's [.,T] shapes
+    "hist_cs_power": ("float32", ("T", "C")), "hist_cs_current": ("float32", ("T", "C")),
+    "hist_tr_overload": ("float64", ("T", "Tr")), "hist_usage": ("float64", ("T",)),
 }
 
 
@@ -214,7 +217,7 @@ class BatchedEngine(SpawnMixin):
 
     def set_outputs(self, names: Iterable[str]):
         torch = self.torch
-        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P, "N": self.topo.n_bus + 1}
+        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P, "N": self.topo.n_bus + 1, "T": self.T}
         self.out = {}
         self._so = _lib.StepOut()
         for n in names:
@@ -343,6 +346,14 @@ class BatchedEngine(SpawnMixin):
         self._check(self.L.ev2b_episode_stats(self.h, out.data_ptr(), self._stream()), "ev2b_episode_stats")
         o = out.cpu().numpy()
         return {n: o[:, i].copy() for i, n in enumerate(STAT_NAMES)}
+
+    def histories(self) -> Dict[str, "torch.Tensor"]:
+        """The history outputs that were asked for (set_outputs(..., "hist_cs_power", ...)) in the reference's shapes:
+        cs_power / cs_current [E,C,T], tr_overload [E,Tr,T], current_power_usage [E,T]  (utils.py:794-861)."""
+        names = {"hist_cs_power": "cs_power", "hist_cs_current": "cs_current", "hist_tr_overload": "tr_overload",
+                 "hist_usage": "current_power_usage"}
+        return {v: (self.out[k].transpose(1, 2) if self.out[k].dim() == 3 else self.out[k])
+                for k, v in names.items() if k in self.out}
 
     def kpis(self) -> Dict[str, np.ndarray]:
         k = self.state_tensors()["env_kpi"].cpu().numpy()

@@ -339,10 +339,16 @@ class EV2GymB200Vec:
     """E env replicas stepped by one kernel launch; torch in / torch out; device-side auto reset."""
 
     def __init__(self, topo: Topology, scenarios: Sequence[Scenario], num_envs: int, state_function="V2G_profit_max",
-                 reward_function="profit_maximization", device: int = 0, auto_reset: bool = True, rank: int = 0):
+                 reward_function="profit_maximization", device: int = 0, auto_reset: bool = True, rank: int = 0,
+                 histories: bool = False):
+        """histories=True keeps, per env, what the reference keeps for plots / statistics / custom plugins
+        (init_statistic_variables, utils.py:794-861): `self.histories()` -> cs_power / cs_current [E,C,T],
+        tr_overload [E,Tr,T], current_power_usage [E,T], filled row by row as the episode runs; `self.sim_step` is the
+        per-env step counter, `self.sim_minutes()` the minutes since each env's sim_date (`_step_date`, ev2gym_env.py:558)."""
         self.topo, self.num_envs, self.auto_reset = topo, num_envs, auto_reset
-        self.engine = BatchedEngine(topo, num_envs, reward=reward_function, state=state_function, device=device,
-                                    outputs=("reward", "status", "obs", "action_mask"))
+        hist = ("hist_cs_power", "hist_cs_current", "hist_tr_overload", "hist_usage") if histories else ()
+        self.engine = _ENGINE_CLS(topo, num_envs, reward=reward_function, state=state_function, device=device,
+                                  outputs=("reward", "status", "obs", "action_mask") + hist)
         self.engine.load_scenarios(scenarios)
         self._first = [(rank * num_envs + e) % len(scenarios) for e in range(num_envs)]
         self.obs_dim, self.n_actions = self.engine.D, topo.P
@@ -372,6 +378,17 @@ class EV2GymB200Vec:
 
     def state_tensors(self):
         return self.engine.state_tensors()
+
+    def histories(self):
+        return self.engine.histories()
+
+    @property
+    def sim_step(self):
+        return self.engine.state_tensors()["env_step"]
+
+    def sim_minutes(self):
+        """Minutes elapsed since each env's sim_date (the reference steps a datetime, ev2gym_env.py:558-561)."""
+        return self.sim_step * self.topo.timescale
 
 
 class EV2GymB200SB3Vec:

@@ -149,7 +149,9 @@ typedef struct {
  * `obs` and `action_mask` are updated IN PLACE: when a step is given the same buffer as the previous step (or as the
  * ev2b_reset before it), only the entries that can have changed are written (ports whose EV stayed, arrived or left,
  * the header, the price / forecast windows); a different pointer gets every entry rewritten.  So a caller that
- * overwrites such a buffer between two steps must hand in another buffer (or reset) -- reading it is always fine. */
+ * overwrites such a buffer between two steps must hand in another buffer (or reset) -- reading it is always fine.
+ * Rows of envs that were ALREADY finished when the step was called (status EV2B_ST_WAS_DONE: the reference raises an
+ * AssertionError there, ev2gym_env.py:343) are not touched: `obs` / `action_mask` keep whatever the buffer held. */
 typedef struct {
     double   *reward;        /* [E]     reward of this step                  ev2gym_env.py:430-432 */
     uint32_t *status;        /* [E]     EV2B_ST_* bits (done etc.)           ev2gym_env.py:460     */
@@ -164,6 +166,14 @@ typedef struct {
     double   *dep_cap;       /* [E,P]   its final battery level (kWh), NaN otherwise  (env.departing_evs)         */
     float    *port_energy;   /* [E,P]   ev.current_energy of this step (kWh)                       */
     double   *node_voltage;  /* [E,n_bus+1] |V| per node, slack first   env.node_voltage[:, t]  ev2gym_env.py:397 */
+    /* Per-episode histories (init_statistic_variables, utils.py:794-861; written by _update_power_statistics,
+     * ev2gym_env.py:520-556): the step that starts at t writes row t of every env, so after an episode the buffers hold
+     * what the reference keeps in env.cs_power[C,T], env.cs_current[C,T], env.tr_overload[Tr,T] and
+     * env.current_power_usage[T] -- time-major here (coalesced rows).  Rows of steps not yet run keep their old content. */
+    float    *hist_cs_power;     /* [E,T,C]  */
+    float    *hist_cs_current;   /* [E,T,C]  */
+    double   *hist_tr_overload;  /* [E,T,Tr] */
+    double   *hist_usage;        /* [E,T]    */
 } ev2b_step_out;
 
 /* Raw DEVICE pointers into the struct-of-arrays state, for zero-copy tensor views. */
@@ -238,8 +248,9 @@ int  ev2b_step_k(ev2b_handle *h, int k, int agent_kind, const void *actions_k, i
  * ev2b_step_k accepts the same kinds and calls this before every step. */
 int  ev2b_agent_actions(ev2b_handle *h, int agent_kind, double *actions_out, void *stream);
 
-/* Device-side auto-reset of every env whose episode is over: next scenario id =
- * (current id + n_envs) mod bank size.  For vectorised RL rollouts. */
+/* Device-side auto-reset of every env whose episode is over: next scenario id = (current id + stride) mod bank size,
+ * stride = n_envs mod bank size (1 if that is 0), increased until it is coprime to the bank size -- so consecutive
+ * episodes of an env walk the whole bank even when n_envs is a multiple of its size.  For vectorised RL rollouts. */
 int  ev2b_reset_done(ev2b_handle *h, float *obs0, void *stream);
 
 int  ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *out);

@@ -68,7 +68,9 @@ _OUT = {"reward": (np.float64, ()), "status": (np.uint32, ()), "obs": (np.float3
         "cs_power": (np.float32, ("C",)), "cs_current": (np.float32, ("C",)), "tr_power": (np.float64, ("Tr",)),
         "tr_overload": (np.float64, ("Tr",)), "total_costs": (np.float64, ()), "action_mask": (np.uint8, ("P",)),
         "dep_sat": (np.float64, ("P",)), "dep_cap": (np.float64, ("P",)), "port_energy": (np.float32, ("P",)),
-        "node_voltage": (np.float64, ("N",))}
+        "node_voltage": (np.float64, ("N",)), "hist_cs_power": (np.float32, ("T", "C")),
+        "hist_cs_current": (np.float32, ("T", "C")), "hist_tr_overload": (np.float64, ("T", "Tr")),
+        "hist_usage": (np.float64, ("T",))}
 
 
 def _spawn_mixin():
@@ -111,7 +113,7 @@ class EmuEngine(_spawn_mixin()):
             self.h = None
 
     def set_outputs(self, names):
-        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P, "N": self.topo.n_bus + 1}
+        dims = {"D": max(self.D, 1), "C": self.C_, "Tr": self.Tr, "P": self.P, "N": self.topo.n_bus + 1, "T": self.T}
         self.out: Dict[str, np.ndarray] = {}
         self._so = self._lib.StepOut()
         for n in names:

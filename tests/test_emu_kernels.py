@@ -506,3 +506,21 @@ def test_more_than_1023_ports_per_env(emu, kernel, monkeypatch):
                               kernel, G=2, monkeypatch=monkeypatch)
     assert eng.state()["env_kpi"][:, 11].min() > 1023          # invalid_actions: more than one step's worth of 10 bits
     eng.close()
+
+
+@pytest.mark.parametrize("kernel,n", [("percharger", 2), ("evlist", 2), ("evlist", 1)])
+def test_history_outputs_equal_the_oracles_histories(emu, kernel, n, monkeypatch):
+    """hist_cs_power / hist_cs_current / hist_tr_overload / hist_usage after an episode == what the reference keeps in
+    env.cs_power[C,T], env.cs_current[C,T], env.tr_overload[Tr,T], env.current_power_usage[T] (utils.py:794-861,
+    ev2gym_env.py:520-556; here: the oracle's restatement of them), for every env of the batch."""
+    topo, bank = _bank(24, n, 3, T=30)
+    hist = ("hist_cs_power", "hist_cs_current", "hist_tr_overload", "hist_usage")
+    eng, orc = _run_vs_oracle(emu, topo, bank, 4, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", "float32",
+                              kernel, G=2, outputs=OUT + hist, monkeypatch=monkeypatch)
+    E, C, T, Tr = 4, topo.C, topo.T, topo.Tr
+    assert _close(eng.out["hist_cs_power"].transpose(0, 2, 1), orc.arr["cs_power_hist"].reshape(E, C, T), 1e-5, 1e-6)
+    assert _close(eng.out["hist_cs_current"].transpose(0, 2, 1), orc.arr["cs_current_hist"].reshape(E, C, T), 1e-5, 1e-6)
+    assert _close(eng.out["hist_tr_overload"].transpose(0, 2, 1), orc.arr["tr_overload_hist"].reshape(E, -1, T)[:, :Tr], 1e-9, 1e-9)
+    assert _close(eng.out["hist_usage"], orc.arr["usage"].reshape(E, -1)[:, :T], 1e-9, 1e-9)
+    assert np.abs(eng.out["hist_cs_power"]).max() > 0
+    eng.close()

@@ -116,6 +116,34 @@ def test_vec_env_auto_reset():
     assert n_done == 64 and int(vec.state_tensors()["env_step"][0]) == 2
 
 
+def test_vec_env_histories_replay_reference_episode():
+    """EV2GymB200Vec(histories=True) on a recorded reference episode: after the episode the device-side histories equal
+    the reference's env.cs_power[C,T] / cs_current / tr_overload[Tr,T] / current_power_usage[T] (fixtures recorded by
+    tools/make_golden.py), the mask of a finished env is cleared by the auto reset, sim_minutes follows _step_date."""
+    import torch
+    from ev2gym_b200.env import EV2GymB200Vec
+    from ev2gym_b200.scenario import ScenarioPack
+    name = "loads_c20n2tr3_mixed_s11"
+    pack = ScenarioPack.load(f"{GOLDEN}/{name}.scenario.npz")
+    tr = np.load(f"{GOLDEN}/{name}.trace.npz")
+    E = 3
+    vec = EV2GymB200Vec(pack.topo, pack.scenarios, E, state_function=str(tr["state_fn"]), reward_function=str(tr["reward_fn"]),
+                        histories=True)
+    vec.reset()
+    T = tr["reward"].shape[0]
+    for t in range(T):
+        a = torch.tensor(np.tile(tr["actions"][t], (E, 1)), device="cuda")
+        assert int(vec.sim_minutes()[0]) == t * pack.topo.timescale
+        obs, r, done, info = vec.step(a)
+    assert bool(done.all()) and int(info["action_mask"].sum()) == 0
+    h = {k: v.cpu().numpy() for k, v in vec.histories().items()}
+    for e in range(E):
+        assert np.allclose(h["cs_power"][e], tr["cs_power"].T, rtol=1e-5, atol=1e-6)
+        assert np.allclose(h["cs_current"][e], tr["cs_current"].T, rtol=1e-5, atol=1e-6)
+        assert np.allclose(h["tr_overload"][e], tr["tr_overload"].T, rtol=1e-9, atol=1e-9)
+        assert np.allclose(h["current_power_usage"][e], tr["usage"][:T], rtol=1e-9, atol=1e-9)
+
+
 def test_sb3_style_vec_env_replays_reference_episode():
     """EV2GymB200SB3Vec (numpy VecEnv convention: step_async / step_wait, auto reset, terminal_observation) on a
     recorded ChargeAsFastAsPossible episode: per-step obs / reward / done, the terminal observation and the episode
