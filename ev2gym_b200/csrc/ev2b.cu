@@ -95,6 +95,7 @@ struct ev2b_handle {
     bool evl = false;                   // lists allocated, schedule built
     bool list_valid = true;             // occ_list / occ_n agree with the hot words of every env
     int evl_G = 4, evl_o[13] = {0};     // warps per env; smem map (v_stride, v_amp, ...)
+    int evl_tpb = kEvlThreads;          // threads per CTA: 128, or 32 (one env per CTA) for launches of more than one wave
     int n_sm = 148, n_sm_create = 148;
     bool evl_mix = false;               // EV2B_EVL_MIX=1 (tests): launches that ask for port_energy take step_kernel
     size_t evl_smem = 0;
@@ -123,7 +124,7 @@ struct ev2b_handle {
             evl_o[10] = take(8 * pp, 8); evl_o[11] = take(8 * pp, 8); evl_o[12] = take(8 * pp, 8);
         }
         evl_o[0] = (int)((off + 15) / 16 * 16);                    // stride
-        evl_smem = (size_t)evl_o[0] * (kEvlThreads / (32 * evl_G));
+        evl_smem = (size_t)evl_o[0] * (evl_tpb / (32 * evl_G));
     }
     // shared-memory map of step_kernel: byte offsets handed to the kernel through Params (constant bank)
     int so[15] = {0}, pre_stride = 0;
@@ -238,37 +239,38 @@ static cudaError_t opt_in_smem(ev2b_handle *h, K kern, size_t bytes) {
 // k_steps > 0: the KSTEP instantiation (p.k_steps steps in one launch; lean kernels only, see evl_kstep_ok)
 template <typename ActT>
 static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st, bool kstep = false) {
-    const int epb = kEvlThreads / (32 * h->evl_G);
+    const int epb = h->evl_tpb / (32 * h->evl_G);
     const unsigned grid = (unsigned)((p.env_end - p.env0 + epb - 1) / epb);
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = opt_in_smem(h, kern, h->evl_smem);
         if (e != cudaSuccess) return e;
-        EV2B_LAUNCH(kern, grid, kEvlThreads, h->evl_smem, st, p);
+        EV2B_LAUNCH(kern, grid, h->evl_tpb, h->evl_smem, st, p);
         return cudaGetLastError();
     };
     const int np = (h->cs_uniform && (h->np_uniform == 1 || h->np_uniform == 2)) ? h->np_uniform : 0;
     // HEAVY: statistics mode, the distribution grid, the dense per-port outputs
     const bool heavy = h->evl_heavy_layout() || p.out.dep_sat || p.out.dep_cap || p.out.port_energy || p.out.node_voltage;
-#define EV2B_EVL_DISPATCH(G)                                                          \
-    do {                                                                              \
-        if (heavy) {                                                                  \
-            if (kstep) return cudaErrorInvalidValue;                                  \
-            if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, true, false>);   \
-            if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, true, false>);   \
-            return go(evl_step_kernel<ActT, 0, false, G, true, false>);               \
-        }                                                                             \
-        if (kstep) {                                                                  \
-            if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, false, true>);   \
-            if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, false, true>);   \
-            return go(evl_step_kernel<ActT, 0, false, G, false, true>);               \
-        }                                                                             \
-        if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, false, false>);      \
-        if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, false, false>);      \
-        return go(evl_step_kernel<ActT, 0, false, G, false, false>);                  \
+#define EV2B_EVL_DISPATCH(G, TPB)                                                          \
+    do {                                                                                   \
+        if (heavy) {                                                                       \
+            if (kstep) return cudaErrorInvalidValue;                                       \
+            if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, true, false, TPB>);   \
+            if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, true, false, TPB>);   \
+            return go(evl_step_kernel<ActT, 0, false, G, true, false, TPB>);               \
+        }                                                                                  \
+        if (kstep) {                                                                       \
+            if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, false, true, TPB>);   \
+            if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, false, true, TPB>);   \
+            return go(evl_step_kernel<ActT, 0, false, G, false, true, TPB>);               \
+        }                                                                                  \
+        if (np == 1) return go(evl_step_kernel<ActT, 1, true, G, false, false, TPB>);      \
+        if (np == 2) return go(evl_step_kernel<ActT, 2, true, G, false, false, TPB>);      \
+        return go(evl_step_kernel<ActT, 0, false, G, false, false, TPB>);                  \
     } while (0)
-    if (h->evl_G == 1) EV2B_EVL_DISPATCH(1);
-    if (h->evl_G == 2) EV2B_EVL_DISPATCH(2);
-    EV2B_EVL_DISPATCH(4);
+    if (h->evl_G == 1 && h->evl_tpb == 32) EV2B_EVL_DISPATCH(1, 32);
+    if (h->evl_G == 1) EV2B_EVL_DISPATCH(1, kEvlThreads);
+    if (h->evl_G == 2) EV2B_EVL_DISPATCH(2, kEvlThreads);
+    EV2B_EVL_DISPATCH(4, kEvlThreads);
 #undef EV2B_EVL_DISPATCH
 }
 
@@ -498,10 +500,14 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
                 h->evl_G = h->E >= cap_warps / 2 ? 1 : (h->E >= cap_warps / 4 ? 2 : 4);
             }
             if (const char *gv = getenv("EV2B_EVL_G")) { const int v = atoi(gv); if (v == 1 || v == 2 || v == 4) h->evl_G = v; }
+            // one env per CTA when the launch is more than the machine holds at once (see evl_step_kernel)
+            h->evl_tpb = (h->evl_G == 1 && h->E > h->n_sm_create * (h->evl_heavy_layout() ? 16 : 28)) ? 32 : kEvlThreads;
+            if (const char *tv = getenv("EV2B_EVL_TPB")) { const int v = atoi(tv); if (v == kEvlThreads || (v == 32 && h->evl_G == 1)) h->evl_tpb = v; }
             if (const char *mv = getenv("EV2B_EVL_MIX")) h->evl_mix = atoi(mv) != 0 && !big;
             cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
             h->layout_evl();
-            while (h->evl_smem > 200 * 1024 && h->evl_G < 4) { h->evl_G *= 2; h->layout_evl(); }   // fewer envs per CTA
+            if (h->evl_smem > 200 * 1024 && h->evl_G == 1) { h->evl_tpb = 32; h->layout_evl(); }     // fewer envs per CTA
+            while (h->evl_smem > 200 * 1024 && h->evl_G < 4) { h->evl_G *= 2; h->evl_tpb = kEvlThreads; h->layout_evl(); }
             if (h->evl_smem > 200 * 1024) h->evl = false;          // does not fit: step_kernel takes every launch
         }
         if (!h->evl && big) {

@@ -35,7 +35,7 @@
 
 namespace ev2b {
 
-constexpr int kEvlThreads = 128;
+constexpr int kEvlThreads = 128;             // threads per CTA (a second instantiation with 32 serves multi-wave launches)
 constexpr unsigned kEvlGone = 0xFFFFu;       // staging mark: this EV left during the step
 // prefetch area of this kernel (doubles): [0,13) KPI sums, [13] charge_power_potential[t] (kPrePot), then
 constexpr int kEvlPotPrev = 14;              // charge_power_potential[t-1]
@@ -75,7 +75,7 @@ __device__ __forceinline__ double warp_sum8(const double (&q)[8], int lane) {
 // `bar.sync 1, 128` of warp 0, passed the emulator and HUNG on the B200 -- round 2, tests/test_gpu_evlist.py.)
 template <int G>
 __device__ __forceinline__ void evl_group_sync(int g) {
-    static_assert(G == 1 || G == 2 || G * 32 == kEvlThreads, "group sizes: one warp, two warps, or the whole CTA");
+    static_assert(G == 1 || G == 2 || G * 32 == kEvlThreads, "group sizes: one warp, two warps, or the whole 128-thread CTA");
     if (G == 1) { __syncwarp(); return; }
     if (G * 32 == kEvlThreads) { __syncthreads(); return; }
 #ifdef EV2B_SIMT_EMU
@@ -720,14 +720,18 @@ __device__ __forceinline__ void evl_reset_env(const Params &p, const int e, cons
 // synchronisation exists; from the second step on the env's rows are found in L1 / L2 instead of HBM and there is no
 // launch gap between steps.  Finished envs restart on their next scenario when p.auto_reset is set (= ev2b_reset_done).
 #ifndef EV2B_EVL_MINB
-#define EV2B_EVL_MINB 7       // resident CTAs per SM the lean instantiation is compiled for: 7 -> 72 registers per thread.
+#define EV2B_EVL_MINB 7       // resident 128-thread CTAs per SM the lean instantiation is compiled for: 7 -> 72 registers per thread.
                               // B200, c3 whole episodes, one warp per env: 8 (64 regs) 25.8 us, 7 (72) 23.3, 6 (80) 31.4 --
                               // 4096 envs are 1024 CTAs = 6.9 per SM, so 7 slots still hold the launch in one wave
 #endif
-template <typename ActT, int NP, bool UNI, int G, bool HEAVY, bool KSTEP>
-__global__ void __launch_bounds__(kEvlThreads, HEAVY ? 4 : EV2B_EVL_MINB) evl_step_kernel(const __grid_constant__ Params p) {
+// TPB = threads per CTA: 128 (4 / G envs per CTA), or 32 with one warp per env -- a launch of more CTAs than the machine
+// holds at once (c4: 8192 envs) ends with a shorter tail when the CTAs are single envs (B200, c4: 44.2 -> 40.9 us per
+// launch; c3, a one-wave launch: 22.6 -> 23.5, so it keeps 128; profiles/r2_ab_cta_size.jsonl).
+template <typename ActT, int NP, bool UNI, int G, bool HEAVY, bool KSTEP, int TPB>
+__global__ void __launch_bounds__(TPB, (HEAVY ? 4 : EV2B_EVL_MINB) * kEvlThreads / TPB) evl_step_kernel(const __grid_constant__ Params p) {
+    static_assert(TPB == kEvlThreads || (TPB == 32 && G == 1), "CTA shapes: 128 threads, or one warp = one env");
     EV2B_DYNAMIC_SMEM(smem_raw);
-    constexpr int GT = 32 * G, EPB = kEvlThreads / GT;
+    constexpr int GT = 32 * G, EPB = TPB / GT;
     const int tid = threadIdx.x;
     const int g = tid / GT, gtid = tid - g * GT;
     const int e = p.env0 + (int)blockIdx.x * EPB + g;

@@ -524,3 +524,19 @@ def test_history_outputs_equal_the_oracles_histories(emu, kernel, n, monkeypatch
     assert _close(eng.out["hist_usage"], orc.arr["usage"].reshape(E, -1)[:, :T], 1e-9, 1e-9)
     assert np.abs(eng.out["hist_cs_power"]).max() > 0
     eng.close()
+
+
+@pytest.mark.parametrize("shape", [0, 1, 3])
+def test_evlist_one_env_per_cta(emu, shape, monkeypatch):
+    """The 32-thread instantiation (one warp = one env = one CTA; chosen for launches of more than one wave, forced here
+    with EV2B_EVL_TPB=32) computes the same thing, incl. the k-step kernel with device-side reset."""
+    C, n, Tr, E, reward, state, adt = SHAPES[shape]
+    monkeypatch.setenv("EV2B_EVL_TPB", "32")
+    topo, bank = _bank(C, n, Tr)
+    eng, _ = _run_vs_oracle(emu, topo, bank, E, reward, state, adt, "evlist", G=1, monkeypatch=monkeypatch)
+    assert eng.kernel_launches() == (0, topo.T, 0)
+    eng.reset()
+    eng.step_k(topo.T + 5, agent="uniform", seed=3, auto_reset=True)
+    st = eng.state()
+    assert (st["env_step"] == 5).all()
+    eng.close()

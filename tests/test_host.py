@@ -135,7 +135,7 @@ def test_step_kernels_keep_their_register_budget():
     checked = 0
     for name, usage in res.items():
         lean_step = "step_kernelIfLi2ELb1ELi128ELi8ELb0ELb0" in name          # c3: float actions, 2 ports, no optional outputs
-        evl = re.search(r"evl_step_kernelI[fd]Li\dELb[01]ELi\dELb([01])ELb[01]EEEvNS_6ParamsE", name)   # <ActT, NP, UNI, G, HEAVY, KSTEP>
+        evl = re.search(r"evl_step_kernelI[fd]Li\dELb[01]ELi\dELb([01])ELb[01]ELi\d+EEEvNS_6ParamsE", name)   # <ActT, NP, UNI, G, HEAVY, KSTEP, TPB>
         if not (lean_step or evl):
             continue
         reg, stack = int(re.search(r"REG:(\d+)", usage).group(1)), int(re.search(r"STACK:(\d+)", usage).group(1))
