@@ -96,7 +96,7 @@ struct ev2b_handle {
     bool list_valid = true;             // occ_list / occ_n agree with the hot words of every env
     int evl_G = 4, evl_o[13] = {0};     // warps per env; smem map (v_stride, v_amp, ...)
     int evl_tpb = kEvlThreads;          // threads per CTA: 128, or 32 (one env per CTA) for launches of more than one wave
-    int n_sm = 148, n_sm_create = 148;
+    int n_sm_create = 148;              // SMs of the device (launch-shape decisions at create time)
     bool evl_mix = false;               // EV2B_EVL_MIX=1 (tests): launches that ask for port_energy take step_kernel
     size_t evl_smem = 0;
     std::set<const void *> smem_opted;  // kernels whose dynamic shared-memory limit has been raised on this device
@@ -236,7 +236,7 @@ static cudaError_t opt_in_smem(ev2b_handle *h, K kern, size_t bytes) {
     return e;
 }
 
-// k_steps > 0: the KSTEP instantiation (p.k_steps steps in one launch; lean kernels only, see evl_kstep_ok)
+// kstep: the KSTEP instantiation (p.k_steps steps in one launch; lean kernels only, see ev2b_step_k)
 template <typename ActT>
 static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st, bool kstep = false) {
     const int epb = h->evl_tpb / (32 * h->evl_G);
@@ -504,7 +504,6 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
             h->evl_tpb = (h->evl_G == 1 && h->E > h->n_sm_create * (h->evl_heavy_layout() ? 16 : 28)) ? 32 : kEvlThreads;
             if (const char *tv = getenv("EV2B_EVL_TPB")) { const int v = atoi(tv); if (v == kEvlThreads || (v == 32 && h->evl_G == 1)) h->evl_tpb = v; }
             if (const char *mv = getenv("EV2B_EVL_MIX")) h->evl_mix = atoi(mv) != 0 && !big;
-            cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
             h->layout_evl();
             if (h->evl_smem > 200 * 1024 && h->evl_G == 1) { h->evl_tpb = 32; h->layout_evl(); }     // fewer envs per CTA
             while (h->evl_smem > 200 * 1024 && h->evl_G < 4) { h->evl_G *= 2; h->evl_tpb = kEvlThreads; h->layout_evl(); }

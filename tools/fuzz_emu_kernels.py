@@ -49,9 +49,9 @@ def trial(k, rng):
     outs = ["reward", "status"] + [o for o in ("obs", "tr_power", "tr_overload", "cs_power", "cs_current", "total_costs",
                                                "action_mask") if rng.random() < 0.7]
     os.environ["EV2B_KERNEL"], os.environ["EV2B_EVL_G"] = "evlist", str(G)
-    os.environ["EV2B_EVL_STAGE"] = "1" if rng.random() < 0.2 else "0"
+    os.environ["EV2B_EVL_TPB"] = "32" if (G == 1 and rng.random() < 0.4) else "128"     # one env per CTA / four warps per CTA
     desc = dict(k=k, C=C, n=n, ragged=ragged, Tr=Tr, T=T, E=E, G=G, reward=reward, state=state, adt=str(adt), outs=outs,
-                stage=os.environ["EV2B_EVL_STAGE"])
+                tpb=os.environ["EV2B_EVL_TPB"])
     bank = sample_bank(topo, 3, seed=int(rng.integers(1 << 30)), min_stay=int(rng.integers(1, 6)),
                        occupancy=float(rng.uniform(0.1, 0.9)))
     eng = emu_engine.EmuEngine(topo, E, reward=reward, state=state, outputs=tuple(outs))
@@ -107,11 +107,16 @@ def stateful_trial(k, rng):
     Tr = int(rng.integers(1, min(C_, 4) + 1))
     T = int(rng.integers(10, 26))
     S = int(rng.integers(1, 4))
-    E = S * int(rng.integers(1, 4))                  # E % S == 0: the auto reset ((scn + E) mod S) keeps every env on its scenario
+    E = S * int(rng.integers(1, 4))                  # every scenario of the bank is in use from the start
     G = int(rng.choice([1, 2, 4]))
     reward = REWARDS[rng.integers(len(REWARDS) - 1)]
     state = STATES[rng.integers(len(STATES) - 1)]
-    os.environ["EV2B_KERNEL"], os.environ["EV2B_EVL_G"], os.environ["EV2B_EVL_STAGE"] = "evlist", str(G), "0"
+    os.environ["EV2B_KERNEL"], os.environ["EV2B_EVL_G"] = "evlist", str(G)
+    os.environ["EV2B_EVL_TPB"] = "32" if (G == 1 and rng.random() < 0.4) else "128"
+    import math
+    stride = E % S or 1                              # ev2b_reset_done: next scenario = (current + stride) mod S  (include/ev2b.h)
+    while S > 1 and math.gcd(stride, S) != 1:
+        stride += 1
     topo = Topology.uniform(C=C_, n_ports=n, Tr=Tr, T=T)
     bank = sample_bank(topo, S, seed=int(rng.integers(1 << 30)), min_stay=int(rng.integers(1, 6)),
                        occupancy=float(rng.uniform(0.2, 0.9)))
@@ -181,9 +186,14 @@ def stateful_trial(k, rng):
             if op == "step_v6":
                 graveyard.append(eng.out)
                 eng.set_outputs(base)
-        if orc.done.any():                           # finished envs restart on their scenario, on both sides
+        if orc.done.any():                           # finished envs restart on their NEXT scenario, on both sides
             eng.reset_done()
-            oracle_reset(np.nonzero(orc.done)[0])
+            fin = np.nonzero(orc.done)[0]
+            for e in fin:
+                ids[e] = (ids[e] + stride) % S
+                orc._scn_ptrs[e] = C.pointer(orc._scn[ids[e]].c)      # (env i < S was built on scenario i)
+            assert np.array_equal(eng.state()["env_scn"], ids), (desc, it, "scenario ids after the auto reset")
+            oracle_reset(fin)
     eng.close()
     return desc
 
