@@ -87,9 +87,10 @@ def occupancy_aware_bytes_per_env_step(topo, obs_dim, series_len, tuple_len, n_c
 
 
 def source_sha():
-    """Hash of the CUDA sources the library is built from: stamps profiles (roofline_traffic.json) to a build."""
+    """Hash of the device code the step kernels are built from (csrc/ev2b_device.cuh, ev2b_evlist.cuh, ev2b_math.h):
+    stamps profiles (roofline_traffic.json) to a build of the kernel they describe."""
     h = hashlib.sha256()
-    for f in ("ev2b.cu", "ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_spawn.cuh", "ev2b_math.h"):
+    for f in ("ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_math.h"):
         p = os.path.join(ROOT, "ev2gym_b200", "csrc", f)
         if os.path.exists(p):
             h.update(open(p, "rb").read())

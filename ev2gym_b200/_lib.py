@@ -137,10 +137,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found and ev2gym_b200/csrc/libev2b.so is missing or stale")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "ev2b.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:       # several ranks may find the library stale at once: one builds, the
+        fcntl.flock(lock, fcntl.LOCK_EX)             # others wait and then find it fresh; the .so appears atomically
+        if force or needs_build():
+            tmp = LIB_PATH + f".tmp{os.getpid()}"
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "ev2b.cu")]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            subprocess.check_call(cmd)
+            os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
