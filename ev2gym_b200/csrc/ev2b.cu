@@ -94,7 +94,7 @@ struct ev2b_handle {
     // event-driven step kernel (ev2b_evlist.cuh); chosen per handle by EV2B_KERNEL=evlist, used for the launches it covers
     bool evl = false;                   // lists allocated, schedule built
     bool list_valid = true;             // occ_list / occ_n agree with the hot words of every env
-    int evl_G = 4, evl_o[13] = {0};     // warps per env; smem map (v_stride, v_amp, ...)
+    int evl_G = 4, evl_o[14] = {0};     // warps per env; smem map (v_stride, v_amp, ...)
     int evl_tpb = kEvlThreads;          // threads per CTA: 128, or 32 (one env per CTA) for launches of more than one wave
     int n_sm_create = 148;              // SMs of the device (launch-shape decisions at create time)
     bool evl_mix = false;               // EV2B_EVL_MIX=1 (tests): launches that ask for port_energy take step_kernel
@@ -123,6 +123,7 @@ struct ev2b_handle {
         if ((dims.flags & EV2B_F_STATS) && pp) {                   // dsat, dcal, dcyc
             evl_o[10] = take(8 * pp, 8); evl_o[11] = take(8 * pp, 8); evl_o[12] = take(8 * pp, 8);
         }
+        evl_o[13] = take(16, 16);                                  // hdr
         evl_o[0] = (int)((off + 15) / 16 * 16);                    // stride
         evl_smem = (size_t)evl_o[0] * (evl_tpb / (32 * evl_G));
     }
@@ -186,7 +187,7 @@ struct ev2b_handle {
         p.v_stride = evl_o[0]; p.v_amp = evl_o[1]; p.v_pot = evl_o[2]; p.v_csP = evl_o[3]; p.v_pre = evl_o[4];
         { int lg = 0; while ((2 << lg) * Tr <= 32) ++lg; p.tr_lg = lg; }
         p.v_wsum = evl_o[5]; p.v_trp = evl_o[6]; p.v_stage = evl_o[7]; p.v_occ = evl_o[8]; p.v_pfv = evl_o[9];
-        p.v_dsat = evl_o[10]; p.v_dcal = evl_o[11]; p.v_dcyc = evl_o[12];
+        p.v_dsat = evl_o[10]; p.v_dcal = evl_o[11]; p.v_dcyc = evl_o[12]; p.v_hdr = evl_o[13];
         {   // auto-reset stride: E mod S (so that with E < S consecutive episodes walk the bank), made coprime to S --
             // when E is a multiple of S that is 1: every env visits every scenario instead of replaying its first one
             int st = S > 0 ? E % S : 0;

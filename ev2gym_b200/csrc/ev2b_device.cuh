@@ -137,6 +137,7 @@ struct Params {
     int tr_lg;                 // 2^tr_lg lanes share one transformer in the CSR sums (largest with 2^tr_lg * Tr <= 32)
     int v_stride, v_amp, v_pot, v_csP, v_pre, v_wsum, v_stage, v_occ;   // byte offsets inside one env's block
     int v_trp, v_pfv, v_dsat, v_dcal, v_dcyc;   // HEAVY instantiation only (grid / statistics mode)
+    int v_hdr;                 // 16 B: env_step / env_scn / occ_n published by warp 0 (whole-CTA groups)
     int mask_full;             // 1: out.action_mask does not hold last step's rows (evl_step_kernel rewrites them)
     int scn_stride;            // auto-reset: next scenario = (current + scn_stride) mod S, gcd(scn_stride, S) = 1
     int k_steps, auto_reset;   // evl_step_kernel<..., KSTEP = true>: steps per launch, device-side reset of finished envs

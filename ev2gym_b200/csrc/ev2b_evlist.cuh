@@ -71,8 +71,8 @@ __device__ __forceinline__ double warp_sum8(const double (&q)[8], int lane) {
 // reserves all 16 barriers for the CTA, which capped the SM at 3 resident CTAs -- ncu: 21 % warps active).  G = 4: the
 // group is the CTA: __syncthreads.  `arrive` does not wait: the idle path of G = 2 uses it so that the warp with nothing
 // to do leaves at once while warp 0 still learns that it has read the env's step counter before advancing it.  (With
-// G = 4 the other warps wait at the CTA barrier instead: `bar.arrive 1, 128` by three warps that then exit, paired with a
-// `bar.sync 1, 128` of warp 0, passed the emulator and HUNG on the B200 -- round 2, tests/test_gpu_evlist.py.)
+// G = 4 warp 0 reads the env scalars and publishes them through shared memory instead, see evl_env_step: `bar.arrive 1, 128`
+// by three warps that then exit, paired with a `bar.sync 1, 128` of warp 0, passed the emulator and HUNG on the B200.)
 template <int G>
 __device__ __forceinline__ void evl_group_sync(int g) {
     static_assert(G == 1 || G == 2 || G * 32 == kEvlThreads, "group sizes: one warp, two warps, or the whole 128-thread CTA");
@@ -87,8 +87,7 @@ __device__ __forceinline__ void evl_group_sync(int g) {
 // The idle path's "I have read the step counter" of a warp other than warp 0.
 template <int G>
 __device__ __forceinline__ void evl_group_arrive(int g) {
-    if (G == 1) return;
-    if (G * 32 == kEvlThreads) { __syncthreads(); return; }
+    if (G == 1 || G * 32 == kEvlThreads) return;      // (whole-CTA groups publish the env scalars through shared memory instead)
 #ifdef EV2B_SIMT_EMU
     simt::bar_arrive(1 + g, 32 * G);
 #else
@@ -202,9 +201,25 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     // volatile: read exactly once.  Warp 0 uses n_old in the KPI update while the group's last warp is storing the new
     // occ_n; a plain load may be re-issued by the compiler at that later use (it was, under register pressure, with
     // G = 4: invalid_actions went wrong on the B200 while every other quantity was right -- round 2, test_gpu_evlist).
-    const int t = *reinterpret_cast<const volatile int *>(p.env_step + e);
-    const int s = *reinterpret_cast<const volatile int *>(p.env_scn + e);
-    const int n_old = *reinterpret_cast<const volatile int *>(p.occ_n + e);
+    int t, s, n_old;
+    if (G * 32 == kEvlThreads) {
+        // The group is the whole CTA: warp 0 reads the scalars and publishes them through shared memory, so the other
+        // warps never look at env_step themselves and the idle path needs no handshake before warp 0 advances it (every
+        // thread meets at THIS __syncthreads; compute-sanitizer's synccheck rejected the earlier variant, in which the
+        // other warps synchronised at a different call site and exited).
+        int *hdr = reinterpret_cast<int *>(sm + p.v_hdr);
+        if (gtid == 0) {
+            hdr[0] = *reinterpret_cast<const volatile int *>(p.env_step + e);
+            hdr[1] = *reinterpret_cast<const volatile int *>(p.env_scn + e);
+            hdr[2] = *reinterpret_cast<const volatile int *>(p.occ_n + e);
+        }
+        __syncthreads();
+        t = hdr[0]; s = hdr[1]; n_old = hdr[2];
+    } else {
+        t = *reinterpret_cast<const volatile int *>(p.env_step + e);
+        s = *reinterpret_cast<const volatile int *>(p.env_scn + e);
+        n_old = *reinterpret_cast<const volatile int *>(p.occ_n + e);
+    }
     if (gw == 0) {                                     // KPI sums, potential[t], potential[t-1]: need nothing but e
         if (lane <= kPrePot) cp_async8(pre + lane, lane < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + lane : p.env_pot + e);
         else if (lane == kEvlPotPrev) cp_async8(pre + lane, p.env_pot_prev + e);
@@ -262,7 +277,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         }
     }
     const bool idle = n_old == 0 && nArr == 0;        // nobody connected, nobody arriving: warp 0 alone, no barriers
-    if (idle && gw != 0) { if (!KSTEP) evl_group_arrive<G>(g); return tq; }
+    if (idle && gw != 0) { if (!KSTEP && G * 32 != kEvlThreads) evl_group_arrive<G>(g); return tq; }
     const int NT = idle ? 32 : GT;                    // threads that share the fills below
     uint8_t *mask_row = p.out.action_mask ? p.out.action_mask + (size_t)e * p.P : nullptr;
     float *h_csP = p.out.hist_cs_power ? p.out.hist_cs_power + ((size_t)e * p.T + t) * p.C : nullptr;     // row t of the histories
@@ -657,7 +672,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     case EV2B_KPI_INVALID_ACTIONS: delta = (double)(p.P - n_old); break;   // every empty port  ev_charger.py:137-140
     default: delta = 1.0; break;                                           // EV2B_KPI_STEPS
     }
-    if (idle && !KSTEP) evl_group_sync<G>(g);         // the group's other warps have read env_step (they only arrive)
+    if (idle && !KSTEP && G * 32 != kEvlThreads) evl_group_sync<G>(g);   // the group's other warp has read env_step (it only arrives)
     if (lane < EV2B_KPI_COUNT) {
         p.env_kpi[(size_t)e * EV2B_KPI_COUNT + lane] = pre[lane] + delta;
     } else if (lane == 13) {
