@@ -319,6 +319,10 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
         if (lut >= 0) eta = ev2b_div_c(lut_get((charging ? p.luts_c : p.luts_d) + (size_t)lut * p.lut_len, p.lut_len, fabs(rint(amps))), 100.0, 0.01);
         else eta = (em == 0xFFFFu) ? __ldg(charging ? &sp->eta_c : &sp->eta_d) : ev2b_div_c((double)em, 1000.0, 0.001);
     }
+    // (Round 2 also measured a formulation with the two directions as warp-uniform blocks of straight-line code -- selects
+    //  instead of per-lane branches, a warp of one direction skipping the other block: bit-identical, 10 % SLOWER on the
+    //  B200 (c3 26.2 vs 23.7 us, c4 46.7 vs 40.7): the extra live results of both blocks cost more registers than the
+    //  removed reconvergence points saved.  profiles/r2_ab_model_formulation.jsonl)
     if (charging) {                                                                // EV._charge  ev.py:240-355
         const unsigned tsm = hz >> 16;
         const double ts = (tsm == 0xFFFFu) ? __ldg(&sp->ts) : ev2b_div_c((double)tsm, 1000.0, 0.001);

@@ -69,7 +69,7 @@ __device__ __forceinline__ double spawn_randint(const SpawnParams &sp, unsigned 
 __global__ void spawn_sessions_kernel(const Params p, const SpawnParams sp) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.S * p.P) return;
-    const int s = (int)(idx / p.P), port = (int)(idx - (long long)s * p.P);
+    const int s = (int)(idx / p.P);                                        // (idx = s * P + spawner port)
     SessRec *out = sp.raw + (size_t)idx * p.Smax;
     const int wd0 = sp.start[3 * s], m0 = sp.start[3 * s + 1] * 60 + sp.start[3 * s + 2];
     int n = 0, next_free = 0;                                             // ports are free at t = 0, 1, 2

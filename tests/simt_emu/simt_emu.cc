@@ -131,6 +131,7 @@ uint64_t shfl(unsigned mask, uint64_t bits, int src_lane) {
 unsigned ballot(unsigned mask, int pred) {
     Warp &w = g_warps[g_cur->tid >> 5];
     const unsigned lane = g_cur->tid & 31u;
+    if (mask == (1u << lane)) return pred ? mask : 0u;       // a collective of one (__activemask() of this emulator): nothing to gather
     w.pred[lane] = pred != 0;
     warp_gather(mask);
     unsigned r = 0;

@@ -79,6 +79,9 @@ template <typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsig
     const int lane = (int)(threadIdx.x & 31u); return __simt_shfl(mask, v, lane + (int)d < 32 ? lane + (int)d : lane);
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred) { return simt::ballot(mask, pred); }
+// The emulator runs one fiber at a time: the "converged" set a thread can rely on is itself (opportunistic warp-level
+// decisions -- "does ANY lane need this block?" -- stay correct with that answer: each lane asks for what it needs).
+static inline unsigned __activemask() { return 1u << (threadIdx.x & 31u); }
 static inline int __any_sync(unsigned mask, int pred) { return simt::ballot(mask, pred) != 0; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
