@@ -75,16 +75,17 @@ EXPORTS = ("ev2b_abi_version", "ev2b_last_error", "ev2b_create", "ev2b_destroy",
            "ev2b_load_scenarios", "ev2b_n_scenarios", "ev2b_reset", "ev2b_step", "ev2b_step_host",
            "ev2b_reset_done", "ev2b_state_view_get", "ev2b_launch_count", "ev2b_episode_stats", "ev2b_step_k",
            "ev2b_agent_actions", "ev2b_kernel_launches", "ev2b_set_spawn_tables", "ev2b_resample_sessions",
-           "ev2b_read_sessions")
+           "ev2b_read_sessions", "ev2b_read_setpoints")
 
 
 class SpawnTablesView(C.Structure):
     _fields_ = [("workplace", C.c_int32), ("heterogeneous", C.c_int32), ("empty_ports_at_end", C.c_int32),
                 ("min_stay_steps", C.c_int32), ("n_models", C.c_int32), ("n_luts", C.c_int32),
+                ("power_setpoint_enabled", C.c_int32), ("reserved", C.c_int32),
                 ("spawn_multiplier", C.c_double), ("desired_frac", C.c_double), ("min_battery_capacity", C.c_double),
                 ("min_emergency_battery_capacity", C.c_double), ("ts_multiplier", C.c_double),
                 ("homog_ts", C.c_double), ("homog_eta_c", C.c_double), ("homog_eta_d", C.c_double),
-                ("arrival_week", _pd), ("arrival_weekend", _pd), ("req_energy_mean", _pd), ("stay_mean", _pd),
+                ("power_setpoint_flexibility", C.c_double), ("arrival_week", _pd), ("arrival_weekend", _pd), ("req_energy_mean", _pd), ("stay_mean", _pd),
                 ("model_prob", _pd), ("model_B", _pd), ("model_pmax_ac", _pd), ("model_pmax_dis", _pd),
                 ("model_pmin_ac", _pd), ("model_pmin_dis", _pd), ("model_phases", _pi), ("model_lut", _pi), ("luts", _pd)]
 
@@ -93,10 +94,10 @@ def spawn_tables_view(t):
     """`ev2b_spawn_tables` over a scenario.SpawnTables; returns (view, arrays to keep alive)."""
     import numpy as np
     v, keep = SpawnTablesView(), []
-    for k in ("workplace", "heterogeneous", "empty_ports_at_end", "min_stay_steps"):
+    for k in ("workplace", "heterogeneous", "empty_ports_at_end", "min_stay_steps", "power_setpoint_enabled"):
         setattr(v, k, int(getattr(t, k)))
     for k in ("spawn_multiplier", "desired_frac", "min_battery_capacity", "min_emergency_battery_capacity",
-              "ts_multiplier", "homog_ts", "homog_eta_c", "homog_eta_d"):
+              "ts_multiplier", "homog_ts", "homog_eta_c", "homog_eta_d", "power_setpoint_flexibility"):
         setattr(v, k, float(getattr(t, k)))
     v.n_models, v.n_luts = int(len(t.model_prob)), int(np.asarray(t.luts).reshape(-1, 101).shape[0])
     for k, ptr, dt in [("arrival_week", _pd, np.float64), ("arrival_weekend", _pd, np.float64),
@@ -118,6 +119,8 @@ def declare_spawn(L):
     L.ev2b_resample_sessions.restype = C.c_int
     L.ev2b_resample_sessions.argtypes = [C.c_void_p, C.c_uint64, _pi, C.c_void_p]
     L.ev2b_read_sessions.restype = C.c_int
+    L.ev2b_read_setpoints.restype = C.c_int
+    L.ev2b_read_setpoints.argtypes = [C.c_void_p, C.c_int, _pd]
     L.ev2b_read_sessions.argtypes = [C.c_void_p, C.c_int, C.c_int, _pi, _pi, _pi, _pi, _pd, _pd, _pd, _pd]
 
 

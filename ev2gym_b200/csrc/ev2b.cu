@@ -102,7 +102,7 @@ struct ev2b_handle {
     std::set<const void *> smem_opted;  // kernels whose dynamic shared-memory limit has been raised on this device
     DevBuf<uint16_t> occ_list; DevBuf<int> occ_n; DevBuf<unsigned> arr_list;
     // device-side scenario sampling (ev2b_spawn.cuh): tables, scratch, the EV-model spec table that replaces the bank's
-    bool spawn_ready = false, spawn_specs_live = false;
+    bool spawn_ready = false, spawn_specs_live = false, spawn_setpoints = false;
     int spawn_smax = 0, spawn_M = 0;
     SpawnParams spawn_p{};
     DevBuf<double> sp_arr_week, sp_arr_weekend, sp_req, sp_stay, sp_cdf, sp_B, sp_luts, sp_pot_kw;
@@ -1133,6 +1133,18 @@ int ev2b_set_spawn_tables(ev2b_handle *h, const ev2b_spawn_tables *t) {
     sp.M = M; sp.workplace = t->workplace; sp.heterogeneous = t->heterogeneous; sp.empty_ports_at_end = t->empty_ports_at_end;
     sp.min_stay_steps = t->min_stay_steps; sp.timescale = h->dims.timescale;
     sp.spawn_multiplier = t->spawn_multiplier; sp.desired_frac = t->desired_frac; sp.min_battery_capacity = t->min_battery_capacity;
+    h->spawn_setpoints = t->power_setpoint_enabled != 0;
+    sp.setpoint_mult = 100.0 + t->power_setpoint_flexibility;
+    {   // charging_stations[0].get_min_charge_power() / get_max_power()   ev_charger.py:251-255
+        const CsStatic &c0 = h->cs_h[0];
+        sp.min_cs_power = c0.imin * c0.veff[1] * std::sqrt((double)c0.phases) / 1000.0;
+        sp.max_cs_power = c0.imax * c0.veff[1] * std::sqrt((double)c0.phases) / 1000.0;
+    }
+    sp.median_window = 5 * std::max(1, 15 / h->dims.timescale);
+    sp.setpoint_threads = 128;                       // 2 * threads * T doubles of shared memory must fit
+    while (sp.setpoint_threads > 1 && (size_t)(2 * sp.setpoint_threads + 2) * h->T * 8 > 200 * 1024) sp.setpoint_threads /= 2;
+    if (h->spawn_setpoints && (size_t)(2 * sp.setpoint_threads + 2) * h->T * 8 > 200 * 1024)
+        return h->fail(EV2B_E_LIMIT, "set_spawn_tables: episode too long for the setpoint generator");
     unsigned k = 0xFFFFu;
     sp.homog_ts_milli = milli(t->homog_ts, &k) ? k : 0xFFFFu;
     sp.homog_eta_c_milli = milli(t->homog_eta_c, &k) ? k : 0xFFFFu;
@@ -1183,6 +1195,18 @@ int ev2b_resample_sessions(ev2b_handle *h, uint64_t seed, const int32_t *start, 
     const size_t sm = ((size_t)(h->T + 2) * ((h->P + 31) / 32) + h->T + 3) * 4;
     CUDA_TRY(h, opt_in_smem(h, spawn_schedule_kernel, sm));
     EV2B_LAUNCH(spawn_schedule_kernel, (unsigned)h->S, blk, sm, st, p, sp);
+    if (h->spawn_setpoints) {                          // generate_power_setpoints from the new sessions  utils.py:664-757
+        const size_t sm2 = (size_t)(2 * sp.setpoint_threads + 2) * h->T * 8;
+        CUDA_TRY(h, opt_in_smem(h, spawn_setpoints_kernel, sm2));
+        EV2B_LAUNCH(spawn_setpoints_kernel, (unsigned)h->S, sp.setpoint_threads, sm2, st, p, sp);
+        h->launches += 1;
+        if (h->obs_static.p && h->dims.state_kind == EV2B_STATE_V2G_GRID) {   // (the only state whose static part holds setpoints)
+            Params q = p; q.obs_static = nullptr;
+            const size_t n = (size_t)h->S * (h->T + 1) * h->W;
+            EV2B_LAUNCH(obs_static_kernel, (unsigned)std::min<size_t>(1024, (n + 255) / 256), 256, 0, st, q, h->obs_static.p);
+            h->launches += 1;
+        }
+    }
     EV2B_LAUNCH(spawn_invalidate_envs_kernel, (unsigned)((h->E + blk - 1) / blk), blk, 0, st, p);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 4;
@@ -1224,6 +1248,17 @@ int ev2b_read_sessions(ev2b_handle *h, int scn, int cap, int32_t *port, int32_t 
         ++n;
     }
     return (int)rows.size();
+}
+
+int ev2b_read_setpoints(ev2b_handle *h, int scn, double *out) {
+    if (!h || !out) return EV2B_E_ARG;
+    if (h->S == 0 || scn < 0 || scn >= h->S) return h->fail(EV2B_E_ARG, "read_setpoints: scenario %d out of range", scn);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    std::vector<EnvT> et((size_t)h->T);
+    CUDA_TRY(h, cudaMemcpy(et.data(), h->env_t.p + (size_t)scn * h->T, et.size() * sizeof(EnvT), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < h->T; ++t) out[t] = et[t].setpoint;
+    return EV2B_OK;
 }
 
 int ev2b_state_view_get(ev2b_handle *h, ev2b_state_view *v) {

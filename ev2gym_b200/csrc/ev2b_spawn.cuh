@@ -16,13 +16,15 @@
 //   * stay ~ N(m, m/5) hours -> steps + 1, at least min_time_of_stay                                   :236-252
 //   * EV model ~ registrations; efficiency round(1 - (u + 1e-5) / 20, 3), transition_soc round(0.9 - (u + 1e-5) / 5, 3)
 //   * the arriving EV takes the FIRST FREE PORT of its charger, not the port the spawner drew          ev_charger.py:273
-// Only the sessions are drawn here; the scenario's time series (prices, loads, PV, limits, forecasts) stay those of the
-// bank entry, and power_setpoints are NOT regenerated (generate_power_setpoints, utils.py:664-757, derives them from the
-// sessions: with power_setpoint_enabled the bank's setpoints no longer match the resampled sessions).
+// The scenario's time series (prices, loads, PV, limits, forecasts) stay those of the bank entry.  power_setpoints are
+// derived from the sessions by the reference (generate_power_setpoints, utils.py:664-757: every EV's required energy is
+// spread over its stay with price-weighted normal noise, pushed inside the power limits, summed, median-smoothed), so with
+// power_setpoint_enabled they are regenerated here too (spawn_setpoints_kernel), with the same distributional parity.
 //
 // Kernels: spawn_sessions_kernel (thread per scenario x spawner port: the sequential loop over t with a counter-based
 // RNG) -> spawn_assign_kernel (thread per scenario x charger: first-free-port replay, packs the SessRec table)
-// -> spawn_schedule_kernel (CTA per scenario: arrival buckets of the event-driven kernel, EnvT.arr0 / n_arr).
+// -> spawn_schedule_kernel (CTA per scenario: arrival buckets of the event-driven kernel, EnvT.arr0 / n_arr)
+// -> spawn_setpoints_kernel (CTA per scenario, only with power_setpoint_enabled).
 #pragma once
 #include "ev2b_device.cuh"
 
@@ -41,13 +43,16 @@ struct SpawnParams {
     unsigned homog_ts_milli, homog_eta_c_milli, homog_eta_d_milli;   // homogeneous config: the fixed encodings
     unsigned seed_lo, seed_hi;
     int cap_per_scn;                                // arr_list entries reserved per scenario (P * Smax)
+    double setpoint_mult;                           // 100 + power_setpoint_flexiblity                  utils.py:680-681
+    double min_cs_power, max_cs_power;              // charging_stations[0].get_min_charge_power() / get_max_power()  :683-684
+    int setpoint_threads, median_window;            // CTA size of spawn_setpoints_kernel; 5 * max(1, 15 // timescale)  :754-757
     // scratch: what the spawner drew, per (scenario, spawner port)
     SessRec *raw; int *raw_n;                       // [S][P][Smax], [S][P]
     // outputs
     SessRec *sess; EnvT *env_t; unsigned *arr_list; int *n_sess;   // n_sess: [S] sessions per scenario
 };
 
-// splitmix64 of (seed, counter): the uniform generator.  counter = ((scenario * P + port) * T + t) * 8 + draw
+// splitmix64 of (seed, counter): the uniform generator.  counter = ((scenario * P + port) * T + t) * 16 + draw
 __device__ __forceinline__ double spawn_uniform(const SpawnParams &sp, unsigned long long counter) {
     unsigned long long z = (((unsigned long long)sp.seed_hi << 32) | sp.seed_lo) + (counter + 1ull) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -237,6 +242,83 @@ __global__ void spawn_schedule_kernel(const Params p, const SpawnParams sp) {
             for (int w = 0; w < (port >> 5); ++w) rank += __popc(bits[(size_t)ta * W + w]);
             sp.arr_list[base + off[ta] + rank] = (unsigned)port | ((unsigned)k << 16);
         }
+    }
+}
+
+// generate_power_setpoints (utils.py:664-757) for one scenario (one CTA).  Every thread takes the sessions of some ports:
+// the EV's required energy is spread over [t_arr + 1, t_dep) with |N(1 - price, min price)| weights, loads below the
+// minimum / above the maximum power are pushed to the next slot (at most 11 sweeps), and the result is added to the
+// thread's OWN row of partial setpoints; the rows are then summed in thread order (deterministic: the same seed gives the
+// same setpoints) and median-smoothed.  Shared memory: [NT][T] partial setpoints, [NT][T] the session being spread,
+// [T] normalised prices, [T] the sum.
+__global__ void spawn_setpoints_kernel(const Params p, const SpawnParams sp) {
+    EV2B_DYNAMIC_SMEM(sm_raw);
+    const int s = blockIdx.x, NT = blockDim.x, T = p.T, tid = threadIdx.x;
+    double *acc = reinterpret_cast<double *>(sm_raw);                     // [NT][T]
+    double *vec = acc + (size_t)NT * T;                                   // [NT][T]
+    double *price = vec + (size_t)NT * T;                                 // [T]
+    double *total = price + T;                                            // [T]
+    for (int i = tid; i < NT * T; i += NT) acc[i] = 0.0;
+    if (tid == 0) {                                                       // prices = |charge_prices[0]| / max  :676-677
+        double mx = 0.0;
+        for (int t = 0; t < T; ++t) { price[t] = fabs(sp.env_t[(size_t)s * T + t].cp); mx = fmax(mx, price[t]); }
+        for (int t = 0; t < T; ++t) price[t] = price[t] / mx;
+    }
+    __syncthreads();
+    double *mine = acc + (size_t)tid * T, *sh = vec + (size_t)tid * T;
+    for (int port = tid; port < p.P; port += NT) {
+        const SessRec *f = sp.sess + ((size_t)s * p.P + port) * p.Smax;
+        for (int k = 0; k < p.Smax; ++k) {
+            const int ta = (int)(f[k].hot.x & 0xFFFFu);
+            if (ta == kNoArrival) break;
+            const int td = min((int)(int16_t)(f[k].hot.x >> 16), T), w0 = ta + 1, L = td - ta - 1;   // window [t + 2, t_dep), t = ta - 1
+            if (L <= 0 || w0 >= T) continue;
+            const EvSpec &es = p.spec[f[k].hot.z & 0xFFFFu];
+            const double required = (es.B - f[k].cap0) * sp.setpoint_mult / 100.0;          // :692-693
+            const double minp = fmax(es.pmin_ac, sp.min_cs_power), maxp = fmin(es.pmax_ac, sp.max_cs_power);   // :694-695
+            double scale = price[w0];
+            for (int i = 1; i < L; ++i) scale = fmin(scale, price[w0 + i]);
+            const unsigned long long c = (1ull << 62) + (((unsigned long long)s * p.P + port) * (unsigned long long)T + ta) * 2ull * T;
+            double sum = 0.0;
+            for (int i = 0; i < L; ++i) {                                 // :698-703
+                sh[i] = fabs(spawn_normal(sp, c + 2ull * i, 1.0 - price[w0 + i], scale));
+                sum += sh[i];
+            }
+            for (int i = 0; i < L; ++i) sh[i] = sh[i] / sum * required * 60.0 / (double)sp.timescale;   // :704-705
+            for (int step = 0; step <= 10; ++step) {                      // :708-733
+                double mn = 1e300, mx = -1e300;
+                for (int i = 0; i < L; ++i) { if (sh[i] != 0.0) mn = fmin(mn, sh[i]); mx = fmax(mx, sh[i]); }
+                if (!(mn < minp || mx > maxp)) break;
+                for (int i = 0; i < L; ++i) {
+                    const int nxt = i == L - 1 ? 0 : i + 1;
+                    if (sh[i] < minp && sh[i] > 0.0) { const double mv = sh[i]; sh[i] = 0.0; sh[nxt] += mv; }
+                    else if (sh[i] > maxp) { const double mv = sh[i] - maxp; sh[i] = maxp; sh[nxt] += mv; }
+                }
+            }
+            for (int i = 0; i < L; ++i) mine[w0 + i] += sh[i];            // :735
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += NT) {
+        double v = 0.0;
+        for (int r = 0; r < NT; ++r) v += acc[(size_t)r * T + t];
+        total[t] = v;
+    }
+    __syncthreads();
+    const int half = sp.median_window / 2;                                // median_smoothing  :652-661
+    for (int t = tid; t < T; t += NT) {
+        const int lo = max(0, t - half), hi = min(T, t + half + 1), n = hi - lo;
+        // the median of n <= window + 1 values by rank counting (no sorting buffer): the k-th smallest is the value with
+        // k smaller-or-equal-and-earlier values before it
+        double m1 = 0.0, m2 = 0.0;
+        const int k1 = (n - 1) / 2, k2 = n / 2;                           // numpy: mean of the two middle values for even n
+        for (int i = lo; i < hi; ++i) {
+            int rank = 0;
+            for (int j = lo; j < hi; ++j) rank += (total[j] < total[i] || (total[j] == total[i] && j < i)) ? 1 : 0;
+            if (rank == k1) m1 = total[i];
+            if (rank == k2) m2 = total[i];
+        }
+        sp.env_t[(size_t)s * T + t].setpoint = 0.5 * (m1 + m2);
     }
 }
 

@@ -168,6 +168,13 @@ class SpawnMixin:
         out.update({k: v[:n].copy() for k, v in d.items()})
         return out
 
+    def read_setpoints(self, scn: int) -> np.ndarray:
+        """env.power_setpoints of scenario `scn` as the device bank holds them (regenerated by resample_sessions when the
+        spawn tables say power_setpoint_enabled)."""
+        out = np.zeros(self.topo.T, dtype=np.float64)
+        self._check(self.L.ev2b_read_setpoints(self.h, int(scn), out.ctypes.data_as(_lib._pd)), "ev2b_read_setpoints")
+        return out
+
 
 class BatchedEngine(SpawnMixin):
     def __init__(self, topo: Topology, n_envs: int, reward=None, state=None, device: int = 0,

@@ -238,6 +238,8 @@ def spawn_tables_from_env(env, starts=None) -> SpawnTables:
         ts_multiplier=float(ev.get("transition_soc_multiplier", 1)),
         empty_ports_at_end=int(bool(env.empty_ports_at_end_of_simulation)),
         heterogeneous=int(bool(cfg["heterogeneous_ev_specs"])),
+        power_setpoint_enabled=int(bool(cfg.get("power_setpoint_enabled", False))),
+        power_setpoint_flexibility=float(cfg.get("power_setpoint_flexiblity", 0.0)),
         model_prob=prob, model_B=np.array(B, dtype=np.float64), model_pmax_ac=np.array(pac, dtype=np.float64),
         model_pmax_dis=np.array(pdis, dtype=np.float64), model_pmin_ac=np.array(pmin_ac, dtype=np.float64),
         model_pmin_dis=np.array(pmin_dis, dtype=np.float64), model_phases=np.array(phases, dtype=np.int32),

@@ -309,6 +309,8 @@ class SpawnTables:
     model_phases: np.ndarray        # [M] int32
     model_lut: np.ndarray           # [M] int32 row of `luts` or -1 (scalar efficiencies drawn per EV, :290-296)
     luts: np.ndarray                # [L,101] percent; the reference uses the same curve for both directions (:288)
+    power_setpoint_enabled: int = 0      # config["power_setpoint_enabled"]: setpoints are derived from the sessions (utils.py:664-757)
+    power_setpoint_flexibility: float = 0.0   # config["power_setpoint_flexiblity"], percent
     homog_ts: float = 1.0           # homogeneous config: transition_soc, charge / discharge efficiency
     homog_eta_c: float = 1.0
     homog_eta_d: float = 1.0
@@ -317,7 +319,7 @@ class SpawnTables:
 
     _SCALARS = ("workplace", "spawn_multiplier", "min_stay_steps", "desired_frac", "min_battery_capacity",
                 "min_emergency_battery_capacity", "ts_multiplier", "empty_ports_at_end", "heterogeneous", "homog_ts",
-                "homog_eta_c", "homog_eta_d")
+                "homog_eta_c", "homog_eta_d", "power_setpoint_enabled", "power_setpoint_flexibility")
     _ARRAYS = ("arrival_week", "arrival_weekend", "req_energy_mean", "stay_mean", "model_prob", "model_B", "model_pmax_ac",
                "model_pmax_dis", "model_pmin_ac", "model_pmin_dis", "model_phases", "model_lut", "luts", "start")
 

@@ -264,8 +264,12 @@ typedef struct {
     int32_t empty_ports_at_end;        /* empty_ports_at_end_of_simulation                                 :254-256   */
     int32_t min_stay_steps;            /* config["ev"]["min_time_of_stay"] // timescale                    :495-496   */
     int32_t n_models, n_luts;          /* EV models; efficiency curves (lut_len entries each, percent)                */
+    int32_t power_setpoint_enabled;    /* config["power_setpoint_enabled"]: regenerate power_setpoints from the sessions
+                                          (generate_power_setpoints, utils.py:664-757); 0: the bank's setpoints stay      */
+    int32_t reserved;
     double  spawn_multiplier, desired_frac, min_battery_capacity, min_emergency_battery_capacity, ts_multiplier;
     double  homog_ts, homog_eta_c, homog_eta_d;   /* homogeneous config: transition_soc, efficiencies                 */
+    double  power_setpoint_flexibility;           /* config["power_setpoint_flexiblity"] (percent)        utils.py:680 */
     const double *arrival_week, *arrival_weekend;  /* [96] percent per quarter of an hour                  :515, 522  */
     const double *req_energy_mean, *stay_mean;     /* [48] by half hour of arrival (kWh, hours)            :203, 231  */
     const double *model_prob, *model_B, *model_pmax_ac, *model_pmax_dis, *model_pmin_ac, *model_pmin_dis;   /* [n_models] */
@@ -279,8 +283,8 @@ int  ev2b_set_spawn_tables(ev2b_handle *h, const ev2b_spawn_tables *tables);
 /* Re-draws the EV sessions of EVERY scenario of the loaded bank on the device (counter-based RNG keyed by `seed`,
  * scenario, port and step: the same seed gives the same sessions on any GPU), keeping each scenario's time series.
  * start: HOST [n_scenarios][3] weekday (0 = Monday), hour, minute of sim_date at reset() for every scenario.
- * Afterwards every env reads as finished until it is reset.  Stream-ordered; three small kernels.
- * power_setpoints are not regenerated (see ev2gym_b200/csrc/ev2b_spawn.cuh). */
+ * Afterwards every env reads as finished until it is reset.  Stream-ordered; a handful of small kernels.
+ * With tables->power_setpoint_enabled the power setpoints are regenerated from the new sessions as well. */
 int  ev2b_resample_sessions(ev2b_handle *h, uint64_t seed, const int32_t *start, void *stream);
 
 /* The sessions of scenario `scn` as the bank currently holds them (arrival order), HOST arrays of capacity `cap`:
@@ -289,6 +293,9 @@ int  ev2b_resample_sessions(ev2b_handle *h, uint64_t seed, const int32_t *start,
  * NaN where the value comes from an efficiency curve or from the spec.  Synchronous. */
 int  ev2b_read_sessions(ev2b_handle *h, int scn, int cap, int32_t *port, int32_t *t_arr, int32_t *t_dep, int32_t *model,
                         double *cap0, double *ts, double *eta_c, double *eta_d);
+
+/* env.power_setpoints of scenario `scn` as the bank currently holds them: HOST out[T] (kW).  Synchronous. */
+int  ev2b_read_setpoints(ev2b_handle *h, int scn, double *out);
 
 /* get_statistics(env) for every env (ev2gym/utilities/utils.py:12-123, incl. EV.get_battery_degradation
  * ev.py:442-521 and the AFAP bound ev.py:407-440).  Needs EV2B_F_STATS.  out: DEVICE [E, EV2B_STAT_COUNT]

@@ -106,10 +106,26 @@ def _check_sample(make_engine, name, reward, state, n_rounds, ks_bar, steps_vs_o
         vals = np.unique(np.concatenate([dev[col], ref[col]]))
         hd = np.array([(dev[col] == v).mean() for v in vals]); hr = np.array([(ref[col] == v).mean() for v in vals])
         assert 0.5 * np.abs(hd - hr).sum() < 2.0 * ks_bar, (col, hd, hr)
-    # the same seed reproduces the same sessions
+    # ---- (2b) power setpoints regenerated from the sampled sessions (generate_power_setpoints, utils.py:664-757)
+    ref_sp = np.stack([sc.setpoint[:T] for sc in pack.scenarios])
+    dev_sp = np.stack([eng.read_setpoints(s) for s in range(S)])
+    if tab.power_setpoint_enabled:
+        assert np.all(dev_sp >= 0.0) and np.all(np.isfinite(dev_sp))
+        # energy under the curve per scenario, shape over the day (mean profile), and the pooled values
+        assert abs(dev_sp.sum(1).mean() - ref_sp.sum(1).mean()) <= 4.0 * ref_sp.sum(1).std() / np.sqrt(S) + 0.04 * ref_sp.sum(1).mean(), \
+            ("setpoint energy", dev_sp.sum(1).mean(), ref_sp.sum(1).mean())
+        prof_d, prof_r = dev_sp.mean(0), ref_sp.mean(0)
+        assert np.abs(prof_d - prof_r).sum() / prof_r.sum() < 0.25, ("mean setpoint profile", np.abs(prof_d - prof_r).sum() / prof_r.sum())
+        assert _ks(dev_sp[dev_sp > 0], ref_sp[ref_sp > 0]) < 2.0 * ks_bar, ("setpoint values", _ks(dev_sp[dev_sp > 0], ref_sp[ref_sp > 0]))
+        assert abs((dev_sp > 0).mean() - (ref_sp > 0).mean()) < 0.05, "share of steps with a setpoint"
+    else:
+        assert np.array_equal(dev_sp, ref_sp), "setpoints stay the bank's when the config does not derive them"
+    # the same seed reproduces the same sessions (and setpoints)
     eng.resample_sessions(seed=1234)
     again = eng.read_sessions(0)
     assert all(np.array_equal(again[k], first[k], equal_nan=True) for k in first)
+    if n_rounds == 1:
+        assert np.array_equal(eng.read_setpoints(0), dev_sp[0])
     # ---- (3) an episode on the sampled sessions == the oracle on the sessions read back
     if steps_vs_oracle:
         E = S
@@ -128,7 +144,9 @@ def _check_sample(make_engine, name, reward, state, n_rounds, ks_bar, steps_vs_o
                         desired=tab.desired_frac * tab.model_B[m],
                         ts=np.where(np.isnan(d["ts"]), tab.homog_ts, d["ts"]), mult=np.full(len(m), tab.ts_multiplier),
                         eta_c=np.where(np.isnan(d["eta_c"]), 1.0, d["eta_c"]), eta_d=np.where(np.isnan(d["eta_d"]), 1.0, d["eta_d"]))
-            scns.append(Scenario(charge_price=base.charge_price, discharge_price=base.discharge_price, setpoint=base.setpoint,
+            setp = np.array(base.setpoint, dtype=np.float64)
+            setp[:T] = eng.read_setpoints(s)
+            scns.append(Scenario(charge_price=base.charge_price, discharge_price=base.discharge_price, setpoint=setp,
                                  tr_infl=base.tr_infl, tr_solar=base.tr_solar, tr_max_power=base.tr_max_power,
                                  tr_min_power=base.tr_min_power, tr_load_fc=base.tr_load_fc, tr_pv_fc=base.tr_pv_fc,
                                  dr_start=base.dr_start, dr_end=base.dr_end, dr_cap=base.dr_cap, dr_count=base.dr_count,
