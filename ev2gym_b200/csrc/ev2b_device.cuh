@@ -180,10 +180,13 @@ __device__ __forceinline__ double lut_get(const double *lut, int lut_len, double
 }
 
 #ifdef EV2B_SIMT_EMU
+__device__ __forceinline__ void prefetch_l2(const void *) {}
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) { simt::cp_async(smem_dst, gmem_src, 8); }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) { simt::cp_async(smem_dst, gmem_src, 16); }
 __device__ __forceinline__ void cp_async_wait_all() { simt::cp_async_wait_all(); }
 #else
+// HBM -> L2 without a destination register: the later load of the same sector finds it in L2.
+__device__ __forceinline__ void prefetch_l2(const void *gmem) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem)); }
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -203,6 +206,13 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// Hides a value from the optimiser (it must materialise x and may assume nothing about it); nothing is emitted.
+#if defined(__CUDA_ARCH__)
+#define EV2B_OPAQUE_F64(x) asm volatile("" : "+d"(x))
+#else
+#define EV2B_OPAQUE_F64(x) ((void)0)
+#endif
 
 template <bool UNI>
 __device__ __forceinline__ const CsStatic &cs_of(const Params &p, int c) {
@@ -343,10 +353,15 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
             // (round 2: ptxas turned the round-1 `if (dz != 0) ratio = dz / maxd` into a SELECT, so the saturated lanes --
             //  half of the charging lanes of the bench workload -- still ran the division and 98 % of the warps called its
             //  slow path, 5.5 % of the kernel's instructions (profiles/r2c_evl_g1_ncu_busy_lines.txt).  Those lanes now
-            //  divide maxd / maxd, which stays on the fast path, and discard the quotient.)
+            //  divide maxd / maxd, which stays on the fast path, and discard the quotient.  The numerator goes through an
+            //  empty asm: without it the optimiser sees that the saturated lanes never use the quotient, drops the select
+            //  and divides dz / maxd in every lane again -- 18 197 of 18 604 warp-iterations of the busiest c3 step still
+            //  called the slow path, 5.8 % of the instructions: profiles/r2g_evl_lines_busiest.txt.)
             const double dz = pilot - maxd;
             const bool sat = dz == 0.0 && maxd != 0.0;
-            const double quot = (sat ? maxd : dz) / maxd;
+            double num = sat ? maxd : dz;
+            EV2B_OPAQUE_F64(num);
+            const double quot = num / maxd;
             const double ratio = sat ? 0.0 : quot;
             const double pts = ts + ratio * (ts - 1.0);
             double nsoc;

@@ -171,6 +171,17 @@ __device__ __forceinline__ void evl_obs_clear(const Params &p, float *obs_row, i
 // pair is not needed); `actions` = the action tensor of this step, `first_it` = first step of the launch (only then may
 // the caller's obs / mask buffers need a full rewrite).  Returns the env's step counter after the call (T + 1: the env
 // was already finished).
+// Starts the HBM -> L2 transfer of the state one EV's thread will load (hot words, battery level, energy exchanged, the
+// action): issued one loop iteration ahead (and for the first iteration from the prologue), so that the dependent gather
+// list entry -> port state, the longest wait of the EV loop, finds its sectors in L2.
+template <typename ActT>
+__device__ __forceinline__ void evl_prefetch_ev(const Params &p, const ActT *actions, size_t ip) {
+    prefetch_l2(p.hot + ip);
+    prefetch_l2(p.cap + ip);
+    prefetch_l2(p.exch + ip);
+    if (p.agent_kind == EV2B_AGENT_EXTERNAL) prefetch_l2(actions + ip);
+}
+
 template <typename ActT, int NP, bool UNI, int G, bool HEAVY, bool KSTEP>
 __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, const int e, const int g, const int gtid,
                                             const ActT *actions, const bool first_it) {
@@ -220,6 +231,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         s = *reinterpret_cast<const volatile int *>(p.env_scn + e);
         n_old = *reinterpret_cast<const volatile int *>(p.occ_n + e);
     }
+    if (gtid < n_old) evl_prefetch_ev<ActT>(p, actions, (size_t)e * p.P + first);
     if (gw == 0) {                                     // KPI sums, potential[t], potential[t-1]: need nothing but e
         if (lane <= kPrePot) cp_async8(pre + lane, lane < kPrePot ? p.env_kpi + (size_t)e * EV2B_KPI_COUNT + lane : p.env_pot + e);
         else if (lane == kEvlPotPrev) cp_async8(pre + lane, p.env_pot_prev + e);
@@ -335,9 +347,10 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     evl_group_sync<G>(g);
 
     // ---- EV: one thread per connected EV ------------------------------------------------------------------------
+    int port = (int)first;
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
-        const int port = i == gtid ? (int)first : (int)lst[i];
+        const int port_next = i + GT < n_old ? (int)lst[i + GT] : -1;    // next iteration's entry, and what to prefetch for it
         const size_t ip = (size_t)e * p.P + port;
         const uint4 h = p.hot[ip];
         double cv = p.cap[ip];
@@ -345,6 +358,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         const double a = agent_action<ActT>(p, actions, ip, t);
         const unsigned hx = NP == 2 ? p.hot[ip ^ 1].x : 0u;
         const double am_raw = NP == 2 ? agent_action<ActT>(p, actions, ip ^ 1, t) : 0.0;   // same 32 B sector as `a`
+        if (port_next >= 0) evl_prefetch_ev<ActT>(p, actions, (size_t)e * p.P + port_next);
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
         const CsStatic &cs = cs_of<UNI>(p, c);
         // Sigma over the charger's occupied ports, in port order (python sum())   ev_charger.py:137-149
@@ -460,6 +474,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
             pot[port] = potv;
             occ[port] = (unsigned char)flags;
         }
+        port = port_next;
     }
     evl_group_sync<G>(g);
 
@@ -514,6 +529,17 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         const CsStatic &cs = cs_of<UNI>(p, c);
         const int p0 = NP > 0 ? c * NP : cs.port_off, n = NP > 0 ? NP : cs.n_ports;
         double rP = 0, rA = 0, rPot = 0;
+        if (NP == 2 && !(HEAVY && p.stats)) {
+            // both ports of the charger at once: one 2-byte load of the flags, three 16-byte loads of the staged values
+            // (entries of empty ports are stale and never enter a sum); same additions in the same order as below
+            const unsigned f2 = reinterpret_cast<const uint16_t *>(occ)[c];
+            const double2 w = reinterpret_cast<const double2 *>(pw)[c], a2 = reinterpret_cast<const double2 *>(amp)[c],
+                          o2 = reinterpret_cast<const double2 *>(pot)[c];
+            if (f2 & 0x001u) { rP += w.x; rA += a2.x; rPot += o2.x; }
+            if (rA - 0.0001 > cs.imax) overflow = true;
+            if (f2 & 0x100u) { rP += w.y; rA += a2.y; rPot += o2.y; }
+            if (rA - 0.0001 > cs.imax) overflow = true;
+        } else
 #pragma unroll
         for (int j = 0; j < n; ++j) {
             const unsigned f = occ[p0 + j];
@@ -656,22 +682,22 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         }
     }
     const double dsp = setpoint - usage;                                  // utils.py:37-44
-    double delta;
-    switch (lane) {
-    case EV2B_KPI_TOTAL_REWARD: delta = reward; break;
-    case EV2B_KPI_TOTAL_PROFITS: delta = costs; break;
-    case EV2B_KPI_ENERGY_CHARGED: delta = q[EvlCharged]; break;
-    case EV2B_KPI_ENERGY_DISCHARGED: delta = q[EvlDischarged]; break;
-    case EV2B_KPI_TR_OVERLOAD: delta = ovsum; break;
-    case EV2B_KPI_EVS_SERVED: delta = (double)n_dep; break;
-    case EV2B_KPI_SAT_SUM: delta = q[EvlSatSum]; break;
-    case EV2B_KPI_TRACKING_ERROR: delta = dsp * dsp; break;
-    case EV2B_KPI_ENERGY_TRACKING_ERROR: delta = fabs(dsp); break;
-    case EV2B_KPI_TRACKER_VIOLATION: delta = usage > setpoint ? usage - setpoint : 0.0; break;
-    case EV2B_KPI_EVS_SPAWNED: delta = (double)nArr; break;
-    case EV2B_KPI_INVALID_ACTIONS: delta = (double)(p.P - n_old); break;   // every empty port  ev_charger.py:137-140
-    default: delta = 1.0; break;                                           // EV2B_KPI_STEPS
-    }
+    // lane k keeps quantity k.  A chain of selects on purpose: a switch (lane) compiles to thirteen one-lane paths that
+    // the warp walks one after the other (75 instructions per env-step on the B200, 11 % of an idle step:
+    // profiles/r2g_evl_lines_idle.txt); every value below is warp-uniform and already computed.
+    double delta = 1.0;                                                              // EV2B_KPI_STEPS
+    delta = lane == EV2B_KPI_TOTAL_REWARD ? reward : delta;
+    delta = lane == EV2B_KPI_TOTAL_PROFITS ? costs : delta;
+    delta = lane == EV2B_KPI_ENERGY_CHARGED ? q[EvlCharged] : delta;
+    delta = lane == EV2B_KPI_ENERGY_DISCHARGED ? q[EvlDischarged] : delta;
+    delta = lane == EV2B_KPI_TR_OVERLOAD ? ovsum : delta;
+    delta = lane == EV2B_KPI_EVS_SERVED ? (double)n_dep : delta;
+    delta = lane == EV2B_KPI_SAT_SUM ? q[EvlSatSum] : delta;
+    delta = lane == EV2B_KPI_TRACKING_ERROR ? dsp * dsp : delta;
+    delta = lane == EV2B_KPI_ENERGY_TRACKING_ERROR ? fabs(dsp) : delta;
+    delta = lane == EV2B_KPI_TRACKER_VIOLATION ? (usage > setpoint ? usage - setpoint : 0.0) : delta;
+    delta = lane == EV2B_KPI_EVS_SPAWNED ? (double)nArr : delta;
+    delta = lane == EV2B_KPI_INVALID_ACTIONS ? (double)(p.P - n_old) : delta;        // every empty port  ev_charger.py:137-140
     if (idle && !KSTEP && G * 32 != kEvlThreads) evl_group_sync<G>(g);   // the group's other warp has read env_step (it only arrives)
     if (lane < EV2B_KPI_COUNT) {
         p.env_kpi[(size_t)e * EV2B_KPI_COUNT + lane] = pre[lane] + delta;

@@ -49,7 +49,7 @@ def main():
     for r, l in zip(body, lines):
         inst[l] += int(r[ci] or 0); smp[l] += int(r[si] or 0); thr[l] += int(r[ti] or 0)
     srcdir = os.path.dirname(os.path.abspath(so))
-    srcs = {f: open(os.path.join(srcdir, f)).read().splitlines() for f in ("ev2b_device.cuh", "ev2b_math.h", "ev2b.cu")
+    srcs = {f: open(os.path.join(srcdir, f)).read().splitlines() for f in ("ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_math.h", "ev2b.cu")
             if os.path.exists(os.path.join(srcdir, f))}
     ti_, ts_ = sum(inst.values()), sum(smp.values())
     print(f"total warp-instructions {ti_}, stall samples {ts_}")
