@@ -16,8 +16,11 @@ LIB_PATH = os.environ.get("EV2B_LIB") or os.path.join(CSRC, "libev2b.so")   # EV
 SOURCES = [os.path.join(CSRC, f) for f in ("ev2b.cu", "ev2b_device.cuh", "ev2b_evlist.cuh", "ev2b_spawn.cuh", "ev2b_math.h")] + \
           [os.path.join(os.path.dirname(_HERE), "include", "ev2b.h")]
 
+# No -split-compile: nvcc's parallel optimisation splits the translation unit differently from run to run (same sources,
+# same flags: 14.6 or 17.8 MB of cubin, 48 or 120 bytes of spill stack in evl_step_kernel), and the step kernel's time
+# moved by +-5 % with it on the B200 (profiles/r2_ab_build_modes.jsonl).  One thread: ~3 min, the same binary every time.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "-split-compile", "0", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off"]
+              "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off"]
 
 _pd, _pi, _pf = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float)
 _pl, _pu, _pb = C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)

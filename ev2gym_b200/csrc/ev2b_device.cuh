@@ -63,14 +63,23 @@ struct CsStatic {            // one per charger; ev_charger.py:41-75 + derived c
     double pad3;
 };
 
-struct EvSpec {              // de-duplicated EV model; ev.py:45-113
-    double B, pmax_ac, pmin_ac, pmax_dis, pmin_dis, bmin, bmin_em, desired, mult;
-    double ts, eta_c, eta_d; // used when the per-session milli encodings are 0xFFFF
+struct alignas(16) EvSpec {  // de-duplicated EV model; ev.py:45-113
+    // 16-byte pairs: EV.step loads a pair with one instruction, and picks the pair of the action's direction by address
+    // ({pmin, pmax} and {ts, mult} when charging, {pmin_dis, pmax_dis} and {bmin, bmin_em} when discharging), so the loads
+    // of a step are all in flight together instead of one dependent cache round trip per field.
+    double B, rB;            // rB = RN(1/B)
+    double pmin_ac, pmax_ac;
+    double pmin_dis, pmax_dis;
+    double ts, mult;         // ts, eta_c, eta_d: used when the per-session milli encodings are 0xFFFF
+    double bmin, bmin_em;
+    double eta_c, eta_d;
+    double desired, pad0;
     int    ev_phases, lut;   // lut < 0: scalar efficiencies
-    double rB;               // RN(1/B)
-    double pad[2];
+    double pad1;
 };
 static_assert(sizeof(EvSpec) == 128, "EvSpec must be 128 B");
+static_assert(offsetof(EvSpec, pmin_dis) == offsetof(EvSpec, pmin_ac) + 16 && offsetof(EvSpec, bmin) == offsetof(EvSpec, ts) + 16,
+              "the discharging pair follows the charging pair");
 
 // "hot" words of the session currently (or last) connected to a port: 16 B, read every step.
 //   w.x = t_arr (i16) | t_dep (i16) << 16
@@ -286,6 +295,12 @@ __global__ void obs_static_kernel(const Params p, float *table) {
     }
 }
 
+// Loads of the EV model's fields in EV.step: 1 = one batch up front, 0 = at their points of use (pairs), 2 = a batch only in
+// the instantiations with registers to spare (statistics / grid); measured in profiles/r2_ab_spec_loads.jsonl.
+#ifndef EV2B_SPEC_BATCH
+#define EV2B_SPEC_BATCH 2
+#endif
+
 // ---- A2: EV.step for one work item ------------------------------------------------------------
 // a = normalised action (non-zero), cap = battery level, hz/hw = hot words z/w of the session.
 // Returns through (energy, act_amps, cap); result = the EV saw non-zero amps (ev.py:158).
@@ -296,29 +311,46 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
     energy = 0.0; act_amps = 0.0; em_cross = false;
     const double action = ev2b_div_c(rint(a * 100000.0), 100000.0, 1e-5);          // round(action, 5)  ev_charger.py:157
     if (action == 0.0) return false;
+    // Everything the step needs of the EV's model, requested here in one batch (four 16-byte / 8-byte loads in flight
+    // together): the kernels are bound by the latency of dependent loads, and field-by-field loads at their points of
+    // use cost one L1 / L2 round trip each (round 2, profiles/r2i_evl_lines_busiest.txt: 26 % of the long-scoreboard
+    // stalls of evl_step_kernel sat on them).
     const EvSpec *sp = p.spec + (hz & 0xFFFFu);
+    const bool pos = action > 0.0;
+    constexpr bool BATCH = EV2B_SPEC_BATCH == 1 || (EV2B_SPEC_BATCH == 2 && STATS);
+    double2 Bv, lim, par;
+    int2 pl;
+    if (BATCH) {
+        Bv = __ldg(reinterpret_cast<const double2 *>(&sp->B));                                // B, 1/B
+        pl = __ldg(reinterpret_cast<const int2 *>(&sp->ev_phases));                           // ev_phases, lut
+        lim = __ldg(reinterpret_cast<const double2 *>(pos ? &sp->pmin_ac : &sp->pmin_dis));   // pmin, pmax of the direction
+        par = __ldg(reinterpret_cast<const double2 *>(pos ? &sp->ts : &sp->bmin));            // (ts, mult) | (bmin, bmin_em)
+    }
     const double veff_cs = cs.veff[cs.phases];
     double amps;
-    if (action > 0.0) {                                                            // ev_charger.py:167-170
+    if (pos) {                                                                     // ev_charger.py:167-170
         amps = action * cs.imax;
         if (amps < cs.imin - 0.01) amps = 0.0;
     } else {                                                                       // ev_charger.py:183-186
         amps = action * cs.imax_dis_abs;
         if (amps > cs.imin_dis - 0.01) amps = cs.imin_dis;
     }
-    if (amps > 0.0) {                                                              // ev.py:151-152
-        const double pmin = __ldg(&sp->pmin_ac);
-        if (pmin != 0.0 && amps < pmin * 1000.0 / veff_cs) amps = 0.0;
-    } else if (amps < 0.0) {                                                       // ev.py:153-154
-        const double pmin = __ldg(&sp->pmin_dis);
-        if (pmin != 0.0 && amps > pmin * 1000.0 / veff_cs) amps = 0.0;
+    if (!BATCH) lim = __ldg(reinterpret_cast<const double2 *>(pos ? &sp->pmin_ac : &sp->pmin_dis));
+    if (lim.x != 0.0) {                                                            // ev.py:151-154
+        const double thr = lim.x * 1000.0 / veff_cs;
+        if (amps > 0.0 ? amps < thr : (amps < 0.0 && amps > thr)) amps = 0.0;
     }
     if (amps == 0.0) return false;
-    const int evph = __ldg(&sp->ev_phases);
+    if (!BATCH) {
+        Bv = __ldg(reinterpret_cast<const double2 *>(&sp->B));
+        pl = __ldg(reinterpret_cast<const int2 *>(&sp->ev_phases));
+        par = __ldg(reinterpret_cast<const double2 *>(pos ? &sp->ts : &sp->bmin));
+    }
+    const int evph = pl.x;
     const int ph = cs.phases < evph ? cs.phases : evph;                            // ev.py:169
     const double veff = cs.veff[ph], rveff = cs.rveff[ph];
-    const int lut = __ldg(&sp->lut);
-    const double B = __ldg(&sp->B), rB = __ldg(&sp->rB);
+    const int lut = pl.y;
+    const double B = Bv.x, rB = Bv.y;
     // charge / discharge efficiency: a scalar, or dict.get(np.round(amps), 1) / 100 resp. dict.get(abs(np.round(amps)), 1) / 100
     // (ev.py:287-290, 375-378).  np.round(amps) >= 0 when charging, so one lookup with |round(amps)| serves both directions:
     // every lane of the warp does it once instead of the charging and the discharging lanes one after the other.
@@ -335,8 +367,8 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
     //  removed reconvergence points saved.  profiles/r2_ab_model_formulation.jsonl)
     if (charging) {                                                                // EV._charge  ev.py:240-355
         const unsigned tsm = hz >> 16;
-        const double ts = (tsm == 0xFFFFu) ? __ldg(&sp->ts) : ev2b_div_c((double)tsm, 1000.0, 0.001);
-        const double pmax = __ldg(&sp->pmax_ac);
+        const double ts = (tsm == 0xFFFFu) ? par.x : ev2b_div_c((double)tsm, 1000.0, 0.001);
+        const double pmax = lim.y;
         // pilot_dsoc = eta*amps*voltage/1000/B/(60/period)                            :295-296
         double pilot = ev2b_div_c(ev2b_div_c(ev2b_div_c(eta * amps * veff, 1000.0, 0.001), B, rB), p.c60, p.rc60);
         const double maxd = ev2b_div_c(ev2b_div_c(eta * pmax, B, rB), p.c60, p.rc60);  // :297-298
@@ -378,7 +410,7 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
                 const bool below = soc < pts;
                 const double x = below ? pilot + soc - pts : pilot;
                 const double y = below ? pts - 1.0 : soc - 1.0;
-                nsoc = 1.0 + exp(__ldg(&sp->mult) * x / (pts - 1.0)) * y;
+                nsoc = 1.0 + exp(par.y * x / (pts - 1.0)) * y;
             }
             const double lim = (maxd > pilot) ? pilot : maxd;                      // :336-339
             curr = (nsoc - soc > lim) ? lim + soc : nsoc;                          // :341-344
@@ -387,7 +419,7 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
         energy = (curr - soc) * B;                                                 // :346,352
         act_amps = ev2b_div_c(ev2b_div_c(energy, p.p60, p.rp60) * 1000.0, veff, rveff);   // :355
     } else {                                                                       // EV._discharge  ev.py:357-405
-        const double pmd = __ldg(&sp->pmax_dis), bmin = __ldg(&sp->bmin);
+        const double pmd = lim.y, bmin = par.x;
         double given_power = ev2b_div_c(amps * veff, 1000.0, 0.001);               // :367
         if (fabs(given_power) > fabs(pmd)) given_power = pmd;                      // :370-371
         double given_energy = ev2b_div_c(given_power * eta * p.period, 60.0, 1.0 / 60.0);   // :381
@@ -400,7 +432,7 @@ __device__ __forceinline__ bool ev_step_item(const Params &p, const CsStatic &cs
             energy = given_energy;
             cap += given_energy;
         }
-        if (STATS && p.stats) { const double be = __ldg(&sp->bmin_em); em_cross = prev_cap > be && cap < be; }   // :401-402
+        if (STATS && p.stats) { const double be = par.y; em_cross = prev_cap > be && cap < be; }   // :401-402
         act_amps = ev2b_div_c(ev2b_div_c(given_energy * 60.0, p.period, p.rperiod) * 1000.0, veff, rveff);   // :405
     }
     cap = ev2b_div_c(ceil(cap * 100.0), 100.0, 0.01);                              // my_ceil  ev.py:183,188-189

@@ -145,7 +145,7 @@ __global__ void evl_rebuild_kernel(const Params p, int lo, int hi) {
 // Observation tuple of the EV on `port` after the step (cv = battery level, h = its hot words)   state.py:37-57, 85-102, 137-151, 262-270
 template <bool HEAVY>
 __device__ __forceinline__ void evl_obs_tuple(const Params &p, float *obs_row, int port, int c, const uint4 &h, double cv,
-                                              double B, const EvSpec *sp, double exch, int tq) {
+                                              double B, double rB, double exch, int tq) {
     float *o = obs_row + p.obs_slot[port];
     if (HEAVY && p.state_kind == EV2B_STATE_V2G_GRID) {
         o[0] = (float)cv;
@@ -156,7 +156,7 @@ __device__ __forceinline__ void evl_obs_tuple(const Params &p, float *obs_row, i
         o[1] = (float)exch;
         o[2] = (float)(tq - hot_t_arr(h));
     } else {
-        o[0] = (float)ev2b_div_c(cv, B, __ldg(&sp->rB));
+        o[0] = (float)ev2b_div_c(cv, B, rB);
         o[1] = (float)(hot_t_dep(h) - tq);
     }
 }
@@ -166,11 +166,6 @@ __device__ __forceinline__ void evl_obs_clear(const Params &p, float *obs_row, i
     if (p.state_kind == EV2B_STATE_PUBLIC_PST || p.state_kind == EV2B_STATE_V2G_GRID) o[2] = 0.f;
 }
 
-// One step of env e by its group (g = group in the CTA, sm = the group's shared memory).  KSTEP: called from the k-step
-// loop of evl_step_kernel (every warp of the group meets at a barrier after each call, so the idle path's arrive / wait
-// pair is not needed); `actions` = the action tensor of this step, `first_it` = first step of the launch (only then may
-// the caller's obs / mask buffers need a full rewrite).  Returns the env's step counter after the call (T + 1: the env
-// was already finished).
 // Starts the HBM -> L2 transfer of the state one EV's thread will load (hot words, battery level, energy exchanged, the
 // action): issued one loop iteration ahead (and for the first iteration from the prologue), so that the dependent gather
 // list entry -> port state, the longest wait of the EV loop, finds its sectors in L2.
@@ -182,6 +177,11 @@ __device__ __forceinline__ void evl_prefetch_ev(const Params &p, const ActT *act
     if (p.agent_kind == EV2B_AGENT_EXTERNAL) prefetch_l2(actions + ip);
 }
 
+// One step of env e by its group (g = group in the CTA, sm = the group's shared memory).  KSTEP: called from the k-step
+// loop of evl_step_kernel (every warp of the group meets at a barrier after each call, so the idle path's arrive / wait
+// pair is not needed); `actions` = the action tensor of this step, `first_it` = first step of the launch (only then may
+// the caller's obs / mask buffers need a full rewrite).  Returns the env's step counter after the call (T + 1: the env
+// was already finished).
 template <typename ActT, int NP, bool UNI, int G, bool HEAVY, bool KSTEP>
 __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, const int e, const int g, const int gtid,
                                             const ActT *actions, const bool first_it) {
@@ -359,6 +359,10 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         const unsigned hx = NP == 2 ? p.hot[ip ^ 1].x : 0u;
         const double am_raw = NP == 2 ? agent_action<ActT>(p, actions, ip ^ 1, t) : 0.0;   // same 32 B sector as `a`
         if (port_next >= 0) evl_prefetch_ev<ActT>(p, actions, (size_t)e * p.P + port_next);
+        const EvSpec *sp = p.spec + hot_spec(h);
+        constexpr bool BATCH = EV2B_SPEC_BATCH == 1 || (EV2B_SPEC_BATCH == 2 && HEAVY);
+        double2 Bv;
+        if (BATCH) Bv = __ldg(reinterpret_cast<const double2 *>(&sp->B));      // B, 1 / B: with the model's own batch of loads
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
         const CsStatic &cs = cs_of<UNI>(p, c);
         // Sigma over the charger's occupied ports, in port order (python sum())   ev_charger.py:137-149
@@ -407,9 +411,9 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
             pwv = ev2b_div_c(energy * 60.0, p.period, p.rperiod);         // :180,196
             if (HEAVY && p.stats && em_cross) atomicAdd(&p.cs_em[(size_t)e * p.C + c], 1);   // ev.py:401-402 (integer: order-free)
         }
+        if (!BATCH) Bv = __ldg(reinterpret_cast<const double2 *>(&sp->B));
         if (HEAVY && p.stats) {             // EV.step bookkeeping: historic_soc / active_steps / |energy|  ev.py:156,178-185
-            const EvSpec *sq = p.spec + hot_spec(h);
-            const double soc0 = ev2b_div_c(cv_old, __ldg(&sq->B), __ldg(&sq->rB));
+            const double soc0 = ev2b_div_c(cv_old, Bv.x, Bv.y);
             int cn = p.st_cnt[ip];
             p.st_soc_sum[ip] += soc0;
             if (an != 0.0 && act_amps != 0.0) { p.st_act[ip * (size_t)p.L + (cn >> 16)] = soc0; cn += 1 << 16; }
@@ -420,7 +424,6 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         if (NP != 1) { pw[port] = pwv; amp[port] = act_amps; }
         double potv = 0.0;
         unsigned flags = 1u;
-        const EvSpec *sp = p.spec + hot_spec(h);
         if (t >= hot_t_dep(h)) {                                          // departure  ev_charger.py:209-224, ev.py:199-214
             const double des = __ldg(&sp->desired);
             const double sat = (cv < des - 0.001) ? cv / des : 1.0;
@@ -446,10 +449,10 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         } else {
             stage[i] = (uint16_t)port;
             if (mask_row) mask_row[port] = 1;
-            const double B = __ldg(&sp->B);
+            const double B = Bv.x;
             aSatExp += evl_unreachable_penalty<HEAVY>(p, sp, cv, hot_t_dep(h) - tq);
             if (cv < B && hot_t_dep(h) > tq) potv = __ldg(&p.pot_kw[hot_spec(h) * p.n_cls + cs.cls]);   // utils.py:766-777
-            if (want_obs) evl_obs_tuple<HEAVY>(p, obs_row, port, c, h, cv, B, sp, exch_new, tq);
+            if (want_obs) evl_obs_tuple<HEAVY>(p, obs_row, port, c, h, cv, B, Bv.y, exch_new, tq);
             if (HEAVY && p.stats && tq >= p.T) {      // episode over: EVs still connected count too (env.EVs)
                 const SessRec r0 = p.sess[((size_t)s * p.P + port) * p.Smax + hot_cursor(h) - 1];
                 double d1, d2;
@@ -491,7 +494,8 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         const int c = NP == 1 ? port : (NP == 2 ? port >> 1 : p.port_cs[port]);
         const CsStatic &cs = cs_of<UNI>(p, c);
         const EvSpec *sp = p.spec + hot_spec(r.hot);
-        const double B = __ldg(&sp->B);
+        const double2 Bv = __ldg(reinterpret_cast<const double2 *>(&sp->B));
+        const double B = Bv.x;
         double potv = 0.0;
         aSatExp += evl_unreachable_penalty<HEAVY>(p, sp, r.cap0, hot_t_dep(r.hot) - tq);
         if (r.cap0 < B && hot_t_dep(r.hot) > tq) potv = __ldg(&p.pot_kw[hot_spec(r.hot) * p.n_cls + cs.cls]);
@@ -519,7 +523,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
             occ[port] = (unsigned char)(flags | 1u);
         }
         if (mask_row) mask_row[port] = 1;
-        if (want_obs) evl_obs_tuple<HEAVY>(p, obs_row, port, c, r.hot, r.cap0, B, sp, 0.0, tq);
+        if (want_obs) evl_obs_tuple<HEAVY>(p, obs_row, port, c, r.hot, r.cap0, B, Bv.y, 0.0, tq);
     }
     evl_group_sync<G>(g);
 

@@ -33,6 +33,7 @@
 
 // ---- vector types ----------------------------------------------------------------------------------------------
 struct alignas(8)  uint2   { unsigned x, y; };
+struct alignas(8)  int2    { int x, y; };
 struct alignas(16) uint4   { unsigned x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(8)  float2  { float x, y; };

@@ -19,6 +19,13 @@ def main():
     h = rows[heads[0]]
     end = heads[1] - 1 if len(heads) > 1 else len(rows)
     body = [r for r in rows[heads[0] + 1:end] if len(r) == len(h)]
+    if "--all" in sys.argv:                       # every column of the page (memory transactions per instruction, stall reasons)
+        with gzip.open(out, "wt", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(h)
+            w.writerows(body)
+        print(len(body), "rows,", len(h), "columns")
+        return
     cols = [h.index(c) for c in ("Address", "Instructions Executed", "Thread Instructions Executed", "# Samples", "Source")]
     with gzip.open(out, "wt", newline="") as f:
         w = csv.writer(f)

@@ -20,7 +20,16 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum",
         "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_global_op_st.sum",
-        "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
+        "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+        # memory pipeline of the SM: is the kernel bound by L1TEX wavefronts (uncoalesced gathers / scatters)?
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "l1tex__lsuin_requests.sum",
+        "smsp__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu.sum", "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
+        "smsp__warps_issue_stalled_lg_throttle.avg", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
 
 
 def run(args):
@@ -44,7 +53,7 @@ def main():
                   if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")]
         if not stalls:
             stalls = [(float(r[i] or 0), h) for i, h in enumerate(hdr) if "issue_stalled" in h and h.endswith(".pct")]
-        for v, h in sorted(stalls, reverse=True)[:8]:
+        for v, h in sorted(stalls, reverse=True)[:12]:
             print(f"  stall {h:70s} {v:10.3f}", file=out)
     src = list(csv.reader(io.StringIO(run(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
     heads = [i for i, r in enumerate(src) if r and r[0] in ("Address", "#")]
