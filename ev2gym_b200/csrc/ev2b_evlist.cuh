@@ -347,6 +347,10 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     evl_group_sync<G>(g);
 
     // ---- EV: one thread per connected EV ------------------------------------------------------------------------
+    // (Round 2 also measured ordering a warp's entries by the direction of the action first -- charging EVs to the front,
+    //  ballot + popc compaction, so that an iteration runs one branch of the battery model: c3 -1.5 %, c4 +3.4 %, removed.
+    //  The warps wait on the loads of the common part of an iteration, not on the two branches.
+    //  profiles/r2_ab_direction_sort.jsonl)
     int port = (int)first;
 #pragma unroll 1
     for (int i = gtid; i < n_old; i += GT) {
