@@ -11,7 +11,7 @@ mkdir -p gpurun_out; export PYTHONUNBUFFERED=1
 TAG=${TAG:-r2}
 L=gpurun_out/steps_$TAG.log; rm -f $L
 timeout 600 python -m pytest tests -m gpu -x -q --timeout 200 --timeout-method=thread > gpurun_out/test_gpu_$TAG.log 2>&1; echo "gpu tests rc=$?" >> $L
-timeout 200 python tools/ab_kernels.py --workloads c3,c4,c5 --variants ${VARIANTS:-evl} --out gpurun_out/ab_$TAG.json > gpurun_out/ab_$TAG.log 2>&1; echo "ab rc=$?" >> $L
+timeout 200 python tools/ab_kernels.py --workloads c3,c4,c5 --variants ${VARIANTS:-evl,evl:G=2} --out gpurun_out/ab_$TAG.json > gpurun_out/ab_$TAG.log 2>&1; echo "ab rc=$?" >> $L
 timeout 500 python bench.py > gpurun_out/bench_c3_$TAG.json 2> gpurun_out/bench_c3_$TAG.err; echo "bench rc=$?" >> $L
 for wl in c4 c5 c2; do timeout 200 python bench.py --workload $wl --no-extras --min-seconds 0.4 --no-cpu-baseline > gpurun_out/bench_${wl}_$TAG.json 2> gpurun_out/bench_${wl}_$TAG.err; echo "bench $wl rc=$?" >> $L; done
 timeout 150 ncu --set full --clock-control none --import-source on -k regex:evl_step_kernel -s 37 -c 1 -o /tmp/prof_busy python tools/ncu_probe.py --steps 39 --variants evl > gpurun_out/prof_busy_$TAG.log 2>&1
