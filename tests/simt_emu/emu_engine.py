@@ -24,9 +24,16 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in _SOURCES):
         return LIB_PATH
     os.makedirs(_BUILD, exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-DEV2B_SIMT_EMU", "-I", _HERE] + _EXTRA + [
-           "-x", "c++", os.path.join(_CSRC, "ev2b.cu"), os.path.join(_HERE, "simt_emu.cc"), "-o", LIB_PATH]
-    subprocess.check_call(cmd)
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:          # pytest-xdist workers: one builds, the others wait and re-check
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in _SOURCES):
+            return LIB_PATH
+        tmp = LIB_PATH + ".tmp%d" % os.getpid()
+        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-DEV2B_SIMT_EMU", "-I", _HERE] + _EXTRA + [
+               "-x", "c++", os.path.join(_CSRC, "ev2b.cu"), os.path.join(_HERE, "simt_emu.cc"), "-o", tmp]
+        subprocess.check_call(cmd)
+        os.replace(tmp, LIB_PATH)                        # a reader never sees a half-written library
     return LIB_PATH
 
 
