@@ -481,16 +481,17 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         h->block = std::min(kMaxThreads, std::max(32, (best_epb * C + 31) / 32 * 32));
         h->layout_smem();
     }
-    // Which step kernel serves this handle (ev2b_evlist.cuh).  The event-driven kernel wins once the batch fills the
-    // machine (B200, mid-episode, us per launch: c3 4096 envs 31.7 vs 37.8; c4 8192 envs 50.2 vs 100.2) and loses below
-    // that (c3 at 1024 envs: 15.7 vs 13.6), so it is the default from 2048 envs up.  EV2B_KERNEL=percharger|evlist forces
-    // one, EV2B_EVL_G = warps per env (1, 2, 4) overrides the group size (tuning / tests).
+    // Which step kernel serves this handle (ev2b_evlist.cuh).  The event-driven kernel is the default from 1024 envs up
+    // (B200, whole episodes, us per launch, event-driven vs step_kernel: c3 4096 envs 19.9 vs 37.8; c4 8192 envs 35.3 vs
+    // 100.2; at 1024 envs, four warps per env: c3 9.0 vs 10.4, c2 8.6 vs 9.1 -- profiles/r2_ab_small_batches.jsonl; round
+    // 1's event-driven kernel lost there, 15.7 vs 13.6).  Smaller batches were not measured and keep step_kernel.
+    // EV2B_KERNEL=percharger|evlist forces one, EV2B_EVL_G = warps per env (1, 2, 4) overrides the group size (tuning / tests).
     {
         const char *kv = getenv("EV2B_KERNEL");
         const bool force_on = kv && (!strcmp(kv, "evlist") || !strcmp(kv, "evl"));
         const bool force_off = kv && !strcmp(kv, "percharger");
         const bool big = C > kMaxThreads || h->smem > 200 * 1024;     // beyond step_kernel's one-thread-per-charger shape
-        const bool want = force_on || big || (!force_off && h->E >= 2048);
+        const bool want = force_on || big || (!force_off && h->E >= 1024);
         if (want && h->P < 65535) {
             h->evl = true;
             // warps per env: as many as it takes to fill the machine (~28 resident warps per SM of the lean kernel, 16 of the
