@@ -66,6 +66,7 @@ struct ev2b_handle {
     DevBuf<CsStatic> cs; DevBuf<int> cs_tr_d; DevBuf<int> tr_cs_off, tr_cs_idx, obs_slot, tr_obs_off, port_cs_d, series_off;
     int W = 0;                          // (scenario, time)-only observation values per env
     int series_pairs = 0;               // they can be copied two at a time (Params::series_pairs)
+    int obs_pairs = 0;                  // an EV's observation tuple is two floats at an even offset (Params::obs_pairs)
     // device: bank
     int S = 0, Smax = 1, n_dr = 1, lut_len = 101;
     DevBuf<EnvT> env_t; DevBuf<TrT> tr_t; DevBuf<SessRec> sess; DevBuf<EvSpec> spec;
@@ -239,7 +240,14 @@ static cudaError_t opt_in_smem(ev2b_handle *h, K kern, size_t bytes) {
 
 // kstep: the KSTEP instantiation (p.k_steps steps in one launch; lean kernels only, see ev2b_step_k)
 template <typename ActT>
-static cudaError_t launch_evl(ev2b_handle *h, const Params &p, cudaStream_t st, bool kstep = false) {
+static cudaError_t launch_evl(ev2b_handle *h, const Params &p_in, cudaStream_t st, bool kstep = false) {
+    Params p = p_in;
+    // two-at-a-time accesses need the caller's buffers on an 8 / 16-byte boundary (cudaMalloc and torch give 256)
+    const bool obs_al = (reinterpret_cast<uintptr_t>(p.out.obs) & 7u) == 0;
+    p.series_pairs = (h->series_pairs && obs_al) ? 1 : 0;
+    p.obs_pairs = (h->obs_pairs && obs_al) ? 1 : 0;
+    p.act_pairs = (p.agent_kind == EV2B_AGENT_EXTERNAL && h->cs_uniform && h->np_uniform == 2 && p.actions &&
+                   (reinterpret_cast<uintptr_t>(p.actions) & (2 * sizeof(ActT) - 1)) == 0) ? 1 : 0;
     const int epb = h->evl_tpb / (32 * h->evl_G);
     const unsigned grid = (unsigned)((p.env_end - p.env0 + epb - 1) / epb);
     auto go = [&](auto kern) -> cudaError_t {
@@ -452,6 +460,9 @@ int ev2b_create(const ev2b_dims *d, const ev2b_topology *tp, int device, ev2b_ha
         for (int i = 0; i < 5; ++i) series_off_h.push_back(i);
         for (int i = 0; i < 2 * h->n_bus; ++i) series_off_h.push_back(6 + i);
     }
+    h->obs_pairs = (h->D % 2 == 0 && d->state_kind != EV2B_STATE_NONE && d->state_kind != EV2B_STATE_PUBLIC_PST &&
+                    d->state_kind != EV2B_STATE_V2G_GRID) ? 1 : 0;          // (those two write three values per EV)
+    for (int i = 0; i < h->P && h->obs_pairs; ++i) if (slot[i] % 2 != 0) h->obs_pairs = 0;
     h->W = (int)series_off_h.size();
     h->series_pairs = (h->W > 0 && h->W % 2 == 0 && h->D % 2 == 0) ? 1 : 0;
     for (int i = 0; i + 1 < h->W && h->series_pairs; i += 2)

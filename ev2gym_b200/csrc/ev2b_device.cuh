@@ -152,6 +152,8 @@ struct Params {
     int k_steps, auto_reset;   // evl_step_kernel<..., KSTEP = true>: steps per launch, device-side reset of finished envs
     int series_pairs;          // 1: W is even, series values 2j / 2j+1 land on neighbouring floats at an even offset and D is
                                //    even: the (scenario, time) observation values are copied as float2
+    int obs_pairs;             // 1: an EV's observation tuple is two floats at an even offset of an 8-byte aligned row: one store
+    int act_pairs;             // 1: two ports per charger, caller-supplied actions on a 2-element boundary: one load per charger
     // state
     uint4 *hot; double *cap; double *exch;   // exch: float64 like the reference's total_energy_exchanged (ev.py:178)
      int *env_step; int *env_scn; double *env_pot; double *env_usage;

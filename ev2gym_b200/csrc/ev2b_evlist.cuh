@@ -142,6 +142,8 @@ __global__ void evl_rebuild_kernel(const Params p, int lo, int hi) {
     if (lane == 0) p.occ_n[e] = base;
 }
 
+template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };      // two neighbouring actions
+
 // Observation tuple of the EV on `port` after the step (cv = battery level, h = its hot words)   state.py:37-57, 85-102, 137-151, 262-270
 template <bool HEAVY>
 __device__ __forceinline__ void evl_obs_tuple(const Params &p, float *obs_row, int port, int c, const uint4 &h, double cv,
@@ -156,12 +158,14 @@ __device__ __forceinline__ void evl_obs_tuple(const Params &p, float *obs_row, i
         o[1] = (float)exch;
         o[2] = (float)(tq - hot_t_arr(h));
     } else {
-        o[0] = (float)ev2b_div_c(cv, B, rB);
-        o[1] = (float)(hot_t_dep(h) - tq);
+        const float soc = (float)ev2b_div_c(cv, B, rB), left = (float)(hot_t_dep(h) - tq);
+        if (p.obs_pairs) *reinterpret_cast<float2 *>(o) = make_float2(soc, left);
+        else { o[0] = soc; o[1] = left; }
     }
 }
 __device__ __forceinline__ void evl_obs_clear(const Params &p, float *obs_row, int port) {
     float *o = obs_row + p.obs_slot[port];
+    if (p.obs_pairs) { *reinterpret_cast<float2 *>(o) = make_float2(0.f, 0.f); return; }
     o[0] = 0.f; o[1] = 0.f;
     if (p.state_kind == EV2B_STATE_PUBLIC_PST || p.state_kind == EV2B_STATE_V2G_GRID) o[2] = 0.f;
 }
@@ -359,9 +363,15 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         const uint4 h = p.hot[ip];
         double cv = p.cap[ip];
         double exch_new = p.exch[ip];
-        const double a = agent_action<ActT>(p, actions, ip, t);
+        double a, am_raw = 0.0;
+        if (NP == 2 && p.act_pairs) {            // both ports of the charger with one load
+            const Pair<ActT> v = *reinterpret_cast<const Pair<ActT> *>(actions + (ip & ~(size_t)1));
+            a = (double)((ip & 1) ? v.y : v.x); am_raw = (double)((ip & 1) ? v.x : v.y);
+        } else {
+            a = agent_action<ActT>(p, actions, ip, t);
+            if (NP == 2) am_raw = agent_action<ActT>(p, actions, ip ^ 1, t);                 // same 32 B sector as `a`
+        }
         const unsigned hx = NP == 2 ? p.hot[ip ^ 1].x : 0u;
-        const double am_raw = NP == 2 ? agent_action<ActT>(p, actions, ip ^ 1, t) : 0.0;   // same 32 B sector as `a`
         if (port_next >= 0) evl_prefetch_ev<ActT>(p, actions, (size_t)e * p.P + port_next);
         const EvSpec *sp = p.spec + hot_spec(h);
         constexpr bool BATCH = EV2B_SPEC_BATCH == 1 || (EV2B_SPEC_BATCH == 2 && HEAVY);
