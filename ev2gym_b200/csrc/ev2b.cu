@@ -118,8 +118,8 @@ struct ev2b_handle {
         evl_o[1] = take(8 * pp, 8); evl_o[2] = take(8 * pp, 8); evl_o[3] = take(8 * (size_t)C, 8);   // amp, pot, csP
         evl_o[4] = take(8 * (size_t)(kEvlTr + 4 * Tr), 16);        // pre (cp.async 16 B destinations)
         evl_o[5] = take(8 * (size_t)EvlNSum * evl_G, 8);           // wsum
-        evl_o[7] = take(2 * (size_t)P, 4);                         // stage
-        evl_o[8] = take((pp + 3) / 4 * 4, 4);                      // occ
+        evl_o[7] = 0;                                              // (stage: gone, the list is rebuilt from the occ flags)
+        evl_o[8] = take(((size_t)P + 3) / 4 * 4, 4);               // occ
         if (n_bus > 0) { evl_o[6] = take(8 * (size_t)Tr, 8); evl_o[9] = take(16 * 3 * (size_t)n_bus, 16); }   // trp, pfv
         if ((dims.flags & EV2B_F_STATS) && pp) {                   // dsat, dcal, dcyc
             evl_o[10] = take(8 * pp, 8); evl_o[11] = take(8 * pp, 8); evl_o[12] = take(8 * pp, 8);

@@ -36,7 +36,6 @@
 namespace ev2b {
 
 constexpr int kEvlThreads = 128;             // threads per CTA (a second instantiation with 32 serves multi-wave launches)
-constexpr unsigned kEvlGone = 0xFFFFu;       // staging mark: this EV left during the step
 // prefetch area of this kernel (doubles): [0,13) KPI sums, [13] charge_power_potential[t] (kPrePot), then
 constexpr int kEvlPotPrev = 14;              // charge_power_potential[t-1]
 constexpr int kEvlSet = 15, kEvlSetNext = 16;   // power_setpoints[t], [t+1]
@@ -197,8 +196,8 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     double *csP   = reinterpret_cast<double *>(sm + p.v_csP);        // [C] charger power, for the transformer sums
     double *pre   = reinterpret_cast<double *>(sm + p.v_pre);        // [pre_stride] prefetched per-env records (kPre*)
     double *wsum  = reinterpret_cast<double *>(sm + p.v_wsum);       // [G][EvlNSum] per-warp partial sums (the last one holds counts)
-    uint16_t *stage = reinterpret_cast<uint16_t *>(sm + p.v_stage);  // [P] by list position: port, or kEvlGone
     unsigned char *occ = sm + p.v_occ;                               // [P] bit 0: the port holds per-port results this step;
+                                                                     //     bit 3: an EV is connected to it at step t+1;
                                                                      //     bit 1 / 2 (statistics): an EV left it / was finalised on it
     double *trp   = reinterpret_cast<double *>(sm + p.v_trp);        // HEAVY: [Tr] transformer power (grid: bus EV power)
     double2 *pfv  = reinterpret_cast<double2 *>(sm + p.v_pfv);       // HEAVY: [3][n_bus] power-flow scratch S, V, lambda
@@ -304,10 +303,9 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         if (NP == 1) {                                // one port per charger: the EV's thread is the charger's thread (no CS phase)
 #pragma unroll 1
             for (int i = gtid; i < p.C; i += GT) csP[i] = 0.0;
-        } else {
-#pragma unroll 1
-            for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
         }
+#pragma unroll 1
+        for (int i = gtid; i < (p.P + 3) >> 2; i += GT) reinterpret_cast<unsigned *>(occ)[i] = 0u;
     }
     if (NP == 1 || idle) {                            // (with a CS phase the charger's thread writes these)
         if (p.out.cs_power || p.out.cs_current || h_csP || h_csA) {
@@ -444,7 +442,6 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
             aSatExp += evl_departure_penalty<HEAVY>(p, cv, des, sat);
             aSat += sat;
             ++nDep;
-            stage[i] = (uint16_t)kEvlGone;
             if (mask_row) mask_row[port] = 0;
             if (want_obs) evl_obs_clear(p, obs_row, port);
             if (HEAVY) {
@@ -461,7 +458,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
                 }
             }
         } else {
-            stage[i] = (uint16_t)port;
+            flags |= 8u;                                                  // stays connected: in next step's list
             if (mask_row) mask_row[port] = 1;
             const double B = Bv.x;
             aSatExp += evl_unreachable_penalty<HEAVY>(p, sp, cv, hot_t_dep(h) - tq);
@@ -489,8 +486,8 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
             if (h_csA) h_csA[port] = (float)rA;
         } else {
             pot[port] = potv;
-            occ[port] = (unsigned char)flags;
         }
+        occ[port] = (unsigned char)flags;
         port = port_next;
     }
     evl_group_sync<G>(g);
@@ -513,7 +510,7 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         double potv = 0.0;
         aSatExp += evl_unreachable_penalty<HEAVY>(p, sp, r.cap0, hot_t_dep(r.hot) - tq);
         if (r.cap0 < B && hot_t_dep(r.hot) > tq) potv = __ldg(&p.pot_kw[hot_spec(r.hot) * p.n_cls + cs.cls]);
-        unsigned flags = NP == 1 ? 0u : (unsigned)occ[port];
+        unsigned flags = (unsigned)occ[port];
         if (HEAVY && p.stats) {
             p.st_soc_sum[ip] = 0.0; p.st_abs_e[ip] = 0.0; p.st_cnt[ip] = 0;
             if (tq >= p.T) {                          // arrives as the episode ends: finalised at once (env.EVs)
@@ -534,8 +531,8 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
         } else {
             if (!(flags & 1u)) { pw[port] = 0.0; amp[port] = 0.0; }      // (an EV may have left this very port in step t)
             pot[port] = potv;
-            occ[port] = (unsigned char)(flags | 1u);
         }
+        occ[port] = (unsigned char)(flags | 9u);                          // per-port results + connected at t+1
         if (mask_row) mask_row[port] = 1;
         if (want_obs) evl_obs_tuple<HEAVY>(p, obs_row, port, c, r.hot, r.cap0, B, Bv.y, 0.0, tq);
     }
@@ -587,21 +584,23 @@ __device__ __forceinline__ int evl_env_step(const Params &p, unsigned char *sm, 
     }
     evl_group_sync<G>(g);
 
-    // ---- LS: the group's last warp writes next step's list: kept EVs in list order, then the arrivals ----------
+    // ---- LS: the group's last warp writes next step's list IN PORT ORDER (a ballot compaction of the "connected at t+1"
+    // flags).  Neighbouring lanes of the EV loop then work on neighbouring ports: their battery levels / energies (four
+    // per 32-byte sector), hot words (two), actions (eight) and observation tuples share sectors -- the gathers and
+    // scatters of an iteration touch 40 % fewer sectors than with the list in arrival order (c3 at its busiest step: 14.6
+    // instead of 25.5 sectors per 32 battery levels, 8.2 instead of 19.6 per 32 actions).
     if (gw == G - 1) {
         uint16_t *nxt = p.occ_list + (size_t)e * p.P;      // in place: every thread is past its last read of the old list
         int base = 0;
 #pragma unroll 1
-        for (int i0 = 0; i0 < n_old; i0 += 32) {
-            const int i = i0 + lane;
-            const unsigned v = i < n_old ? (unsigned)stage[i] : kEvlGone;
-            const unsigned m = __ballot_sync(0xffffffffu, v != kEvlGone);
-            if (v != kEvlGone) nxt[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)v;
+        for (int i0 = 0; i0 < p.P; i0 += 32) {
+            const int pt = i0 + lane;
+            const bool on = pt < p.P && (occ[pt] & 8u);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) nxt[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)pt;
             base += __popc(m);
         }
-#pragma unroll 1
-        for (int k = lane; k < nArr; k += 32) nxt[base + k] = (uint16_t)(p.arr_list[a0 + k] & 0xFFFFu);
-        if (lane == 0) p.occ_n[e] = base + nArr;
+        if (lane == 0) p.occ_n[e] = base;
     }
     if (gw != 0) return tq;
     }  // !idle

@@ -147,8 +147,8 @@ def test_evlist_random_thread_schedule(emu, G, monkeypatch):
 
 @pytest.mark.parametrize("G", [1, 4])
 def test_evlist_list_is_the_set_of_connected_ports(emu, G, monkeypatch):
-    """occ_list / occ_n after every step == the ports whose hot words say an EV is connected (stable order: EVs that
-    stay keep their relative order, arrivals are appended in schedule order)."""
+    """occ_list / occ_n after every step == the ports whose hot words say an EV is connected, in ascending port order
+    (neighbouring threads of the EV loop then touch neighbouring ports: shared memory sectors)."""
     import ctypes as C
     from ev2gym_b200.engine import BatchedEngine
     topo, bank = _bank(40, 2, 5)
@@ -162,7 +162,6 @@ def test_evlist_list_is_the_set_of_connected_ports(emu, G, monkeypatch):
     L = eng.L
     L.ev2b_debug_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.ev2b_debug_list.restype = C.c_int
-    prev = [[] for _ in range(E)]
     for t in range(topo.T - 1):
         eng.step(np.ascontiguousarray(rng.uniform(-1, 1, (E, topo.P)).astype(np.float32)))
         for e in range(E):
@@ -171,12 +170,7 @@ def test_evlist_list_is_the_set_of_connected_ports(emu, G, monkeypatch):
             got = [int(x) for x in buf[:n]]
             want = set(int(x) for x in _occupied_ports(eng, e))
             assert set(got) == want and len(got) == len(want), (t, e)
-            t_arr = BatchedEngine.decode_hot(eng.state()["port_hot"][e])["t_arr"]
-            ident = [(x, int(t_arr[x])) for x in got]                    # (port, arrival step) names a session
-            kept = [x for x in prev[e] if x in ident]
-            assert ident[:len(kept)] == kept, (t, e, "EVs that stay keep their order")
-            assert all(ta == t + 1 for _, ta in ident[len(kept):]), (t, e, "then this step's arrivals")
-            prev[e] = ident
+            assert got == sorted(got), (t, e, "port order")
     eng.close()
 
 
