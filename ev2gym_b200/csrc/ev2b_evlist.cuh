@@ -41,6 +41,11 @@ constexpr int kEvlPotPrev = 14;              // charge_power_potential[t-1]
 constexpr int kEvlSet = 15, kEvlSetNext = 16;   // power_setpoints[t], [t+1]
 constexpr int kEvlTr = 18;                   // [18 + 4k, +4) TrT of transformer k (16 B aligned)
 enum { EvlProfit = 0, EvlSatExp, EvlCharged, EvlDischarged, EvlSatSum, EvlUsage, EvlPot, EvlCounts, EvlNSum };
+#ifndef EV2B_EVL_PF
+#define EV2B_EVL_PF 1         // L2 prefetch of the next iteration's EV state: 0 none, 1 hot + cap + exch + action, 2 hot only, 3 no action
+                              // (us per launch c3 / c4 / c5 with the port-ordered list: 0: 18.61 / 32.38 / 55.54, 1: 18.53 / 31.65 / 53.74,
+                              //  profiles/r2_ab_build_modes.jsonl; before the list was ordered the prefetch was worth 9 % on c3)
+#endif
 static_assert(EvlNSum == 8, "warp_sum8 reduces exactly 8 quantities");
 
 // Warp totals of 8 per-lane values in 9 exchanges instead of 40 (a reduce-scatter butterfly: at distance 16 every lane
@@ -174,10 +179,16 @@ __device__ __forceinline__ void evl_obs_clear(const Params &p, float *obs_row, i
 // list entry -> port state, the longest wait of the EV loop, finds its sectors in L2.
 template <typename ActT>
 __device__ __forceinline__ void evl_prefetch_ev(const Params &p, const ActT *actions, size_t ip) {
+#if EV2B_EVL_PF >= 1
     prefetch_l2(p.hot + ip);
+#endif
+#if EV2B_EVL_PF == 1 || EV2B_EVL_PF == 3
     prefetch_l2(p.cap + ip);
     prefetch_l2(p.exch + ip);
+#endif
+#if EV2B_EVL_PF == 1
     if (p.agent_kind == EV2B_AGENT_EXTERNAL) prefetch_l2(actions + ip);
+#endif
 }
 
 // One step of env e by its group (g = group in the CTA, sm = the group's shared memory).  KSTEP: called from the k-step
