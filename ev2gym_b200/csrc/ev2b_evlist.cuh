@@ -14,7 +14,8 @@
 //   AR  one thread per ARRIVAL of step t+1 (from the schedule)                  ev2gym_env.py:399-417
 //   CS  one thread per charger: power / amps / potential in port order, clamp   transformer.py:264-274, utils.py:779-789
 //       (not with one port per charger: there the EV's own thread does it)
-//   LS  last warp: stable compaction of the kept EVs + arrivals back into the list
+//   LS  last warp: the list of step t+1, IN PORT ORDER (ballot compaction of per-port "connected at t+1" flags), so that
+//       neighbouring threads of the EV phase work on neighbouring ports and their loads / stores share memory sectors
 //   TR  warp 0: transformer sums (CSR) + overload; distribution-grid power flow; then reward, the 13 KPI sums, step
 //       counter, done flag and observation header, ONE LANE PER QUANTITY (lane k owns KPI k: a load, an add, a store --
 //       not thirteen dependent read-modify-writes by one thread)
