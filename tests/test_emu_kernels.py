@@ -174,6 +174,62 @@ def test_evlist_list_is_the_set_of_connected_ports(emu, G, monkeypatch):
     eng.close()
 
 
+@pytest.mark.parametrize("n_ports", [1, 2, 3])
+def test_evlist_list_in_port_order_for_every_charger_shape(emu, n_ports, monkeypatch):
+    """The port-ordered list with one port per charger (no per-port staging, the flags exist only for the list), two (the
+    paired CS phase) and three (the generic path)."""
+    import ctypes as C
+    topo, bank = _bank(24, n_ports, 3)
+    monkeypatch.setenv("EV2B_KERNEL", "evlist")
+    monkeypatch.setenv("EV2B_EVL_G", "1")
+    eng = emu.EmuEngine(topo, 3, reward="profit_maximization", state="V2G_profit_max", outputs=("reward", "status"))
+    eng.load_scenarios(bank)
+    eng.reset()
+    rng = np.random.default_rng(5)
+    L = eng.L
+    L.ev2b_debug_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.ev2b_debug_list.restype = C.c_int
+    for t in range(topo.T - 1):
+        eng.step(np.ascontiguousarray(rng.uniform(-1, 1, (3, topo.P)).astype(np.float32)))
+        for e in range(3):
+            buf = np.zeros(topo.P, dtype=np.uint16)
+            n = L.ev2b_debug_list(eng.h, e, buf.ctypes.data)
+            got = [int(x) for x in buf[:n]]
+            assert got == sorted(int(x) for x in _occupied_ports(eng, e)), (t, e)
+    eng.close()
+
+
+@pytest.mark.parametrize("adt", ["float32", "float64"])
+def test_evlist_unaligned_action_buffer_takes_the_scalar_loads(emu, adt, monkeypatch):
+    """Two ports per charger: both actions of a charger are read with ONE load when the caller's buffer sits on a
+    two-element boundary.  A buffer that does not (a view one element into an allocation) must give the same episode."""
+    topo, bank = _bank(20, 2, 2, T=30)
+    monkeypatch.setenv("EV2B_KERNEL", "evlist")
+    monkeypatch.setenv("EV2B_EVL_G", "1")
+    E = 3
+    engs = [emu.EmuEngine(topo, E, reward="profit_maximization", state="V2G_profit_max", outputs=("reward", "status", "obs"))
+            for _ in range(2)]
+    for g in engs:
+        g.load_scenarios(bank)
+        g.reset()
+    rng = np.random.default_rng(11)
+    item = np.dtype(adt).itemsize
+    for t in range(topo.T):
+        a = rng.uniform(-1, 1, (E, topo.P)).astype(adt)
+        raw = np.zeros(E * topo.P + 4, dtype=adt)
+        off = next(k for k in range(4) if (raw[k:].ctypes.data % (2 * item)) != 0)      # an odd element boundary
+        shifted = raw[off:off + E * topo.P].reshape(E, topo.P)
+        shifted[:] = a
+        assert shifted.flags.c_contiguous and shifted.ctypes.data % (2 * item) != 0
+        o0 = engs[0].step(np.ascontiguousarray(a))
+        o1 = engs[1].step(shifted)
+        for k in ("reward", "status", "obs"):
+            assert np.array_equal(np.asarray(o0[k]), np.asarray(o1[k])), (t, k)
+    assert np.array_equal(engs[0].state()["port_cap"], engs[1].state()["port_cap"])
+    for g in engs:
+        g.close()
+
+
 @pytest.mark.parametrize("G", [1, 2])
 def test_evlist_action_mask_incremental(emu, G, monkeypatch):
     """action_mask from the event-driven kernel: rows are updated in place (arrivals / departures only), rewritten when

@@ -183,3 +183,39 @@ def test_evlist_equals_step_kernel_at_c3_size(G, monkeypatch):
         assert np.array_equal(a[i], m[i]), i
     assert _close(b[3], a[3], 1e-9, 1e-9)
     assert _close(b[4], a[4], 1e-9, 1e-9) and _close(m[4], a[4], 1e-9, 1e-9)
+
+
+@pytest.mark.parametrize("adt", ["float32", "float64"])
+def test_unaligned_action_and_observation_buffers(adt, monkeypatch):
+    """The event-driven kernel reads both actions of a charger with one load and writes an EV's observation tuple / the
+    series values with 8-byte stores when the caller's buffers allow it.  Buffers that start one element into an allocation
+    take the scalar paths and must give the same episode."""
+    import torch
+    from ev2gym_b200.scenario import Topology
+    from ev2gym_b200.synthetic import sample_bank
+    monkeypatch.setenv("EV2B_KERNEL", "evlist")
+    topo = Topology.uniform(C=40, n_ports=2, Tr=5, T=40)
+    bank = sample_bank(topo, 4, seed=3, min_stay=5)
+    E = 37
+    a_eng = _engine(topo, bank, E, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", outputs=("reward", "status", "obs"))
+    b_eng = _engine(topo, bank, E, "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads", outputs=("reward", "status", "obs"))
+    dev = torch.device("cuda", 0)
+    tdt = torch.float32 if adt == "float32" else torch.float64
+    raw_act = torch.zeros(E * topo.P + 1, dtype=tdt, device=dev)
+    act_odd = raw_act[1:].view(E, topo.P)                        # one element into the allocation: not on a pair boundary
+    raw_obs = torch.zeros(E * a_eng.D + 1, dtype=torch.float32, device=dev)
+    obs_odd = raw_obs[1:].view(E, a_eng.D)                       # 4 bytes off an 8-byte boundary
+    assert act_odd.data_ptr() % (2 * act_odd.element_size()) != 0 and obs_odd.data_ptr() % 8 != 0
+    b_eng.out["obs"] = obs_odd                                   # (the engine's own buffer is replaced before the first reset)
+    b_eng._so.obs = obs_odd.data_ptr()
+    a_eng.reset(); b_eng.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(5)
+    for t in range(topo.T):
+        a = (torch.rand((E, topo.P), device=dev, generator=gen) * 2 - 1).to(tdt)
+        act_odd.copy_(a)
+        oa = a_eng.step(a)
+        ob = b_eng.step(act_odd)
+        assert torch.equal(oa["reward"], ob["reward"]) and torch.equal(oa["status"], ob["status"]), t
+        assert torch.equal(oa["obs"], obs_odd), t
+    assert torch.equal(a_eng.state_tensors()["port_cap"], b_eng.state_tensors()["port_cap"])
+    a_eng.close(); b_eng.close()
