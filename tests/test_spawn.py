@@ -196,3 +196,53 @@ def test_device_sampler_on_gpu(name, reward, state, monkeypatch):
     def make(topo, E, rw, st):
         return Eng(topo, E, reward=rw, state=st, outputs=("reward", "status", "obs"))
     _check_sample(make, name, reward, state, n_rounds=8, ks_bar=0.05 if "c3" in name else 0.07, steps_vs_oracle=112)
+
+
+# ---- the same seed gives the same sessions on the emulated and on the real build ---------------------------------------
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SAMPLER_GOLDEN = [("c2_publicpst_c25", "SquaredTrackingErrorReward", "PublicPST"),
+                  ("c3_v2gloads_c100n2tr5", "ProfitMax_TrPenalty_UserIncentives", "V2G_profit_max_loads")]
+
+
+def _check_against_sampler_golden(make_engine, name, reward, state):
+    """tests/golden/sampler_<bank>.npz (tools/make_sampler_golden.py: the emulated kernels, which
+    tests/test_spawner_reference.py / test_setpoints_reference.py pin to the unmodified reference functions)."""
+    pack, tab = _load(name)
+    z = np.load(os.path.join(GOLDEN, "sampler_" + name + ".npz"))
+    S = int(z["n_scenarios"][0])
+    eng = make_engine(pack.topo, S, reward, state)
+    eng.set_spawn_tables(tab)
+    eng.load_scenarios(pack.scenarios[:S])
+    eng.resample_sessions(seed=int(z["seed"][0]))
+    n = 0
+    for s in range(S):
+        d = eng.read_sessions(s)
+        for k in ("port", "t_arr", "t_dep", "model"):
+            assert np.array_equal(d[k], z[f"s{s}_{k}"]), (s, k)
+        assert np.allclose(d["cap0"], z[f"s{s}_cap0"], rtol=1e-9, atol=1e-9), s
+        for k in ("ts", "eta_c", "eta_d"):
+            assert np.array_equal(d[k], z[f"s{s}_{k}"], equal_nan=True), (s, k)
+        sp = eng.read_setpoints(s)
+        assert np.allclose(sp, z[f"s{s}_setpoint"], rtol=1e-9, atol=1e-9), (s, "setpoints")
+        n += len(d["port"])
+    assert n > 200
+    eng.close()
+
+
+@pytest.mark.parametrize("name,reward,state", SAMPLER_GOLDEN)
+def test_emulated_sampler_equals_the_golden_sessions(name, reward, state, monkeypatch):
+    """(guards the fixture: it must be regenerated when the sampler's keying or arithmetic changes)"""
+    import emu_engine
+    emu_engine.build()
+    monkeypatch.setenv("EV2B_KERNEL", "evlist")
+    _check_against_sampler_golden(lambda topo, E, rw, st: emu_engine.EmuEngine(topo, E, reward=rw, state=st, outputs=("reward",)),
+                                  name, reward, state)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,reward,state", SAMPLER_GOLDEN)
+def test_gpu_sampler_equals_the_golden_sessions(name, reward, state, monkeypatch):
+    from ev2gym_b200.engine import BatchedEngine
+    monkeypatch.setenv("EV2B_KERNEL", "evlist")
+    _check_against_sampler_golden(lambda topo, E, rw, st: BatchedEngine(topo, E, reward=rw, state=st, outputs=("reward",)),
+                                  name, reward, state)
